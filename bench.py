@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — hot-path throughput of the B200-native galvanise_zero self-play path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload propnet|puct] [--impl reference]
+
+Under torchrun (N>1) every rank owns a disjoint range of game slots (no data-path collective;
+"weak" scaling); the timed region is bracketed by barrier + synchronize, timed with CUDA events on
+the launching stream, max over ranks. Rank 0 prints ONE JSON line.
+
+Workloads
+  propnet  BASELINE config "Breakthrough 8x8 propnet: batched uniform-random playouts": one step =
+           one playout ply over all slots (one launch of the fused choose+transition kernel).
+  puct     BASELINE config "Reversi 8x8 PUCT self-play, 800 evals/move, small residual net,
+           4096 concurrent games per GPU" (see galvanise_zero_b200/selfplay.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d.get('bf16_tflops'),
+                'bf16_tflops_sustained': d.get('bf16_tflops_sustained'), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0,
+            'source': 'fallback'}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1])); mx.append(float(s[2]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                'sw_power_cap'), s[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def all_max(x, world, device):
+    import torch
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def all_sum(x, world, device):
+    import torch
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+PROPNET_GAME = 'breakthrough'
+PROPNET_SLOTS = 1 << 21          # per GPU; working set 166 MB > 126 MB L2
+
+
+def transition_bytes(sm):
+    """Algorithmic bytes of one transition: state in + out, legal masks out,
+    move indices in (int16), terminal, goals."""
+    nb = (sm.n_bases + 7) // 8
+    return 2 * nb + (sum(sm.role_sizes) + 7) // 8 + 2 * sm.n_roles + 1 + sm.n_roles
+
+
+def cpu_baseline_propnet(game, seconds_target=12.0, threads=None):
+    from galvanise_zero_b200 import tables
+    from oracle import pnref
+    threads = threads or os.cpu_count() or 1
+    blob = tables.blob_by_name(game)
+    # calibrate
+    secs, tr, _ = pnref.playout_bench(blob, 64 * threads, 50, 0xB200, threads)
+    rate = tr / max(secs, 1e-9)
+    steps = 200
+    slots = max(threads, int(rate * seconds_target / steps))
+    secs, tr, _ = pnref.playout_bench(blob, slots, steps, 0xB200, threads)
+    return {'value': tr / secs, 'unit': 'transitions/s', 'cores': threads, 'kind': 'port',
+            'sample': '%s: %d slots x %d playout plies, %d host threads, %.1f s '
+                      '(oracle/propnet_ref.c, nextState+updateBases per ply)' % (
+                          game, slots, steps, threads, secs)}
+
+
+def run_propnet(args, rank, world, local):
+    import numpy as np
+    import torch
+    from galvanise_zero_b200.statemachine import DeviceStateMachine
+    from galvanise_zero_b200 import lib as gzlib
+
+    peaks = load_peaks()
+    dev = DeviceStateMachine(PROPNET_GAME, device=local, goals_mode=gzlib.GOALS_ALWAYS)
+    n = args.slots or PROPNET_SLOTS
+    slot0 = rank * n
+    s = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
+    l, t, g = dev.alloc_views(n)
+    t.fill_(1)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev.device)
+    seed = 0xB200
+    step = 0
+    # bring the slots to mixed mid-game positions, then warm up
+    for _ in range(30 + args.warmup):
+        dev.playout_step(s, l, t, g, seed, step, slot0=slot0, counter=None)
+        step += 1
+    barrier(world)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    cnt.zero_()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    ev0.record()
+    for _ in range(args.steps):
+        dev.playout_step(s, l, t, g, seed, step, slot0=slot0, counter=cnt)
+        step += 1
+    ev1.record()
+    barrier(world)
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary() if sampler else None
+    ms_max = all_max(ms, world, dev.device)
+    transitions = all_sum(float(cnt.item()), world, dev.device)
+    value = transitions / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (pn_kernel<PLAYOUT>): algorithmic bytes / launch time
+    tb = transition_bytes(dev)
+    per_launch_bytes = tb * n
+    launch_s = (ms * 1e-3) / args.steps
+    achieved = per_launch_bytes / launch_s / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                'kernel': 'pn_kernel<MODE_PLAYOUT>', 'bytes_per_unit': tb,
+                'units_per_launch': n, 'peak_source': peaks['source']}
+
+    # ---- e2e: the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
+    e2e = None
+    if rank == 0 or world > 1:
+        ne = min(n, 1 << 20)
+        hs = torch.empty((ne, dev.state_words), dtype=torch.int32).pin_memory()
+        hm = torch.empty((ne, dev.n_roles), dtype=torch.int16).pin_memory()
+        hn = torch.empty((ne, dev.state_words), dtype=torch.int32).pin_memory()
+        hl = torch.empty((ne, dev.legal_words), dtype=torch.int32).pin_memory()
+        ht = torch.empty((ne,), dtype=torch.uint8).pin_memory()
+        hg = torch.empty((ne, dev.n_roles), dtype=torch.uint8).pin_memory()
+        # a legal joint move for every (non-terminal) state: take the playout kernel's own choice
+        mo = torch.zeros((n, dev.n_roles), dtype=torch.int16, device=dev.device)
+        s_prev = s.clone()
+        dev.playout_step(s, l, t, g, seed, step, slot0=slot0, moves_out=mo)
+        step += 1
+        live = (mo[:ne, 0] >= 0)
+        mo_c = mo[:ne].clone()
+        mo_c[~live] = 0
+        hs.copy_(s_prev[:ne]); hm.copy_(mo_c)
+        torch.cuda.synchronize()
+        out = (hn.numpy().view(np.uint32), hl.numpy().view(np.uint32), ht.numpy(), hg.numpy())
+        hs_np, hm_np = hs.numpy().view(np.uint32), hm.numpy()
+        for _ in range(2):
+            dev.transition_host(hs_np, hm_np, out=out)
+        reps = max(3, min(args.steps, 10))
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dev.transition_host(hs_np, hm_np, out=out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dt = all_max(dt, world, dev.device)
+        e2e_val = all_sum(float(ne * reps), world, dev.device) / dt
+        e2e = {'value': e2e_val, 'unit': 'transitions/s',
+               'h2d_bytes_per_step': int(hs.numel() * 4 + hm.numel() * 2),
+               'd2h_bytes_per_step': int(hn.numel() * 4 + hl.numel() * 4 + ht.numel() + hg.numel()),
+               'api': 'gz_sm_transition_host (DeviceStateMachine.transition_host), pinned host buffers',
+               'units_per_step': ne}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_propnet(PROPNET_GAME)
+
+    if rank == 0:
+        line = {
+            'metric': 'propnet transitions/sec', 'value': value, 'unit': 'transitions/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
+            'config': {'workload': 'breakthrough 8x8 propnet, batched uniform-random playouts',
+                       'slots_per_gpu': n, 'l2': 'working set %.0f MB per GPU > 126 MB L2' % (
+                           n * (dev.state_words * 4 + dev.legal_words * 4 + 1 + dev.n_roles) / 1e6),
+                       'parallelism': 'games sharded across %d GPU(s), no collective' % world,
+                       'launch': dev.launch_info},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': args.steps,
+            'clocks': clocks,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def run_reference(args):
+    """CPU reference arm: the oracle port of the reference's state-machine loop on all host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from galvanise_zero_b200 import tables
+    from oracle import pnref
+    blob = tables.blob_by_name(PROPNET_GAME)
+    secs, tr, _ = pnref.playout_bench(blob, 64 * threads, 50, 0xB200, threads)
+    rate = tr / max(secs, 1e-9)
+    plies = 100
+    slots = max(threads, int(rate * 3.0 / plies))       # ~3 s of CPU work per step
+    for _ in range(args.warmup):
+        pnref.playout_bench(blob, max(threads, slots // 8), plies, 0xB200, threads)
+    t0 = time.perf_counter()
+    total = 0
+    for k in range(args.steps):
+        secs, tr, _ = pnref.playout_bench(blob, slots, plies, 0xB200 + k, threads)
+        total += tr
+    dt = time.perf_counter() - t0
+    val = total / dt
+    cpu = {'value': val, 'unit': 'transitions/s', 'cores': threads, 'kind': 'port',
+           'sample': '%s: %d slots x %d plies per step, %d host threads (oracle/propnet_ref.c; ggplib '
+                     'is absent so the reference state machine itself cannot be built)' % (
+                         PROPNET_GAME, slots, plies, threads)}
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'propnet transitions/sec', 'value': val,
+        'unit': 'transitions/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3 / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': 'breakthrough 8x8 propnet, batched uniform-random playouts'},
+        'cpu_baseline': cpu,
+        'e2e': {'value': val, 'unit': 'transitions/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='propnet', choices=['propnet', 'puct'])
+    ap.add_argument('--slots', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+    rank, world, local = dist_setup(args.gpus)
+    if args.workload == 'propnet':
+        run_propnet(args, rank, world, local)
+    else:
+        raise SystemExit('puct workload not built yet')
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

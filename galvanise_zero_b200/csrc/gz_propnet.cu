@@ -1,0 +1,559 @@
+// gz_propnet.cu — batched, bit-sliced propnet state machine for sm_100a.
+//
+// One warp owns a tile of 32 game states. The value of every live gate for those 32 games is one
+// 32-bit word in the warp's value array in shared memory (bit g = game g). Gate programs are
+// levelised 32-gate chunks (csrc/gz_devformat.h, devprog.py): lane i evaluates gate i of the chunk,
+// __syncwarp() separates levels. Packed per-game rows (states, legal masks) are moved between HBM
+// and shared memory with coalesced 128-bit accesses and converted to/from the bit-sliced form with
+// 32x32 shuffle transposes.
+//
+// Replaces (batched): GGPLib::StateMachineInterface::updateBases / getLegalState / nextState /
+// isTerminal / getGoalValue as called from src/cpp/puct/node.cpp:153-221,
+// src/cpp/puct/evaluator.cpp:216-239 and src/cpp/pyobjects/gdltransformer_impl.cpp:50-124 of the
+// reference. Results are bit-exact with oracle/propnet_ref.c (tests/test_gpu_propnet.py).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/gz_b200.h"
+#include "../../include/gz_propnet_format.h"
+#include "gz_devformat.h"
+#include "gz_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+struct PnParams {
+    const uint32_t* prog[3];  // A (next-state cone), LT (legal+terminal), GL (goals)
+    int chunks[3];
+    int words[3];
+    int staged[3];
+    const uint16_t* next_lit;   // [nbw*32]   padded with FALSE
+    const uint16_t* legal_lit;  // [lw_used*32] padded with FALSE, role words concatenated
+    const uint16_t* goal_lit;
+    const uint8_t* goal_val;
+    const uint32_t* init_words;  // [state_words]
+    int goal_off[GZ_PN_MAX_ROLES + 1];
+    int role_sizes[GZ_PN_MAX_ROLES];
+    int legal_word_off[GZ_PN_MAX_ROLES + 1];
+    int input_slot0[GZ_PN_MAX_ROLES];
+    int n_bases, n_roles, n_inputs, state_words, legal_words, val_words, terminal_lit;
+    int nbw;           // words holding base bits = ceil(n_bases/32)
+    int lw_used;       // legal words actually used
+    int row_stride;    // odd stride of the per-warp staging rows
+    int warp_words;    // shared-memory words per warp
+    int staged_words;  // shared-memory words holding staged programs
+};
+
+enum { MODE_EVAL = 0, MODE_TRANSITION = 1, MODE_PLAYOUT = 2 };
+
+// lane i holds row i of a 32x32 bit matrix; returns column i (bit j of result = bit i of row j).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t m = (s == 16) ? 0x0000FFFFu : (s == 8) ? 0x00FF00FFu : (s == 4) ? 0x0F0F0F0Fu
+                         : (s == 2) ? 0x33333333u : 0x55555555u;
+        uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? (((y >> s) & m) | (x & ~m)) : ((x & m) | ((y << s) & ~m));
+    }
+    return x;
+}
+
+__device__ __forceinline__ uint32_t lit_word(const uint32_t* val, uint32_t lit) {
+    return val[lit >> 1] ^ (0u - (lit & 1u));
+}
+
+// Evaluates one chunk stream on the warp's value array.
+__device__ __forceinline__ void run_program(const uint32_t* __restrict__ prog, int n_chunks,
+                                            uint32_t* __restrict__ val, int lane) {
+    const uint32_t* p = prog;
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t hdr = p[0];
+        const int nl2 = (int)((hdr & 0xffu) >> 1);
+        const uint32_t ow = p[1 + (lane >> 1)];
+        const uint32_t out = (lane & 1) ? (ow >> 16) : (ow & 0xffffu);
+        uint32_t acc = 0xffffffffu;
+        const uint32_t* lp = p + 17 + lane;
+#pragma unroll 2
+        for (int k = 0; k < nl2; ++k) {
+            const uint32_t pr = lp[k * 32];
+            acc &= lit_word(val, pr & 0xffffu) & lit_word(val, pr >> 16);
+        }
+        val[out] = acc;
+        p += 17 + 32 * nl2;
+        if (hdr & 0x100u) __syncwarp();
+    }
+}
+
+// Coalesced copy of `rows` packed rows (row_words words each, multiple of 4) HBM -> staging rows.
+__device__ __forceinline__ void load_rows(const uint32_t* __restrict__ src, int row_words, int rows,
+                                          uint32_t* stage, int rs, int lane) {
+    if (lane >= rows)
+        for (int c = 0; c < row_words; ++c) stage[lane * rs + c] = 0;
+    const int qpr = row_words >> 2;
+    const int nq = rows * qpr;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    for (int q = lane; q < nq; q += 32) {
+        const uint4 v = s4[q];
+        const int r = q / qpr;
+        const int c = (q - r * qpr) << 2;
+        uint32_t* d = stage + r * rs + c;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void store_rows(uint32_t* __restrict__ dst, int row_words, int rows,
+                                           const uint32_t* stage, int rs, int lane) {
+    __syncwarp();
+    const int qpr = row_words >> 2;
+    const int nq = rows * qpr;
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int q = lane; q < nq; q += 32) {
+        const int r = q / qpr;
+        const int c = (q - r * qpr) << 2;
+        const uint32_t* s = stage + r * rs + c;
+        d4[q] = make_uint4(s[0], s[1], s[2], s[3]);
+    }
+    __syncwarp();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1)
+pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
+          const uint32_t* states_in, const int16_t* __restrict__ moves_in,
+          uint32_t* states_out, uint32_t* legal,
+          uint8_t* terminal, uint8_t* __restrict__ goals, int16_t* __restrict__ moves_out,
+          unsigned long long* __restrict__ transitions, uint64_t seed, uint64_t step, int goals_mode) {
+    extern __shared__ __align__(16) uint32_t smem[];
+
+    // ---- stage gate programs in shared memory (those the host decided fit)
+    const uint32_t* prog[3];
+    {
+        uint32_t* sp = smem;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (P.staged[k]) {
+                for (int i = threadIdx.x; i < P.words[k]; i += blockDim.x) sp[i] = P.prog[k][i];
+                prog[k] = sp;
+                sp += (P.words[k] + 3) & ~3;
+            } else {
+                prog[k] = P.prog[k];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps = blockDim.x >> 5;
+    uint32_t* val = smem + P.staged_words + warp * P.warp_words;
+    uint32_t* stage = val + P.val_words;
+    uint32_t* slices = stage + 32 * P.row_stride;
+    const int rs = P.row_stride;
+    const int R = P.n_roles;
+    if (lane == 0) val[0] = 0xffffffffu;
+
+    const int64_t n_tiles = (n + 31) >> 5;
+    for (int64_t tile = (int64_t)blockIdx.x * warps + warp; tile < n_tiles;
+         tile += (int64_t)gridDim.x * warps) {
+        const int64_t g0 = tile << 5;
+        const int64_t game = g0 + lane;
+        const int rows = (int)((n - g0) < 32 ? (n - g0) : 32);
+        const bool valid = lane < rows;
+        const uint32_t valid_mask = rows == 32 ? 0xffffffffu : ((1u << rows) - 1u);
+        uint32_t reset_mask = 0;
+        int mv[GZ_PN_MAX_ROLES];
+
+        if (MODE == MODE_PLAYOUT) {
+            // ---- pick one uniformly random legal action per role from the stored legal rows
+            const bool term = valid ? (terminal[game] != 0) : false;
+            reset_mask = __ballot_sync(0xffffffffu, term);
+            load_rows(legal + g0 * P.legal_words, P.legal_words, rows, stage, rs, lane);
+#pragma unroll
+            for (int r = 0; r < GZ_PN_MAX_ROLES; ++r) {
+                mv[r] = -1;
+                if (r < R && valid && !term) {
+                    const uint32_t* w = stage + lane * rs + P.legal_word_off[r];
+                    const int nw = P.legal_word_off[r + 1] - P.legal_word_off[r];
+                    uint32_t cnt = 0;
+                    for (int j = 0; j < nw; ++j) cnt += __popc(w[j]);
+                    uint32_t pick = gz_pick(gz_rand32(seed, (uint64_t)(slot0 + game), step, (uint32_t)r), cnt);
+                    int idx = 0;
+                    for (int j = 0; j < nw; ++j) {
+                        uint32_t x = w[j];
+                        const uint32_t c = __popc(x);
+                        if (pick < c) {
+                            for (uint32_t i = 0; i < pick; ++i) x &= x - 1;
+                            idx = j * 32 + (__ffs(x) - 1);
+                            break;
+                        }
+                        pick -= c;
+                    }
+                    mv[r] = idx;
+                }
+                if (r < R && valid && moves_out) moves_out[game * R + r] = (int16_t)mv[r];
+            }
+            __syncwarp();
+        } else if (MODE == MODE_TRANSITION) {
+#pragma unroll
+            for (int r = 0; r < GZ_PN_MAX_ROLES; ++r)
+                mv[r] = (r < R && valid) ? (int)moves_in[game * R + r] : -1;
+        }
+
+        // ---- load packed states, slice them into the base slots
+        load_rows(states_in + g0 * P.state_words, P.state_words, rows, stage, rs, lane);
+        for (int j = 0; j < P.nbw; ++j) {
+            const uint32_t t = warp_transpose32(stage[lane * rs + j], lane);
+            const int b = j * 32 + lane;
+            if (b < P.n_bases) val[1 + b] = t;
+        }
+
+        if (MODE != MODE_EVAL) {
+            // ---- one-hot the chosen actions into the input slots, run the next-state cone
+            for (int i = lane; i < P.n_inputs; i += 32) val[1 + P.n_bases + i] = 0;
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < GZ_PN_MAX_ROLES; ++r)
+                if (r < R && mv[r] >= 0) atomicOr(&val[P.input_slot0[r] + mv[r]], 1u << lane);
+            __syncwarp();
+            run_program(prog[0], P.chunks[0], val, lane);
+
+            for (int j = 0; j < P.nbw; ++j) {
+                const int b = j * 32 + lane;
+                uint32_t t = lit_word(val, P.next_lit[b]);
+                if (MODE == MODE_PLAYOUT) {
+                    const uint32_t ib = (P.init_words[j] >> lane) & 1u;
+                    t = (t & ~reset_mask) | (ib ? reset_mask : 0u);
+                }
+                t &= valid_mask;
+                slices[b] = t;
+                stage[lane * rs + j] = warp_transpose32(t, lane);
+            }
+            for (int j = P.nbw; j < P.state_words; ++j) stage[lane * rs + j] = 0;
+            store_rows(states_out + g0 * P.state_words, P.state_words, rows, stage, rs, lane);
+            for (int j = 0; j < P.nbw; ++j) {
+                const int b = j * 32 + lane;
+                if (b < P.n_bases) val[1 + b] = slices[b];
+            }
+        }
+        __syncwarp();
+
+        // ---- views of the (new) state: legal masks, terminal, goals
+        run_program(prog[1], P.chunks[1], val, lane);
+        const uint32_t tw = lit_word(val, (uint32_t)P.terminal_lit) & valid_mask;
+        const bool need_goals = (goals_mode == GZ_GOALS_ALWAYS) || (tw != 0u);
+        if (need_goals) run_program(prog[2], P.chunks[2], val, lane);
+
+        for (int j = 0; j < P.lw_used; ++j) {
+            const uint32_t t = lit_word(val, P.legal_lit[j * 32 + lane]) & valid_mask;
+            stage[lane * rs + j] = warp_transpose32(t, lane);
+        }
+        for (int j = P.lw_used; j < P.legal_words; ++j) stage[lane * rs + j] = 0;
+        store_rows(legal + g0 * P.legal_words, P.legal_words, rows, stage, rs, lane);
+
+        const bool is_term = (tw >> lane) & 1u;
+        if (valid) terminal[game] = is_term ? 1 : 0;
+        for (int r = 0; r < R; ++r) {
+            uint32_t gv = 255u;
+            if (need_goals) {
+                for (int k = P.goal_off[r]; k < P.goal_off[r + 1]; ++k) {
+                    const uint32_t w = lit_word(val, P.goal_lit[k]);
+                    if ((w >> lane) & 1u) gv = P.goal_val[k];
+                }
+            }
+            if (goals_mode == GZ_GOALS_TERMINAL_ONLY && !is_term) gv = 255u;
+            if (valid) goals[game * R + r] = (uint8_t)gv;
+        }
+        if (MODE == MODE_PLAYOUT && transitions && lane == 0) {
+            const int cnt = __popc(valid_mask & ~reset_mask);
+            if (cnt) atomicAdd(transitions, (unsigned long long)cnt);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct gz_propnet {
+    int device = 0;
+    PnParams P{};
+    void* d_arena = nullptr;
+    int warps_per_cta = 0;
+    int grid_max = 0;
+    size_t smem_bytes = 0;
+    int n_sms = 0;
+    // scratch for the host-buffer API
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    cudaStream_t host_stream = nullptr;
+};
+
+extern "C" int gz_version(void) { return 100; }
+
+static int configure_launch(gz_propnet* pn, const int32_t* h) {
+    PnParams& P = pn->P;
+    cudaDeviceProp prop;
+    GZ_CUDA(cudaGetDeviceProperties(&prop, pn->device));
+    pn->n_sms = prop.multiProcessorCount;
+    const size_t max_smem = prop.sharedMemPerBlockOptin;  // 227 KB on sm_100
+    const int rs = std::max(P.state_words, P.legal_words) | 1;
+    P.row_stride = rs;
+    P.warp_words = ((P.val_words + 32 * rs + P.nbw * 32) + 3) & ~3;
+    const size_t warp_bytes = (size_t)P.warp_words * 4;
+    // stage programs (A, LT, GL in that priority) while at least MIN_WARPS warps still fit
+    const int MIN_WARPS = 8;
+    size_t staged = 0;
+    for (int k = 0; k < 3; ++k) {
+        const size_t w = (size_t)((P.words[k] + 3) & ~3) * 4;
+        if (P.words[k] > 0 && staged + w + MIN_WARPS * warp_bytes <= max_smem) {
+            P.staged[k] = 1;
+            staged += w;
+        } else {
+            P.staged[k] = 0;
+        }
+    }
+    P.staged_words = (int)(staged / 4);
+    int warps = (int)((max_smem - staged) / warp_bytes);
+    if (warps < 1) {
+        gz_set_error("propnet value array (%zu bytes per warp) does not fit in shared memory", warp_bytes);
+        return GZ_ERR_LIMIT;
+    }
+    warps = std::min(warps, 32);
+    pn->warps_per_cta = warps;
+    pn->smem_bytes = staged + (size_t)warps * warp_bytes;
+    pn->grid_max = pn->n_sms;  // one persistent CTA per SM
+    GZ_CUDA(cudaFuncSetAttribute(pn_kernel<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn->smem_bytes));
+    GZ_CUDA(cudaFuncSetAttribute(pn_kernel<MODE_TRANSITION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn->smem_bytes));
+    GZ_CUDA(cudaFuncSetAttribute(pn_kernel<MODE_PLAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn->smem_bytes));
+    (void)h;
+    return GZ_OK;
+}
+
+extern "C" int gz_propnet_create(const int32_t* h, int64_t n_words, int device, gz_propnet** out) {
+    if (!h || !out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    *out = nullptr;
+    if (n_words < GZ_DEV_HEADER_WORDS || h[D_MAGIC] != GZ_DEV_MAGIC || h[D_VERSION] != GZ_DEV_VERSION ||
+        h[D_TOTAL_WORDS] != n_words) {
+        gz_set_error("not a gz device program blob (magic/version/size mismatch)");
+        return GZ_ERR_FORMAT;
+    }
+    const int R = h[D_N_ROLES];
+    if (R < 1 || R > GZ_PN_MAX_ROLES) { gz_set_error("unsupported role count %d", R); return GZ_ERR_LIMIT; }
+    GZ_CUDA(cudaSetDevice(device));
+    gz_propnet* pn = new gz_propnet();
+    pn->device = device;
+    PnParams& P = pn->P;
+    P.n_bases = h[D_N_BASES];
+    P.n_roles = R;
+    P.n_inputs = h[D_N_INPUTS];
+    P.state_words = h[D_STATE_WORDS];
+    P.legal_words = h[D_LEGAL_WORDS];
+    P.val_words = h[D_VAL_WORDS];
+    P.terminal_lit = h[D_TERMINAL_LIT];
+    P.nbw = (P.n_bases + 31) / 32;
+    const int32_t* role_sizes = h + h[D_OFF_ROLE_SIZES];
+    const int32_t* lwo = h + h[D_OFF_LEGAL_WORD_OFF];
+    const int32_t* goal_off = h + h[D_OFF_GOAL_OFF];
+    int in_off = 1 + P.n_bases;
+    for (int r = 0; r < R; ++r) {
+        P.role_sizes[r] = role_sizes[r];
+        P.input_slot0[r] = in_off;
+        in_off += role_sizes[r];
+    }
+    for (int r = 0; r <= R; ++r) { P.legal_word_off[r] = lwo[r]; P.goal_off[r] = goal_off[r]; }
+    P.lw_used = lwo[R];
+
+    // ---- host-side tables: padded literal arrays
+    std::vector<uint16_t> next_lit((size_t)P.nbw * 32, 1);
+    for (int b = 0; b < P.n_bases; ++b) next_lit[b] = (uint16_t)h[h[D_OFF_NEXT_LIT] + b];
+    std::vector<uint16_t> legal_lit((size_t)P.lw_used * 32, 1);
+    {
+        int src = h[D_OFF_LEGAL_LIT];
+        for (int r = 0; r < R; ++r)
+            for (int a = 0; a < role_sizes[r]; ++a) legal_lit[(size_t)lwo[r] * 32 + a] = (uint16_t)h[src++];
+    }
+    const int n_goal = goal_off[R];
+    std::vector<uint16_t> goal_lit(std::max(n_goal, 1));
+    std::vector<uint8_t> goal_val(std::max(n_goal, 1));
+    for (int k = 0; k < n_goal; ++k) {
+        goal_lit[k] = (uint16_t)h[h[D_OFF_GOAL_LIT] + k];
+        goal_val[k] = (uint8_t)h[h[D_OFF_GOAL_VAL] + k];
+    }
+    const int offs[3] = {D_OFF_PROG_A, D_OFF_PROG_LT, D_OFF_PROG_GL};
+    const int chs[3] = {D_CHUNKS_A, D_CHUNKS_LT, D_CHUNKS_GL};
+    const int hfs[3] = {D_HALFS_A, D_HALFS_LT, D_HALFS_GL};
+
+    // ---- one device arena, every section 16-byte aligned
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    size_t pos = 0;
+    size_t o_prog[3];
+    for (int k = 0; k < 3; ++k) { o_prog[k] = pos; pos += al((size_t)(h[hfs[k]] / 2 + 4) * 4); }
+    const size_t o_next = pos; pos += al(next_lit.size() * 2);
+    const size_t o_legal = pos; pos += al(legal_lit.size() * 2);
+    const size_t o_glit = pos; pos += al(goal_lit.size() * 2);
+    const size_t o_gval = pos; pos += al(goal_val.size());
+    const size_t o_init = pos; pos += al((size_t)P.state_words * 4);
+    std::vector<uint8_t> arena(pos, 0);
+    for (int k = 0; k < 3; ++k) {
+        P.chunks[k] = h[chs[k]];
+        P.words[k] = h[hfs[k]] / 2;
+        memcpy(arena.data() + o_prog[k], h + h[offs[k]], (size_t)P.words[k] * 4);
+    }
+    memcpy(arena.data() + o_next, next_lit.data(), next_lit.size() * 2);
+    memcpy(arena.data() + o_legal, legal_lit.data(), legal_lit.size() * 2);
+    memcpy(arena.data() + o_glit, goal_lit.data(), goal_lit.size() * 2);
+    memcpy(arena.data() + o_gval, goal_val.data(), goal_val.size());
+    memcpy(arena.data() + o_init, h + h[D_OFF_INIT], (size_t)P.state_words * 4);
+    cudaError_t e = cudaMalloc(&pn->d_arena, pos);
+    if (e != cudaSuccess) { gz_set_error("cudaMalloc: %s", cudaGetErrorString(e)); delete pn; return GZ_ERR_CUDA; }
+    e = cudaMemcpy(pn->d_arena, arena.data(), pos, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { gz_set_error("cudaMemcpy: %s", cudaGetErrorString(e)); cudaFree(pn->d_arena); delete pn; return GZ_ERR_CUDA; }
+    const uint8_t* base = (const uint8_t*)pn->d_arena;
+    for (int k = 0; k < 3; ++k) P.prog[k] = (const uint32_t*)(base + o_prog[k]);
+    P.next_lit = (const uint16_t*)(base + o_next);
+    P.legal_lit = (const uint16_t*)(base + o_legal);
+    P.goal_lit = (const uint16_t*)(base + o_glit);
+    P.goal_val = (const uint8_t*)(base + o_gval);
+    P.init_words = (const uint32_t*)(base + o_init);
+    int rc = configure_launch(pn, h);
+    if (rc != GZ_OK) { cudaFree(pn->d_arena); delete pn; return rc; }
+    *out = pn;
+    return GZ_OK;
+}
+
+extern "C" void gz_propnet_destroy(gz_propnet* pn) {
+    if (!pn) return;
+    cudaSetDevice(pn->device);
+    if (pn->d_arena) cudaFree(pn->d_arena);
+    if (pn->d_scratch) cudaFree(pn->d_scratch);
+    if (pn->host_stream) cudaStreamDestroy(pn->host_stream);
+    delete pn;
+}
+
+extern "C" int64_t gz_propnet_info(const gz_propnet* pn, int what) {
+    if (!pn) return -1;
+    const PnParams& P = pn->P;
+    switch (what) {
+        case GZ_INFO_N_BASES: return P.n_bases;
+        case GZ_INFO_N_ROLES: return P.n_roles;
+        case GZ_INFO_STATE_WORDS: return P.state_words;
+        case GZ_INFO_LEGAL_WORDS: return P.legal_words;
+        case GZ_INFO_VAL_WORDS: return P.val_words;
+        case GZ_INFO_WARPS_PER_CTA: return pn->warps_per_cta;
+        case GZ_INFO_SMEM_BYTES: return (int64_t)pn->smem_bytes;
+        case GZ_INFO_GRID: return pn->grid_max;
+        case GZ_INFO_STAGED_MASK: return P.staged[0] | (P.staged[1] << 1) | (P.staged[2] << 2);
+        case GZ_INFO_N_INPUTS: return P.n_inputs;
+        default: break;
+    }
+    if (what >= GZ_INFO_ROLE_SIZE0 && what < GZ_INFO_ROLE_SIZE0 + P.n_roles) return P.role_sizes[what - GZ_INFO_ROLE_SIZE0];
+    if (what >= GZ_INFO_LEGAL_WORD_OFF0 && what <= GZ_INFO_LEGAL_WORD_OFF0 + P.n_roles) return P.legal_word_off[what - GZ_INFO_LEGAL_WORD_OFF0];
+    return -1;
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+template <int MODE>
+static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* states_in, const int16_t* moves_in,
+                  uint32_t* states_out, uint32_t* legal, uint8_t* terminal, uint8_t* goals,
+                  int16_t* moves_out, unsigned long long* transitions, uint64_t seed, uint64_t step,
+                  int goals_mode, void* stream) {
+    if (!pn) { gz_set_error("null propnet"); return GZ_ERR_ARG; }
+    if (n < 0) { gz_set_error("negative batch"); return GZ_ERR_ARG; }
+    if (n == 0) return GZ_OK;
+    if (!states_in || !legal || !terminal || !goals || (MODE != MODE_EVAL && !states_out) ||
+        (MODE == MODE_TRANSITION && !moves_in)) {
+        gz_set_error("null device pointer");
+        return GZ_ERR_ARG;
+    }
+    if (!aligned16(states_in) || !aligned16(legal) || (states_out && !aligned16(states_out))) {
+        gz_set_error("state / legal arrays must be 16-byte aligned");
+        return GZ_ERR_ARG;
+    }
+    if (goals_mode != GZ_GOALS_ALWAYS && goals_mode != GZ_GOALS_TERMINAL_ONLY) {
+        gz_set_error("bad goals_mode");
+        return GZ_ERR_ARG;
+    }
+    GZ_CUDA(cudaSetDevice(pn->device));
+    const int64_t n_tiles = (n + 31) / 32;
+    // one persistent CTA per SM; small batches shrink the CTA so that tiles spread over all SMs
+    const int block_warps = (int)std::max<int64_t>(
+        1, std::min<int64_t>(pn->warps_per_cta, (n_tiles + pn->grid_max - 1) / pn->grid_max));
+    const int grid2 = (int)std::min<int64_t>((n_tiles + block_warps - 1) / block_warps, pn->grid_max);
+    const size_t smem = (size_t)pn->P.staged_words * 4 + (size_t)block_warps * pn->P.warp_words * 4;
+    pn_kernel<MODE><<<grid2, block_warps * 32, smem, (cudaStream_t)stream>>>(
+        pn->P, n, slot0, states_in, moves_in, states_out, legal, terminal, goals, moves_out, transitions,
+        seed, step, goals_mode);
+    GZ_CUDA(cudaGetLastError());
+    return GZ_OK;
+}
+
+extern "C" int gz_sm_eval(gz_propnet* pn, int64_t n, const uint32_t* d_states, uint32_t* d_legal,
+                          uint8_t* d_terminal, uint8_t* d_goals, int goals_mode, void* stream) {
+    return launch<MODE_EVAL>(pn, n, 0, d_states, nullptr, nullptr, d_legal, d_terminal, d_goals, nullptr,
+                             nullptr, 0, 0, goals_mode, stream);
+}
+
+extern "C" int gz_sm_transition(gz_propnet* pn, int64_t n, const uint32_t* d_states, const int16_t* d_moves,
+                                uint32_t* d_next, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,
+                                int goals_mode, void* stream) {
+    return launch<MODE_TRANSITION>(pn, n, 0, d_states, d_moves, d_next, d_legal, d_terminal, d_goals,
+                                   nullptr, nullptr, 0, 0, goals_mode, stream);
+}
+
+extern "C" int gz_sm_playout_step(gz_propnet* pn, int64_t slot0, int64_t n, uint64_t seed, uint64_t step,
+                                  uint32_t* d_states, uint32_t* d_legal, uint8_t* d_terminal,
+                                  uint8_t* d_goals, int16_t* d_moves_out,
+                                  unsigned long long* d_transitions, int goals_mode, void* stream) {
+    return launch<MODE_PLAYOUT>(pn, n, slot0, d_states, nullptr, d_states, d_legal, d_terminal, d_goals,
+                                d_moves_out, d_transitions, seed, step, goals_mode, stream);
+}
+
+extern "C" int gz_sm_transition_host(gz_propnet* pn, int64_t n, const uint32_t* h_states,
+                                     const int16_t* h_moves, uint32_t* h_next, uint32_t* h_legal,
+                                     uint8_t* h_terminal, uint8_t* h_goals, int goals_mode) {
+    if (!pn) { gz_set_error("null propnet"); return GZ_ERR_ARG; }
+    if (n <= 0) return n == 0 ? GZ_OK : GZ_ERR_ARG;
+    if (!h_states || !h_moves || !h_next || !h_legal || !h_terminal || !h_goals) {
+        gz_set_error("null host pointer");
+        return GZ_ERR_ARG;
+    }
+    GZ_CUDA(cudaSetDevice(pn->device));
+    const PnParams& P = pn->P;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_states = al((size_t)n * P.state_words * 4);
+    const size_t b_moves = al((size_t)n * P.n_roles * 2);
+    const size_t b_legal = al((size_t)n * P.legal_words * 4);
+    const size_t b_term = al((size_t)n);
+    const size_t b_goals = al((size_t)n * P.n_roles);
+    const size_t need = 2 * b_states + b_moves + b_legal + b_term + b_goals;
+    if (need > pn->scratch_bytes) {
+        if (pn->d_scratch) cudaFree(pn->d_scratch);
+        pn->d_scratch = nullptr;
+        pn->scratch_bytes = 0;
+        GZ_CUDA(cudaMalloc(&pn->d_scratch, need));
+        pn->scratch_bytes = need;
+    }
+    if (!pn->host_stream) GZ_CUDA(cudaStreamCreateWithFlags(&pn->host_stream, cudaStreamNonBlocking));
+    uint8_t* p = (uint8_t*)pn->d_scratch;
+    uint32_t* d_states = (uint32_t*)p; p += b_states;
+    uint32_t* d_next = (uint32_t*)p; p += b_states;
+    int16_t* d_moves = (int16_t*)p; p += b_moves;
+    uint32_t* d_legal = (uint32_t*)p; p += b_legal;
+    uint8_t* d_term = p; p += b_term;
+    uint8_t* d_goals = p;
+    cudaStream_t s = pn->host_stream;
+    GZ_CUDA(cudaMemcpyAsync(d_states, h_states, (size_t)n * P.state_words * 4, cudaMemcpyHostToDevice, s));
+    GZ_CUDA(cudaMemcpyAsync(d_moves, h_moves, (size_t)n * P.n_roles * 2, cudaMemcpyHostToDevice, s));
+    int rc = gz_sm_transition(pn, n, d_states, d_moves, d_next, d_legal, d_term, d_goals, goals_mode, s);
+    if (rc != GZ_OK) return rc;
+    GZ_CUDA(cudaMemcpyAsync(h_next, d_next, (size_t)n * P.state_words * 4, cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaMemcpyAsync(h_legal, d_legal, (size_t)n * P.legal_words * 4, cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaMemcpyAsync(h_terminal, d_term, (size_t)n, cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaMemcpyAsync(h_goals, d_goals, (size_t)n * P.n_roles, cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaStreamSynchronize(s));
+    return GZ_OK;
+}

@@ -1,0 +1,95 @@
+/* gz_b200.h — C-ABI of the B200-native self-play hot path (libgz_b200.so).
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in the signatures (streams cross as void*,
+ * i.e. a cudaStream_t; 0 = the legacy default stream). Pointers named d_* are DEVICE pointers,
+ * h_* are HOST pointers. All functions return 0 on success, a negative gz_status otherwise, and
+ * gz_last_error() describes the failure. There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with GZ_ERR_CUDA.
+ *
+ * What each entry point replaces in the reference (the calls a maintainer would re-bind):
+ *
+ *   gz_propnet_create            ggplib's state-machine construction for a game, consumed through
+ *                                sm_ptr by Supervisor/Player (src/cpp/pyobjects/supervisor_impl.cpp:215-237,
+ *                                src/cpp/supervisor.cpp:20-31 `sm->dupe()`)
+ *   gz_sm_eval                   StateMachineInterface::updateBases + getLegalState + isTerminal +
+ *                                getGoalValue            (src/cpp/puct/node.cpp:157-217), batched
+ *   gz_sm_transition             updateBases + nextState + updateBases + legal/terminal/goal
+ *                                (src/cpp/puct/evaluator.cpp:216-239 expandChild -> node.cpp:153-221)
+ *   gz_sm_playout_step           the random playout loop of GdlBasesTransformer.test
+ *                                (src/cpp/pyobjects/gdltransformer_impl.cpp:50-124), one ply per call
+ *   gz_sm_transition_host        same as gz_sm_transition with host buffers (copies inside)
+ */
+#ifndef GZ_B200_H
+#define GZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GZ_OK = 0,
+    GZ_ERR_ARG = -1,
+    GZ_ERR_CUDA = -2,
+    GZ_ERR_FORMAT = -3,
+    GZ_ERR_LIMIT = -4
+} gz_status;
+
+typedef struct gz_propnet gz_propnet;
+
+/* goals_mode */
+#define GZ_GOALS_ALWAYS 0        /* goal values computed for every state */
+#define GZ_GOALS_TERMINAL_ONLY 1 /* goal cone only evaluated for tiles holding a terminal state;
+                                    non-terminal states report 255 */
+
+const char* gz_last_error(void);
+int gz_version(void);
+
+/* Builds the device-resident program of one game from a device blob (galvanise_zero_b200/devprog.py,
+ * layout in csrc/gz_devformat.h) on CUDA device `device`. */
+int gz_propnet_create(const int32_t* h_dev_blob, int64_t n_words, int device, gz_propnet** out);
+void gz_propnet_destroy(gz_propnet* pn);
+
+/* info selectors for gz_propnet_info */
+enum {
+    GZ_INFO_N_BASES = 0, GZ_INFO_N_ROLES = 1, GZ_INFO_STATE_WORDS = 2, GZ_INFO_LEGAL_WORDS = 3,
+    GZ_INFO_VAL_WORDS = 4, GZ_INFO_WARPS_PER_CTA = 5, GZ_INFO_SMEM_BYTES = 6, GZ_INFO_GRID = 7,
+    GZ_INFO_STAGED_MASK = 8, GZ_INFO_N_INPUTS = 9, GZ_INFO_ROLE_SIZE0 = 16 /* +r */,
+    GZ_INFO_LEGAL_WORD_OFF0 = 24 /* +r */
+};
+int64_t gz_propnet_info(const gz_propnet* pn, int what);
+
+/* Layouts (n = number of states, R = roles):
+ *   states  uint32 [n][state_words]   packed bases, LSB first, rows padded to 16 B
+ *   legal   uint32 [n][legal_words]   per role ceil(A_r/32) words at legal_word_off[r], padded to 16 B
+ *   moves   int16  [n][R]             one action index per role
+ *   terminal uint8 [n]     goals uint8 [n][R] (255 = no goal proposition true / not evaluated)
+ */
+int gz_sm_eval(gz_propnet* pn, int64_t n, const uint32_t* d_states, uint32_t* d_legal,
+               uint8_t* d_terminal, uint8_t* d_goals, int goals_mode, void* stream);
+
+int gz_sm_transition(gz_propnet* pn, int64_t n, const uint32_t* d_states, const int16_t* d_moves,
+                     uint32_t* d_next, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,
+                     int goals_mode, void* stream);
+
+/* One random-playout ply for slots [slot0, slot0+n), in place. Terminal slots restart from the
+ * initial state; the others draw one uniformly random legal action per role with
+ * gz_rand32(seed, slot, step, role) (include/gz_propnet_format.h) and advance.
+ * d_moves_out (optional, may be NULL) receives the chosen actions (-1 on restart);
+ * d_transitions (optional) is incremented by the number of real transitions. */
+int gz_sm_playout_step(gz_propnet* pn, int64_t slot0, int64_t n, uint64_t seed, uint64_t step,
+                       uint32_t* d_states, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,
+                       int16_t* d_moves_out, unsigned long long* d_transitions, int goals_mode,
+                       void* stream);
+
+/* Host-buffer variant of gz_sm_transition: H2D copies, kernel, D2H copies and a stream
+ * synchronise happen inside the call (pinned staging owned by `pn`). */
+int gz_sm_transition_host(gz_propnet* pn, int64_t n, const uint32_t* h_states, const int16_t* h_moves,
+                          uint32_t* h_next, uint32_t* h_legal, uint8_t* h_terminal, uint8_t* h_goals,
+                          int goals_mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,157 @@
+"""GPU parity: the CUDA propnet kernels, called through the C-ABI, are bit-exact with the C oracle
+(oracle/propnet_ref.c) on seeded random playouts: legal masks, next states, terminal, goals."""
+import numpy as np
+import pytest
+import torch
+
+from galvanise_zero_b200 import lib as gzlib
+from galvanise_zero_b200 import tables
+from oracle.pnref import RefStateMachine
+
+pytestmark = pytest.mark.gpu
+
+GAMES = ['breakthrough', 'reversi', 'connect6', 'amazons_10x10', 'breakthroughSmall']
+
+
+def _sm(game, **kw):
+    from galvanise_zero_b200.statemachine import DeviceStateMachine
+    return DeviceStateMachine(game, **kw)
+
+
+def _np(t):
+    a = t.cpu().numpy()
+    return a.view(np.uint32) if a.dtype == np.int32 else a
+
+
+@pytest.mark.parametrize('game', GAMES)
+@pytest.mark.parametrize('n', [1, 33, 1000])
+def test_playout_steps_bit_exact(game, n):
+    dev = _sm(game)
+    ref = RefStateMachine(tables.blob_by_name(game))
+    assert dev.state_words == ref.state_words and dev.legal_words == ref.legal_words
+    steps = {'breakthrough': 90, 'reversi': 70, 'connect6': 25, 'amazons_10x10': 30,
+             'breakthroughSmall': 60}[game]
+    if n == 1000:
+        steps = min(steps, 40)
+    seed = 0xB200 + n
+    # oracle arrays
+    s_r = np.zeros((n, ref.state_words), dtype=np.uint32)
+    l_r = np.zeros((n, ref.legal_words), dtype=np.uint32)
+    t_r = np.ones(n, dtype=np.uint8)
+    g_r = np.zeros((n, ref.n_roles), dtype=np.uint8)
+    m_r = np.zeros((n, ref.n_roles), dtype=np.int16)
+    # device arrays
+    s_d = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
+    l_d, t_d, g_d = dev.alloc_views(n)
+    t_d.fill_(1)
+    m_d = torch.zeros((n, dev.n_roles), dtype=torch.int16, device=dev.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev.device)
+    total = 0
+    for step in range(steps):
+        total += ref.playout_step(5, seed, step, s_r, l_r, t_r, g_r, m_r)
+        dev.playout_step(s_d, l_d, t_d, g_d, seed, step, slot0=5, moves_out=m_d, counter=cnt)
+        assert np.array_equal(_np(m_d), m_r), (game, step, 'moves')
+        assert np.array_equal(_np(s_d), s_r), (game, step, 'states')
+        assert np.array_equal(_np(l_d), l_r), (game, step, 'legal')
+        assert np.array_equal(_np(t_d), t_r), (game, step, 'terminal')
+        assert np.array_equal(_np(g_d), g_r), (game, step, 'goals')
+    assert int(cnt.item()) == total
+
+
+@pytest.mark.parametrize('game', ['breakthrough', 'reversi'])
+def test_transition_eval_and_host_api(game):
+    dev = _sm(game)
+    ref = RefStateMachine(tables.blob_by_name(game))
+    n = 777
+    s = np.zeros((n, ref.state_words), dtype=np.uint32)
+    l = np.zeros((n, ref.legal_words), dtype=np.uint32)
+    t = np.ones(n, dtype=np.uint8)
+    g = np.zeros((n, ref.n_roles), dtype=np.uint8)
+    m = np.zeros((n, ref.n_roles), dtype=np.int16)
+    for step in range(25):
+        prev = s.copy()
+        ref.playout_step(0, 99, step, s, l, t, g, m)
+    # last step: prev --m--> s for the slots that were not restarted
+    live = (m[:, 0] >= 0)
+    assert live.sum() > n // 2
+    prev_l, mv = prev[live], m[live]
+    want = ref.transition_batch(prev_l, mv)
+    got = dev.transition(torch.from_numpy(prev_l.view(np.int32)).to(dev.device),
+                         torch.from_numpy(mv).to(dev.device))
+    for a, b in zip(got, want):
+        assert np.array_equal(_np(a), b)
+    got_h = dev.transition_host(prev_l, mv)
+    for a, b in zip(got_h, want):
+        assert np.array_equal(a, b)
+    ev = dev.eval(torch.from_numpy(s.view(np.int32)).to(dev.device))
+    for a, b in zip(ev, ref.eval_batch(s)):
+        assert np.array_equal(_np(a), b)
+
+
+def test_goals_terminal_only_mode():
+    game = 'breakthroughSmall'
+    dev = _sm(game, goals_mode=gzlib.GOALS_TERMINAL_ONLY)
+    ref = RefStateMachine(tables.blob_by_name(game))
+    n = 256
+    s = np.zeros((n, ref.state_words), dtype=np.uint32)
+    l = np.zeros((n, ref.legal_words), dtype=np.uint32)
+    t = np.ones(n, dtype=np.uint8)
+    g = np.zeros((n, ref.n_roles), dtype=np.uint8)
+    for step in range(45):
+        ref.playout_step(0, 3, step, s, l, t, g, None)
+    assert t.any() and not t.all()
+    lg, tm, gl = dev.eval(torch.from_numpy(s.view(np.int32)).to(dev.device))
+    gl = _np(gl)
+    assert np.array_equal(_np(tm), t)
+    assert np.array_equal(gl[t == 1], g[t == 1])
+    assert (gl[t == 0] == 255).all()
+
+
+def test_empty_and_bad_arguments():
+    dev = _sm('breakthrough')
+    s = torch.zeros((0, dev.state_words), dtype=torch.int32, device=dev.device)
+    lg, tm, gl = dev.eval(s)
+    assert lg.shape[0] == 0
+    L = gzlib.lib()
+    rc = L.gz_sm_eval(dev._h, 4, None, None, None, None, 0, None)
+    assert rc != 0 and b'null' in L.gz_last_error()
+
+
+def test_full_size_playout_properties():
+    """BASELINE config 1 size (2^20 slots): size-independent checks — transition count equals the
+    number of non-terminal slots, restarted slots hold the initial state, legal masks non-empty."""
+    dev = _sm('breakthrough')
+    n = 1 << 20
+    s = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
+    l, t, g = dev.alloc_views(n)
+    t.fill_(1)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev.device)
+    expect = 0
+    for step in range(70):
+        live = int((t == 0).sum().item())
+        expect += live
+        was_term = t.clone()
+        dev.playout_step(s, l, t, g, 0xB200, step, counter=cnt)
+        if step in (0, 69):
+            init = torch.from_numpy(dev.init_words.view(np.int32)).to(dev.device)
+            restarted = s[was_term == 1]
+            assert (restarted == init).all()
+    assert int(cnt.item()) == expect
+    # every non-terminal state has at least one legal move per role
+    lw = l[t == 0]
+    for r in range(dev.n_roles):
+        words = lw[:, dev.legal_word_off[r]:dev.legal_word_off[r + 1]]
+        assert (words != 0).any(dim=1).all()
+    # bit-exact against the oracle on a 2^12-slot slice of the same run (same slot ids and seed)
+    ref = RefStateMachine(tables.blob_by_name('breakthrough'))
+    m = 1 << 12
+    sr = np.zeros((m, ref.state_words), dtype=np.uint32)
+    lr = np.zeros((m, ref.legal_words), dtype=np.uint32)
+    tr = np.ones(m, dtype=np.uint8)
+    gr = np.zeros((m, ref.n_roles), dtype=np.uint8)
+    off = 123 * 32
+    for step in range(70):
+        ref.playout_step(off, 0xB200, step, sr, lr, tr, gr, None)
+    assert np.array_equal(_np(s[off:off + m]), sr)
+    assert np.array_equal(_np(l[off:off + m]), lr)
+    assert np.array_equal(_np(t[off:off + m]), tr)
