@@ -1,0 +1,230 @@
+// gz_encoder.cu — base states -> NCHW input planes (bf16 or f32), batched.
+//
+// Replaces GdlBasesTransformer::toChannels (src/cpp/gdltransformer.cpp:22-52) and the builder
+// methods addBoardBase / addControlBase (src/cpp/gdltransformer.h:87-95, exported to Python at
+// src/cpp/pyobjects/gdltransformer_impl.cpp:27-48,186-219). The kernel is output-oriented: every
+// thread produces 8 consecutive plane elements and stores them with one 128-bit (bf16) or two
+// 128-bit (f32) writes; the scatter tables of the reference are inverted at finalise time.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/gz_b200.h"
+#include "gz_common.cuh"
+#include "gz_encoder.cuh"
+#include "gz_transformer.h"
+
+#define ENC_STATES_PER_BLOCK 8
+#define ENC_THREADS 256
+
+template <typename OutT>
+__device__ __forceinline__ OutT enc_cast(float v);
+template <>
+__device__ __forceinline__ float enc_cast<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 enc_cast<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(ENC_THREADS)
+encode_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint32_t* __restrict__ states,
+              const uint32_t* __restrict__ prev, const uint8_t* __restrict__ prev_count, int max_prev,
+              OutT* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t esm[];
+    uint32_t* cur = esm;                                      // [SB][sw]
+    uint32_t* por = cur + ENC_STATES_PER_BLOCK * sw;          // [SB][sw]  OR of previous states
+    float* ctrl = reinterpret_cast<float*>(por + ENC_STATES_PER_BLOCK * sw);  // [SB][NC]
+    const int nc = E.num_control_channels;
+
+    for (int64_t n0 = (int64_t)blockIdx.x * ENC_STATES_PER_BLOCK; n0 < n;
+         n0 += (int64_t)gridDim.x * ENC_STATES_PER_BLOCK) {
+        const int nb = (int)((n - n0) < ENC_STATES_PER_BLOCK ? (n - n0) : ENC_STATES_PER_BLOCK);
+        for (int i = threadIdx.x; i < nb * sw; i += ENC_THREADS) {
+            const int s = i / sw, w = i - s * sw;
+            cur[i] = states[(n0 + s) * sw + w];
+            uint32_t p = 0;
+            if (prev && E.num_prev_states > 0) {
+                const int np = prev_count ? prev_count[n0 + s] : max_prev;
+                for (int k = 0; k < np && k < max_prev; ++k)
+                    p |= prev[((n0 + s) * max_prev + k) * sw + w];
+            }
+            por[i] = p;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * nc; i += ENC_THREADS) {
+            const int s = i / nc, c = i - s * nc;
+            ctrl[s * nc + c] = enc_control_value(E, cur + s * sw, c);
+        }
+        __syncthreads();
+        const int64_t flat0 = n0 * E.total;
+        const int64_t flat_n = (int64_t)nb * E.total;
+        // n0 is a multiple of 8 and rows are E.total elements: flat0 is a multiple of 8 elements
+        for (int64_t v = threadIdx.x; v * 8 < flat_n; v += ENC_THREADS) {
+            OutT vals[8];
+            const int64_t e0 = v * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int64_t e = e0 + k;
+                float x = 0.0f;
+                if (e < flat_n) {
+                    const int s = (int)(e / E.total);
+                    const int le = (int)(e - (int64_t)s * E.total);
+                    x = enc_element(E, cur + s * sw, (prev && E.num_prev_states > 0) ? por + s * sw : nullptr,
+                                    ctrl + s * nc, le);
+                }
+                vals[k] = enc_cast<OutT>(x);
+            }
+            OutT* dst = out + flat0 + e0;
+            if (e0 + 8 <= flat_n) {
+                if (sizeof(OutT) == 2) {
+                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(vals);
+                } else {
+                    reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(vals)[0];
+                    reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(vals)[1];
+                }
+            } else {
+                for (int k = 0; k < 8 && e0 + k < flat_n; ++k) dst[k] = vals[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int gz_transformer_create(int channel_size, int channels_per_state, int num_control_channels,
+                                     int num_prev_states, int num_rewards, const int* policy_sizes,
+                                     int n_policies, gz_transformer** out) {
+    if (!out || channel_size <= 0 || channels_per_state <= 0 || num_control_channels < 0 ||
+        num_prev_states < 0 || n_policies < 0 || (n_policies > 0 && !policy_sizes)) {
+        gz_set_error("bad transformer shape");
+        return GZ_ERR_ARG;
+    }
+    gz_transformer* t = new gz_transformer();
+    t->channel_size = channel_size;
+    t->channels_per_state = channels_per_state;
+    t->num_control_channels = num_control_channels;
+    t->num_prev_states = num_prev_states;
+    t->num_rewards = num_rewards;
+    t->policy_sizes.assign(policy_sizes, policy_sizes + n_policies);
+    *out = t;
+    return GZ_OK;
+}
+
+extern "C" void gz_transformer_destroy(gz_transformer* t) {
+    if (!t) return;
+    if (t->d_arena) { cudaSetDevice(t->device); cudaFree(t->d_arena); }
+    delete t;
+}
+
+extern "C" int gz_transformer_add_board_base(gz_transformer* t, int base_idx, int buf_offset) {
+    if (!t || t->finalized) { gz_set_error("transformer is null or already finalised"); return GZ_ERR_ARG; }
+    const int group = t->channels_per_state * t->channel_size;
+    if (base_idx < 0 || buf_offset < 0 || buf_offset >= group) {
+        gz_set_error("board base %d: offset %d outside one state's planes (%d)", base_idx, buf_offset, group);
+        return GZ_ERR_ARG;
+    }
+    t->board_base.push_back(base_idx);
+    t->board_off.push_back(buf_offset);
+    return GZ_OK;
+}
+
+extern "C" int gz_transformer_add_control_base(gz_transformer* t, int base_idx, int channel_id, float value) {
+    if (!t || t->finalized) { gz_set_error("transformer is null or already finalised"); return GZ_ERR_ARG; }
+    if (base_idx < 0 || channel_id < 0 || channel_id >= t->num_control_channels) {
+        gz_set_error("control base %d: channel %d out of range", base_idx, channel_id);
+        return GZ_ERR_ARG;
+    }
+    t->ctrl_base.push_back(base_idx);
+    t->ctrl_channel.push_back(channel_id);
+    t->ctrl_value.push_back(value);
+    return GZ_OK;
+}
+
+extern "C" int gz_transformer_total_size(const gz_transformer* t) {
+    if (!t) return -1;
+    return t->channel_size * (t->channels_per_state * (t->num_prev_states + 1) + t->num_control_channels);
+}
+
+extern "C" int gz_transformer_finalize(gz_transformer* t, int n_bases, int device) {
+    if (!t) { gz_set_error("null transformer"); return GZ_ERR_ARG; }
+    if (t->finalized) return GZ_OK;
+    const int group = t->channels_per_state * t->channel_size;
+    std::vector<int> src(group, -1);
+    for (size_t i = 0; i < t->board_base.size(); ++i) {
+        if (t->board_base[i] >= n_bases) { gz_set_error("board base index %d >= #bases %d", t->board_base[i], n_bases); return GZ_ERR_ARG; }
+        if (src[t->board_off[i]] >= 0 && src[t->board_off[i]] != t->board_base[i]) {
+            gz_set_error("two board bases (%d, %d) map to plane cell %d; unsupported", src[t->board_off[i]],
+                         t->board_base[i], t->board_off[i]);
+            return GZ_ERR_LIMIT;
+        }
+        src[t->board_off[i]] = t->board_base[i];
+    }
+    for (int b : t->ctrl_base)
+        if (b >= n_bases) { gz_set_error("control base index %d >= #bases %d", b, n_bases); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(device));
+    const size_t nctl = t->ctrl_base.size();
+    const size_t bytes = (group + 2 * nctl + 8) * sizeof(int) + (nctl + 8) * sizeof(float);
+    GZ_CUDA(cudaMalloc(&t->d_arena, bytes));
+    int* d = (int*)t->d_arena;
+    GZ_CUDA(cudaMemcpy(d, src.data(), group * sizeof(int), cudaMemcpyHostToDevice));
+    int* d_cb = d + group;
+    int* d_cc = d_cb + nctl;
+    float* d_cv = (float*)(d_cc + nctl);
+    if (nctl) {
+        GZ_CUDA(cudaMemcpy(d_cb, t->ctrl_base.data(), nctl * sizeof(int), cudaMemcpyHostToDevice));
+        GZ_CUDA(cudaMemcpy(d_cc, t->ctrl_channel.data(), nctl * sizeof(int), cudaMemcpyHostToDevice));
+        GZ_CUDA(cudaMemcpy(d_cv, t->ctrl_value.data(), nctl * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    EncParams& E = t->E;
+    E.src_base = d;
+    E.ctrl_base = d_cb;
+    E.ctrl_channel = d_cc;
+    E.ctrl_value = d_cv;
+    E.n_control = (int)nctl;
+    E.channel_size = t->channel_size;
+    E.group_size = group;
+    E.num_prev_states = t->num_prev_states;
+    E.num_control_channels = t->num_control_channels;
+    E.board_total = group * (t->num_prev_states + 1);
+    E.total = gz_transformer_total_size(t);
+    t->device = device;
+    t->n_bases = n_bases;
+    t->finalized = true;
+    cudaDeviceProp prop;
+    GZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    t->n_sms = prop.multiProcessorCount;
+    return GZ_OK;
+}
+
+extern "C" int gz_encode(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
+                         const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
+                         int out_dtype, void* stream) {
+    if (!t || !t->finalized) { gz_set_error("transformer is null or not finalised"); return GZ_ERR_ARG; }
+    if (n < 0 || state_words * 32 < t->n_bases) { gz_set_error("bad batch / state_words"); return GZ_ERR_ARG; }
+    if (n == 0) return GZ_OK;
+    if (!d_states || !d_out) { gz_set_error("null device pointer"); return GZ_ERR_ARG; }
+    if (d_prev && max_prev < 1) { gz_set_error("max_prev must be >= 1 with previous states"); return GZ_ERR_ARG; }
+    if ((((uintptr_t)d_out) & 15) != 0) { gz_set_error("plane buffer must be 16-byte aligned"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(t->device));
+    const size_t smem = (size_t)ENC_STATES_PER_BLOCK * (2 * state_words * 4 + t->num_control_channels * 4) + 16;
+    const int64_t blocks = (n + ENC_STATES_PER_BLOCK - 1) / ENC_STATES_PER_BLOCK;
+    const int grid = (int)std::min<int64_t>(blocks, (int64_t)t->n_sms * 8);
+    if (out_dtype == GZ_DTYPE_BF16) {
+        if (smem > 48 * 1024)
+            GZ_CUDA(cudaFuncSetAttribute(encode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encode_kernel<__nv_bfloat16><<<grid, ENC_THREADS, smem, (cudaStream_t)stream>>>(
+            t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (__nv_bfloat16*)d_out);
+    } else if (out_dtype == GZ_DTYPE_F32) {
+        if (smem > 48 * 1024)
+            GZ_CUDA(cudaFuncSetAttribute(encode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        encode_kernel<float><<<grid, ENC_THREADS, smem, (cudaStream_t)stream>>>(
+            t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (float*)d_out);
+    } else {
+        gz_set_error("bad out_dtype");
+        return GZ_ERR_ARG;
+    }
+    GZ_CUDA(cudaGetLastError());
+    return GZ_OK;
+}

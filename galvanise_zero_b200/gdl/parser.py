@@ -36,7 +36,7 @@ def tokenize(text: str) -> List[str]:
 
 
 def parse_sexprs(text: str) -> List[Term]:
-    """Parse all top-level s-expressions. Symbols are lower-cased (KIF is case-insensitive)."""
+    """Parse all top-level s-expressions. Symbol case is preserved (as ggplib does: the reference matches "cellHolds", "justMoved")."""
     toks = tokenize(text)
     pos = 0
     n = len(toks)
@@ -54,7 +54,7 @@ def parse_sexprs(text: str) -> List[Term]:
             return tuple(items)
         if t == ')':
             raise ValueError("unbalanced ')'")
-        return intern(t.lower())
+        return intern(t)
 
     res = []
     while pos < n:

@@ -1,0 +1,122 @@
+"""``ggpzero_interface`` — the reference's extension-module surface, re-hosted on libgz_b200.
+
+The reference module (``src/cpp/ggpzero_interface.cpp:50-96``) exports three factories —
+``GdlBasesTransformer``, ``Player``, ``Supervisor`` — plus ``buf_to_tuple_reverse_bytes`` and the
+exception ``GGPZeroInterfaceError``. The same names, argument orders and method names are kept here;
+each object forwards to the C-ABI of ``include/gz_b200.h``. New, additive methods (``encode`` on
+device tensors, ``poll_device``) carry the north-star requirement that planes never round-trip
+through the host.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import lib as _lib
+
+GGPZeroInterfaceError = _lib.GzError
+
+
+def buf_to_tuple_reverse_bytes(buf) -> tuple:
+    """bytes -> tuple of bools, MSB first per byte (inverse of ``np.packbits``);
+    reference: ``src/cpp/ggpzero_interface.cpp:22-46``."""
+    a = np.frombuffer(bytes(buf), dtype=np.uint8)
+    return tuple(bool(x) for x in np.unpackbits(a))
+
+
+def _declare(L):
+    if getattr(L, '_gz_tr_declared', False):
+        return
+    vp, ci, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    L.gz_transformer_create.argtypes = [ci, ci, ci, ci, ci, ctypes.POINTER(ci), ci, ctypes.POINTER(vp)]
+    L.gz_transformer_destroy.argtypes = [vp]
+    L.gz_transformer_add_board_base.argtypes = [vp, ci, ci]
+    L.gz_transformer_add_control_base.argtypes = [vp, ci, ci, ctypes.c_float]
+    L.gz_transformer_finalize.argtypes = [vp, ci, ci]
+    L.gz_transformer_total_size.argtypes = [vp]
+    L.gz_encode.argtypes = [vp, i64, ci, vp, vp, vp, ci, vp, ci, vp]
+    L._gz_tr_declared = True
+
+
+class GdlBasesTransformer(object):
+    """C-side transformer (reference: ``src/cpp/pyobjects/gdltransformer_impl.cpp:186-219``)."""
+
+    def __init__(self, channel_size, channels_per_state, num_control_channels, num_prev_states,
+                 num_rewards, policy_sizes):
+        self._L = _lib.lib()
+        _declare(self._L)
+        self.channel_size = int(channel_size)
+        self.channels_per_state = int(channels_per_state)
+        self.num_control_channels = int(num_control_channels)
+        self.num_prev_states = int(num_prev_states)
+        self.num_rewards = int(num_rewards)
+        self.policy_sizes = [int(x) for x in policy_sizes]
+        arr = (ctypes.c_int * len(self.policy_sizes))(*self.policy_sizes)
+        h = ctypes.c_void_p()
+        _lib.check(self._L.gz_transformer_create(self.channel_size, self.channels_per_state,
+                                                 self.num_control_channels, self.num_prev_states,
+                                                 self.num_rewards, arr, len(self.policy_sizes),
+                                                 ctypes.byref(h)))
+        self._h = h
+        self._finalized_for = None
+        self.board_bases = []       # kept for introspection / oracle construction in tests
+        self.control_bases = []
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            self._L.gz_transformer_destroy(h)
+            self._h = None
+
+    # ---- builder methods (same names as the reference)
+    def add_board_base(self, base_idx, buf_offset):
+        _lib.check(self._L.gz_transformer_add_board_base(self._h, int(base_idx), int(buf_offset)))
+        self.board_bases.append((int(base_idx), int(buf_offset)))
+
+    def add_control_base(self, base_idx, channel_id, value):
+        _lib.check(self._L.gz_transformer_add_control_base(self._h, int(base_idx), int(channel_id),
+                                                           float(value)))
+        self.control_bases.append((int(base_idx), int(channel_id), float(value)))
+
+    def total_size(self):
+        return int(self._L.gz_transformer_total_size(self._h))
+
+    @property
+    def num_channels(self):
+        return self.channels_per_state * (self.num_prev_states + 1) + self.num_control_channels
+
+    # ---- device side
+    def finalize(self, n_bases, device=0):
+        if self._finalized_for is None:
+            _lib.check(self._L.gz_transformer_finalize(self._h, int(n_bases), int(device)))
+            self._finalized_for = (int(n_bases), int(device))
+        return self
+
+    def encode(self, states, prev_states=None, prev_count=None, out=None, dtype=None):
+        """states int32 [n, sw] (CUDA) -> planes [n, total_size] (bf16 default, or float32).
+        prev_states int32 [n, max_prev, sw], nearest ancestor first; prev_count uint8 [n]."""
+        import torch
+        assert self._finalized_for is not None, 'call finalize(n_bases, device) first'
+        assert states.is_cuda and states.dtype == torch.int32 and states.is_contiguous()
+        n, sw = states.shape
+        if dtype is None:
+            dtype = out.dtype if out is not None else torch.bfloat16
+        if out is None:
+            out = torch.empty((n, self.total_size()), dtype=dtype, device=states.device)
+        assert out.is_contiguous() and out.shape[0] == n and out[0].numel() == self.total_size()
+        code = {torch.float32: 0, torch.bfloat16: 1}[out.dtype]
+        max_prev = 0
+        pp = pc = None
+        if prev_states is not None:
+            assert prev_states.is_cuda and prev_states.dtype == torch.int32 and prev_states.is_contiguous()
+            assert prev_states.dim() == 3 and prev_states.shape[0] == n and prev_states.shape[2] == sw
+            max_prev = prev_states.shape[1]
+            pp = prev_states.data_ptr()
+            if prev_count is not None:
+                assert prev_count.dtype == torch.uint8 and prev_count.shape == (n,)
+                pc = prev_count.data_ptr()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(states.device).cuda_stream)
+        _lib.check(self._L.gz_encode(self._h, n, sw, states.data_ptr(), pp, pc, max_prev,
+                                     out.data_ptr(), code, stream))
+        return out

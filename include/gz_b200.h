@@ -89,6 +89,37 @@ int gz_sm_transition_host(gz_propnet* pn, int64_t n, const uint32_t* h_states, c
                           uint32_t* h_next, uint32_t* h_legal, uint8_t* h_terminal, uint8_t* h_goals,
                           int goals_mode);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Base-state -> input-plane encoder. Replaces GdlBasesTransformer (src/cpp/gdltransformer.h:69-149,
+ * exported as ggpzero_interface.GdlBasesTransformer, src/cpp/pyobjects/gdltransformer_impl.cpp:186-219):
+ *   gz_transformer_create            the constructor "iiiiiO!" (channel_size, channels_per_state,
+ *                                    num_control_channels, num_prev_states, num_rewards, [policy sizes])
+ *   gz_transformer_add_board_base    .add_board_base(base_idx, buf_offset)     (gdltransformer_impl.cpp:27-36)
+ *   gz_transformer_add_control_base  .add_control_base(base_idx, channel, value) (gdltransformer_impl.cpp:38-48)
+ *   gz_transformer_finalize          (new) freezes the tables and uploads them to `device`
+ *   gz_encode                        GdlBasesTransformer::toChannels (src/cpp/gdltransformer.cpp:22-52), batched
+ */
+typedef struct gz_transformer gz_transformer;
+#define GZ_DTYPE_F32 0
+#define GZ_DTYPE_BF16 1
+
+int gz_transformer_create(int channel_size, int channels_per_state, int num_control_channels,
+                          int num_prev_states, int num_rewards, const int* policy_sizes, int n_policies,
+                          gz_transformer** out);
+void gz_transformer_destroy(gz_transformer* t);
+int gz_transformer_add_board_base(gz_transformer* t, int base_idx, int buf_offset);
+int gz_transformer_add_control_base(gz_transformer* t, int base_idx, int channel_id, float value);
+int gz_transformer_finalize(gz_transformer* t, int n_bases, int device);
+int gz_transformer_total_size(const gz_transformer* t);
+
+/* d_states uint32 [n][state_words]; d_prev uint32 [n][max_prev][state_words] (nearest ancestor first,
+ * may be NULL); d_prev_count uint8 [n] = how many of them exist (NULL = all max_prev);
+ * d_out [n][total_size] of out_dtype, channels-first. */
+int gz_encode(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
+              const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
+              int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

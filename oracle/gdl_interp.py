@@ -47,7 +47,7 @@ def parse(text):
                 items.append(read())
             pos += 1
             return tuple(items)
-        return sys.intern(t.lower())
+        return sys.intern(t)
 
     res = []
     while pos < len(toks):

@@ -145,3 +145,55 @@ def playout_bench(blob, n_slots, n_steps, seed, n_threads):
     secs = lib().pnref_playout_bench(_p(blob, ctypes.c_int32), len(blob), n_slots, n_steps, seed,
                                      n_threads, ctypes.byref(tr), ctypes.byref(ck))
     return secs, tr.value, ck.value
+
+
+# ------------------------------------------------------------------------------------------------
+class RefEncoder:
+    """ctypes binding of oracle/encoder_ref.c (restatement of gdltransformer.cpp:14-52)."""
+
+    def __init__(self, channel_size, channels_per_state, num_control_channels, num_prev_states):
+        L = lib()
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.encref_create.restype = vp
+        L.encref_create.argtypes = [ci, ci, ci, ci]
+        L.encref_destroy.argtypes = [vp]
+        L.encref_add_board_base.argtypes = [vp, ci, ci]
+        L.encref_add_control_base.argtypes = [vp, ci, ci, ctypes.c_float]
+        L.encref_total_size.argtypes = [vp]
+        L.encref_batch.argtypes = [vp, ctypes.c_int64, ci, vp, vp, vp, ci, vp]
+        self.L = L
+        self.h = L.encref_create(channel_size, channels_per_state, num_control_channels, num_prev_states)
+
+    @classmethod
+    def from_c_transformer(cls, ct):
+        e = cls(ct.channel_size, ct.channels_per_state, ct.num_control_channels, ct.num_prev_states)
+        for b, off in ct.board_bases:
+            e.L.encref_add_board_base(e.h, b, off)
+        for b, c, v in ct.control_bases:
+            e.L.encref_add_control_base(e.h, b, c, v)
+        return e
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            self.L.encref_destroy(self.h)
+            self.h = None
+
+    def total_size(self):
+        return self.L.encref_total_size(self.h)
+
+    def encode(self, states, prev=None, prev_count=None):
+        states = np.ascontiguousarray(states, dtype=np.uint32)
+        n, sw = states.shape
+        out = np.empty((n, self.total_size()), dtype=np.float32)
+        max_prev = 0
+        pp = pc = None
+        if prev is not None:
+            prev = np.ascontiguousarray(prev, dtype=np.uint32)
+            max_prev = prev.shape[1]
+            pp = prev.ctypes.data
+            if prev_count is None:
+                prev_count = np.full(n, max_prev, dtype=np.uint8)
+            prev_count = np.ascontiguousarray(prev_count, dtype=np.uint8)
+            pc = prev_count.ctypes.data
+        self.L.encref_batch(self.h, n, sw, states.ctypes.data, pp, pc, max_prev, out.ctypes.data)
+        return out

@@ -1,0 +1,115 @@
+"""Encoder parity. CPU: the C oracle (restatement of gdltransformer.cpp) agrees with the Python
+reference encoder restated from nn/bases.py:242-287 on golden-fixture states, and the plane shapes
+match the reference's shipped models. GPU: gz_encode is bit-exact with the oracle (f32 and bf16)."""
+import numpy as np
+import pytest
+
+from galvanise_zero_b200 import bases, cppinterface, lookup, tables
+from galvanise_zero_b200.defs import datadesc
+from oracle.pnref import RefEncoder, RefStateMachine
+
+GAMES = ['breakthrough', 'reversi', 'connect6', 'amazons_10x10', 'breakthroughSmall']
+SHAPES = {'breakthrough': (5, 8, 8), 'reversi': (5, 8, 8), 'connect6': (8, 19, 19),
+          'amazons_10x10': (12, 10, 10)}   # data/*/models/*.json batch_input_shape of the reference
+
+
+def _setup(game, num_prev=1):
+    gi = lookup.by_name(game)
+    tr = bases.GdlBasesTransformer(gi, datadesc.generation_for(game, num_previous_states=num_prev))
+    ct = cppinterface.create_c_transformer(tr)
+    return gi, tr, ct
+
+
+def _trajectory(game, n_games=6, plies=40, seed=11):
+    ref = RefStateMachine(tables.blob_by_name(game))
+    s = np.zeros((n_games, ref.state_words), dtype=np.uint32)
+    l = np.zeros((n_games, ref.legal_words), dtype=np.uint32)
+    t = np.ones(n_games, dtype=np.uint8)
+    g = np.zeros((n_games, ref.n_roles), dtype=np.uint8)
+    hist = []
+    for step in range(plies):
+        ref.playout_step(0, seed, step, s, l, t, g, None)
+        hist.append(s.copy())
+    return hist
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_oracle_encoder_matches_python_reference_encoder(game):
+    gi, tr, ct = _setup(game)
+    if game in SHAPES:
+        assert (tr.num_channels, tr.num_cols, tr.num_rows) == SHAPES[game]
+    assert ct.total_size() == tr.num_channels * tr.channel_size
+    enc = RefEncoder.from_c_transformer(ct)
+    hist = _trajectory(game)
+    nb = tr.num_bases
+    for k in range(0, len(hist), 3):
+        cur = hist[k]
+        prev = hist[k - 1] if k > 0 else None
+        if prev is not None:
+            got = enc.encode(cur, prev[:, None, :])
+        else:
+            got = enc.encode(cur)
+        for i in range(cur.shape[0]):
+            bits = tables.unpack_state_bits(cur[i], nb)
+            pbits = [tables.unpack_state_bits(prev[i], nb)] if prev is not None else []
+            want = tr.state_to_channels(bits, pbits).reshape(-1)
+            assert np.array_equal(got[i], want)
+
+
+def test_oracle_prev_state_quirk_all_prev_land_in_group_one():
+    """gdltransformer.cpp:39-43: `count` is never incremented."""
+    gi, tr, ct = _setup('breakthroughSmall', num_prev=2)
+    enc = RefEncoder.from_c_transformer(ct)
+    hist = _trajectory('breakthroughSmall', n_games=3, plies=10)
+    cur, p1, p2 = hist[9], hist[8], hist[7]
+    prev = np.stack([p1, p2], axis=1)
+    got = enc.encode(cur, prev)
+    gs = tr.raw_channels_per_state * tr.channel_size
+    one = enc.encode(p1)[:, :gs]
+    two = enc.encode(p2)[:, :gs]
+    assert np.array_equal(got[:, gs:2 * gs], np.maximum(one, two))
+    assert not got[:, 2 * gs:3 * gs].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('game', GAMES)
+def test_gpu_encoder_bit_exact(game):
+    import torch
+    gi, tr, ct = _setup(game)
+    ct.finalize(tr.num_bases, 0)
+    enc = RefEncoder.from_c_transformer(ct)
+    hist = _trajectory(game, n_games=37, plies=30)
+    dev = torch.device('cuda', 0)
+    for k in (0, 1, 14, 29):
+        cur = hist[k]
+        prev = hist[k - 1][:, None, :] if k > 0 else None
+        cnt = None
+        if prev is not None:
+            cnt = (np.arange(cur.shape[0]) % 2).astype(np.uint8)     # some roots have no parent
+        want = enc.encode(cur, prev, cnt)
+        d_cur = torch.from_numpy(cur.view(np.int32)).to(dev)
+        d_prev = torch.from_numpy(prev.view(np.int32).copy()).to(dev) if prev is not None else None
+        d_cnt = torch.from_numpy(cnt).to(dev) if cnt is not None else None
+        got32 = ct.encode(d_cur, d_prev, d_cnt, dtype=torch.float32).cpu().numpy()
+        assert np.array_equal(got32, want)
+        got16 = ct.encode(d_cur, d_prev, d_cnt, dtype=torch.bfloat16)
+        want16 = torch.from_numpy(want).to(torch.bfloat16)
+        assert torch.equal(got16.cpu(), want16)
+
+
+@pytest.mark.gpu
+def test_gpu_encoder_multi_prev_quirk_and_tail():
+    import torch
+    gi, tr, ct = _setup('breakthroughSmall', num_prev=2)
+    ct.finalize(tr.num_bases, 0)
+    enc = RefEncoder.from_c_transformer(ct)
+    hist = _trajectory('breakthroughSmall', n_games=13, plies=12)
+    cur = hist[11]
+    prev = np.stack([hist[10], hist[9]], axis=1)
+    cnt = (np.arange(13) % 3).astype(np.uint8)
+    want = enc.encode(cur, prev, cnt)
+    dev = torch.device('cuda', 0)
+    got = ct.encode(torch.from_numpy(cur.view(np.int32)).to(dev),
+                    torch.from_numpy(prev.view(np.int32).copy()).to(dev),
+                    torch.from_numpy(cnt).to(dev), dtype=torch.float32).cpu().numpy()
+    assert np.array_equal(got, want)
