@@ -1,0 +1,1497 @@
+// gz_puct_core.h — PUCT search + self-play control for ONE game tree, written as host/device code.
+//
+// The same source is compiled into the CUDA kernels of gz_puct.cu (one game per warp; lane 0 runs
+// the sequential control flow) and, for CPU-side validation only, into tests/hostsim (g++), where
+// it is driven against the reference's own C++ compiled in oracle/_ref.
+//
+// It re-states, batch-synchronously, what the reference does with one coroutine per game:
+//   PuctNode::create / createNode        src/cpp/puct/node.cpp:42-221, evaluator.cpp:165-214
+//   PuctNodeRequest::reply               src/cpp/puct/node.cpp:463-511
+//   selectChild / priorScore / setPuctConstant / setDirichletNoise
+//                                        src/cpp/puct/evaluator.cpp:341-517,1195-1307
+//   backup                               src/cpp/puct/evaluator.cpp:519-656
+//   treePlayout / playoutMain / onNextMove / converged
+//                                        src/cpp/puct/evaluator.cpp:658-886,1032-1098,1342-1362
+//   choose / chooseTopVisits / chooseTemperature / getProbabilities / getTemperature
+//                                        src/cpp/puct/evaluator.cpp:1100-1192,1309-1340,1473-1510
+//   fastApplyMove / resetRootNode / establishRoot     evaluator.cpp:888-1030
+//   SelfPlay::playOnce / collectSamples / runToEnd / resign / addSamples   src/cpp/selfplay.cpp:45-343
+//   SelfPlayManager::createSample, UniqueStates       selfplaymanager.cpp:72-119, uniquestates.h:12-79
+// Arithmetic types (float vs double, rounding points) follow the reference expression by
+// expression so that, with identical network outputs, visit counts are identical.
+//
+// Scope notes: one outstanding evaluation per tree (PuctConfig.batch_size == 1, the self-play
+// setting, templates.py:76); transposition lookup is not implemented (off in self-play,
+// confs.py:72-73); games in which two roles have a real choice in the same state are rejected.
+#ifndef GZ_PUCT_CORE_H
+#define GZ_PUCT_CORE_H
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define GZP_HD __host__ __device__ __forceinline__
+#define GZP_HDN __host__ __device__
+#else
+#define GZP_HD static inline
+#define GZP_HDN static inline
+#endif
+
+#define GZP_MAX_ROLES 4
+
+// ---- phases of the per-game controller
+enum {
+    PH_NEW_GAME = 0,
+    PH_COLLECT_NEXT = 1,   // top of SelfPlay::collectSamples loop
+    PH_SEARCH = 2,         // inside playoutMain
+    PH_MOVE_DONE = 3,      // search finished: choose, sample, apply
+    PH_AFTER_MOVE = 4,     // new root in place: post-move checks
+    PH_RUNTOEND_NEXT = 5,  // top of SelfPlay::runToEnd loop
+    PH_GAME_END = 6,
+    PH_IDLE = 7,           // (player mode) waiting for a command
+    PH_HALT = 8            // error
+};
+
+// ---- requests to the batch pipeline
+enum { REQ_NONE = 0, REQ_EXPAND = 1, REQ_ROOT = 2 };
+enum { PUR_PLAYOUT = 0, PUR_REROOT = 1, PUR_ROOT = 2 };
+
+// ---- node flags
+enum { NF_FINALISED = 1, NF_NOISE_SET = 2, NF_FORCE_TERMINAL = 4 };
+
+enum { GZP_ERR_NONE = 0, GZP_ERR_NODES = 1, GZP_ERR_CHILDREN = 2, GZP_ERR_PATH = 3, GZP_ERR_SIMULTANEOUS = 4,
+       GZP_ERR_SAMPLES = 5, GZP_ERR_ROOT_TERMINAL = 6 };
+
+struct PuctConf {
+    float puct_constant, puct_constant_root;
+    float dirichlet_noise_pct, noise_policy_squash_pct, noise_policy_squash_prob;
+    int choose;  // 0 top visits, 1 temperature
+    float random_scale, temperature;
+    int depth_temperature_start;
+    float depth_temperature_increment;
+    int depth_temperature_stop;
+    float depth_temperature_max;
+    float fpu_prior_discount, fpu_prior_discount_root;
+    float top_visits_best_guess_converge_ratio;
+    float think_time;
+    int converged_visits;
+    int batch_size;
+    int use_legals_count_draw;
+    int backup_finalised;
+    int lookup_transpositions;
+    float evaluation_multiplier_to_convergence;
+};
+
+struct SpConf {
+    float oscillate_sampling_pct, temperature_for_policy;
+    int evals_per_move;
+    float resign0_score_probability, resign0_pct, resign1_score_probability, resign1_pct;
+    float run_to_end_pct;
+    int run_to_end_evals;
+    float run_to_end_early_score;
+    int run_to_end_minimum_game_depth;
+    int abort_max_length;
+    PuctConf puct;
+    PuctConf run_to_end;
+};
+
+// ---- per-game controller record
+struct GameCtl {
+    int32_t phase, arena, root, n_nodes, n_children, game_depth;
+    uint64_t rng_eval[2], rng_sp[2];
+    int32_t conf_sel, max_evaluations, num_evaluations, num_tree_playouts, playouts_finals;
+    int32_t cur, path_len, in_playout;
+    int32_t req, req_parent, req_child, req_purpose;
+    int32_t eval_node, new_node, choice, resume;
+    // player-mode command mailbox (mode == 1)
+    int32_t cmd, cmd_arg, cmd_evals, cmd_done;
+    int32_t match_count, has_resigned, can_resign0, can_resign1, resign0_set, resign1_set;
+    float resign0_scores[GZP_MAX_ROLES], resign1_scores[GZP_MAX_ROLES];
+    int32_t n_samples, starting_sample_depth, do_sample, in_run_to_end, run_to_end_can_resign;
+    int32_t root_has_prev;
+    int32_t error;
+    int32_t mode;   // 0 self-play, 1 player (single search on command)
+    // counters (monotonic)
+    uint64_t total_evals, total_moves, total_games, total_samples, total_playouts;
+    // per-manager style stats (selfplaymanager.h:46-72)
+    int32_t saw_dupes, no_samples_taken, false_positive_resigns0, false_positive_resigns1,
+        number_early_run_to_ends, number_resigns, number_aborts_game_length;
+    int32_t pad;
+};
+
+// sample record header (int32 words), followed by state, prev state, policy pairs
+enum {
+    SR_READY = 0, SR_DEPTH, SR_GAME_LENGTH, SR_SLOT, SR_MATCH, SR_HAS_RESIGNED, SR_RESIGN_FP,
+    SR_START_DEPTH, SR_VISITS, SR_LEAD, SR_N_PREV, SR_N_CHILDREN,
+    SR_FINAL_SCORE = 12,      // float[4]
+    SR_PUCT_SCORE = 16,       // float[4]
+    SR_OTHER_MOVES = 20,      // int[4]: every role's action of child 0 (non-lead roles: their only move)
+    SR_HEADER = 24
+};
+
+struct PuctEngine {
+    int G, R, SW, LW, NCAP, CCAP, MAXD, n_rewards, max_actions;
+    int role_sizes[GZP_MAX_ROLES];
+    int legal_word_off[GZP_MAX_ROLES + 1];
+    int policy_off[GZP_MAX_ROLES];      // offset of role r's policy row inside a concatenated row
+    int policy_stride;                  // sum of role sizes
+    // node arrays, two arenas per game: index = (g*2 + arena)*NCAP + n
+    int32_t *n_parent, *n_child0, *n_nchild, *n_inflight, *n_flags, *n_lead, *n_depth;
+    uint32_t* n_visits;
+    float *n_score, *n_final;           // [.. * GZP_MAX_ROLES]
+    float* n_puct;
+    uint32_t* n_state;                  // [.. * SW]
+    int32_t* n_other;                   // [.. * GZP_MAX_ROLES] every role's only action (non-lead roles)
+    // child arrays: index = (g*2 + arena)*CCAP + c
+    int32_t *c_to, *c_move;
+    uint32_t* c_trav;
+    float *c_prob, *c_prob_orig, *c_next;
+    // per game
+    GameCtl* ctl;
+    int32_t *path_node, *path_choice;   // [G*MAXD]
+    uint32_t* root_prev_state;          // [G*SW] state of the root's parent (for samples)
+    // pipeline scratch, one row per game
+    uint32_t *x_in_state, *x_state, *x_legal;   // [G*SW], [G*SW], [G*LW]
+    int16_t* x_moves;                           // [G*R]   (-1 = identity / inactive)
+    uint8_t *x_term, *x_goals, *x_prevcnt;      // [G], [G*R], [G]
+    uint8_t* x_need_eval;                       // [G] 1 when the row of planes is a live request
+    int32_t* x_order;                           // [G*max_actions] child ordering scratch
+    float* x_noise;                             // [G*max_actions] dirichlet scratch
+    // network outputs, one row per game
+    const float* nn_policy;   // [G * policy_stride]  role rows concatenated
+    const float* nn_value;    // [G * n_rewards]
+    // samples
+    int32_t* pend;            // [G * MAXPEND * srec] per-game pending samples
+    int MAXPEND, srec;
+    int32_t* ready;           // [READYCAP * srec] finished samples
+    int READYCAP;
+    unsigned long long* ready_count;
+    // unique states: open-addressing table of 64-bit masked-state hashes with counters
+    unsigned long long* uniq_keys;
+    int32_t* uniq_counts;
+    int uniq_cap;             // power of two
+    const uint32_t* uniq_mask;  // [SW] createHashMask (gdltransformer.cpp:54-63)
+    const uint32_t* init_state; // [SW]
+    SpConf conf;
+    uint64_t seed;
+    int max_iters_per_step;
+};
+
+// ------------------------------------------------------------------------------------------------
+// RNG: xoroshiro128+ (32-bit output), same mapping as oracle/shims/k273/rng.h
+GZP_HD void gzp_rng_seed(uint64_t* st, uint64_t s) {
+    for (int i = 0; i < 2; i++) {
+        s += 0x9E3779B97F4A7C15ULL;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        st[i] = z ^ (z >> 31);
+    }
+}
+GZP_HD uint32_t gzp_rng_next(uint64_t* st) {
+    const uint64_t s0 = st[0];
+    uint64_t s1 = st[1];
+    const uint64_t r = s0 + s1;
+    s1 ^= s0;
+    st[0] = ((s0 << 55) | (s0 >> 9)) ^ s1 ^ (s1 << 14);
+    st[1] = (s1 << 36) | (s1 >> 28);
+    return (uint32_t)(r >> 32);
+}
+GZP_HD double gzp_rng_get(uint64_t* st) { return gzp_rng_next(st) * (1.0 / 4294967296.0); }
+GZP_HD uint32_t gzp_rng_with_max(uint64_t* st, uint32_t n) { return n ? gzp_rng_next(st) % n : 0; }
+
+
+// ------------------------------------------------------------------------------------------------
+// Child ordering. The reference orders children with std::sort and comparators that leave many
+// ties (and, in selectChild, are not even a strict weak order), so the visiting order under ties is
+// whatever libstdc++'s introsort produces. To reproduce the reference's choices exactly the same
+// algorithm is restated here (introsort: median-of-three to first, unguarded Hoare partition,
+// recursion on the right part, depth limit 2*floor(log2 n) with heap-sort fallback, then the final
+// insertion sort with threshold 16), operating on an array of child indices that starts in index
+// order exactly like the reference's push_back loop (evaluator.cpp:244-248, node.cpp:318-322).
+template <typename Cmp>
+GZP_HDN void gzp_unguarded_linear_insert(int* a, int last, Cmp& cmp) {
+    const int val = a[last];
+    int next = last - 1;
+    while (cmp(val, a[next])) { a[last] = a[next]; last = next; --next; }
+    a[last] = val;
+}
+template <typename Cmp>
+GZP_HDN void gzp_insertion_sort(int* a, int first, int last, Cmp& cmp) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (cmp(a[i], a[first])) {
+            const int val = a[i];
+            for (int k = i; k > first; --k) a[k] = a[k - 1];
+            a[first] = val;
+        } else {
+            gzp_unguarded_linear_insert(a, i, cmp);
+        }
+    }
+}
+template <typename Cmp>
+GZP_HDN void gzp_push_heap(int* a, int first, int hole, int top, int value, Cmp& cmp) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && cmp(a[first + parent], value)) {
+        a[first + hole] = a[first + parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    a[first + hole] = value;
+}
+template <typename Cmp>
+GZP_HDN void gzp_adjust_heap(int* a, int first, int hole, int len, int value, Cmp& cmp) {
+    const int top = hole;
+    int second = hole;
+    while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (cmp(a[first + second], a[first + (second - 1)])) second--;
+        a[first + hole] = a[first + second];
+        hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        a[first + hole] = a[first + (second - 1)];
+        hole = second - 1;
+    }
+    gzp_push_heap(a, first, hole, top, value, cmp);
+}
+template <typename Cmp>
+GZP_HDN void gzp_heap_sort(int* a, int first, int last, Cmp& cmp) {
+    const int len = last - first;
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            const int value = a[first + parent];
+            gzp_adjust_heap(a, first, parent, len, value, cmp);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    int l = last;
+    while (l - first > 1) {
+        --l;
+        const int value = a[l];
+        a[l] = a[first];
+        gzp_adjust_heap(a, first, 0, l - first, value, cmp);
+    }
+}
+template <typename Cmp>
+GZP_HDN void gzp_std_sort(int* a, int n, Cmp cmp) {
+    if (n <= 0) return;
+    // introsort loop, iterative: pending right-hand ranges on a small stack
+    int stack_first[64], stack_last[64], stack_depth[64];
+    int sp = 0;
+    int lg = 0;
+    for (int t = n; t > 1; t >>= 1) lg++;
+    stack_first[0] = 0; stack_last[0] = n; stack_depth[0] = 2 * lg; sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = stack_first[sp], last = stack_last[sp], depth = stack_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) { gzp_heap_sort(a, first, last, cmp); break; }
+            --depth;
+            // median of (first+1, mid, last-1) moved to first
+            const int mid = first + (last - first) / 2;
+            const int ia = first + 1, ib = mid, ic = last - 1;
+            int m;
+            if (cmp(a[ia], a[ib])) {
+                if (cmp(a[ib], a[ic])) m = ib;
+                else if (cmp(a[ia], a[ic])) m = ic;
+                else m = ia;
+            } else if (cmp(a[ia], a[ic])) m = ia;
+            else if (cmp(a[ib], a[ic])) m = ic;
+            else m = ib;
+            { const int t = a[first]; a[first] = a[m]; a[m] = t; }
+            // unguarded partition of [first+1, last) around a[first]
+            int lo = first + 1, hi = last;
+            while (true) {
+                while (cmp(a[lo], a[first])) ++lo;
+                --hi;
+                while (cmp(a[first], a[hi])) --hi;
+                if (!(lo < hi)) break;
+                const int t = a[lo]; a[lo] = a[hi]; a[hi] = t;
+                ++lo;
+            }
+            const int cut = lo;
+            if (sp < 64) { stack_first[sp] = cut; stack_last[sp] = last; stack_depth[sp] = depth; sp++; }
+            last = cut;
+        }
+    }
+    // final insertion sort
+    if (n > 16) {
+        gzp_insertion_sort(a, 0, 16, cmp);
+        for (int i = 16; i != n; ++i) gzp_unguarded_linear_insert(a, i, cmp);
+    } else {
+        gzp_insertion_sort(a, 0, n, cmp);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct GameView {
+    const PuctEngine* E;
+    int g;
+    GameCtl* c;
+    int64_t nb, cb;   // node / child base index of the active arena
+};
+
+GZP_HD GameView gzp_view(const PuctEngine* E, int g) {
+    GameView v;
+    v.E = E; v.g = g; v.c = &E->ctl[g];
+    v.nb = ((int64_t)g * 2 + v.c->arena) * E->NCAP;
+    v.cb = ((int64_t)g * 2 + v.c->arena) * E->CCAP;
+    return v;
+}
+
+#define NODE(field, n) (V.E->field[V.nb + (n)])
+#define CHILD(field, c) (V.E->field[V.cb + (c)])
+#define NSCORE(n, r) (V.E->n_score[(V.nb + (n)) * GZP_MAX_ROLES + (r)])
+#define NFINAL(n, r) (V.E->n_final[(V.nb + (n)) * GZP_MAX_ROLES + (r)])
+#define NOTHER(n, r) (V.E->n_other[(V.nb + (n)) * GZP_MAX_ROLES + (r)])
+#define NSTATE(n) (V.E->n_state + (V.nb + (n)) * V.E->SW)
+
+GZP_HD const PuctConf& gzp_conf(const GameView& V) { return V.c->conf_sel ? V.E->conf.run_to_end : V.E->conf.puct; }
+GZP_HD bool gzp_is_terminal(const GameView& V, int n) {
+    return (NODE(n_flags, n) & NF_FORCE_TERMINAL) || NODE(n_nchild, n) == 0;
+}
+GZP_HD bool gzp_is_finalised(const GameView& V, int n) { return (NODE(n_flags, n) & NF_FINALISED) != 0; }
+
+// ------------------------------------------------------------------------------------------------
+// Node creation from the propnet outputs of this game's scratch row (PuctNode::create + createNode).
+// Returns the node index or -1 (arena full -> error flagged).
+GZP_HDN int gzp_create_node(GameView& V, int parent, int depth) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    const int g = V.g;
+    const int R = E->R;
+    if (c->n_nodes >= E->NCAP) { c->error = GZP_ERR_NODES; return -1; }
+    const int n = c->n_nodes++;
+    const uint32_t* legal = E->x_legal + (int64_t)g * E->LW;
+    const bool terminal = E->x_term[g] != 0;
+    int lead = 0, total_children = 0;
+    int counts[GZP_MAX_ROLES];
+    if (!terminal) {
+        total_children = 1;
+        int max_moves = 1;
+        for (int r = 0; r < R; r++) {
+            int cnt = 0;
+            for (int w = E->legal_word_off[r]; w < E->legal_word_off[r + 1]; w++) {
+#ifdef __CUDA_ARCH__
+                cnt += __popc(legal[w]);
+#else
+                cnt += __builtin_popcount(legal[w]);
+#endif
+            }
+            counts[r] = cnt;
+            total_children *= cnt;
+            if (cnt > max_moves) { max_moves = cnt; lead = r; }
+        }
+        if (max_moves > 1) {
+            for (int r = 0; r < R; r++)
+                if (r != lead && counts[r] > 1) { c->error = GZP_ERR_SIMULTANEOUS; lead = -1; }
+        }
+        if (lead < 0) return -1;
+    }
+    NODE(n_parent, n) = parent;
+    NODE(n_visits, n) = 0;
+    NODE(n_inflight, n) = 0;
+    NODE(n_nchild, n) = total_children;
+    NODE(n_puct, n) = 1.44f;
+    NODE(n_flags, n) = terminal ? NF_FINALISED : 0;
+    NODE(n_lead, n) = lead;
+    NODE(n_depth, n) = depth;
+    NODE(n_child0, n) = -1;
+    for (int r = 0; r < GZP_MAX_ROLES; r++) { NSCORE(n, r) = 0.0f; NFINAL(n, r) = 0.0f; NOTHER(n, r) = 0; }
+    uint32_t* st = NSTATE(n);
+    const uint32_t* xs = E->x_state + (int64_t)g * E->SW;
+    for (int w = 0; w < E->SW; w++) st[w] = xs[w];
+    if (!terminal) {
+        if (c->n_children + total_children > E->CCAP) { c->error = GZP_ERR_CHILDREN; c->n_nodes--; return -1; }
+        const int c0 = c->n_children;
+        c->n_children += total_children;
+        NODE(n_child0, n) = c0;
+        // every role's first legal action (the only one for non-lead roles)
+        for (int r = 0; r < R; r++) {
+            int first = 0;
+            for (int w = E->legal_word_off[r]; w < E->legal_word_off[r + 1]; w++) {
+                if (legal[w]) {
+#ifdef __CUDA_ARCH__
+                    first = (w - E->legal_word_off[r]) * 32 + (__ffs(legal[w]) - 1);
+#else
+                    first = (w - E->legal_word_off[r]) * 32 + __builtin_ctz(legal[w]);
+#endif
+                    break;
+                }
+            }
+            NOTHER(n, r) = first;
+        }
+        // children = the lead role's legal actions in ascending index order
+        int k = 0;
+        for (int w = E->legal_word_off[lead]; w < E->legal_word_off[lead + 1]; w++) {
+            uint32_t x = legal[w];
+            while (x) {
+#ifdef __CUDA_ARCH__
+                const int b = __ffs(x) - 1;
+#else
+                const int b = __builtin_ctz(x);
+#endif
+                x &= x - 1;
+                const int ci = c0 + k++;
+                CHILD(c_to, ci) = -1;
+                CHILD(c_trav, ci) = 0;
+                CHILD(c_prob_orig, ci) = 1.0f;
+                CHILD(c_prob, ci) = 1.0f;
+                CHILD(c_next, ci) = 0.0f;
+                CHILD(c_move, ci) = (w - E->legal_word_off[lead]) * 32 + b;
+            }
+        }
+    } else {
+        for (int r = 0; r < R; r++) {
+            const int gv = E->x_goals[(int64_t)g * R + r];
+            const float s = (float)((gv == 255 ? 0 : gv) / 100.0);
+            NFINAL(n, r) = s;
+            float cs = s;
+            // terminal score sharpening (evaluator.cpp:188-198)
+            if (cs > 0.99) cs = (float)(cs * 1.05);
+            else if (cs < 0.01) cs = -0.05f;
+            NSCORE(n, r) = cs;
+        }
+    }
+    return n;
+}
+
+// PuctNodeRequest::reply (node.cpp:463-511) from this game's row of network outputs.
+GZP_HDN void gzp_reply(GameView& V, int n) {
+    const PuctEngine* E = V.E;
+    const int g = V.g;
+    const int lead = NODE(n_lead, n);
+    const int nc = NODE(n_nchild, n);
+    const int c0 = NODE(n_child0, n);
+    const float* pol = E->nn_policy + (int64_t)g * E->policy_stride + E->policy_off[lead];
+    float total = 0.0f;
+    for (int i = 0; i < nc; i++) {
+        float p = pol[CHILD(c_move, c0 + i)];
+        p = p > 0.001f ? p : 0.001f;          // std::max(0.001f, p)
+        CHILD(c_prob_orig, c0 + i) = p;
+        total += p;
+    }
+    for (int i = 0; i < nc; i++) {
+        const float p = CHILD(c_prob_orig, c0 + i) / total;
+        CHILD(c_prob_orig, c0 + i) = p;
+        CHILD(c_prob, c0 + i) = p;
+    }
+    const float* val = E->nn_value + (int64_t)g * E->n_rewards;
+    for (int r = 0; r < E->R; r++) {
+        float s = val[r];
+        if (E->n_rewards == 3) {
+            const float mid = val[2] / 2.0f;
+            s += mid;
+        }
+        if (s > 1.0) s = 1.0f;
+        else if (s < 0.0) s = 0.0f;
+        NFINAL(n, r) = s;
+        NSCORE(n, r) = s;   // clamp of an already clamped value
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// chooseTopVisits (evaluator.cpp:1100-1159). Sort key: traversals desc, then policy_prob desc
+// (node.cpp:346-373), ordered with the restated std::sort.
+GZP_HDN int gzp_choose_top_visits(const GameView& V, int n) {
+    const int nc = NODE(n_nchild, n);
+    const int c0 = NODE(n_child0, n);
+    const int role = NODE(n_lead, n);
+    const PuctConf& cf = gzp_conf(V);
+    int* order = V.E->x_order + (int64_t)V.g * V.E->max_actions;
+    for (int i = 0; i < nc; i++) order[i] = i;
+    const PuctEngine* E = V.E;
+    const int64_t cb = V.cb + c0;
+    gzp_std_sort(order, nc, [E, cb](int a, int b) {
+        const int ta = (int)E->c_trav[cb + a], tb = (int)E->c_trav[cb + b];
+        if (ta == tb) return E->c_prob[cb + a] > E->c_prob[cb + b];
+        return ta > tb;
+    });
+    int indx0 = -1, indx1 = -1;
+    int count = 0;
+    for (int k = 0; k < nc; k++) {
+        const int ci = order[k];
+        const int to = CHILD(c_to, c0 + ci);
+        if (to >= 0 && gzp_is_finalised(V, to)) {
+            const float sc = NSCORE(to, role);
+            if (sc > 0.99) return ci;
+            if (sc < 0.01) { count++; continue; }
+        }
+        if (indx0 == -1) indx0 = count;
+        else if (indx1 == -1) indx1 = count;
+        count++;
+    }
+    if (cf.top_visits_best_guess_converge_ratio > 0 && indx0 != -1 && indx1 != -1) {
+        const int i0 = order[indx0], i1 = order[indx1];
+        const int t0 = CHILD(c_to, c0 + i0), t1 = CHILD(c_to, c0 + i1);
+        if (t0 >= 0 && t1 >= 0) {
+            if ((float)CHILD(c_trav, c0 + i1) > (float)CHILD(c_trav, c0 + i0) * cf.top_visits_best_guess_converge_ratio &&
+                NSCORE(t1, role) > NSCORE(t0, role))
+                return i1;
+            return i0;
+        }
+    }
+    return order[0];
+}
+
+// priorScore (evaluator.cpp:1195-1224)
+GZP_HDN float gzp_prior_score(const GameView& V, int n, int depth) {
+    const PuctConf& cf = gzp_conf(V);
+    const int lead = NODE(n_lead, n);
+    float prior = NFINAL(n, lead);
+    if (NODE(n_visits, n) > 8) {
+        const int best = gzp_choose_top_visits(V, n);
+        const int to = CHILD(c_to, NODE(n_child0, n) + best);
+        if (to >= 0) prior = NSCORE(to, lead);
+    }
+    float fpu = depth == 0 ? cf.fpu_prior_discount_root : cf.fpu_prior_discount;
+    if (fpu > 0) {
+        float total = 0.0f;
+        const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+        for (int i = 0; i < nc; i++) {
+            const int to = CHILD(c_to, c0 + i);
+            if (to >= 0 && NODE(n_visits, to) > 0) total += CHILD(c_prob, c0 + i);
+        }
+        fpu *= sqrtf(total);
+        prior -= fpu;
+    }
+    return prior;
+}
+
+// Gamma(alpha, 1) sample, Marsaglia-Tsang; statistical (not bit-level) counterpart of the
+// reference's std::gamma_distribution<float> (evaluator.cpp:1249-1258).
+GZP_HDN float gzp_gamma(uint64_t* rng, float alpha) {
+    float boost = 1.0f;
+    if (alpha < 1.0f) {
+        double u = gzp_rng_get(rng);
+        if (u < 1e-12) u = 1e-12;
+        boost = (float)pow(u, 1.0 / alpha);
+        alpha += 1.0f;
+    }
+    const double d = alpha - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+    for (int it = 0; it < 64; it++) {
+        // normal via Box-Muller
+        double u1 = gzp_rng_get(rng), u2 = gzp_rng_get(rng);
+        if (u1 < 1e-12) u1 = 1e-12;
+        const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        double v = 1.0 + cc * x;
+        if (v <= 0) continue;
+        v = v * v * v;
+        double u = gzp_rng_get(rng);
+        if (u < 1e-12) u = 1e-12;
+        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return (float)(d * v) * boost;
+    }
+    return (float)d * boost;
+}
+
+// setDirichletNoise (evaluator.cpp:1227-1297)
+GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n, float* scratch /* >= nchild floats */) {
+    const PuctConf& cf = gzp_conf(V);
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+    if ((NODE(n_flags, n) & NF_NOISE_SET) || nc < 2 || cf.dirichlet_noise_pct < 0) return;
+    if (NSCORE(n, NODE(n_lead, n)) > 0.95) return;
+    const float alpha = 10.83f / nc;
+    float total_noise = 0.0f;
+    for (int i = 0; i < nc; i++) {
+        const float x = gzp_gamma(V.c->rng_eval, alpha);
+        scratch[i] = x;
+        total_noise += x;
+    }
+    if (total_noise < 1.17549435e-38f) return;
+    for (int i = 0; i < nc; i++) scratch[i] /= total_noise;
+    const bool squash = cf.noise_policy_squash_pct > 0 && gzp_rng_get(V.c->rng_eval) < cf.noise_policy_squash_pct;
+    float total_policy = 0;
+    const float pct = cf.dirichlet_noise_pct;
+    for (int i = 0; i < nc; i++) {
+        float p = CHILD(c_prob, c0 + i);
+        if (squash) p = cf.noise_policy_squash_prob < p ? cf.noise_policy_squash_prob : p;
+        p = (1.0f - pct) * p + pct * scratch[i];
+        CHILD(c_prob, c0 + i) = p;
+        total_policy += p;
+    }
+    for (int i = 0; i < nc; i++) CHILD(c_prob, c0 + i) /= total_policy;
+    NODE(n_flags, n) |= NF_NOISE_SET;
+}
+
+// selectChild (evaluator.cpp:341-517). Appends to the path; returns the child index within the
+// node (or -1 when nothing is selectable, which cannot happen with one evaluation in flight).
+GZP_HDN int gzp_select_child(GameView& V, int n, float* scratch_unused) {
+    float* scratch = V.E->x_noise + (int64_t)V.g * V.E->max_actions;
+    (void)scratch_unused;
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    const PuctConf& cf = gzp_conf(V);
+    const int depth = c->path_len;
+    if (c->path_len >= E->MAXD) { c->error = GZP_ERR_PATH; return -1; }
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+    const int lead = NODE(n_lead, n);
+    int32_t* pn = E->path_node + (int64_t)V.g * E->MAXD;
+    int32_t* pc = E->path_choice + (int64_t)V.g * E->MAXD;
+
+    // setPuctConstant (evaluator.cpp:1300-1307)
+    {
+        const float base = 19652.0f;
+        const float k = depth == 0 ? cf.puct_constant_root : cf.puct_constant;
+        float pcst = logf(((float)(1u + NODE(n_visits, n)) + base) / base);
+        pcst += k;
+        NODE(n_puct, n) = pcst;
+    }
+    if (nc == 1) {
+        pn[c->path_len] = n; pc[c->path_len] = 0; c->path_len++;
+        return 0;
+    }
+    if (depth == 0) gzp_set_dirichlet_noise(V, n, scratch);
+
+    const float prior_score = gzp_prior_score(V, n, depth);
+    const double sqrt_node_visits = sqrt((double)(NODE(n_visits, n) + 1u));
+    const float puct_c = NODE(n_puct, n);
+    const uint32_t node_visits = NODE(n_visits, n);
+
+    float best_score = -1;
+    int best_child = -1;
+    float best_child_score_actual = -1;
+    int best_child_score = -1;
+    int bad_fallback = -1;
+    float best_fallback_score = -1;
+    int best_fallback = -1;
+
+    // iterate children in sortedChildrenSelect order (evaluator.cpp:242-263): key sa = node score
+    // for the lead role (-1 when unexpanded); both negative -> policy_prob_orig desc, else sa desc.
+    int* order = E->x_order + (int64_t)V.g * E->max_actions;
+    for (int i = 0; i < nc; i++) order[i] = i;
+    {
+        const int64_t cb = V.cb + c0;
+        const int64_t nb = V.nb;
+        gzp_std_sort(order, nc, [E, cb, nb, lead](int a, int b) {
+            const int ta = E->c_to[cb + a], tb = E->c_to[cb + b];
+            const float sa = ta < 0 ? -1.0f : E->n_score[(nb + ta) * GZP_MAX_ROLES + lead];
+            const float sb = tb < 0 ? -1.0f : E->n_score[(nb + tb) * GZP_MAX_ROLES + lead];
+            if (sa < 0 && sb < 0) return E->c_prob_orig[cb + a] > E->c_prob_orig[cb + b];
+            return sa > sb;
+        });
+    }
+    for (int rank = 0; rank < nc; rank++) {
+        const int pick = order[rank];
+        const int ci = c0 + pick;
+        const int to = CHILD(c_to, ci);
+        double child_score = prior_score;
+        const int traversals = (int)CHILD(c_trav, ci) + 1;
+        const double inflight = to >= 0 ? (double)NODE(n_inflight, to) : 0.0;
+        double exploration = (double)(puct_c * CHILD(c_prob, ci)) * sqrt_node_visits / (traversals + inflight);
+        if (to >= 0) {
+            child_score = NSCORE(to, lead);
+            const bool fin = gzp_is_finalised(V, to);
+            if (fin) {
+                if (child_score > 0.99) {
+                    if (depth > 0) {
+                        pn[c->path_len] = n; pc[c->path_len] = pick; c->path_len++;
+                        return pick;
+                    }
+                    child_score *= 1.0f + puct_c;
+                } else if (child_score < 0.01) {
+                    bad_fallback = pick;
+                    continue;
+                } else {
+                    exploration = 0.0;
+                }
+            }
+            if ((fin || NODE(n_visits, to) > 42) && child_score > best_child_score_actual) {
+                best_child_score_actual = (float)child_score;
+                best_child_score = pick;
+            }
+        }
+        if (CHILD(c_trav, ci) > 0 && inflight > 0) {
+            const double discounted = inflight * (gzp_rng_get(c->rng_eval) + 0.5);
+            child_score = (child_score * CHILD(c_trav, ci)) / (CHILD(c_trav, ci) + discounted);
+        }
+        const float limit_latch_root = 0.66f;
+        const double score = child_score + exploration;
+        if (node_visits > 1000 && node_visits < 40000000 && depth == 0 && gzp_rng_get(c->rng_eval) > 0.1) {
+            if (CHILD(c_trav, ci) > 16 && CHILD(c_trav, ci) > node_visits * limit_latch_root) {
+                if (best_fallback < 0 || score > best_fallback_score) {
+                    best_fallback = pick;
+                    best_fallback_score = (float)score;
+                }
+                continue;
+            }
+        }
+        if (score > best_score) {
+            best_child = pick;
+            best_score = (float)score;
+        }
+    }
+    if (best_child < 0) {
+        if (best_fallback >= 0) best_child = best_child_score >= 0 ? best_child_score : best_fallback;
+        else if (bad_fallback >= 0) best_child = bad_fallback;
+    }
+    if (best_child >= 0) {
+        pn[c->path_len] = n; pc[c->path_len] = best_child; c->path_len++;
+    }
+    return best_child;
+}
+
+// backup (evaluator.cpp:519-656)
+GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    const PuctConf& cf = gzp_conf(V);
+    const int R = E->R;
+    const int32_t* pn = E->path_node + (int64_t)V.g * E->MAXD;
+    const int32_t* pc = E->path_choice + (int64_t)V.g * E->MAXD;
+    bool bp_finalised_only_once = cf.backup_finalised != 0;
+    for (int index = c->path_len - 1; index >= 0; index--) {
+        const int n = pn[index];
+        const int choice = pc[index];
+        const int lead = NODE(n_lead, n);
+        if (bp_finalised_only_once && !gzp_is_finalised(V, n) && lead >= 0) {
+            bp_finalised_only_once = false;
+            // forceFinalise
+            float best_s = -1;
+            int best = -1, win = -1;
+            bool more = false;
+            const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+            for (int i = 0; i < nc; i++) {
+                const int to = CHILD(c_to, c0 + i);
+                if (to >= 0 && gzp_is_finalised(V, to)) {
+                    const float s = NSCORE(to, lead);
+                    if (s > 0.99) { win = i; break; }
+                    if (s > best_s) { best_s = s; best = i; }
+                } else {
+                    more = true;
+                }
+            }
+            const int fc = win >= 0 ? win : (more ? -1 : best);
+            if (fc >= 0) {
+                const int to = CHILD(c_to, c0 + fc);
+                for (int r = 0; r < R; r++) NSCORE(n, r) = NSCORE(to, r);
+                NODE(n_flags, n) |= NF_FINALISED;
+            }
+        }
+        if (gzp_is_finalised(V, n)) {
+            for (int r = 0; r < R; r++) new_scores[r] = NSCORE(n, r);
+        } else {
+            for (int r = 0; r < R; r++) {
+                float visits = (float)NODE(n_visits, n);
+                if (visits > 100000) visits = 100000 + 0.1f * (visits - 100000);
+                const float score = (visits * NSCORE(n, r) + new_scores[r]) / (visits + 1.0f);
+                NSCORE(n, r) = score;
+            }
+        }
+        NODE(n_visits, n) = NODE(n_visits, n) + 1;
+        if (NODE(n_inflight, n) > 0) NODE(n_inflight, n) = NODE(n_inflight, n) - 1;
+        if (choice >= 0) {
+            const int ci = NODE(n_child0, n) + choice;
+            CHILD(c_trav, ci) = CHILD(c_trav, ci) + 1;
+            if (NODE(n_visits, n) > 23) {
+                const float cur_score = NSCORE(n, lead);
+                float apply, mn;
+                if (cur_score > 0.3 && cur_score < 0.7) { apply = 0.995f; mn = 0.02f; }
+                else if (cur_score > 0.15 && cur_score < 0.85) { apply = 0.9975f; mn = 0.03f; }
+                else { apply = 0.9975f; mn = 0.10f; }
+                float p = CHILD(c_prob, ci);
+                if (p > mn) {
+                    p *= apply;
+                    p = mn > p ? mn : p;
+                    CHILD(c_prob, ci) = p;
+                }
+            }
+        }
+        if (NODE(n_visits, n) % 100 == 0) {
+            // normaliseX (node.h:192-214)
+            const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+            float total = 0;
+            for (int i = 0; i < nc; i++) total += CHILD(c_prob, c0 + i);
+            if (total > 1.17549435e-38f) {
+                for (int i = 0; i < nc; i++) CHILD(c_prob, c0 + i) /= total;
+            } else {
+                for (int i = 0; i < nc; i++) CHILD(c_prob, c0 + i) = (float)(1.0 / nc);
+            }
+        }
+    }
+}
+
+// converged (evaluator.cpp:1342-1362); sortedChildren = by visits of the child node desc, ties by
+// policy_prob desc (node.cpp:312-343), unexpanded children count as 0 visits.
+GZP_HDN bool gzp_converged(const GameView& V, int count) {
+    const int n = V.c->root;
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+    if (nc < 2) return true;
+    const PuctEngine* E = V.E;
+    int* order = E->x_order + (int64_t)V.g * E->max_actions;
+    for (int i = 0; i < nc; i++) order[i] = i;
+    const int64_t cb = V.cb + c0, nb = V.nb;
+    gzp_std_sort(order, nc, [E, cb, nb](int a, int b) {
+        const int ta = E->c_to[cb + a], tb = E->c_to[cb + b];
+        const int va = ta < 0 ? 0 : (int)E->n_visits[nb + ta];
+        const int vb = tb < 0 ? 0 : (int)E->n_visits[nb + tb];
+        if (va == vb) return E->c_prob[cb + a] > E->c_prob[cb + b];
+        return va > vb;
+    });
+    const int n0 = CHILD(c_to, c0 + order[0]), n1 = CHILD(c_to, c0 + order[1]);
+    if (n0 >= 0 && n1 >= 0) {
+        const int role = NODE(n_lead, n);
+        if (NSCORE(n0, role) > NSCORE(n1, role) && NODE(n_visits, n0) > NODE(n_visits, n1) + (uint32_t)count) return true;
+    }
+    return false;
+}
+
+// getTemperature (evaluator.cpp:1309-1322)
+GZP_HD float gzp_temperature(const PuctConf& cf, int depth) {
+    if (depth >= cf.depth_temperature_stop) return -1;
+    float mult = 1.0f + ((depth - cf.depth_temperature_start) * cf.depth_temperature_increment);
+    mult = mult > 1.0f ? mult : 1.0f;
+    const float t = cf.temperature * mult;
+    return t < cf.depth_temperature_max ? t : cf.depth_temperature_max;
+}
+
+// getProbabilities (evaluator.cpp:1161-1192): fills next_prob of every child.
+GZP_HDN void gzp_get_probabilities(GameView& V, int n, float temperature, bool use_policy) {
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+    const float node_visits = (float)(NODE(n_visits, n) + 0.001 * nc);
+    float total = 0.0f;
+    for (int i = 0; i < nc; i++) {
+        const float child_visits = CHILD(c_to, c0 + i) >= 0 ? (float)CHILD(c_trav, c0 + i) + 0.001f : 0.001f;
+        float np = use_policy ? CHILD(c_prob, c0 + i) + 0.001f : child_visits / node_visits;
+        np = (float)pow((double)np, (double)temperature);
+        CHILD(c_next, c0 + i) = np;
+        total += np;
+    }
+    for (int i = 0; i < nc; i++) CHILD(c_next, c0 + i) /= total;
+}
+
+// chooseTemperature (evaluator.cpp:1473-1510); iteration order = sortedChildren(.., next_prob).
+GZP_HDN int gzp_choose_temperature(GameView& V, int n) {
+    const PuctConf& cf = gzp_conf(V);
+    const float temperature = gzp_temperature(cf, NODE(n_depth, n));
+    if (temperature < 0) return gzp_choose_top_visits(V, n);
+    const int root = V.c->root;
+    gzp_get_probabilities(V, root, temperature, cf.dirichlet_noise_pct < 0 && NODE(n_visits, n) < 3);
+    const float expected = (float)(gzp_rng_get(V.c->rng_eval) * cf.random_scale);
+    const int nc = NODE(n_nchild, root), c0 = NODE(n_child0, root);
+    const PuctEngine* E = V.E;
+    int* order = E->x_order + (int64_t)V.g * E->max_actions;
+    for (int i = 0; i < nc; i++) order[i] = i;
+    const int64_t cb = V.cb + c0, nb = V.nb;
+    gzp_std_sort(order, nc, [E, cb, nb](int a, int b) {
+        const int ta = E->c_to[cb + a], tb = E->c_to[cb + b];
+        const int va = ta < 0 ? 0 : (int)E->n_visits[nb + ta];
+        const int vb = tb < 0 ? 0 : (int)E->n_visits[nb + tb];
+        if (va == vb) return E->c_next[cb + a] > E->c_next[cb + b];
+        return va > vb;
+    });
+    float seen = 0;
+    for (int k = 0; k < nc; k++) {
+        seen += CHILD(c_next, c0 + order[k]);
+        if (seen > expected) return order[k];
+    }
+    return order[nc - 1];
+}
+
+GZP_HDN int gzp_choose(GameView& V, int n) {
+    const PuctConf& cf = gzp_conf(V);
+    return cf.choose == 1 ? gzp_choose_temperature(V, n) : gzp_choose_top_visits(V, n);
+}
+
+// resetRootNode (evaluator.cpp:1019-1030)
+GZP_HDN void gzp_reset_root_node(GameView& V) {
+    const int n = V.c->root;
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+    for (int i = 0; i < nc; i++) {
+        CHILD(c_prob, c0 + i) = CHILD(c_prob_orig, c0 + i);
+        if (CHILD(c_trav, c0 + i) > 1u) CHILD(c_trav, c0 + i) = 1u;
+    }
+    NODE(n_flags, n) &= ~NF_NOISE_SET;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unique states (uniquestates.h): masked 64-bit hash -> saturating counter
+GZP_HDN uint64_t gzp_state_hash(const PuctEngine* E, const uint32_t* st) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (int w = 0; w < E->SW; w++) {
+        const uint64_t x = st[w] & E->uniq_mask[w];
+        h ^= x + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
+    }
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ULL; h ^= h >> 32;
+    return h ? h : 1;
+}
+
+GZP_HDN int gzp_uniq_find(const PuctEngine* E, uint64_t key, bool insert) {
+    if (!E->uniq_cap) return -1;
+    uint32_t pos = (uint32_t)(key & (uint64_t)(E->uniq_cap - 1));
+    for (int probe = 0; probe < 64; probe++) {
+        unsigned long long cur = E->uniq_keys[pos];
+        if (cur == key) return (int)pos;
+        if (cur == 0ULL) {
+            if (!insert) return -1;
+#ifdef __CUDA_ARCH__
+            const unsigned long long prev = atomicCAS(&E->uniq_keys[pos], 0ULL, (unsigned long long)key);
+            if (prev == 0ULL || prev == key) return (int)pos;
+#else
+            E->uniq_keys[pos] = key;
+            return (int)pos;
+#endif
+        }
+        pos = (pos + 1) & (uint32_t)(E->uniq_cap - 1);
+    }
+    return -1;
+}
+
+GZP_HDN bool gzp_is_unique(const PuctEngine* E, const uint32_t* st, int depth) {
+    const int pos = gzp_uniq_find(E, gzp_state_hash(E, st), false);
+    if (pos < 0) return true;
+    const int max_num_dupes = 1000;
+    int allowed = max_num_dupes - 5 * depth;
+    if (allowed < 2) allowed = 2;
+    return E->uniq_counts[pos] < allowed;
+}
+
+GZP_HDN void gzp_uniq_add(const PuctEngine* E, const uint32_t* st) {
+    const int pos = gzp_uniq_find(E, gzp_state_hash(E, st), true);
+    if (pos < 0) return;
+#ifdef __CUDA_ARCH__
+    if (E->uniq_counts[pos] < 1000) atomicAdd(&E->uniq_counts[pos], 1);
+#else
+    if (E->uniq_counts[pos] < 1000) E->uniq_counts[pos]++;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// SelfPlayManager::createSample (selfplaymanager.cpp:72-119) into the game's pending list.
+GZP_HDN void gzp_create_sample(GameView& V, int n) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    if (c->n_samples >= E->MAXPEND) { c->error = GZP_ERR_SAMPLES; return; }
+    int32_t* rec = E->pend + ((int64_t)V.g * E->MAXPEND + c->n_samples) * E->srec;
+    c->n_samples++;
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+    const int lead = NODE(n_lead, n);
+    rec[SR_READY] = 0;
+    rec[SR_DEPTH] = NODE(n_depth, n);
+    rec[SR_SLOT] = V.g;
+    rec[SR_VISITS] = (int32_t)NODE(n_visits, n);
+    rec[SR_LEAD] = lead;
+    rec[SR_N_PREV] = c->root_has_prev ? 1 : 0;
+    rec[SR_N_CHILDREN] = nc;
+    float* fr = reinterpret_cast<float*>(rec);
+    for (int r = 0; r < GZP_MAX_ROLES; r++) {
+        fr[SR_PUCT_SCORE + r] = r < E->R ? NSCORE(n, r) : 0.0f;
+        rec[SR_OTHER_MOVES + r] = r < E->R ? NOTHER(n, r) : 0;
+    }
+    int32_t* p = rec + SR_HEADER;
+    const uint32_t* st = NSTATE(n);
+    for (int w = 0; w < E->SW; w++) p[w] = (int32_t)st[w];
+    p += E->SW;
+    const uint32_t* ps = E->root_prev_state + (int64_t)V.g * E->SW;
+    for (int w = 0; w < E->SW; w++) p[w] = c->root_has_prev ? (int32_t)ps[w] : 0;
+    p += E->SW;
+    for (int i = 0; i < nc; i++) {
+        p[2 * i] = CHILD(c_move, c0 + i);
+        reinterpret_cast<float*>(p)[2 * i + 1] = CHILD(c_next, c0 + i);
+    }
+}
+
+// SelfPlay::addSamples (selfplay.cpp:244-288): stamp the game's samples and publish them.
+GZP_HDN void gzp_add_samples(GameView& V, const float* final_scores, int game_depth) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    bool fp0 = false, fp1 = false;
+    for (int r = 0; r < E->R; r++) {
+        const float fs = final_scores[r];
+        if (c->has_resigned) {
+            if (!fp0 && c->resign0_set) {
+                const float s = c->resign0_scores[r];
+                if ((s < E->conf.resign0_score_probability * 1.05) && fs > 0.49) { fp0 = true; c->false_positive_resigns0++; }
+            }
+            if (!fp1 && c->resign1_set) {
+                const float s = c->resign1_scores[r];
+                if ((s < E->conf.resign1_score_probability * 1.05) && fs > 0.49) { fp1 = true; c->false_positive_resigns1++; }
+            }
+        }
+    }
+    for (int k = 0; k < c->n_samples; k++) {
+        int32_t* rec = E->pend + ((int64_t)V.g * E->MAXPEND + k) * E->srec;
+        float* fr = reinterpret_cast<float*>(rec);
+        for (int r = 0; r < GZP_MAX_ROLES; r++) fr[SR_FINAL_SCORE + r] = r < E->R ? final_scores[r] : 0.0f;
+        rec[SR_GAME_LENGTH] = game_depth;
+        rec[SR_MATCH] = c->match_count;
+        rec[SR_HAS_RESIGNED] = c->has_resigned;
+        rec[SR_RESIGN_FP] = (fp0 || fp1) ? 1 : 0;
+        rec[SR_START_DEPTH] = c->starting_sample_depth;
+        rec[SR_READY] = 1;
+#ifdef __CUDA_ARCH__
+        const unsigned long long slot = atomicAdd(E->ready_count, 1ULL);
+#else
+        const unsigned long long slot = (*E->ready_count)++;
+#endif
+        if (slot < (unsigned long long)E->READYCAP) {
+            int32_t* dst = E->ready + (int64_t)slot * E->srec;
+            for (int w = 0; w < E->srec; w++) dst[w] = rec[w];
+        }
+        c->total_samples++;
+    }
+    c->n_samples = 0;
+}
+
+// SelfPlay::resign (selfplay.cpp:45-74)
+GZP_HDN bool gzp_resign(GameView& V, int n) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    const float score = NSCORE(n, NODE(n_lead, n));
+    if (c->can_resign0 && score < E->conf.resign0_score_probability) {
+        c->has_resigned = 1;
+        c->resign0_set = 1;
+        for (int r = 0; r < E->R; r++) c->resign0_scores[r] = NSCORE(n, r);
+    } else if (c->can_resign1 && score < E->conf.resign1_score_probability) {
+        c->has_resigned = 1;
+        c->resign1_set = 1;
+        for (int r = 0; r < E->R; r++) c->resign1_scores[r] = NSCORE(n, r);
+    }
+    return c->has_resigned != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Re-rooting: copy the subtree under `new_root` into the other arena in BFS order (replaces
+// fastApplyMove's ref-count release of the sibling subtrees, evaluator.cpp:888-943).
+GZP_HDN void gzp_reroot(GameView& V, int new_root) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    const int64_t onb = V.nb, ocb = V.cb;
+    const int na = c->arena ^ 1;
+    const int64_t nnb = ((int64_t)V.g * 2 + na) * E->NCAP;
+    const int64_t ncb = ((int64_t)V.g * 2 + na) * E->CCAP;
+    // keep the state of the old root for sample prev_states
+    {
+        const int old_root = c->root;
+        uint32_t* ps = E->root_prev_state + (int64_t)V.g * E->SW;
+        const uint32_t* st = E->n_state + (onb + old_root) * E->SW;
+        for (int w = 0; w < E->SW; w++) ps[w] = st[w];
+        c->root_has_prev = 1;
+    }
+    // the BFS queue is the new node array itself; n_parent of a copied node temporarily holds its
+    // OLD index (in n_child0's slot we keep the old child0 until its children are processed).
+    int tail = 0, ctail = 0;
+    auto copy_node = [&](int old_n, int new_parent) {
+        const int nn = tail++;
+        E->n_parent[nnb + nn] = new_parent;
+        E->n_child0[nnb + nn] = E->n_child0[onb + old_n];   // old index for now
+        E->n_nchild[nnb + nn] = E->n_nchild[onb + old_n];
+        E->n_visits[nnb + nn] = E->n_visits[onb + old_n];
+        E->n_inflight[nnb + nn] = E->n_inflight[onb + old_n];
+        E->n_flags[nnb + nn] = E->n_flags[onb + old_n];
+        E->n_lead[nnb + nn] = E->n_lead[onb + old_n];
+        E->n_depth[nnb + nn] = E->n_depth[onb + old_n];
+        E->n_puct[nnb + nn] = E->n_puct[onb + old_n];
+        for (int r = 0; r < GZP_MAX_ROLES; r++) {
+            E->n_score[(nnb + nn) * GZP_MAX_ROLES + r] = E->n_score[(onb + old_n) * GZP_MAX_ROLES + r];
+            E->n_final[(nnb + nn) * GZP_MAX_ROLES + r] = E->n_final[(onb + old_n) * GZP_MAX_ROLES + r];
+            E->n_other[(nnb + nn) * GZP_MAX_ROLES + r] = E->n_other[(onb + old_n) * GZP_MAX_ROLES + r];
+        }
+        const uint32_t* s = E->n_state + (onb + old_n) * E->SW;
+        uint32_t* d = E->n_state + (nnb + nn) * E->SW;
+        for (int w = 0; w < E->SW; w++) d[w] = s[w];
+        return nn;
+    };
+    copy_node(new_root, -1);
+    for (int head = 0; head < tail; head++) {
+        const int nc = E->n_nchild[nnb + head];
+        if (nc == 0) { E->n_child0[nnb + head] = -1; continue; }
+        const int oc0 = E->n_child0[nnb + head];
+        const int nc0 = ctail;
+        ctail += nc;
+        E->n_child0[nnb + head] = nc0;
+        for (int i = 0; i < nc; i++) {
+            const int64_t o = ocb + oc0 + i, d = ncb + nc0 + i;
+            E->c_trav[d] = E->c_trav[o];
+            E->c_prob[d] = E->c_prob[o];
+            E->c_prob_orig[d] = E->c_prob_orig[o];
+            E->c_next[d] = E->c_next[o];
+            E->c_move[d] = E->c_move[o];
+            const int to = E->c_to[o];
+            E->c_to[d] = to >= 0 ? copy_node(to, head) : -1;
+        }
+    }
+    c->arena = na;
+    c->root = 0;
+    c->n_nodes = tail;
+    c->n_children = ctail;
+    c->game_depth++;
+    V.nb = nnb;
+    V.cb = ncb;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Controller: the reference's coroutine per game (SelfPlay::playGamesForever -> playOnce ->
+// collectSamples / runToEnd -> PuctEvaluator::onNextMove -> playoutMain -> treePlayout), turned
+// into a resumable state machine. gzp_step_pre runs until the game needs the batch pipeline
+// (a propnet transition and possibly a network evaluation); gzp_step_post consumes the propnet
+// outputs and creates the node.
+enum { CMD_NONE = 0, CMD_RESET = 1, CMD_APPLY = 2, CMD_SEARCH = 3 };
+
+GZP_HDN void gzp_request_expand(GameView& V, int parent, int child, int purpose) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    c->req = REQ_EXPAND;
+    c->req_parent = parent;
+    c->req_child = child;
+    c->req_purpose = purpose;
+    uint32_t* xin = E->x_in_state + (int64_t)V.g * E->SW;
+    const uint32_t* st = NSTATE(parent);
+    for (int w = 0; w < E->SW; w++) xin[w] = st[w];
+    const int lead = NODE(n_lead, parent);
+    const int ci = NODE(n_child0, parent) + child;
+    for (int r = 0; r < E->R; r++)
+        E->x_moves[(int64_t)V.g * E->R + r] = (int16_t)(r == lead ? CHILD(c_move, ci) : NOTHER(parent, r));
+}
+
+GZP_HDN void gzp_request_root(GameView& V, const uint32_t* state) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    c->req = REQ_ROOT;
+    c->req_parent = -1;
+    c->req_child = -1;
+    c->req_purpose = PUR_ROOT;
+    uint32_t* xin = E->x_in_state + (int64_t)V.g * E->SW;
+    for (int w = 0; w < E->SW; w++) xin[w] = state[w];
+    for (int r = 0; r < E->R; r++) E->x_moves[(int64_t)V.g * E->R + r] = -1;   // identity transition
+}
+
+GZP_HDN void gzp_finish_playout(GameView& V, int leaf) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    float scores[GZP_MAX_ROLES];
+    if (gzp_is_finalised(V, leaf)) c->playouts_finals++;
+    for (int r = 0; r < E->R; r++) scores[r] = NSCORE(leaf, r);
+    gzp_backup(V, scores);
+    c->num_tree_playouts++;
+    c->total_playouts++;
+    c->in_playout = 0;
+}
+
+GZP_HDN void gzp_path_push(GameView& V, int n, int choice) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    if (c->path_len >= E->MAXD) { c->error = GZP_ERR_PATH; return; }
+    E->path_node[(int64_t)V.g * E->MAXD + c->path_len] = n;
+    E->path_choice[(int64_t)V.g * E->MAXD + c->path_len] = choice;
+    c->path_len++;
+}
+
+// treePlayout (evaluator.cpp:658-720), resumable. Returns true when blocked on an expansion.
+GZP_HDN bool gzp_playout_continue(GameView& V, float* scratch) {
+    GameCtl* c = V.c;
+    while (true) {
+        const int cur = c->cur;
+        if (gzp_is_terminal(V, cur) || gzp_is_finalised(V, cur)) {
+            gzp_path_push(V, cur, -1);
+            gzp_finish_playout(V, cur);
+            return false;
+        }
+        const int child = gzp_select_child(V, cur, scratch);
+        if (child < 0 || c->error) { c->error = c->error ? c->error : GZP_ERR_PATH; return true; }
+        const int ci = NODE(n_child0, cur) + child;
+        if (CHILD(c_to, ci) < 0) {
+            gzp_request_expand(V, cur, child, PUR_PLAYOUT);
+            return true;
+        }
+        NODE(n_inflight, cur) = NODE(n_inflight, cur) + 1;
+        c->cur = CHILD(c_to, ci);
+    }
+}
+
+GZP_HDN void gzp_start_search(GameView& V, int evals, int conf_sel) {
+    GameCtl* c = V.c;
+    c->conf_sel = conf_sel;
+    c->max_evaluations = evals;
+    c->num_evaluations = 0;
+    c->num_tree_playouts = 0;
+    c->playouts_finals = 0;
+    c->in_playout = 0;
+    c->phase = PH_SEARCH;
+}
+
+GZP_HDN void gzp_begin_game(GameView& V) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    c->match_count++;
+    c->n_samples = 0;
+    c->has_resigned = 0;
+    const double r = gzp_rng_get(c->rng_sp);
+    c->can_resign0 = r > E->conf.resign0_pct;
+    c->can_resign1 = r > E->conf.resign1_pct;
+    c->resign0_set = c->resign1_set = 0;
+    // PuctEvaluator::reset(0)
+    c->n_nodes = 0;
+    c->n_children = 0;
+    c->game_depth = 0;
+    c->root = -1;
+    c->root_has_prev = 0;
+    c->in_run_to_end = 0;
+    c->in_playout = 0;
+    c->conf_sel = 0;
+    gzp_request_root(V, E->init_state);
+}
+
+// Returns when the game is blocked on the pipeline (c->req != REQ_NONE or c->eval_node >= 0),
+// idle, halted, or the per-step iteration budget is spent.
+GZP_HDN void gzp_step_pre(GameView& V, float* scratch) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    if (c->phase == PH_HALT) return;
+    if (c->eval_node >= 0) {
+        gzp_reply(V, c->eval_node);
+        c->num_evaluations++;
+        c->total_evals++;
+        c->eval_node = -1;
+        c->resume = 1;
+    }
+    for (int iter = 0; iter < E->max_iters_per_step; iter++) {
+        if (c->error) { c->phase = PH_HALT; return; }
+        if (c->req != REQ_NONE) return;
+        if (c->resume) {
+            c->resume = 0;
+            const int N = c->new_node;
+            if (c->req_purpose == PUR_PLAYOUT) {
+                if (gzp_is_finalised(V, N) || NODE(n_nchild, N) > 1) {
+                    gzp_path_push(V, N, -1);
+                    gzp_finish_playout(V, N);
+                } else {
+                    NODE(n_inflight, N) = NODE(n_inflight, N) + 1;
+                    c->cur = N;
+                }
+            } else if (c->req_purpose == PUR_REROOT) {
+                gzp_reroot(V, N);
+                c->phase = PH_AFTER_MOVE;
+            } else {
+                c->root = N;
+                if (gzp_is_terminal(V, N)) { c->error = GZP_ERR_ROOT_TERMINAL; continue; }
+                if (c->mode == 0) {
+                    c->starting_sample_depth = NODE(n_depth, N);
+                    c->conf_sel = 0;
+                    c->phase = PH_COLLECT_NEXT;
+                } else {
+                    c->phase = PH_IDLE;
+                    c->cmd_done = 1;
+                }
+            }
+            continue;
+        }
+        switch (c->phase) {
+        case PH_NEW_GAME:
+            gzp_begin_game(V);
+            break;
+        case PH_COLLECT_NEXT: {
+            const int node = c->root;
+            c->conf_sel = 0;
+            bool stop = false;
+            if (E->conf.abort_max_length > 0 && NODE(n_depth, node) > E->conf.abort_max_length) stop = true;
+            if (!stop && gzp_is_terminal(V, node)) stop = true;
+            if (stop) { c->phase = PH_GAME_END; c->in_run_to_end = 0; break; }
+            bool do_skip = false;
+            if (!gzp_is_unique(E, NSTATE(node), NODE(n_depth, node))) {
+                c->saw_dupes++;
+                do_skip = true;
+            } else if (E->conf.oscillate_sampling_pct > 0 && gzp_rng_get(c->rng_sp) > E->conf.oscillate_sampling_pct) {
+                do_skip = true;
+            }
+            if (!do_skip) {
+                gzp_uniq_add(E, NSTATE(node));
+                gzp_reset_root_node(V);
+                c->do_sample = 1;
+                gzp_start_search(V, E->conf.evals_per_move, 0);
+            } else {
+                int skip_evals = (int)gzp_rng_with_max(c->rng_sp, (uint32_t)(E->conf.evals_per_move / 3 + 1));
+                if (skip_evals < 16) skip_evals = 16;
+                c->do_sample = 0;
+                gzp_start_search(V, skip_evals, 1);
+            }
+            break;
+        }
+        case PH_SEARCH: {
+            if (!c->in_playout) {
+                const PuctConf& cf = gzp_conf(V);
+                const int root = c->root;
+                const bool is_converged = gzp_converged(V, cf.converged_visits);
+                const int max_non_converged = (int)(c->max_evaluations * cf.evaluation_multiplier_to_convergence);
+                const int max_tree_playouts = 4 * max_non_converged;
+                bool brk = false;
+                if (gzp_is_finalised(V, root) && c->num_tree_playouts > 100) brk = true;
+                else if (is_converged && c->num_tree_playouts > max_tree_playouts) brk = true;
+                else if (c->n_nodes + 4 > E->NCAP || c->n_children + E->max_actions + 4 > E->CCAP) brk = true;  // arena nearly full ("max nodes")
+                else if (is_converged && c->num_evaluations > c->max_evaluations) brk = true;
+                else if (!is_converged && c->num_evaluations > max_non_converged) brk = true;
+                if (brk || c->max_evaluations == 0) { c->phase = PH_MOVE_DONE; break; }
+                c->cur = root;
+                c->path_len = 0;
+                c->in_playout = 1;
+            }
+            if (gzp_playout_continue(V, scratch)) return;
+            break;
+        }
+        case PH_MOVE_DONE: {
+            const int root = c->root;
+            const int choice = gzp_choose(V, root);
+            c->choice = choice;
+            if (c->mode == 1) {       // player: search result is ready, wait for apply
+                c->phase = PH_IDLE;
+                c->cmd_done = 1;
+                break;
+            }
+            if (!c->in_run_to_end) {
+                if (c->do_sample) {
+                    gzp_get_probabilities(V, root, E->conf.temperature_for_policy, false);
+                    gzp_create_sample(V, root);
+                } else {
+                    c->conf_sel = 0;
+                }
+            }
+            c->total_moves++;
+            const int ci = NODE(n_child0, root) + choice;
+            if (CHILD(c_to, ci) < 0) {
+                gzp_request_expand(V, root, choice, PUR_REROOT);
+                c->phase = PH_AFTER_MOVE;   // entered once the re-root completes
+                return;
+            }
+            gzp_reroot(V, CHILD(c_to, ci));
+            c->phase = PH_AFTER_MOVE;
+            break;
+        }
+        case PH_AFTER_MOVE: {
+            const int node = c->root;
+            if (!c->in_run_to_end) {
+                if (gzp_is_terminal(V, node)) { c->phase = PH_GAME_END; break; }
+                if (!c->has_resigned) gzp_resign(V, node);
+                if (c->has_resigned && c->n_samples > 1) {
+                    c->number_resigns++;
+                    c->phase = PH_GAME_END;
+                    break;
+                }
+                c->phase = PH_COLLECT_NEXT;
+            } else {
+                if (gzp_is_finalised(V, node)) { c->phase = PH_GAME_END; break; }
+                if (c->run_to_end_can_resign && NODE(n_depth, node) > E->conf.run_to_end_minimum_game_depth) {
+                    const int lead = NODE(n_lead, node);
+                    const float lead_score = NSCORE(node, lead);
+                    if (lead_score < E->conf.run_to_end_early_score) {
+                        c->number_early_run_to_ends++;
+                        float fs[GZP_MAX_ROLES];
+                        for (int r = 0; r < E->R; r++) fs[r] = (r == lead) ? 0.0f : 1.0f;
+                        gzp_add_samples(V, fs, NODE(n_depth, node));
+                        c->total_games++;
+                        c->phase = PH_NEW_GAME;
+                        break;
+                    }
+                }
+                c->phase = PH_RUNTOEND_NEXT;
+            }
+            break;
+        }
+        case PH_GAME_END: {
+            if (!c->in_run_to_end) {
+                // end of collectSamples: either nothing sampled, or switch to runToEnd
+                if (c->n_samples == 0) {
+                    c->no_samples_taken++;
+                    c->total_games++;
+                    c->phase = PH_NEW_GAME;
+                    break;
+                }
+                c->in_run_to_end = 1;
+                c->conf_sel = 1;
+                c->run_to_end_can_resign = (c->has_resigned && gzp_rng_get(c->rng_sp) > E->conf.run_to_end_pct) ? 1 : 0;
+                c->phase = PH_RUNTOEND_NEXT;
+                break;
+            }
+            // end of runToEnd
+            const int node = c->root;
+            if (E->conf.abort_max_length > 0 && NODE(n_depth, node) > E->conf.abort_max_length) {
+                c->number_aborts_game_length++;
+                c->n_samples = 0;
+            } else {
+                float fs[GZP_MAX_ROLES];
+                for (int r = 0; r < E->R; r++) fs[r] = NSCORE(node, r);
+                gzp_add_samples(V, fs, NODE(n_depth, node));
+            }
+            c->total_games++;
+            c->phase = PH_NEW_GAME;
+            break;
+        }
+        case PH_RUNTOEND_NEXT: {
+            const int node = c->root;
+            const bool done = (E->conf.abort_max_length > 0 && NODE(n_depth, node) > E->conf.abort_max_length) ||
+                              gzp_is_finalised(V, node);
+            if (done) { c->phase = PH_GAME_END; break; }
+            c->do_sample = 0;
+            gzp_start_search(V, E->conf.run_to_end_evals, 1);
+            break;
+        }
+        case PH_IDLE: {
+            if (c->cmd == CMD_NONE) return;
+            const int cmd = c->cmd;
+            c->cmd = CMD_NONE;
+            if (cmd == CMD_RESET) {
+                c->n_nodes = 0; c->n_children = 0; c->root = -1; c->root_has_prev = 0;
+                c->game_depth = c->cmd_arg;
+                c->in_run_to_end = 0; c->in_playout = 0; c->conf_sel = 0;
+                // root state was placed in x_in_state by the host
+                c->req = REQ_ROOT; c->req_parent = -1; c->req_child = -1; c->req_purpose = PUR_ROOT;
+                for (int r = 0; r < E->R; r++) E->x_moves[(int64_t)V.g * E->R + r] = -1;
+                return;
+            } else if (cmd == CMD_APPLY) {
+                // cmd_arg = lead-role action index of the move played
+                const int root = c->root;
+                int found = -1;
+                for (int i = 0; i < NODE(n_nchild, root); i++)
+                    if (CHILD(c_move, NODE(n_child0, root) + i) == c->cmd_arg) found = i;
+                if (found < 0) { c->cmd_done = -1; break; }
+                const int ci = NODE(n_child0, root) + found;
+                if (CHILD(c_to, ci) < 0) {
+                    gzp_request_expand(V, root, found, PUR_REROOT);
+                    c->phase = PH_AFTER_MOVE;
+                    return;
+                }
+                gzp_reroot(V, CHILD(c_to, ci));
+                c->cmd_done = 1;
+            } else if (cmd == CMD_SEARCH) {
+                gzp_start_search(V, c->cmd_evals, 0);
+            }
+            break;
+        }
+        default:
+            return;
+        }
+        if (c->mode == 1 && c->phase == PH_AFTER_MOVE && c->req == REQ_NONE) {
+            c->phase = PH_IDLE;
+            c->cmd_done = 1;
+        }
+    }
+}
+
+// After the propnet pass: build the requested node from the scratch row and decide whether the
+// network has to look at it.
+GZP_HDN void gzp_step_post(GameView& V) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    E->x_need_eval[V.g] = 0;
+    if (c->phase == PH_HALT || c->req == REQ_NONE) return;
+    const int parent = c->req == REQ_ROOT ? -1 : c->req_parent;
+    const int depth = parent < 0 ? c->game_depth : NODE(n_depth, parent) + 1;
+    const int N = gzp_create_node(V, parent, depth);
+    c->req = REQ_NONE;
+    if (N < 0) { c->phase = PH_HALT; return; }
+    if (parent >= 0) CHILD(c_to, NODE(n_child0, parent) + c->req_child) = N;
+    c->new_node = N;
+    const bool needs_eval = !gzp_is_finalised(V, N) && NODE(n_nchild, N) > 1;
+    if (needs_eval) {
+        c->eval_node = N;
+        E->x_need_eval[V.g] = 1;
+        E->x_prevcnt[V.g] = parent >= 0 ? 1 : (c->root_has_prev ? 1 : 0);
+    } else {
+        c->resume = 1;
+    }
+}
+
+#endif  // GZ_PUCT_CORE_H

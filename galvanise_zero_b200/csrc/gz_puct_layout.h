@@ -1,0 +1,71 @@
+// Memory layout of a PuctEngine: one arena, every array 256-byte aligned. Used by gz_puct.cu
+// (cudaMalloc'd arena) and by the CPU validation build in tests/hostsim (malloc'd arena).
+#ifndef GZ_PUCT_LAYOUT_H
+#define GZ_PUCT_LAYOUT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gz_puct_core.h"
+
+// Assigns all array pointers of E inside [base, base+return). With base == nullptr only the size
+// is computed. Dimensions (G, R, SW, LW, NCAP, CCAP, MAXD, MAXPEND, srec, READYCAP, uniq_cap,
+// n_rewards, policy_stride) must be set beforehand.
+static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
+    size_t pos = 0;
+    auto take = [&](size_t bytes) -> uint8_t* {
+        uint8_t* p = base ? base + pos : nullptr;
+        pos += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    const size_t NN = (size_t)E->G * 2 * E->NCAP;
+    const size_t CC = (size_t)E->G * 2 * E->CCAP;
+    const size_t G = (size_t)E->G;
+    E->n_parent = (int32_t*)take(NN * 4);
+    E->n_child0 = (int32_t*)take(NN * 4);
+    E->n_nchild = (int32_t*)take(NN * 4);
+    E->n_inflight = (int32_t*)take(NN * 4);
+    E->n_flags = (int32_t*)take(NN * 4);
+    E->n_lead = (int32_t*)take(NN * 4);
+    E->n_depth = (int32_t*)take(NN * 4);
+    E->n_visits = (uint32_t*)take(NN * 4);
+    E->n_score = (float*)take(NN * 4 * GZP_MAX_ROLES);
+    E->n_final = (float*)take(NN * 4 * GZP_MAX_ROLES);
+    E->n_puct = (float*)take(NN * 4);
+    E->n_state = (uint32_t*)take(NN * 4 * E->SW);
+    E->n_other = (int32_t*)take(NN * 4 * GZP_MAX_ROLES);
+    E->c_to = (int32_t*)take(CC * 4);
+    E->c_move = (int32_t*)take(CC * 4);
+    E->c_trav = (uint32_t*)take(CC * 4);
+    E->c_prob = (float*)take(CC * 4);
+    E->c_prob_orig = (float*)take(CC * 4);
+    E->c_next = (float*)take(CC * 4);
+    E->ctl = (GameCtl*)take(G * sizeof(GameCtl));
+    E->path_node = (int32_t*)take(G * E->MAXD * 4);
+    E->path_choice = (int32_t*)take(G * E->MAXD * 4);
+    E->root_prev_state = (uint32_t*)take(G * E->SW * 4);
+    E->x_in_state = (uint32_t*)take(G * E->SW * 4);
+    E->x_state = (uint32_t*)take(G * E->SW * 4);
+    E->x_legal = (uint32_t*)take(G * E->LW * 4);
+    E->x_moves = (int16_t*)take(G * E->R * 2);
+    E->x_term = (uint8_t*)take(G);
+    E->x_goals = (uint8_t*)take(G * E->R);
+    E->x_prevcnt = (uint8_t*)take(G);
+    E->x_need_eval = (uint8_t*)take(G);
+    E->x_order = (int32_t*)take(G * (size_t)E->max_actions * 4);
+    E->x_noise = (float*)take(G * (size_t)E->max_actions * 4);
+    E->pend = (int32_t*)take(G * E->MAXPEND * (size_t)E->srec * 4);
+    E->ready = (int32_t*)take((size_t)E->READYCAP * E->srec * 4);
+    E->ready_count = (unsigned long long*)take(8);
+    E->uniq_keys = (unsigned long long*)take((size_t)E->uniq_cap * 8);
+    E->uniq_counts = (int32_t*)take((size_t)E->uniq_cap * 4);
+    E->uniq_mask = (const uint32_t*)take((size_t)E->SW * 4);
+    E->init_state = (const uint32_t*)take((size_t)E->SW * 4);
+    return pos;
+}
+
+static inline int gzp_sample_record_words(int SW, int max_actions) {
+    return SR_HEADER + 2 * SW + 2 * max_actions;
+}
+
+#endif

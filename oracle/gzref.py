@@ -1,0 +1,139 @@
+"""ORACLE (test infrastructure): ctypes binding of oracle/_ref/libgzref.so — the reference's own
+PUCT / scheduler / self-play C++ compiled unmodified against shims (oracle/Makefile `ref`).
+Only tests/, smoke() and bench.py's CPU-baseline legs may import this."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, '_ref', 'libgzref.so')
+REF_SRC = '/root/reference/src/cpp'
+
+PUCT_FIELDS = ['puct_constant', 'puct_constant_root', 'dirichlet_noise_pct', 'noise_policy_squash_pct',
+               'noise_policy_squash_prob', 'choose', 'random_scale', 'temperature',
+               'depth_temperature_start', 'depth_temperature_increment', 'depth_temperature_stop',
+               'depth_temperature_max', 'fpu_prior_discount', 'fpu_prior_discount_root',
+               'top_visits_best_guess_converge_ratio', 'think_time', 'converged_visits', 'batch_size',
+               'use_legals_count_draw', 'backup_finalised', 'lookup_transpositions',
+               'evaluation_multiplier_to_convergence']
+SP_FIELDS = ['oscillate_sampling_pct', 'temperature_for_policy', 'evals_per_move',
+             'resign0_score_probability', 'resign0_pct', 'resign1_score_probability', 'resign1_pct',
+             'run_to_end_pct', 'run_to_end_evals', 'run_to_end_early_score',
+             'run_to_end_minimum_game_depth', 'abort_max_length']
+
+
+def available():
+    return os.path.exists(LIB) or os.path.isdir(REF_SRC)
+
+
+def build():
+    """Builds oracle/_ref/libgzref.so when the reference sources are present (build container)."""
+    if os.path.isdir(REF_SRC):
+        subprocess.check_call(['make', '-s', '-C', HERE, 'ref'])
+    return os.path.exists(LIB)
+
+
+_L = None
+
+
+def lib():
+    global _L
+    if _L is None:
+        if not os.path.exists(LIB):
+            if not build():
+                raise RuntimeError('oracle/_ref/libgzref.so is missing and /root/reference is absent')
+        L = ctypes.CDLL(LIB)
+        vp, ci, dp = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double)
+        L.gzref_create.restype = vp
+        L.gzref_create.argtypes = [vp, ctypes.c_int64, ci, ci, ci, ci, ci, vp, ci]
+        L.gzref_destroy.argtypes = [vp]
+        L.gzref_add_board_base.argtypes = [vp, ci, ci]
+        L.gzref_add_control_base.argtypes = [vp, ci, ci, ctypes.c_float]
+        L.gzref_seed.argtypes = [ctypes.c_uint64]
+        L.gzref_search.argtypes = [vp, dp, vp, ci, ci, ctypes.c_uint64, ci, vp, vp, vp, vp, vp, vp, vp]
+        L.gzref_selfplay.argtypes = [vp, dp, dp, dp, ci, ci, ctypes.c_uint64, ctypes.c_int64,
+                                     ctypes.c_double, dp, vp, ctypes.c_int64, ci]
+        _L = L
+    return _L
+
+
+def puct_conf_array(conf):
+    d = conf if isinstance(conf, dict) else __import__('attr').asdict(conf)
+    vals = []
+    for f in PUCT_FIELDS:
+        v = d[f]
+        if f == 'choose':
+            v = 1.0 if v == 'choose_temperature' else 0.0
+        vals.append(float(v))
+    return (ctypes.c_double * len(vals))(*vals)
+
+
+def sp_conf_array(conf):
+    d = conf if isinstance(conf, dict) else __import__('attr').asdict(conf)
+    return (ctypes.c_double * len(SP_FIELDS))(*[float(d[f]) for f in SP_FIELDS])
+
+
+class RefEngine:
+    def __init__(self, blob, c_transformer):
+        """blob: tables.blob_by_name(game); c_transformer: interface.GdlBasesTransformer (tables)."""
+        self.L = lib()
+        self.blob = np.ascontiguousarray(blob, dtype=np.int32)
+        ct = c_transformer
+        ps = (ctypes.c_int * len(ct.policy_sizes))(*ct.policy_sizes)
+        self.h = self.L.gzref_create(self.blob.ctypes.data, len(self.blob), ct.channel_size,
+                                     ct.channels_per_state, ct.num_control_channels,
+                                     ct.num_prev_states, ct.num_rewards, ps, len(ct.policy_sizes))
+        assert self.h
+        for b, off in ct.board_bases:
+            self.L.gzref_add_board_base(self.h, b, off)
+        for b, c, v in ct.control_bases:
+            self.L.gzref_add_control_base(self.h, b, c, v)
+
+    def search(self, puct_conf, evals, n_moves=1, root_state=None, nn_seed=1, max_children=512,
+               rng_seed=0x5EED0000):
+        self.L.gzref_seed(rng_seed)
+        counts = np.zeros(n_moves, dtype=np.int32)
+        move = np.full((n_moves, max_children), -1, dtype=np.int32)
+        trav = np.zeros((n_moves, max_children), dtype=np.int32)
+        prob = np.zeros((n_moves, max_children), dtype=np.float32)
+        score = np.zeros((n_moves, max_children), dtype=np.float32)
+        choice = np.zeros(n_moves, dtype=np.int32)
+        root = np.zeros((n_moves, 4), dtype=np.float32)
+        rs = None
+        if root_state is not None:
+            rs = np.ascontiguousarray(root_state, dtype=np.uint32)
+        n = self.L.gzref_search(self.h, puct_conf_array(puct_conf), rs.ctypes.data if rs is not None else None,
+                                evals, n_moves, nn_seed, max_children, counts.ctypes.data,
+                                move.ctypes.data, trav.ctypes.data, prob.ctypes.data,
+                                score.ctypes.data, choice.ctypes.data, root.ctypes.data)
+        out = []
+        for m in range(n):
+            k = int(counts[m])
+            out.append({'moves': move[m, :k].copy(), 'traversals': trav[m, :k].copy(),
+                        'policy_prob': prob[m, :k].copy(), 'scores': score[m, :k].copy(),
+                        'choice': int(choice[m]), 'root_visits': int(root[m, 0]),
+                        'lead_role': int(root[m, 1]), 'root_score': float(root[m, 2]),
+                        'nodes': int(root[m, 3])})
+        return out
+
+    def selfplay(self, sp_conf, batch_size, num_workers, nn_seed=1, target_samples=0,
+                 max_seconds=10.0, rng_seed=0x5EED0000, sample_capacity=0, srec=0):
+        """Runs the reference Supervisor. With sample_capacity > 0 also returns the samples as an
+        int32 array [n, srec] in the record layout of csrc/gz_puct_core.h (SR_*)."""
+        self.L.gzref_seed(rng_seed)
+        import attr
+        d = sp_conf if isinstance(sp_conf, dict) else attr.asdict(sp_conf)
+        stats = (ctypes.c_double * 8)()
+        buf = np.zeros((max(sample_capacity, 1), max(srec, 1)), dtype=np.int32)
+        self.L.gzref_selfplay(self.h, sp_conf_array(d), puct_conf_array(d['puct_config']),
+                              puct_conf_array(d['run_to_end_puct_config']), batch_size, num_workers,
+                              nn_seed, target_samples, max_seconds, stats,
+                              buf.ctypes.data if sample_capacity else None, sample_capacity, srec)
+        keys = ['samples', 'evaluations', 'polls', 'seconds', 'depth_sum', 'sampled_moves', 'games',
+                'plies']
+        res = dict(zip(keys, [float(x) for x in stats]))
+        if sample_capacity:
+            res['records'] = buf[:min(int(res['samples']), sample_capacity)]
+        return res
