@@ -14,8 +14,9 @@ three programs over one slot space:
 
 * ``V``   — cone of legal / terminal / goal outputs (depends on bases only),
 * ``T``   — cone of the next-state outputs (depends on bases and inputs),
-* ``TV``  — ``T`` minus the gates already evaluated by ``V`` (used by the fused playout kernel,
-            where ``V`` has just been run on the same state).
+* ``TV``  — ``T`` minus the gates already evaluated by ``V``;
+* ``LT`` / ``GL`` — ``V`` split into the legal+terminal cone and the remaining goal-only gates;
+* ``TL``  — ``T`` minus ``LT`` (next-state cone when only ``LT`` is known to be current).
 
 One soundness assumption is used while optimising: **exactly one input per role is true** — which
 holds by construction, because moves cross the C-ABI as one action index per role.
@@ -388,7 +389,8 @@ def _make_programs(pn: Propnet):
     inLT = set(LT.tolist())
     G = _cone(pn, g_roots)
     GL = np.array([i for i in G.tolist() if i not in inLT], dtype=np.int32)
-    pn.prog = {'V': V, 'T': T, 'TV': TV, 'LT': LT, 'GL': GL}
+    TL = np.array([i for i in T.tolist() if i not in inLT], dtype=np.int32)
+    pn.prog = {'V': V, 'T': T, 'TV': TV, 'LT': LT, 'GL': GL, 'TL': TL}
 
 
 # --------------------------------------------------------------------------------------------
@@ -455,4 +457,7 @@ def load_propnet(path: str) -> Propnet:
     pn.goal_values = [z['goal_values_%d' % r] for r in range(nr)]
     pn.goal_lit = [z['goal_lit_%d' % r] for r in range(nr)]
     pn.prog = {k[5:]: z[k] for k in z.files if k.startswith('prog_')}
+    if 'TL' not in pn.prog:
+        in_lt = set(pn.prog['LT'].tolist())
+        pn.prog['TL'] = np.array([i for i in pn.prog['T'].tolist() if i not in in_lt], dtype=np.int32)
     return pn

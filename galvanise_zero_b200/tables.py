@@ -17,14 +17,14 @@ GAMES_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'games')
 
 # header indices (mirror include/gz_propnet_format.h)
 MAGIC = 0x475A504E
-VERSION = 2
+VERSION = 3
 HEADER_WORDS = 48
 (H_MAGIC, H_VERSION, H_N_BASES, H_N_ROLES, H_N_SLOTS, H_N_GATES, H_TERMINAL_LIT, H_STATE_WORDS,
  H_LEGAL_WORDS, H_N_INPUTS, H_TOTAL_WORDS, H_OFF_ROLE_SIZES, H_OFF_GATE_OUT, H_OFF_LIT_OFF,
  H_OFF_LIT_DATA, H_OFF_NEXT_LIT, H_OFF_LEGAL_OFF, H_OFF_LEGAL_LIT, H_OFF_GOAL_OFF, H_OFF_GOAL_VAL,
  H_OFF_GOAL_LIT, H_OFF_INIT, H_OFF_PROG_V, H_LEN_PROG_V, H_OFF_PROG_T, H_LEN_PROG_T,
  H_OFF_PROG_TV, H_LEN_PROG_TV, H_OFF_PROG_LT, H_LEN_PROG_LT, H_OFF_PROG_GL, H_LEN_PROG_GL,
- H_OFF_LEGAL_WORD_OFF) = range(33)
+ H_OFF_LEGAL_WORD_OFF, H_OFF_PROG_TL, H_LEN_PROG_TL) = range(35)
 
 
 def available_games():
@@ -112,6 +112,7 @@ def pack_blob(pn: Propnet) -> np.ndarray:
     add(pn.prog['LT'], H_OFF_PROG_LT, H_LEN_PROG_LT)
     add(pn.prog['GL'], H_OFF_PROG_GL, H_LEN_PROG_GL)
     add(lwo, H_OFF_LEGAL_WORD_OFF)
+    add(pn.prog['TL'], H_OFF_PROG_TL, H_LEN_PROG_TL)
     hdr[H_MAGIC] = MAGIC
     hdr[H_VERSION] = VERSION
     hdr[H_N_BASES] = pn.n_bases

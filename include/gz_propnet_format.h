@@ -23,7 +23,7 @@
 #include <stdint.h>
 
 #define GZ_PN_MAGIC 0x475A504E /* 'GZPN' */
-#define GZ_PN_VERSION 2
+#define GZ_PN_VERSION 3
 #define GZ_PN_HEADER_WORDS 48
 #define GZ_PN_MAX_ROLES 4
 
@@ -57,7 +57,8 @@ enum {
     GZ_H_OFF_PROG_TV = 26, GZ_H_LEN_PROG_TV = 27,
     GZ_H_OFF_PROG_LT = 28, GZ_H_LEN_PROG_LT = 29,
     GZ_H_OFF_PROG_GL = 30, GZ_H_LEN_PROG_GL = 31,
-    GZ_H_OFF_LEGAL_WORD_OFF = 32 /* [n_roles+1] word offset of each role inside a legal row */
+    GZ_H_OFF_LEGAL_WORD_OFF = 32, /* [n_roles+1] word offset of each role inside a legal row */
+    GZ_H_OFF_PROG_TL = 33, GZ_H_LEN_PROG_TL = 34   /* T minus LT */
 };
 
 /* Counter-based RNG shared bit-for-bit by the oracle and the CUDA playout kernels:

@@ -41,10 +41,11 @@ typedef struct pnref_sm {
     int n_bases, n_roles, n_slots, n_gates, state_words, legal_words, n_inputs;
     const int32_t *role_sizes, *next_lit, *legal_off, *legal_lit, *goal_off, *goal_val, *goal_lit,
         *init, *legal_word_off;
-    pnref_prog V, T, TV, LT, GL;
+    pnref_prog V, T, TV, LT, GL, TL;
     uint8_t* val;        /* [n_slots] */
     int32_t* legal_list; /* [n_inputs] ascending legal indices per role */
     int32_t legal_count[GZ_PN_MAX_ROLES];
+    int goals_valid; /* the goal cone (GL) is propagated lazily, on the first getGoalValue */
 } pnref_sm;
 
 static void build_prog(pnref_sm* sm, pnref_prog* p, int off_idx, int len_idx) {
@@ -121,6 +122,7 @@ pnref_sm* pnref_create(const int32_t* blob, int64_t n_words) {
     build_prog(sm, &sm->TV, GZ_H_OFF_PROG_TV, GZ_H_LEN_PROG_TV);
     build_prog(sm, &sm->LT, GZ_H_OFF_PROG_LT, GZ_H_LEN_PROG_LT);
     build_prog(sm, &sm->GL, GZ_H_OFF_PROG_GL, GZ_H_LEN_PROG_GL);
+    build_prog(sm, &sm->TL, GZ_H_OFF_PROG_TL, GZ_H_LEN_PROG_TL);
     sm->val = (uint8_t*)calloc(sm->n_slots + 8, 1);
     sm->val[0] = 1;
     sm->legal_list = (int32_t*)malloc(sizeof(int32_t) * (sm->n_inputs + 1));
@@ -129,7 +131,7 @@ pnref_sm* pnref_create(const int32_t* blob, int64_t n_words) {
 
 void pnref_destroy(pnref_sm* sm) {
     if (!sm) return;
-    free_prog(&sm->V); free_prog(&sm->T); free_prog(&sm->TV); free_prog(&sm->LT); free_prog(&sm->GL);
+    free_prog(&sm->V); free_prog(&sm->T); free_prog(&sm->TV); free_prog(&sm->LT); free_prog(&sm->GL); free_prog(&sm->TL);
     free(sm->val); free(sm->legal_list); free(sm->blob); free(sm);
 }
 
@@ -138,6 +140,7 @@ pnref_sm* pnref_dupe(const pnref_sm* sm) {
     memcpy(d->val, sm->val, sm->n_slots);
     memcpy(d->legal_list, sm->legal_list, sizeof(int32_t) * sm->n_inputs);
     memcpy(d->legal_count, sm->legal_count, sizeof(sm->legal_count));
+    d->goals_valid = sm->goals_valid;
     return d;
 }
 
@@ -157,7 +160,8 @@ static void load_bases(pnref_sm* sm, const uint32_t* state) {
 /* updateBases: load the base bits, propagate the views (legal / terminal / goal cone). */
 void pnref_update_bases(pnref_sm* sm, const uint32_t* state) {
     load_bases(sm, state);
-    run_prog(&sm->V, sm->val);
+    run_prog(&sm->LT, sm->val);
+    sm->goals_valid = 0;
     for (int r = 0; r < sm->n_roles; r++) {
         int32_t* list = sm->legal_list + sm->legal_off[r];
         int c = 0;
@@ -174,8 +178,12 @@ int pnref_legal(const pnref_sm* sm, int role, int i) {
 int pnref_is_terminal(const pnref_sm* sm) { return lit_val(sm->val, sm->h[GZ_H_TERMINAL_LIT]); }
 
 /* goal value of `role`: the largest value whose goal proposition holds; -1 when none does. */
-int pnref_goal(const pnref_sm* sm, int role) {
+int pnref_goal(pnref_sm* sm, int role) {
     int res = -1;
+    if (!sm->goals_valid) {
+        run_prog(&sm->GL, sm->val);
+        sm->goals_valid = 1;
+    }
     for (int k = sm->goal_off[role]; k < sm->goal_off[role + 1]; k++)
         if (lit_val(sm->val, sm->goal_lit[k])) res = sm->goal_val[k];
     return res;
@@ -190,7 +198,9 @@ void pnref_next_state(pnref_sm* sm, const int32_t* joint_move, uint32_t* out) {
         in[off + joint_move[r]] = 1;
         off += sm->role_sizes[r];
     }
-    run_prog(&sm->TV, sm->val); /* views of this state are already valid (updateBases ran V) */
+    /* only the legal/terminal cone is known to be current: run the rest of the next-state cone.
+       TL may overwrite goal-only gates it shares with GL with the same values. */
+    run_prog(&sm->TL, sm->val);
     memset(out, 0, sizeof(uint32_t) * sm->state_words);
     for (int b = 0; b < sm->n_bases; b++)
         if (lit_val(sm->val, sm->next_lit[b])) out[b >> 5] |= 1u << (b & 31);

@@ -68,6 +68,12 @@ class HostSim:
         assert L.hs_wait(self.h, g, 100000) == 1
         out = []
         for m in range(n_moves):
+            probe = np.zeros(8, dtype=np.float32)
+            tmp_i = np.zeros(max_children, dtype=np.int32)
+            tmp_f = np.zeros(max_children, dtype=np.float32)
+            if L.hs_root_children(self.h, g, max_children, tmp_i.ctypes.data, tmp_i.ctypes.data,
+                                  tmp_f.ctypes.data, tmp_f.ctypes.data, probe.ctypes.data) == 0:
+                break       # terminal root
             L.hs_cmd_search(self.h, g, evals)
             rc = L.hs_wait(self.h, g, 10000000)
             assert rc == 1, rc
