@@ -1324,6 +1324,10 @@ GZP_HDN void gzp_step_pre(GameView& V, float* scratch) {
                 else if (c->n_nodes + 4 > E->NCAP || c->n_children + E->max_actions + 4 > E->CCAP) brk = true;  // arena nearly full ("max nodes")
                 else if (is_converged && c->num_evaluations > c->max_evaluations) brk = true;
                 else if (!is_converged && c->num_evaluations > max_non_converged) brk = true;
+                // Deviation (documented in DESIGN.md): the reference loops forever when a search only
+                // reaches terminal / finalised nodes and the root never 'converges' (no evaluation is
+                // ever counted); a game slot must not be lost, so such a search stops here.
+                else if (c->num_tree_playouts > 4 * max_tree_playouts + 1000) brk = true;
                 if (brk || c->max_evaluations == 0) { c->phase = PH_MOVE_DONE; break; }
                 c->cur = root;
                 c->path_len = 0;

@@ -60,7 +60,7 @@ def test_backup_finalised_and_temperature_choice_match():
 
 
 @pytest.mark.parametrize('game,G,evals,target', [('breakthrough', 6, 60, 120), ('breakthroughSmall', 8, 40, 150),
-                                                 ('reversi', 3, 40, 30)])
+                                                 ('reversi', 4, 50, 60)])
 def test_selfplay_samples_match_reference_supervisor(game, G, evals, target):
     from hostsim_util import HostSim
     ct, eng = _setup(game)
