@@ -1327,7 +1327,7 @@ GZP_HDN void gzp_step_pre(GameView& V, float* scratch) {
                 // Deviation (documented in DESIGN.md): the reference loops forever when a search only
                 // reaches terminal / finalised nodes and the root never 'converges' (no evaluation is
                 // ever counted); a game slot must not be lost, so such a search stops here.
-                else if (c->num_tree_playouts > 4 * max_tree_playouts + 1000) brk = true;
+                else if (c->num_tree_playouts > 64 * max_tree_playouts + 10000) brk = true;
                 if (brk || c->max_evaluations == 0) { c->phase = PH_MOVE_DONE; break; }
                 c->cur = root;
                 c->path_len = 0;
