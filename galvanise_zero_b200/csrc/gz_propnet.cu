@@ -165,7 +165,7 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
         const int rows = (int)((n - g0) < 32 ? (n - g0) : 32);
         const bool valid = lane < rows;
         const uint32_t valid_mask = rows == 32 ? 0xffffffffu : ((1u << rows) - 1u);
-        uint32_t reset_mask = 0;
+        uint32_t reset_mask = 0, pass_mask = 0;
         int mv[GZ_PN_MAX_ROLES];
 
         if (MODE == MODE_PLAYOUT) {
@@ -202,6 +202,7 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
 #pragma unroll
             for (int r = 0; r < GZ_PN_MAX_ROLES; ++r)
                 mv[r] = (r < R && valid) ? (int)moves_in[game * R + r] : -1;
+            pass_mask = __ballot_sync(0xffffffffu, valid && mv[0] < 0);
         }
 
         // ---- load packed states, slice them into the base slots
@@ -228,6 +229,10 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
                 if (MODE == MODE_PLAYOUT) {
                     const uint32_t ib = (P.init_words[j] >> lane) & 1u;
                     t = (t & ~reset_mask) | (ib ? reset_mask : 0u);
+                } else {
+                    // games whose first move index is negative keep their state (identity): used by
+                    // the PUCT pipeline to evaluate a root without moving
+                    if (b < P.n_bases) t = (t & ~pass_mask) | (val[1 + b] & pass_mask);
                 }
                 t &= valid_mask;
                 slices[b] = t;
@@ -432,6 +437,8 @@ extern "C" void gz_propnet_destroy(gz_propnet* pn) {
     if (pn->host_stream) cudaStreamDestroy(pn->host_stream);
     delete pn;
 }
+
+extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn) { return pn ? pn->P.init_words : nullptr; }
 
 extern "C" int64_t gz_propnet_info(const gz_propnet* pn, int what) {
     if (!pn) return -1;

@@ -1,0 +1,471 @@
+// gz_puct.cu — batched PUCT self-play engine on the device.
+//
+// G independent game trees live in SoA node / child arenas in HBM (gz_puct_core.h, two arenas per
+// game for re-rooting). One engine step ("advance") is a fixed sequence of launches on one stream:
+//
+//   puct_pre_kernel    one warp per game: consume the network's answer (reply + backup), run the
+//                      self-play controller and select down the tree until the game needs a new node
+//   pn_kernel          (gz_propnet.cu) next state, legal masks, terminal, goals for every request
+//   puct_post_kernel   one warp per game: create the node (children from the legal mask)
+//   [repeat the three launches `sub_iters` times for games that did not need the network]
+//   encode_kernel      (gz_encoder.cu) bf16 NCHW planes for every game waiting for the network
+//
+// then the caller runs the policy/value network on the planes (a PyTorch module on the same stream;
+// nothing leaves the device) and hands the outputs to the next advance. The sequence has fixed
+// shapes and no host synchronisation, so it can be captured in a CUDA graph.
+//
+// Replaces: NetworkScheduler's greenlet batching (src/cpp/scheduler.cpp), SelfPlayManager /
+// SelfPlay / Supervisor (src/cpp/selfplaymanager.cpp, selfplay.cpp, supervisor.cpp) and the
+// PuctEvaluator they drive (src/cpp/puct/evaluator.cpp); the search semantics are restated in
+// gz_puct_core.h and are bit-exact with the reference's own C++ (tests/test_puct_hostsim.py on the
+// CPU build of the same source, tests/test_gpu_puct.py on the device).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/gz_b200.h"
+#include "../../include/gz_synth.h"
+#include "gz_common.cuh"
+#include "gz_puct_layout.h"
+#include "gz_transformer.h"
+
+extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn);   // gz_propnet.cu (device pointer)
+
+#define PUCT_WARPS_PER_BLOCK 4
+
+__global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32)
+puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh) {
+    const int g = blockIdx.x * PUCT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (g >= E.G || (threadIdx.x & 31) != 0) return;
+    GameView V = gzp_view(&E, g);
+    gzp_step_pre(V, nullptr, nn_fresh != 0);
+}
+
+__global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32)
+puct_post_kernel(const __grid_constant__ PuctEngine E) {
+    const int g = blockIdx.x * PUCT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (g >= E.G || (threadIdx.x & 31) != 0) return;
+    GameView V = gzp_view(&E, g);
+    gzp_step_post(V);
+}
+
+__global__ void puct_init_kernel(const __grid_constant__ PuctEngine E, int mode) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= E.G) return;
+    GameCtl& c = E.ctl[g];
+    c.mode = mode;
+    c.phase = mode == 0 ? PH_NEW_GAME : PH_IDLE;
+    c.eval_node = -1;
+    // evaluator stream then self-play stream, in game order: the construction order of the
+    // reference (selfplaymanager.cpp:133-149) under oracle/shims/k273/rng.h seeding
+    const uint64_t phi = 0x9E3779B97F4A7C15ULL;
+    gzp_rng_seed(c.rng_eval, E.seed + (uint64_t)(2 * g) * phi);
+    gzp_rng_seed(c.rng_sp, E.seed + (uint64_t)(2 * g + 1) * phi);
+}
+
+struct PuctTotals {
+    unsigned long long evals, moves, games, samples, playouts;
+    int errors, halted, first_error, max_nodes, max_children;
+    int dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts;
+    int waiting_eval;
+};
+
+__global__ void puct_totals_kernel(const __grid_constant__ PuctEngine E, PuctTotals* out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= E.G) return;
+    const GameCtl& c = E.ctl[g];
+    atomicAdd(&out->evals, (unsigned long long)c.total_evals);
+    atomicAdd(&out->moves, (unsigned long long)c.total_moves);
+    atomicAdd(&out->games, (unsigned long long)c.total_games);
+    atomicAdd(&out->samples, (unsigned long long)c.total_samples);
+    atomicAdd(&out->playouts, (unsigned long long)c.total_playouts);
+    if (c.error) { atomicAdd(&out->errors, 1); atomicMax(&out->first_error, c.error); }
+    if (c.phase == PH_HALT) atomicAdd(&out->halted, 1);
+    atomicMax(&out->max_nodes, c.n_nodes);
+    atomicMax(&out->max_children, c.n_children);
+    atomicAdd(&out->dupes, c.saw_dupes);
+    atomicAdd(&out->no_samples, c.no_samples_taken);
+    atomicAdd(&out->fp_resign0, c.false_positive_resigns0);
+    atomicAdd(&out->fp_resign1, c.false_positive_resigns1);
+    atomicAdd(&out->early_run_to_ends, c.number_early_run_to_ends);
+    atomicAdd(&out->resigns, c.number_resigns);
+    atomicAdd(&out->aborts, c.number_aborts_game_length);
+    if (c.eval_node >= 0) atomicAdd(&out->waiting_eval, 1);
+}
+
+// ---- synthetic network (parity / bench utility): same function as oracle/ref_harness.cpp
+template <typename T>
+__device__ __forceinline__ float synth_load(const T* p, int64_t i);
+template <>
+__device__ __forceinline__ float synth_load<float>(const float* p, int64_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float synth_load<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+
+template <typename T>
+__global__ void synth_nn_kernel(const T* __restrict__ planes, int64_t n, int total, uint64_t seed, int n_roles,
+                                const int* __restrict__ role_sizes_off /* [2*n_roles]: size, offset */,
+                                int policy_stride, int n_rewards, float* __restrict__ policy,
+                                float* __restrict__ value) {
+    // one warp per row
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    uint64_t h = 0;
+    for (int e = lane; e < total; e += 32) {
+        const float v = synth_load<T>(planes, row * total + e);
+        if (v != 0.0f) h += gz_synth_elem((uint32_t)e, __float_as_uint(v), seed);
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) h += __shfl_xor_sync(0xffffffffu, h, s);
+    for (int r = 0; r < n_roles; r++) {
+        const int sz = role_sizes_off[2 * r], off = role_sizes_off[2 * r + 1];
+        for (int a = lane; a < sz; a += 32)
+            policy[row * policy_stride + off + a] = gz_synth_policy(h, (uint32_t)r, (uint32_t)a);
+    }
+    if (lane == 0) {
+        float out[8];
+        gz_synth_values(h, n_rewards, out);
+        for (int i = 0; i < n_rewards; i++) value[row * n_rewards + i] = out[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct gz_puct {
+    int device = 0;
+    PuctEngine E{};
+    void* d_arena = nullptr;
+    size_t arena_bytes = 0;
+    gz_propnet* pn = nullptr;
+    gz_transformer* tr = nullptr;
+    PuctTotals* d_totals = nullptr;
+    int* d_role_sizes_off = nullptr;
+    int mode = 0;
+    int total_size = 0;
+};
+
+static void fill_puct_conf(PuctConf& p, const double* c) {
+    int i = 0;
+    p.puct_constant = (float)c[i++]; p.puct_constant_root = (float)c[i++];
+    p.dirichlet_noise_pct = (float)c[i++]; p.noise_policy_squash_pct = (float)c[i++];
+    p.noise_policy_squash_prob = (float)c[i++]; p.choose = c[i++] > 0.5 ? 1 : 0;
+    p.random_scale = (float)c[i++]; p.temperature = (float)c[i++];
+    p.depth_temperature_start = (int)c[i++]; p.depth_temperature_increment = (float)c[i++];
+    p.depth_temperature_stop = (int)c[i++]; p.depth_temperature_max = (float)c[i++];
+    p.fpu_prior_discount = (float)c[i++]; p.fpu_prior_discount_root = (float)c[i++];
+    p.top_visits_best_guess_converge_ratio = (float)c[i++]; p.think_time = (float)c[i++];
+    p.converged_visits = (int)c[i++]; p.batch_size = (int)c[i++]; p.use_legals_count_draw = (int)c[i++];
+    p.backup_finalised = c[i++] > 0.5; p.lookup_transpositions = c[i++] > 0.5;
+    p.evaluation_multiplier_to_convergence = (float)c[i++];
+}
+
+static void fill_sp_conf(SpConf& s, const double* c) {
+    int i = 0;
+    s.oscillate_sampling_pct = (float)c[i++]; s.temperature_for_policy = (float)c[i++];
+    s.evals_per_move = (int)c[i++]; s.resign0_score_probability = (float)c[i++]; s.resign0_pct = (float)c[i++];
+    s.resign1_score_probability = (float)c[i++]; s.resign1_pct = (float)c[i++]; s.run_to_end_pct = (float)c[i++];
+    s.run_to_end_evals = (int)c[i++]; s.run_to_end_early_score = (float)c[i++];
+    s.run_to_end_minimum_game_depth = (int)c[i++]; s.abort_max_length = (int)c[i++];
+}
+
+extern "C" int gz_puct_set_config(gz_puct* h, const double* sp_conf, const double* puct_conf, const double* rte_conf) {
+    if (!h || !sp_conf || !puct_conf || !rte_conf) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    fill_sp_conf(h->E.conf, sp_conf);
+    fill_puct_conf(h->E.conf.puct, puct_conf);
+    fill_puct_conf(h->E.conf.run_to_end, rte_conf);
+    if (h->E.conf.puct.lookup_transpositions || h->E.conf.run_to_end.lookup_transpositions) {
+        gz_set_error("lookup_transpositions is not supported by the device engine");
+        return GZ_ERR_LIMIT;
+    }
+    return GZ_OK;
+}
+
+extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, int mode, int node_cap,
+                              int child_cap, int max_pending_samples, int ready_cap, const double* sp_conf,
+                              const double* puct_conf, const double* rte_conf, uint64_t seed, gz_puct** out) {
+    if (!pn || !tr || !out || n_games <= 0 || node_cap < 16 || child_cap < 16) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
+    if (!tr->finalized) { gz_set_error("transformer must be finalised"); return GZ_ERR_ARG; }
+    *out = nullptr;
+    gz_puct* h = new gz_puct();
+    h->pn = pn;
+    h->tr = tr;
+    h->mode = mode;
+    h->device = tr->device;
+    PuctEngine& E = h->E;
+    E.G = n_games;
+    E.R = (int)gz_propnet_info(pn, GZ_INFO_N_ROLES);
+    E.SW = (int)gz_propnet_info(pn, GZ_INFO_STATE_WORDS);
+    E.LW = (int)gz_propnet_info(pn, GZ_INFO_LEGAL_WORDS);
+    E.NCAP = node_cap;
+    E.CCAP = child_cap;
+    E.MAXD = 512;
+    E.n_rewards = tr->num_rewards;
+    int off = 0, maxa = 0;
+    std::vector<int> rso;
+    for (int r = 0; r < E.R; r++) {
+        E.role_sizes[r] = (int)gz_propnet_info(pn, GZ_INFO_ROLE_SIZE0 + r);
+        E.policy_off[r] = off;
+        rso.push_back(E.role_sizes[r]);
+        rso.push_back(off);
+        off += E.role_sizes[r];
+        maxa = std::max(maxa, E.role_sizes[r]);
+    }
+    for (int r = 0; r <= E.R; r++) E.legal_word_off[r] = (int)gz_propnet_info(pn, GZ_INFO_LEGAL_WORD_OFF0 + r);
+    E.policy_stride = off;
+    E.max_actions = maxa;
+    E.MAXPEND = max_pending_samples > 0 ? max_pending_samples : 128;
+    E.srec = gzp_sample_record_words(E.SW, maxa);
+    E.READYCAP = ready_cap > 0 ? ready_cap : 1 << 16;
+    E.uniq_cap = 1 << 20;
+    E.max_iters_per_step = 16;
+    E.seed = seed;
+    if ((int)tr->policy_sizes.size() != E.R) { gz_set_error("transformer policy heads != roles"); delete h; return GZ_ERR_ARG; }
+    for (int r = 0; r < E.R; r++)
+        if (tr->policy_sizes[r] != E.role_sizes[r]) { gz_set_error("policy size of role %d: %d != %d actions", r, tr->policy_sizes[r], E.role_sizes[r]); delete h; return GZ_ERR_ARG; }
+    int rc = gz_puct_set_config(h, sp_conf, puct_conf, rte_conf);
+    if (rc != GZ_OK) { delete h; return rc; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    h->arena_bytes = gzp_layout(&E, nullptr);
+    cudaError_t e = cudaMalloc(&h->d_arena, h->arena_bytes);
+    if (e != cudaSuccess) {
+        gz_set_error("cudaMalloc of %.1f MB for %d game trees failed: %s", h->arena_bytes / 1e6, n_games, cudaGetErrorString(e));
+        delete h;
+        return GZ_ERR_CUDA;
+    }
+    GZ_CUDA(cudaMemset(h->d_arena, 0, h->arena_bytes));
+    gzp_layout(&E, (uint8_t*)h->d_arena);
+    // initial state + hash mask
+    {
+        std::vector<uint32_t> init(E.SW), mask(E.SW, 0);
+        GZ_CUDA(cudaMemcpy(init.data(), gz_propnet_init_words(pn), E.SW * 4, cudaMemcpyDeviceToHost));
+        for (int b : tr->board_base) mask[b >> 5] |= 1u << (b & 31);
+        for (int b : tr->ctrl_base) mask[b >> 5] |= 1u << (b & 31);
+        GZ_CUDA(cudaMemcpy((void*)E.init_state, init.data(), E.SW * 4, cudaMemcpyHostToDevice));
+        GZ_CUDA(cudaMemcpy((void*)E.uniq_mask, mask.data(), E.SW * 4, cudaMemcpyHostToDevice));
+    }
+    GZ_CUDA(cudaMalloc(&h->d_totals, sizeof(PuctTotals)));
+    GZ_CUDA(cudaMalloc(&h->d_role_sizes_off, rso.size() * sizeof(int)));
+    GZ_CUDA(cudaMemcpy(h->d_role_sizes_off, rso.data(), rso.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->total_size = tr->E.total;
+    puct_init_kernel<<<(E.G + 127) / 128, 128>>>(E, mode);
+    GZ_CUDA(cudaGetLastError());
+    GZ_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    return GZ_OK;
+}
+
+extern "C" void gz_puct_destroy(gz_puct* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->d_arena) cudaFree(h->d_arena);
+    if (h->d_totals) cudaFree(h->d_totals);
+    if (h->d_role_sizes_off) cudaFree(h->d_role_sizes_off);
+    delete h;
+}
+
+extern "C" int64_t gz_puct_info(const gz_puct* h, int what) {
+    if (!h) return -1;
+    switch (what) {
+        case 0: return h->E.G;
+        case 1: return h->total_size;
+        case 2: return h->E.policy_stride;
+        case 3: return h->E.n_rewards;
+        case 4: return h->E.srec;
+        case 5: return (int64_t)h->arena_bytes;
+        case 6: return h->E.SW;
+        case 7: return h->E.max_actions;
+        case 8: return h->E.READYCAP;
+        default: return -1;
+    }
+}
+
+// One engine step. d_policy [G][policy_stride] f32 and d_value [G][n_rewards] f32 are the network's
+// outputs for the planes produced by the previous advance (ignored when nn_fresh == 0, e.g. on the
+// very first call). d_planes receives [G][total_size] of plane_dtype, one row per game.
+extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
+                               void* d_planes, int plane_dtype, void* stream) {
+    if (!h) { gz_set_error("null engine"); return GZ_ERR_ARG; }
+    if (nn_fresh && (!d_policy || !d_value)) { gz_set_error("network outputs missing"); return GZ_ERR_ARG; }
+    if (sub_iters < 1) sub_iters = 1;
+    GZ_CUDA(cudaSetDevice(h->device));
+    PuctEngine E = h->E;
+    E.nn_policy = d_policy;
+    E.nn_value = d_value;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = (E.G + PUCT_WARPS_PER_BLOCK - 1) / PUCT_WARPS_PER_BLOCK;
+    for (int it = 0; it < sub_iters; it++) {
+        puct_pre_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, s>>>(E, (it == 0 && nn_fresh) ? 1 : 0);
+        GZ_CUDA(cudaGetLastError());
+        int rc = gz_sm_transition(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
+                                  GZ_GOALS_TERMINAL_ONLY, stream);
+        if (rc != GZ_OK) return rc;
+        puct_post_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, s>>>(E);
+        GZ_CUDA(cudaGetLastError());
+    }
+    if (d_planes) {
+        // every row is encoded (rows of games that do not wait for the network hold a stale but valid
+        // state; their network outputs are never read)
+        int rc = gz_encode(h->tr, E.G, E.SW, E.x_state, E.x_in_state, E.x_prevcnt, 1, d_planes, plane_dtype, stream);
+        if (rc != GZ_OK) return rc;
+    }
+    return GZ_OK;
+}
+
+extern "C" const uint8_t* gz_puct_need_eval_ptr(const gz_puct* h) { return h ? h->E.x_need_eval : nullptr; }
+
+// totals: [evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children,
+//          dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval,
+//          ready_count]
+extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
+    if (!h || !out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    GZ_CUDA(cudaMemsetAsync(h->d_totals, 0, sizeof(PuctTotals), s));
+    puct_totals_kernel<<<(h->E.G + 127) / 128, 128, 0, s>>>(h->E, h->d_totals);
+    GZ_CUDA(cudaGetLastError());
+    PuctTotals t;
+    unsigned long long ready = 0;
+    GZ_CUDA(cudaMemcpyAsync(&t, h->d_totals, sizeof(t), cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaMemcpyAsync(&ready, h->E.ready_count, 8, cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaStreamSynchronize(s));
+    out[0] = (double)t.evals; out[1] = (double)t.moves; out[2] = (double)t.games; out[3] = (double)t.samples;
+    out[4] = (double)t.playouts; out[5] = t.errors; out[6] = t.halted; out[7] = t.first_error;
+    out[8] = t.max_nodes; out[9] = t.max_children; out[10] = t.dupes; out[11] = t.no_samples;
+    out[12] = t.fp_resign0; out[13] = t.fp_resign1; out[14] = t.early_run_to_ends; out[15] = t.resigns;
+    out[16] = t.aborts; out[17] = t.waiting_eval; out[18] = (double)ready;
+    return GZ_OK;
+}
+
+// Copies the finished samples to the host (records of gz_puct_info(h,4) int32 words, layout SR_* in
+// gz_puct_core.h) and empties the device buffer. Returns the number of records copied (<= cap), or
+// a negative status. Synchronises `stream`.
+extern "C" int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream) {
+    if (!h || (!h_out && cap > 0)) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    cudaSetDevice(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long ready = 0;
+    if (cudaMemcpyAsync(&ready, h->E.ready_count, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) { gz_set_error("sample count copy failed"); return GZ_ERR_CUDA; }
+    int64_t n = (int64_t)std::min<unsigned long long>(ready, (unsigned long long)h->E.READYCAP);
+    n = std::min<int64_t>(n, cap);
+    if (n > 0 && cudaMemcpyAsync(h_out, h->E.ready, (size_t)n * h->E.srec * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+        gz_set_error("sample copy failed");
+        return GZ_ERR_CUDA;
+    }
+    cudaMemsetAsync(h->E.ready_count, 0, 8, s);
+    cudaStreamSynchronize(s);
+    return n;
+}
+
+extern "C" int gz_puct_clear_unique_states(gz_puct* h, void* stream) {
+    if (!h) return GZ_ERR_ARG;
+    GZ_CUDA(cudaSetDevice(h->device));
+    GZ_CUDA(cudaMemsetAsync(h->E.uniq_keys, 0, (size_t)h->E.uniq_cap * 8, (cudaStream_t)stream));
+    GZ_CUDA(cudaMemsetAsync(h->E.uniq_counts, 0, (size_t)h->E.uniq_cap * 4, (cudaStream_t)stream));
+    return GZ_OK;
+}
+
+// ---- player mode (mode == 1): commands for game `g`; they take effect in the next advance.
+__global__ void puct_cmd_kernel(const __grid_constant__ PuctEngine E, int g, int cmd, int arg, int evals) {
+    GameCtl& c = E.ctl[g];
+    c.cmd = cmd; c.cmd_arg = arg; c.cmd_evals = evals; c.cmd_done = 0;
+}
+
+extern "C" int gz_puct_command(gz_puct* h, int g, int cmd, int arg, int evals, const uint32_t* h_state, void* stream) {
+    if (!h || g < 0 || g >= h->E.G) { gz_set_error("bad game index"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cmd == CMD_RESET) {
+        if (h_state) GZ_CUDA(cudaMemcpyAsync(h->E.x_in_state + (size_t)g * h->E.SW, h_state, h->E.SW * 4, cudaMemcpyHostToDevice, s));
+        else GZ_CUDA(cudaMemcpyAsync(h->E.x_in_state + (size_t)g * h->E.SW, h->E.init_state, h->E.SW * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    puct_cmd_kernel<<<1, 1, 0, s>>>(h->E, g, cmd, arg, evals);
+    GZ_CUDA(cudaGetLastError());
+    return GZ_OK;
+}
+
+// Snapshot of game g: out_i[0..7] = cmd_done, phase, error, choice, n_nodes, n_children, root visits,
+// lead role; out_f[0] = root score for the lead role; then per child (max_children): move, traversals,
+// policy_prob, child score (-1 unexpanded), next_prob. Returns the number of children. Synchronises.
+__global__ void puct_snapshot_kernel(const __grid_constant__ PuctEngine E, int g, int max_children, int* oi, float* of,
+                                     int* moves, int* trav, float* prob, float* score, float* next_prob) {
+    GameView V = gzp_view(&E, g);
+    const GameCtl& c = *V.c;
+    oi[0] = c.cmd_done; oi[1] = c.phase; oi[2] = c.error; oi[3] = c.choice; oi[4] = c.n_nodes; oi[5] = c.n_children;
+    oi[6] = 0; oi[7] = 0; oi[8] = 0;
+    of[0] = 0.0f;
+    if (c.root < 0 || c.n_nodes <= 0) return;
+    const int n = c.root;
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n), lead = NODE(n_lead, n);
+    oi[6] = (int)NODE(n_visits, n); oi[7] = lead; oi[8] = nc;
+    of[0] = NSCORE(n, lead);
+    for (int i = 0; i < nc && i < max_children; i++) {
+        moves[i] = CHILD(c_move, c0 + i);
+        trav[i] = (int)CHILD(c_trav, c0 + i);
+        prob[i] = CHILD(c_prob, c0 + i);
+        const int to = CHILD(c_to, c0 + i);
+        score[i] = to >= 0 ? NSCORE(to, lead) : -1.0f;
+        next_prob[i] = CHILD(c_next, c0 + i);
+    }
+}
+
+extern "C" int gz_puct_snapshot(gz_puct* h, int g, int max_children, int* out_i, float* out_f, int* moves, int* trav,
+                                float* prob, float* score, float* next_prob, void* stream) {
+    if (!h || g < 0 || g >= h->E.G || max_children < 0) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = 16 * 4 + (size_t)max_children * 5 * 4 + 64;
+    void* d = nullptr;
+    GZ_CUDA(cudaMalloc(&d, bytes));
+    int* di = (int*)d;
+    float* df = (float*)(di + 12);
+    int* dm = (int*)(df + 4);
+    int* dt = dm + max_children;
+    float* dp = (float*)(dt + max_children);
+    float* ds = dp + max_children;
+    float* dn = ds + max_children;
+    puct_snapshot_kernel<<<1, 1, 0, s>>>(h->E, g, max_children, di, df, dm, dt, dp, ds, dn);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_i, di, 9 * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_f, df, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && max_children) {
+        cudaMemcpyAsync(moves, dm, max_children * 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(trav, dt, max_children * 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(prob, dp, max_children * 4, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(score, ds, max_children * 4, cudaMemcpyDeviceToHost, s);
+        e = cudaMemcpyAsync(next_prob, dn, max_children * 4, cudaMemcpyDeviceToHost, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) { gz_set_error("snapshot failed: %s", cudaGetErrorString(e)); return GZ_ERR_CUDA; }
+    return out_i[8];
+}
+
+extern "C" int gz_synth_nn(const void* d_planes, int plane_dtype, int64_t n, int total, uint64_t seed, int n_roles,
+                           const int* h_role_sizes, int n_rewards, float* d_policy, float* d_value, void* stream) {
+    if (!d_planes || !d_policy || !d_value || n_roles < 1 || n_roles > GZP_MAX_ROLES) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
+    if (n <= 0) return GZ_OK;
+    static thread_local int* d_rso = nullptr;
+    static thread_local int cached[2 * GZP_MAX_ROLES + 1] = {0};
+    int rso[2 * GZP_MAX_ROLES];
+    int off = 0;
+    for (int r = 0; r < n_roles; r++) { rso[2 * r] = h_role_sizes[r]; rso[2 * r + 1] = off; off += h_role_sizes[r]; }
+    if (!d_rso) GZ_CUDA(cudaMalloc(&d_rso, sizeof(rso)));
+    if (memcmp(cached, rso, sizeof(int) * 2 * n_roles) != 0) {
+        GZ_CUDA(cudaMemcpy(d_rso, rso, sizeof(int) * 2 * n_roles, cudaMemcpyHostToDevice));
+        memcpy(cached, rso, sizeof(int) * 2 * n_roles);
+    }
+    const int wpb = 4;
+    const int blocks = (int)((n + wpb - 1) / wpb);
+    if (plane_dtype == GZ_DTYPE_BF16)
+        synth_nn_kernel<__nv_bfloat16><<<blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)d_planes, n, total, seed, n_roles, d_rso, off, n_rewards, d_policy, d_value);
+    else
+        synth_nn_kernel<float><<<blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
+            (const float*)d_planes, n, total, seed, n_roles, d_rso, off, n_rewards, d_policy, d_value);
+    GZ_CUDA(cudaGetLastError());
+    return GZ_OK;
+}

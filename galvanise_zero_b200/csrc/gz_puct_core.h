@@ -1238,11 +1238,13 @@ GZP_HDN void gzp_begin_game(GameView& V) {
 
 // Returns when the game is blocked on the pipeline (c->req != REQ_NONE or c->eval_node >= 0),
 // idle, halted, or the per-step iteration budget is spent.
-GZP_HDN void gzp_step_pre(GameView& V, float* scratch) {
+GZP_HDN void gzp_step_pre(GameView& V, float* scratch, bool nn_fresh = true) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     if (c->phase == PH_HALT) return;
     if (c->eval_node >= 0) {
+        if (!nn_fresh) return;          // still waiting for the network
+        E->x_need_eval[V.g] = 0;
         gzp_reply(V, c->eval_node);
         c->num_evaluations++;
         c->total_evals++;
@@ -1479,7 +1481,6 @@ GZP_HDN void gzp_step_pre(GameView& V, float* scratch) {
 GZP_HDN void gzp_step_post(GameView& V) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
-    E->x_need_eval[V.g] = 0;
     if (c->phase == PH_HALT || c->req == REQ_NONE) return;
     const int parent = c->req == REQ_ROOT ? -1 : c->req_parent;
     const int depth = parent < 0 ? c->game_depth : NODE(n_depth, parent) + 1;

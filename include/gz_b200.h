@@ -120,6 +120,55 @@ int gz_encode(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_s
               const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
               int out_dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched PUCT self-play engine. Replaces the reference's Supervisor / SelfPlayManager / SelfPlay /
+ * NetworkScheduler / PuctEvaluator stack for `n_games` concurrent games:
+ *   gz_puct_create          ggpzero_interface.Supervisor(sm_ptr, transformer, batch_size, identifier)
+ *                           + .start_self_play(num_workers, conf_dict)
+ *                           (src/cpp/pyobjects/supervisor_impl.cpp:14-32,215-237); mode 1 = Player(...)
+ *                           (src/cpp/pyobjects/player_impl.cpp:183-201)
+ *   gz_puct_advance         Supervisor.poll(n_predictions, [policy_0.., value]) -> planes
+ *                           (src/cpp/pyobjects/common.cpp:160-218, src/cpp/supervisor.cpp:101-168), with
+ *                           device tensors on both sides (no host round trip)
+ *   gz_puct_fetch_samples   Supervisor.fetch_samples()           (supervisor_impl.cpp:75-128)
+ *   gz_puct_clear_unique_states  .clear_unique_states()          (supervisor_impl.cpp:138-144)
+ *   gz_puct_command / gz_puct_snapshot   Player.player_reset / player_move / player_apply_move /
+ *                           player_get_move / player_tree_debug (src/cpp/pyobjects/player_impl.cpp:8-129)
+ *   gz_puct_totals          the counters of SelfPlayManager::reportAndResetStats
+ *                           (src/cpp/selfplaymanager.cpp:161-200) plus throughput counters
+ * Config arrays are flat doubles in the field order of oracle/gzref.py SP_FIELDS / PUCT_FIELDS, i.e.
+ * the fields of SelfPlayConfig / PUCTEvaluatorConfig (src/ggpzero/defs/confs.py:9-123).
+ */
+typedef struct gz_puct gz_puct;
+#define GZ_PUCT_MODE_SELFPLAY 0
+#define GZ_PUCT_MODE_PLAYER 1
+#define GZ_PUCT_CMD_RESET 1
+#define GZ_PUCT_CMD_APPLY 2
+#define GZ_PUCT_CMD_SEARCH 3
+
+int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, int mode, int node_cap, int child_cap,
+                   int max_pending_samples, int ready_cap, const double* sp_conf, const double* puct_conf,
+                   const double* run_to_end_puct_conf, uint64_t seed, gz_puct** out);
+void gz_puct_destroy(gz_puct* h);
+int gz_puct_set_config(gz_puct* h, const double* sp_conf, const double* puct_conf, const double* run_to_end_puct_conf);
+/* what: 0 games, 1 plane row size, 2 policy row size (sum of role sizes), 3 value row size,
+ *       4 sample record words, 5 arena bytes, 6 state words, 7 max actions, 8 ready capacity */
+int64_t gz_puct_info(const gz_puct* h, int what);
+int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
+                    void* d_planes, int plane_dtype, void* stream);
+const uint8_t* gz_puct_need_eval_ptr(const gz_puct* h);
+int gz_puct_totals(gz_puct* h, double* h_out19, void* stream);
+int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream);
+int gz_puct_clear_unique_states(gz_puct* h, void* stream);
+int gz_puct_command(gz_puct* h, int game, int cmd, int arg, int evals, const uint32_t* h_state, void* stream);
+int gz_puct_snapshot(gz_puct* h, int game, int max_children, int* out_i9, float* out_f1, int* moves, int* trav,
+                     float* prob, float* score, float* next_prob, void* stream);
+
+/* Deterministic synthetic policy/value network (include/gz_synth.h) on encoded planes — parity and
+ * benchmarking utility; the production network is a PyTorch module. */
+int gz_synth_nn(const void* d_planes, int plane_dtype, int64_t n, int total, uint64_t seed, int n_roles,
+                const int* h_role_sizes, int n_rewards, float* d_policy, float* d_value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,128 @@
+"""GPU: the device PUCT engine (gz_puct_* through the C-ABI) against the reference's own C++ search
+(oracle/_ref, built in the container and shipped with the snapshot) under the shared synthetic network.
+
+Tolerance: total-variation distance between root visit distributions <= 0.02 per
+move and identical arg-max move in >= 99 % of positions. The device differs from the host reference
+only in libm (logf / pow), so the expected distance is 0; the test reports the maximum seen."""
+import numpy as np
+import pytest
+import torch
+
+from galvanise_zero_b200 import tables
+from galvanise_zero_b200.defs import confs
+from oracle import gzref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not gzref.available(), reason='oracle/_ref missing')]
+
+
+def _wait(eng, game=0, max_steps=200000, seed=1):
+    for i in range(max_steps):
+        if i % 64 == 63 or i < 4:
+            snap = eng.snapshot(game, 0)
+            if snap['cmd_done'] or snap['phase'] == 8:
+                return snap
+        eng.run_synthetic(1, seed=seed)
+    raise AssertionError('engine did not finish the command')
+
+
+def _device_search(eng, evals, n_moves, seed=1):
+    eng.command(0, 1)          # reset to the initial state
+    assert _wait(eng, seed=seed)['cmd_done'] == 1
+    out = []
+    for m in range(n_moves):
+        s = eng.snapshot(0)
+        if len(s['moves']) == 0:
+            break
+        eng.command(0, 3, evals=evals)
+        assert _wait(eng, seed=seed)['cmd_done'] == 1
+        s = eng.snapshot(0)
+        out.append(s)
+        eng.command(0, 2, arg=int(s['moves'][s['choice']]))
+        if _wait(eng, seed=seed)['cmd_done'] != 1:
+            break
+    return out
+
+
+@pytest.mark.parametrize('game,evals,moves', [('reversi', 200, 20), ('breakthrough', 300, 20),
+                                              ('connect6', 100, 4)])
+def test_device_search_matches_reference(game, evals, moves):
+    from galvanise_zero_b200.engine import PuctEngine
+    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits')
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    eng = PuctEngine(game, sp, n_games=1, mode=1, node_cap=8192, child_cap=1 << 18, plane_dtype=torch.float32)
+    ref = gzref.RefEngine(tables.blob_by_name(game), eng.c_transformer).search(conf, evals, n_moves=moves)
+    mine = _device_search(eng, evals, moves)
+    assert len(mine) == len(ref)
+    worst_tv, same_choice = 0.0, 0
+    for a, b in zip(ref, mine):
+        assert np.array_equal(a['moves'], b['moves'])
+        pa = a['traversals'] / max(1, a['traversals'].sum())
+        pb = b['traversals'] / max(1, b['traversals'].sum())
+        worst_tv = max(worst_tv, 0.5 * float(np.abs(pa - pb).sum()))
+        same_choice += int(a['choice'] == b['choice'])
+        if a['choice'] != b['choice']:
+            break     # trajectories differ from here on
+    print('max TV distance', worst_tv, 'same choice', same_choice, '/', len(ref))
+    assert worst_tv <= 0.02
+    assert same_choice >= 0.99 * len(ref)
+
+
+def test_device_selfplay_samples_match_reference():
+    from galvanise_zero_b200.engine import PuctEngine
+    game, G, evals, target = 'breakthroughSmall', 8, 40, 150
+    sp = confs.selfplay_config_template(evals_per_move=evals)
+    sp.puct_config.dirichlet_noise_pct = -1
+    sp.run_to_end_puct_config.dirichlet_noise_pct = -1
+    eng = PuctEngine(game, sp, n_games=G, mode=0, node_cap=4096, child_cap=1 << 16, plane_dtype=torch.float32)
+    srec = eng.srec
+    ref = gzref.RefEngine(tables.blob_by_name(game), eng.c_transformer).selfplay(
+        sp, G, 0, target_samples=target, max_seconds=120, sample_capacity=target * 6, srec=srec)
+    recs = ref['records']
+    got = []
+    for _ in range(4000):
+        eng.run_synthetic(64)
+        r = eng.fetch_sample_records()
+        if len(r):
+            got.append(r)
+        if sum(len(x) for x in got) >= len(recs):
+            break
+    mine = np.concatenate(got)
+    t = eng.totals()
+    assert t['errors'] == 0 and t['halted'] == 0
+
+    def key(r):
+        return (int(r[3]), int(r[4]), int(r[1]))
+    rd = {key(r): r for r in recs}
+    md = {key(r): r for r in mine}
+    common = sorted(set(rd) & set(md))
+    assert len(common) >= 0.8 * len(rd)
+    sw = eng.state_words
+    bad = 0
+    for k in common:
+        a, b = rd[k], md[k]
+        nc = int(a[11])
+        bad += int(not np.array_equal(a[:24 + 2 * sw + 2 * nc], b[:24 + 2 * sw + 2 * nc]))
+    print('samples compared', len(common), 'mismatching', bad)
+    assert bad <= 0.01 * len(common)
+
+
+def test_selfplay_at_scale_properties():
+    """4096 concurrent reversi games (BASELINE config 2 size): the engine keeps every game alive, no
+    arena overflows, samples are well-formed (policies sum to 1, final scores in range)."""
+    from galvanise_zero_b200.engine import PuctEngine
+    sp = confs.selfplay_config_template(evals_per_move=60)
+    eng = PuctEngine('reversi', sp, n_games=4096, mode=0, node_cap=1024, child_cap=1024 * 16)
+    eng.run_synthetic(1500)
+    t = eng.totals()
+    assert t['errors'] == 0 and t['halted'] == 0, t
+    assert t['evals'] > 4096 * 1000 and t['moves'] > 4096 * 5
+    eng.run_synthetic(3000)
+    recs = eng.fetch_sample_records()
+    assert len(recs) > 100
+    samples = eng.records_to_samples(recs[:200])
+    for s in samples:
+        lead_pol = max(s['policies'], key=len)
+        assert abs(sum(p for _, p in lead_pol) - 1.0) < 1e-3
+        assert all(-0.06 <= x <= 1.06 for x in s['final_score'])
+        assert len(s['state']) == 130 and 0 <= s['depth'] <= s['game_length'] <= 64
