@@ -259,6 +259,223 @@ def run_propnet(args, rank, world, local):
         print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------
+PUCT_GAME = 'reversi'
+PUCT_GAMES_PER_GPU = 4096
+PUCT_EVALS_PER_MOVE = 800
+PUCT_WORKLOAD = ('reversi 8x8 PUCT self-play, 800 evals/move, small residual net (64f x 5), '
+                 '4096 concurrent games per GPU')
+
+
+def puct_selfplay_conf():
+    from galvanise_zero_b200.defs import confs
+    return confs.selfplay_config_template(evals_per_move=PUCT_EVALS_PER_MOVE)
+
+
+def cpu_reference_selfplay(seconds=14.0, warm=3.0, threads=None, batch=32):
+    """The reference's own C++ PUCT self-play (oracle/_ref: Supervisor worker mode, N threads x 2
+    managers x `batch` games, src/cpp/supervisor.cpp:79-99) on the host cores, network replaced by
+    the synthetic hash network so that it measures propnet + PUCT + encode (the reference's
+    acc_time_polling notion)."""
+    from galvanise_zero_b200 import bases, cppinterface, lookup, tables
+    from galvanise_zero_b200.defs import datadesc
+    from oracle import gzref
+    threads = threads or max(1, (os.cpu_count() or 2) - 1)
+    gi = lookup.by_name(PUCT_GAME)
+    tr = bases.GdlBasesTransformer(gi, datadesc.generation_for(PUCT_GAME))
+    ct = cppinterface.create_c_transformer(tr)
+    eng = gzref.RefEngine(tables.blob_by_name(PUCT_GAME), ct)
+    st = eng.selfplay(puct_selfplay_conf(), batch, threads, max_seconds=seconds, warm_seconds=warm)
+    w = max(st['window_seconds'], 1e-9)
+    return {'value': st['window_moves'] / w, 'unit': 'moves/s', 'cores': threads + 1, 'kind': 'reference',
+            'evals_per_s': st['window_evals'] / w,
+            'sample': '%s, reference C++ (puct/evaluator.cpp, selfplay.cpp, supervisor.cpp compiled unmodified '
+                      'against shims) in worker mode: %d worker threads x 2 managers x %d games, %d evals/move, '
+                      'synthetic network, %.1f s window after %.1f s warm-up'
+                      % (PUCT_GAME, threads, batch, PUCT_EVALS_PER_MOVE, w, warm)}
+
+
+def time_region(fn, device):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1)
+
+
+def run_puct(args, rank, world, local):
+    import numpy as np
+    import torch
+    from galvanise_zero_b200.engine import PuctEngine
+    from galvanise_zero_b200.nn import make_inference_network
+    from galvanise_zero_b200.selfplay import SelfPlayRunner
+
+    peaks = load_peaks()
+    torch.cuda.set_device(local)
+    G = args.slots or PUCT_GAMES_PER_GPU
+    sp = puct_selfplay_conf()
+    eng = PuctEngine(PUCT_GAME, sp, n_games=G, mode=0, device=local, seed=0xB200 + 7919 * rank,
+                     node_cap=4096, child_cap=4096 * 16)
+    net = make_inference_network(eng.transformer, 'small', seed=1234, device=eng.device)
+    runner = SelfPlayRunner(eng, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph)
+    # bring the games to a desynchronised steady state (untimed), then warm up
+    runner.step(args.presteps)
+    runner.step(args.warmup)
+    barrier(world)
+    t_before = eng.totals()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    ev0.record()
+    runner.step(args.steps)
+    ev1.record()
+    barrier(world)
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary() if sampler else None
+    t_after = eng.totals()
+    d_moves = t_after['moves'] - t_before['moves']
+    d_evals = t_after['evals'] - t_before['evals']
+    ms_max = all_max(ms, world, eng.device)
+    moves = all_sum(d_moves, world, eng.device)
+    evals = all_sum(d_evals, world, eng.device)
+    value = moves / (ms_max * 1e-3)
+
+    # ---- per-kernel timing of one step, eager, CUDA events on the launching stream
+    parts = {}
+    with torch.no_grad():
+        reps = 10
+        parts['engine_advance_ms'] = time_region(lambda: [eng.advance(eng.policy, eng.value, args.sub_iters) for _ in range(reps)], eng.device) / reps
+        x = eng.planes.contiguous(memory_format=torch.channels_last)
+        parts['network_forward_ms'] = time_region(lambda: [net(x) for _ in range(reps)], eng.device) / reps
+        st = eng.sm
+        s_in = st.initial_states(G)
+        mv = torch.full((G, st.n_roles), -1, dtype=torch.int16, device=eng.device)
+        outb = (torch.empty_like(s_in),) + st.alloc_views(G)
+        parts['propnet_transition_ms'] = time_region(lambda: [st.transition(s_in, mv, out=outb) for _ in range(reps)], eng.device) / reps
+    flops = net.flops_per_position * G
+    nn_s = parts['network_forward_ms'] * 1e-3
+    achieved = flops / nn_s / 1e12
+    peak = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                'frac': achieved / peak, 'traffic': None,
+                'kernel': 'residual tower forward (cuDNN/cuBLAS via PyTorch, bf16 channels_last), %d positions' % G,
+                'flops_per_unit': net.flops_per_position, 'units_per_launch': G,
+                'peak_source': peaks['source'] + ' (sustained bf16)'}
+
+    # ---- e2e: the reference-shaped numpy poll() API with host buffers (D2H planes, H2D planes for the
+    # network as Keras predict_on_batch does, D2H policy/value, H2D into the engine), every step
+    e2e = None
+    if rank == 0 or world > 1:
+        from galvanise_zero_b200 import interface
+        sup = interface.Supervisor(PUCT_GAME, eng.c_transformer, G, 'bench', device=local, seed=0xE2E + rank,
+                                   node_cap=2048, child_cap=2048 * 16)
+        import attr
+        sup.start_self_play(0, attr.asdict(sp))
+        R = len(eng.role_sizes)
+        h2d = d2h = 0
+
+        def e2e_step(pred):
+            nonlocal h2d, d2h
+            n, arrays = pred
+            planes = sup.poll(n, arrays)
+            if planes is None:
+                return (0, [])
+            n_req = planes.size // eng.total_size
+            d2h += planes.nbytes
+            xin = torch.from_numpy(planes.reshape((n_req,) + eng.plane_shape)).pin_memory()
+            xd = xin.to(eng.device, non_blocking=True).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            h2d += planes.nbytes
+            with torch.no_grad():
+                pol, val = net(xd)
+            pol = pol.cpu().numpy()
+            val = val.cpu().numpy()
+            d2h += pol.nbytes + val.nbytes
+            h2d += pol.nbytes + val.nbytes
+            off = 0
+            arrs = []
+            for r in range(R):
+                arrs.append(np.ascontiguousarray(pol[:, off:off + eng.role_sizes[r]]))
+                off += eng.role_sizes[r]
+            arrs.append(np.ascontiguousarray(val))
+            return (n_req, arrs)
+
+        pred = (0, [])
+        for _ in range(min(args.presteps, 600)):
+            pred = e2e_step(pred)
+        m0 = sup.engine.totals()
+        h2d = d2h = 0
+        reps = max(20, min(args.steps, 200))
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pred = e2e_step(pred)
+        torch.cuda.synchronize()
+        dt = all_max(time.perf_counter() - t0, world, eng.device)
+        m1 = sup.engine.totals()
+        e2e_moves = all_sum(m1['moves'] - m0['moves'], world, eng.device)
+        e2e_evals = all_sum(m1['evals'] - m0['evals'], world, eng.device)
+        e2e = {'value': e2e_moves / dt, 'unit': 'moves/s', 'h2d_bytes_per_step': int(h2d / reps),
+               'd2h_bytes_per_step': int(d2h / reps), 'evals_per_s': e2e_evals / dt,
+               'api': 'interface.Supervisor.poll (numpy in / numpy out, reference contract), network fed from pinned host memory',
+               'steps': reps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_reference_selfplay()
+        except Exception as exc:   # oracle/_ref missing on this box
+            cpu = {'value': None, 'unit': 'moves/s', 'cores': os.cpu_count(), 'kind': 'reference',
+                   'sample': 'unavailable: %s' % exc}
+
+    if rank == 0:
+        line = {
+            'metric': 'PUCT self-play moves/sec', 'value': value, 'unit': 'moves/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': PUCT_WORKLOAD, 'games_per_gpu': G, 'evals_per_move': PUCT_EVALS_PER_MOVE,
+                       'network': 'random-init small tower, %.1f MFLOP/position' % (net.flops_per_position / 1e6),
+                       'step': 'one engine advance (select/backup + propnet + expand + encode) + one network '
+                               'forward over %d leaves' % G,
+                       'l2': 'tree arenas %.1f GB per GPU >> 126 MB L2' % (eng.arena_bytes / 1e9),
+                       'presteps': args.presteps, 'cuda_graph': not args.no_graph,
+                       'parallelism': 'games sharded across %d GPU(s), no collective on the hot path' % world},
+            'evals_per_s': evals / (ms_max * 1e-3), 'moves_in_window': moves,
+            'roofline': roofline, 'kernel_times_ms': parts, 'cpu_baseline': cpu, 'e2e': e2e,
+            'gpu_launches': args.steps * runner.kernels_per_step, 'clocks': clocks,
+            'engine_totals': {k: t_after[k] for k in ('errors', 'halted', 'max_nodes', 'max_children', 'games', 'samples')},
+        }
+        print(json.dumps(line), flush=True)
+
+
+def run_reference_puct(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    per_step = 6.0
+    total = max(1, args.steps) * per_step
+    cpu = cpu_reference_selfplay(seconds=min(total, 150.0) + 3.0, warm=3.0)
+    dt = time.perf_counter() - t0
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'PUCT self-play moves/sec', 'value': cpu['value'], 'unit': 'moves/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3 / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': PUCT_WORKLOAD, 'evals_per_move': PUCT_EVALS_PER_MOVE,
+                   'note': 'host-core run of the reference C++ search; concurrent games bounded to what the '
+                           'host threads hold (the GPU arm holds 4096 per GPU)'},
+        'evals_per_s': cpu['evals_per_s'], 'cpu_baseline': cpu,
+        'e2e': {'value': cpu['value'], 'unit': 'moves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}),
+        flush=True)
+
+
 def run_reference(args):
     """CPU reference arm: the oracle port of the reference's state-machine loop on all host cores."""
     rank = int(os.environ.get('RANK', '0'))
@@ -299,22 +516,28 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=400)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='propnet', choices=['propnet', 'puct'])
+    ap.add_argument('--workload', default='puct', choices=['propnet', 'puct'])
+    ap.add_argument('--sub-iters', type=int, default=1)
+    ap.add_argument('--presteps', type=int, default=3000)
+    ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--slots', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
-        run_reference(args)
+        if args.workload == 'puct':
+            run_reference_puct(args)
+        else:
+            run_reference(args)
         return
     rank, world, local = dist_setup(args.gpus)
     if args.workload == 'propnet':
         run_propnet(args, rank, world, local)
     else:
-        raise SystemExit('puct workload not built yet')
+        run_puct(args, rank, world, local)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -316,6 +316,14 @@ extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d
 
 extern "C" const uint8_t* gz_puct_need_eval_ptr(const gz_puct* h) { return h ? h->E.x_need_eval : nullptr; }
 
+// Copies the per-game "waiting for the network" flags (uint8 [G]) into a caller-owned device buffer.
+extern "C" int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream) {
+    if (!h || !d_out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    GZ_CUDA(cudaMemcpyAsync(d_out, h->E.x_need_eval, (size_t)h->E.G, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GZ_OK;
+}
+
 // totals: [evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children,
 //          dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval,
 //          ready_count]

@@ -120,3 +120,102 @@ class GdlBasesTransformer(object):
         _lib.check(self._L.gz_encode(self._h, n, sw, states.data_ptr(), pp, pc, max_prev,
                                      out.data_ptr(), code, stream))
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+class Supervisor(object):
+    """``ggpzero_interface.Supervisor(sm, transformer, batch_size, identifier)``
+    (``src/cpp/pyobjects/supervisor_impl.cpp:215-237``) on the device engine.
+
+    ``poll`` keeps the reference's numpy contract (``src/cpp/pyobjects/common.cpp:160-218``): it takes
+    the predictions for the rows handed out by the previous poll and returns a 1-D float32 array of
+    ``n_req * total_size`` planes (or None when there is nothing to evaluate). ``poll_device`` is the
+    additive zero-copy variant on CUDA tensors."""
+
+    def __init__(self, sm, c_transformer, batch_size, identifier, device=0, seed=0x5EED0000,
+                 node_cap=4096, child_cap=None):
+        self.sm = sm
+        self.game = sm if isinstance(sm, str) else getattr(sm, 'game', None)
+        if self.game is None:
+            raise GGPZeroInterfaceError('Supervisor needs a state machine created by name')
+        self.c_transformer = c_transformer
+        self.batch_size = int(batch_size)
+        self.identifier = identifier
+        self.device = device
+        self.seed = seed
+        self.node_cap, self.child_cap = node_cap, child_cap
+        self.engine = None
+        self._rows = None
+        self._primed = False
+
+    def set_num_workers(self, n):
+        """Not in the reference's method table although its Python wrapper calls it
+        (``cppinterface.py:197-198``); accepted and ignored — the device engine has no worker threads."""
+
+    def start_self_play(self, num_workers, conf_dict):
+        from .engine import PuctEngine
+        import torch
+        self.engine = PuctEngine(self.game, conf_dict, n_games=self.batch_size, mode=0, device=self.device,
+                                 seed=self.seed, node_cap=self.node_cap, child_cap=self.child_cap,
+                                 c_transformer=self.c_transformer, plane_dtype=torch.float32,
+                                 sm=self.sm if not isinstance(self.sm, str) else None)
+
+    # -- zero-copy path
+    def poll_device(self, policy=None, value=None, sub_iters=1):
+        return self.engine.advance(policy, value, sub_iters)
+
+    # -- reference-shaped numpy path
+    def poll(self, n_predictions, arrays):
+        import torch
+        e = self.engine
+        if e is None:
+            raise GGPZeroInterfaceError('start_self_play() has not been called')
+        if not (0 <= n_predictions <= self.batch_size):
+            raise GGPZeroInterfaceError('n_predictions out of range')
+        if self._rows is None:
+            if n_predictions != 0:
+                raise GGPZeroInterfaceError('first poll must pass n_predictions == 0')
+            e.advance(None, None)
+        else:
+            if n_predictions != len(self._rows):
+                raise GGPZeroInterfaceError('expected %d predictions, got %d' % (len(self._rows), n_predictions))
+            for a in arrays:
+                if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
+                    raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
+            R = len(e.role_sizes)
+            pol = np.concatenate([arrays[r].reshape(n_predictions, e.role_sizes[r]) for r in range(R)], axis=1)
+            val = arrays[R].reshape(n_predictions, e.n_rewards)
+            rows = self._rows_dev
+            e.policy[rows] = torch.from_numpy(pol).to(e.device, non_blocking=True)
+            e.value[rows] = torch.from_numpy(val).to(e.device, non_blocking=True)
+            e.advance(e.policy, e.value)
+        need = self._need_eval()
+        rows = torch.nonzero(need, as_tuple=False).flatten()
+        self._rows_dev = rows
+        self._rows = rows.cpu().numpy()
+        if len(self._rows) == 0:
+            return None
+        planes = e.planes.reshape(e.n_games, -1)[rows].to(torch.float32).cpu().numpy()
+        return planes.reshape(-1)
+
+    def _need_eval(self):
+        import ctypes
+        import torch
+        e = self.engine
+        if not hasattr(self, '_need_buf'):
+            self._need_buf = torch.zeros(e.n_games, dtype=torch.uint8, device=e.device)
+            e._L.gz_puct_copy_need_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.check(e._L.gz_puct_copy_need_eval(e._h, self._need_buf.data_ptr(), e._stream()))
+        return self._need_buf
+
+    def fetch_samples(self):
+        recs = self.engine.fetch_sample_records()
+        if len(recs) == 0:
+            return None
+        return self.engine.records_to_samples(recs, self.identifier)
+
+    def add_unique_state(self, bs):
+        """The reference's Python wrapper no-ops this call as well (``cppinterface.py:218-219``)."""
+
+    def clear_unique_states(self):
+        self.engine.clear_unique_states()

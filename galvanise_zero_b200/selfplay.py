@@ -1,0 +1,68 @@
+"""Self-play driver: engine step + network forward on one stream, optionally as one CUDA graph.
+
+The reference's equivalent is the loop ``Supervisor.poll_loop`` -> ``PollerBase.poll``
+(``src/ggpzero/util/cppinterface.py:78-144``): C++ poll, reshape, ``predict_on_batch``, feed back.
+Here both halves stay on the device: ``PuctEngine.advance`` writes bf16 planes, the PyTorch tower
+reads them in place and writes the policy / value buffers the next ``advance`` consumes.
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import PuctEngine
+
+
+class SelfPlayRunner(object):
+    def __init__(self, engine: PuctEngine, net, sub_iters=1, use_cuda_graph=True):
+        self.engine = engine
+        self.net = net
+        self.sub_iters = sub_iters
+        self.graph = None
+        self.steps_done = 0
+        e = engine
+        self._planes_cl = None
+        with torch.no_grad():
+            # first step: nothing to feed back yet
+            e.advance(None, None, sub_iters)
+            self._forward()
+            if use_cuda_graph:
+                self._capture()
+
+    def _forward(self):
+        e = self.engine
+        x = e.planes.contiguous(memory_format=torch.channels_last)
+        pol, val = self.net(x)
+        e.policy.copy_(pol)
+        e.value.copy_(val)
+
+    def _step_eager(self):
+        e = self.engine
+        e.advance(e.policy, e.value, self.sub_iters)
+        self._forward()
+
+    def _capture(self):
+        e = self.engine
+        s = torch.cuda.Stream(device=e.device)
+        s.wait_stream(torch.cuda.current_stream(e.device))
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(3):        # warm up cuDNN / allocator on the side stream
+                self._step_eager()
+        torch.cuda.current_stream(e.device).wait_stream(s)
+        torch.cuda.synchronize(e.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self._step_eager()
+
+    def step(self, n=1):
+        with torch.no_grad():
+            for _ in range(n):
+                if self.graph is not None:
+                    self.graph.replay()
+                else:
+                    self._step_eager()
+        self.steps_done += n
+
+    @property
+    def kernels_per_step(self):
+        """Launches of this repo's own kernels per step: (pre, propnet, post) x sub_iters + encode."""
+        return 3 * self.sub_iters + 1

@@ -157,6 +157,7 @@ int64_t gz_puct_info(const gz_puct* h, int what);
 int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
                     void* d_planes, int plane_dtype, void* stream);
 const uint8_t* gz_puct_need_eval_ptr(const gz_puct* h);
+int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream);
 int gz_puct_totals(gz_puct* h, double* h_out19, void* stream);
 int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream);
 int gz_puct_clear_unique_states(gz_puct* h, void* stream);

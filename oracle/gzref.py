@@ -119,20 +119,21 @@ class RefEngine:
         return out
 
     def selfplay(self, sp_conf, batch_size, num_workers, nn_seed=1, target_samples=0,
-                 max_seconds=10.0, rng_seed=0x5EED0000, sample_capacity=0, srec=0):
+                 max_seconds=10.0, rng_seed=0x5EED0000, sample_capacity=0, srec=0, warm_seconds=0.0):
         """Runs the reference Supervisor. With sample_capacity > 0 also returns the samples as an
         int32 array [n, srec] in the record layout of csrc/gz_puct_core.h (SR_*)."""
         self.L.gzref_seed(rng_seed)
         import attr
         d = sp_conf if isinstance(sp_conf, dict) else attr.asdict(sp_conf)
-        stats = (ctypes.c_double * 8)()
+        stats = (ctypes.c_double * 12)()
+        stats[8] = float(warm_seconds)
         buf = np.zeros((max(sample_capacity, 1), max(srec, 1)), dtype=np.int32)
         self.L.gzref_selfplay(self.h, sp_conf_array(d), puct_conf_array(d['puct_config']),
                               puct_conf_array(d['run_to_end_puct_config']), batch_size, num_workers,
                               nn_seed, target_samples, max_seconds, stats,
                               buf.ctypes.data if sample_capacity else None, sample_capacity, srec)
         keys = ['samples', 'evaluations', 'polls', 'seconds', 'depth_sum', 'sampled_moves', 'games',
-                'plies']
+                'plies', 'moves_total', 'window_seconds', 'window_moves', 'window_evals']
         res = dict(zip(keys, [float(x) for x in stats]))
         if sample_capacity:
             res['records'] = buf[:min(int(res['samples']), sample_capacity)]

@@ -380,6 +380,34 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
     return done_moves;
 }
 
+/* Plies played so far by every SelfPlay of a manager. The build compiles this translation unit and
+ * the reference sources with -Dprivate=public (no source is modified) so that the harness can read
+ * SelfPlay::match_count and PuctEvaluator::game_depth. Reads race benignly with the worker threads. */
+struct MoveCounter {
+    std::vector<int> last_match, last_depth;
+    double finished_plies = 0;
+    double count(const std::vector<SelfPlayManager*>& mans) {
+        size_t idx = 0;
+        double cur = 0;
+        for (SelfPlayManager* m : mans) {
+            for (SelfPlay* sp : m->self_plays) {
+                if (idx >= last_match.size()) { last_match.push_back(sp->match_count); last_depth.push_back(0); }
+                const int mc = sp->match_count;
+                const int d = sp->pe->game_depth;
+                if (mc != last_match[idx]) {
+                    finished_plies += last_depth[idx];
+                    last_match[idx] = mc;
+                    last_depth[idx] = 0;
+                }
+                if (mc == last_match[idx] && d >= last_depth[idx]) last_depth[idx] = d;
+                cur += last_depth[idx];
+                idx++;
+            }
+        }
+        return finished_plies + cur;
+    }
+};
+
 /* SelfPlayConfig flat layout */
 enum {
     SC_OSCILLATE_SAMPLING_PCT = 0, SC_TEMPERATURE_FOR_POLICY, SC_EVALS_PER_MOVE, SC_RESIGN0_SCORE_PROBABILITY,
@@ -392,7 +420,9 @@ enum {
  * out_stats: [0] samples, [1] evaluations (NN rows), [2] polls, [3] seconds,
  *            [4] sum of sample depth (for sanity), [5] sampled moves == samples.
  * Moves/s is derived by the caller from game_length of completed games:
- *            [6] completed games (distinct match ids seen), [7] total plies of completed games. */
+ *            [6] completed games (distinct match ids seen), [7] total plies of completed games,
+ *            [8] in: warm-up seconds / out: plies played in total, [9] window seconds,
+ *            [10] plies in the window, [11] evaluations in the window. */
 extern "C" int gzref_selfplay(void* h, const double* sp_conf, const double* puct_conf,
                               const double* run_to_end_puct_conf, int batch_size, int num_workers,
                               uint64_t nn_seed, int64_t target_samples, double max_seconds, double* out_stats,
@@ -433,6 +463,12 @@ extern "C" int gzref_selfplay(void* h, const double* sp_conf, const double* puct
     double depth_sum = 0, plies_sum = 0;
     int64_t games = 0;
     std::string last_id;
+    std::vector<SelfPlayManager*> managers;
+    if (sup->inline_sp_manager) managers.push_back(sup->inline_sp_manager);
+    for (SelfPlayWorker* w : sup->self_play_workers) { managers.push_back(w->man0); managers.push_back(w->man1); }
+    MoveCounter mc;
+    double moves_now = 0, moves_at_warm = 0, evals_at_warm = 0, t_warm = -1;
+    const double warm_seconds = out_stats[8];     /* in: seconds to exclude from the rates */
     const double t0 = K273::get_time();
     while (true) {
         const ReadyEvent* ev = sup->poll(n_pred, data);
@@ -445,6 +481,14 @@ extern "C" int gzref_selfplay(void* h, const double* sp_conf, const double* puct
         for (size_t r = 0; r < policies.size(); r++) data.push_back(policies[r].data());
         data.push_back(values.data());
         n_pred = n;
+        if ((n_polls & 15) == 0) {
+            moves_now = mc.count(managers);
+            if (t_warm < 0 && K273::get_time() - t0 >= warm_seconds) {
+                t_warm = K273::get_time();
+                moves_at_warm = moves_now;
+                evals_at_warm = (double)n_evals;
+            }
+        }
         if ((n_polls & 63) == 0) {
             std::vector<Sample*> ss = sup->getSamples();
             for (Sample* s : ss) {
@@ -501,6 +545,11 @@ extern "C" int gzref_selfplay(void* h, const double* sp_conf, const double* puct
     out_stats[5] = (double)n_samples;
     out_stats[6] = (double)games;
     out_stats[7] = plies_sum;
+    moves_now = mc.count(managers);
+    out_stats[8] = moves_now;                                   /* plies played in total */
+    out_stats[9] = t_warm < 0 ? 0 : K273::get_time() - t_warm;  /* measured window (after warm-up) */
+    out_stats[10] = moves_now - moves_at_warm;                  /* plies in the window */
+    out_stats[11] = (double)n_evals - evals_at_warm;            /* evaluations in the window */
     /* Supervisor::~Supervisor does not stop its workers ("for now kill -9", supervisor.cpp:34-40):
        worker threads keep running detached; callers run this in a short-lived process. */
     return 0;
