@@ -37,12 +37,19 @@ extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn);   // gz_
 
 #define PUCT_WARPS_PER_BLOCK 4
 
+// All 32 lanes of a warp run the controller of their game redundantly (identical loads, identical
+// stores), which keeps the warp converged and lets the lanes cooperate where it pays: staging a
+// node's children and their statistics in shared memory (gzp_cache_fill), gathering the policy row
+// (gzp_reply), copying sample records. Atomics are issued by lane 0 only.
 __global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32)
-puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh) {
-    const int g = blockIdx.x * PUCT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (g >= E.G || (threadIdx.x & 31) != 0) return;
-    GameView V = gzp_view(&E, g);
-    gzp_step_pre(V, nullptr, nn_fresh != 0);
+puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_words) {
+    extern __shared__ __align__(16) uint32_t puct_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * PUCT_WARPS_PER_BLOCK + warp;
+    if (g >= E.G) return;
+    uint32_t* cmem = cache_words > 0 ? puct_smem + (size_t)warp * cache_words : nullptr;
+    GameView V = gzp_view(&E, g, lane, cmem);
+    gzp_step_pre(V, nn_fresh != 0);
 }
 
 __global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32)
@@ -145,6 +152,7 @@ struct gz_puct {
     int* d_role_sizes_off = nullptr;
     int mode = 0;
     int total_size = 0;
+    int cache_words = 0;      // per-warp shared-memory words for the child cache (0: use the global scratch)
 };
 
 static void fill_puct_conf(PuctConf& p, const double* c) {
@@ -250,6 +258,15 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     GZ_CUDA(cudaMalloc(&h->d_role_sizes_off, rso.size() * sizeof(int)));
     GZ_CUDA(cudaMemcpy(h->d_role_sizes_off, rso.data(), rso.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->total_size = tr->E.total;
+    {
+        const size_t words = gzp_cache_words(E.max_actions);
+        const size_t bytes = words * 4 * PUCT_WARPS_PER_BLOCK;
+        if (bytes <= 96 * 1024) {
+            h->cache_words = (int)words;
+            if (bytes > 48 * 1024)
+                GZ_CUDA(cudaFuncSetAttribute(puct_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        }
+    }
     puct_init_kernel<<<(E.G + 127) / 128, 128>>>(E, mode);
     GZ_CUDA(cudaGetLastError());
     GZ_CUDA(cudaDeviceSynchronize());
@@ -297,7 +314,8 @@ extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d
     cudaStream_t s = (cudaStream_t)stream;
     const int blocks = (E.G + PUCT_WARPS_PER_BLOCK - 1) / PUCT_WARPS_PER_BLOCK;
     for (int it = 0; it < sub_iters; it++) {
-        puct_pre_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, s>>>(E, (it == 0 && nn_fresh) ? 1 : 0);
+        puct_pre_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, (size_t)h->cache_words * 4 * PUCT_WARPS_PER_BLOCK, s>>>(
+            E, (it == 0 && nn_fresh) ? 1 : 0, h->cache_words);
         GZ_CUDA(cudaGetLastError());
         int rc = gz_sm_transition(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
                                   GZ_GOALS_TERMINAL_ONLY, stream);

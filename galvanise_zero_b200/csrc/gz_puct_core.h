@@ -155,8 +155,7 @@ struct PuctEngine {
     int16_t* x_moves;                           // [G*R]   (-1 = identity / inactive)
     uint8_t *x_term, *x_goals, *x_prevcnt;      // [G], [G*R], [G]
     uint8_t* x_need_eval;                       // [G] 1 when the row of planes is a live request
-    int32_t* x_order;                           // [G*max_actions] child ordering scratch
-    float* x_noise;                             // [G*max_actions] dirichlet scratch
+    uint32_t* x_cache;                          // [G * 12 * max_actions] child staging when it does not fit on chip
     // network outputs, one row per game
     const float* nn_policy;   // [G * policy_stride]  role rows concatenated
     const float* nn_value;    // [G * n_rewards]
@@ -328,18 +327,60 @@ GZP_HDN void gzp_std_sort(int* a, int n, Cmp cmp) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Staging area for the children of ONE node: the child records and the statistics of the nodes they
+// point to. On the device it lives in shared memory (per warp) and is filled cooperatively by the 32
+// lanes, so that the sequential decision logic below reads on-chip data instead of chasing pointers
+// through HBM; on the host build it is plain memory filled by a loop.
+struct ChildCache {
+    int cap;
+    int32_t *to, *move, *flags, *inflight, *order;
+    uint32_t *trav, *visits;
+    float *prob, *prob_orig, *next, *score, *tmp;
+};
+
+static inline size_t gzp_cache_words(int cap) { return (size_t)12 * (size_t)cap; }
+
+GZP_HD void gzp_cache_bind(ChildCache& C, uint32_t* mem, int cap) {
+    C.cap = cap;
+    C.to = (int32_t*)mem; mem += cap;
+    C.move = (int32_t*)mem; mem += cap;
+    C.flags = (int32_t*)mem; mem += cap;
+    C.inflight = (int32_t*)mem; mem += cap;
+    C.order = (int32_t*)mem; mem += cap;
+    C.trav = mem; mem += cap;
+    C.visits = mem; mem += cap;
+    C.prob = (float*)mem; mem += cap;
+    C.prob_orig = (float*)mem; mem += cap;
+    C.next = (float*)mem; mem += cap;
+    C.score = (float*)mem; mem += cap;
+    C.tmp = (float*)mem;
+}
+
 struct GameView {
     const PuctEngine* E;
     int g;
     GameCtl* c;
     int64_t nb, cb;   // node / child base index of the active arena
+    int lane;         // 0..31 on the device (all lanes run the controller redundantly), 0 on the host
+    ChildCache C;
 };
 
-GZP_HD GameView gzp_view(const PuctEngine* E, int g) {
+#ifdef __CUDA_ARCH__
+#define GZP_LANES 32
+#define GZP_SYNC() __syncwarp()
+#else
+#define GZP_LANES 1
+#define GZP_SYNC() ((void)0)
+#endif
+
+GZP_HD GameView gzp_view(const PuctEngine* E, int g, int lane = 0, uint32_t* cache_mem = nullptr) {
     GameView v;
     v.E = E; v.g = g; v.c = &E->ctl[g];
     v.nb = ((int64_t)g * 2 + v.c->arena) * E->NCAP;
     v.cb = ((int64_t)g * 2 + v.c->arena) * E->CCAP;
+    v.lane = lane;
+    if (!cache_mem) cache_mem = E->x_cache + (int64_t)g * gzp_cache_words(E->max_actions);
+    gzp_cache_bind(v.C, cache_mem, E->max_actions);
     return v;
 }
 
@@ -355,6 +396,34 @@ GZP_HD bool gzp_is_terminal(const GameView& V, int n) {
     return (NODE(n_flags, n) & NF_FORCE_TERMINAL) || NODE(n_nchild, n) == 0;
 }
 GZP_HD bool gzp_is_finalised(const GameView& V, int n) { return (NODE(n_flags, n) & NF_FINALISED) != 0; }
+
+// Stage node n's children (and the statistics of their nodes for role `lead`) in the cache.
+GZP_HDN void gzp_cache_fill(GameView& V, int n) {
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n), lead = NODE(n_lead, n);
+    ChildCache& C = V.C;
+    GZP_SYNC();
+    for (int i = V.lane; i < nc; i += GZP_LANES) {
+        const int to = CHILD(c_to, c0 + i);
+        C.to[i] = to;
+        C.move[i] = CHILD(c_move, c0 + i);
+        C.trav[i] = CHILD(c_trav, c0 + i);
+        C.prob[i] = CHILD(c_prob, c0 + i);
+        C.prob_orig[i] = CHILD(c_prob_orig, c0 + i);
+        C.next[i] = CHILD(c_next, c0 + i);
+        if (to >= 0) {
+            C.score[i] = NSCORE(to, lead < 0 ? 0 : lead);
+            C.visits[i] = NODE(n_visits, to);
+            C.flags[i] = NODE(n_flags, to);
+            C.inflight[i] = NODE(n_inflight, to);
+        } else {
+            C.score[i] = -1.0f;
+            C.visits[i] = 0;
+            C.flags[i] = 0;
+            C.inflight[i] = 0;
+        }
+    }
+    GZP_SYNC();
+}
 
 // ------------------------------------------------------------------------------------------------
 // Node creation from the propnet outputs of this game's scratch row (PuctNode::create + createNode).
@@ -468,18 +537,22 @@ GZP_HDN void gzp_reply(GameView& V, int n) {
     const int nc = NODE(n_nchild, n);
     const int c0 = NODE(n_child0, n);
     const float* pol = E->nn_policy + (int64_t)g * E->policy_stride + E->policy_off[lead];
-    float total = 0.0f;
-    for (int i = 0; i < nc; i++) {
-        float p = pol[CHILD(c_move, c0 + i)];
-        p = p > 0.001f ? p : 0.001f;          // std::max(0.001f, p)
-        CHILD(c_prob_orig, c0 + i) = p;
-        total += p;
+    float* stage = V.C.tmp;
+    // gather the raw policy of every child (lanes in parallel), then sum in child order
+    GZP_SYNC();
+    for (int i = V.lane; i < nc; i += GZP_LANES) {
+        const float p = pol[CHILD(c_move, c0 + i)];
+        stage[i] = p > 0.001f ? p : 0.001f;          // std::max(0.001f, p)
     }
-    for (int i = 0; i < nc; i++) {
-        const float p = CHILD(c_prob_orig, c0 + i) / total;
+    GZP_SYNC();
+    float total = 0.0f;
+    for (int i = 0; i < nc; i++) total += stage[i];
+    for (int i = V.lane; i < nc; i += GZP_LANES) {
+        const float p = stage[i] / total;
         CHILD(c_prob_orig, c0 + i) = p;
         CHILD(c_prob, c0 + i) = p;
     }
+    GZP_SYNC();
     const float* val = E->nn_value + (int64_t)g * E->n_rewards;
     for (int r = 0; r < E->R; r++) {
         float s = val[r];
@@ -497,27 +570,24 @@ GZP_HDN void gzp_reply(GameView& V, int n) {
 // ------------------------------------------------------------------------------------------------
 // chooseTopVisits (evaluator.cpp:1100-1159). Sort key: traversals desc, then policy_prob desc
 // (node.cpp:346-373), ordered with the restated std::sort.
+// Expects the cache to hold node n's children (gzp_cache_fill).
 GZP_HDN int gzp_choose_top_visits(const GameView& V, int n) {
     const int nc = NODE(n_nchild, n);
-    const int c0 = NODE(n_child0, n);
-    const int role = NODE(n_lead, n);
     const PuctConf& cf = gzp_conf(V);
-    int* order = V.E->x_order + (int64_t)V.g * V.E->max_actions;
+    const ChildCache& C = V.C;
+    int* order = C.order;
     for (int i = 0; i < nc; i++) order[i] = i;
-    const PuctEngine* E = V.E;
-    const int64_t cb = V.cb + c0;
-    gzp_std_sort(order, nc, [E, cb](int a, int b) {
-        const int ta = (int)E->c_trav[cb + a], tb = (int)E->c_trav[cb + b];
-        if (ta == tb) return E->c_prob[cb + a] > E->c_prob[cb + b];
+    gzp_std_sort(order, nc, [&C](int a, int b) {
+        const int ta = (int)C.trav[a], tb = (int)C.trav[b];
+        if (ta == tb) return C.prob[a] > C.prob[b];
         return ta > tb;
     });
     int indx0 = -1, indx1 = -1;
     int count = 0;
     for (int k = 0; k < nc; k++) {
         const int ci = order[k];
-        const int to = CHILD(c_to, c0 + ci);
-        if (to >= 0 && gzp_is_finalised(V, to)) {
-            const float sc = NSCORE(to, role);
+        if (C.to[ci] >= 0 && (C.flags[ci] & NF_FINALISED)) {
+            const float sc = C.score[ci];
             if (sc > 0.99) return ci;
             if (sc < 0.01) { count++; continue; }
         }
@@ -527,10 +597,9 @@ GZP_HDN int gzp_choose_top_visits(const GameView& V, int n) {
     }
     if (cf.top_visits_best_guess_converge_ratio > 0 && indx0 != -1 && indx1 != -1) {
         const int i0 = order[indx0], i1 = order[indx1];
-        const int t0 = CHILD(c_to, c0 + i0), t1 = CHILD(c_to, c0 + i1);
-        if (t0 >= 0 && t1 >= 0) {
-            if ((float)CHILD(c_trav, c0 + i1) > (float)CHILD(c_trav, c0 + i0) * cf.top_visits_best_guess_converge_ratio &&
-                NSCORE(t1, role) > NSCORE(t0, role))
+        if (C.to[i0] >= 0 && C.to[i1] >= 0) {
+            if ((float)C.trav[i1] > (float)C.trav[i0] * cf.top_visits_best_guess_converge_ratio &&
+                C.score[i1] > C.score[i0])
                 return i1;
             return i0;
         }
@@ -541,21 +610,19 @@ GZP_HDN int gzp_choose_top_visits(const GameView& V, int n) {
 // priorScore (evaluator.cpp:1195-1224)
 GZP_HDN float gzp_prior_score(const GameView& V, int n, int depth) {
     const PuctConf& cf = gzp_conf(V);
+    const ChildCache& C = V.C;
     const int lead = NODE(n_lead, n);
     float prior = NFINAL(n, lead);
     if (NODE(n_visits, n) > 8) {
         const int best = gzp_choose_top_visits(V, n);
-        const int to = CHILD(c_to, NODE(n_child0, n) + best);
-        if (to >= 0) prior = NSCORE(to, lead);
+        if (C.to[best] >= 0) prior = C.score[best];
     }
     float fpu = depth == 0 ? cf.fpu_prior_discount_root : cf.fpu_prior_discount;
     if (fpu > 0) {
         float total = 0.0f;
-        const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
-        for (int i = 0; i < nc; i++) {
-            const int to = CHILD(c_to, c0 + i);
-            if (to >= 0 && NODE(n_visits, to) > 0) total += CHILD(c_prob, c0 + i);
-        }
+        const int nc = NODE(n_nchild, n);
+        for (int i = 0; i < nc; i++)
+            if (C.to[i] >= 0 && C.visits[i] > 0) total += C.prob[i];
         fpu *= sqrtf(total);
         prior -= fpu;
     }
@@ -589,7 +656,8 @@ GZP_HDN float gzp_gamma(uint64_t* rng, float alpha) {
 }
 
 // setDirichletNoise (evaluator.cpp:1227-1297)
-GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n, float* scratch /* >= nchild floats */) {
+GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n) {
+    float* scratch = V.C.tmp;
     const PuctConf& cf = gzp_conf(V);
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
     if ((NODE(n_flags, n) & NF_NOISE_SET) || nc < 2 || cf.dirichlet_noise_pct < 0) return;
@@ -613,15 +681,17 @@ GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n, float* scratch /* >= nc
         CHILD(c_prob, c0 + i) = p;
         total_policy += p;
     }
-    for (int i = 0; i < nc; i++) CHILD(c_prob, c0 + i) /= total_policy;
+    for (int i = 0; i < nc; i++) {
+        const float p = CHILD(c_prob, c0 + i) / total_policy;
+        CHILD(c_prob, c0 + i) = p;
+        V.C.prob[i] = p;     // keep the staged copy current
+    }
     NODE(n_flags, n) |= NF_NOISE_SET;
 }
 
 // selectChild (evaluator.cpp:341-517). Appends to the path; returns the child index within the
 // node (or -1 when nothing is selectable, which cannot happen with one evaluation in flight).
-GZP_HDN int gzp_select_child(GameView& V, int n, float* scratch_unused) {
-    float* scratch = V.E->x_noise + (int64_t)V.g * V.E->max_actions;
-    (void)scratch_unused;
+GZP_HDN int gzp_select_child(GameView& V, int n) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     const PuctConf& cf = gzp_conf(V);
@@ -644,7 +714,9 @@ GZP_HDN int gzp_select_child(GameView& V, int n, float* scratch_unused) {
         pn[c->path_len] = n; pc[c->path_len] = 0; c->path_len++;
         return 0;
     }
-    if (depth == 0) gzp_set_dirichlet_noise(V, n, scratch);
+    gzp_cache_fill(V, n);
+    ChildCache& C = V.C;
+    if (depth == 0) gzp_set_dirichlet_noise(V, n);
 
     const float prior_score = gzp_prior_score(V, n, depth);
     const double sqrt_node_visits = sqrt((double)(NODE(n_visits, n) + 1u));
@@ -661,30 +733,24 @@ GZP_HDN int gzp_select_child(GameView& V, int n, float* scratch_unused) {
 
     // iterate children in sortedChildrenSelect order (evaluator.cpp:242-263): key sa = node score
     // for the lead role (-1 when unexpanded); both negative -> policy_prob_orig desc, else sa desc.
-    int* order = E->x_order + (int64_t)V.g * E->max_actions;
+    int* order = C.order;
     for (int i = 0; i < nc; i++) order[i] = i;
-    {
-        const int64_t cb = V.cb + c0;
-        const int64_t nb = V.nb;
-        gzp_std_sort(order, nc, [E, cb, nb, lead](int a, int b) {
-            const int ta = E->c_to[cb + a], tb = E->c_to[cb + b];
-            const float sa = ta < 0 ? -1.0f : E->n_score[(nb + ta) * GZP_MAX_ROLES + lead];
-            const float sb = tb < 0 ? -1.0f : E->n_score[(nb + tb) * GZP_MAX_ROLES + lead];
-            if (sa < 0 && sb < 0) return E->c_prob_orig[cb + a] > E->c_prob_orig[cb + b];
-            return sa > sb;
-        });
-    }
+    gzp_std_sort(order, nc, [&C](int a, int b) {
+        const float sa = C.score[a], sb = C.score[b];     // -1 when unexpanded
+        if (sa < 0 && sb < 0) return C.prob_orig[a] > C.prob_orig[b];
+        return sa > sb;
+    });
     for (int rank = 0; rank < nc; rank++) {
         const int pick = order[rank];
-        const int ci = c0 + pick;
-        const int to = CHILD(c_to, ci);
+        const int to = C.to[pick];
+        const uint32_t ctrav = C.trav[pick];
         double child_score = prior_score;
-        const int traversals = (int)CHILD(c_trav, ci) + 1;
-        const double inflight = to >= 0 ? (double)NODE(n_inflight, to) : 0.0;
-        double exploration = (double)(puct_c * CHILD(c_prob, ci)) * sqrt_node_visits / (traversals + inflight);
+        const int traversals = (int)ctrav + 1;
+        const double inflight = to >= 0 ? (double)C.inflight[pick] : 0.0;
+        double exploration = (double)(puct_c * C.prob[pick]) * sqrt_node_visits / (traversals + inflight);
         if (to >= 0) {
-            child_score = NSCORE(to, lead);
-            const bool fin = gzp_is_finalised(V, to);
+            child_score = C.score[pick];
+            const bool fin = (C.flags[pick] & NF_FINALISED) != 0;
             if (fin) {
                 if (child_score > 0.99) {
                     if (depth > 0) {
@@ -699,19 +765,19 @@ GZP_HDN int gzp_select_child(GameView& V, int n, float* scratch_unused) {
                     exploration = 0.0;
                 }
             }
-            if ((fin || NODE(n_visits, to) > 42) && child_score > best_child_score_actual) {
+            if ((fin || C.visits[pick] > 42) && child_score > best_child_score_actual) {
                 best_child_score_actual = (float)child_score;
                 best_child_score = pick;
             }
         }
-        if (CHILD(c_trav, ci) > 0 && inflight > 0) {
+        if (ctrav > 0 && inflight > 0) {
             const double discounted = inflight * (gzp_rng_get(c->rng_eval) + 0.5);
-            child_score = (child_score * CHILD(c_trav, ci)) / (CHILD(c_trav, ci) + discounted);
+            child_score = (child_score * ctrav) / (ctrav + discounted);
         }
         const float limit_latch_root = 0.66f;
         const double score = child_score + exploration;
         if (node_visits > 1000 && node_visits < 40000000 && depth == 0 && gzp_rng_get(c->rng_eval) > 0.1) {
-            if (CHILD(c_trav, ci) > 16 && CHILD(c_trav, ci) > node_visits * limit_latch_root) {
+            if (ctrav > 16 && ctrav > node_visits * limit_latch_root) {
                 if (best_fallback < 0 || score > best_fallback_score) {
                     best_fallback = pick;
                     best_fallback_score = (float)score;
@@ -816,25 +882,22 @@ GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
 
 // converged (evaluator.cpp:1342-1362); sortedChildren = by visits of the child node desc, ties by
 // policy_prob desc (node.cpp:312-343), unexpanded children count as 0 visits.
-GZP_HDN bool gzp_converged(const GameView& V, int count) {
+GZP_HDN bool gzp_converged(GameView& V, int count) {
     const int n = V.c->root;
-    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+    const int nc = NODE(n_nchild, n);
     if (nc < 2) return true;
-    const PuctEngine* E = V.E;
-    int* order = E->x_order + (int64_t)V.g * E->max_actions;
+    gzp_cache_fill(V, n);
+    const ChildCache& C = V.C;
+    int* order = C.order;
     for (int i = 0; i < nc; i++) order[i] = i;
-    const int64_t cb = V.cb + c0, nb = V.nb;
-    gzp_std_sort(order, nc, [E, cb, nb](int a, int b) {
-        const int ta = E->c_to[cb + a], tb = E->c_to[cb + b];
-        const int va = ta < 0 ? 0 : (int)E->n_visits[nb + ta];
-        const int vb = tb < 0 ? 0 : (int)E->n_visits[nb + tb];
-        if (va == vb) return E->c_prob[cb + a] > E->c_prob[cb + b];
+    gzp_std_sort(order, nc, [&C](int a, int b) {
+        const int va = (int)C.visits[a], vb = (int)C.visits[b];     // 0 when unexpanded
+        if (va == vb) return C.prob[a] > C.prob[b];
         return va > vb;
     });
-    const int n0 = CHILD(c_to, c0 + order[0]), n1 = CHILD(c_to, c0 + order[1]);
-    if (n0 >= 0 && n1 >= 0) {
-        const int role = NODE(n_lead, n);
-        if (NSCORE(n0, role) > NSCORE(n1, role) && NODE(n_visits, n0) > NODE(n_visits, n1) + (uint32_t)count) return true;
+    const int a = order[0], b = order[1];
+    if (C.to[a] >= 0 && C.to[b] >= 0) {
+        if (C.score[a] > C.score[b] && C.visits[a] > C.visits[b] + (uint32_t)count) return true;
     }
     return false;
 }
@@ -867,25 +930,23 @@ GZP_HDN void gzp_get_probabilities(GameView& V, int n, float temperature, bool u
 GZP_HDN int gzp_choose_temperature(GameView& V, int n) {
     const PuctConf& cf = gzp_conf(V);
     const float temperature = gzp_temperature(cf, NODE(n_depth, n));
-    if (temperature < 0) return gzp_choose_top_visits(V, n);
+    if (temperature < 0) { gzp_cache_fill(V, n); return gzp_choose_top_visits(V, n); }
     const int root = V.c->root;
     gzp_get_probabilities(V, root, temperature, cf.dirichlet_noise_pct < 0 && NODE(n_visits, n) < 3);
     const float expected = (float)(gzp_rng_get(V.c->rng_eval) * cf.random_scale);
-    const int nc = NODE(n_nchild, root), c0 = NODE(n_child0, root);
-    const PuctEngine* E = V.E;
-    int* order = E->x_order + (int64_t)V.g * E->max_actions;
+    const int nc = NODE(n_nchild, root);
+    gzp_cache_fill(V, root);
+    const ChildCache& C = V.C;
+    int* order = C.order;
     for (int i = 0; i < nc; i++) order[i] = i;
-    const int64_t cb = V.cb + c0, nb = V.nb;
-    gzp_std_sort(order, nc, [E, cb, nb](int a, int b) {
-        const int ta = E->c_to[cb + a], tb = E->c_to[cb + b];
-        const int va = ta < 0 ? 0 : (int)E->n_visits[nb + ta];
-        const int vb = tb < 0 ? 0 : (int)E->n_visits[nb + tb];
-        if (va == vb) return E->c_next[cb + a] > E->c_next[cb + b];
+    gzp_std_sort(order, nc, [&C](int a, int b) {
+        const int va = (int)C.visits[a], vb = (int)C.visits[b];
+        if (va == vb) return C.next[a] > C.next[b];
         return va > vb;
     });
     float seen = 0;
     for (int k = 0; k < nc; k++) {
-        seen += CHILD(c_next, c0 + order[k]);
+        seen += C.next[order[k]];
         if (seen > expected) return order[k];
     }
     return order[nc - 1];
@@ -893,7 +954,9 @@ GZP_HDN int gzp_choose_temperature(GameView& V, int n) {
 
 GZP_HDN int gzp_choose(GameView& V, int n) {
     const PuctConf& cf = gzp_conf(V);
-    return cf.choose == 1 ? gzp_choose_temperature(V, n) : gzp_choose_top_visits(V, n);
+    if (cf.choose == 1) return gzp_choose_temperature(V, n);
+    gzp_cache_fill(V, n);
+    return gzp_choose_top_visits(V, n);
 }
 
 // resetRootNode (evaluator.cpp:1019-1030)
@@ -919,7 +982,8 @@ GZP_HDN uint64_t gzp_state_hash(const PuctEngine* E, const uint32_t* st) {
     return h ? h : 1;
 }
 
-GZP_HDN int gzp_uniq_find(const PuctEngine* E, uint64_t key, bool insert) {
+GZP_HDN int gzp_uniq_find(const PuctEngine* E, uint64_t key, bool insert, int lane) {
+    (void)lane;
     if (!E->uniq_cap) return -1;
     uint32_t pos = (uint32_t)(key & (uint64_t)(E->uniq_cap - 1));
     for (int probe = 0; probe < 64; probe++) {
@@ -928,7 +992,9 @@ GZP_HDN int gzp_uniq_find(const PuctEngine* E, uint64_t key, bool insert) {
         if (cur == 0ULL) {
             if (!insert) return -1;
 #ifdef __CUDA_ARCH__
-            const unsigned long long prev = atomicCAS(&E->uniq_keys[pos], 0ULL, (unsigned long long)key);
+            unsigned long long prev = 0ULL;
+            if (lane == 0) prev = atomicCAS(&E->uniq_keys[pos], 0ULL, (unsigned long long)key);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
             if (prev == 0ULL || prev == key) return (int)pos;
 #else
             E->uniq_keys[pos] = key;
@@ -940,8 +1006,8 @@ GZP_HDN int gzp_uniq_find(const PuctEngine* E, uint64_t key, bool insert) {
     return -1;
 }
 
-GZP_HDN bool gzp_is_unique(const PuctEngine* E, const uint32_t* st, int depth) {
-    const int pos = gzp_uniq_find(E, gzp_state_hash(E, st), false);
+GZP_HDN bool gzp_is_unique(const PuctEngine* E, const uint32_t* st, int depth, int lane) {
+    const int pos = gzp_uniq_find(E, gzp_state_hash(E, st), false, lane);
     if (pos < 0) return true;
     const int max_num_dupes = 1000;
     int allowed = max_num_dupes - 5 * depth;
@@ -949,11 +1015,12 @@ GZP_HDN bool gzp_is_unique(const PuctEngine* E, const uint32_t* st, int depth) {
     return E->uniq_counts[pos] < allowed;
 }
 
-GZP_HDN void gzp_uniq_add(const PuctEngine* E, const uint32_t* st) {
-    const int pos = gzp_uniq_find(E, gzp_state_hash(E, st), true);
+GZP_HDN void gzp_uniq_add(const PuctEngine* E, const uint32_t* st, int lane) {
+    const int pos = gzp_uniq_find(E, gzp_state_hash(E, st), true, lane);
     if (pos < 0) return;
 #ifdef __CUDA_ARCH__
-    if (E->uniq_counts[pos] < 1000) atomicAdd(&E->uniq_counts[pos], 1);
+    if (lane == 0 && E->uniq_counts[pos] < 1000) atomicAdd(&E->uniq_counts[pos], 1);
+    __syncwarp();
 #else
     if (E->uniq_counts[pos] < 1000) E->uniq_counts[pos]++;
 #endif
@@ -1023,14 +1090,18 @@ GZP_HDN void gzp_add_samples(GameView& V, const float* final_scores, int game_de
         rec[SR_START_DEPTH] = c->starting_sample_depth;
         rec[SR_READY] = 1;
 #ifdef __CUDA_ARCH__
-        const unsigned long long slot = atomicAdd(E->ready_count, 1ULL);
+        unsigned long long slot = 0ULL;
+        __syncwarp();
+        if (V.lane == 0) slot = atomicAdd(E->ready_count, 1ULL);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
 #else
         const unsigned long long slot = (*E->ready_count)++;
 #endif
         if (slot < (unsigned long long)E->READYCAP) {
             int32_t* dst = E->ready + (int64_t)slot * E->srec;
-            for (int w = 0; w < E->srec; w++) dst[w] = rec[w];
+            for (int w = V.lane; w < E->srec; w += GZP_LANES) dst[w] = rec[w];
         }
+        GZP_SYNC();
         c->total_samples++;
     }
     c->n_samples = 0;
@@ -1182,7 +1253,7 @@ GZP_HDN void gzp_path_push(GameView& V, int n, int choice) {
 }
 
 // treePlayout (evaluator.cpp:658-720), resumable. Returns true when blocked on an expansion.
-GZP_HDN bool gzp_playout_continue(GameView& V, float* scratch) {
+GZP_HDN bool gzp_playout_continue(GameView& V) {
     GameCtl* c = V.c;
     while (true) {
         const int cur = c->cur;
@@ -1191,7 +1262,7 @@ GZP_HDN bool gzp_playout_continue(GameView& V, float* scratch) {
             gzp_finish_playout(V, cur);
             return false;
         }
-        const int child = gzp_select_child(V, cur, scratch);
+        const int child = gzp_select_child(V, cur);
         if (child < 0 || c->error) { c->error = c->error ? c->error : GZP_ERR_PATH; return true; }
         const int ci = NODE(n_child0, cur) + child;
         if (CHILD(c_to, ci) < 0) {
@@ -1238,7 +1309,7 @@ GZP_HDN void gzp_begin_game(GameView& V) {
 
 // Returns when the game is blocked on the pipeline (c->req != REQ_NONE or c->eval_node >= 0),
 // idle, halted, or the per-step iteration budget is spent.
-GZP_HDN void gzp_step_pre(GameView& V, float* scratch, bool nn_fresh = true) {
+GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     if (c->phase == PH_HALT) return;
@@ -1294,14 +1365,14 @@ GZP_HDN void gzp_step_pre(GameView& V, float* scratch, bool nn_fresh = true) {
             if (!stop && gzp_is_terminal(V, node)) stop = true;
             if (stop) { c->phase = PH_GAME_END; c->in_run_to_end = 0; break; }
             bool do_skip = false;
-            if (!gzp_is_unique(E, NSTATE(node), NODE(n_depth, node))) {
+            if (!gzp_is_unique(E, NSTATE(node), NODE(n_depth, node), V.lane)) {
                 c->saw_dupes++;
                 do_skip = true;
             } else if (E->conf.oscillate_sampling_pct > 0 && gzp_rng_get(c->rng_sp) > E->conf.oscillate_sampling_pct) {
                 do_skip = true;
             }
             if (!do_skip) {
-                gzp_uniq_add(E, NSTATE(node));
+                gzp_uniq_add(E, NSTATE(node), V.lane);
                 gzp_reset_root_node(V);
                 c->do_sample = 1;
                 gzp_start_search(V, E->conf.evals_per_move, 0);
@@ -1335,7 +1406,7 @@ GZP_HDN void gzp_step_pre(GameView& V, float* scratch, bool nn_fresh = true) {
                 c->path_len = 0;
                 c->in_playout = 1;
             }
-            if (gzp_playout_continue(V, scratch)) return;
+            if (gzp_playout_continue(V)) return;
             break;
         }
         case PH_MOVE_DONE: {

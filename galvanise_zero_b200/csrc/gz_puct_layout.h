@@ -52,8 +52,7 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     E->x_goals = (uint8_t*)take(G * E->R);
     E->x_prevcnt = (uint8_t*)take(G);
     E->x_need_eval = (uint8_t*)take(G);
-    E->x_order = (int32_t*)take(G * (size_t)E->max_actions * 4);
-    E->x_noise = (float*)take(G * (size_t)E->max_actions * 4);
+    E->x_cache = (uint32_t*)take(G * gzp_cache_words(E->max_actions) * 4);
     E->pend = (int32_t*)take(G * E->MAXPEND * (size_t)E->srec * 4);
     E->ready = (int32_t*)take((size_t)E->READYCAP * E->srec * 4);
     E->ready_count = (unsigned long long*)take(8);

@@ -20,6 +20,7 @@ class SelfPlayRunner(object):
         self.graph = None
         self.steps_done = 0
         e = engine
+        torch.backends.cudnn.benchmark = True
         self._planes_cl = None
         with torch.no_grad():
             # first step: nothing to feed back yet

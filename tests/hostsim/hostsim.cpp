@@ -151,10 +151,9 @@ extern "C" void hs_destroy(void* h) {
 extern "C" void hs_step(void* h) {
     HostSim* H = (HostSim*)h;
     PuctEngine& E = H->E;
-    std::vector<float> scratch(E.max_actions + 8);
     for (int g = 0; g < E.G; g++) {
         GameView V = gzp_view(&E, g);
-        gzp_step_pre(V, scratch.data());
+        gzp_step_pre(V);
     }
     for (int g = 0; g < E.G; g++) {
         GameCtl& c = E.ctl[g];
