@@ -338,7 +338,7 @@ struct ChildCache {
     float *prob, *prob_orig, *next, *score, *tmp;
 };
 
-static inline size_t gzp_cache_words(int cap) { return (size_t)12 * (size_t)cap; }
+GZP_HD size_t gzp_cache_words(int cap) { return (size_t)12 * (size_t)cap; }
 
 GZP_HD void gzp_cache_bind(ChildCache& C, uint32_t* mem, int cap) {
     C.cap = cap;

@@ -179,15 +179,16 @@ class Supervisor(object):
         else:
             if n_predictions != len(self._rows):
                 raise GGPZeroInterfaceError('expected %d predictions, got %d' % (len(self._rows), n_predictions))
-            for a in arrays:
+            for a in (arrays if n_predictions else []):
                 if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
                     raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
-            R = len(e.role_sizes)
-            pol = np.concatenate([arrays[r].reshape(n_predictions, e.role_sizes[r]) for r in range(R)], axis=1)
-            val = arrays[R].reshape(n_predictions, e.n_rewards)
-            rows = self._rows_dev
-            e.policy[rows] = torch.from_numpy(pol).to(e.device, non_blocking=True)
-            e.value[rows] = torch.from_numpy(val).to(e.device, non_blocking=True)
+            if n_predictions:
+                R = len(e.role_sizes)
+                pol = np.concatenate([arrays[r].reshape(n_predictions, e.role_sizes[r]) for r in range(R)], axis=1)
+                val = arrays[R].reshape(n_predictions, e.n_rewards)
+                rows = self._rows_dev
+                e.policy[rows] = torch.from_numpy(pol).to(e.device, non_blocking=True)
+                e.value[rows] = torch.from_numpy(val).to(e.device, non_blocking=True)
             e.advance(e.policy, e.value)
         need = self._need_eval()
         rows = torch.nonzero(need, as_tuple=False).flatten()
