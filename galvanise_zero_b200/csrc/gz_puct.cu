@@ -41,7 +41,7 @@ extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn);   // gz_
 // stores), which keeps the warp converged and lets the lanes cooperate where it pays: staging a
 // node's children and their statistics in shared memory (gzp_cache_fill), gathering the policy row
 // (gzp_reply), copying sample records. Atomics are issued by lane 0 only.
-__global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32, 8)
 puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_words) {
     extern __shared__ __align__(16) uint32_t puct_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

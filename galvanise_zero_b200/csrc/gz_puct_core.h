@@ -567,6 +567,34 @@ GZP_HDN void gzp_reply(GameView& V, int n) {
     }
 }
 
+
+// Orders the staged children into C.order exactly as the reference's std::sort call would. For
+// n <= 16 libstdc++'s std::sort is a plain (stable) insertion sort and all comparators used here are
+// strict weak orders, so on the device every lane computes the final rank of one child directly;
+// larger nodes go through the restated introsort.
+template <typename Cmp>
+GZP_HDN void gzp_order_children(GameView& V, int nc, Cmp cmp) {
+    int* order = V.C.order;
+#ifdef __CUDA_ARCH__
+    if (nc <= 16) {
+        __syncwarp();
+        if (V.lane < nc) {
+            const int i = V.lane;
+            int rank = 0;
+            for (int j = 0; j < nc; j++) {
+                if (j == i) continue;
+                if (cmp(j, i) || (!cmp(i, j) && j < i)) rank++;
+            }
+            order[rank] = i;
+        }
+        __syncwarp();
+        return;
+    }
+#endif
+    for (int i = 0; i < nc; i++) order[i] = i;
+    gzp_std_sort(order, nc, cmp);
+}
+
 // ------------------------------------------------------------------------------------------------
 // chooseTopVisits (evaluator.cpp:1100-1159). Sort key: traversals desc, then policy_prob desc
 // (node.cpp:346-373), ordered with the restated std::sort.
@@ -576,8 +604,7 @@ GZP_HDN int gzp_choose_top_visits(const GameView& V, int n) {
     const PuctConf& cf = gzp_conf(V);
     const ChildCache& C = V.C;
     int* order = C.order;
-    for (int i = 0; i < nc; i++) order[i] = i;
-    gzp_std_sort(order, nc, [&C](int a, int b) {
+    gzp_order_children(const_cast<GameView&>(V), nc, [&C](int a, int b) {
         const int ta = (int)C.trav[a], tb = (int)C.trav[b];
         if (ta == tb) return C.prob[a] > C.prob[b];
         return ta > tb;
@@ -734,8 +761,7 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
     // iterate children in sortedChildrenSelect order (evaluator.cpp:242-263): key sa = node score
     // for the lead role (-1 when unexpanded); both negative -> policy_prob_orig desc, else sa desc.
     int* order = C.order;
-    for (int i = 0; i < nc; i++) order[i] = i;
-    gzp_std_sort(order, nc, [&C](int a, int b) {
+    gzp_order_children(V, nc, [&C](int a, int b) {
         const float sa = C.score[a], sb = C.score[b];     // -1 when unexpanded
         if (sa < 0 && sb < 0) return C.prob_orig[a] > C.prob_orig[b];
         return sa > sb;
@@ -889,8 +915,7 @@ GZP_HDN bool gzp_converged(GameView& V, int count) {
     gzp_cache_fill(V, n);
     const ChildCache& C = V.C;
     int* order = C.order;
-    for (int i = 0; i < nc; i++) order[i] = i;
-    gzp_std_sort(order, nc, [&C](int a, int b) {
+    gzp_order_children(V, nc, [&C](int a, int b) {
         const int va = (int)C.visits[a], vb = (int)C.visits[b];     // 0 when unexpanded
         if (va == vb) return C.prob[a] > C.prob[b];
         return va > vb;
@@ -938,8 +963,7 @@ GZP_HDN int gzp_choose_temperature(GameView& V, int n) {
     gzp_cache_fill(V, root);
     const ChildCache& C = V.C;
     int* order = C.order;
-    for (int i = 0; i < nc; i++) order[i] = i;
-    gzp_std_sort(order, nc, [&C](int a, int b) {
+    gzp_order_children(V, nc, [&C](int a, int b) {
         const int va = (int)C.visits[a], vb = (int)C.visits[b];
         if (va == vb) return C.next[a] > C.next[b];
         return va > vb;
