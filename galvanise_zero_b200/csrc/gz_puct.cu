@@ -1,10 +1,11 @@
 // gz_puct.cu — batched PUCT self-play engine on the device.
 //
-// G independent game trees live in SoA node / child arenas in HBM (gz_puct_core.h, two arenas per
-// game for re-rooting). One engine step ("advance") is a fixed sequence of launches on one stream:
+// G independent game trees live in SoA node / child arenas in HBM (gz_puct_core.h; re-rooting
+// compacts a game's arena in place). One engine step ("advance") is a fixed sequence of launches on one stream:
 //
 //   puct_pre_kernel    one warp per game: consume the network's answer (reply + backup), run the
 //                      self-play controller and select down the tree until the game needs a new node
+//   puct_reroot_kernel one CTA per game that just played a move: in-place compaction of the kept subtree
 //   pn_kernel          (gz_propnet.cu) next state, legal masks, terminal, goals for every request
 //   puct_post_kernel   one warp per game: create the node (children from the legal mask)
 //   [repeat the three launches `sub_iters` times for games that did not need the network]
@@ -58,6 +59,49 @@ puct_post_kernel(const __grid_constant__ PuctEngine E) {
     if (g >= E.G || (threadIdx.x & 31) != 0) return;
     GameView V = gzp_view(&E, g);
     gzp_step_post(V);
+}
+
+
+// Re-rooting: one CTA per game that asked for it (a handful per step); in-place parallel
+// mark-compact of the kept subtree (gzp_reroot_compact).
+#define REROOT_THREADS 256
+struct GzpCta {
+    int* sm;   // [2 * (REROOT_THREADS / 32)]
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void scan2(int a, int b, int& ea, int& eb, int& ta, int& tb) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        int ia = a, ib = b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int xa = __shfl_up_sync(0xffffffffu, ia, d), xb = __shfl_up_sync(0xffffffffu, ib, d);
+            if (lane >= d) { ia += xa; ib += xb; }
+        }
+        if (lane == 31) { sm[warp] = ia; sm[nw + warp] = ib; }
+        __syncthreads();
+        int pa = 0, pb = 0, sa = 0, sb = 0;
+        for (int w = 0; w < nw; w++) {
+            const int va = sm[w], vb = sm[nw + w];
+            if (w < warp) { pa += va; pb += vb; }
+            sa += va; sb += vb;
+        }
+        ea = pa + ia - a; eb = pb + ib - b; ta = sa; tb = sb;
+        __syncthreads();
+    }
+};
+
+__global__ void __launch_bounds__(REROOT_THREADS)
+puct_reroot_kernel(const __grid_constant__ PuctEngine E) {
+    __shared__ int scan_sm[2 * (REROOT_THREADS / 32)];
+    const int g = blockIdx.x;
+    GameCtl& c = E.ctl[g];
+    if (c.req != REQ_REROOT) return;
+    GameView V = gzp_view(&E, g);
+    GzpCta grp;
+    grp.sm = scan_sm;
+    const int new_root = c.req_parent;
+    __syncthreads();
+    gzp_reroot_compact(V, new_root, (int)threadIdx.x, (int)blockDim.x, grp);
+    if (threadIdx.x == 0) c.req = REQ_NONE;
 }
 
 __global__ void puct_init_kernel(const __grid_constant__ PuctEngine E, int mode) {
@@ -316,6 +360,8 @@ extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d
     for (int it = 0; it < sub_iters; it++) {
         puct_pre_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, (size_t)h->cache_words * 4 * PUCT_WARPS_PER_BLOCK, s>>>(
             E, (it == 0 && nn_fresh) ? 1 : 0, h->cache_words);
+        GZ_CUDA(cudaGetLastError());
+        puct_reroot_kernel<<<E.G, REROOT_THREADS, 0, s>>>(E);
         GZ_CUDA(cudaGetLastError());
         int rc = gz_sm_transition(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
                                   GZ_GOALS_TERMINAL_ONLY, stream);

@@ -53,7 +53,7 @@ enum {
 };
 
 // ---- requests to the batch pipeline
-enum { REQ_NONE = 0, REQ_EXPAND = 1, REQ_ROOT = 2 };
+enum { REQ_NONE = 0, REQ_EXPAND = 1, REQ_ROOT = 2, REQ_REROOT = 3 };
 enum { PUR_PLAYOUT = 0, PUR_REROOT = 1, PUR_ROOT = 2 };
 
 // ---- node flags
@@ -135,15 +135,16 @@ struct PuctEngine {
     int legal_word_off[GZP_MAX_ROLES + 1];
     int policy_off[GZP_MAX_ROLES];      // offset of role r's policy row inside a concatenated row
     int policy_stride;                  // sum of role sizes
-    // node arrays, two arenas per game: index = (g*2 + arena)*NCAP + n
+    // node arrays: index = g*NCAP + n (nodes of a game are in creation order: parent < child)
     int32_t *n_parent, *n_child0, *n_nchild, *n_inflight, *n_flags, *n_lead, *n_depth;
     uint32_t* n_visits;
     float *n_score, *n_final;           // [.. * GZP_MAX_ROLES]
     float* n_puct;
     uint32_t* n_state;                  // [.. * SW]
     int32_t* n_other;                   // [.. * GZP_MAX_ROLES] every role's only action (non-lead roles)
-    // child arrays: index = (g*2 + arena)*CCAP + c
-    int32_t *c_to, *c_move;
+    // child arrays: index = g*CCAP + c (blocks in the creation order of their nodes)
+    int32_t *c_to, *c_move, *c_owner;           // c_owner: node the child record belongs to
+    int32_t *n_newidx, *n_newc0;                // re-root scratch: new node index / new child0
     uint32_t* c_trav;
     float *c_prob, *c_prob_orig, *c_next;
     // per game
@@ -376,8 +377,8 @@ struct GameView {
 GZP_HD GameView gzp_view(const PuctEngine* E, int g, int lane = 0, uint32_t* cache_mem = nullptr) {
     GameView v;
     v.E = E; v.g = g; v.c = &E->ctl[g];
-    v.nb = ((int64_t)g * 2 + v.c->arena) * E->NCAP;
-    v.cb = ((int64_t)g * 2 + v.c->arena) * E->CCAP;
+    v.nb = (int64_t)g * E->NCAP;
+    v.cb = (int64_t)g * E->CCAP;
     v.lane = lane;
     if (!cache_mem) cache_mem = E->x_cache + (int64_t)g * gzp_cache_words(E->max_actions);
     gzp_cache_bind(v.C, cache_mem, E->max_actions);
@@ -507,6 +508,7 @@ GZP_HDN int gzp_create_node(GameView& V, int parent, int depth) {
                 x &= x - 1;
                 const int ci = c0 + k++;
                 CHILD(c_to, ci) = -1;
+                CHILD(c_owner, ci) = n;
                 CHILD(c_trav, ci) = 0;
                 CHILD(c_prob_orig, ci) = 1.0f;
                 CHILD(c_prob, ci) = 1.0f;
@@ -1149,75 +1151,153 @@ GZP_HDN bool gzp_resign(GameView& V, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Re-rooting: copy the subtree under `new_root` into the other arena in BFS order (replaces
-// fastApplyMove's ref-count release of the sibling subtrees, evaluator.cpp:888-943).
-GZP_HDN void gzp_reroot(GameView& V, int new_root) {
+// Re-rooting (replaces fastApplyMove's ref-count release of the sibling subtrees,
+// evaluator.cpp:888-943): the subtree under `new_root` is compacted IN PLACE to the front of the
+// game's arenas. Nodes are stored in creation order, so parent index < child index, new index <= old
+// index, and child blocks keep their relative order: both arrays can be compacted left to right.
+// The work is written for a cooperating group of `T` threads (`tid` in [0,T), `sync()` a group
+// barrier, `scan()` an exclusive group prefix sum that also returns the total): a whole CTA on the
+// device (puct_reroot_kernel), a single thread on the host build.
+struct GzpSeq {   // trivial group of one thread
+    int total_a, total_b;
+    GZP_HD void sync() {}
+    GZP_HD void scan2(int a, int b, int& ea, int& eb, int& ta, int& tb) { ea = 0; eb = 0; ta = a; tb = b; }
+};
+
+template <typename Group>
+GZP_HDN void gzp_reroot_compact(GameView& V, int new_root, int tid, int T, Group& grp) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
-    const int64_t onb = V.nb, ocb = V.cb;
-    const int na = c->arena ^ 1;
-    const int64_t nnb = ((int64_t)V.g * 2 + na) * E->NCAP;
-    const int64_t ncb = ((int64_t)V.g * 2 + na) * E->CCAP;
-    // keep the state of the old root for sample prev_states
+    const int64_t nb = V.nb, cb = V.cb;
+    const int N = c->n_nodes, NC = c->n_children;
+    const int r = new_root;
+    // keep the state of the old root: it is the previous state of the new root (samples, encoder)
     {
-        const int old_root = c->root;
         uint32_t* ps = E->root_prev_state + (int64_t)V.g * E->SW;
-        const uint32_t* st = E->n_state + (onb + old_root) * E->SW;
-        for (int w = 0; w < E->SW; w++) ps[w] = st[w];
+        const uint32_t* st = E->n_state + (nb + c->root) * E->SW;
+        for (int w = tid; w < E->SW; w += T) ps[w] = st[w];
+    }
+    // ---- pass 1: reachability + new indices, chunk by chunk in index order
+    int node_base = 0, child_base = 0;
+    for (int b = 0; b < N; b += T) {
+        const int i = b + tid;
+        int reach = 0, nch = 0;
+        if (i < N) {
+            int q = i;
+            while (q > r && q >= b) q = E->n_parent[nb + q];
+            if (q == r) reach = 1;
+            else if (q > r) reach = E->n_newidx[nb + q] >= 0;     // q < b: decided by an earlier chunk
+            if (reach) nch = E->n_nchild[nb + i];
+        }
+        int en, ec, tn, tc;
+        grp.scan2(reach, nch, en, ec, tn, tc);
+        if (i < N) {
+            E->n_newidx[nb + i] = reach ? node_base + en : -1;
+            E->n_newc0[nb + i] = reach ? child_base + ec : -1;
+        }
+        node_base += tn;
+        child_base += tc;
+        grp.sync();
+    }
+    // ---- pass 2: children, in place, left to right (new position <= old position)
+    for (int b = 0; b < NC; b += T) {
+        const int k = b + tid;
+        int dst = -1, to = -1, mv = 0, own = 0;
+        uint32_t tr = 0;
+        float p = 0, po = 0, nx = 0;
+        if (k < NC) {
+            const int o = E->c_owner[cb + k];
+            const int no = E->n_newidx[nb + o];
+            if (no >= 0) {
+                dst = E->n_newc0[nb + o] + (k - E->n_child0[nb + o]);
+                const int t0 = E->c_to[cb + k];
+                to = t0 >= 0 ? E->n_newidx[nb + t0] : -1;
+                mv = E->c_move[cb + k]; tr = E->c_trav[cb + k];
+                p = E->c_prob[cb + k]; po = E->c_prob_orig[cb + k]; nx = E->c_next[cb + k];
+                own = no;
+            }
+        }
+        grp.sync();
+        if (dst >= 0) {
+            E->c_to[cb + dst] = to; E->c_move[cb + dst] = mv; E->c_owner[cb + dst] = own;
+            E->c_trav[cb + dst] = tr; E->c_prob[cb + dst] = p; E->c_prob_orig[cb + dst] = po; E->c_next[cb + dst] = nx;
+        }
+        grp.sync();
+    }
+    // ---- pass 3: nodes, in place
+    for (int b = 0; b < N; b += T) {
+        const int i = b + tid;
+        int dst = -1;
+        int parent = -1, child0 = -1, nchild = 0, inflight = 0, flags = 0, lead = 0, depth = 0;
+        uint32_t visits = 0;
+        float puct = 0, sc[GZP_MAX_ROLES], fn[GZP_MAX_ROLES];
+        int ot[GZP_MAX_ROLES];
+        if (i < N) {
+            dst = E->n_newidx[nb + i];
+            if (dst >= 0) {
+                const int p0 = E->n_parent[nb + i];
+                parent = (i == r || p0 < 0) ? -1 : E->n_newidx[nb + p0];
+                child0 = E->n_newc0[nb + i];
+                nchild = E->n_nchild[nb + i];
+                if (nchild == 0) child0 = -1;
+                inflight = E->n_inflight[nb + i]; flags = E->n_flags[nb + i]; lead = E->n_lead[nb + i];
+                depth = E->n_depth[nb + i]; visits = E->n_visits[nb + i]; puct = E->n_puct[nb + i];
+                for (int k = 0; k < GZP_MAX_ROLES; k++) {
+                    sc[k] = E->n_score[(nb + i) * GZP_MAX_ROLES + k];
+                    fn[k] = E->n_final[(nb + i) * GZP_MAX_ROLES + k];
+                    ot[k] = E->n_other[(nb + i) * GZP_MAX_ROLES + k];
+                }
+            }
+        }
+        grp.sync();
+        if (dst >= 0) {
+            E->n_parent[nb + dst] = parent; E->n_child0[nb + dst] = child0; E->n_nchild[nb + dst] = nchild;
+            E->n_inflight[nb + dst] = inflight; E->n_flags[nb + dst] = flags; E->n_lead[nb + dst] = lead;
+            E->n_depth[nb + dst] = depth; E->n_visits[nb + dst] = visits; E->n_puct[nb + dst] = puct;
+            for (int k = 0; k < GZP_MAX_ROLES; k++) {
+                E->n_score[(nb + dst) * GZP_MAX_ROLES + k] = sc[k];
+                E->n_final[(nb + dst) * GZP_MAX_ROLES + k] = fn[k];
+                E->n_other[(nb + dst) * GZP_MAX_ROLES + k] = ot[k];
+            }
+        }
+        grp.sync();
+    }
+    // ---- pass 4: states (rows of SW words), in place; every thread moves whole rows in index order
+    for (int b = 0; b < N; b += T) {
+        const int i = b + tid;
+        const int dst = i < N ? E->n_newidx[nb + i] : -1;
+        // rows are small (SW words); a thread copies its row into registers chunk-wise
+        for (int w0 = 0; w0 < E->SW; w0 += 8) {
+            uint32_t tmp[8];
+            const int nw = E->SW - w0 < 8 ? E->SW - w0 : 8;
+            if (dst >= 0) for (int w = 0; w < nw; w++) tmp[w] = E->n_state[(nb + i) * E->SW + w0 + w];
+            grp.sync();
+            if (dst >= 0) for (int w = 0; w < nw; w++) E->n_state[(nb + dst) * E->SW + w0 + w] = tmp[w];
+            grp.sync();
+        }
+    }
+    if (tid == 0) {
+        c->root = 0;
+        c->n_nodes = node_base;
+        c->n_children = child_base;
+        c->game_depth++;
         c->root_has_prev = 1;
     }
-    // the BFS queue is the new node array itself; n_parent of a copied node temporarily holds its
-    // OLD index (in n_child0's slot we keep the old child0 until its children are processed).
-    int tail = 0, ctail = 0;
-    auto copy_node = [&](int old_n, int new_parent) {
-        const int nn = tail++;
-        E->n_parent[nnb + nn] = new_parent;
-        E->n_child0[nnb + nn] = E->n_child0[onb + old_n];   // old index for now
-        E->n_nchild[nnb + nn] = E->n_nchild[onb + old_n];
-        E->n_visits[nnb + nn] = E->n_visits[onb + old_n];
-        E->n_inflight[nnb + nn] = E->n_inflight[onb + old_n];
-        E->n_flags[nnb + nn] = E->n_flags[onb + old_n];
-        E->n_lead[nnb + nn] = E->n_lead[onb + old_n];
-        E->n_depth[nnb + nn] = E->n_depth[onb + old_n];
-        E->n_puct[nnb + nn] = E->n_puct[onb + old_n];
-        for (int r = 0; r < GZP_MAX_ROLES; r++) {
-            E->n_score[(nnb + nn) * GZP_MAX_ROLES + r] = E->n_score[(onb + old_n) * GZP_MAX_ROLES + r];
-            E->n_final[(nnb + nn) * GZP_MAX_ROLES + r] = E->n_final[(onb + old_n) * GZP_MAX_ROLES + r];
-            E->n_other[(nnb + nn) * GZP_MAX_ROLES + r] = E->n_other[(onb + old_n) * GZP_MAX_ROLES + r];
-        }
-        const uint32_t* s = E->n_state + (onb + old_n) * E->SW;
-        uint32_t* d = E->n_state + (nnb + nn) * E->SW;
-        for (int w = 0; w < E->SW; w++) d[w] = s[w];
-        return nn;
-    };
-    copy_node(new_root, -1);
-    for (int head = 0; head < tail; head++) {
-        const int nc = E->n_nchild[nnb + head];
-        if (nc == 0) { E->n_child0[nnb + head] = -1; continue; }
-        const int oc0 = E->n_child0[nnb + head];
-        const int nc0 = ctail;
-        ctail += nc;
-        E->n_child0[nnb + head] = nc0;
-        for (int i = 0; i < nc; i++) {
-            const int64_t o = ocb + oc0 + i, d = ncb + nc0 + i;
-            E->c_trav[d] = E->c_trav[o];
-            E->c_prob[d] = E->c_prob[o];
-            E->c_prob_orig[d] = E->c_prob_orig[o];
-            E->c_next[d] = E->c_next[o];
-            E->c_move[d] = E->c_move[o];
-            const int to = E->c_to[o];
-            E->c_to[d] = to >= 0 ? copy_node(to, head) : -1;
-        }
-    }
-    c->arena = na;
-    c->root = 0;
-    c->n_nodes = tail;
-    c->n_children = ctail;
-    c->game_depth++;
-    V.nb = nnb;
-    V.cb = ncb;
+    grp.sync();
 }
 
+GZP_HDN void gzp_reroot_host(GameView& V, int new_root) {
+    GzpSeq grp;
+    gzp_reroot_compact(V, new_root, 0, 1, grp);
+}
+
+GZP_HDN void gzp_request_reroot(GameView& V, int new_root) {
+    GameCtl* c = V.c;
+    c->req = REQ_REROOT;
+    c->req_parent = new_root;
+    c->req_child = -1;
+    c->phase = PH_AFTER_MOVE;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Controller: the reference's coroutine per game (SelfPlay::playGamesForever -> playOnce ->
@@ -1349,6 +1429,11 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
     for (int iter = 0; iter < E->max_iters_per_step; iter++) {
         if (c->error) { c->phase = PH_HALT; return; }
         if (c->req != REQ_NONE) return;
+        if (c->mode == 1 && c->phase == PH_AFTER_MOVE && !c->resume) {   // player: move applied
+            c->phase = PH_IDLE;
+            c->cmd_done = 1;
+            continue;
+        }
         if (c->resume) {
             c->resume = 0;
             const int N = c->new_node;
@@ -1361,8 +1446,7 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
                     c->cur = N;
                 }
             } else if (c->req_purpose == PUR_REROOT) {
-                gzp_reroot(V, N);
-                c->phase = PH_AFTER_MOVE;
+                gzp_request_reroot(V, N);
             } else {
                 c->root = N;
                 if (gzp_is_terminal(V, N)) { c->error = GZP_ERR_ROOT_TERMINAL; continue; }
@@ -1457,9 +1541,8 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
                 c->phase = PH_AFTER_MOVE;   // entered once the re-root completes
                 return;
             }
-            gzp_reroot(V, CHILD(c_to, ci));
-            c->phase = PH_AFTER_MOVE;
-            break;
+            gzp_request_reroot(V, CHILD(c_to, ci));
+            return;
         }
         case PH_AFTER_MOVE: {
             const int node = c->root;
@@ -1554,8 +1637,8 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
                     c->phase = PH_AFTER_MOVE;
                     return;
                 }
-                gzp_reroot(V, CHILD(c_to, ci));
-                c->cmd_done = 1;
+                gzp_request_reroot(V, CHILD(c_to, ci));
+                return;
             } else if (cmd == CMD_SEARCH) {
                 gzp_start_search(V, c->cmd_evals, 0);
             }
@@ -1563,10 +1646,6 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
         }
         default:
             return;
-        }
-        if (c->mode == 1 && c->phase == PH_AFTER_MOVE && c->req == REQ_NONE) {
-            c->phase = PH_IDLE;
-            c->cmd_done = 1;
         }
     }
 }
@@ -1576,7 +1655,7 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
 GZP_HDN void gzp_step_post(GameView& V) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
-    if (c->phase == PH_HALT || c->req == REQ_NONE) return;
+    if (c->phase == PH_HALT || c->req == REQ_NONE || c->req == REQ_REROOT) return;
     const int parent = c->req == REQ_ROOT ? -1 : c->req_parent;
     const int depth = parent < 0 ? c->game_depth : NODE(n_depth, parent) + 1;
     const int N = gzp_create_node(V, parent, depth);

@@ -18,8 +18,8 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
         pos += (bytes + 255) & ~(size_t)255;
         return p;
     };
-    const size_t NN = (size_t)E->G * 2 * E->NCAP;
-    const size_t CC = (size_t)E->G * 2 * E->CCAP;
+    const size_t NN = (size_t)E->G * E->NCAP;
+    const size_t CC = (size_t)E->G * E->CCAP;
     const size_t G = (size_t)E->G;
     E->n_parent = (int32_t*)take(NN * 4);
     E->n_child0 = (int32_t*)take(NN * 4);
@@ -36,6 +36,9 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     E->n_other = (int32_t*)take(NN * 4 * GZP_MAX_ROLES);
     E->c_to = (int32_t*)take(CC * 4);
     E->c_move = (int32_t*)take(CC * 4);
+    E->c_owner = (int32_t*)take(CC * 4);
+    E->n_newidx = (int32_t*)take(NN * 4);
+    E->n_newc0 = (int32_t*)take(NN * 4);
     E->c_trav = (uint32_t*)take(CC * 4);
     E->c_prob = (float*)take(CC * 4);
     E->c_prob_orig = (float*)take(CC * 4);

@@ -65,5 +65,5 @@ class SelfPlayRunner(object):
 
     @property
     def kernels_per_step(self):
-        """Launches of this repo's own kernels per step: (pre, propnet, post) x sub_iters + encode."""
-        return 3 * self.sub_iters + 1
+        """Launches of this repo's own kernels per step: (pre, reroot, propnet, post) x sub_iters + encode."""
+        return 4 * self.sub_iters + 1

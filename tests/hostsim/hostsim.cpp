@@ -155,6 +155,13 @@ extern "C" void hs_step(void* h) {
         GameView V = gzp_view(&E, g);
         gzp_step_pre(V);
     }
+    for (int g = 0; g < E.G; g++) {      // the device runs puct_reroot_kernel here
+        GameCtl& c = E.ctl[g];
+        if (c.req != REQ_REROOT) continue;
+        GameView V = gzp_view(&E, g);
+        gzp_reroot_host(V, c.req_parent);
+        c.req = REQ_NONE;
+    }
     for (int g = 0; g < E.G; g++) {
         GameCtl& c = E.ctl[g];
         if (c.req == REQ_NONE) continue;
