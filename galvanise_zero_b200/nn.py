@@ -149,12 +149,26 @@ class InferenceTower(nn.Module):
         self.value_conv = tower.value_conv.fold()
         self.value_hidden = tower.value_hidden
         self.value_out = tower.value_out
+        self.use_fused = tower.conf.cnn_kernel_size == 3 and hasattr(torch, 'cudnn_convolution_add_relu')
 
-    def forward(self, planes):
+    def _tower(self, planes):
+        if planes.is_cuda and self.use_fused:
+            # cuDNN runtime-fused conv+bias+ReLU and conv+bias+residual-add+ReLU: one kernel per
+            # convolution instead of conv + 1-2 elementwise passes over the 33 MB activation
+            one = (1, 1)
+            x = torch.cudnn_convolution_relu(planes, self.stem.weight, self.stem.bias, one, one, one, 1)
+            for c0, c1 in self.blocks:
+                y = torch.cudnn_convolution_relu(x, c0.weight, c0.bias, one, one, one, 1)
+                x = torch.cudnn_convolution_add_relu(y, c1.weight, x, 1.0, c1.bias, one, one, one, 1)
+            return x
         x = F.relu(self.stem(planes))
         for c0, c1 in self.blocks:
             y = F.relu(c0(x))
             x = F.relu(c1(y) + x)
+        return x
+
+    def forward(self, planes):
+        x = self._tower(planes)
         pols = []
         for conv, dense in zip(self.policy_convs, self.policy_dense):
             p = F.relu(conv(x)).flatten(1)
