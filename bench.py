@@ -312,21 +312,24 @@ def run_puct(args, rank, world, local):
     import torch
     from galvanise_zero_b200.engine import PuctEngine
     from galvanise_zero_b200.nn import make_inference_network
-    from galvanise_zero_b200.selfplay import SelfPlayRunner
+    from galvanise_zero_b200.selfplay import SelfPlayPool
 
     peaks = load_peaks()
     torch.cuda.set_device(local)
     G = args.slots or PUCT_GAMES_PER_GPU
     sp = puct_selfplay_conf()
-    eng = PuctEngine(PUCT_GAME, sp, n_games=G, mode=0, device=local, seed=0xB200 + 7919 * rank,
-                     node_cap=4096, child_cap=4096 * 16)
+    P = max(1, args.pipelines)
+    engines = [PuctEngine(PUCT_GAME, sp, n_games=G // P, mode=0, device=local,
+                          seed=0xB200 + 7919 * rank + 104729 * k, node_cap=4096, child_cap=4096 * 16)
+               for k in range(P)]
+    eng = engines[0]
     net = make_inference_network(eng.transformer, 'small', seed=1234, device=eng.device)
-    runner = SelfPlayRunner(eng, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph)
+    runner = SelfPlayPool(engines, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph)
     # bring the games to a desynchronised steady state (untimed), then warm up
     runner.step(args.presteps)
     runner.step(args.warmup)
     barrier(world)
-    t_before = eng.totals()
+    t_before = runner.totals()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -338,7 +341,7 @@ def run_puct(args, rank, world, local):
     barrier(world)
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.summary() if sampler else None
-    t_after = eng.totals()
+    t_after = runner.totals()
     d_moves = t_after['moves'] - t_before['moves']
     d_evals = t_after['evals'] - t_before['evals']
     ms_max = all_max(ms, world, eng.device)
@@ -365,18 +368,19 @@ def run_puct(args, rank, world, local):
         g_nn.replay()
         parts['network_forward_ms'] = time_region(lambda: [g_nn.replay() for _ in range(reps)], eng.device) / reps
         st = eng.sm
-        s_in = st.initial_states(G)
-        mv = torch.full((G, st.n_roles), -1, dtype=torch.int16, device=eng.device)
-        outb = (torch.empty_like(s_in),) + st.alloc_views(G)
+        s_in = st.initial_states(Gp)
+        mv = torch.full((Gp, st.n_roles), -1, dtype=torch.int16, device=eng.device)
+        outb = (torch.empty_like(s_in),) + st.alloc_views(Gp)
         parts['propnet_transition_ms'] = time_region(lambda: [st.transition(s_in, mv, out=outb) for _ in range(reps)], eng.device) / reps
-    flops = net.flops_per_position * G
+    Gp = G // P
+    flops = net.flops_per_position * Gp
     nn_s = parts['network_forward_ms'] * 1e-3
     achieved = flops / nn_s / 1e12
     peak = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': achieved / peak, 'traffic': None,
-                'kernel': 'residual tower forward (cuDNN/cuBLAS via PyTorch, bf16 channels_last), %d positions' % G,
-                'flops_per_unit': net.flops_per_position, 'units_per_launch': G,
+                'kernel': 'residual tower forward (cuDNN runtime-fused conv+bias+ReLU via PyTorch, bf16 channels_last), %d positions per launch' % Gp,
+                'flops_per_unit': net.flops_per_position, 'units_per_launch': Gp,
                 'peak_source': peaks['source'] + ' (sustained bf16)'}
 
     # ---- e2e: the reference-shaped numpy poll() API with host buffers (D2H planes, H2D planes for the
@@ -391,29 +395,35 @@ def run_puct(args, rank, world, local):
         R = len(eng.role_sizes)
         h2d = d2h = 0
 
+        pin_pol = torch.empty((G, eng.policy_stride), dtype=torch.float32).pin_memory()
+        pin_val = torch.empty((G, eng.n_rewards), dtype=torch.float32).pin_memory()
+
         def e2e_step(pred):
             nonlocal h2d, d2h
             n, arrays = pred
-            planes = sup.poll(n, arrays)
+            planes = sup.poll(n, arrays)                 # numpy view of pinned engine memory
             if planes is None:
                 return (0, [])
             n_req = planes.size // eng.total_size
             d2h += planes.nbytes
-            xin = torch.from_numpy(planes.reshape((n_req,) + eng.plane_shape)).pin_memory()
+            xin = torch.from_numpy(planes).view((n_req,) + eng.plane_shape)
             xd = xin.to(eng.device, non_blocking=True).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
             h2d += planes.nbytes
             with torch.no_grad():
                 pol, val = net(xd)
-            pol = pol.cpu().numpy()
-            val = val.cpu().numpy()
-            d2h += pol.nbytes + val.nbytes
-            h2d += pol.nbytes + val.nbytes
+            pin_pol[:n_req].copy_(pol, non_blocking=True)
+            pin_val[:n_req].copy_(val, non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            pol_h = pin_pol.numpy()[:n_req]
+            val_h = pin_val.numpy()[:n_req]
+            d2h += pol_h.nbytes + val_h.nbytes
+            h2d += pol_h.nbytes + val_h.nbytes
             off = 0
             arrs = []
             for r in range(R):
-                arrs.append(np.ascontiguousarray(pol[:, off:off + eng.role_sizes[r]]))
+                arrs.append(np.ascontiguousarray(pol_h[:, off:off + eng.role_sizes[r]]))
                 off += eng.role_sizes[r]
-            arrs.append(np.ascontiguousarray(val))
+            arrs.append(np.ascontiguousarray(val_h))
             return (n_req, arrs)
 
         pred = (0, [])
@@ -454,8 +464,9 @@ def run_puct(args, rank, world, local):
                        'network': 'random-init small tower, %.1f MFLOP/position' % (net.flops_per_position / 1e6),
                        'step': 'one engine advance (select/backup + propnet + expand + encode) + one network '
                                'forward over %d leaves' % G,
-                       'l2': 'tree arenas %.1f GB per GPU >> 126 MB L2' % (eng.arena_bytes / 1e9),
+                       'l2': 'tree arenas %.1f GB per GPU >> 126 MB L2' % (sum(e.arena_bytes for e in engines) / 1e9),
                        'presteps': args.presteps, 'cuda_graph': not args.no_graph,
+                       'pipelines': '%d engine+network pipelines of %d games each on separate streams' % (P, G // P),
                        'parallelism': 'games sharded across %d GPU(s), no collective on the hot path' % world},
             'evals_per_s': evals / (ms_max * 1e-3), 'moves_in_window': moves,
             'roofline': roofline, 'kernel_times_ms': parts, 'cpu_baseline': cpu, 'e2e': e2e,
@@ -534,6 +545,7 @@ def main():
     ap.add_argument('--sub-iters', type=int, default=1)
     ap.add_argument('--presteps', type=int, default=3000)
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--pipelines', type=int, default=2)
     ap.add_argument('--slots', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -166,6 +166,8 @@ class Supervisor(object):
 
     # -- reference-shaped numpy path
     def poll(self, n_predictions, arrays):
+        """Returns a 1-D float32 numpy array VIEWING engine-owned pinned host memory (valid until the
+        next poll, as in the reference: common.cpp:204-209), or None when nothing needs evaluating."""
         import torch
         e = self.engine
         if e is None:
@@ -175,29 +177,42 @@ class Supervisor(object):
         if self._rows is None:
             if n_predictions != 0:
                 raise GGPZeroInterfaceError('first poll must pass n_predictions == 0')
+            self._host_planes = torch.empty((e.n_games, e.total_size), dtype=torch.float32).pin_memory()
+            self._host_count = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self._stage_pol = torch.empty((e.n_games, e.policy_stride), dtype=torch.float32).pin_memory()
+            self._stage_val = torch.empty((e.n_games, e.n_rewards), dtype=torch.float32).pin_memory()
             e.advance(None, None)
         else:
             if n_predictions != len(self._rows):
                 raise GGPZeroInterfaceError('expected %d predictions, got %d' % (len(self._rows), n_predictions))
-            for a in (arrays if n_predictions else []):
-                if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
-                    raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
             if n_predictions:
                 R = len(e.role_sizes)
-                pol = np.concatenate([arrays[r].reshape(n_predictions, e.role_sizes[r]) for r in range(R)], axis=1)
-                val = arrays[R].reshape(n_predictions, e.n_rewards)
+                if len(arrays) != R + 1:
+                    raise GGPZeroInterfaceError('expected %d policy arrays and one value array' % R)
+                off = 0
+                sp = self._stage_pol.numpy()
+                for r in range(R):
+                    a = arrays[r]
+                    if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
+                        raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
+                    sp[:n_predictions, off:off + e.role_sizes[r]] = a.reshape(n_predictions, e.role_sizes[r])
+                    off += e.role_sizes[r]
+                self._stage_val.numpy()[:n_predictions] = arrays[R].reshape(n_predictions, e.n_rewards)
                 rows = self._rows_dev
-                e.policy[rows] = torch.from_numpy(pol).to(e.device, non_blocking=True)
-                e.value[rows] = torch.from_numpy(val).to(e.device, non_blocking=True)
+                e.policy.index_copy_(0, rows, self._stage_pol[:n_predictions].to(e.device, non_blocking=True))
+                e.value.index_copy_(0, rows, self._stage_val[:n_predictions].to(e.device, non_blocking=True))
             e.advance(e.policy, e.value)
         need = self._need_eval()
-        rows = torch.nonzero(need, as_tuple=False).flatten()
+        rows = torch.nonzero(need, as_tuple=False).flatten()        # device sync: the request count
+        n_req = int(rows.numel())
         self._rows_dev = rows
-        self._rows = rows.cpu().numpy()
-        if len(self._rows) == 0:
+        self._rows = rows                                           # only its length is used on the host
+        if n_req == 0:
             return None
-        planes = e.planes.reshape(e.n_games, -1)[rows].to(torch.float32).cpu().numpy()
-        return planes.reshape(-1)
+        gathered = e.planes.reshape(e.n_games, -1).index_select(0, rows).to(torch.float32)
+        self._host_planes[:n_req].copy_(gathered, non_blocking=True)
+        torch.cuda.current_stream(e.device).synchronize()
+        return self._host_planes.numpy()[:n_req].reshape(-1)
 
     def _need_eval(self):
         import ctypes

@@ -13,8 +13,9 @@ from .engine import PuctEngine
 
 
 class SelfPlayRunner(object):
-    def __init__(self, engine: PuctEngine, net, sub_iters=1, use_cuda_graph=True):
+    def __init__(self, engine: PuctEngine, net, sub_iters=1, use_cuda_graph=True, stream=None):
         self.engine = engine
+        self.stream = stream
         self.net = net
         self.sub_iters = sub_iters
         self.graph = None
@@ -28,6 +29,8 @@ class SelfPlayRunner(object):
             self._forward()
             if use_cuda_graph:
                 self._capture()
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(e.device))
 
     def _forward(self):
         e = self.engine
@@ -56,14 +59,62 @@ class SelfPlayRunner(object):
 
     def step(self, n=1):
         with torch.no_grad():
-            for _ in range(n):
-                if self.graph is not None:
-                    self.graph.replay()
-                else:
-                    self._step_eager()
+            if self.stream is not None:
+                with torch.cuda.stream(self.stream):
+                    self._step_n(n)
+            else:
+                self._step_n(n)
         self.steps_done += n
+
+    def _step_n(self, n):
+        for _ in range(n):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._step_eager()
 
     @property
     def kernels_per_step(self):
         """Launches of this repo's own kernels per step: (pre, reroot, propnet, post) x sub_iters + encode."""
         return 4 * self.sub_iters + 1
+
+
+class SelfPlayPool(object):
+    """Several independent engine+network pipelines on separate CUDA streams (each with its own
+    graph). While one pipeline's network forward occupies the tensor cores, another pipeline's
+    latency-bound tree kernels run beside it — the device-side analogue of the reference's two
+    managers per worker thread, which overlap CPU search with the GPU call
+    (``src/cpp/supervisor.cpp:79-99,196-231``)."""
+
+    def __init__(self, engines, net, sub_iters=1, use_cuda_graph=True):
+        dev = engines[0].device
+        self.engines = engines
+        self.streams = [torch.cuda.Stream(device=dev) for _ in engines]
+        self.runners = [SelfPlayRunner(e, net, sub_iters, use_cuda_graph, stream=s)
+                        for e, s in zip(engines, self.streams)]
+        self.device = dev
+
+    def step(self, n=1):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        for _ in range(n):
+            for r in self.runners:
+                r.step(1)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def totals(self):
+        out = None
+        for e in self.engines:
+            t = e.totals()
+            if out is None:
+                out = dict(t)
+            else:
+                for k, v in t.items():
+                    out[k] = max(out[k], v) if k.startswith('max_') or k == 'first_error' else out[k] + v
+        return out
+
+    @property
+    def kernels_per_step(self):
+        return sum(r.kernels_per_step for r in self.runners)
