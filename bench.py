@@ -319,6 +319,7 @@ def run_puct(args, rank, world, local):
     G = args.slots or PUCT_GAMES_PER_GPU
     sp = puct_selfplay_conf()
     P = max(1, args.pipelines)
+    Gp = G // P
     engines = [PuctEngine(PUCT_GAME, sp, n_games=G // P, mode=0, device=local,
                           seed=0xB200 + 7919 * rank + 104729 * k, node_cap=4096, child_cap=4096 * 16)
                for k in range(P)]
@@ -372,7 +373,6 @@ def run_puct(args, rank, world, local):
         mv = torch.full((Gp, st.n_roles), -1, dtype=torch.int16, device=eng.device)
         outb = (torch.empty_like(s_in),) + st.alloc_views(Gp)
         parts['propnet_transition_ms'] = time_region(lambda: [st.transition(s_in, mv, out=outb) for _ in range(reps)], eng.device) / reps
-    Gp = G // P
     flops = net.flops_per_position * Gp
     nn_s = parts['network_forward_ms'] * 1e-3
     achieved = flops / nn_s / 1e12
