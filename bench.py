@@ -545,7 +545,7 @@ def main():
     ap.add_argument('--sub-iters', type=int, default=1)
     ap.add_argument('--presteps', type=int, default=3000)
     ap.add_argument('--no-graph', action='store_true')
-    ap.add_argument('--pipelines', type=int, default=2)
+    ap.add_argument('--pipelines', type=int, default=1)
     ap.add_argument('--slots', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
