@@ -313,6 +313,7 @@ def run_puct(args, rank, world, local):
     from galvanise_zero_b200.engine import PuctEngine
     from galvanise_zero_b200.nn import make_inference_network
     from galvanise_zero_b200.selfplay import SelfPlayPool
+    from galvanise_zero_b200 import distributed as gzdist
 
     peaks = load_peaks()
     torch.cuda.set_device(local)
@@ -321,7 +322,7 @@ def run_puct(args, rank, world, local):
     P = max(1, args.pipelines)
     Gp = G // P
     engines = [PuctEngine(PUCT_GAME, sp, n_games=G // P, mode=0, device=local,
-                          seed=0xB200 + 7919 * rank + 104729 * k, node_cap=4096, child_cap=4096 * 16)
+                          seed=gzdist.rank_seed(0xB200, rank) + 104729 * k, node_cap=4096, child_cap=4096 * 16)
                for k in range(P)]
     eng = engines[0]
     net = make_inference_network(eng.transformer, 'small', seed=1234, device=eng.device)
@@ -446,6 +447,11 @@ def run_puct(args, rank, world, local):
                'api': 'interface.Supervisor.poll (numpy in / numpy out, reference contract), network fed from pinned host memory',
                'steps': reps}
 
+    # ---- end of 'generation': gather the finished samples to rank 0 (the only collective; untimed)
+    recs = np.concatenate([e.fetch_sample_records() for e in engines], axis=0)
+    gathered = gzdist.gather_sample_records(torch.from_numpy(recs).to(eng.device), dst=0)
+    n_gathered = int(gathered.shape[0]) if gathered is not None else 0
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -472,6 +478,7 @@ def run_puct(args, rank, world, local):
             'roofline': roofline, 'kernel_times_ms': parts, 'cpu_baseline': cpu, 'e2e': e2e,
             'gpu_launches': args.steps * runner.kernels_per_step, 'clocks': clocks,
             'engine_totals': {k: t_after[k] for k in ('errors', 'halted', 'max_nodes', 'max_children', 'games', 'samples')},
+            'samples_gathered_to_rank0': n_gathered,
         }
         print(json.dumps(line), flush=True)
 
