@@ -64,7 +64,7 @@ puct_post_kernel(const __grid_constant__ PuctEngine E) {
 
 // Re-rooting: one CTA per game that asked for it (a handful per step); in-place parallel
 // mark-compact of the kept subtree (gzp_reroot_compact).
-#define REROOT_THREADS 256
+#define REROOT_THREADS 1024
 struct GzpCta {
     int* sm;   // [2 * (REROOT_THREADS / 32)]
     __device__ __forceinline__ void sync() { __syncthreads(); }

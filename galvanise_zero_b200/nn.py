@@ -167,8 +167,58 @@ class InferenceTower(nn.Module):
             x = F.relu(c1(y) + x)
         return x
 
+    def _build_fused_heads(self):
+        """One 1x1 convolution for all head channels (policy heads 2 each + value 1, padded to 8) and one
+        GEMM for every dense layer that reads them, with the dense weights re-indexed to consume the
+        channels-last activation directly (row = position*8 + channel)."""
+        convs = list(self.policy_convs) + [self.value_conv]
+        f = convs[0].in_channels
+        n_ch = sum(c.out_channels for c in convs)
+        assert n_ch <= 8
+        dev, dt = convs[0].weight.device, convs[0].weight.dtype
+        w = torch.zeros((8, f, 1, 1), device=dev, dtype=dt)
+        b = torch.zeros((8,), device=dev, dtype=dt)
+        ch0 = []
+        c = 0
+        for cv in convs:
+            w[c:c + cv.out_channels] = cv.weight.detach()
+            b[c:c + cv.out_channels] = cv.bias.detach()
+            ch0.append(c)
+            c += cv.out_channels
+        self.head_w = w.contiguous(memory_format=torch.channels_last)
+        self.head_b = b
+        denses = list(self.policy_dense) + [self.value_hidden]
+        hw = denses[0].in_features // convs[0].out_channels
+        outs = [d.out_features for d in denses]
+        big = torch.zeros((hw * 8, sum(outs)), device=dev, dtype=dt)
+        bias = torch.zeros((sum(outs),), device=dev, dtype=dt)
+        o = 0
+        for d, cv, c0 in zip(denses, convs, ch0):
+            wd = d.weight.detach()                      # [out, ch*hw], input index = ch_local*hw + pos
+            for cl in range(cv.out_channels):
+                rows = torch.arange(hw, device=dev) * 8 + (c0 + cl)
+                big[rows, o:o + d.out_features] = wd[:, cl * hw:(cl + 1) * hw].t()
+            bias[o:o + d.out_features] = d.bias.detach()
+            o += d.out_features
+        self.head_dense_w = big.contiguous()
+        self.head_dense_b = bias
+        self.head_splits = outs
+        self.fused_heads = True
+
     def forward(self, planes):
         x = self._tower(planes)
+        if planes.is_cuda and self.use_fused:
+            if not getattr(self, 'fused_heads', False):
+                self._build_fused_heads()
+            one, zero = (1, 1), (0, 0)
+            h = torch.cudnn_convolution_relu(x, self.head_w, self.head_b, one, zero, one, 1)   # [N,8,H,W] NHWC
+            flat = h.permute(0, 2, 3, 1).reshape(h.shape[0], -1)                                # view: pos*8 + ch
+            z = torch.addmm(self.head_dense_b, flat, self.head_dense_w)
+            parts = torch.split(z, self.head_splits, dim=1)
+            pols = [F.softmax(p.float(), dim=1) for p in parts[:-1]]
+            v = F.relu(parts[-1])
+            v = F.softmax(self.value_out(v).float(), dim=1)
+            return torch.cat(pols, dim=1).contiguous(), v.contiguous()
         pols = []
         for conv, dense in zip(self.policy_convs, self.policy_dense):
             p = F.relu(conv(x)).flatten(1)
