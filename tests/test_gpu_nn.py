@@ -1,6 +1,7 @@
-"""GPU: the fused inference path of the tower (cuDNN runtime-fused convolutions, merged heads) computes
-the same function as the plain PyTorch fp32 module of the same weights (tolerance: bf16 arithmetic,
-|dp| <= 2e-2 on probabilities)."""
+"""GPU: the fused inference path of the tower (cuDNN runtime-fused convolutions, merged head conv,
+re-indexed dense GEMM) computes the same function as the plain PyTorch fp32 module of the same weights.
+Tolerances: fused fp32 vs plain fp32 |dp| <= 2e-3 (TF32-free fp32 kernels differ only in summation
+order); fused bf16 vs plain fp32 |dp| <= 0.15 (bf16 through 11 randomly initialised layers and a softmax)."""
 import pytest
 import torch
 
@@ -19,10 +20,14 @@ def test_fused_tower_matches_fp32_reference(game):
     ref = gznn.make_inference_network(tr, 'small', seed=3, device='cuda', dtype=torch.float32)
     ref.use_fused = False
     x = (torch.rand(257, tr.num_channels, tr.num_cols, tr.num_rows, device='cuda') > 0.7).float()
+    f32 = gznn.make_inference_network(tr, 'small', seed=3, device='cuda', dtype=torch.float32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     with torch.no_grad():
         p, v = net(x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+        pf, vf = f32(x.contiguous(memory_format=torch.channels_last))
         pr, vr = ref(x)
     assert p.shape == pr.shape and v.shape == vr.shape
     assert torch.allclose(p.sum(1), torch.full((257,), float(len(tr.policy_dist_count)), device='cuda'), atol=1e-3)
-    assert (p - pr).abs().max().item() < 2e-2
-    assert (v - vr).abs().max().item() < 2e-2
+    assert (pf - pr).abs().max().item() < 2e-3 and (vf - vr).abs().max().item() < 2e-3
+    assert (p - pr).abs().max().item() < 0.15 and (v - vr).abs().max().item() < 0.15
