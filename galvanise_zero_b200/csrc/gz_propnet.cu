@@ -66,25 +66,35 @@ __device__ __forceinline__ uint32_t lit_word(const uint32_t* val, uint32_t lit) 
     return val[lit >> 1] ^ (0u - (lit & 1u));
 }
 
-// Evaluates one chunk stream on the warp's value array.
+// Barrier of the WPT warps that share one tile (WPT == 1: just this warp).
+template <int WPT>
+__device__ __forceinline__ void tile_sync() {
+    if (WPT == 1) __syncwarp(); else __syncthreads();
+}
+
+// Evaluates one chunk stream on the tile's value array. With WPT > 1 the CTA's WPT warps share the
+// tile: warp `wt` evaluates chunks wt, wt+WPT, ... and the CTA meets at every level boundary.
+template <int WPT>
 __device__ __forceinline__ void run_program(const uint32_t* __restrict__ prog, int n_chunks,
-                                            uint32_t* __restrict__ val, int lane) {
+                                            uint32_t* __restrict__ val, int lane, int wt) {
     const uint32_t* p = prog;
     for (int c = 0; c < n_chunks; ++c) {
         const uint32_t hdr = p[0];
         const int nl2 = (int)((hdr & 0xffu) >> 1);
-        const uint32_t ow = p[1 + (lane >> 1)];
-        const uint32_t out = (lane & 1) ? (ow >> 16) : (ow & 0xffffu);
-        uint32_t acc = 0xffffffffu;
-        const uint32_t* lp = p + 17 + lane;
+        if (WPT == 1 || (c % WPT) == wt) {
+            const uint32_t ow = p[1 + (lane >> 1)];
+            const uint32_t out = (lane & 1) ? (ow >> 16) : (ow & 0xffffu);
+            uint32_t acc = 0xffffffffu;
+            const uint32_t* lp = p + 17 + lane;
 #pragma unroll 2
-        for (int k = 0; k < nl2; ++k) {
-            const uint32_t pr = lp[k * 32];
-            acc &= lit_word(val, pr & 0xffffu) & lit_word(val, pr >> 16);
+            for (int k = 0; k < nl2; ++k) {
+                const uint32_t pr = lp[k * 32];
+                acc &= lit_word(val, pr & 0xffffu) & lit_word(val, pr >> 16);
+            }
+            val[out] = acc;
         }
-        val[out] = acc;
         p += 17 + 32 * nl2;
-        if (hdr & 0x100u) __syncwarp();
+        if (hdr & 0x100u) tile_sync<WPT>();
     }
 }
 
@@ -121,7 +131,7 @@ __device__ __forceinline__ void store_rows(uint32_t* __restrict__ dst, int row_w
     __syncwarp();
 }
 
-template <int MODE>
+template <int MODE, int WPT>
 __global__ void __launch_bounds__(1024, 1)
 pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
           const uint32_t* states_in, const int16_t* __restrict__ moves_in,
@@ -149,16 +159,20 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int warps = blockDim.x >> 5;
-    uint32_t* val = smem + P.staged_words + warp * P.warp_words;
+    // WPT == 1: every warp owns its own tile (and value array). WPT > 1: the CTA is WPT warps sharing
+    // ONE tile; warp 0 does the row I/O and transposes, all warps evaluate the gate programs.
+    const int warps = WPT == 1 ? (int)(blockDim.x >> 5) : 1;
+    const int wt = WPT == 1 ? 0 : warp;
+    const bool io = (WPT == 1) || (warp == 0);
+    uint32_t* val = smem + P.staged_words + (WPT == 1 ? warp : 0) * P.warp_words;
     uint32_t* stage = val + P.val_words;
     uint32_t* slices = stage + 32 * P.row_stride;
     const int rs = P.row_stride;
     const int R = P.n_roles;
-    if (lane == 0) val[0] = 0xffffffffu;
+    if (lane == 0 && io) val[0] = 0xffffffffu;
 
     const int64_t n_tiles = (n + 31) >> 5;
-    for (int64_t tile = (int64_t)blockIdx.x * warps + warp; tile < n_tiles;
+    for (int64_t tile = (int64_t)blockIdx.x * warps + (WPT == 1 ? warp : 0); tile < n_tiles;
          tile += (int64_t)gridDim.x * warps) {
         const int64_t g0 = tile << 5;
         const int64_t game = g0 + lane;
@@ -168,6 +182,7 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
         uint32_t reset_mask = 0, pass_mask = 0;
         int mv[GZ_PN_MAX_ROLES];
 
+        if (io) {
         if (MODE == MODE_PLAYOUT) {
             // ---- pick one uniformly random legal action per role from the stored legal rows
             const bool term = valid ? (terminal[game] != 0) : false;
@@ -214,15 +229,20 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
         }
 
         if (MODE != MODE_EVAL) {
-            // ---- one-hot the chosen actions into the input slots, run the next-state cone
+            // ---- one-hot the chosen actions into the input slots
             for (int i = lane; i < P.n_inputs; i += 32) val[1 + P.n_bases + i] = 0;
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < GZ_PN_MAX_ROLES; ++r)
                 if (r < R && mv[r] >= 0) atomicOr(&val[P.input_slot0[r] + mv[r]], 1u << lane);
-            __syncwarp();
-            run_program(prog[0], P.chunks[0], val, lane);
+        }
+        }   // io
+        tile_sync<WPT>();
 
+        if (MODE != MODE_EVAL) {
+            // ---- next-state cone
+            run_program<WPT>(prog[0], P.chunks[0], val, lane, wt);
+            if (io) {
             for (int j = 0; j < P.nbw; ++j) {
                 const int b = j * 32 + lane;
                 uint32_t t = lit_word(val, P.next_lit[b]);
@@ -244,15 +264,17 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
                 const int b = j * 32 + lane;
                 if (b < P.n_bases) val[1 + b] = slices[b];
             }
+            }   // io
         }
-        __syncwarp();
+        tile_sync<WPT>();
 
         // ---- views of the (new) state: legal masks, terminal, goals
-        run_program(prog[1], P.chunks[1], val, lane);
+        run_program<WPT>(prog[1], P.chunks[1], val, lane, wt);
         const uint32_t tw = lit_word(val, (uint32_t)P.terminal_lit) & valid_mask;
         const bool need_goals = (goals_mode == GZ_GOALS_ALWAYS) || (tw != 0u);
-        if (need_goals) run_program(prog[2], P.chunks[2], val, lane);
+        if (need_goals) run_program<WPT>(prog[2], P.chunks[2], val, lane, wt);
 
+        if (io) {
         for (int j = 0; j < P.lw_used; ++j) {
             const uint32_t t = lit_word(val, P.legal_lit[j * 32 + lane]) & valid_mask;
             stage[lane * rs + j] = warp_transpose32(t, lane);
@@ -277,7 +299,8 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
             const int cnt = __popc(valid_mask & ~reset_mask);
             if (cnt) atomicAdd(transitions, (unsigned long long)cnt);
         }
-        __syncwarp();
+        }   // io
+        tile_sync<WPT>();
     }
 }
 
@@ -330,9 +353,11 @@ static int configure_launch(gz_propnet* pn, const int32_t* h) {
     pn->warps_per_cta = warps;
     pn->smem_bytes = staged + (size_t)warps * warp_bytes;
     pn->grid_max = pn->n_sms;  // one persistent CTA per SM
-    GZ_CUDA(cudaFuncSetAttribute(pn_kernel<MODE_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn->smem_bytes));
-    GZ_CUDA(cudaFuncSetAttribute(pn_kernel<MODE_TRANSITION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn->smem_bytes));
-    GZ_CUDA(cudaFuncSetAttribute(pn_kernel<MODE_PLAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn->smem_bytes));
+#define GZ_SET_SMEM(M, W) GZ_CUDA(cudaFuncSetAttribute(pn_kernel<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pn->smem_bytes))
+    GZ_SET_SMEM(MODE_EVAL, 1); GZ_SET_SMEM(MODE_TRANSITION, 1); GZ_SET_SMEM(MODE_PLAYOUT, 1);
+    GZ_SET_SMEM(MODE_EVAL, 4); GZ_SET_SMEM(MODE_TRANSITION, 4); GZ_SET_SMEM(MODE_PLAYOUT, 4);
+    GZ_SET_SMEM(MODE_EVAL, 8); GZ_SET_SMEM(MODE_TRANSITION, 8); GZ_SET_SMEM(MODE_PLAYOUT, 8);
+#undef GZ_SET_SMEM
     (void)h;
     return GZ_OK;
 }
@@ -486,14 +511,32 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
     }
     GZ_CUDA(cudaSetDevice(pn->device));
     const int64_t n_tiles = (n + 31) / 32;
-    // one persistent CTA per SM; small batches shrink the CTA so that tiles spread over all SMs
-    const int block_warps = (int)std::max<int64_t>(
-        1, std::min<int64_t>(pn->warps_per_cta, (n_tiles + pn->grid_max - 1) / pn->grid_max));
-    const int grid2 = (int)std::min<int64_t>((n_tiles + block_warps - 1) / block_warps, pn->grid_max);
-    const size_t smem = (size_t)pn->P.staged_words * 4 + (size_t)block_warps * pn->P.warp_words * 4;
-    pn_kernel<MODE><<<grid2, block_warps * 32, smem, (cudaStream_t)stream>>>(
-        pn->P, n, slot0, states_in, moves_in, states_out, legal, terminal, goals, moves_out, transitions,
-        seed, step, goals_mode);
+    cudaStream_t st = (cudaStream_t)stream;
+    // Small batches (the PUCT pipeline: a few thousand games) do not fill the machine with one warp per
+    // tile and are bound by the serial latency of the gate programs: give every tile a CTA of 4 or 8
+    // warps that share its value array. Large batches keep one warp per tile, many tiles per CTA.
+    int wpt = 1;
+    if (n_tiles * 8 <= (int64_t)pn->grid_max * 4) wpt = 8;
+    else if (n_tiles * 4 <= (int64_t)pn->grid_max * 8) wpt = 4;
+    if (wpt > 1) {
+        const size_t smem = (size_t)pn->P.staged_words * 4 + (size_t)pn->P.warp_words * 4;
+        const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)pn->grid_max * 8);
+        if (wpt == 8)
+            pn_kernel<MODE, 8><<<grid, 8 * 32, smem, st>>>(pn->P, n, slot0, states_in, moves_in, states_out, legal,
+                                                          terminal, goals, moves_out, transitions, seed, step, goals_mode);
+        else
+            pn_kernel<MODE, 4><<<grid, 4 * 32, smem, st>>>(pn->P, n, slot0, states_in, moves_in, states_out, legal,
+                                                          terminal, goals, moves_out, transitions, seed, step, goals_mode);
+    } else {
+        // one persistent CTA per SM; medium batches shrink the CTA so that tiles spread over all SMs
+        const int block_warps = (int)std::max<int64_t>(
+            1, std::min<int64_t>(pn->warps_per_cta, (n_tiles + pn->grid_max - 1) / pn->grid_max));
+        const int grid2 = (int)std::min<int64_t>((n_tiles + block_warps - 1) / block_warps, pn->grid_max);
+        const size_t smem = (size_t)pn->P.staged_words * 4 + (size_t)block_warps * pn->P.warp_words * 4;
+        pn_kernel<MODE, 1><<<grid2, block_warps * 32, smem, st>>>(
+            pn->P, n, slot0, states_in, moves_in, states_out, legal, terminal, goals, moves_out, transitions,
+            seed, step, goals_mode);
+    }
     GZ_CUDA(cudaGetLastError());
     return GZ_OK;
 }
