@@ -205,20 +205,20 @@ class InferenceTower(nn.Module):
         self.head_splits = outs
         self.fused_heads = True
 
-    def forward(self, planes):
-        x = self._tower(planes)
-        if planes.is_cuda and self.use_fused:
-            if not getattr(self, 'fused_heads', False):
-                self._build_fused_heads()
-            one, zero = (1, 1), (0, 0)
-            h = torch.cudnn_convolution_relu(x, self.head_w, self.head_b, one, zero, one, 1)   # [N,8,H,W] NHWC
-            flat = h.permute(0, 2, 3, 1).reshape(h.shape[0], -1)                                # view: pos*8 + ch
-            z = torch.addmm(self.head_dense_b, flat, self.head_dense_w)
-            parts = torch.split(z, self.head_splits, dim=1)
-            pols = [F.softmax(p.float(), dim=1) for p in parts[:-1]]
-            v = F.relu(parts[-1])
-            v = F.softmax(self.value_out(v).float(), dim=1)
-            return torch.cat(pols, dim=1).contiguous(), v.contiguous()
+    def _heads_fused(self, x):
+        if not getattr(self, 'fused_heads', False):
+            self._build_fused_heads()
+        one, zero = (1, 1), (0, 0)
+        h = torch.cudnn_convolution_relu(x, self.head_w, self.head_b, one, zero, one, 1)   # [N,8,H,W] NHWC
+        flat = h.permute(0, 2, 3, 1).reshape(h.shape[0], -1)                                # view: pos*8 + ch
+        z = torch.addmm(self.head_dense_b, flat, self.head_dense_w)
+        parts = torch.split(z, self.head_splits, dim=1)
+        pols = [F.softmax(p.float(), dim=1) for p in parts[:-1]]
+        v = F.relu(parts[-1])
+        v = F.softmax(self.value_out(v).float(), dim=1)
+        return torch.cat(pols, dim=1).contiguous(), v.contiguous()
+
+    def _heads_plain(self, x):
         pols = []
         for conv, dense in zip(self.policy_convs, self.policy_dense):
             p = F.relu(conv(x)).flatten(1)
@@ -227,6 +227,12 @@ class InferenceTower(nn.Module):
         v = F.relu(self.value_hidden(v))
         v = F.softmax(self.value_out(v).float(), dim=1)
         return torch.cat(pols, dim=1).contiguous(), v.contiguous()
+
+    def forward(self, planes):
+        x = self._tower(planes)
+        if planes.is_cuda and self.use_fused:
+            return self._heads_fused(x)
+        return self._heads_plain(x)
 
 
 def make_inference_network(transformer, size='small', seed=0, device='cuda', dtype=torch.bfloat16):
