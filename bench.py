@@ -312,7 +312,7 @@ def run_puct(args, rank, world, local):
     import torch
     from galvanise_zero_b200.engine import PuctEngine
     from galvanise_zero_b200.nn import make_inference_network
-    from galvanise_zero_b200.selfplay import SelfPlayPool
+    from galvanise_zero_b200.selfplay import SelfPlayPool, StaggeredSelfPlay
     from galvanise_zero_b200 import distributed as gzdist
 
     peaks = load_peaks()
@@ -326,7 +326,10 @@ def run_puct(args, rank, world, local):
                for k in range(P)]
     eng = engines[0]
     net = make_inference_network(eng.transformer, 'small', seed=1234, device=eng.device)
-    runner = SelfPlayPool(engines, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph)
+    if args.staggered and P > 1:
+        runner = StaggeredSelfPlay(engines, net, sub_iters=args.sub_iters)
+    else:
+        runner = SelfPlayPool(engines, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph)
     # bring the games to a desynchronised steady state (untimed), then warm up
     runner.step(args.presteps)
     runner.step(args.warmup)
@@ -387,7 +390,7 @@ def run_puct(args, rank, world, local):
     # ---- e2e: the reference-shaped numpy poll() API with host buffers (D2H planes, H2D planes for the
     # network as Keras predict_on_batch does, D2H policy/value, H2D into the engine), every step
     e2e = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.no_e2e:
         from galvanise_zero_b200 import interface
         sup = interface.Supervisor(PUCT_GAME, eng.c_transformer, G, 'bench', device=local, seed=0xE2E + rank,
                                    node_cap=2048, child_cap=2048 * 16)
@@ -553,6 +556,8 @@ def main():
     ap.add_argument('--presteps', type=int, default=3000)
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--pipelines', type=int, default=1)
+    ap.add_argument('--staggered', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--slots', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

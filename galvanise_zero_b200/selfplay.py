@@ -118,3 +118,88 @@ class SelfPlayPool(object):
     @property
     def kernels_per_step(self):
         return sum(r.kernels_per_step for r in self.runners)
+
+
+class StaggeredSelfPlay(object):
+    """Q engine shards whose tree kernels run on their own streams while ALL network forwards are
+    serialised on one stream. The tree kernels are latency-bound (pointer chasing) and the tower is
+    throughput-bound, so shard q's select/backup/expand hides behind the forwards of the other shards.
+    Engine and network parts of every shard are separate CUDA graphs chained by events:
+
+        eng stream q :  wait nn_done[q]  -> G_eng[q] -> record eng_done[q]
+        nn stream    :  wait eng_done[q] -> G_nn[q]  -> record nn_done[q]
+
+    This is the device-side counterpart of the reference's double-buffered managers
+    (``src/cpp/supervisor.cpp:79-99,196-231``)."""
+
+    def __init__(self, engines, net, sub_iters=1):
+        dev = engines[0].device
+        self.device = dev
+        self.engines = engines
+        self.net = net
+        self.sub_iters = sub_iters
+        torch.backends.cudnn.benchmark = True
+        self.eng_streams = [torch.cuda.Stream(device=dev) for _ in engines]
+        self.nn_stream = torch.cuda.Stream(device=dev)
+        self.eng_done = [torch.cuda.Event() for _ in engines]
+        self.nn_done = [torch.cuda.Event() for _ in engines]
+        self.g_eng, self.g_nn = [], []
+        cur = torch.cuda.current_stream(dev)
+        with torch.no_grad():
+            for e in engines:
+                e.advance(None, None, sub_iters)
+                self._forward(e)
+            torch.cuda.synchronize(dev)
+            for q, e in enumerate(engines):
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        e.advance(e.policy, e.value, sub_iters)
+                        self._forward(e)
+                cur.wait_stream(side)
+                torch.cuda.synchronize(dev)
+                ge = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ge):
+                    e.advance(e.policy, e.value, sub_iters)
+                gn = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gn):
+                    self._forward(e)
+                self.g_eng.append(ge)
+                self.g_nn.append(gn)
+            torch.cuda.synchronize(dev)
+            for q in range(len(engines)):
+                self.nn_done[q].record(cur)
+        self.steps_done = 0
+
+    def _forward(self, e):
+        x = e.planes.contiguous(memory_format=torch.channels_last)
+        pol, val = self.net(x)
+        e.policy.copy_(pol)
+        e.value.copy_(val)
+
+    def step(self, n=1):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.eng_streams + [self.nn_stream]:
+            s.wait_stream(cur)
+        Q = len(self.engines)
+        for _ in range(n):
+            for q in range(Q):
+                es = self.eng_streams[q]
+                es.wait_event(self.nn_done[q])
+                with torch.cuda.stream(es):
+                    self.g_eng[q].replay()
+                self.eng_done[q].record(es)
+                self.nn_stream.wait_event(self.eng_done[q])
+                with torch.cuda.stream(self.nn_stream):
+                    self.g_nn[q].replay()
+                self.nn_done[q].record(self.nn_stream)
+        for s in self.eng_streams + [self.nn_stream]:
+            cur.wait_stream(s)
+        self.steps_done += n
+
+    totals = SelfPlayPool.totals
+
+    @property
+    def kernels_per_step(self):
+        return len(self.engines) * (4 * self.sub_iters + 1)
