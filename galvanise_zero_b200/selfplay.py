@@ -139,7 +139,7 @@ class StaggeredSelfPlay(object):
         self.net = net
         self.sub_iters = sub_iters
         torch.backends.cudnn.benchmark = True
-        self.eng_streams = [torch.cuda.Stream(device=dev) for _ in engines]
+        self.eng_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in engines]   # tree kernels first
         self.nn_stream = torch.cuda.Stream(device=dev)
         self.eng_done = [torch.cuda.Event() for _ in engines]
         self.nn_done = [torch.cuda.Event() for _ in engines]
