@@ -516,8 +516,8 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
     // tile and are bound by the serial latency of the gate programs: give every tile a CTA of 4 or 8
     // warps that share its value array. Large batches keep one warp per tile, many tiles per CTA.
     int wpt = 1;
-    if (n_tiles * 8 <= (int64_t)pn->grid_max * 4) wpt = 8;
-    else if (n_tiles * 4 <= (int64_t)pn->grid_max * 8) wpt = 4;
+    if (n_tiles <= (int64_t)pn->grid_max) wpt = 8;
+    else if (n_tiles <= (int64_t)pn->grid_max * 2) wpt = 4;
     if (wpt > 1) {
         const size_t smem = (size_t)pn->P.staged_words * 4 + (size_t)pn->P.warp_words * 4;
         const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)pn->grid_max * 8);

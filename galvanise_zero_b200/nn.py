@@ -156,7 +156,22 @@ class InferenceTower(nn.Module):
             # cuDNN runtime-fused conv+bias+ReLU and conv+bias+residual-add+ReLU: one kernel per
             # convolution instead of conv + 1-2 elementwise passes over the 33 MB activation
             one = (1, 1)
-            x = torch.cudnn_convolution_relu(planes, self.stem.weight, self.stem.bias, one, one, one, 1)
+            cin = planes.shape[1]
+            if cin % 8:
+                # pad the input channels to a multiple of 8 (zero planes, zero weights): with e.g. 5
+                # channels cuDNN falls back to a generic NHWC kernel that costs 3x a tower convolution
+                if getattr(self, 'stem_w8', None) is None:
+                    pad = 8 - cin % 8
+                    w = torch.zeros((self.stem.out_channels, cin + pad) + tuple(self.stem.kernel_size),
+                                    device=planes.device, dtype=self.stem.weight.dtype)
+                    w[:, :cin] = self.stem.weight.detach()
+                    self.stem_w8 = w.contiguous(memory_format=torch.channels_last)
+                x8 = torch.zeros((planes.shape[0], self.stem_w8.shape[1]) + tuple(planes.shape[2:]),
+                                 device=planes.device, dtype=planes.dtype).contiguous(memory_format=torch.channels_last)
+                x8[:, :cin] = planes
+                x = torch.cudnn_convolution_relu(x8, self.stem_w8, self.stem.bias, one, one, one, 1)
+            else:
+                x = torch.cudnn_convolution_relu(planes, self.stem.weight, self.stem.bias, one, one, one, 1)
             for c0, c1 in self.blocks:
                 y = torch.cudnn_convolution_relu(x, c0.weight, c0.bias, one, one, one, 1)
                 x = torch.cudnn_convolution_add_relu(y, c1.weight, x, 1.0, c1.bias, one, one, one, 1)
