@@ -322,7 +322,8 @@ def run_puct(args, rank, world, local):
     P = max(1, args.pipelines)
     Gp = G // P
     engines = [PuctEngine(PUCT_GAME, sp, n_games=G // P, mode=0, device=local,
-                          seed=gzdist.rank_seed(0xB200, rank) + 104729 * k, node_cap=4096, child_cap=4096 * 16)
+                          seed=gzdist.rank_seed(0xB200, rank) + 104729 * k, node_cap=4096, child_cap=4096 * 16,
+                          plane_c_pad=16)
                for k in range(P)]
     eng = engines[0]
     net = make_inference_network(eng.transformer, 'small', seed=1234, device=eng.device)
@@ -359,7 +360,7 @@ def run_puct(args, rank, world, local):
     with torch.no_grad():
         reps = 10
         parts['engine_advance_ms'] = time_region(lambda: [eng.advance(eng.policy, eng.value, args.sub_iters) for _ in range(reps)], eng.device) / reps
-        x = eng.planes.contiguous(memory_format=torch.channels_last)
+        x = eng.planes
         side = torch.cuda.Stream(device=eng.device)
         side.wait_stream(torch.cuda.current_stream(eng.device))
         with torch.cuda.stream(side):

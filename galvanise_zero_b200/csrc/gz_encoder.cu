@@ -31,7 +31,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(ENC_THREADS)
 encode_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint32_t* __restrict__ states,
               const uint32_t* __restrict__ prev, const uint8_t* __restrict__ prev_count, int max_prev,
-              OutT* __restrict__ out) {
+              OutT* __restrict__ out, int c_pad) {
     extern __shared__ __align__(16) uint32_t esm[];
     uint32_t* cur = esm;                                      // [SB][sw]
     uint32_t* por = cur + ENC_STATES_PER_BLOCK * sw;          // [SB][sw]  OR of previous states
@@ -58,8 +58,13 @@ encode_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint
             ctrl[s * nc + c] = enc_control_value(E, cur + s * sw, c);
         }
         __syncthreads();
-        const int64_t flat0 = n0 * E.total;
-        const int64_t flat_n = (int64_t)nb * E.total;
+        // c_pad == 0: rows are [C][H][W] (NCHW, the reference layout). c_pad > 0: rows are
+        // [H][W][c_pad] (channels-last with the channel count padded with zero planes), the layout the
+        // tower's first convolution consumes without any conversion pass.
+        const int row_elems = c_pad > 0 ? E.channel_size * c_pad : E.total;
+        const int n_ch = E.total / E.channel_size;
+        const int64_t flat0 = n0 * row_elems;
+        const int64_t flat_n = (int64_t)nb * row_elems;
         // n0 is a multiple of 8 and rows are E.total elements: flat0 is a multiple of 8 elements
         for (int64_t v = threadIdx.x; v * 8 < flat_n; v += ENC_THREADS) {
             OutT vals[8];
@@ -69,10 +74,17 @@ encode_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint
                 const int64_t e = e0 + k;
                 float x = 0.0f;
                 if (e < flat_n) {
-                    const int s = (int)(e / E.total);
-                    const int le = (int)(e - (int64_t)s * E.total);
-                    x = enc_element(E, cur + s * sw, (prev && E.num_prev_states > 0) ? por + s * sw : nullptr,
-                                    ctrl + s * nc, le);
+                    const int s = (int)(e / row_elems);
+                    int le = (int)(e - (int64_t)s * row_elems);
+                    bool live = true;
+                    if (c_pad > 0) {
+                        const int pos = le / c_pad, c = le - pos * c_pad;
+                        live = c < n_ch;
+                        le = c * E.channel_size + pos;
+                    }
+                    if (live)
+                        x = enc_element(E, cur + s * sw, (prev && E.num_prev_states > 0) ? por + s * sw : nullptr,
+                                        ctrl + s * nc, le);
                 }
                 vals[k] = enc_cast<OutT>(x);
             }
@@ -198,14 +210,25 @@ extern "C" int gz_transformer_finalize(gz_transformer* t, int n_bases, int devic
     return GZ_OK;
 }
 
+extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
+                                const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
+                                int out_dtype, int c_pad, void* stream);
+
 extern "C" int gz_encode(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
                          const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
                          int out_dtype, void* stream) {
+    return gz_encode_layout(t, n, state_words, d_states, d_prev, d_prev_count, max_prev, d_out, out_dtype, 0, stream);
+}
+
+extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
+                                const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
+                                int out_dtype, int c_pad, void* stream) {
     if (!t || !t->finalized) { gz_set_error("transformer is null or not finalised"); return GZ_ERR_ARG; }
     if (n < 0 || state_words * 32 < t->n_bases) { gz_set_error("bad batch / state_words"); return GZ_ERR_ARG; }
     if (n == 0) return GZ_OK;
     if (!d_states || !d_out) { gz_set_error("null device pointer"); return GZ_ERR_ARG; }
     if (d_prev && max_prev < 1) { gz_set_error("max_prev must be >= 1 with previous states"); return GZ_ERR_ARG; }
+    if (c_pad != 0 && (c_pad < t->E.total / t->E.channel_size || (c_pad & 7))) { gz_set_error("c_pad must be a multiple of 8 and >= the channel count"); return GZ_ERR_ARG; }
     if ((((uintptr_t)d_out) & 15) != 0) { gz_set_error("plane buffer must be 16-byte aligned"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(t->device));
     const size_t smem = (size_t)ENC_STATES_PER_BLOCK * (2 * state_words * 4 + t->num_control_channels * 4) + 16;
@@ -215,12 +238,12 @@ extern "C" int gz_encode(gz_transformer* t, int64_t n, int state_words, const ui
         if (smem > 48 * 1024)
             GZ_CUDA(cudaFuncSetAttribute(encode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         encode_kernel<__nv_bfloat16><<<grid, ENC_THREADS, smem, (cudaStream_t)stream>>>(
-            t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (__nv_bfloat16*)d_out);
+            t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (__nv_bfloat16*)d_out, c_pad);
     } else if (out_dtype == GZ_DTYPE_F32) {
         if (smem > 48 * 1024)
             GZ_CUDA(cudaFuncSetAttribute(encode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         encode_kernel<float><<<grid, ENC_THREADS, smem, (cudaStream_t)stream>>>(
-            t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (float*)d_out);
+            t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (float*)d_out, c_pad);
     } else {
         gz_set_error("bad out_dtype");
         return GZ_ERR_ARG;

@@ -35,6 +35,9 @@
 #include "gz_transformer.h"
 
 extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn);   // gz_propnet.cu (device pointer)
+extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
+                                const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
+                                int out_dtype, int c_pad, void* stream);
 
 #define PUCT_WARPS_PER_BLOCK 4
 
@@ -197,6 +200,7 @@ struct gz_puct {
     int mode = 0;
     int total_size = 0;
     int cache_words = 0;      // per-warp shared-memory words for the child cache (0: use the global scratch)
+    int plane_c_pad = 0;      // 0: planes are NCHW rows; >0: channels-last rows padded to this channel count
 };
 
 static void fill_puct_conf(PuctConf& p, const double* c) {
@@ -372,9 +376,18 @@ extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d
     if (d_planes) {
         // every row is encoded (rows of games that do not wait for the network hold a stale but valid
         // state; their network outputs are never read)
-        int rc = gz_encode(h->tr, E.G, E.SW, E.x_state, E.x_in_state, E.x_prevcnt, 1, d_planes, plane_dtype, stream);
+        int rc = gz_encode_layout(h->tr, E.G, E.SW, E.x_state, E.x_in_state, E.x_prevcnt, 1, d_planes, plane_dtype,
+                                  h->plane_c_pad, stream);
         if (rc != GZ_OK) return rc;
     }
+    return GZ_OK;
+}
+
+// Planes layout written by gz_puct_advance: c_pad == 0 -> [G][C][H][W]; c_pad > 0 (multiple of 8) ->
+// channels-last [G][H][W][c_pad] with zero planes beyond C.
+extern "C" int gz_puct_set_plane_layout(gz_puct* h, int c_pad) {
+    if (!h || c_pad < 0 || (c_pad & 7) || (c_pad && c_pad < h->tr->E.total / h->tr->E.channel_size)) { gz_set_error("bad plane layout"); return GZ_ERR_ARG; }
+    h->plane_c_pad = c_pad;
     return GZ_OK;
 }
 

@@ -79,7 +79,7 @@ class PuctEngine(object):
 
     def __init__(self, game, sp_conf=None, n_games=1024, mode=0, device=0, seed=0x5EED0000,
                  node_cap=4096, child_cap=None, generation=None, sm=None, c_transformer=None,
-                 max_pending_samples=128, ready_cap=1 << 16, plane_dtype=torch.bfloat16):
+                 max_pending_samples=128, ready_cap=1 << 16, plane_dtype=torch.bfloat16, plane_c_pad=0):
         self._L = _lib.lib()
         _declare(self._L)
         self.game = game
@@ -115,7 +115,15 @@ class PuctEngine(object):
         self.ready_cap = info(8)
         tr = self.transformer
         self.plane_shape = (tr.num_channels, tr.num_cols, tr.num_rows)
-        self.planes = torch.zeros((n_games,) + self.plane_shape, dtype=plane_dtype, device=self.device)
+        self.plane_c_pad = plane_c_pad
+        if plane_c_pad:
+            # channels-last, channel count padded: logical [G, c_pad, H, W] over [G, H, W, c_pad] memory
+            self._L.gz_puct_set_plane_layout.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            _lib.check(self._L.gz_puct_set_plane_layout(self._h, plane_c_pad))
+            mem = torch.zeros((n_games, tr.num_cols, tr.num_rows, plane_c_pad), dtype=plane_dtype, device=self.device)
+            self.planes = mem.permute(0, 3, 1, 2)
+        else:
+            self.planes = torch.zeros((n_games,) + self.plane_shape, dtype=plane_dtype, device=self.device)
         self.policy = torch.zeros((n_games, self.policy_stride), dtype=torch.float32, device=self.device)
         self.value = torch.zeros((n_games, self.n_rewards), dtype=torch.float32, device=self.device)
         self._fresh = False

@@ -36,6 +36,7 @@ def _declare(L):
     L.gz_transformer_finalize.argtypes = [vp, ci, ci]
     L.gz_transformer_total_size.argtypes = [vp]
     L.gz_encode.argtypes = [vp, i64, ci, vp, vp, vp, ci, vp, ci, vp]
+    L.gz_encode_layout.argtypes = [vp, i64, ci, vp, vp, vp, ci, vp, ci, ci, vp]
     L._gz_tr_declared = True
 
 
@@ -93,7 +94,7 @@ class GdlBasesTransformer(object):
             self._finalized_for = (int(n_bases), int(device))
         return self
 
-    def encode(self, states, prev_states=None, prev_count=None, out=None, dtype=None):
+    def encode(self, states, prev_states=None, prev_count=None, out=None, dtype=None, c_pad=0):
         """states int32 [n, sw] (CUDA) -> planes [n, total_size] (bf16 default, or float32).
         prev_states int32 [n, max_prev, sw], nearest ancestor first; prev_count uint8 [n]."""
         import torch
@@ -102,9 +103,10 @@ class GdlBasesTransformer(object):
         n, sw = states.shape
         if dtype is None:
             dtype = out.dtype if out is not None else torch.bfloat16
+        row = self.channel_size * c_pad if c_pad else self.total_size()   # c_pad: [n][H*W][c_pad] rows
         if out is None:
-            out = torch.empty((n, self.total_size()), dtype=dtype, device=states.device)
-        assert out.is_contiguous() and out.shape[0] == n and out[0].numel() == self.total_size()
+            out = torch.empty((n, row), dtype=dtype, device=states.device)
+        assert out.is_contiguous() and out.shape[0] == n and out[0].numel() == row
         code = {torch.float32: 0, torch.bfloat16: 1}[out.dtype]
         max_prev = 0
         pp = pc = None
@@ -117,8 +119,8 @@ class GdlBasesTransformer(object):
                 assert prev_count.dtype == torch.uint8 and prev_count.shape == (n,)
                 pc = prev_count.data_ptr()
         stream = ctypes.c_void_p(torch.cuda.current_stream(states.device).cuda_stream)
-        _lib.check(self._L.gz_encode(self._h, n, sw, states.data_ptr(), pp, pc, max_prev,
-                                     out.data_ptr(), code, stream))
+        _lib.check(self._L.gz_encode_layout(self._h, n, sw, states.data_ptr(), pp, pc, max_prev,
+                                            out.data_ptr(), code, c_pad, stream))
         return out
 
 

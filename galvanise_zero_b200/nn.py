@@ -157,19 +157,16 @@ class InferenceTower(nn.Module):
             # convolution instead of conv + 1-2 elementwise passes over the 33 MB activation
             one = (1, 1)
             cin = planes.shape[1]
-            if cin % 8:
-                # pad the input channels to a multiple of 8 (zero planes, zero weights): with e.g. 5
-                # channels cuDNN falls back to a generic NHWC kernel that costs 3x a tower convolution
-                if getattr(self, 'stem_w8', None) is None:
-                    pad = 8 - cin % 8
-                    w = torch.zeros((self.stem.out_channels, cin + pad) + tuple(self.stem.kernel_size),
+            if cin != self.stem.in_channels:
+                # the engine can hand over channels-last planes whose channel count is padded with zero
+                # planes (PuctEngine(plane_c_pad=16)): pad the stem weights with zeros to match, so the
+                # first convolution runs the same tensor-core kernel family as the tower
+                if getattr(self, 'stem_wpad', None) is None or self.stem_wpad.shape[1] != cin:
+                    w = torch.zeros((self.stem.out_channels, cin) + tuple(self.stem.kernel_size),
                                     device=planes.device, dtype=self.stem.weight.dtype)
-                    w[:, :cin] = self.stem.weight.detach()
-                    self.stem_w8 = w.contiguous(memory_format=torch.channels_last)
-                x8 = torch.zeros((planes.shape[0], self.stem_w8.shape[1]) + tuple(planes.shape[2:]),
-                                 device=planes.device, dtype=planes.dtype).contiguous(memory_format=torch.channels_last)
-                x8[:, :cin] = planes
-                x = torch.cudnn_convolution_relu(x8, self.stem_w8, self.stem.bias, one, one, one, 1)
+                    w[:, :self.stem.in_channels] = self.stem.weight.detach()
+                    self.stem_wpad = w.contiguous(memory_format=torch.channels_last)
+                x = torch.cudnn_convolution_relu(planes, self.stem_wpad, self.stem.bias, one, one, one, 1)
             else:
                 x = torch.cudnn_convolution_relu(planes, self.stem.weight, self.stem.bias, one, one, one, 1)
             for c0, c1 in self.blocks:

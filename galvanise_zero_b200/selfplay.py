@@ -34,7 +34,7 @@ class SelfPlayRunner(object):
 
     def _forward(self):
         e = self.engine
-        x = e.planes.contiguous(memory_format=torch.channels_last)
+        x = e.planes if e.plane_c_pad else e.planes.contiguous(memory_format=torch.channels_last)
         pol, val = self.net(x)
         e.policy.copy_(pol)
         e.value.copy_(val)
@@ -173,7 +173,7 @@ class StaggeredSelfPlay(object):
         self.steps_done = 0
 
     def _forward(self, e):
-        x = e.planes.contiguous(memory_format=torch.channels_last)
+        x = e.planes if e.plane_c_pad else e.planes.contiguous(memory_format=torch.channels_last)
         pol, val = self.net(x)
         e.policy.copy_(pol)
         e.value.copy_(val)

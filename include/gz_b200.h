@@ -119,6 +119,10 @@ int gz_transformer_total_size(const gz_transformer* t);
 int gz_encode(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
               const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
               int out_dtype, void* stream);
+/* same, with the output layout selectable: c_pad == 0 -> NCHW rows; c_pad > 0 -> [n][H][W][c_pad] */
+int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
+                     const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
+                     int out_dtype, int c_pad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched PUCT self-play engine. Replaces the reference's Supervisor / SelfPlayManager / SelfPlay /
@@ -156,6 +160,9 @@ int gz_puct_set_config(gz_puct* h, const double* sp_conf, const double* puct_con
 int64_t gz_puct_info(const gz_puct* h, int what);
 int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
                     void* d_planes, int plane_dtype, void* stream);
+/* planes written by gz_puct_advance: c_pad == 0 -> [G][C][H][W] (reference layout, default);
+ * c_pad > 0 (multiple of 8) -> channels-last [G][H][W][c_pad], zero planes beyond C */
+int gz_puct_set_plane_layout(gz_puct* h, int c_pad);
 const uint8_t* gz_puct_need_eval_ptr(const gz_puct* h);
 int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream);
 int gz_puct_totals(gz_puct* h, double* h_out19, void* stream);

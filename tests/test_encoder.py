@@ -113,3 +113,21 @@ def test_gpu_encoder_multi_prev_quirk_and_tail():
                     torch.from_numpy(prev.view(np.int32).copy()).to(dev),
                     torch.from_numpy(cnt).to(dev), dtype=torch.float32).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('game,c_pad', [('reversi', 8), ('reversi', 16), ('amazons_10x10', 16)])
+def test_gpu_encoder_channels_last_padded_layout(game, c_pad):
+    """The additive [n][H][W][c_pad] layout holds exactly the reference planes, permuted, plus zero planes."""
+    import torch
+    gi, tr, ct = _setup(game)
+    ct.finalize(tr.num_bases, 0)
+    enc = RefEncoder.from_c_transformer(ct)
+    hist = _trajectory(game, n_games=19, plies=12)
+    cur, prev = hist[11], hist[10][:, None, :]
+    want = enc.encode(cur, prev).reshape(19, tr.num_channels, tr.channel_size)
+    dev = torch.device('cuda', 0)
+    got = ct.encode(torch.from_numpy(cur.view(np.int32)).to(dev), torch.from_numpy(prev.view(np.int32).copy()).to(dev),
+                    dtype=torch.bfloat16, c_pad=c_pad).float().cpu().numpy().reshape(19, tr.channel_size, c_pad)
+    assert np.array_equal(got[:, :, :tr.num_channels], want.transpose(0, 2, 1))
+    assert not got[:, :, tr.num_channels:].any()
