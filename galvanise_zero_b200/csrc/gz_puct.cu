@@ -45,15 +45,39 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
 // stores), which keeps the warp converged and lets the lanes cooperate where it pays: staging a
 // node's children and their statistics in shared memory (gzp_cache_fill), gathering the policy row
 // (gzp_reply), copying sample records. Atomics are issued by lane 0 only.
+#define PUCT_CTL_WORDS ((int)((sizeof(GameCtl) + 3) / 4))
 __global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32, 8)
 puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_words) {
     extern __shared__ __align__(16) uint32_t puct_smem[];
+    // per warp: the game's controller record and playout path live in shared memory while the kernel
+    // runs (they are read and written dozens of times per playout; through global memory every
+    // read-after-write is an L2 round trip), followed by the child cache
+    __shared__ __align__(16) uint32_t ctl_sm[PUCT_WARPS_PER_BLOCK][PUCT_CTL_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * PUCT_WARPS_PER_BLOCK + warp;
     if (g >= E.G) return;
-    uint32_t* cmem = cache_words > 0 ? puct_smem + (size_t)warp * cache_words : nullptr;
+    uint32_t* cmem = cache_words > 0 ? puct_smem + (size_t)warp * (cache_words + 2 * E.MAXD) : nullptr;
     GameView V = gzp_view(&E, g, lane, cmem);
+    uint32_t* gctl = reinterpret_cast<uint32_t*>(&E.ctl[g]);
+    for (int i = lane; i < PUCT_CTL_WORDS; i += 32) ctl_sm[warp][i] = gctl[i];
+    __syncwarp();
+    V.c = reinterpret_cast<GameCtl*>(ctl_sm[warp]);
+    int32_t *gpn = V.pn, *gpc = V.pc;
+    if (cmem) {
+        int32_t* spn = reinterpret_cast<int32_t*>(cmem + cache_words);
+        int32_t* spc = spn + E.MAXD;
+        const int pl = V.c->path_len;
+        for (int i = lane; i < pl; i += 32) { spn[i] = gpn[i]; spc[i] = gpc[i]; }
+        __syncwarp();
+        V.pn = spn; V.pc = spc;
+    }
     gzp_step_pre(V, nn_fresh != 0);
+    __syncwarp();
+    if (cmem) {
+        const int pl = V.c->path_len;
+        for (int i = lane; i < pl; i += 32) { gpn[i] = V.pn[i]; gpc[i] = V.pc[i]; }
+    }
+    for (int i = lane; i < PUCT_CTL_WORDS; i += 32) gctl[i] = ctl_sm[warp][i];
 }
 
 __global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32)
@@ -257,7 +281,7 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     E.LW = (int)gz_propnet_info(pn, GZ_INFO_LEGAL_WORDS);
     E.NCAP = node_cap;
     E.CCAP = child_cap;
-    E.MAXD = 512;
+    E.MAXD = 128;     // longest playout path (plies below the root)
     E.n_rewards = tr->num_rewards;
     int off = 0, maxa = 0;
     std::vector<int> rso;
@@ -308,7 +332,7 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     h->total_size = tr->E.total;
     {
         const size_t words = gzp_cache_words(E.max_actions);
-        const size_t bytes = words * 4 * PUCT_WARPS_PER_BLOCK;
+        const size_t bytes = (words + 2 * (size_t)E.MAXD) * 4 * PUCT_WARPS_PER_BLOCK;
         if (bytes <= 96 * 1024) {
             h->cache_words = (int)words;
             if (bytes > 48 * 1024)
@@ -362,7 +386,8 @@ extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d
     cudaStream_t s = (cudaStream_t)stream;
     const int blocks = (E.G + PUCT_WARPS_PER_BLOCK - 1) / PUCT_WARPS_PER_BLOCK;
     for (int it = 0; it < sub_iters; it++) {
-        puct_pre_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, (size_t)h->cache_words * 4 * PUCT_WARPS_PER_BLOCK, s>>>(
+        puct_pre_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32,
+                          h->cache_words ? ((size_t)h->cache_words + 2 * (size_t)E.MAXD) * 4 * PUCT_WARPS_PER_BLOCK : 0, s>>>(
             E, (it == 0 && nn_fresh) ? 1 : 0, h->cache_words);
         GZ_CUDA(cudaGetLastError());
         puct_reroot_kernel<<<E.G, REROOT_THREADS, 0, s>>>(E);

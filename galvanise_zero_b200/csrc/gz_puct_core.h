@@ -363,6 +363,7 @@ struct GameView {
     GameCtl* c;
     int64_t nb, cb;   // node / child base index of the active arena
     int lane;         // 0..31 on the device (all lanes run the controller redundantly), 0 on the host
+    int32_t *pn, *pc; // playout path (node, chosen child); global rows, or a shared-memory copy on the device
     ChildCache C;
 };
 
@@ -380,6 +381,8 @@ GZP_HD GameView gzp_view(const PuctEngine* E, int g, int lane = 0, uint32_t* cac
     v.nb = (int64_t)g * E->NCAP;
     v.cb = (int64_t)g * E->CCAP;
     v.lane = lane;
+    v.pn = E->path_node + (int64_t)g * E->MAXD;
+    v.pc = E->path_choice + (int64_t)g * E->MAXD;
     if (!cache_mem) cache_mem = E->x_cache + (int64_t)g * gzp_cache_words(E->max_actions);
     gzp_cache_bind(v.C, cache_mem, E->max_actions);
     return v;
@@ -728,8 +731,8 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
     if (c->path_len >= E->MAXD) { c->error = GZP_ERR_PATH; return -1; }
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
     const int lead = NODE(n_lead, n);
-    int32_t* pn = E->path_node + (int64_t)V.g * E->MAXD;
-    int32_t* pc = E->path_choice + (int64_t)V.g * E->MAXD;
+    int32_t* pn = V.pn;
+    int32_t* pc = V.pc;
 
     // setPuctConstant (evaluator.cpp:1300-1307)
     {
@@ -834,8 +837,8 @@ GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
     GameCtl* c = V.c;
     const PuctConf& cf = gzp_conf(V);
     const int R = E->R;
-    const int32_t* pn = E->path_node + (int64_t)V.g * E->MAXD;
-    const int32_t* pc = E->path_choice + (int64_t)V.g * E->MAXD;
+    const int32_t* pn = V.pn;
+    const int32_t* pc = V.pc;
     bool bp_finalised_only_once = cf.backup_finalised != 0;
     for (int index = c->path_len - 1; index >= 0; index--) {
         const int n = pn[index];
@@ -1351,8 +1354,8 @@ GZP_HDN void gzp_path_push(GameView& V, int n, int choice) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     if (c->path_len >= E->MAXD) { c->error = GZP_ERR_PATH; return; }
-    E->path_node[(int64_t)V.g * E->MAXD + c->path_len] = n;
-    E->path_choice[(int64_t)V.g * E->MAXD + c->path_len] = choice;
+    V.pn[c->path_len] = n;
+    V.pc[c->path_len] = choice;
     c->path_len++;
 }
 
