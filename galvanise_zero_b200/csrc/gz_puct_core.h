@@ -581,20 +581,30 @@ template <typename Cmp>
 GZP_HDN void gzp_order_children(GameView& V, int nc, Cmp cmp) {
     int* order = V.C.order;
 #ifdef __CUDA_ARCH__
-    if (nc <= 16) {
-        __syncwarp();
-        if (V.lane < nc) {
-            const int i = V.lane;
-            int rank = 0;
-            for (int j = 0; j < nc; j++) {
-                if (j == i) continue;
-                if (cmp(j, i) || (!cmp(i, j) && j < i)) rank++;
-            }
-            order[rank] = i;
+    // Every lane ranks its children directly: rank(i) = #{j before i} under the stable order.
+    //  * n <= 16: std::sort IS a stable insertion sort, so this is exact.
+    //  * n  > 16: introsort is not stable, but when no two children compare equivalent the sorted
+    //    order is unique and any correct sort agrees with it; only in the presence of ties the
+    //    restated introsort below decides (sequentially, as the reference's library would).
+    __syncwarp();
+    bool tie = false;
+    for (int i = V.lane; i < nc; i += 32) {
+        int rank = 0;
+        for (int j = 0; j < nc; j++) {
+            if (j == i) continue;
+            const bool ji = cmp(j, i), ij = cmp(i, j);
+            if (ji || (!ij && j < i)) rank++;
+            if (!ji && !ij) tie = true;
         }
+        reinterpret_cast<int*>(V.C.tmp)[i] = rank;
+    }
+    const bool any_tie = __any_sync(0xffffffffu, tie);
+    if (nc <= 16 || !any_tie) {
+        for (int i = V.lane; i < nc; i += 32) order[reinterpret_cast<int*>(V.C.tmp)[i]] = i;
         __syncwarp();
         return;
     }
+    __syncwarp();
 #endif
     for (int i = 0; i < nc; i++) order[i] = i;
     gzp_std_sort(order, nc, cmp);
