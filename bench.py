@@ -396,28 +396,57 @@ def run_puct(args, rank, world, local):
         sup = interface.Supervisor(PUCT_GAME, eng.c_transformer, G, 'bench', device=local, seed=0xE2E + rank,
                                    node_cap=2048, child_cap=2048 * 16)
         import attr
-        sup.start_self_play(0, attr.asdict(sp))
+        # worker mode = the reference's double-buffered managers (supervisor.cpp:79-99): two managers of
+        # G/2 games; the engine step of one overlaps the network call on the other's batch
+        sup.start_self_play(0 if args.e2e_inline else 1, attr.asdict(sp))
         R = len(eng.role_sizes)
         h2d = d2h = 0
+        G = max(m.engine.n_games for m in sup.managers)       # rows per poll
 
         pin_pol = torch.empty((G, eng.policy_stride), dtype=torch.float32).pin_memory()
         pin_val = torch.empty((G, eng.n_rewards), dtype=torch.float32).pin_memory()
+        # the user's network call (the reference's model.predict_on_batch): host planes in, host
+        # predictions out; the forward itself is a CUDA graph over a fixed-size device batch
+        x_dev = torch.zeros((G,) + eng.plane_shape, dtype=torch.float32, device=eng.device)
+        pol_dev = torch.zeros((G, eng.policy_stride), dtype=torch.float32, device=eng.device)
+        val_dev = torch.zeros((G, eng.n_rewards), dtype=torch.float32, device=eng.device)
+
+        def nn_static():
+            xb = x_dev.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            p_, v_ = net(xb)
+            pol_dev.copy_(p_)
+            val_dev.copy_(v_)
+        with torch.no_grad():
+            side2 = torch.cuda.Stream(device=eng.device)
+            side2.wait_stream(torch.cuda.current_stream(eng.device))
+            with torch.cuda.stream(side2):
+                for _ in range(3):
+                    nn_static()
+            torch.cuda.current_stream(eng.device).wait_stream(side2)
+            torch.cuda.synchronize(eng.device)
+            g_e2e = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_e2e):
+                nn_static()
+
+        t_poll = t_nn = 0.0
 
         def e2e_step(pred):
-            nonlocal h2d, d2h
+            nonlocal h2d, d2h, t_poll, t_nn
             n, arrays = pred
+            tp0 = time.perf_counter()
             planes = sup.poll(n, arrays)                 # numpy view of pinned engine memory
+            tp1 = time.perf_counter()
+            t_poll += tp1 - tp0
             if planes is None:
                 return (0, [])
             n_req = planes.size // eng.total_size
             d2h += planes.nbytes
             xin = torch.from_numpy(planes).view((n_req,) + eng.plane_shape)
-            xd = xin.to(eng.device, non_blocking=True).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            x_dev[:n_req].copy_(xin, non_blocking=True)
             h2d += planes.nbytes
-            with torch.no_grad():
-                pol, val = net(xd)
-            pin_pol[:n_req].copy_(pol, non_blocking=True)
-            pin_val[:n_req].copy_(val, non_blocking=True)
+            g_e2e.replay()
+            pin_pol[:n_req].copy_(pol_dev[:n_req], non_blocking=True)
+            pin_val[:n_req].copy_(val_dev[:n_req], non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
             pol_h = pin_pol.numpy()[:n_req]
             val_h = pin_val.numpy()[:n_req]
@@ -429,27 +458,32 @@ def run_puct(args, rank, world, local):
                 arrs.append(np.ascontiguousarray(pol_h[:, off:off + eng.role_sizes[r]]))
                 off += eng.role_sizes[r]
             arrs.append(np.ascontiguousarray(val_h))
+            t_nn += time.perf_counter() - tp1
             return (n_req, arrs)
 
         pred = (0, [])
         for _ in range(min(args.presteps, 600)):
             pred = e2e_step(pred)
-        m0 = sup.engine.totals()
+        m0 = sup.totals()
         h2d = d2h = 0
-        reps = max(20, min(args.steps, 200))
+        t_poll = t_nn = 0.0
+        reps = max(20, min(args.steps, 200)) * len(sup.managers)
         barrier(world)
         t0 = time.perf_counter()
         for _ in range(reps):
             pred = e2e_step(pred)
         torch.cuda.synchronize()
         dt = all_max(time.perf_counter() - t0, world, eng.device)
-        m1 = sup.engine.totals()
+        m1 = sup.totals()
         e2e_moves = all_sum(m1['moves'] - m0['moves'], world, eng.device)
         e2e_evals = all_sum(m1['evals'] - m0['evals'], world, eng.device)
-        e2e = {'value': e2e_moves / dt, 'unit': 'moves/s', 'h2d_bytes_per_step': int(h2d / reps),
-               'd2h_bytes_per_step': int(d2h / reps), 'evals_per_s': e2e_evals / dt,
+        e2e = {'value': e2e_moves / dt, 'unit': 'moves/s', 'h2d_bytes_per_step': int(h2d / reps) * len(sup.managers),
+               'd2h_bytes_per_step': int(d2h / reps) * len(sup.managers), 'evals_per_s': e2e_evals / dt,
                'api': 'interface.Supervisor.poll (numpy in / numpy out, reference contract), network fed from pinned host memory',
-               'steps': reps}
+               'managers': '%d x %d games (%s)' % (len(sup.managers), G, 'inline' if len(sup.managers) == 1 else
+                                                   'worker mode: engine step of one manager overlaps the network call of the other'),
+               'polls': reps, 'host_ms_per_poll': {'poll': t_poll * 1e3 / reps, 'network_call': t_nn * 1e3 / reps}}
+        G = args.slots or PUCT_GAMES_PER_GPU
 
     # ---- end of 'generation': gather the finished samples to rank 0 (the only collective; untimed)
     recs = np.concatenate([e.fetch_sample_records() for e in engines], axis=0)
@@ -559,6 +593,7 @@ def main():
     ap.add_argument('--pipelines', type=int, default=1)
     ap.add_argument('--staggered', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--e2e-inline', action='store_true')
     ap.add_argument('--slots', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

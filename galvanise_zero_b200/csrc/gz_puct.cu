@@ -225,6 +225,21 @@ struct gz_puct {
     int total_size = 0;
     int cache_words = 0;      // per-warp shared-memory words for the child cache (0: use the global scratch)
     int plane_c_pad = 0;      // 0: planes are NCHW rows; >0: channels-last rows padded to this channel count
+    struct HostPoll* hp = nullptr;   // host-buffer poll state (gz_puct_host_poll_*), created on first use
+};
+
+// State of the host-buffer poll (the reference's numpy Supervisor.poll contract): pinned hand-off
+// buffers on the host, staging + compaction buffers on the device, one event per engine.
+struct HostPoll {
+    float *h_pol = nullptr, *h_val = nullptr, *h_planes = nullptr;   // pinned
+    int* h_count = nullptr;                                          // pinned
+    float *d_stage_pol = nullptr, *d_stage_val = nullptr;            // [G][..] predictions in hand-out order
+    float *d_pol = nullptr, *d_val = nullptr;                        // [G][..] predictions in game order
+    float *d_planes = nullptr, *d_planes_c = nullptr;                // [G][total] all games / compacted
+    int *d_rows = nullptr, *d_count = nullptr;
+    cudaEvent_t ev = nullptr;
+    int outstanding = 0;      // rows handed out by the last wait
+    bool in_flight = false;
 };
 
 static void fill_puct_conf(PuctConf& p, const double* c) {
@@ -352,6 +367,17 @@ extern "C" void gz_puct_destroy(gz_puct* h) {
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->d_totals) cudaFree(h->d_totals);
     if (h->d_role_sizes_off) cudaFree(h->d_role_sizes_off);
+    if (h->hp) {
+        HostPoll* q = h->hp;
+        if (q->h_pol) cudaFreeHost(q->h_pol);
+        if (q->h_val) cudaFreeHost(q->h_val);
+        if (q->h_planes) cudaFreeHost(q->h_planes);
+        if (q->h_count) cudaFreeHost(q->h_count);
+        void* dv[] = {q->d_stage_pol, q->d_stage_val, q->d_pol, q->d_val, q->d_planes, q->d_planes_c, q->d_rows, q->d_count};
+        for (void* d : dv) if (d) cudaFree(d);
+        if (q->ev) cudaEventDestroy(q->ev);
+        delete q;
+    }
     delete h;
 }
 
@@ -426,6 +452,155 @@ extern "C" int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream) 
     return GZ_OK;
 }
 
+// ---- host-buffer poll ---------------------------------------------------------------------------
+// The reference's Supervisor.poll contract (src/cpp/pyobjects/common.cpp:160-218, src/cpp/supervisor.cpp:
+// 101-168) with HOST buffers on both sides: predictions arrive as R policy arrays [n][A_r] + one value
+// array [n][rewards] in the order the rows were handed out; the planes of the games that now wait for
+// the network leave as [n_req][total] float32 in pinned memory owned by the engine.
+// submit() stages the predictions and enqueues copy-in, scatter, the engine step, compaction, gather
+// and copy-out on `stream` without waiting; wait() blocks on the engine's event. Two engines polled
+// alternately overlap one engine's step with the caller's network call on the other's batch (the
+// reference's two managers per worker, supervisor.cpp:79-99).
+__global__ void hostpoll_scatter_kernel(const float* __restrict__ sp, const float* __restrict__ sv,
+                                        const int* __restrict__ rows, int n, int stride, int nrew,
+                                        float* __restrict__ pol, float* __restrict__ val) {
+    const int per = stride + nrew;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * per; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / per), c = (int)(i % per);
+        const int g = rows[r];
+        if (c < stride) pol[(int64_t)g * stride + c] = sp[(int64_t)r * stride + c];
+        else val[(int64_t)g * nrew + (c - stride)] = sv[(int64_t)r * nrew + (c - stride)];
+    }
+}
+
+// single CTA: rows[] = indices of games with need_eval set, ascending; *count = how many
+__global__ void __launch_bounds__(1024) hostpoll_compact_kernel(const uint8_t* __restrict__ need, int G,
+                                                                int* __restrict__ rows, int* __restrict__ count) {
+    __shared__ int wsum[32];
+    __shared__ int base_sm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_sm = 0;
+    __syncthreads();
+    for (int g0 = 0; g0 < G; g0 += 1024) {
+        const int g = g0 + threadIdx.x;
+        const bool f = g < G && need[g] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[warp] = __popc(b);
+        __syncthreads();
+        int pre = 0, tot = 0;
+        for (int w = 0; w < 32; w++) { const int v = wsum[w]; if (w < warp) pre += v; tot += v; }
+        const int base = base_sm;
+        if (f) rows[base + pre + __popc(b & ((1u << lane) - 1))] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) base_sm = base + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base_sm;
+}
+
+__global__ void hostpoll_gather_kernel(const float* __restrict__ planes, const int* __restrict__ rows,
+                                       const int* __restrict__ count, int total, float* __restrict__ out) {
+    const int n = *count;
+    if ((total & 3) == 0) {
+        const int t4 = total >> 2;
+        const float4* src = reinterpret_cast<const float4*>(planes);
+        float4* dst = reinterpret_cast<float4*>(out);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * t4; i += (int64_t)gridDim.x * blockDim.x) {
+            const int r = (int)(i / t4), c = (int)(i % t4);
+            dst[i] = src[(int64_t)rows[r] * t4 + c];
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int r = (int)(i / total), c = (int)(i % total);
+            out[i] = planes[(int64_t)rows[r] * total + c];
+        }
+    }
+}
+
+static int hostpoll_init(gz_puct* h) {
+    if (h->hp) return GZ_OK;
+    if (h->plane_c_pad) { gz_set_error("host polls need the reference plane layout (plane_c_pad == 0)"); return GZ_ERR_ARG; }
+    HostPoll* q = new HostPoll();
+    const size_t G = (size_t)h->E.G, st = (size_t)h->E.policy_stride, nr = (size_t)h->E.n_rewards, tot = (size_t)h->total_size;
+    GZ_CUDA(cudaSetDevice(h->device));
+    GZ_CUDA(cudaHostAlloc((void**)&q->h_pol, G * st * 4, cudaHostAllocDefault));
+    GZ_CUDA(cudaHostAlloc((void**)&q->h_val, G * nr * 4, cudaHostAllocDefault));
+    GZ_CUDA(cudaHostAlloc((void**)&q->h_planes, G * tot * 4, cudaHostAllocDefault));
+    GZ_CUDA(cudaHostAlloc((void**)&q->h_count, 64, cudaHostAllocDefault));
+    GZ_CUDA(cudaMalloc((void**)&q->d_stage_pol, G * st * 4));
+    GZ_CUDA(cudaMalloc((void**)&q->d_stage_val, G * nr * 4));
+    GZ_CUDA(cudaMalloc((void**)&q->d_pol, G * st * 4));
+    GZ_CUDA(cudaMalloc((void**)&q->d_val, G * nr * 4));
+    GZ_CUDA(cudaMalloc((void**)&q->d_planes, G * tot * 4));
+    GZ_CUDA(cudaMalloc((void**)&q->d_planes_c, G * tot * 4));
+    GZ_CUDA(cudaMalloc((void**)&q->d_rows, G * 4));
+    GZ_CUDA(cudaMalloc((void**)&q->d_count, 64));
+    GZ_CUDA(cudaMemset(q->d_pol, 0, G * st * 4));
+    GZ_CUDA(cudaMemset(q->d_val, 0, G * nr * 4));
+    GZ_CUDA(cudaMemset(q->d_rows, 0, G * 4));
+    GZ_CUDA(cudaMemset(q->d_count, 0, 64));
+    GZ_CUDA(cudaEventCreateWithFlags(&q->ev, cudaEventDisableTiming));
+    q->h_count[0] = 0;
+    h->hp = q;
+    return GZ_OK;
+}
+
+extern "C" int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* const* h_arrays, int n_arrays, void* stream) {
+    if (!h) { gz_set_error("null engine"); return GZ_ERR_ARG; }
+    int rc = hostpoll_init(h);
+    if (rc != GZ_OK) return rc;
+    HostPoll* q = h->hp;
+    const PuctEngine& E = h->E;
+    if (q->in_flight) { gz_set_error("host poll already submitted; call gz_puct_host_poll_wait first"); return GZ_ERR_ARG; }
+    if (n_pred != q->outstanding) { gz_set_error("expected %d predictions, got %d", q->outstanding, n_pred); return GZ_ERR_ARG; }
+    if (n_pred > 0 && (!h_arrays || n_arrays != E.R + 1)) { gz_set_error("expected %d policy arrays and one value array", E.R); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int st = E.policy_stride, nr = E.n_rewards;
+    if (n_pred > 0) {
+        for (int r = 0; r < E.R; r++) {
+            if (!h_arrays[r]) { gz_set_error("null prediction array"); return GZ_ERR_ARG; }
+            const int sz = E.role_sizes[r], off = E.policy_off[r];
+            const float* src = h_arrays[r];
+            for (int i = 0; i < n_pred; i++) memcpy(q->h_pol + (size_t)i * st + off, src + (size_t)i * sz, (size_t)sz * 4);
+        }
+        if (!h_arrays[E.R]) { gz_set_error("null value array"); return GZ_ERR_ARG; }
+        memcpy(q->h_val, h_arrays[E.R], (size_t)n_pred * nr * 4);
+        GZ_CUDA(cudaMemcpyAsync(q->d_stage_pol, q->h_pol, (size_t)n_pred * st * 4, cudaMemcpyHostToDevice, s));
+        GZ_CUDA(cudaMemcpyAsync(q->d_stage_val, q->h_val, (size_t)n_pred * nr * 4, cudaMemcpyHostToDevice, s));
+        const int64_t work = (int64_t)n_pred * (st + nr);
+        hostpoll_scatter_kernel<<<(int)std::min<int64_t>((work + 255) / 256, 1184), 256, 0, s>>>(
+            q->d_stage_pol, q->d_stage_val, q->d_rows, n_pred, st, nr, q->d_pol, q->d_val);
+        GZ_CUDA(cudaGetLastError());
+    }
+    rc = gz_puct_advance(h, q->d_pol, q->d_val, n_pred > 0 ? 1 : 0, 1, q->d_planes, GZ_DTYPE_F32, stream);
+    if (rc != GZ_OK) return rc;
+    hostpoll_compact_kernel<<<1, 1024, 0, s>>>(E.x_need_eval, E.G, q->d_rows, q->d_count);
+    GZ_CUDA(cudaGetLastError());
+    const int64_t gw = (int64_t)E.G * h->total_size / 4;
+    hostpoll_gather_kernel<<<(int)std::min<int64_t>((gw + 255) / 256, 1184), 256, 0, s>>>(
+        q->d_planes, q->d_rows, q->d_count, h->total_size, q->d_planes_c);
+    GZ_CUDA(cudaGetLastError());
+    GZ_CUDA(cudaMemcpyAsync(q->h_count, q->d_count, 4, cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaMemcpyAsync(q->h_planes, q->d_planes_c, (size_t)E.G * h->total_size * 4, cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaEventRecord(q->ev, s));
+    q->outstanding = 0;
+    q->in_flight = true;
+    return GZ_OK;
+}
+
+// Blocks until the submitted poll has finished. *h_planes = pinned [n_req][total] float32 (valid until
+// the next submit on this engine); returns n_req (>= 0) or a negative gz_status.
+extern "C" int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes) {
+    if (!h || !h->hp || !h->hp->in_flight) { gz_set_error("no host poll in flight"); return GZ_ERR_ARG; }
+    HostPoll* q = h->hp;
+    GZ_CUDA(cudaEventSynchronize(q->ev));
+    q->in_flight = false;
+    q->outstanding = q->h_count[0];
+    if (h_planes) *h_planes = q->h_planes;
+    return q->outstanding;
+}
+
 // totals: [evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children,
 //          dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval,
 //          ready_count]
@@ -497,7 +672,7 @@ extern "C" int gz_puct_command(gz_puct* h, int g, int cmd, int arg, int evals, c
     return GZ_OK;
 }
 
-// Snapshot of game g: out_i[0..7] = cmd_done, phase, error, choice, n_nodes, n_children, root visits,
+// Snapshot of game g: out_i[0..15] (out_i[9+r] = role r's only action at the root) = cmd_done, phase, error, choice, n_nodes, n_children, root visits,
 // lead role; out_f[0] = root score for the lead role; then per child (max_children): move, traversals,
 // policy_prob, child score (-1 unexpanded), next_prob. Returns the number of children. Synchronises.
 __global__ void puct_snapshot_kernel(const __grid_constant__ PuctEngine E, int g, int max_children, int* oi, float* of,
@@ -506,11 +681,13 @@ __global__ void puct_snapshot_kernel(const __grid_constant__ PuctEngine E, int g
     const GameCtl& c = *V.c;
     oi[0] = c.cmd_done; oi[1] = c.phase; oi[2] = c.error; oi[3] = c.choice; oi[4] = c.n_nodes; oi[5] = c.n_children;
     oi[6] = 0; oi[7] = 0; oi[8] = 0;
+    for (int r = 0; r < GZP_MAX_ROLES; r++) oi[9 + r] = -1;
     of[0] = 0.0f;
     if (c.root < 0 || c.n_nodes <= 0) return;
     const int n = c.root;
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n), lead = NODE(n_lead, n);
     oi[6] = (int)NODE(n_visits, n); oi[7] = lead; oi[8] = nc;
+    for (int r = 0; r < E.R && r < GZP_MAX_ROLES; r++) oi[9 + r] = NOTHER(n, r);   // non-lead roles' only action
     of[0] = NSCORE(n, lead);
     for (int i = 0; i < nc && i < max_children; i++) {
         moves[i] = CHILD(c_move, c0 + i);
@@ -531,7 +708,7 @@ extern "C" int gz_puct_snapshot(gz_puct* h, int g, int max_children, int* out_i,
     void* d = nullptr;
     GZ_CUDA(cudaMalloc(&d, bytes));
     int* di = (int*)d;
-    float* df = (float*)(di + 12);
+    float* df = (float*)(di + 16);
     int* dm = (int*)(df + 4);
     int* dt = dm + max_children;
     float* dp = (float*)(dt + max_children);
@@ -539,7 +716,7 @@ extern "C" int gz_puct_snapshot(gz_puct* h, int g, int max_children, int* out_i,
     float* dn = ds + max_children;
     puct_snapshot_kernel<<<1, 1, 0, s>>>(h->E, g, max_children, di, df, dm, dt, dp, ds, dn);
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_i, di, 9 * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_i, di, 16 * 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_f, df, 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && max_children) {
         cudaMemcpyAsync(moves, dm, max_children * 4, cudaMemcpyDeviceToHost, s);

@@ -251,5 +251,6 @@ class PuctEngine(object):
             _lib.check(n)
         return dict(cmd_done=int(oi[0]), phase=int(oi[1]), error=int(oi[2]), choice=int(oi[3]),
                     nodes=int(oi[4]), children=int(oi[5]), root_visits=int(oi[6]), lead_role=int(oi[7]),
+                    other_moves=[int(x) for x in oi[9:9 + len(self.role_sizes)]],
                     root_score=float(of[0]), moves=moves[:n].copy(), traversals=trav[:n].copy(),
                     policy_prob=prob[:n].copy(), scores=score[:n].copy(), next_prob=nxt[:n].copy())

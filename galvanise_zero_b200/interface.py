@@ -125,6 +125,58 @@ class GdlBasesTransformer(object):
 
 
 # ------------------------------------------------------------------------------------------------
+class _Manager(object):
+    """One engine + its stream — the device counterpart of a ``SelfPlayManager``
+    (``src/cpp/selfplaymanager.h:20-114``). The hand-off itself (pinned buffers, copy-in, engine step,
+    compaction of the waiting rows, copy-out) is native: ``gz_puct_host_poll_submit`` / ``_wait``."""
+
+    def __init__(self, engine, stream):
+        e = self.engine = engine
+        self.stream = stream                     # None: the caller's current stream (inline mode)
+        self.n_req = 0                           # rows handed out and not yet answered
+        L = e._L
+        L.gz_puct_host_poll_submit.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                               ctypes.c_int, ctypes.c_void_p]
+        L.gz_puct_host_poll_wait.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_float))]
+        self._n_arrays = len(e.role_sizes) + 1
+        self._ptrs = (ctypes.c_void_p * self._n_arrays)()
+        self._planes_ptr = ctypes.POINTER(ctypes.c_float)()
+        self._planes_np = None
+
+    def _ctx(self):
+        import contextlib
+        import torch
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def _stream_ptr(self):
+        import torch
+        s = self.stream if self.stream is not None else torch.cuda.current_stream(self.engine.device)
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def launch(self, n_predictions, arrays=None):
+        """Enqueues, without waiting: predictions -> engine rows, one engine step, the compaction of
+        the rows that now wait for the network and the copy of their planes to pinned host memory."""
+        e = self.engine
+        if n_predictions:
+            for i in range(self._n_arrays):
+                self._ptrs[i] = arrays[i].ctypes.data
+        _lib.check(e._L.gz_puct_host_poll_submit(e._h, int(n_predictions), self._ptrs if n_predictions else None,
+                                                 self._n_arrays if n_predictions else 0, self._stream_ptr()))
+
+    def wait(self):
+        e = self.engine
+        n = e._L.gz_puct_host_poll_wait(e._h, ctypes.byref(self._planes_ptr))
+        if n < 0:
+            _lib.check(n)
+        if self._planes_np is None:
+            self._planes_np = np.ctypeslib.as_array(self._planes_ptr, shape=(e.n_games * e.total_size,))
+        self.n_req = n
+        return n
+
+    def planes(self):
+        return self._planes_np[:self.n_req * self.engine.total_size]
+
+
 class Supervisor(object):
     """``ggpzero_interface.Supervisor(sm, transformer, batch_size, identifier)``
     (``src/cpp/pyobjects/supervisor_impl.cpp:215-237``) on the device engine.
@@ -132,7 +184,15 @@ class Supervisor(object):
     ``poll`` keeps the reference's numpy contract (``src/cpp/pyobjects/common.cpp:160-218``): it takes
     the predictions for the rows handed out by the previous poll and returns a 1-D float32 array of
     ``n_req * total_size`` planes (or None when there is nothing to evaluate). ``poll_device`` is the
-    additive zero-copy variant on CUDA tensors."""
+    additive zero-copy variant on CUDA tensors.
+
+    ``start_self_play(num_workers, conf)``: ``num_workers <= 0`` is the reference's inline mode — one
+    manager holding ``batch_size`` games, strictly serial. ``num_workers > 0`` is its worker mode
+    (``src/cpp/supervisor.cpp:79-99``: two managers per worker so that the search of one overlaps the
+    network call of the other): here two managers of ``batch_size / 2`` games each on their own CUDA
+    streams — while the caller runs the network on the batch of one manager, the other manager's engine
+    step runs on the device. Batches alternate between the managers, as ready managers do in the
+    reference (``supervisor.cpp:129-167``)."""
 
     def __init__(self, sm, c_transformer, batch_size, identifier, device=0, seed=0x5EED0000,
                  node_cap=4096, child_cap=None):
@@ -147,7 +207,8 @@ class Supervisor(object):
         self.seed = seed
         self.node_cap, self.child_cap = node_cap, child_cap
         self.engine = None
-        self._rows = None
+        self.managers = []
+        self._cur = None            # manager whose planes were handed out by the last poll
         self._primed = False
 
     def set_num_workers(self, n):
@@ -157,83 +218,290 @@ class Supervisor(object):
     def start_self_play(self, num_workers, conf_dict):
         from .engine import PuctEngine
         import torch
-        self.engine = PuctEngine(self.game, conf_dict, n_games=self.batch_size, mode=0, device=self.device,
-                                 seed=self.seed, node_cap=self.node_cap, child_cap=self.child_cap,
-                                 c_transformer=self.c_transformer, plane_dtype=torch.float32,
-                                 sm=self.sm if not isinstance(self.sm, str) else None)
+        n_man = 2 if (num_workers > 0 and self.batch_size >= 2) else 1
+        sizes = [self.batch_size // n_man + (1 if k < self.batch_size % n_man else 0) for k in range(n_man)]
+        self.managers = []
+        dsm = self.sm if not isinstance(self.sm, str) else None
+        for k, g in enumerate(sizes):
+            eng = PuctEngine(self.game, conf_dict, n_games=g, mode=0, device=self.device,
+                             seed=self.seed + 104729 * k, node_cap=self.node_cap, child_cap=self.child_cap,
+                             c_transformer=self.c_transformer, plane_dtype=torch.float32, sm=dsm)
+            dsm = eng.sm                                      # managers share the device program
+            stream = torch.cuda.Stream(device=eng.device) if n_man > 1 else None
+            self.managers.append(_Manager(eng, stream))
+        self.engine = self.managers[0].engine
+        torch.cuda.synchronize(self.engine.device)
+        self._cur = None
+        self._primed = False
 
-    # -- zero-copy path
+    # -- zero-copy path (inline mode)
     def poll_device(self, policy=None, value=None, sub_iters=1):
         return self.engine.advance(policy, value, sub_iters)
 
     # -- reference-shaped numpy path
     def poll(self, n_predictions, arrays):
         """Returns a 1-D float32 numpy array VIEWING engine-owned pinned host memory (valid until the
-        next poll, as in the reference: common.cpp:204-209), or None when nothing needs evaluating."""
-        import torch
-        e = self.engine
-        if e is None:
+        next poll that returns the same manager's batch, as in the reference: common.cpp:204-209), or
+        None when nothing needs evaluating."""
+        if not self.managers:
             raise GGPZeroInterfaceError('start_self_play() has not been called')
         if not (0 <= n_predictions <= self.batch_size):
             raise GGPZeroInterfaceError('n_predictions out of range')
-        if self._rows is None:
+        M = self.managers
+        if not self._primed:
             if n_predictions != 0:
                 raise GGPZeroInterfaceError('first poll must pass n_predictions == 0')
-            self._host_planes = torch.empty((e.n_games, e.total_size), dtype=torch.float32).pin_memory()
-            self._host_count = torch.zeros(1, dtype=torch.int64).pin_memory()
-            self._stage_pol = torch.empty((e.n_games, e.policy_stride), dtype=torch.float32).pin_memory()
-            self._stage_val = torch.empty((e.n_games, e.n_rewards), dtype=torch.float32).pin_memory()
-            e.advance(None, None)
+            for m in M:
+                m.launch(0)
+            self._primed = True
+            nxt = 0
         else:
-            if n_predictions != len(self._rows):
-                raise GGPZeroInterfaceError('expected %d predictions, got %d' % (len(self._rows), n_predictions))
+            cur = self._cur
+            m = M[cur]
+            if n_predictions != m.n_req:
+                raise GGPZeroInterfaceError('expected %d predictions, got %d' % (m.n_req, n_predictions))
             if n_predictions:
+                e = m.engine
                 R = len(e.role_sizes)
                 if len(arrays) != R + 1:
                     raise GGPZeroInterfaceError('expected %d policy arrays and one value array' % R)
-                off = 0
-                sp = self._stage_pol.numpy()
-                for r in range(R):
-                    a = arrays[r]
+                widths = list(e.role_sizes) + [e.n_rewards]
+                for a, w in zip(arrays, widths):
                     if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
                         raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
-                    sp[:n_predictions, off:off + e.role_sizes[r]] = a.reshape(n_predictions, e.role_sizes[r])
-                    off += e.role_sizes[r]
-                self._stage_val.numpy()[:n_predictions] = arrays[R].reshape(n_predictions, e.n_rewards)
-                rows = self._rows_dev
-                e.policy.index_copy_(0, rows, self._stage_pol[:n_predictions].to(e.device, non_blocking=True))
-                e.value.index_copy_(0, rows, self._stage_val[:n_predictions].to(e.device, non_blocking=True))
-            e.advance(e.policy, e.value)
-        need = self._need_eval()
-        rows = torch.nonzero(need, as_tuple=False).flatten()        # device sync: the request count
-        n_req = int(rows.numel())
-        self._rows_dev = rows
-        self._rows = rows                                           # only its length is used on the host
-        if n_req == 0:
-            return None
-        gathered = e.planes.reshape(e.n_games, -1).index_select(0, rows).to(torch.float32)
-        self._host_planes[:n_req].copy_(gathered, non_blocking=True)
-        torch.cuda.current_stream(e.device).synchronize()
-        return self._host_planes.numpy()[:n_req].reshape(-1)
+                    if a.size != n_predictions * w:
+                        raise GGPZeroInterfaceError('prediction array holds %d values, expected %d x %d'
+                                                    % (a.size, n_predictions, w))
+            m.n_req = 0
+            m.launch(n_predictions, arrays)
+            nxt = (cur + 1) % len(M)
+        # hand out the next ready batch; a manager with nothing to evaluate is stepped again
+        for _ in range(64 * len(M)):
+            m = M[nxt]
+            if m.wait() > 0:
+                self._cur = nxt
+                return m.planes()
+            m.launch(0)
+            nxt = (nxt + 1) % len(M)
+        self._primed = False
+        self._cur = None
+        return None
 
-    def _need_eval(self):
-        import ctypes
-        import torch
-        e = self.engine
-        if not hasattr(self, '_need_buf'):
-            self._need_buf = torch.zeros(e.n_games, dtype=torch.uint8, device=e.device)
-            e._L.gz_puct_copy_need_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-        _lib.check(e._L.gz_puct_copy_need_eval(e._h, self._need_buf.data_ptr(), e._stream()))
-        return self._need_buf
+    def totals(self):
+        out = None
+        for m in self.managers:
+            with m._ctx():                         # ordered behind the manager's queued engine step
+                t = m.engine.totals()
+            out = t if out is None else {k: (max(out[k], t[k]) if k.startswith('max_') else out[k] + t[k])
+                                         for k in out}
+        return out
 
     def fetch_samples(self):
-        recs = self.engine.fetch_sample_records()
-        if len(recs) == 0:
-            return None
-        return self.engine.records_to_samples(recs, self.identifier)
+        res = []
+        for k, m in enumerate(self.managers):
+            with m._ctx():
+                recs = m.engine.fetch_sample_records()
+            if len(recs):
+                ident = self.identifier if len(self.managers) == 1 else '%s_m%d' % (self.identifier, k)
+                res.extend(m.engine.records_to_samples(recs, ident))
+        return res or None
 
     def add_unique_state(self, bs):
         """The reference's Python wrapper no-ops this call as well (``cppinterface.py:218-219``)."""
 
     def clear_unique_states(self):
-        self.engine.clear_unique_states()
+        for m in self.managers:
+            with m._ctx():
+                m.engine.clear_unique_states()
+
+
+# ------------------------------------------------------------------------------------------------
+class Player(object):
+    """``ggpzero_interface.Player(sm, transformer, puct_conf_dict)``
+    (``src/cpp/pyobjects/player_impl.cpp:8-129,183-201``, ``src/cpp/player.cpp``) on the device engine
+    in player mode (one tree).
+
+    As in the reference, ``player_apply_move`` / ``player_move`` only *enqueue* work
+    (``player.cpp:59-103``); it is carried out by the following ``poll`` calls, which hand out the
+    planes of the leaf to evaluate and return ``None`` once the queue has drained.
+
+    Differences from the reference: one outstanding evaluation per tree whatever
+    ``batch_size`` says; ``end_time`` / ``think_time`` wall-clock limits are not consulted (the search
+    stops on its evaluation budget and convergence rules); ``player_balance_moves`` is accepted and
+    does nothing; ``player_tree_debug`` reports no variation lines."""
+
+    CMD_RESET, CMD_APPLY, CMD_SEARCH = 1, 2, 3
+
+    def __init__(self, sm, c_transformer, puct_conf_dict, device=0, seed=0x5EED0001, node_cap=1 << 16,
+                 child_cap=None):
+        from .engine import PuctEngine
+        from .defs import confs
+        import attr
+        import torch
+        self.sm = sm
+        self.game = sm if isinstance(sm, str) else getattr(sm, 'game', None)
+        if self.game is None:
+            raise GGPZeroInterfaceError('Player needs a state machine created by name')
+        if not isinstance(puct_conf_dict, dict):
+            raise GGPZeroInterfaceError('puct config must be a dict (attr.asdict(PUCTEvaluatorConfig))')
+        self.conf = dict(attr.asdict(confs.PUCTEvaluatorConfig()))
+        self.conf.update(puct_conf_dict)
+        sp = attr.asdict(confs.selfplay_config_template())
+        sp['puct_config'] = dict(self.conf)
+        sp['run_to_end_puct_config'] = dict(self.conf)
+        self._sp = sp
+        self.c_transformer = c_transformer
+        self.engine = PuctEngine(self.game, sp, n_games=1, mode=PuctEngine.MODE_PLAYER, device=device, seed=seed,
+                                 node_cap=node_cap, child_cap=child_cap, c_transformer=c_transformer,
+                                 plane_dtype=torch.float32,
+                                 sm=self.sm if not isinstance(self.sm, str) else None)
+        e = self.engine
+        self._host_planes = torch.empty((1, e.total_size), dtype=torch.float32).pin_memory()
+        self._queue = []            # pending (kind, payload) commands, reference: scheduler runnables
+        self._busy = False          # a command is in the engine's mailbox
+        self._current = None
+        self._waiting = 0           # rows handed out by the last poll
+        self._first_play = False
+        self._game_depth = 0
+        self._choice = None         # (snapshot) of the last finished search
+        self._fresh = False
+
+    # ---- reference method table
+    def player_reset(self, game_depth):
+        self._game_depth = int(game_depth)
+        self._first_play = True
+        self._queue = []
+        self._choice = None
+
+    def player_update_config(self, think_time, converged_visits, verbose):
+        from .engine import _puct_array, _sp_array
+        self.conf['think_time'] = float(think_time)
+        self.conf['converged_visits'] = int(converged_visits)
+        self.conf['verbose'] = bool(verbose)
+        self._sp['puct_config'] = dict(self.conf)
+        self._sp['run_to_end_puct_config'] = dict(self.conf)
+        e = self.engine
+        _lib.check(e._L.gz_puct_set_config(e._h, _sp_array(self._sp), _puct_array(self.conf),
+                                           _puct_array(self.conf)))
+
+    def _joint_move_list(self, jm):
+        if hasattr(jm, 'get') and hasattr(jm, 'get_count'):
+            return [int(jm.get(i)) for i in range(jm.get_count())]
+        return [int(x) for x in jm]
+
+    def _state_words(self, bs):
+        from . import tables
+        if hasattr(bs, 'to_list'):
+            bits = np.asarray(bs.to_list(), dtype=np.uint8)
+            return tables.pack_state_bits(bits, self.engine.state_words)
+        return np.ascontiguousarray(bs, dtype=np.uint32)
+
+    def player_apply_move(self, joint_move):
+        moves = self._joint_move_list(joint_move)
+        if self._first_play:
+            self._first_play = False
+            self._queue.append(('reset', None))           # establishRoot(nullptr): the initial state
+        self._queue.append(('apply', moves))
+
+    def player_move(self, basestate, evaluations, end_time):
+        self._choice = None
+        if self._first_play:
+            self._first_play = False
+            self._queue.append(('reset', self._state_words(basestate)))
+        self._queue.append(('search', int(evaluations)))
+
+    def player_get_move(self, lead_role_index):
+        """-> (legal index of ``lead_role_index``'s move, score of the chosen child or -1, node count)."""
+        s = self._choice
+        if s is None or s['choice'] < 0 or len(s['moves']) == 0:
+            return (-1, -1.0, -1)
+        ch = s['choice']
+        if lead_role_index == s['lead_role']:
+            move = int(s['moves'][ch])
+        else:
+            move = int(s['other_moves'][lead_role_index])
+        return (move, float(s['scores'][ch]), int(s['nodes']))
+
+    def player_balance_moves(self, max_count):
+        """Accepted for API parity; the device engine does not rebalance first moves
+        (``src/cpp/puct/evaluator.cpp:282-339`` is an analysis aid of the tournament tooling)."""
+
+    def player_tree_debug(self, max_count):
+        """-> tuple of (score, lead_role_index, move_index, variation) for the root's most visited
+        expanded children (``src/cpp/puct/node.cpp:400-440``); variation lines are not reported."""
+        s = self.engine.snapshot(0)
+        order = sorted(range(len(s['moves'])), key=lambda i: -int(s['traversals'][i]))
+        out = []
+        for i in order[:max(0, int(max_count))]:
+            if s['scores'][i] < 0:
+                continue
+            out.append((float(s['scores'][i]), int(s['lead_role']), int(s['moves'][i]), ()))
+        return tuple(out)
+
+    # ---- the poll contract (src/cpp/player.cpp:155-173, src/cpp/pyobjects/common.cpp:160-218)
+    def _issue_next(self):
+        e = self.engine
+        kind, payload = self._queue.pop(0)
+        self._current = kind
+        if kind == 'reset':
+            e.command(0, self.CMD_RESET, arg=self._game_depth, state=payload)
+        elif kind == 'apply':
+            s = e.snapshot(0, 0)
+            lead = s['lead_role'] if s['lead_role'] >= 0 else 0
+            e.command(0, self.CMD_APPLY, arg=payload[lead])
+            self._game_depth += 1
+        else:
+            e.command(0, self.CMD_SEARCH, evals=payload)
+        self._busy = True
+
+    def poll(self, n_predictions, arrays):
+        import torch
+        e = self.engine
+        if n_predictions != self._waiting:
+            raise GGPZeroInterfaceError('expected %d predictions, got %d' % (self._waiting, n_predictions))
+        fresh = False
+        if n_predictions:
+            R = len(e.role_sizes)
+            if len(arrays) != R + 1:
+                raise GGPZeroInterfaceError('expected %d policy arrays and one value array' % R)
+            off = 0
+            row = np.zeros((1, e.policy_stride), dtype=np.float32)
+            for r in range(R):
+                a = arrays[r]
+                if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
+                    raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
+                row[0, off:off + e.role_sizes[r]] = a.reshape(-1)[:e.role_sizes[r]]
+                off += e.role_sizes[r]
+            e.policy.copy_(torch.from_numpy(row))
+            e.value.copy_(torch.from_numpy(np.ascontiguousarray(arrays[R], dtype=np.float32).reshape(1, e.n_rewards)))
+            fresh = True
+        self._waiting = 0
+        guard = 0
+        while True:
+            if not self._busy:
+                if not self._queue:
+                    return None
+                self._issue_next()
+            e.advance(e.policy if fresh else None, e.value if fresh else None)
+            fresh = False
+            if not hasattr(self, '_need_buf'):
+                self._need_buf = torch.zeros(1, dtype=torch.uint8, device=e.device)
+                e._L.gz_puct_copy_need_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+            _lib.check(e._L.gz_puct_copy_need_eval(e._h, self._need_buf.data_ptr(), e._stream()))
+            need = int(self._need_buf[0].item())                       # device sync
+            if need:
+                self._host_planes.copy_(e.planes.reshape(1, -1).to(torch.float32), non_blocking=True)
+                torch.cuda.current_stream(e.device).synchronize()
+                self._waiting = 1
+                return self._host_planes.numpy().reshape(-1)
+            guard += 1
+            if guard % 4 == 0 or guard < 3:
+                s = e.snapshot(0, 0)
+                if s['error'] or s['cmd_done'] < 0:
+                    raise GGPZeroInterfaceError('device player failed: error %d, cmd_done %d' % (s['error'], s['cmd_done']))
+                if s['cmd_done'] == 1:
+                    self._busy = False
+                    if self._current == 'search':
+                        self._choice = e.snapshot(0)
+            if guard > 10000000:
+                raise GGPZeroInterfaceError('device player did not finish')

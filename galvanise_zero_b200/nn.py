@@ -265,3 +265,78 @@ def make_inference_network(transformer, size='small', seed=0, device='cuda', dty
     net.eval()
     net.flops_per_position = tower.flops_per_position()
     return net
+
+
+class HeadResult(object):
+    """``src/ggpzero/nn/network.py:9-17``."""
+
+    def __init__(self, transformer, policies, values):
+        assert len(transformer.policy_dist_count) == len(policies)
+        self.policies = policies
+        self.scores = values
+
+    def __repr__(self):
+        return "HeadResult(policies=%s, scores=%s" % (self.policies, self.scores)
+
+
+class _HostBatchModel(object):
+    """What the reference's pollers call: ``nn.get_model().predict_on_batch(planes)``
+    (``src/ggpzero/util/cppinterface.py:119``) — host planes in, a list of host arrays
+    ``[policy_0, .., policy_{R-1}, value]`` out. The forward is the PyTorch module on the device."""
+
+    def __init__(self, module, transformer, device):
+        self.module = module
+        self.transformer = transformer
+        self.device = torch.device(device)
+
+    def predict_on_batch(self, planes):
+        import numpy as np
+        x = torch.from_numpy(np.ascontiguousarray(planes, dtype=np.float32))
+        p = next(self.module.parameters())
+        x = x.to(self.device, non_blocking=True).to(p.dtype)
+        if self.device.type == 'cuda':
+            x = x.contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            pol, val = self.module(x)
+        pol = pol.float().cpu().numpy()
+        val = val.float().cpu().numpy()
+        out, off = [], 0
+        for c in self.transformer.policy_dist_count:
+            out.append(np.ascontiguousarray(pol[:, off:off + c]))
+            off += c
+        out.append(np.ascontiguousarray(val))
+        return out
+
+    predict = predict_on_batch
+
+
+class NeuralNetwork(object):
+    """The reference's ``NeuralNetwork`` surface on the hot path (``src/ggpzero/nn/network.py:20-68``):
+    ``gdl_bases_transformer``, ``get_model()``, ``predict_n`` / ``predict_1``; the Keras model is
+    replaced by the PyTorch tower. Training / compile / save are out of scope."""
+
+    def __init__(self, gdl_bases_transformer, module, generation_descr=None, device='cuda'):
+        self.gdl_bases_transformer = gdl_bases_transformer
+        self.module = module
+        self.generation_descr = generation_descr
+        self._model = _HostBatchModel(module, gdl_bases_transformer, device)
+
+    def get_model(self):
+        return self._model
+
+    def predict_n(self, states, prev_states=None):
+        import numpy as np
+        to_channels = self.gdl_bases_transformer.state_to_channels
+        if prev_states:
+            assert len(prev_states) == len(states)
+            X = np.array([to_channels(s, prevs) for s, prevs in zip(states, prev_states)])
+        else:
+            X = np.array([to_channels(s) for s in states])
+        Y = self._model.predict_on_batch(X)
+        return [HeadResult(self.gdl_bases_transformer, [Y[k][i] for k in range(len(Y) - 1)], Y[-1][i])
+                for i in range(len(states))]
+
+    def predict_1(self, state, prev_states=None):
+        if prev_states:
+            return self.predict_n([state], [prev_states])[0]
+        return self.predict_n([state])[0]

@@ -165,11 +165,21 @@ int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int
 int gz_puct_set_plane_layout(gz_puct* h, int c_pad);
 const uint8_t* gz_puct_need_eval_ptr(const gz_puct* h);
 int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream);
+/* Host-buffer poll — Supervisor.poll(n_predictions, [policy_0.., value]) with HOST arrays on both sides
+ * (src/cpp/pyobjects/common.cpp:160-218): h_arrays = R policy arrays [n_pred][A_r] + one value array
+ * [n_pred][rewards], float32, rows in the order handed out by the previous wait (n_pred must equal it;
+ * 0 on the first call). submit() enqueues copy-in, the engine step, compaction and copy-out on `stream`
+ * and returns; wait() blocks until they finished and returns the number of rows now waiting for the
+ * network, *h_planes = [n_req][total_size] float32 in pinned memory owned by the engine (valid until
+ * the next submit). Two engines polled alternately overlap one's step with the network call on the
+ * other's batch (the reference's two managers per worker, src/cpp/supervisor.cpp:79-99). */
+int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* const* h_arrays, int n_arrays, void* stream);
+int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes);
 int gz_puct_totals(gz_puct* h, double* h_out19, void* stream);
 int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream);
 int gz_puct_clear_unique_states(gz_puct* h, void* stream);
 int gz_puct_command(gz_puct* h, int game, int cmd, int arg, int evals, const uint32_t* h_state, void* stream);
-int gz_puct_snapshot(gz_puct* h, int game, int max_children, int* out_i9, float* out_f1, int* moves, int* trav,
+int gz_puct_snapshot(gz_puct* h, int game, int max_children, int* out_i16, float* out_f1, int* moves, int* trav,
                      float* prob, float* score, float* next_prob, void* stream);
 
 /* Deterministic synthetic policy/value network (include/gz_synth.h) on encoded planes — parity and

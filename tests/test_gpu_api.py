@@ -84,3 +84,117 @@ def test_supervisor_numpy_poll_contract_and_samples():
         lead = max(s['policies'], key=len)
         assert abs(sum(p for _, p in lead) - 1.0) < 1e-3
         assert len(s['final_score']) == 2 and s['depth'] <= s['game_length']
+
+
+class _SynthNN(object):
+    """nn object for the pollers: ``gdl_bases_transformer`` + ``get_model().predict_on_batch`` that
+    evaluates the shared synthetic network (include/gz_synth.h) on host planes."""
+
+    def __init__(self, transformer, seed=1):
+        import ctypes
+        from galvanise_zero_b200 import lib as gzlib
+        self.gdl_bases_transformer = transformer
+        self.seed = seed
+        self.L = gzlib.lib()
+        self.ctypes = ctypes
+        self.calls = 0
+
+    def get_model(self):
+        return self
+
+    def predict_on_batch(self, planes):
+        ct = self.ctypes
+        tr = self.gdl_bases_transformer
+        n = planes.shape[0]
+        total = tr.num_channels * tr.channel_size
+        x = torch.from_numpy(np.ascontiguousarray(planes, dtype=np.float32).reshape(n, total)).cuda()
+        sizes = list(tr.policy_dist_count)
+        pol = torch.zeros((n, sum(sizes)), dtype=torch.float32, device='cuda')
+        val = torch.zeros((n, tr.num_rewards), dtype=torch.float32, device='cuda')
+        vp = ct.c_void_p
+        self.L.gz_synth_nn.argtypes = [vp, ct.c_int, ct.c_int64, ct.c_int, ct.c_uint64, ct.c_int,
+                                       ct.POINTER(ct.c_int), ct.c_int, vp, vp, vp]
+        rc = self.L.gz_synth_nn(x.data_ptr(), 0, n, total, self.seed, len(sizes), (ct.c_int * len(sizes))(*sizes),
+                                tr.num_rewards, pol.data_ptr(), val.data_ptr(), None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        self.calls += 1
+        pol, val = pol.cpu().numpy(), val.cpu().numpy()
+        out, off = [], 0
+        for c in sizes:
+            out.append(np.ascontiguousarray(pol[:, off:off + c]))
+            off += c
+        return out + [np.ascontiguousarray(val)]
+
+
+@pytest.mark.parametrize('game,evals,moves', [('reversi', 150, 12), ('breakthroughSmall', 200, 10)])
+def test_play_poller_matches_reference_search(game, evals, moves):
+    """PUCTPlayer's call sequence (src/ggpzero/player/puctplayer.py:60-95) through PlayPoller /
+    ggpzero_interface.Player against the reference's PuctEvaluator (oracle/_ref), same synthetic
+    network: identical root visit counts, choices and reported scores, move after move."""
+    from oracle import gzref
+    if not gzref.available():
+        pytest.skip('oracle/_ref missing')
+    gi = lookup.by_name(game)
+    tr = bases.GdlBasesTransformer(gi, datadesc.generation_for(game))
+    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits')
+    nn = _SynthNN(tr)
+    sm = gi.get_sm()
+    poller = cppinterface.PlayPoller(sm, nn, conf)
+    ref = gzref.RefEngine(tables.blob_by_name(game), poller.c_transformer).search(conf, evals, n_moves=moves)
+    assert len(ref) > 3
+
+    poller.player_reset(0)
+    assert poller.player_get_move(0) == (-1, -1.0, -1)
+    state = sm.get_initial_state()
+    for k, r in enumerate(ref):
+        poller.player_move(state, evals, -1.0)
+        poller.poll_loop()
+        lead = r['lead_role']
+        mv, score, nodes = poller.player_get_move(lead)
+        snap = poller.c_player._choice
+        assert np.array_equal(snap['moves'], r['moves'])
+        assert np.array_equal(snap['traversals'], r['traversals']), 'visit counts differ at move %d' % k
+        assert snap['choice'] == r['choice']
+        assert mv == int(r['moves'][r['choice']])
+        assert abs(score - float(r['scores'][r['choice']])) < 1e-6
+        assert abs(nodes - r['nodes']) <= 2          # the reference counts nodes awaiting release
+        other, _, _ = poller.player_get_move(1 - lead)
+        sm.update_bases(state)
+        ls = sm.get_legal_state(1 - lead)
+        assert ls.get_count() == 1 and ls.get_legal(0) == other       # the non-lead role's only move
+        dbg = poller.player_tree_debug(3)
+        assert len(dbg) >= 1 and dbg[0][1] == lead
+        jm = sm.get_joint_move()
+        jm.set(lead, mv)
+        jm.set(1 - lead, other)
+        poller.player_apply_move(jm)
+        poller.poll_loop()
+        nxt = sm.new_base_state()
+        sm.next_state(jm, nxt)
+        state = nxt
+    assert nn.calls > evals
+
+
+def test_supervisor_poller_wrapper_collects_samples():
+    """cppinterface.Supervisor (src/ggpzero/util/cppinterface.py:185-226) driven with poll_loop and
+    a callback, as Worker.on_request_samples does (src/ggpzero/distributed/worker.py:176-191)."""
+    game = 'breakthroughSmall'
+    gi = lookup.by_name(game)
+    tr = bases.GdlBasesTransformer(gi, datadesc.generation_for(game))
+    nn = _SynthNN(tr)
+    sup = cppinterface.Supervisor(gi.get_sm(), nn, batch_size=64, identifier='w0')
+    sup.start_self_play(confs.selfplay_config_template(evals_per_move=20), 0)
+    got = []
+
+    def cb():
+        got.extend(sup.fetch_samples())
+        return len(got) >= 30
+    sup.poll_loop(cb=cb, do_stats=True)
+    assert len(got) >= 30 and all(isinstance(s, datadesc.Sample) for s in got)
+    assert sup.total_predictions > 0 and sup.acc_time_polling > 0
+    sup.clear_unique_states()
+    # resumable: a second loop keeps producing (src/test/cpp/test_interface.py:166-170)
+    n0 = len(got)
+    sup.poll_loop(cb=lambda: bool(got.extend(sup.fetch_samples())) or len(got) >= n0 + 10)
+    assert len(got) >= n0 + 10
