@@ -393,29 +393,35 @@ def run_puct(args, rank, world, local):
     e2e = None
     if (rank == 0 or world > 1) and not args.no_e2e:
         from galvanise_zero_b200 import interface
-        sup = interface.Supervisor(PUCT_GAME, eng.c_transformer, G, 'bench', device=local, seed=0xE2E + rank,
-                                   node_cap=2048, child_cap=2048 * 16)
         import attr
         # worker mode = the reference's double-buffered managers (supervisor.cpp:79-99): two managers of
-        # G/2 games; the engine step of one overlaps the network call on the other's batch
-        sup.start_self_play(0 if args.e2e_inline else 1, attr.asdict(sp))
+        # batch_size games each; the engine step of one overlaps the network call on the other's batch.
+        # Supervisor(batch_size = G/2) + one worker therefore holds the configured G concurrent games.
+        inline = args.e2e_inline
+        sup = interface.Supervisor(PUCT_GAME, eng.c_transformer, G if inline else G // 2, 'bench', device=local,
+                                   seed=0xE2E + rank, node_cap=2048, child_cap=2048 * 16)
+        sup.start_self_play(0 if inline else 1, attr.asdict(sp))
         R = len(eng.role_sizes)
         h2d = d2h = 0
-        G = max(m.engine.n_games for m in sup.managers)       # rows per poll
+        Gm = sup.batch_size                                     # rows per poll
 
-        pin_pol = torch.empty((G, eng.policy_stride), dtype=torch.float32).pin_memory()
-        pin_val = torch.empty((G, eng.n_rewards), dtype=torch.float32).pin_memory()
         # the user's network call (the reference's model.predict_on_batch): host planes in, host
-        # predictions out; the forward itself is a CUDA graph over a fixed-size device batch
-        x_dev = torch.zeros((G,) + eng.plane_shape, dtype=torch.float32, device=eng.device)
-        pol_dev = torch.zeros((G, eng.policy_stride), dtype=torch.float32, device=eng.device)
-        val_dev = torch.zeros((G, eng.n_rewards), dtype=torch.float32, device=eng.device)
+        # predictions out (one array per policy head + value, each in its own pinned buffer); the forward
+        # itself is a CUDA graph over a fixed-size device batch
+        x_dev = torch.zeros((Gm,) + eng.plane_shape, dtype=torch.float32, device=eng.device)
+        out_dev = [torch.zeros((Gm, w), dtype=torch.float32, device=eng.device)
+                   for w in list(eng.role_sizes) + [eng.n_rewards]]
+        out_pin = [torch.empty((Gm, w), dtype=torch.float32).pin_memory() for w in list(eng.role_sizes) + [eng.n_rewards]]
+        out_np = [t.numpy() for t in out_pin]
 
         def nn_static():
             xb = x_dev.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
             p_, v_ = net(xb)
-            pol_dev.copy_(p_)
-            val_dev.copy_(v_)
+            off = 0
+            for r in range(R):
+                out_dev[r].copy_(p_[:, off:off + eng.role_sizes[r]])
+                off += eng.role_sizes[r]
+            out_dev[R].copy_(v_)
         with torch.no_grad():
             side2 = torch.cuda.Stream(device=eng.device)
             side2.wait_stream(torch.cuda.current_stream(eng.device))
@@ -445,19 +451,13 @@ def run_puct(args, rank, world, local):
             x_dev[:n_req].copy_(xin, non_blocking=True)
             h2d += planes.nbytes
             g_e2e.replay()
-            pin_pol[:n_req].copy_(pol_dev[:n_req], non_blocking=True)
-            pin_val[:n_req].copy_(val_dev[:n_req], non_blocking=True)
+            for k in range(R + 1):
+                out_pin[k][:n_req].copy_(out_dev[k][:n_req], non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
-            pol_h = pin_pol.numpy()[:n_req]
-            val_h = pin_val.numpy()[:n_req]
-            d2h += pol_h.nbytes + val_h.nbytes
-            h2d += pol_h.nbytes + val_h.nbytes
-            off = 0
-            arrs = []
-            for r in range(R):
-                arrs.append(np.ascontiguousarray(pol_h[:, off:off + eng.role_sizes[r]]))
-                off += eng.role_sizes[r]
-            arrs.append(np.ascontiguousarray(val_h))
+            arrs = [a[:n_req] for a in out_np]           # C-contiguous views, no host copies
+            nb = sum(a.nbytes for a in arrs)
+            d2h += nb
+            h2d += nb
             t_nn += time.perf_counter() - tp1
             return (n_req, arrs)
 
@@ -480,10 +480,9 @@ def run_puct(args, rank, world, local):
         e2e = {'value': e2e_moves / dt, 'unit': 'moves/s', 'h2d_bytes_per_step': int(h2d / reps) * len(sup.managers),
                'd2h_bytes_per_step': int(d2h / reps) * len(sup.managers), 'evals_per_s': e2e_evals / dt,
                'api': 'interface.Supervisor.poll (numpy in / numpy out, reference contract), network fed from pinned host memory',
-               'managers': '%d x %d games (%s)' % (len(sup.managers), G, 'inline' if len(sup.managers) == 1 else
+               'managers': '%d x %d games (%s)' % (len(sup.managers), Gm, 'inline' if len(sup.managers) == 1 else
                                                    'worker mode: engine step of one manager overlaps the network call of the other'),
-               'polls': reps, 'host_ms_per_poll': {'poll': t_poll * 1e3 / reps, 'network_call': t_nn * 1e3 / reps}}
-        G = args.slots or PUCT_GAMES_PER_GPU
+               'polls': reps, 'rows_per_poll': Gm, 'host_ms_per_poll': {'poll': t_poll * 1e3 / reps, 'network_call': t_nn * 1e3 / reps}}
 
     # ---- end of 'generation': gather the finished samples to rank 0 (the only collective; untimed)
     recs = np.concatenate([e.fetch_sample_records() for e in engines], axis=0)
@@ -583,7 +582,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='puct', choices=['propnet', 'puct'])

@@ -237,7 +237,7 @@ struct HostPoll {
     float *d_pol = nullptr, *d_val = nullptr;                        // [G][..] predictions in game order
     float *d_planes = nullptr, *d_planes_c = nullptr;                // [G][total] all games / compacted
     int *d_rows = nullptr, *d_count = nullptr;
-    cudaEvent_t ev = nullptr;
+    cudaEvent_t ev = nullptr, ev_in = nullptr;
     int outstanding = 0;      // rows handed out by the last wait
     bool in_flight = false;
 };
@@ -376,6 +376,7 @@ extern "C" void gz_puct_destroy(gz_puct* h) {
         void* dv[] = {q->d_stage_pol, q->d_stage_val, q->d_pol, q->d_val, q->d_planes, q->d_planes_c, q->d_rows, q->d_count};
         for (void* d : dv) if (d) cudaFree(d);
         if (q->ev) cudaEventDestroy(q->ev);
+        if (q->ev_in) cudaEventDestroy(q->ev_in);
         delete q;
     }
     delete h;
@@ -461,15 +462,22 @@ extern "C" int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream) 
 // and copy-out on `stream` without waiting; wait() blocks on the engine's event. Two engines polled
 // alternately overlap one engine's step with the caller's network call on the other's batch (the
 // reference's two managers per worker, supervisor.cpp:79-99).
+// staged predictions: role r's array [n][A_r] sits contiguously at sp + G * policy_off[r] (as it arrived)
+struct HostPollRoles { int n_roles; int size[GZP_MAX_ROLES]; int off[GZP_MAX_ROLES]; };
 __global__ void hostpoll_scatter_kernel(const float* __restrict__ sp, const float* __restrict__ sv,
-                                        const int* __restrict__ rows, int n, int stride, int nrew,
-                                        float* __restrict__ pol, float* __restrict__ val) {
+                                        const int* __restrict__ rows, int n, int G, int stride, int nrew,
+                                        const HostPollRoles rl, float* __restrict__ pol, float* __restrict__ val) {
     const int per = stride + nrew;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * per; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / per), c = (int)(i % per);
         const int g = rows[r];
-        if (c < stride) pol[(int64_t)g * stride + c] = sp[(int64_t)r * stride + c];
-        else val[(int64_t)g * nrew + (c - stride)] = sv[(int64_t)r * nrew + (c - stride)];
+        if (c < stride) {
+            int k = 0;
+            while (k + 1 < rl.n_roles && c >= rl.off[k + 1]) k++;
+            pol[(int64_t)g * stride + c] = sp[(int64_t)G * rl.off[k] + (int64_t)r * rl.size[k] + (c - rl.off[k])];
+        } else {
+            val[(int64_t)g * nrew + (c - stride)] = sv[(int64_t)r * nrew + (c - stride)];
+        }
     }
 }
 
@@ -540,6 +548,7 @@ static int hostpoll_init(gz_puct* h) {
     GZ_CUDA(cudaMemset(q->d_rows, 0, G * 4));
     GZ_CUDA(cudaMemset(q->d_count, 0, 64));
     GZ_CUDA(cudaEventCreateWithFlags(&q->ev, cudaEventDisableTiming));
+    GZ_CUDA(cudaEventCreateWithFlags(&q->ev_in, cudaEventDisableTiming));
     q->h_count[0] = 0;
     h->hp = q;
     return GZ_OK;
@@ -557,20 +566,37 @@ extern "C" int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* con
     GZ_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     const int st = E.policy_stride, nr = E.n_rewards;
+    bool direct = false;
     if (n_pred > 0) {
-        for (int r = 0; r < E.R; r++) {
+        for (int r = 0; r <= E.R; r++)
             if (!h_arrays[r]) { gz_set_error("null prediction array"); return GZ_ERR_ARG; }
-            const int sz = E.role_sizes[r], off = E.policy_off[r];
-            const float* src = h_arrays[r];
-            for (int i = 0; i < n_pred; i++) memcpy(q->h_pol + (size_t)i * st + off, src + (size_t)i * sz, (size_t)sz * 4);
+        // arrays that already live in pinned host memory are copied from where they are (one contiguous
+        // copy per array); pageable arrays go through the engine's pinned staging rows first
+        direct = true;
+        for (int r = 0; r <= E.R && direct; r++) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, h_arrays[r]) != cudaSuccess || at.type != cudaMemoryTypeHost) direct = false;
         }
-        if (!h_arrays[E.R]) { gz_set_error("null value array"); return GZ_ERR_ARG; }
-        memcpy(q->h_val, h_arrays[E.R], (size_t)n_pred * nr * 4);
-        GZ_CUDA(cudaMemcpyAsync(q->d_stage_pol, q->h_pol, (size_t)n_pred * st * 4, cudaMemcpyHostToDevice, s));
-        GZ_CUDA(cudaMemcpyAsync(q->d_stage_val, q->h_val, (size_t)n_pred * nr * 4, cudaMemcpyHostToDevice, s));
+        cudaGetLastError();
+        for (int r = 0; r < E.R; r++) {
+            const size_t bytes = (size_t)n_pred * E.role_sizes[r] * 4;
+            const size_t blk = (size_t)E.G * E.policy_off[r];
+            const float* src = h_arrays[r];
+            if (!direct) { memcpy(q->h_pol + blk, h_arrays[r], bytes); src = q->h_pol + blk; }
+            GZ_CUDA(cudaMemcpyAsync(q->d_stage_pol + blk, src, bytes, cudaMemcpyHostToDevice, s));
+        }
+        {
+            const float* src = h_arrays[E.R];
+            if (!direct) { memcpy(q->h_val, h_arrays[E.R], (size_t)n_pred * nr * 4); src = q->h_val; }
+            GZ_CUDA(cudaMemcpyAsync(q->d_stage_val, src, (size_t)n_pred * nr * 4, cudaMemcpyHostToDevice, s));
+        }
+        if (direct) GZ_CUDA(cudaEventRecord(q->ev_in, s));
+        HostPollRoles rl;
+        rl.n_roles = E.R;
+        for (int r = 0; r < E.R; r++) { rl.size[r] = E.role_sizes[r]; rl.off[r] = E.policy_off[r]; }
         const int64_t work = (int64_t)n_pred * (st + nr);
         hostpoll_scatter_kernel<<<(int)std::min<int64_t>((work + 255) / 256, 1184), 256, 0, s>>>(
-            q->d_stage_pol, q->d_stage_val, q->d_rows, n_pred, st, nr, q->d_pol, q->d_val);
+            q->d_stage_pol, q->d_stage_val, q->d_rows, n_pred, E.G, st, nr, rl, q->d_pol, q->d_val);
         GZ_CUDA(cudaGetLastError());
     }
     rc = gz_puct_advance(h, q->d_pol, q->d_val, n_pred > 0 ? 1 : 0, 1, q->d_planes, GZ_DTYPE_F32, stream);
@@ -586,6 +612,8 @@ extern "C" int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* con
     GZ_CUDA(cudaEventRecord(q->ev, s));
     q->outstanding = 0;
     q->in_flight = true;
+    // the caller may reuse its arrays as soon as this returns (the reference copies them: supervisor.cpp:104-120)
+    if (direct) GZ_CUDA(cudaEventSynchronize(q->ev_in));
     return GZ_OK;
 }
 

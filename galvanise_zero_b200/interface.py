@@ -189,8 +189,8 @@ class Supervisor(object):
     ``start_self_play(num_workers, conf)``: ``num_workers <= 0`` is the reference's inline mode — one
     manager holding ``batch_size`` games, strictly serial. ``num_workers > 0`` is its worker mode
     (``src/cpp/supervisor.cpp:79-99``: two managers per worker so that the search of one overlaps the
-    network call of the other): here two managers of ``batch_size / 2`` games each on their own CUDA
-    streams — while the caller runs the network on the batch of one manager, the other manager's engine
+    network call of the other): here, likewise, two managers of ``batch_size`` games each on their own
+    CUDA streams — while the caller runs the network on the batch of one manager, the other manager's engine
     step runs on the device. Batches alternate between the managers, as ready managers do in the
     reference (``supervisor.cpp:129-167``)."""
 
@@ -218,8 +218,8 @@ class Supervisor(object):
     def start_self_play(self, num_workers, conf_dict):
         from .engine import PuctEngine
         import torch
-        n_man = 2 if (num_workers > 0 and self.batch_size >= 2) else 1
-        sizes = [self.batch_size // n_man + (1 if k < self.batch_size % n_man else 0) for k in range(n_man)]
+        n_man = 2 if num_workers > 0 else 1
+        sizes = [self.batch_size] * n_man
         self.managers = []
         dsm = self.sm if not isinstance(self.sm, str) else None
         for k, g in enumerate(sizes):
