@@ -17,7 +17,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/gz_b200.h"
@@ -46,6 +48,12 @@ struct PnParams {
     int row_stride;    // odd stride of the per-warp staging rows
     int warp_words;    // shared-memory words per warp
     int staged_words;  // shared-memory words holding staged programs
+    // wide format (games with more than 32 K live slots: chess_15d, hexLG13): 32-bit literals, value
+    // array in a per-CTA global scratch region (pn_wide_kernel)
+    int wide;
+    const uint32_t* next_lit32;
+    const uint32_t* legal_lit32;
+    const uint32_t* goal_lit32;
 };
 
 enum { MODE_EVAL = 0, MODE_TRANSITION = 1, MODE_PLAYOUT = 2 };
@@ -305,6 +313,178 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wide games. The value array of a tile (55 K words for chess_15d, 412 K for hexLG13) does not fit in
+// shared memory, so it lives in a per-CTA region of a global scratch buffer that stays L2-resident;
+// one CTA of WIDE_WARPS warps owns one tile, warp w evaluates chunks w, w+WIDE_WARPS, ... of a level
+// and the CTA meets at level boundaries. Same bit-sliced evaluation and the same results as pn_kernel.
+#define WIDE_WARPS 16
+
+__device__ __forceinline__ uint32_t wlit(const uint32_t* val, uint32_t lit) {
+    return __ldcg(val + (lit >> 1)) ^ (0u - (lit & 1u));
+}
+
+__device__ __forceinline__ void run_program_wide(const uint32_t* __restrict__ prog, int n_chunks,
+                                                 uint32_t* val, int lane, int warp) {
+    const uint32_t* p = prog;
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t hdr = __ldg(p);
+        const int nl = (int)(hdr & 0xffu);
+        if ((c % WIDE_WARPS) == warp) {
+            const uint32_t out = __ldg(p + 1 + lane);
+            uint32_t acc = 0xffffffffu;
+            const uint32_t* lp = p + 33 + lane;
+#pragma unroll 4
+            for (int k = 0; k < nl; ++k) acc &= wlit(val, __ldg(lp + k * 32));
+            __stcg(val + out, acc);
+        }
+        p += 33 + 32 * nl;
+        if (hdr & 0x100u) __syncthreads();
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WIDE_WARPS * 32)
+pn_wide_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
+               const uint32_t* states_in, const int16_t* __restrict__ moves_in,
+               uint32_t* states_out, uint32_t* legal, uint8_t* terminal, uint8_t* __restrict__ goals,
+               int16_t* __restrict__ moves_out, unsigned long long* __restrict__ transitions,
+               uint64_t seed, uint64_t step, int goals_mode, uint32_t* scratch, int64_t scratch_stride) {
+    __shared__ int mv_sm[32][GZ_PN_MAX_ROLES];
+    __shared__ uint32_t masks_sm[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* val = scratch + (int64_t)blockIdx.x * scratch_stride;
+    uint32_t* slices = val + P.val_words;          // [nbw * 32] next-state slices of the tile
+    const int R = P.n_roles;
+    const int SW = P.state_words, LW = P.legal_words;
+    if (threadIdx.x == 0) __stcg(val, 0xffffffffu);
+    const int64_t n_tiles = (n + 31) >> 5;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t g0 = tile << 5;
+        const int64_t game = g0 + lane;
+        const int rows = (int)((n - g0) < 32 ? (n - g0) : 32);
+        const bool valid = lane < rows;
+        const uint32_t valid_mask = rows == 32 ? 0xffffffffu : ((1u << rows) - 1u);
+
+        // ---- moves (warp 0): chosen from the stored legal rows (PLAYOUT) or given (TRANSITION)
+        if (warp == 0) {
+            uint32_t reset_mask = 0, pass_mask = 0;
+            int mv[GZ_PN_MAX_ROLES];
+            if (MODE == MODE_PLAYOUT) {
+                const bool term = valid ? (terminal[game] != 0) : false;
+                reset_mask = __ballot_sync(0xffffffffu, term);
+                for (int r = 0; r < R; ++r) {
+                    mv[r] = -1;
+                    if (valid && !term) {
+                        const uint32_t* w = legal + game * LW + P.legal_word_off[r];
+                        const int nw = P.legal_word_off[r + 1] - P.legal_word_off[r];
+                        uint32_t cnt = 0;
+                        for (int j = 0; j < nw; ++j) cnt += __popc(w[j]);
+                        uint32_t pick = gz_pick(gz_rand32(seed, (uint64_t)(slot0 + game), step, (uint32_t)r), cnt);
+                        int idx = 0;
+                        for (int j = 0; j < nw; ++j) {
+                            uint32_t x = w[j];
+                            const uint32_t c = __popc(x);
+                            if (pick < c) {
+                                for (uint32_t i = 0; i < pick; ++i) x &= x - 1;
+                                idx = j * 32 + (__ffs(x) - 1);
+                                break;
+                            }
+                            pick -= c;
+                        }
+                        mv[r] = idx;
+                    }
+                    if (valid && moves_out) moves_out[game * R + r] = (int16_t)mv[r];
+                }
+            } else if (MODE == MODE_TRANSITION) {
+                for (int r = 0; r < R; ++r) mv[r] = valid ? (int)moves_in[game * R + r] : -1;
+                pass_mask = __ballot_sync(0xffffffffu, valid && mv[0] < 0);
+            }
+            if (MODE != MODE_EVAL)
+                for (int r = 0; r < R; ++r) mv_sm[lane][r] = mv[r];
+            if (lane == 0) { masks_sm[0] = reset_mask; masks_sm[1] = pass_mask; }
+        }
+        // ---- packed states -> base slots (every warp takes state words w, w+WIDE_WARPS, ...)
+        for (int j = warp; j < P.nbw; j += WIDE_WARPS) {
+            const uint32_t x = valid ? states_in[game * SW + j] : 0u;
+            const uint32_t t = warp_transpose32(x, lane);
+            const int b = j * 32 + lane;
+            if (b < P.n_bases) __stcg(val + 1 + b, t);
+        }
+        if (MODE != MODE_EVAL)
+            for (int i = threadIdx.x; i < P.n_inputs; i += blockDim.x) __stcg(val + 1 + P.n_bases + i, 0u);
+        __syncthreads();
+        const uint32_t reset_mask = masks_sm[0], pass_mask = masks_sm[1];
+
+        if (MODE != MODE_EVAL) {
+            if (warp == 0)
+                for (int r = 0; r < R; ++r) {
+                    const int m = mv_sm[lane][r];
+                    if (m >= 0) atomicOr(val + P.input_slot0[r] + m, 1u << lane);
+                }
+            __syncthreads();
+            // ---- next-state cone
+            run_program_wide(P.prog[0], P.chunks[0], val, lane, warp);
+            __syncthreads();
+            for (int j = warp; j < P.nbw; j += WIDE_WARPS) {
+                const int b = j * 32 + lane;
+                uint32_t t = wlit(val, __ldg(P.next_lit32 + b));
+                if (MODE == MODE_PLAYOUT) {
+                    const uint32_t ib = (P.init_words[j] >> lane) & 1u;
+                    t = (t & ~reset_mask) | (ib ? reset_mask : 0u);
+                } else if (b < P.n_bases) {
+                    t = (t & ~pass_mask) | (__ldcg(val + 1 + b) & pass_mask);
+                }
+                t &= valid_mask;
+                slices[b] = t;
+                const uint32_t x = warp_transpose32(t, lane);
+                if (valid) states_out[game * SW + j] = x;
+            }
+            for (int j = P.nbw + warp; j < SW; j += WIDE_WARPS)
+                if (valid) states_out[game * SW + j] = 0u;
+            __syncthreads();
+            for (int b = threadIdx.x; b < P.n_bases; b += blockDim.x) __stcg(val + 1 + b, slices[b]);
+            __syncthreads();
+        }
+
+        // ---- views of the (new) state
+        run_program_wide(P.prog[1], P.chunks[1], val, lane, warp);
+        __syncthreads();
+        const uint32_t tw = wlit(val, (uint32_t)P.terminal_lit) & valid_mask;
+        const bool need_goals = (goals_mode == GZ_GOALS_ALWAYS) || (tw != 0u);
+        if (need_goals) { run_program_wide(P.prog[2], P.chunks[2], val, lane, warp); __syncthreads(); }
+
+        for (int j = warp; j < LW; j += WIDE_WARPS) {
+            uint32_t x = 0u;
+            if (j < P.lw_used) {
+                const uint32_t t = wlit(val, __ldg(P.legal_lit32 + j * 32 + lane)) & valid_mask;
+                x = warp_transpose32(t, lane);
+            }
+            if (valid) legal[game * LW + j] = x;
+        }
+        if (warp == 0) {
+            const bool is_term = (tw >> lane) & 1u;
+            if (valid) terminal[game] = is_term ? 1 : 0;
+            for (int r = 0; r < R; ++r) {
+                uint32_t gv = 255u;
+                if (need_goals) {
+                    for (int k = P.goal_off[r]; k < P.goal_off[r + 1]; ++k) {
+                        const uint32_t w = wlit(val, __ldg(P.goal_lit32 + k));
+                        if ((w >> lane) & 1u) gv = P.goal_val[k];
+                    }
+                }
+                if (goals_mode == GZ_GOALS_TERMINAL_ONLY && !is_term) gv = 255u;
+                if (valid) goals[game * R + r] = (uint8_t)gv;
+            }
+            if (MODE == MODE_PLAYOUT && transitions && lane == 0) {
+                const int cnt = __popc(valid_mask & ~reset_mask);
+                if (cnt) atomicAdd(transitions, (unsigned long long)cnt);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct gz_propnet {
     int device = 0;
     PnParams P{};
@@ -317,6 +497,11 @@ struct gz_propnet {
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    // wide games: one value-array scratch per stream that launches (engines on different streams may
+    // share one gz_propnet)
+    std::vector<std::pair<cudaStream_t, uint32_t*>> wide_scratch;
+    int wide_grid = 0;
+    int64_t wide_stride = 0;
 };
 
 extern "C" int gz_version(void) { return 100; }
@@ -326,6 +511,17 @@ static int configure_launch(gz_propnet* pn, const int32_t* h) {
     cudaDeviceProp prop;
     GZ_CUDA(cudaGetDeviceProperties(&prop, pn->device));
     pn->n_sms = prop.multiProcessorCount;
+    if (P.wide) {
+        // value array + next-state slices per CTA in global scratch (allocated per launching stream)
+        pn->wide_grid = pn->n_sms * 2;
+        pn->wide_stride = (((int64_t)P.val_words + (int64_t)P.nbw * 32) + 31) & ~(int64_t)31;
+        pn->warps_per_cta = WIDE_WARPS;
+        pn->grid_max = pn->wide_grid;
+        pn->smem_bytes = 0;
+        P.row_stride = P.warp_words = P.staged_words = 0;
+        for (int k = 0; k < 3; ++k) P.staged[k] = 0;
+        return GZ_OK;
+    }
     const size_t max_smem = prop.sharedMemPerBlockOptin;  // 227 KB on sm_100
     const int rs = std::max(P.state_words, P.legal_words) | 1;
     P.row_stride = rs;
@@ -384,6 +580,7 @@ extern "C" int gz_propnet_create(const int32_t* h, int64_t n_words, int device, 
     P.val_words = h[D_VAL_WORDS];
     P.terminal_lit = h[D_TERMINAL_LIT];
     P.nbw = (P.n_bases + 31) / 32;
+    P.wide = h[D_WIDE] ? 1 : 0;
     const int32_t* role_sizes = h + h[D_OFF_ROLE_SIZES];
     const int32_t* lwo = h + h[D_OFF_LEGAL_WORD_OFF];
     const int32_t* goal_off = h + h[D_OFF_GOAL_OFF];
@@ -426,6 +623,22 @@ extern "C" int gz_propnet_create(const int32_t* h, int64_t n_words, int device, 
     const size_t o_glit = pos; pos += al(goal_lit.size() * 2);
     const size_t o_gval = pos; pos += al(goal_val.size());
     const size_t o_init = pos; pos += al((size_t)P.state_words * 4);
+    // wide games: the same literal tables with 32-bit entries
+    std::vector<uint32_t> next32, legal32, goal32;
+    size_t o_next32 = 0, o_legal32 = 0, o_glit32 = 0;
+    if (P.wide) {
+        next32.assign((size_t)P.nbw * 32, 1u);
+        for (int b = 0; b < P.n_bases; ++b) next32[b] = (uint32_t)h[h[D_OFF_NEXT_LIT] + b];
+        legal32.assign((size_t)P.lw_used * 32, 1u);
+        int src = h[D_OFF_LEGAL_LIT];
+        for (int r = 0; r < R; ++r)
+            for (int a = 0; a < role_sizes[r]; ++a) legal32[(size_t)lwo[r] * 32 + a] = (uint32_t)h[src++];
+        goal32.assign(std::max(n_goal, 1), 1u);
+        for (int k = 0; k < n_goal; ++k) goal32[k] = (uint32_t)h[h[D_OFF_GOAL_LIT] + k];
+        o_next32 = pos; pos += al(next32.size() * 4);
+        o_legal32 = pos; pos += al(legal32.size() * 4);
+        o_glit32 = pos; pos += al(goal32.size() * 4);
+    }
     std::vector<uint8_t> arena(pos, 0);
     for (int k = 0; k < 3; ++k) {
         P.chunks[k] = h[chs[k]];
@@ -437,6 +650,11 @@ extern "C" int gz_propnet_create(const int32_t* h, int64_t n_words, int device, 
     memcpy(arena.data() + o_glit, goal_lit.data(), goal_lit.size() * 2);
     memcpy(arena.data() + o_gval, goal_val.data(), goal_val.size());
     memcpy(arena.data() + o_init, h + h[D_OFF_INIT], (size_t)P.state_words * 4);
+    if (P.wide) {
+        memcpy(arena.data() + o_next32, next32.data(), next32.size() * 4);
+        memcpy(arena.data() + o_legal32, legal32.data(), legal32.size() * 4);
+        memcpy(arena.data() + o_glit32, goal32.data(), goal32.size() * 4);
+    }
     cudaError_t e = cudaMalloc(&pn->d_arena, pos);
     if (e != cudaSuccess) { gz_set_error("cudaMalloc: %s", cudaGetErrorString(e)); delete pn; return GZ_ERR_CUDA; }
     e = cudaMemcpy(pn->d_arena, arena.data(), pos, cudaMemcpyHostToDevice);
@@ -448,6 +666,9 @@ extern "C" int gz_propnet_create(const int32_t* h, int64_t n_words, int device, 
     P.goal_lit = (const uint16_t*)(base + o_glit);
     P.goal_val = (const uint8_t*)(base + o_gval);
     P.init_words = (const uint32_t*)(base + o_init);
+    P.next_lit32 = P.wide ? (const uint32_t*)(base + o_next32) : nullptr;
+    P.legal_lit32 = P.wide ? (const uint32_t*)(base + o_legal32) : nullptr;
+    P.goal_lit32 = P.wide ? (const uint32_t*)(base + o_glit32) : nullptr;
     int rc = configure_launch(pn, h);
     if (rc != GZ_OK) { cudaFree(pn->d_arena); delete pn; return rc; }
     *out = pn;
@@ -459,6 +680,7 @@ extern "C" void gz_propnet_destroy(gz_propnet* pn) {
     cudaSetDevice(pn->device);
     if (pn->d_arena) cudaFree(pn->d_arena);
     if (pn->d_scratch) cudaFree(pn->d_scratch);
+    for (auto& ws : pn->wide_scratch) cudaFree(ws.second);
     if (pn->host_stream) cudaStreamDestroy(pn->host_stream);
     delete pn;
 }
@@ -492,7 +714,7 @@ template <int MODE>
 static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* states_in, const int16_t* moves_in,
                   uint32_t* states_out, uint32_t* legal, uint8_t* terminal, uint8_t* goals,
                   int16_t* moves_out, unsigned long long* transitions, uint64_t seed, uint64_t step,
-                  int goals_mode, void* stream) {
+                  int goals_mode, void* stream, uint32_t* own_scratch = nullptr) {
     if (!pn) { gz_set_error("null propnet"); return GZ_ERR_ARG; }
     if (n < 0) { gz_set_error("negative batch"); return GZ_ERR_ARG; }
     if (n == 0) return GZ_OK;
@@ -512,6 +734,27 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
     GZ_CUDA(cudaSetDevice(pn->device));
     const int64_t n_tiles = (n + 31) / 32;
     cudaStream_t st = (cudaStream_t)stream;
+    if (pn->P.wide) {
+        static std::mutex mu;
+        uint32_t* scratch = own_scratch;
+        if (!scratch) {
+            std::lock_guard<std::mutex> lk(mu);
+            for (auto& ws : pn->wide_scratch) if (ws.first == st) scratch = ws.second;
+            if (!scratch) {
+                const size_t bytes = (size_t)pn->wide_grid * (size_t)pn->wide_stride * 4;
+                cudaError_t e = cudaMalloc((void**)&scratch, bytes);
+                if (e != cudaSuccess) { gz_set_error("cudaMalloc of %.1f MB propnet scratch failed: %s", bytes / 1e6, cudaGetErrorString(e)); return GZ_ERR_CUDA; }
+                GZ_CUDA(cudaMemset(scratch, 0, bytes));
+                pn->wide_scratch.emplace_back(st, scratch);
+            }
+        }
+        const int grid = (int)std::min<int64_t>(n_tiles, pn->wide_grid);
+        pn_wide_kernel<MODE><<<grid, WIDE_WARPS * 32, 0, st>>>(pn->P, n, slot0, states_in, moves_in, states_out, legal,
+                                                            terminal, goals, moves_out, transitions, seed, step,
+                                                            goals_mode, scratch, pn->wide_stride);
+        GZ_CUDA(cudaGetLastError());
+        return GZ_OK;
+    }
     // Small batches (the PUCT pipeline: a few thousand games) do not fill the machine with one warp per
     // tile and are bound by the serial latency of the gate programs: give every tile a CTA of 4 or 8
     // warps that share its value array. Large batches keep one warp per tile, many tiles per CTA.
@@ -552,6 +795,19 @@ extern "C" int gz_sm_transition(gz_propnet* pn, int64_t n, const uint32_t* d_sta
                                 int goals_mode, void* stream) {
     return launch<MODE_TRANSITION>(pn, n, 0, d_states, d_moves, d_next, d_legal, d_terminal, d_goals,
                                    nullptr, nullptr, 0, 0, goals_mode, stream);
+}
+
+// Internal (not part of the C-ABI): wide games evaluated with a caller-owned scratch region of
+// gz_propnet_wide_scratch_bytes() bytes, so that an engine's steps can be captured in a CUDA graph and
+// engines on different streams never share a value array.
+extern "C" int64_t gz_propnet_wide_scratch_bytes(const gz_propnet* pn) {
+    return (pn && pn->P.wide) ? (int64_t)pn->wide_grid * pn->wide_stride * 4 : 0;
+}
+extern "C" int gz_sm_transition_scratch(gz_propnet* pn, int64_t n, const uint32_t* d_states, const int16_t* d_moves,
+                                        uint32_t* d_next, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,
+                                        int goals_mode, void* stream, uint32_t* d_scratch) {
+    return launch<MODE_TRANSITION>(pn, n, 0, d_states, d_moves, d_next, d_legal, d_terminal, d_goals,
+                                   nullptr, nullptr, 0, 0, goals_mode, stream, d_scratch);
 }
 
 extern "C" int gz_sm_playout_step(gz_propnet* pn, int64_t slot0, int64_t n, uint64_t seed, uint64_t step,

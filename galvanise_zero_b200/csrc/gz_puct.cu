@@ -35,6 +35,10 @@
 #include "gz_transformer.h"
 
 extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn);   // gz_propnet.cu (device pointer)
+extern "C" int64_t gz_propnet_wide_scratch_bytes(const gz_propnet* pn);
+extern "C" int gz_sm_transition_scratch(gz_propnet* pn, int64_t n, const uint32_t* d_states, const int16_t* d_moves,
+                                        uint32_t* d_next, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,
+                                        int goals_mode, void* stream, uint32_t* d_scratch);
 extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
                                 const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
                                 int out_dtype, int c_pad, void* stream);
@@ -225,6 +229,7 @@ struct gz_puct {
     int total_size = 0;
     int cache_words = 0;      // per-warp shared-memory words for the child cache (0: use the global scratch)
     int plane_c_pad = 0;      // 0: planes are NCHW rows; >0: channels-last rows padded to this channel count
+    uint32_t* d_pn_scratch = nullptr;   // wide games: this engine's propnet value-array scratch
     struct HostPoll* hp = nullptr;   // host-buffer poll state (gz_puct_host_poll_*), created on first use
 };
 
@@ -342,6 +347,10 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
         GZ_CUDA(cudaMemcpy((void*)E.uniq_mask, mask.data(), E.SW * 4, cudaMemcpyHostToDevice));
     }
     GZ_CUDA(cudaMalloc(&h->d_totals, sizeof(PuctTotals)));
+    if (gz_propnet_wide_scratch_bytes(pn) > 0) {
+        GZ_CUDA(cudaMalloc((void**)&h->d_pn_scratch, (size_t)gz_propnet_wide_scratch_bytes(pn)));
+        GZ_CUDA(cudaMemset(h->d_pn_scratch, 0, (size_t)gz_propnet_wide_scratch_bytes(pn)));
+    }
     GZ_CUDA(cudaMalloc(&h->d_role_sizes_off, rso.size() * sizeof(int)));
     GZ_CUDA(cudaMemcpy(h->d_role_sizes_off, rso.data(), rso.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->total_size = tr->E.total;
@@ -366,6 +375,7 @@ extern "C" void gz_puct_destroy(gz_puct* h) {
     cudaSetDevice(h->device);
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->d_totals) cudaFree(h->d_totals);
+    if (h->d_pn_scratch) cudaFree(h->d_pn_scratch);
     if (h->d_role_sizes_off) cudaFree(h->d_role_sizes_off);
     if (h->hp) {
         HostPoll* q = h->hp;
@@ -419,8 +429,8 @@ extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d
         GZ_CUDA(cudaGetLastError());
         puct_reroot_kernel<<<E.G, REROOT_THREADS, 0, s>>>(E);
         GZ_CUDA(cudaGetLastError());
-        int rc = gz_sm_transition(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
-                                  GZ_GOALS_TERMINAL_ONLY, stream);
+        int rc = gz_sm_transition_scratch(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
+                                          GZ_GOALS_TERMINAL_ONLY, stream, h->d_pn_scratch);
         if (rc != GZ_OK) return rc;
         puct_post_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, s>>>(E);
         GZ_CUDA(cudaGetLastError());

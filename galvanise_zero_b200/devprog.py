@@ -42,7 +42,7 @@ MAX_SLOT = 32767 - 32   # 15-bit slot index, minus the 32 dump slots
  D_OFF_PROG_GL, D_CHUNKS_GL, D_HALFS_GL,
  D_OFF_NEXT_LIT, D_OFF_LEGAL_LIT, D_OFF_GOAL_OFF, D_OFF_GOAL_VAL, D_OFF_GOAL_LIT,
  D_N_GATES_A, D_N_GATES_LT, D_N_GATES_GL, D_N_LITS_A, D_N_LITS_LT, D_N_LITS_GL,
- D_DUMP_SLOT) = range(34)
+ D_DUMP_SLOT, D_WIDE) = range(35)
 
 
 class _Alloc:
@@ -66,7 +66,7 @@ class _Alloc:
 
 
 def _pack_phase(pn: Propnet, parts: List[Sequence[int]], keep_lits: Sequence[int],
-                n_leaves: int) -> Tuple[List[np.ndarray], Dict[int, int], int, List[Tuple[int, int]]]:
+                n_leaves: int, wide: bool = False) -> Tuple[List[np.ndarray], Dict[int, int], int, List[Tuple[int, int]]]:
     """Allocate slots and emit chunk streams for consecutive sub-programs ``parts`` that share one
     slot space. ``keep_lits``: output literals (old slot space) that must stay readable at the end.
     Returns (streams per part, old_slot->new_slot map for kept slots, slots used, stats per part)."""
@@ -136,8 +136,24 @@ def _pack_phase(pn: Propnet, parts: List[Sequence[int]], keep_lits: Sequence[int
             for c0 in range(0, len(gates), 32):
                 cg = gates[c0:c0 + 32]
                 nl = max(len(pn.gate_lits[g]) for g in cg)
-                nl += nl & 1
                 last = (c0 + 32 >= len(gates))
+                if wide:
+                    # wide stream (uint32 units): [nl | sync<<8, out[32], literal rows nl x 32]
+                    chw = np.zeros(1 + 32 + 32 * nl, dtype=np.uint32)
+                    chw[0] = nl | ((1 if last else 0) << 8)
+                    outs32 = np.full(32, 0xFFFFFFFF, dtype=np.uint32)
+                    lits32 = np.zeros((nl, 32), dtype=np.uint32)
+                    for i, g in enumerate(cg):
+                        outs32[i] = new_slot[g]
+                        ml = [map_lit(l) for l in pn.gate_lits[g]]
+                        lits32[:len(ml), i] = ml
+                        n_g += 1
+                        n_l += len(ml)
+                    chw[1:33] = outs32
+                    chw[33:] = lits32.reshape(-1)
+                    chunks.append(chw)
+                    continue
+                nl += nl & 1
                 ch = np.zeros(2 + 32 + 32 * nl, dtype=np.uint16)
                 ch[0] = nl | ((1 if last else 0) << 8)
                 outs = np.zeros(32, dtype=np.uint16)
@@ -161,7 +177,7 @@ def _pack_phase(pn: Propnet, parts: List[Sequence[int]], keep_lits: Sequence[int
             for g in release_at.get(li, ()):
                 pending_release.append(new_slot[g])
             # gates never read and not kept (shouldn't exist) would leak a slot; harmless.
-        streams.append(np.concatenate(chunks) if chunks else np.zeros(0, np.uint16))
+        streams.append(np.concatenate(chunks) if chunks else np.zeros(0, np.uint32 if wide else np.uint16))
         stats.append((n_g, n_l))
     kept = {}
     for l in keep_lits:
@@ -192,7 +208,7 @@ def _remap_lits(lits: np.ndarray, kept: Dict[int, int]) -> np.ndarray:
     return out
 
 
-def pack_device_program(pn: Propnet) -> np.ndarray:
+def pack_device_program(pn: Propnet, force_wide=None) -> np.ndarray:
     """Returns the int32 device blob for ``gz_propnet_create``."""
     nr = len(pn.roles)
     role_sizes = pn.role_sizes
@@ -203,21 +219,40 @@ def pack_device_program(pn: Propnet) -> np.ndarray:
     leaves_a = 1 + nb + n_inputs
     leaves_b = 1 + nb
 
-    # phase A: next-state cone
-    sa, kept_a, high_a, st_a = _pack_phase(pn, [pn.prog['T']], list(pn.next_lit), leaves_a)
-    # phase B: LT then GL in one slot space
     keep_b = [l for ls in pn.legal_lit for l in ls] + [pn.terminal_lit] + \
         [l for ls in pn.goal_lit for l in ls]
-    sb, kept_b, high_b, st_b = _pack_phase(pn, [pn.prog['LT'], pn.prog['GL']], keep_b, leaves_b)
-    n_val = max(high_a, high_b)
-    if n_val > MAX_SLOT:
-        raise ValueError('propnet needs %d live slots; the 16-bit device format supports %d'
-                         % (n_val, MAX_SLOT))
+    max_fanin = max((len(l) for l in pn.gate_lits), default=0)
+    for wide in ([False, True] if force_wide is None else [bool(force_wide)]):
+        try:
+            # phase A: next-state cone
+            sa, kept_a, high_a, st_a = _pack_phase(pn, [pn.prog['T']], list(pn.next_lit), leaves_a, wide)
+            # phase B: LT then GL in one slot space
+            sb, kept_b, high_b, st_b = _pack_phase(pn, [pn.prog['LT'], pn.prog['GL']], keep_b, leaves_b, wide)
+        except OverflowError:
+            if wide:
+                raise
+            continue
+        n_val = max(high_a, high_b)
+        if wide or (n_val <= MAX_SLOT and max_fanin < 255):
+            break
+        # more live slots than a 15-bit slot index addresses: the wide format (32-bit literals, value
+        # array in global memory) takes over
     dump = n_val
     val_words = n_val + 32
 
     def finish(stream: np.ndarray) -> Tuple[np.ndarray, int]:
         s = stream.copy()
+        if wide:
+            pos = 0
+            nch = 0
+            while pos < len(s):
+                nl = int(s[pos]) & 0xFF
+                outs = s[pos + 1:pos + 33]
+                pad = outs == 0xFFFFFFFF
+                outs[pad] = dump + np.arange(32, dtype=np.uint32)[pad]
+                pos += 33 + 32 * nl
+                nch += 1
+            return s, nch
         # patch padding lanes' out slots to per-lane dump slots
         pos = 0
         nch = 0
@@ -256,7 +291,7 @@ def pack_device_program(pn: Propnet) -> np.ndarray:
         pos += len(arr)
 
     def add_stream(s16: np.ndarray, idx):
-        add(s16.view('<u4').astype(np.int64), idx)
+        add((s16 if wide else s16.view('<u4')).astype(np.int64), idx)
 
     add(role_sizes, D_OFF_ROLE_SIZES)
     add(lwo, D_OFF_LEGAL_WORD_OFF)
@@ -279,9 +314,12 @@ def pack_device_program(pn: Propnet) -> np.ndarray:
     hdr[D_TOTAL_WORDS] = pos
     hdr[D_VAL_WORDS] = val_words
     hdr[D_TERMINAL_LIT] = term_lit
-    hdr[D_CHUNKS_A], hdr[D_HALFS_A] = nca, len(pa)
-    hdr[D_CHUNKS_LT], hdr[D_HALFS_LT] = nclt, len(plt)
-    hdr[D_CHUNKS_GL], hdr[D_HALFS_GL] = ncgl, len(pgl)
+    # stream lengths in 16-bit units (wide streams: 2 per word) so that words = halfs / 2 either way
+    k = 2 if wide else 1
+    hdr[D_CHUNKS_A], hdr[D_HALFS_A] = nca, len(pa) * k
+    hdr[D_CHUNKS_LT], hdr[D_HALFS_LT] = nclt, len(plt) * k
+    hdr[D_CHUNKS_GL], hdr[D_HALFS_GL] = ncgl, len(pgl) * k
+    hdr[D_WIDE] = 1 if wide else 0
     hdr[D_N_GATES_A], hdr[D_N_LITS_A] = st_a[0]
     hdr[D_N_GATES_LT], hdr[D_N_LITS_LT] = st_b[0]
     hdr[D_N_GATES_GL], hdr[D_N_LITS_GL] = st_b[1]
@@ -299,6 +337,20 @@ def emulate_stream(blob: np.ndarray, which: str, val: np.ndarray):
     off, nch, nh = {'A': (h[D_OFF_PROG_A], h[D_CHUNKS_A], h[D_HALFS_A]),
                     'LT': (h[D_OFF_PROG_LT], h[D_CHUNKS_LT], h[D_HALFS_LT]),
                     'GL': (h[D_OFF_PROG_GL], h[D_CHUNKS_GL], h[D_HALFS_GL])}[which]
+    if h[D_WIDE]:
+        s = blob[off:off + nh // 2].view(np.uint32)
+        pos = 0
+        for _ in range(int(nch)):
+            nl = int(s[pos]) & 0xFF
+            outs = s[pos + 1:pos + 33].astype(np.int64)
+            lits = s[pos + 33:pos + 33 + 32 * nl].reshape(nl, 32).astype(np.int64)
+            acc = np.full(32, 0xFFFFFFFF, dtype=np.uint32)
+            for k in range(nl):
+                l = lits[k]
+                acc &= val[l >> 1] ^ (np.where(l & 1, 0xFFFFFFFF, 0).astype(np.uint32))
+            val[outs] = acc
+            pos += 33 + 32 * nl
+        return val
     s = blob[off:off + (nh + 1) // 2].view('<u2')
     pos = 0
     for _ in range(int(nch)):

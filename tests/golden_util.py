@@ -18,15 +18,17 @@ class FixtureMap:
 
     def __init__(self, fx, pn):
         assert fx['roles'] == pn.roles
-        b = {s: i for i, s in enumerate(pn.bases)}
-        self.base = np.array([b[s] for s in fx['bases']], dtype=np.int64)
+        # GDL symbols are case-insensitive: the interpreter that made the fixtures folds case, the
+        # compiled tables keep the rulesheet's spelling (the reference's gamedesc uses it: kingHasMoved)
+        b = {s.lower(): i for i, s in enumerate(pn.bases)}
+        self.base = np.array([b[s.lower()] for s in fx['bases']], dtype=np.int64)
         assert len(set(self.base.tolist())) == len(pn.bases) == len(fx['bases'])
         self.inp = []
         for r in range(len(pn.roles)):
-            m = {s: i for i, s in enumerate(pn.inputs[r])}
+            m = {s.lower(): i for i, s in enumerate(pn.inputs[r])}
             # fixture inputs are the rulesheet's `input` relation; must be the same set
-            assert set(fx['inputs'][r]) == set(pn.inputs[r])
-            self.inp.append(np.array([m[s] for s in fx['inputs'][r]], dtype=np.int64))
+            assert set(x.lower() for x in fx['inputs'][r]) == set(x.lower() for x in pn.inputs[r])
+            self.inp.append(np.array([m[s.lower()] for s in fx['inputs'][r]], dtype=np.int64))
         self.n_bases = len(pn.bases)
 
     def state_bits(self, idx_list):

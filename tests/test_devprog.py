@@ -22,10 +22,15 @@ def lit_words(val, lits):
     return val[lits >> 1] ^ np.where(lits & 1, 0xFFFFFFFF, 0).astype(np.uint32)
 
 
-@pytest.mark.parametrize('game', GAMES)
+@pytest.mark.parametrize('game', GAMES + ['breakthrough:wide', 'chess_15d'])
 def test_device_stream_emulation_matches_oracle(game):
+    force_wide = None
+    if game.endswith(':wide'):              # the wide (32-bit literal) stream format on a small game
+        game, force_wide = game.split(':')[0], True
     pn = tables.propnet_by_name(game)
-    blob = dp.pack_device_program(pn)
+    blob = dp.pack_device_program(pn, force_wide=force_wide)
+    if game == 'chess_15d' or force_wide:
+        assert blob[dp.D_WIDE] == 1
     h = blob[:dp.DEV_HEADER_WORDS].astype(np.int64)
     sm = RefStateMachine(tables.blob_by_name(game))
     nb, nr = pn.n_bases, len(pn.roles)
@@ -44,7 +49,7 @@ def test_device_stream_emulation_matches_oracle(game):
     goals = np.zeros((n, nr), dtype=np.uint8)
     moves = np.zeros((n, nr), dtype=np.int16)
     val = np.zeros(int(h[dp.D_VAL_WORDS]), dtype=np.uint32)
-    steps = 70 if game != 'amazons_10x10' else 40
+    steps = {'amazons_10x10': 40, 'chess_15d': 6}.get(game, 70)
     for step in range(steps):
         prev = states.copy()
         was_term = term.copy()

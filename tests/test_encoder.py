@@ -8,9 +8,10 @@ from galvanise_zero_b200 import bases, cppinterface, lookup, tables
 from galvanise_zero_b200.defs import datadesc
 from oracle.pnref import RefEncoder, RefStateMachine
 
-GAMES = ['breakthrough', 'reversi', 'connect6', 'amazons_10x10', 'breakthroughSmall']
+GAMES = ['breakthrough', 'reversi', 'connect6', 'amazons_10x10', 'breakthroughSmall', 'chess_15d', 'hexLG13']
 SHAPES = {'breakthrough': (5, 8, 8), 'reversi': (5, 8, 8), 'connect6': (8, 19, 19),
-          'amazons_10x10': (12, 10, 10)}   # data/*/models/*.json batch_input_shape of the reference
+          'amazons_10x10': (12, 10, 10), 'chess_15d': (32, 8, 8),
+          'hexLG13': (5, 13, 13)}          # data/*/models/*.json batch_input_shape of the reference
 
 
 def _setup(game, num_prev=1):
@@ -20,7 +21,10 @@ def _setup(game, num_prev=1):
     return gi, tr, ct
 
 
-def _trajectory(game, n_games=6, plies=40, seed=11):
+def _trajectory(game, n_games=None, plies=None, seed=11):
+    big = game in ('chess_15d', 'hexLG13')
+    n_games = n_games or (3 if big else 6)
+    plies = plies or (16 if big else 40)
     ref = RefStateMachine(tables.blob_by_name(game))
     s = np.zeros((n_games, ref.state_words), dtype=np.uint32)
     l = np.zeros((n_games, ref.legal_words), dtype=np.uint32)

@@ -58,6 +58,44 @@ def test_playout_steps_bit_exact(game, n):
     assert int(cnt.item()) == total
 
 
+@pytest.mark.parametrize('game,n,steps', [('chess_15d', 100, 24), ('chess_15d', 1, 10), ('hexLG13', 40, 12)])
+def test_wide_games_playout_bit_exact(game, n, steps):
+    """BASELINE configs 3 and 5: games whose propnets exceed the 16-bit slot format (chess_15d: 243 K
+    gates, hexLG13: 29 753 bases / 574 K gates) run through the wide kernel (32-bit literals, value
+    array in L2-resident scratch) — same bit-exact contract against the C oracle."""
+    dev = _sm(game)
+    ref = RefStateMachine(tables.blob_by_name(game))
+    assert dev.state_words == ref.state_words and dev.legal_words == ref.legal_words
+    seed = 0xC0DE + n
+    s_r = np.zeros((n, ref.state_words), dtype=np.uint32)
+    l_r = np.zeros((n, ref.legal_words), dtype=np.uint32)
+    t_r = np.ones(n, dtype=np.uint8)
+    g_r = np.zeros((n, ref.n_roles), dtype=np.uint8)
+    m_r = np.zeros((n, ref.n_roles), dtype=np.int16)
+    s_d = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
+    l_d, t_d, g_d = dev.alloc_views(n)
+    t_d.fill_(1)
+    m_d = torch.zeros((n, dev.n_roles), dtype=torch.int16, device=dev.device)
+    prev = None
+    for step in range(steps):
+        prev = s_r.copy()
+        ref.playout_step(0, seed, step, s_r, l_r, t_r, g_r, m_r)
+        dev.playout_step(s_d, l_d, t_d, g_d, seed, step, moves_out=m_d)
+        assert np.array_equal(_np(m_d), m_r), (game, step, 'moves')
+        assert np.array_equal(_np(s_d), s_r), (game, step, 'states')
+        assert np.array_equal(_np(l_d), l_r), (game, step, 'legal')
+        assert np.array_equal(_np(t_d), t_r), (game, step, 'terminal')
+        assert np.array_equal(_np(g_d), g_r), (game, step, 'goals')
+    # transition + eval entry points on the last ply
+    live = m_r[:, 0] >= 0
+    got = dev.transition(torch.from_numpy(prev[live].view(np.int32)).to(dev.device),
+                         torch.from_numpy(m_r[live]).to(dev.device))
+    for a, b in zip(got, ref.transition_batch(prev[live], m_r[live])):
+        assert np.array_equal(_np(a), b)
+    for a, b in zip(dev.eval(s_d), ref.eval_batch(s_r)):
+        assert np.array_equal(_np(a), b)
+
+
 @pytest.mark.parametrize('game', ['breakthrough', 'reversi'])
 def test_transition_eval_and_host_api(game):
     dev = _sm(game)

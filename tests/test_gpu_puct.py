@@ -44,6 +44,7 @@ def _device_search(eng, evals, n_moves, seed=1):
 
 
 @pytest.mark.parametrize('game,evals,moves', [('reversi', 200, 20), ('breakthrough', 300, 20),
+                                              ('chess_15d', 60, 3), ('hexLG13', 40, 3),
                                               ('connect6', 100, 4)])
 def test_device_search_matches_reference(game, evals, moves):
     from galvanise_zero_b200.engine import PuctEngine

@@ -7,7 +7,7 @@ from galvanise_zero_b200 import tables
 from oracle.pnref import RefStateMachine
 from golden_util import FixtureMap, load_fixture
 
-GAMES = ['breakthrough', 'reversi', 'connect6', 'amazons_10x10', 'breakthroughSmall']
+GAMES = ['breakthrough', 'reversi', 'connect6', 'amazons_10x10', 'breakthroughSmall', 'chess_15d', 'hexLG13']
 
 
 @pytest.mark.parametrize('game', GAMES)
