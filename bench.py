@@ -261,6 +261,9 @@ def run_propnet(args, rank, world, local):
 
 
 # ------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum of one puct_pre_kernel launch in the bench configuration
+# (ncu --set full capture, profiles/r01_puct_pre_kernel_ncu_full.md)
+PUCT_PRE_NCU_TRAFFIC_BYTES = 56526592
 PUCT_GAME = 'reversi'
 PUCT_GAMES_PER_GPU = 4096
 PUCT_EVALS_PER_MOVE = 800
@@ -355,11 +358,25 @@ def run_puct(args, rank, world, local):
     evals = all_sum(d_evals, world, eng.device)
     value = moves / (ms_max * 1e-3)
 
-    # ---- per-kernel timing of one step, eager, CUDA events on the launching stream
+    # ---- per-kernel timing, eager, CUDA events on the launching stream: 40 engine steps with events
+    # between the launches (gz_puct_advance_timed), each followed by the real network forward so that the
+    # trees keep evolving; the same steps give the algorithmic bytes from the engine's traffic counters
     parts = {}
     with torch.no_grad():
-        reps = 10
-        parts['engine_advance_ms'] = time_region(lambda: [eng.advance(eng.policy, eng.value, args.sub_iters) for _ in range(reps)], eng.device) / reps
+        reps = 40
+        acc = {}
+        t0c = eng.totals()
+        pol, val = net(eng.planes)
+        for _ in range(reps):
+            planes, ms_k = eng.advance_timed(pol, val)
+            for k, v in ms_k.items():
+                acc[k] = acc.get(k, 0.0) + v
+            pol, val = net(planes)
+        torch.cuda.synchronize(eng.device)
+        t1c = eng.totals()
+        for k, v in acc.items():
+            parts[k + '_ms'] = v / reps
+        parts['engine_advance_ms'] = sum(acc.values()) / reps
         x = eng.planes
         side = torch.cuda.Stream(device=eng.device)
         side.wait_stream(torch.cuda.current_stream(eng.device))
@@ -372,21 +389,39 @@ def run_puct(args, rank, world, local):
         with torch.cuda.graph(g_nn):
             net(x)
         g_nn.replay()
-        parts['network_forward_ms'] = time_region(lambda: [g_nn.replay() for _ in range(reps)], eng.device) / reps
-        st = eng.sm
-        s_in = st.initial_states(Gp)
-        mv = torch.full((Gp, st.n_roles), -1, dtype=torch.int16, device=eng.device)
-        outb = (torch.empty_like(s_in),) + st.alloc_views(Gp)
-        parts['propnet_transition_ms'] = time_region(lambda: [st.transition(s_in, mv, out=outb) for _ in range(reps)], eng.device) / reps
+        parts['network_forward_ms'] = time_region(lambda: [g_nn.replay() for _ in range(10)], eng.device) / 10
+    # roofline of the dominant hand-written kernel, puct_pre_kernel (select + reply + backup + controller):
+    # algorithmic bytes per evaluation = sum over path nodes of (32 B node record +
+    # 24 B per child scanned) + 24 B per path node written by backup + 20 B per child created
+    d_nodes = t1c['select_nodes'] - t0c['select_nodes']
+    d_children = t1c['select_children'] - t0c['select_children']
+    d_new = t1c['new_children'] - t0c['new_children']
+    d_ev = max(t1c['evals'] - t0c['evals'], 1.0)
+    alg_bytes = 32.0 * d_nodes + 24.0 * d_children + 24.0 * d_nodes + 20.0 * d_new
+    per_launch = alg_bytes / reps
+    pre_s = parts['puct_pre_kernel_ms'] * 1e-3
+    achieved = per_launch / pre_s / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / peaks['hbm_gbs'], 'traffic': PUCT_PRE_NCU_TRAFFIC_BYTES,
+                'kernel': 'puct_pre_kernel (one warp per game tree: reply + backup + controller + select; '
+                          'dependent pointer chasing over a %.1f GB arena, latency-bound)' % (eng.arena_bytes / 1e9),
+                'bytes_per_unit': alg_bytes / d_ev, 'unit_name': 'evaluation', 'units_per_launch': d_ev / reps,
+                'algorithmic_bytes_per_launch': per_launch,
+                'mean_path_nodes_per_eval': d_nodes / d_ev, 'mean_children_scanned_per_eval': d_children / d_ev,
+                'mean_children_created_per_eval': d_new / d_ev,
+                'launch_ms': parts['puct_pre_kernel_ms'], 'peak_source': peaks['source'] + ' (HBM copy)',
+                'traffic_source': 'ncu --set full, profiles/r01_puct_pre_kernel_ncu_full.md (dram read+write per launch)'}
     flops = net.flops_per_position * Gp
     nn_s = parts['network_forward_ms'] * 1e-3
-    achieved = flops / nn_s / 1e12
+    nn_ach = flops / nn_s / 1e12
     peak = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
-    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                'frac': achieved / peak, 'traffic': None,
-                'kernel': 'residual tower forward (cuDNN runtime-fused conv+bias+ReLU via PyTorch, bf16 channels_last), %d positions per launch' % Gp,
-                'flops_per_unit': net.flops_per_position, 'units_per_launch': Gp,
-                'peak_source': peaks['source'] + ' (sustained bf16)'}
+    network_roofline = {'bound': 'tensor', 'achieved': nn_ach, 'peak': peak, 'unit': 'TFLOP/s',
+                        'frac': nn_ach / peak, 'traffic': None,
+                        'kernel': 'residual tower forward (PyTorch module, cuDNN runtime-fused conv+bias+ReLU, bf16 '
+                                  'channels_last) — the consumer of the planes, not part of the hot path; %d positions '
+                                  'per launch' % Gp,
+                        'flops_per_unit': net.flops_per_position, 'units_per_launch': Gp,
+                        'peak_source': peaks['source'] + ' (sustained bf16)'}
 
     # ---- e2e: the reference-shaped numpy poll() API with host buffers (D2H planes, H2D planes for the
     # network as Keras predict_on_batch does, D2H policy/value, H2D into the engine), every step
@@ -512,7 +547,8 @@ def run_puct(args, rank, world, local):
                        'pipelines': '%d engine+network pipelines of %d games each on separate streams' % (P, G // P),
                        'parallelism': 'games sharded across %d GPU(s), no collective on the hot path' % world},
             'evals_per_s': evals / (ms_max * 1e-3), 'moves_in_window': moves,
-            'roofline': roofline, 'kernel_times_ms': parts, 'cpu_baseline': cpu, 'e2e': e2e,
+            'roofline': roofline, 'network_roofline': network_roofline, 'kernel_times_ms': parts,
+            'cpu_baseline': cpu, 'e2e': e2e,
             'gpu_launches': args.steps * runner.kernels_per_step, 'clocks': clocks,
             'engine_totals': {k: t_after[k] for k in ('errors', 'halted', 'max_nodes', 'max_children', 'games', 'samples')},
             'samples_gathered_to_rank0': n_gathered,

@@ -36,6 +36,7 @@
 
 extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn);   // gz_propnet.cu (device pointer)
 extern "C" int64_t gz_propnet_wide_scratch_bytes(const gz_propnet* pn);
+
 extern "C" int gz_sm_transition_scratch(gz_propnet* pn, int64_t n, const uint32_t* d_states, const int16_t* d_moves,
                                         uint32_t* d_next, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,
                                         int goals_mode, void* stream, uint32_t* d_scratch);
@@ -154,6 +155,7 @@ struct PuctTotals {
     int errors, halted, first_error, max_nodes, max_children;
     int dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts;
     int waiting_eval;
+    unsigned long long sel_nodes, sel_children, new_children;
 };
 
 __global__ void puct_totals_kernel(const __grid_constant__ PuctEngine E, PuctTotals* out) {
@@ -177,6 +179,9 @@ __global__ void puct_totals_kernel(const __grid_constant__ PuctEngine E, PuctTot
     atomicAdd(&out->resigns, c.number_resigns);
     atomicAdd(&out->aborts, c.number_aborts_game_length);
     if (c.eval_node >= 0) atomicAdd(&out->waiting_eval, 1);
+    atomicAdd(&out->sel_nodes, (unsigned long long)c.total_sel_nodes);
+    atomicAdd(&out->sel_children, (unsigned long long)c.total_sel_children);
+    atomicAdd(&out->new_children, (unsigned long long)c.total_new_children);
 }
 
 // ---- synthetic network (parity / bench utility): same function as oracle/ref_harness.cpp
@@ -230,6 +235,7 @@ struct gz_puct {
     int cache_words = 0;      // per-warp shared-memory words for the child cache (0: use the global scratch)
     int plane_c_pad = 0;      // 0: planes are NCHW rows; >0: channels-last rows padded to this channel count
     uint32_t* d_pn_scratch = nullptr;   // wide games: this engine's propnet value-array scratch
+
     struct HostPoll* hp = nullptr;   // host-buffer poll state (gz_puct_host_poll_*), created on first use
 };
 
@@ -411,8 +417,8 @@ extern "C" int64_t gz_puct_info(const gz_puct* h, int what) {
 // One engine step. d_policy [G][policy_stride] f32 and d_value [G][n_rewards] f32 are the network's
 // outputs for the planes produced by the previous advance (ignored when nn_fresh == 0, e.g. on the
 // very first call). d_planes receives [G][total_size] of plane_dtype, one row per game.
-extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
-                               void* d_planes, int plane_dtype, void* stream) {
+static int advance_impl(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
+                        void* d_planes, int plane_dtype, void* stream, cudaEvent_t* evs /* 6 or null */) {
     if (!h) { gz_set_error("null engine"); return GZ_ERR_ARG; }
     if (nn_fresh && (!d_policy || !d_value)) { gz_set_error("network outputs missing"); return GZ_ERR_ARG; }
     if (sub_iters < 1) sub_iters = 1;
@@ -422,18 +428,23 @@ extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d
     E.nn_value = d_value;
     cudaStream_t s = (cudaStream_t)stream;
     const int blocks = (E.G + PUCT_WARPS_PER_BLOCK - 1) / PUCT_WARPS_PER_BLOCK;
+    if (evs) GZ_CUDA(cudaEventRecord(evs[0], s));
     for (int it = 0; it < sub_iters; it++) {
         puct_pre_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32,
                           h->cache_words ? ((size_t)h->cache_words + 2 * (size_t)E.MAXD) * 4 * PUCT_WARPS_PER_BLOCK : 0, s>>>(
             E, (it == 0 && nn_fresh) ? 1 : 0, h->cache_words);
         GZ_CUDA(cudaGetLastError());
+        if (evs) GZ_CUDA(cudaEventRecord(evs[1], s));
         puct_reroot_kernel<<<E.G, REROOT_THREADS, 0, s>>>(E);
         GZ_CUDA(cudaGetLastError());
+        if (evs) GZ_CUDA(cudaEventRecord(evs[2], s));
         int rc = gz_sm_transition_scratch(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
                                           GZ_GOALS_TERMINAL_ONLY, stream, h->d_pn_scratch);
         if (rc != GZ_OK) return rc;
+        if (evs) GZ_CUDA(cudaEventRecord(evs[3], s));
         puct_post_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, s>>>(E);
         GZ_CUDA(cudaGetLastError());
+        if (evs) GZ_CUDA(cudaEventRecord(evs[4], s));
     }
     if (d_planes) {
         // every row is encoded (rows of games that do not wait for the network hold a stale but valid
@@ -442,7 +453,32 @@ extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d
                                   h->plane_c_pad, stream);
         if (rc != GZ_OK) return rc;
     }
+    if (evs) GZ_CUDA(cudaEventRecord(evs[5], s));
     return GZ_OK;
+}
+
+extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
+                               void* d_planes, int plane_dtype, void* stream) {
+    return advance_impl(h, d_policy, d_value, nn_fresh, sub_iters, d_planes, plane_dtype, stream, nullptr);
+}
+
+// Measurement aid: one engine step (sub_iters == 1) with CUDA events between its launches on `stream`;
+// waits for the step and returns the device time of each launch in milliseconds:
+// h_ms5 = [puct_pre_kernel, puct_reroot_kernel, pn_kernel, puct_post_kernel, encode_kernel].
+extern "C" int gz_puct_advance_timed(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh,
+                                     void* d_planes, int plane_dtype, void* stream, float* h_ms5) {
+    if (!h || !h_ms5) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    cudaEvent_t evs[6];
+    for (int i = 0; i < 6; i++) GZ_CUDA(cudaEventCreate(&evs[i]));
+    int rc = advance_impl(h, d_policy, d_value, nn_fresh, 1, d_planes, plane_dtype, stream, evs);
+    if (rc == GZ_OK) {
+        cudaError_t e = cudaEventSynchronize(evs[5]);
+        if (e != cudaSuccess) { gz_set_error("timed step failed: %s", cudaGetErrorString(e)); rc = GZ_ERR_CUDA; }
+        for (int i = 0; i < 5 && rc == GZ_OK; i++) cudaEventElapsedTime(&h_ms5[i], evs[i], evs[i + 1]);
+    }
+    for (int i = 0; i < 6; i++) cudaEventDestroy(evs[i]);
+    return rc;
 }
 
 // Planes layout written by gz_puct_advance: c_pad == 0 -> [G][C][H][W]; c_pad > 0 (multiple of 8) ->
@@ -641,7 +677,7 @@ extern "C" int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes) {
 
 // totals: [evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children,
 //          dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval,
-//          ready_count]
+//          ready_count, select_nodes, select_children, new_children]
 extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     if (!h || !out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
@@ -659,6 +695,7 @@ extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     out[8] = t.max_nodes; out[9] = t.max_children; out[10] = t.dupes; out[11] = t.no_samples;
     out[12] = t.fp_resign0; out[13] = t.fp_resign1; out[14] = t.early_run_to_ends; out[15] = t.resigns;
     out[16] = t.aborts; out[17] = t.waiting_eval; out[18] = (double)ready;
+    out[19] = (double)t.sel_nodes; out[20] = (double)t.sel_children; out[21] = (double)t.new_children;
     return GZ_OK;
 }
 

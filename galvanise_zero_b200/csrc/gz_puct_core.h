@@ -113,6 +113,9 @@ struct GameCtl {
     int32_t mode;   // 0 self-play, 1 player (single search on command)
     // counters (monotonic)
     uint64_t total_evals, total_moves, total_games, total_samples, total_playouts;
+    // traffic accounting for the roofline: nodes passed through by select, children
+    // scanned there, children written by node creation
+    uint64_t total_sel_nodes, total_sel_children, total_new_children;
     // per-manager style stats (selfplaymanager.h:46-72)
     int32_t saw_dupes, no_samples_taken, false_positive_resigns0, false_positive_resigns1,
         number_early_run_to_ends, number_resigns, number_aborts_game_length;
@@ -752,6 +755,8 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
         pcst += k;
         NODE(n_puct, n) = pcst;
     }
+    c->total_sel_nodes++;
+    c->total_sel_children += (uint64_t)nc;
     if (nc == 1) {
         pn[c->path_len] = n; pc[c->path_len] = 0; c->path_len++;
         return 0;
@@ -1676,6 +1681,7 @@ GZP_HDN void gzp_step_post(GameView& V) {
     if (N < 0) { c->phase = PH_HALT; return; }
     if (parent >= 0) CHILD(c_to, NODE(n_child0, parent) + c->req_child) = N;
     c->new_node = N;
+    c->total_new_children += (uint64_t)NODE(n_nchild, N);
     const bool needs_eval = !gzp_is_finalised(V, N) && NODE(n_nchild, N) > 1;
     if (needs_eval) {
         c->eval_node = N;

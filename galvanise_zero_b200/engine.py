@@ -31,7 +31,8 @@ SP_FIELDS = ['oscillate_sampling_pct', 'temperature_for_policy', 'evals_per_move
              'run_to_end_minimum_game_depth', 'abort_max_length']
 TOTAL_KEYS = ['evals', 'moves', 'games', 'samples', 'playouts', 'errors', 'halted', 'first_error',
               'max_nodes', 'max_children', 'dupes', 'no_samples', 'fp_resign0', 'fp_resign1',
-              'early_run_to_ends', 'resigns', 'aborts', 'waiting_eval', 'ready']
+              'early_run_to_ends', 'resigns', 'aborts', 'waiting_eval', 'ready',
+              'select_nodes', 'select_children', 'new_children']
 # sample record header (csrc/gz_puct_core.h SR_*)
 SR_DEPTH, SR_GAME_LENGTH, SR_SLOT, SR_MATCH, SR_HAS_RESIGNED, SR_RESIGN_FP, SR_START_DEPTH, SR_VISITS, \
     SR_LEAD, SR_N_PREV, SR_N_CHILDREN = range(1, 12)
@@ -154,6 +155,21 @@ class PuctEngine(object):
                                            sub_iters, self.planes.data_ptr(), code, self._stream()))
         return self.planes
 
+    def advance_timed(self, policy=None, value=None):
+        """One engine step with CUDA events between its launches (measurement aid); returns
+        (planes, {kernel: ms})."""
+        fresh = policy is not None
+        code = {torch.float32: 0, torch.bfloat16: 1}[self.planes.dtype]
+        ms = (ctypes.c_float * 5)()
+        self._L.gz_puct_advance_timed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                  ctypes.POINTER(ctypes.c_float)]
+        _lib.check(self._L.gz_puct_advance_timed(self._h, policy.data_ptr() if fresh else None,
+                                                 value.data_ptr() if fresh else None, 1 if fresh else 0,
+                                                 self.planes.data_ptr(), code, self._stream(), ms))
+        names = ['puct_pre_kernel', 'puct_reroot_kernel', 'pn_kernel', 'puct_post_kernel', 'encode_kernel']
+        return self.planes, dict(zip(names, [float(x) for x in ms]))
+
     def synth_nn(self, planes=None, seed=1):
         """Deterministic synthetic network (include/gz_synth.h) into self.policy / self.value."""
         planes = self.planes if planes is None else planes
@@ -175,7 +191,7 @@ class PuctEngine(object):
 
     # ---- results
     def totals(self):
-        out = (ctypes.c_double * 19)()
+        out = (ctypes.c_double * 22)()
         _lib.check(self._L.gz_puct_totals(self._h, out, self._stream()))
         return dict(zip(TOTAL_KEYS, [float(x) for x in out]))
 

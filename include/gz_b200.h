@@ -160,6 +160,11 @@ int gz_puct_set_config(gz_puct* h, const double* sp_conf, const double* puct_con
 int64_t gz_puct_info(const gz_puct* h, int what);
 int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
                     void* d_planes, int plane_dtype, void* stream);
+/* Measurement aid: one engine step with CUDA events between its launches; waits for it and returns the
+ * device time of each launch in ms: [puct_pre_kernel, puct_reroot_kernel, pn_kernel, puct_post_kernel,
+ * encode_kernel]. */
+int gz_puct_advance_timed(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh,
+                          void* d_planes, int plane_dtype, void* stream, float* h_ms5);
 /* planes written by gz_puct_advance: c_pad == 0 -> [G][C][H][W] (reference layout, default);
  * c_pad > 0 (multiple of 8) -> channels-last [G][H][W][c_pad], zero planes beyond C */
 int gz_puct_set_plane_layout(gz_puct* h, int c_pad);
@@ -175,7 +180,7 @@ int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream);
  * other's batch (the reference's two managers per worker, src/cpp/supervisor.cpp:79-99). */
 int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* const* h_arrays, int n_arrays, void* stream);
 int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes);
-int gz_puct_totals(gz_puct* h, double* h_out19, void* stream);
+int gz_puct_totals(gz_puct* h, double* h_out22, void* stream);
 int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream);
 int gz_puct_clear_unique_states(gz_puct* h, void* stream);
 int gz_puct_command(gz_puct* h, int game, int cmd, int arg, int evals, const uint32_t* h_state, void* stream);
