@@ -42,3 +42,13 @@ def generation_for(game, num_previous_states=1, draw_head=None):
     return GenerationDescription(game=game, name='b200_synthetic', channel_last=False,
                                  multiple_policy_heads=True,
                                  num_previous_states=num_previous_states, draw_head=draw_head)
+
+
+@attr.s
+class GenerationSamples(object):
+    """``src/ggpzero/defs/datadesc.py:39-53`` — one generation's samples as stored on disk / sent on the wire."""
+    game = attr.ib(default="game")
+    date_created = attr.ib(default='2018-01-24 22:28')
+    with_generation = attr.ib(default="v6_123")
+    num_samples = attr.ib(default=1024)
+    samples = attr.ib(default=attr.Factory(list))

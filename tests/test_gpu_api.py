@@ -198,3 +198,29 @@ def test_supervisor_poller_wrapper_collects_samples():
     n0 = len(got)
     sup.poll_loop(cb=lambda: bool(got.extend(sup.fetch_samples())) or len(got) >= n0 + 10)
     assert len(got) >= n0 + 10
+
+
+def test_worker_rehost_request_samples_and_generation_file(tmp_path):
+    """SelfPlayWorker (src/ggpzero/distributed/worker.py:138-206 re-hosted): worker-mode supervisor (two
+    managers, double-buffered), samples with base64 states, written and re-read as a generation file."""
+    from galvanise_zero_b200 import gendata, worker
+    game = 'breakthroughSmall'
+    gi = lookup.by_name(game)
+    tr = bases.GdlBasesTransformer(gi, datadesc.generation_for(game))
+    w = worker.SelfPlayWorker(gi.get_sm(), _SynthNN(tr), self_play_batch_size=32, min_num_samples=25,
+                              identifier='wk')
+    w.configure_self_play(confs.selfplay_config_template(evals_per_move=20))
+    assert len(w.supervisor.c_supervisor.managers) == 2
+    samples = w.on_request_samples()
+    assert len(samples) > 25 and w.last_stats['predictions'] > 0
+    assert all(isinstance(s.state, str) for s in samples)
+    idents = {s.match_identifier.split('_')[1] for s in samples}
+    assert idents <= {'m0', 'm1'}                      # samples come from both managers
+    path = str(tmp_path / gendata.gendata_filename(game, 1))
+    gendata.write_gendata(path, game, 'b200_1', samples)
+    back = gendata.read_gendata(path)
+    assert back.num_samples == len(samples)
+    st = gendata.decode_state(back.samples[0].state)
+    assert len(st) >= tr.num_bases and set(st) <= {0, 1}
+    more = w.on_request_samples()                      # resumable
+    assert len(more) > 25
