@@ -26,6 +26,7 @@
 #include "../../include/gz_propnet_format.h"
 #include "gz_devformat.h"
 #include "gz_common.cuh"
+#include "gz_spec.cuh"
 
 // ------------------------------------------------------------------------------------------------
 struct PnParams {
@@ -499,12 +500,29 @@ struct gz_propnet {
     cudaStream_t host_stream = nullptr;
     // wide games: one value-array scratch per stream that launches (engines on different streams may
     // share one gz_propnet)
+    // game-specialised thread-sliced kernels (gz_spec.cuh), used for batches >= spec_min_batch
+    const GzSpecEntry* spec = nullptr;
+    int64_t spec_min_batch = (int64_t)1 << 18;
     std::vector<std::pair<cudaStream_t, uint32_t*>> wide_scratch;
     int wide_grid = 0;
     int64_t wide_stride = 0;
 };
 
 extern "C" int gz_version(void) { return 100; }
+
+// registry of specialised games (filled by static initialisers of csrc/gz_spec_<game>.cu)
+static GzSpecEntry* g_spec_head = nullptr;
+void gz_spec_register(GzSpecEntry* e) { e->next = g_spec_head; g_spec_head = e; }
+const GzSpecEntry* gz_spec_find(uint64_t hash) {
+    for (const GzSpecEntry* e = g_spec_head; e; e = e->next) if (e->hash == hash) return e;
+    return nullptr;
+}
+static uint64_t fnv1a64(const void* data, size_t bytes) {
+    const uint8_t* p = (const uint8_t*)data;
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 0x100000001b3ULL; }
+    return h;
+}
 
 static int configure_launch(gz_propnet* pn, const int32_t* h) {
     PnParams& P = pn->P;
@@ -671,6 +689,7 @@ extern "C" int gz_propnet_create(const int32_t* h, int64_t n_words, int device, 
     P.goal_lit32 = P.wide ? (const uint32_t*)(base + o_glit32) : nullptr;
     int rc = configure_launch(pn, h);
     if (rc != GZ_OK) { cudaFree(pn->d_arena); delete pn; return rc; }
+    pn->spec = gz_spec_find(fnv1a64(h, (size_t)n_words * 4));
     *out = pn;
     return GZ_OK;
 }
@@ -683,6 +702,12 @@ extern "C" void gz_propnet_destroy(gz_propnet* pn) {
     for (auto& ws : pn->wide_scratch) cudaFree(ws.second);
     if (pn->host_stream) cudaStreamDestroy(pn->host_stream);
     delete pn;
+}
+
+extern "C" int gz_propnet_set_spec_min_batch(gz_propnet* pn, int64_t min_batch) {
+    if (!pn) { gz_set_error("null propnet"); return GZ_ERR_ARG; }
+    pn->spec_min_batch = min_batch;
+    return GZ_OK;
 }
 
 extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn) { return pn ? pn->P.init_words : nullptr; }
@@ -701,6 +726,7 @@ extern "C" int64_t gz_propnet_info(const gz_propnet* pn, int what) {
         case GZ_INFO_GRID: return pn->grid_max;
         case GZ_INFO_STAGED_MASK: return P.staged[0] | (P.staged[1] << 1) | (P.staged[2] << 2);
         case GZ_INFO_N_INPUTS: return P.n_inputs;
+        case GZ_INFO_SPECIALISED: return pn->spec ? 1 : 0;
         default: break;
     }
     if (what >= GZ_INFO_ROLE_SIZE0 && what < GZ_INFO_ROLE_SIZE0 + P.n_roles) return P.role_sizes[what - GZ_INFO_ROLE_SIZE0];
@@ -734,6 +760,20 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
     GZ_CUDA(cudaSetDevice(pn->device));
     const int64_t n_tiles = (n + 31) / 32;
     cudaStream_t st = (cudaStream_t)stream;
+    if (pn->spec && pn->spec_min_batch >= 0 && n >= pn->spec_min_batch) {
+        // large batch of a game with a specialised kernel: one thread per 32-game tile
+        SpecArgs a;
+        a.n = n; a.slot0 = slot0; a.states_in = states_in; a.moves_in = moves_in; a.states_out = states_out;
+        a.legal = legal; a.terminal = terminal; a.goals = goals; a.moves_out = moves_out;
+        a.transitions = transitions; a.seed = seed; a.step = step; a.goals_mode = goals_mode;
+        const int64_t n_batches = (n + 1023) / 1024;
+        const int grid = (int)std::min<int64_t>((n_batches + SPEC_WARPS - 1) / SPEC_WARPS, pn->n_sms);
+        if (pn->spec->launch(MODE, a, grid, st) != 0) {
+            gz_set_error("specialised kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return GZ_ERR_CUDA;
+        }
+        return GZ_OK;
+    }
     if (pn->P.wide) {
         static std::mutex mu;
         uint32_t* scratch = own_scratch;

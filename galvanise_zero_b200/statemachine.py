@@ -51,6 +51,13 @@ class DeviceStateMachine:
             'staged_mask': info(_lib.INFO_STAGED_MASK),
         }
         self.init_words = tables.pack_state_bits(self.propnet.init_state, self.state_words)
+        self.specialised = bool(info(10))      # a generated thread-sliced kernel exists for this game
+        self.launch_info['specialised'] = self.specialised
+
+    def set_spec_min_batch(self, n: int):
+        """Batches of at least ``n`` states use the game-specialised kernel (default 2^18; < 0 disables)."""
+        self._L.gz_propnet_set_spec_min_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        _lib.check(self._L.gz_propnet_set_spec_min_batch(self._h, int(n)))
 
     def __del__(self):
         h = getattr(self, '_h', None)

@@ -55,10 +55,14 @@ void gz_propnet_destroy(gz_propnet* pn);
 enum {
     GZ_INFO_N_BASES = 0, GZ_INFO_N_ROLES = 1, GZ_INFO_STATE_WORDS = 2, GZ_INFO_LEGAL_WORDS = 3,
     GZ_INFO_VAL_WORDS = 4, GZ_INFO_WARPS_PER_CTA = 5, GZ_INFO_SMEM_BYTES = 6, GZ_INFO_GRID = 7,
-    GZ_INFO_STAGED_MASK = 8, GZ_INFO_N_INPUTS = 9, GZ_INFO_ROLE_SIZE0 = 16 /* +r */,
+    GZ_INFO_STAGED_MASK = 8, GZ_INFO_N_INPUTS = 9, GZ_INFO_SPECIALISED = 10, GZ_INFO_ROLE_SIZE0 = 16 /* +r */,
     GZ_INFO_LEGAL_WORD_OFF0 = 24 /* +r */
 };
 int64_t gz_propnet_info(const gz_propnet* pn, int what);
+/* Games with a generated, game-specialised kernel (csrc/gz_spec_<game>.cu; GZ_INFO_SPECIALISED == 1) use it
+ * for batches of at least `min_batch` states (default 2^18); min_batch < 0 disables it, 0 forces it. The
+ * table-driven kernel and the specialised one return identical results. */
+int gz_propnet_set_spec_min_batch(gz_propnet* pn, int64_t min_batch);
 
 /* Layouts (n = number of states, R = roles):
  *   states  uint32 [n][state_words]   packed bases, LSB first, rows padded to 16 B

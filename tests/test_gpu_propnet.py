@@ -96,6 +96,55 @@ def test_wide_games_playout_bit_exact(game, n, steps):
         assert np.array_equal(_np(a), b)
 
 
+@pytest.mark.parametrize('n', [1, 33, 1000, 1024, 5000])
+def test_specialised_kernel_bit_exact(n):
+    """The generated thread-sliced kernel of breakthrough (csrc/gz_spec_breakthrough.cu), forced on for small
+    batches: playout / transition / eval bit-exact with the C oracle, ragged tails included."""
+    game = 'breakthrough'
+    dev = _sm(game)
+    assert dev.specialised, 'device program hash does not match the generated kernel: rerun tools/gen_spec_kernel.py'
+    dev.set_spec_min_batch(0)
+    ref = RefStateMachine(tables.blob_by_name(game))
+    seed = 0x5BEC + n
+    s_r = np.zeros((n, ref.state_words), dtype=np.uint32)
+    l_r = np.zeros((n, ref.legal_words), dtype=np.uint32)
+    t_r = np.ones(n, dtype=np.uint8)
+    g_r = np.zeros((n, ref.n_roles), dtype=np.uint8)
+    m_r = np.zeros((n, ref.n_roles), dtype=np.int16)
+    s_d = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
+    l_d, t_d, g_d = dev.alloc_views(n)
+    t_d.fill_(1)
+    m_d = torch.zeros((n, dev.n_roles), dtype=torch.int16, device=dev.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev.device)
+    total = 0
+    prev = None
+    for step in range(80):
+        prev = s_r.copy()
+        total += ref.playout_step(3, seed, step, s_r, l_r, t_r, g_r, m_r)
+        dev.playout_step(s_d, l_d, t_d, g_d, seed, step, slot0=3, moves_out=m_d, counter=cnt)
+        assert np.array_equal(_np(m_d), m_r), (step, 'moves')
+        assert np.array_equal(_np(s_d), s_r), (step, 'states')
+        assert np.array_equal(_np(l_d), l_r), (step, 'legal')
+        assert np.array_equal(_np(t_d), t_r), (step, 'terminal')
+        assert np.array_equal(_np(g_d), g_r), (step, 'goals')
+    assert int(cnt.item()) == total
+    mv = m_r.copy()
+    want = ref.transition_batch(prev, np.where(mv < 0, 0, mv).astype(np.int16))
+    mv_dev = torch.from_numpy(mv).to(dev.device)
+    got = dev.transition(torch.from_numpy(prev.view(np.int32)).to(dev.device), mv_dev)
+    live = mv[:, 0] >= 0
+    for a, b in zip(got, want):
+        assert np.array_equal(_np(a)[live], b[live])
+    # rows with a negative first move keep their state (the PUCT pipeline's root evaluation)
+    assert np.array_equal(_np(got[0])[~live], prev[~live])
+    for a, b in zip(dev.eval(s_d), ref.eval_batch(s_r)):
+        assert np.array_equal(_np(a), b)
+    # the table-driven kernel gives the same answers
+    dev.set_spec_min_batch(-1)
+    for a, b in zip(dev.eval(s_d), ref.eval_batch(s_r)):
+        assert np.array_equal(_np(a), b)
+
+
 @pytest.mark.parametrize('game', ['breakthrough', 'reversi'])
 def test_transition_eval_and_host_api(game):
     dev = _sm(game)
