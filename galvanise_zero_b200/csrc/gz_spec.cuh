@@ -42,29 +42,33 @@ struct SpecArgs {
 // In-register transpose of a 32x32 bit matrix, LSB-first: bit c of a[r] <-> bit r of a[c].
 // Block-swap butterfly: the 16- and 8-bit stages are byte permutes (2 PRMT per pair), the 4/2/1-bit stages
 // a shift + LOP3 per output word.
-__device__ __forceinline__ void spec_transpose32(uint32_t (&a)[32]) {
+template <int J>
+__device__ __forceinline__ void spec_transpose_stage(uint32_t (&a)[32]) {
+    constexpr uint32_t m = J == 4 ? 0x0F0F0F0Fu : J == 2 ? 0x33333333u : 0x55555555u;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const uint32_t x = a[k], y = a[k + 16];
-        a[k] = __byte_perm(x, y, 0x5410);
-        a[k + 16] = __byte_perm(x, y, 0x7632);
-    }
+    for (int base = 0; base < 32; base += 2 * J) {
 #pragma unroll
-    for (int k = 0; k < 32; k = (k + 8 + 1) & ~8) {
-        const uint32_t x = a[k], y = a[k + 8];
-        a[k] = __byte_perm(x, y, 0x6240);
-        a[k + 8] = __byte_perm(x, y, 0x7351);
-    }
-#pragma unroll
-    for (int j = 4; j != 0; j >>= 1) {
-        const uint32_t m = j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
-#pragma unroll
-        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
-            const uint32_t x = a[k], y = a[k + j];
-            a[k] = (x & m) | ((y << j) & ~m);
-            a[k + j] = ((x >> j) & m) | (y & ~m);
+        for (int k = base; k < base + J; ++k) {               // constant indices: a[] stays in registers
+            const uint32_t x = a[k], y = a[k + J];
+            if (J == 16) {
+                a[k] = __byte_perm(x, y, 0x5410);
+                a[k + J] = __byte_perm(x, y, 0x7632);
+            } else if (J == 8) {
+                a[k] = __byte_perm(x, y, 0x6240);
+                a[k + J] = __byte_perm(x, y, 0x7351);
+            } else {
+                a[k] = (x & m) | ((y << J) & ~m);
+                a[k + J] = ((x >> J) & m) | (y & ~m);
+            }
         }
     }
+}
+__device__ __forceinline__ void spec_transpose32(uint32_t (&a)[32]) {
+    spec_transpose_stage<16>(a);
+    spec_transpose_stage<8>(a);
+    spec_transpose_stage<4>(a);
+    spec_transpose_stage<2>(a);
+    spec_transpose_stage<1>(a);
 }
 
 // index of the (k+1)-th set bit of x (k < popc(x)), branch-free binary search
@@ -79,22 +83,29 @@ __device__ __forceinline__ int spec_kth_bit(uint32_t x, uint32_t k) {
     return pos;
 }
 
-// A warp's shared-memory block holds 32 tile blocks of BW words (BW % 32 == 0), each padded by 4 words:
-// the coalesced fill / drain (consecutive lanes, consecutive 16-byte chunks) and every lane's 128-bit
-// accesses to its own tile block are both bank-conflict free. The fill is cp.async (global -> shared
-// without a register round trip): all of a warp's 16-byte chunks are in flight at once.
-template <int BW>
-__device__ __forceinline__ void spec_fill_async(uint32_t* buf, const uint32_t* __restrict__ src, int64_t rows_avail,
-                                                int row_words, int lane) {
-    const int64_t words_avail = rows_avail * row_words;
+// Staging. A lane's tile is 32 consecutive rows in HBM; a warp's 32 tiles are contiguous. Rows move
+// between HBM and the lanes in GROUPS of SPEC_GR rows per tile: the warp copies, for every tile, the
+// group's SPEC_GR * RW contiguous words with coalesced 16-byte cp.async / stores into a per-warp
+// shared-memory block [32 tiles][SPEC_GR * RW + 4 pad], and every lane then reads / writes its own
+// tile's rows there (128-bit accesses are bank-conflict free with the 4-word pad). Staging a quarter of
+// the rows at a time keeps the block at 12.8 KB per warp, so that eight warps fit on an SM.
+#define SPEC_GR 8
+#define SPEC_NG (32 / SPEC_GR)
+
+template <int RW>
+__device__ __forceinline__ void spec_fill_group(uint32_t* buf, const uint32_t* __restrict__ base, int h,
+                                                int64_t warp_rows, int lane) {
+    // base: first word of the warp's first row; group h covers rows [h*GR, h*GR+GR) of each tile
+    constexpr int GW = SPEC_GR * RW, CPT = GW / 4;             // words, 16-byte chunks per tile and group
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(buf);
-#pragma unroll 8
-    for (int q = lane; q < 32 * BW / 4; q += 32) {
-        const int w = q * 4;
-        const int t = w / BW, o = w - t * BW;
-        const uint32_t dst = sbase + (uint32_t)(t * (BW + 4) + o) * 4u;
-        const int bytes = (int64_t)w < words_avail ? 16 : 0;          // rows beyond the batch read as zero
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src + w), "r"(bytes) : "memory");
+#pragma unroll 4
+    for (int c = lane; c < 32 * CPT; c += 32) {
+        const int t = c / CPT, o = (c - t * CPT) * 4;
+        const int row = t * 32 + h * SPEC_GR + o / RW;
+        const uint32_t dst = sbase + (uint32_t)(t * (GW + 4) + o) * 4u;
+        const uint32_t* src = base + (int64_t)(t * 32 + h * SPEC_GR) * RW + o;
+        const int bytes = row < warp_rows ? 16 : 0;             // rows beyond the batch read as zero
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
@@ -103,17 +114,18 @@ __device__ __forceinline__ void spec_fill_wait() {
     __syncwarp();
 }
 
-template <int BW>
-__device__ __forceinline__ void spec_drain(const uint32_t* buf, uint32_t* __restrict__ dst, int64_t rows_avail,
-                                           int row_words, int lane) {
+template <int RW>
+__device__ __forceinline__ void spec_drain_group(const uint32_t* buf, uint32_t* __restrict__ base, int h,
+                                                 int64_t warp_rows, int lane) {
+    constexpr int GW = SPEC_GR * RW, CPT = GW / 4;
     __syncwarp();
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    const int64_t words_avail = rows_avail * row_words;
-#pragma unroll 8
-    for (int q = lane; q < 32 * BW / 4; q += 32) {
-        const int w = q * 4;
-        const int t = w / BW, o = w - t * BW;
-        if ((int64_t)w < words_avail) d4[q] = *reinterpret_cast<const uint4*>(buf + t * (BW + 4) + o);
+#pragma unroll 4
+    for (int c = lane; c < 32 * CPT; c += 32) {
+        const int t = c / CPT, o = (c - t * CPT) * 4;
+        const int row = t * 32 + h * SPEC_GR + o / RW;
+        if (row < warp_rows)
+            *reinterpret_cast<uint4*>(base + (int64_t)(t * 32 + h * SPEC_GR) * RW + o) =
+                *reinterpret_cast<const uint4*>(buf + t * (GW + 4) + o);
     }
     __syncwarp();
 }
@@ -127,25 +139,25 @@ __device__ __forceinline__ void spec_for(F&& f) {
     }
 }
 
-#define SPEC_WARPS 4
+#define SPEC_WARPS 8
 
 // G: the generated game description (csrc/gz_spec_<game>.cu), see tools/gen_spec_kernel.py.
 //
 // Code size matters here: the gate networks are straight-line by nature (a few thousand LOP3s that
 // every warp runs once per batch), so everything repetitive — the per-game move chooser, the word-by-word
 // transposes back to packed rows — is a real loop whose body stays in the instruction cache, and the
-// four warps of a CTA enter the straight-line sections together (__syncthreads) so that one fetch of a
+// warps of a CTA enter the straight-line sections together (__syncthreads) so that one fetch of a
 // line feeds all of them.
 template <typename G, int MODE>
 __global__ void __launch_bounds__(SPEC_WARPS * 32, 1) spec_kernel(const SpecArgs A) {
     extern __shared__ __align__(16) uint32_t spec_smem[];
-    constexpr int SW = G::SW, LW = G::LW, R = G::R, NBW = G::NBW;
-    constexpr int SBW = 32 * SW, LBW = 32 * LW;                  // words per tile block
-    constexpr int BUFW = 32 * ((LBW > SBW ? LBW : SBW) + 4);     // words per warp buffer
+    constexpr int SW = G::SW, LW = G::LW, R = G::R, NBW = G::NBW, LWU = G::LWU;
+    constexpr int SGW = SPEC_GR * SW, LGW = SPEC_GR * LW;        // words per tile and group
+    constexpr int BUFW = 32 * ((LGW > SGW ? LGW : SGW) + 4);     // words per warp buffer
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* buf = spec_smem + (size_t)warp * BUFW;
-    uint32_t* mine_s = buf + lane * (SBW + 4);                   // this lane's tile block (state rows)
-    uint32_t* mine_l = buf + lane * (LBW + 4);                   // ... (legal rows)
+    uint32_t* mine_s = buf + lane * (SGW + 4);                   // this lane's rows of the group (state)
+    uint32_t* mine_l = buf + lane * (LGW + 4);                   // ... (legal)
 
     const int64_t n = A.n;
     const int64_t n_batches = (n + 1023) >> 10;                  // a warp's unit: 32 tiles = 1024 games
@@ -154,7 +166,7 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 1) spec_kernel(const SpecArgs
     for (int64_t round = 0; round < rounds; ++round) {
         const int64_t batch = round * per_round + (int64_t)blockIdx.x * SPEC_WARPS + warp;
         const bool active = batch < n_batches;                   // idle warps still meet the barriers
-        const int64_t w0 = batch << 10;                          // first game of the warp
+        const int64_t w0 = active ? batch << 10 : 0;             // first game of the warp
         const int64_t g0 = w0 + ((int64_t)lane << 5);            // first game of this lane's tile
         const int64_t warp_rows = !active ? 0 : (n - w0 < 1024 ? n - w0 : 1024);
         int rows = !active ? 0 : (int)(n - g0 < 32 ? n - g0 : 32);
@@ -168,9 +180,8 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 1) spec_kernel(const SpecArgs
 #pragma unroll
             for (int k = 0; k < G::MVBITS; ++k) mv[r][k] = 0u;
 
-        if (MODE == SPEC_PLAYOUT && active) {
+        if (MODE == SPEC_PLAYOUT) {
             // ---- one uniformly random legal action per role and game, from the stored legal rows
-            spec_fill_async<LBW>(buf, A.legal + w0 * LW, warp_rows, LW, lane);
             if (rows == 32) {
                 const uint4* t4 = reinterpret_cast<const uint4*>(A.terminal + g0);
                 const uint4 ta = t4[0], tb2 = t4[1];
@@ -185,45 +196,50 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 1) spec_kernel(const SpecArgs
             } else {
                 for (int i = 0; i < rows; ++i) reset_mask |= (A.terminal[g0 + i] ? 1u : 0u) << i;
             }
-            spec_fill_wait();
+#pragma unroll 1
+            for (int h = 0; h < SPEC_NG; ++h) {
+                spec_fill_group<LW>(buf, A.legal + w0 * LW, h, warp_rows, lane);
+                spec_fill_wait();
 #pragma unroll 2
-            for (int i = 0; i < 32; ++i) {
-                const bool term = (reset_mask >> i) & 1u;
-                const bool valid = i < rows;
-                uint32_t lw[LW];
+                for (int ii = 0; ii < SPEC_GR; ++ii) {
+                    const int i = h * SPEC_GR + ii;
+                    const bool term = (reset_mask >> i) & 1u;
+                    const bool valid = i < rows;
+                    uint32_t lw[LW];
 #pragma unroll
-                for (int q = 0; q < LW / 4; ++q) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(mine_l + i * LW + q * 4);
-                    lw[q * 4] = v.x; lw[q * 4 + 1] = v.y; lw[q * 4 + 2] = v.z; lw[q * 4 + 3] = v.w;
-                }
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int wlo = G::lwo(r), whi = G::lwo(r + 1);
-                    uint32_t cnt = 0;
-#pragma unroll
-                    for (int j = wlo; j < whi; ++j) cnt += __popc(lw[j]);
-                    uint32_t pick = gz_pick(gz_rand32(A.seed, (uint64_t)(A.slot0 + g0 + i), A.step, (uint32_t)r), cnt);
-                    // the word holding the pick-th legal action, then its position inside the word
-                    uint32_t xsel = 0u;
-                    int base = 0;
-                    bool found = false;
-#pragma unroll
-                    for (int j = wlo; j < whi; ++j) {
-                        const uint32_t c = __popc(lw[j]);
-                        const bool here = !found && pick < c;
-                        if (here) { xsel = lw[j]; base = (j - wlo) * 32; }
-                        found = found || here;
-                        if (!found) pick -= c;
+                    for (int q = 0; q < LW / 4; ++q) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(mine_l + ii * LW + q * 4);
+                        lw[q * 4] = v.x; lw[q * 4 + 1] = v.y; lw[q * 4 + 2] = v.z; lw[q * 4 + 3] = v.w;
                     }
-                    int idx = found ? base + spec_kth_bit(xsel, pick) : 0;
-                    if (!valid || term) idx = 0;
-                    if (valid && A.moves_out) A.moves_out[(g0 + i) * R + r] = (int16_t)(term ? -1 : idx);
 #pragma unroll
-                    for (int k = 0; k < G::MVBITS; ++k) mv[r][k] |= ((uint32_t)(idx >> k) & 1u) << i;
+                    for (int r = 0; r < R; ++r) {
+                        const int wlo = G::lwo(r), whi = G::lwo(r + 1);
+                        uint32_t cnt = 0;
+#pragma unroll
+                        for (int j = wlo; j < whi; ++j) cnt += __popc(lw[j]);
+                        uint32_t pick = gz_pick(gz_rand32(A.seed, (uint64_t)(A.slot0 + g0 + i), A.step, (uint32_t)r), cnt);
+                        // the word holding the pick-th legal action, then its position inside the word
+                        uint32_t xsel = 0u;
+                        int base = 0;
+                        bool found = false;
+#pragma unroll
+                        for (int j = wlo; j < whi; ++j) {
+                            const uint32_t c = __popc(lw[j]);
+                            const bool here = !found && pick < c;
+                            if (here) { xsel = lw[j]; base = (j - wlo) * 32; }
+                            found = found || here;
+                            if (!found) pick -= c;
+                        }
+                        int idx = found ? base + spec_kth_bit(xsel, pick) : 0;
+                        if (!valid || term) idx = 0;
+                        if (valid && A.moves_out) A.moves_out[(g0 + i) * R + r] = (int16_t)(term ? -1 : idx);
+#pragma unroll
+                        for (int k = 0; k < G::MVBITS; ++k) mv[r][k] |= ((uint32_t)(idx >> k) & 1u) << i;
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
-        } else if (MODE == SPEC_TRANSITION && active) {
+        } else if (MODE == SPEC_TRANSITION) {
 #pragma unroll 1
             for (int i = 0; i < rows; ++i) {
 #pragma unroll
@@ -237,23 +253,36 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 1) spec_kernel(const SpecArgs
             }
         }
 
-        // ---- packed state rows -> bit-sliced bases in registers
+        // ---- packed state rows -> registers (row-major), then 32x32 transposes in place -> bit-sliced bases
         uint32_t b[NBW * 32];
-        if (active) spec_fill_async<SBW>(buf, A.states_in + w0 * SW, warp_rows, SW, lane);
-        spec_fill_wait();
-        __syncthreads();
+        spec_for<0, SPEC_NG>([&](auto H) {
+            constexpr int h = decltype(H)::value;
+            spec_fill_group<SW>(buf, A.states_in + w0 * SW, h, warp_rows, lane);
+            spec_fill_wait();
+#pragma unroll
+            for (int ii = 0; ii < SPEC_GR; ++ii) {
+#pragma unroll
+                for (int q = 0; q < (NBW + 3) / 4; ++q) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(mine_s + ii * SW + q * 4);
+                    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (q * 4 + e < NBW) b[(q * 4 + e) * 32 + h * SPEC_GR + ii] = vv[e];
+                }
+            }
+            __syncwarp();
+        });
         spec_for<0, NBW>([&](auto J) {
             constexpr int j = decltype(J)::value;
             uint32_t a[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) a[i] = mine_s[i * SW + j];
+            for (int i = 0; i < 32; ++i) a[i] = b[j * 32 + i];
             spec_transpose32(a);
 #pragma unroll
             for (int i = 0; i < 32; ++i) b[j * 32 + i] = a[i];
         });
-        __syncwarp();
 
-        uint32_t sl[(G::LWU > NBW ? G::LWU : NBW) * 32];        // bit-sliced outputs, indexed in loops (local memory)
+        uint32_t sl[(LWU > NBW ? LWU : NBW) * 32];              // bit-sliced outputs, indexed in loops (local memory)
 
         if (MODE != SPEC_EVAL) {
             // ---- next state: straight-line gate network per state word ...
@@ -277,9 +306,10 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 1) spec_kernel(const SpecArgs
                     sl[j * 32 + i] = t;
                 }
             });
-            // ... the new bases replace the old ones, and go back to packed rows word by word
+            // ... the new bases replace the old ones ...
 #pragma unroll
             for (int i = 0; i < NBW * 32; ++i) b[i] = sl[i];
+            // ... and go back to packed rows: transpose word by word in place, then drain group by group
 #pragma unroll 1
             for (int j = 0; j < NBW; ++j) {
                 uint32_t o[32];
@@ -287,18 +317,28 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 1) spec_kernel(const SpecArgs
                 for (int i = 0; i < 32; ++i) o[i] = sl[j * 32 + i];
                 spec_transpose32(o);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mine_s[i * SW + j] = o[i];
+                for (int i = 0; i < 32; ++i) sl[j * 32 + i] = o[i];
             }
+#pragma unroll 1
+            for (int h = 0; h < SPEC_NG; ++h) {
 #pragma unroll
-            for (int j = NBW; j < SW; ++j)
+                for (int ii = 0; ii < SPEC_GR; ++ii) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mine_s[i * SW + j] = 0u;
-            if (active) spec_drain<SBW>(buf, A.states_out + w0 * SW, warp_rows, SW, lane);
+                    for (int q = 0; q < SW / 4; ++q) {
+                        uint32_t vv[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            vv[e] = (q * 4 + e < NBW) ? sl[(q * 4 + e) * 32 + h * SPEC_GR + ii] : 0u;
+                        *reinterpret_cast<uint4*>(mine_s + ii * SW + q * 4) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+                    }
+                }
+                spec_drain_group<SW>(buf, A.states_out + w0 * SW, h, warp_rows, lane);
+            }
         }
 
         // ---- views of the (new) state: legal masks, terminal, goals
         __syncthreads();
-        spec_for<0, G::LWU>([&](auto J) {
+        spec_for<0, LWU>([&](auto J) {
             constexpr int j = decltype(J)::value;
             uint32_t o[32];
             G::template legal_word<j>(b, o);
@@ -312,19 +352,29 @@ __global__ void __launch_bounds__(SPEC_WARPS * 32, 1) spec_kernel(const SpecArgs
         for (int k = 0; k < (G::NGOAL > 0 ? G::NGOAL : 1); ++k) gw[k] = 0u;
         if (need_goals) G::goal_words(b, gw);
 #pragma unroll 1
-        for (int j = 0; j < G::LWU; ++j) {
+        for (int j = 0; j < LWU; ++j) {
             uint32_t o[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = sl[j * 32 + i];
             spec_transpose32(o);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mine_l[i * LW + j] = o[i];
+            for (int i = 0; i < 32; ++i) sl[j * 32 + i] = o[i];
         }
+#pragma unroll 1
+        for (int h = 0; h < SPEC_NG; ++h) {
 #pragma unroll
-        for (int j = G::LWU; j < LW; ++j)
+            for (int ii = 0; ii < SPEC_GR; ++ii) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mine_l[i * LW + j] = 0u;
-        if (active) spec_drain<LBW>(buf, A.legal + w0 * LW, warp_rows, LW, lane);
+                for (int q = 0; q < LW / 4; ++q) {
+                    uint32_t vv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        vv[e] = (q * 4 + e < LWU) ? sl[(q * 4 + e) * 32 + h * SPEC_GR + ii] : 0u;
+                    *reinterpret_cast<uint4*>(mine_l + ii * LW + q * 4) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+                }
+            }
+            spec_drain_group<LW>(buf, A.legal + w0 * LW, h, warp_rows, lane);
+        }
 
         if (rows == 32) {
             // 32 terminal bytes and 32 x R goal bytes per tile, written as 128-bit words
@@ -391,8 +441,8 @@ const GzSpecEntry* gz_spec_find(uint64_t hash);
 
 template <typename G>
 int gz_spec_launch_impl(int mode, const SpecArgs& a, int grid, cudaStream_t s) {
-    constexpr int SBW = 32 * G::SW, LBW = 32 * G::LW;
-    constexpr size_t smem = (size_t)SPEC_WARPS * 32 * ((LBW > SBW ? LBW : SBW) + 4) * 4;
+    constexpr int SGW = SPEC_GR * G::SW, LGW = SPEC_GR * G::LW;
+    constexpr size_t smem = (size_t)SPEC_WARPS * 32 * ((LGW > SGW ? LGW : SGW) + 4) * 4;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(spec_kernel<G, SPEC_EVAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
