@@ -122,6 +122,8 @@ def all_sum(x, world, device):
 
 
 # ------------------------------------------------------------------------------------------------
+PROPNET_SPEC_NCU_TRAFFIC_BYTES = 429494400     # 178.7 MB read + 250.8 MB written
+PROPNET_TABLE_NCU_TRAFFIC_BYTES = 284900000    # 170.0 MB read + 114.9 MB written
 PROPNET_GAME = 'breakthrough'
 PROPNET_SLOTS = 1 << 21          # per GPU; working set 166 MB > 126 MB L2
 
@@ -194,10 +196,17 @@ def run_propnet(args, rank, world, local):
     per_launch_bytes = tb * n
     launch_s = (ms * 1e-3) / args.steps
     achieved = per_launch_bytes / launch_s / 1e9
+    spec = dev.specialised and n >= (1 << 18)
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
-                'kernel': 'pn_kernel<MODE_PLAYOUT>', 'bytes_per_unit': tb,
-                'units_per_launch': n, 'peak_source': peaks['source']}
+                'frac': achieved / peaks['hbm_gbs'],
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^21 slots (ncu --set full)
+                'traffic': (PROPNET_SPEC_NCU_TRAFFIC_BYTES if spec else PROPNET_TABLE_NCU_TRAFFIC_BYTES) if n == PROPNET_SLOTS else None,
+                'kernel': 'spec_kernel<GzSpec_breakthrough, PLAYOUT> (game-specialised, thread-sliced)' if spec
+                          else 'pn_kernel<MODE_PLAYOUT> (table-driven)',
+                'bytes_per_unit': tb, 'units_per_launch': n, 'launch_ms': launch_s * 1e3,
+                'peak_source': peaks['source'] + ' (HBM copy)',
+                'traffic_source': 'profiles/r01b_propnet_spec_kernel_ncu_full.md' if spec
+                                  else 'profiles/r01_propnet_playout_ncu_full.md'}
 
     # ---- e2e: the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     e2e = None
