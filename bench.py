@@ -159,7 +159,8 @@ def run_propnet(args, rank, world, local):
     from galvanise_zero_b200 import lib as gzlib
 
     peaks = load_peaks()
-    dev = DeviceStateMachine(PROPNET_GAME, device=local, goals_mode=gzlib.GOALS_ALWAYS)
+    game = args.game or PROPNET_GAME
+    dev = DeviceStateMachine(game, device=local, goals_mode=gzlib.GOALS_ALWAYS)
     n = args.slots or PROPNET_SLOTS
     slot0 = rank * n
     s = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
@@ -200,9 +201,9 @@ def run_propnet(args, rank, world, local):
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                 'frac': achieved / peaks['hbm_gbs'],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^21 slots (ncu --set full)
-                'traffic': (PROPNET_SPEC_NCU_TRAFFIC_BYTES if spec else PROPNET_TABLE_NCU_TRAFFIC_BYTES) if n == PROPNET_SLOTS else None,
-                'kernel': 'spec_kernel<GzSpec_breakthrough, PLAYOUT> (game-specialised, thread-sliced)' if spec
-                          else 'pn_kernel<MODE_PLAYOUT> (table-driven)',
+                'traffic': (PROPNET_SPEC_NCU_TRAFFIC_BYTES if spec else PROPNET_TABLE_NCU_TRAFFIC_BYTES) if (n == PROPNET_SLOTS and game == PROPNET_GAME) else None,
+                'kernel': 'spec_kernel<GzSpec_%s, PLAYOUT> (game-specialised, thread-sliced)' % game if spec
+                          else ('pn_wide_kernel<MODE_PLAYOUT>' if dev.launch_info['smem_bytes'] == 0 else 'pn_kernel<MODE_PLAYOUT> (table-driven)'),
                 'bytes_per_unit': tb, 'units_per_launch': n, 'launch_ms': launch_s * 1e3,
                 'peak_source': peaks['source'] + ' (HBM copy)',
                 'traffic_source': 'profiles/r01b_propnet_spec_kernel_ncu_full.md' if spec
@@ -211,7 +212,7 @@ def run_propnet(args, rank, world, local):
     # ---- e2e: the host-buffer C-ABI call (pinned host memory, copies inside the timed region)
     e2e = None
     if rank == 0 or world > 1:
-        ne = min(n, 1 << 20)
+        ne = min(n, 1 << 20, max(1024, (256 << 20) // (dev.state_words * 8 + dev.legal_words * 4)))
         hs = torch.empty((ne, dev.state_words), dtype=torch.int32).pin_memory()
         hm = torch.empty((ne, dev.n_roles), dtype=torch.int16).pin_memory()
         hn = torch.empty((ne, dev.state_words), dtype=torch.int32).pin_memory()
@@ -247,9 +248,37 @@ def run_propnet(args, rank, world, local):
                'api': 'gz_sm_transition_host (DeviceStateMachine.transition_host), pinned host buffers',
                'units_per_step': ne}
 
+    # ---- the encoder on the same slots (encode GB/s on random-played positions)
+    encoder = None
+    try:
+        from galvanise_zero_b200 import bases, cppinterface, lookup
+        from galvanise_zero_b200.defs import datadesc
+        tr = bases.GdlBasesTransformer(lookup.by_name(game), datadesc.generation_for(game))
+        ct = cppinterface.create_c_transformer(tr, device=local)
+        ne = min(n, 1 << 19)
+        out = torch.empty((ne, ct.total_size()), dtype=torch.bfloat16, device=dev.device)
+        prev = s[:ne].clone().reshape(ne, 1, dev.state_words)
+        for _ in range(3):
+            ct.encode(s[:ne], prev, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            ct.encode(s[:ne], prev, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        enc_ms = e0.elapsed_time(e1) / 20
+        eb = 2 * ((dev.n_bases + 7) // 8) + 2 * ct.total_size()
+        ach = eb * ne / (enc_ms * 1e-3) / 1e9
+        encoder = {'kernel': 'encode_kernel<bf16>', 'positions_per_launch': ne, 'launch_ms': enc_ms,
+                   'bytes_per_unit': eb, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                   'frac': ach / peaks['hbm_gbs'], 'planes': [tr.num_channels, tr.num_cols, tr.num_rows]}
+    except Exception as exc:           # a game without a plane description
+        encoder = {'unavailable': str(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_propnet(PROPNET_GAME)
+        cpu = cpu_baseline_propnet(game)
 
     if rank == 0:
         line = {
@@ -257,13 +286,14 @@ def run_propnet(args, rank, world, local):
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
-            'config': {'workload': 'breakthrough 8x8 propnet, batched uniform-random playouts',
+            'config': {'workload': '%s propnet, batched uniform-random playouts' % (
+                           'breakthrough 8x8' if game == 'breakthrough' else game),
                        'slots_per_gpu': n, 'l2': 'working set %.0f MB per GPU > 126 MB L2' % (
                            n * (dev.state_words * 4 + dev.legal_words * 4 + 1 + dev.n_roles) / 1e6),
                        'parallelism': 'games sharded across %d GPU(s), no collective' % world,
                        'launch': dev.launch_info},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': args.steps,
-            'clocks': clocks,
+            'roofline': roofline, 'encoder_roofline': encoder, 'cpu_baseline': cpu, 'e2e': e2e,
+            'gpu_launches': args.steps, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)
 
@@ -639,6 +669,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-inline', action='store_true')
     ap.add_argument('--slots', type=int, default=0)
+    ap.add_argument('--game', default='', help='propnet workload: another compiled game (default breakthrough)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

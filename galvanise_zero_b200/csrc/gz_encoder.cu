@@ -104,6 +104,99 @@ encode_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint
     }
 }
 
+// Fast path (rows of a multiple of 8 elements — every shipped game but hexLG13 in NCHW): the per-element
+// decisions (which base bit, current or previous state, which control channel) do not depend on the
+// state, so a CTA resolves them ONCE into a descriptor table in shared memory and then streams states
+// through it: per 8 output elements one descriptor read each, a bit test on the state words staged in
+// shared memory, one 128-bit (bf16) or two 128-bit (f32) coalesced stores. No divisions per element.
+#define ENCF_STATES 32
+#define ENCF_THREADS 256
+// descriptor: kind in bits 30-31 (0 zero, 1 bit of the state, 2 bit of the OR of previous states,
+// 3 control channel), payload in bits 0-29 (base index / control channel)
+template <typename OutT>
+__global__ void __launch_bounds__(ENCF_THREADS)
+encode_fast_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint32_t* __restrict__ states,
+                   const uint32_t* __restrict__ prev, const uint8_t* __restrict__ prev_count, int max_prev,
+                   OutT* __restrict__ out, int c_pad, int row_elems) {
+    extern __shared__ __align__(16) uint32_t fsm[];
+    uint32_t* desc = fsm;                                       // [row_elems]
+    uint32_t* cur = desc + row_elems;                           // [ENCF_STATES][sw]
+    uint32_t* por = cur + ENCF_STATES * sw;                     // [ENCF_STATES][sw]
+    uint32_t* ctrl = por + ENCF_STATES * sw;                    // [ENCF_STATES][nc] output bit patterns
+    const int nc = E.num_control_channels;
+    const int n_ch = E.total / E.channel_size;
+    const bool has_prev = prev && E.num_prev_states > 0;
+    for (int le0 = threadIdx.x; le0 < row_elems; le0 += ENCF_THREADS) {
+        int le = le0;
+        uint32_t d = 0u;
+        bool live = true;
+        if (c_pad > 0) {
+            const int pos = le / c_pad, c = le - pos * c_pad;
+            live = c < n_ch;
+            le = c * E.channel_size + pos;
+        }
+        if (live) {
+            if (le < E.board_total) {
+                const int g = le / E.group_size;
+                const int b = E.src_base[le - g * E.group_size];
+                if (b >= 0 && g == 0) d = (1u << 30) | (uint32_t)b;
+                else if (b >= 0 && g == 1 && has_prev) d = (2u << 30) | (uint32_t)b;
+            } else {
+                d = (3u << 30) | (uint32_t)((le - E.board_total) / E.channel_size);
+            }
+        }
+        desc[le0] = d;
+    }
+    const int row_vecs = row_elems >> 3;
+    constexpr uint32_t ONE = sizeof(OutT) == 2 ? 0x3F80u : 0x3F800000u;
+    for (int64_t n0 = (int64_t)blockIdx.x * ENCF_STATES; n0 < n; n0 += (int64_t)gridDim.x * ENCF_STATES) {
+        const int nb = (int)((n - n0) < ENCF_STATES ? (n - n0) : ENCF_STATES);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * sw; i += ENCF_THREADS) {
+            const int s = i / sw, w = i - s * sw;
+            cur[i] = states[(n0 + s) * sw + w];
+            uint32_t p = 0;
+            if (has_prev) {
+                const int np = prev_count ? prev_count[n0 + s] : max_prev;
+                for (int k = 0; k < np && k < max_prev; ++k) p |= prev[((n0 + s) * max_prev + k) * sw + w];
+            }
+            por[i] = p;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * nc; i += ENCF_THREADS) {
+            const int s = i / nc, c = i - s * nc;
+            const float v = enc_control_value(E, cur + s * sw, c);
+            ctrl[i] = sizeof(OutT) == 2 ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)) : __float_as_uint(v);
+        }
+        __syncthreads();
+        const int items = nb * row_vecs;
+        for (int w = threadIdx.x; w < items; w += ENCF_THREADS) {
+            const int s = w / row_vecs, vi = w - s * row_vecs;
+            const uint32_t* cs = cur + s * sw;
+            const uint32_t* ps = por + s * sw;
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t d = desc[vi * 8 + k];
+                const uint32_t kind = d >> 30, pl = d & 0x3FFFFFFFu;
+                uint32_t x = 0u;
+                if (kind == 1u) x = ((cs[pl >> 5] >> (pl & 31)) & 1u) ? ONE : 0u;
+                else if (kind == 2u) x = ((ps[pl >> 5] >> (pl & 31)) & 1u) ? ONE : 0u;
+                else if (kind == 3u) x = ctrl[s * nc + pl];
+                v[k] = x;
+            }
+            OutT* dst = out + (n0 + s) * (int64_t)row_elems + vi * 8;
+            if (sizeof(OutT) == 2) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16),
+                                                            v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+            } else {
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 extern "C" int gz_transformer_create(int channel_size, int channels_per_state, int num_control_channels,
                                      int num_prev_states, int num_rewards, const int* policy_sizes,
@@ -231,6 +324,27 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
     if (c_pad != 0 && (c_pad < t->E.total / t->E.channel_size || (c_pad & 7))) { gz_set_error("c_pad must be a multiple of 8 and >= the channel count"); return GZ_ERR_ARG; }
     if ((((uintptr_t)d_out) & 15) != 0) { gz_set_error("plane buffer must be 16-byte aligned"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(t->device));
+    {
+        const int row_elems = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
+        const size_t fsmem = ((size_t)row_elems + (size_t)ENCF_STATES * (2 * state_words + t->num_control_channels)) * 4 + 16;
+        if ((row_elems & 7) == 0 && fsmem <= 200 * 1024 && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32)) {
+            const int64_t blocks = (n + ENCF_STATES - 1) / ENCF_STATES;
+            const int grid = (int)std::min<int64_t>(blocks, (int64_t)t->n_sms * 8);
+            if (out_dtype == GZ_DTYPE_BF16) {
+                if (fsmem > 48 * 1024)
+                    GZ_CUDA(cudaFuncSetAttribute(encode_fast_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                encode_fast_kernel<__nv_bfloat16><<<grid, ENCF_THREADS, fsmem, (cudaStream_t)stream>>>(
+                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (__nv_bfloat16*)d_out, c_pad, row_elems);
+            } else {
+                if (fsmem > 48 * 1024)
+                    GZ_CUDA(cudaFuncSetAttribute(encode_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                encode_fast_kernel<float><<<grid, ENCF_THREADS, fsmem, (cudaStream_t)stream>>>(
+                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (float*)d_out, c_pad, row_elems);
+            }
+            GZ_CUDA(cudaGetLastError());
+            return GZ_OK;
+        }
+    }
     const size_t smem = (size_t)ENC_STATES_PER_BLOCK * (2 * state_words * 4 + t->num_control_channels * 4) + 16;
     const int64_t blocks = (n + ENC_STATES_PER_BLOCK - 1) / ENC_STATES_PER_BLOCK;
     const int grid = (int)std::min<int64_t>(blocks, (int64_t)t->n_sms * 8);

@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -52,7 +53,8 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
 // (gzp_reply), copying sample records. Atomics are issued by lane 0 only.
 #define PUCT_CTL_WORDS ((int)((sizeof(GameCtl) + 3) / 4))
 __global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32, 8)
-puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_words) {
+puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_words, int* __restrict__ rr_list,
+                int* __restrict__ rr_count) {
     extern __shared__ __align__(16) uint32_t puct_smem[];
     // per warp: the game's controller record and playout path live in shared memory while the kernel
     // runs (they are read and written dozens of times per playout; through global memory every
@@ -78,6 +80,8 @@ puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_wo
     }
     gzp_step_pre(V, nn_fresh != 0);
     __syncwarp();
+    // games that just played a move ask for their tree to be re-rooted: hand their ids to the re-root kernel
+    if (lane == 0 && V.c->req == REQ_REROOT) rr_list[atomicAdd(rr_count, 1)] = g;
     if (cmem) {
         const int pl = V.c->path_len;
         for (int i = lane; i < pl; i += 32) { gpn[i] = V.pn[i]; gpc[i] = V.pc[i]; }
@@ -122,18 +126,22 @@ struct GzpCta {
 };
 
 __global__ void __launch_bounds__(REROOT_THREADS)
-puct_reroot_kernel(const __grid_constant__ PuctEngine E) {
+puct_reroot_kernel(const __grid_constant__ PuctEngine E, const int* __restrict__ rr_list,
+                   const int* __restrict__ rr_count) {
     __shared__ int scan_sm[2 * (REROOT_THREADS / 32)];
-    const int g = blockIdx.x;
-    GameCtl& c = E.ctl[g];
-    if (c.req != REQ_REROOT) return;
-    GameView V = gzp_view(&E, g);
-    GzpCta grp;
-    grp.sm = scan_sm;
-    const int new_root = c.req_parent;
-    __syncthreads();
-    gzp_reroot_compact(V, new_root, (int)threadIdx.x, (int)blockDim.x, grp);
-    if (threadIdx.x == 0) c.req = REQ_NONE;
+    const int n = *rr_count;                       // a handful per step: one CTA each
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int g = rr_list[k];
+        GameCtl& c = E.ctl[g];
+        GameView V = gzp_view(&E, g);
+        GzpCta grp;
+        grp.sm = scan_sm;
+        const int new_root = c.req_parent;
+        __syncthreads();
+        gzp_reroot_compact(V, new_root, (int)threadIdx.x, (int)blockDim.x, grp);
+        __syncthreads();
+        if (threadIdx.x == 0) c.req = REQ_NONE;
+    }
 }
 
 __global__ void puct_init_kernel(const __grid_constant__ PuctEngine E, int mode) {
@@ -235,6 +243,8 @@ struct gz_puct {
     int cache_words = 0;      // per-warp shared-memory words for the child cache (0: use the global scratch)
     int plane_c_pad = 0;      // 0: planes are NCHW rows; >0: channels-last rows padded to this channel count
     uint32_t* d_pn_scratch = nullptr;   // wide games: this engine's propnet value-array scratch
+    int* d_rr_list = nullptr;           // ids of the games that asked for a re-root this step, and their count
+    int* d_rr_count = nullptr;
 
     struct HostPoll* hp = nullptr;   // host-buffer poll state (gz_puct_host_poll_*), created on first use
 };
@@ -353,6 +363,9 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
         GZ_CUDA(cudaMemcpy((void*)E.uniq_mask, mask.data(), E.SW * 4, cudaMemcpyHostToDevice));
     }
     GZ_CUDA(cudaMalloc(&h->d_totals, sizeof(PuctTotals)));
+    GZ_CUDA(cudaMalloc((void**)&h->d_rr_list, (size_t)E.G * 4));
+    GZ_CUDA(cudaMalloc((void**)&h->d_rr_count, 64));
+    GZ_CUDA(cudaMemset(h->d_rr_count, 0, 64));
     if (gz_propnet_wide_scratch_bytes(pn) > 0) {
         GZ_CUDA(cudaMalloc((void**)&h->d_pn_scratch, (size_t)gz_propnet_wide_scratch_bytes(pn)));
         GZ_CUDA(cudaMemset(h->d_pn_scratch, 0, (size_t)gz_propnet_wide_scratch_bytes(pn)));
@@ -382,6 +395,8 @@ extern "C" void gz_puct_destroy(gz_puct* h) {
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->d_totals) cudaFree(h->d_totals);
     if (h->d_pn_scratch) cudaFree(h->d_pn_scratch);
+    if (h->d_rr_list) cudaFree(h->d_rr_list);
+    if (h->d_rr_count) cudaFree(h->d_rr_count);
     if (h->d_role_sizes_off) cudaFree(h->d_role_sizes_off);
     if (h->hp) {
         HostPoll* q = h->hp;
@@ -430,12 +445,13 @@ static int advance_impl(gz_puct* h, const float* d_policy, const float* d_value,
     const int blocks = (E.G + PUCT_WARPS_PER_BLOCK - 1) / PUCT_WARPS_PER_BLOCK;
     if (evs) GZ_CUDA(cudaEventRecord(evs[0], s));
     for (int it = 0; it < sub_iters; it++) {
+        GZ_CUDA(cudaMemsetAsync(h->d_rr_count, 0, 4, s));
         puct_pre_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32,
                           h->cache_words ? ((size_t)h->cache_words + 2 * (size_t)E.MAXD) * 4 * PUCT_WARPS_PER_BLOCK : 0, s>>>(
-            E, (it == 0 && nn_fresh) ? 1 : 0, h->cache_words);
+            E, (it == 0 && nn_fresh) ? 1 : 0, h->cache_words, h->d_rr_list, h->d_rr_count);
         GZ_CUDA(cudaGetLastError());
         if (evs) GZ_CUDA(cudaEventRecord(evs[1], s));
-        puct_reroot_kernel<<<E.G, REROOT_THREADS, 0, s>>>(E);
+        puct_reroot_kernel<<<std::min(E.G, 148), REROOT_THREADS, 0, s>>>(E, h->d_rr_list, h->d_rr_count);
         GZ_CUDA(cudaGetLastError());
         if (evs) GZ_CUDA(cudaEventRecord(evs[2], s));
         int rc = gz_sm_transition_scratch(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
