@@ -245,6 +245,10 @@ struct gz_puct {
     uint32_t* d_pn_scratch = nullptr;   // wide games: this engine's propnet value-array scratch
     int* d_rr_list = nullptr;           // ids of the games that asked for a re-root this step, and their count
     int* d_rr_count = nullptr;
+    // re-rooting runs on a side stream, concurrently with the propnet pass, node creation and encoding
+    // of the same step (the games that re-root take no part in those); joined before the step ends
+    cudaStream_t rr_stream = nullptr;
+    cudaEvent_t rr_fork = nullptr, rr_join = nullptr;
 
     struct HostPoll* hp = nullptr;   // host-buffer poll state (gz_puct_host_poll_*), created on first use
 };
@@ -363,6 +367,9 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
         GZ_CUDA(cudaMemcpy((void*)E.uniq_mask, mask.data(), E.SW * 4, cudaMemcpyHostToDevice));
     }
     GZ_CUDA(cudaMalloc(&h->d_totals, sizeof(PuctTotals)));
+    GZ_CUDA(cudaStreamCreateWithFlags(&h->rr_stream, cudaStreamNonBlocking));
+    GZ_CUDA(cudaEventCreateWithFlags(&h->rr_fork, cudaEventDisableTiming));
+    GZ_CUDA(cudaEventCreateWithFlags(&h->rr_join, cudaEventDisableTiming));
     GZ_CUDA(cudaMalloc((void**)&h->d_rr_list, (size_t)E.G * 4));
     GZ_CUDA(cudaMalloc((void**)&h->d_rr_count, 64));
     GZ_CUDA(cudaMemset(h->d_rr_count, 0, 64));
@@ -397,6 +404,9 @@ extern "C" void gz_puct_destroy(gz_puct* h) {
     if (h->d_pn_scratch) cudaFree(h->d_pn_scratch);
     if (h->d_rr_list) cudaFree(h->d_rr_list);
     if (h->d_rr_count) cudaFree(h->d_rr_count);
+    if (h->rr_fork) cudaEventDestroy(h->rr_fork);
+    if (h->rr_join) cudaEventDestroy(h->rr_join);
+    if (h->rr_stream) cudaStreamDestroy(h->rr_stream);
     if (h->d_role_sizes_off) cudaFree(h->d_role_sizes_off);
     if (h->hp) {
         HostPoll* q = h->hp;
@@ -451,8 +461,17 @@ static int advance_impl(gz_puct* h, const float* d_policy, const float* d_value,
             E, (it == 0 && nn_fresh) ? 1 : 0, h->cache_words, h->d_rr_list, h->d_rr_count);
         GZ_CUDA(cudaGetLastError());
         if (evs) GZ_CUDA(cudaEventRecord(evs[1], s));
-        puct_reroot_kernel<<<std::min(E.G, 148), REROOT_THREADS, 0, s>>>(E, h->d_rr_list, h->d_rr_count);
-        GZ_CUDA(cudaGetLastError());
+        const bool fork = (evs == nullptr) && (it + 1 == sub_iters);
+        if (fork) {
+            GZ_CUDA(cudaEventRecord(h->rr_fork, s));
+            GZ_CUDA(cudaStreamWaitEvent(h->rr_stream, h->rr_fork, 0));
+            puct_reroot_kernel<<<std::min(E.G, 148), REROOT_THREADS, 0, h->rr_stream>>>(E, h->d_rr_list, h->d_rr_count);
+            GZ_CUDA(cudaGetLastError());
+            GZ_CUDA(cudaEventRecord(h->rr_join, h->rr_stream));
+        } else {
+            puct_reroot_kernel<<<std::min(E.G, 148), REROOT_THREADS, 0, s>>>(E, h->d_rr_list, h->d_rr_count);
+            GZ_CUDA(cudaGetLastError());
+        }
         if (evs) GZ_CUDA(cudaEventRecord(evs[2], s));
         int rc = gz_sm_transition_scratch(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
                                           GZ_GOALS_TERMINAL_ONLY, stream, h->d_pn_scratch);
@@ -469,6 +488,7 @@ static int advance_impl(gz_puct* h, const float* d_policy, const float* d_value,
                                   h->plane_c_pad, stream);
         if (rc != GZ_OK) return rc;
     }
+    if (!evs) GZ_CUDA(cudaStreamWaitEvent(s, h->rr_join, 0));      // join the re-root of this step
     if (evs) GZ_CUDA(cudaEventRecord(evs[5], s));
     return GZ_OK;
 }
