@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/gz_b200.h"
@@ -365,3 +366,51 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
     GZ_CUDA(cudaGetLastError());
     return GZ_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Board symmetries of packed states (src/ggpzero/util/symmetry.py translate_basestate, batched):
+// out bit j of every state = in bit src[j] — one bit-permutation shared by the whole batch. A CTA
+// stages 32 states in shared memory; a thread assembles one output word from 32 gathered bits.
+#define PERM_STATES 32
+__global__ void __launch_bounds__(256)
+permute_state_bits_kernel(int64_t n, int sw, int n_bases, const uint32_t* __restrict__ states,
+                          const int* __restrict__ src, uint32_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t psm[];
+    for (int64_t n0 = (int64_t)blockIdx.x * PERM_STATES; n0 < n; n0 += (int64_t)gridDim.x * PERM_STATES) {
+        const int nb = (int)((n - n0) < PERM_STATES ? (n - n0) : PERM_STATES);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * sw; i += blockDim.x) psm[i] = states[n0 * sw + i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * sw; i += blockDim.x) {
+            const int s = i / sw, w = i - s * sw;
+            const uint32_t* row = psm + s * sw;
+            uint32_t v = 0u;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const int j = w * 32 + k;
+                if (j < n_bases) {
+                    const int b = __ldg(src + j);
+                    v |= ((row[b >> 5] >> (b & 31)) & 1u) << k;
+                }
+            }
+            out[n0 * sw + i] = v;
+        }
+    }
+}
+
+extern "C" int gz_permute_state_bits(int64_t n, int state_words, int n_bases, const uint32_t* d_states,
+                                     const int* d_src, uint32_t* d_out, void* stream) {
+    if (n < 0 || state_words <= 0 || n_bases <= 0 || n_bases > state_words * 32) { gz_set_error("bad shape"); return GZ_ERR_ARG; }
+    if (n == 0) return GZ_OK;
+    if (!d_states || !d_src || !d_out || d_states == d_out) { gz_set_error("null or aliased device pointer"); return GZ_ERR_ARG; }
+    const size_t smem = (size_t)PERM_STATES * state_words * 4;
+    if (smem > 200 * 1024) { gz_set_error("state rows too large for the staging block"); return GZ_ERR_LIMIT; }
+    if (smem > 48 * 1024)
+        GZ_CUDA(cudaFuncSetAttribute(permute_state_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (n + PERM_STATES - 1) / PERM_STATES;
+    permute_state_bits_kernel<<<(int)std::min<int64_t>(blocks, 148 * 8), 256, smem, (cudaStream_t)stream>>>(
+        n, state_words, n_bases, d_states, d_src, d_out);
+    GZ_CUDA(cudaGetLastError());
+    return GZ_OK;
+}
+

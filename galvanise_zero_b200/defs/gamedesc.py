@@ -124,3 +124,66 @@ class Games(object):
                                             BoardTerm(4, ["king", "rook", "pawn", "knight",
                                                           "queen", "bishop"])])
         return GameDesc("chess_15d", _letters(8), _nums(8), [cell], controls)
+
+
+# ---- symmetry descriptions (src/ggpzero/defs/gamedesc.py:78-110,497-593)
+@attr.s
+class ApplySymmetry(object):
+    base_term = attr.ib(default="cell")
+    x_terms_idx = attr.ib(default=attr.Factory(list))     # index/indices of the terms holding x / y coordinates
+    y_terms_idx = attr.ib(default=attr.Factory(list))
+
+
+@attr.s
+class Symmetries(object):
+    apply_bases = attr.ib(default=attr.Factory(list))
+    skip_bases = attr.ib(default=attr.Factory(list))
+    apply_actions = attr.ib(default=attr.Factory(list))
+    skip_actions = attr.ib(default=attr.Factory(list))
+    do_rotations_90 = attr.ib(default=False)
+    do_rotations_180 = attr.ib(default=False)
+    do_reflection = attr.ib(default=False)
+
+
+class GameSymmetries(object):
+    """Namespace: one method per game name (the games compiled here)."""
+
+    def breakthroughSmall(self):
+        return Symmetries(skip_bases=["control"], apply_bases=[ApplySymmetry("cell", 1, 2)],
+                          skip_actions=["noop"], apply_actions=[ApplySymmetry("move", [1, 3], [2, 4])],
+                          do_reflection=True)
+
+    def breakthrough(self):
+        return Symmetries(skip_bases=["control"], apply_bases=[ApplySymmetry("cellHolds", 1, 2)],
+                          skip_actions=["noop"], apply_actions=[ApplySymmetry("move", [1, 3], [2, 4])],
+                          do_reflection=True)
+
+    def reversi(self):
+        return Symmetries(skip_bases=["control"], apply_bases=[ApplySymmetry("cell", 1, 2)],
+                          skip_actions=["noop"], apply_actions=[ApplySymmetry("move", 1, 2)],
+                          do_rotations_90=True, do_reflection=True)
+
+    def connect6(self):
+        return Symmetries(skip_bases=["control"], apply_bases=[ApplySymmetry("cell", 1, 2)],
+                          skip_actions=["noop"], apply_actions=[ApplySymmetry("place", 1, 2)],
+                          do_rotations_90=True, do_reflection=True)
+
+    def _hex(self):
+        return Symmetries(skip_bases=["control", "step", "owner", "canSwap"],
+                          apply_bases=[ApplySymmetry("cell", 1, 2), ApplySymmetry("connected", 2, 3)],
+                          skip_actions=["noop", "swap"], apply_actions=[ApplySymmetry("place", 1, 2)],
+                          do_rotations_180=True)
+    hexLG11 = _hex
+    hexLG13 = _hex
+
+    def amazons_10x10(self):
+        return Symmetries(skip_bases=["turn"],
+                          apply_bases=[ApplySymmetry("cell", 1, 2), ApplySymmetry("justMoved", 1, 2)],
+                          skip_actions=["noop"],
+                          apply_actions=[ApplySymmetry("move", [1, 3], [2, 4]), ApplySymmetry("fire", 1, 2)],
+                          do_rotations_90=True, do_reflection=True)
+
+
+def get_symmetries_desc(game):
+    fn = getattr(GameSymmetries(), game, None)
+    return fn() if fn else None

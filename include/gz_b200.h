@@ -128,6 +128,12 @@ int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32
                      const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
                      int out_dtype, int c_pad, void* stream);
 
+/* Board symmetry of packed states, batched (src/ggpzero/util/symmetry.py:153-204 translate_basestate): bit j of
+ * every output state = bit d_src[j] of the input state (d_src: int32 [n_bases], a permutation; padding bits
+ * come out zero). d_out must not alias d_states. */
+int gz_permute_state_bits(int64_t n, int state_words, int n_bases, const uint32_t* d_states, const int* d_src,
+                          uint32_t* d_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Batched PUCT self-play engine. Replaces the reference's Supervisor / SelfPlayManager / SelfPlay /
  * NetworkScheduler / PuctEvaluator stack for `n_games` concurrent games:
