@@ -20,7 +20,7 @@ from oracle.gdl_interp import GdlInterpreter, to_str  # noqa: E402
 
 RULES = '/root/reference/data/rulesheets'
 DEFAULT = ['breakthrough:4:400', 'reversi:3:100', 'connect6:2:60', 'amazons_10x10:2:120',
-           'breakthroughSmall:4:200', 'chess_15d:1:30', 'hexLG13:1:45']
+           'breakthroughSmall:4:200', 'chess_15d:2:70', 'hexLG13:1:45']
 
 
 def make(game, n_games, max_plies, seed=20260118):
