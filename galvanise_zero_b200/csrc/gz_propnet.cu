@@ -58,6 +58,9 @@ struct PnParams {
 };
 
 enum { MODE_EVAL = 0, MODE_TRANSITION = 1, MODE_PLAYOUT = 2 };
+// internal goals mode: the goal cone is never evaluated (goals = 255); the PUCT engine evaluates it off
+// the critical path, in a compacted pass over the terminal states only (gz_sm_eval_devcount)
+#define GZ_GOALS_NEVER_INTERNAL 2
 
 // lane i holds row i of a 32x32 bit matrix; returns column i (bit j of result = bit i of row j).
 __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
@@ -146,8 +149,10 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
           const uint32_t* states_in, const int16_t* __restrict__ moves_in,
           uint32_t* states_out, uint32_t* legal,
           uint8_t* terminal, uint8_t* __restrict__ goals, int16_t* __restrict__ moves_out,
-          unsigned long long* __restrict__ transitions, uint64_t seed, uint64_t step, int goals_mode) {
+          unsigned long long* __restrict__ transitions, uint64_t seed, uint64_t step, int goals_mode,
+          const int* __restrict__ n_dev) {
     extern __shared__ __align__(16) uint32_t smem[];
+    if (n_dev) n = (int64_t)*n_dev;      // batch size decided on the device (compacted sub-batches)
 
     // ---- stage gate programs in shared memory (those the host decided fit)
     const uint32_t* prog[3];
@@ -280,7 +285,7 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
         // ---- views of the (new) state: legal masks, terminal, goals
         run_program<WPT>(prog[1], P.chunks[1], val, lane, wt);
         const uint32_t tw = lit_word(val, (uint32_t)P.terminal_lit) & valid_mask;
-        const bool need_goals = (goals_mode == GZ_GOALS_ALWAYS) || (tw != 0u);
+        const bool need_goals = (goals_mode == GZ_GOALS_ALWAYS) || (goals_mode == GZ_GOALS_TERMINAL_ONLY && tw != 0u);
         if (need_goals) run_program<WPT>(prog[2], P.chunks[2], val, lane, wt);
 
         if (io) {
@@ -349,8 +354,10 @@ pn_wide_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
                const uint32_t* states_in, const int16_t* __restrict__ moves_in,
                uint32_t* states_out, uint32_t* legal, uint8_t* terminal, uint8_t* __restrict__ goals,
                int16_t* __restrict__ moves_out, unsigned long long* __restrict__ transitions,
-               uint64_t seed, uint64_t step, int goals_mode, uint32_t* scratch, int64_t scratch_stride) {
+               uint64_t seed, uint64_t step, int goals_mode, uint32_t* scratch, int64_t scratch_stride,
+               const int* __restrict__ n_dev) {
     __shared__ int mv_sm[32][GZ_PN_MAX_ROLES];
+    if (n_dev) n = (int64_t)*n_dev;
     __shared__ uint32_t masks_sm[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* val = scratch + (int64_t)blockIdx.x * scratch_stride;
@@ -451,7 +458,7 @@ pn_wide_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
         run_program_wide(P.prog[1], P.chunks[1], val, lane, warp);
         __syncthreads();
         const uint32_t tw = wlit(val, (uint32_t)P.terminal_lit) & valid_mask;
-        const bool need_goals = (goals_mode == GZ_GOALS_ALWAYS) || (tw != 0u);
+        const bool need_goals = (goals_mode == GZ_GOALS_ALWAYS) || (goals_mode == GZ_GOALS_TERMINAL_ONLY && tw != 0u);
         if (need_goals) { run_program_wide(P.prog[2], P.chunks[2], val, lane, warp); __syncthreads(); }
 
         for (int j = warp; j < LW; j += WIDE_WARPS) {
@@ -740,7 +747,7 @@ template <int MODE>
 static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* states_in, const int16_t* moves_in,
                   uint32_t* states_out, uint32_t* legal, uint8_t* terminal, uint8_t* goals,
                   int16_t* moves_out, unsigned long long* transitions, uint64_t seed, uint64_t step,
-                  int goals_mode, void* stream, uint32_t* own_scratch = nullptr) {
+                  int goals_mode, void* stream, uint32_t* own_scratch = nullptr, const int* n_dev = nullptr) {
     if (!pn) { gz_set_error("null propnet"); return GZ_ERR_ARG; }
     if (n < 0) { gz_set_error("negative batch"); return GZ_ERR_ARG; }
     if (n == 0) return GZ_OK;
@@ -753,14 +760,14 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
         gz_set_error("state / legal arrays must be 16-byte aligned");
         return GZ_ERR_ARG;
     }
-    if (goals_mode != GZ_GOALS_ALWAYS && goals_mode != GZ_GOALS_TERMINAL_ONLY) {
+    if (goals_mode != GZ_GOALS_ALWAYS && goals_mode != GZ_GOALS_TERMINAL_ONLY && goals_mode != GZ_GOALS_NEVER_INTERNAL) {
         gz_set_error("bad goals_mode");
         return GZ_ERR_ARG;
     }
     GZ_CUDA(cudaSetDevice(pn->device));
     const int64_t n_tiles = (n + 31) / 32;
     cudaStream_t st = (cudaStream_t)stream;
-    if (pn->spec && pn->spec_min_batch >= 0 && n >= pn->spec_min_batch) {
+    if (pn->spec && pn->spec_min_batch >= 0 && n >= pn->spec_min_batch && !n_dev && goals_mode != GZ_GOALS_NEVER_INTERNAL) {
         // large batch of a game with a specialised kernel: one thread per 32-game tile
         SpecArgs a;
         a.n = n; a.slot0 = slot0; a.states_in = states_in; a.moves_in = moves_in; a.states_out = states_out;
@@ -791,7 +798,7 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
         const int grid = (int)std::min<int64_t>(n_tiles, pn->wide_grid);
         pn_wide_kernel<MODE><<<grid, WIDE_WARPS * 32, 0, st>>>(pn->P, n, slot0, states_in, moves_in, states_out, legal,
                                                             terminal, goals, moves_out, transitions, seed, step,
-                                                            goals_mode, scratch, pn->wide_stride);
+                                                            goals_mode, scratch, pn->wide_stride, n_dev);
         GZ_CUDA(cudaGetLastError());
         return GZ_OK;
     }
@@ -806,10 +813,10 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
         const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)pn->grid_max * 8);
         if (wpt == 8)
             pn_kernel<MODE, 8><<<grid, 8 * 32, smem, st>>>(pn->P, n, slot0, states_in, moves_in, states_out, legal,
-                                                          terminal, goals, moves_out, transitions, seed, step, goals_mode);
+                                                          terminal, goals, moves_out, transitions, seed, step, goals_mode, n_dev);
         else
             pn_kernel<MODE, 4><<<grid, 4 * 32, smem, st>>>(pn->P, n, slot0, states_in, moves_in, states_out, legal,
-                                                          terminal, goals, moves_out, transitions, seed, step, goals_mode);
+                                                          terminal, goals, moves_out, transitions, seed, step, goals_mode, n_dev);
     } else {
         // one persistent CTA per SM; medium batches shrink the CTA so that tiles spread over all SMs
         const int block_warps = (int)std::max<int64_t>(
@@ -818,7 +825,7 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
         const size_t smem = (size_t)pn->P.staged_words * 4 + (size_t)block_warps * pn->P.warp_words * 4;
         pn_kernel<MODE, 1><<<grid2, block_warps * 32, smem, st>>>(
             pn->P, n, slot0, states_in, moves_in, states_out, legal, terminal, goals, moves_out, transitions,
-            seed, step, goals_mode);
+            seed, step, goals_mode, n_dev);
     }
     GZ_CUDA(cudaGetLastError());
     return GZ_OK;
@@ -849,6 +856,15 @@ extern "C" int gz_sm_transition_scratch(gz_propnet* pn, int64_t n, const uint32_
     return launch<MODE_TRANSITION>(pn, n, 0, d_states, d_moves, d_next, d_legal, d_terminal, d_goals,
                                    nullptr, nullptr, 0, 0, goals_mode, stream, d_scratch);
 }
+
+// Internal: evaluate the first *d_n (<= n_max) states; the count stays on the device.
+extern "C" int gz_sm_eval_devcount(gz_propnet* pn, int64_t n_max, const int* d_n, const uint32_t* d_states,
+                                   uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals, int goals_mode,
+                                   void* stream, uint32_t* d_scratch) {
+    return launch<MODE_EVAL>(pn, n_max, 0, d_states, nullptr, nullptr, d_legal, d_terminal, d_goals, nullptr,
+                             nullptr, 0, 0, goals_mode, stream, d_scratch, d_n);
+}
+extern "C" int gz_propnet_goal_chunks(const gz_propnet* pn) { return pn ? pn->P.chunks[2] : 0; }
 
 extern "C" int gz_sm_playout_step(gz_propnet* pn, int64_t slot0, int64_t n, uint64_t seed, uint64_t step,
                                   uint32_t* d_states, uint32_t* d_legal, uint8_t* d_terminal,

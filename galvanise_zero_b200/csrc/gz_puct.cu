@@ -37,6 +37,11 @@
 
 extern "C" const uint32_t* gz_propnet_init_words(const gz_propnet* pn);   // gz_propnet.cu (device pointer)
 extern "C" int64_t gz_propnet_wide_scratch_bytes(const gz_propnet* pn);
+extern "C" int gz_propnet_goal_chunks(const gz_propnet* pn);
+extern "C" int gz_sm_eval_devcount(gz_propnet* pn, int64_t n_max, const int* d_n, const uint32_t* d_states,
+                                   uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals, int goals_mode,
+                                   void* stream, uint32_t* d_scratch);
+#define GZ_GOALS_NEVER_INTERNAL 2
 
 extern "C" int gz_sm_transition_scratch(gz_propnet* pn, int64_t n, const uint32_t* d_states, const int16_t* d_moves,
                                         uint32_t* d_next, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,
@@ -90,9 +95,10 @@ puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_wo
 }
 
 __global__ void __launch_bounds__(PUCT_WARPS_PER_BLOCK * 32)
-puct_post_kernel(const __grid_constant__ PuctEngine E) {
+puct_post_kernel(const __grid_constant__ PuctEngine E, int which /* 0 all, 1 non-terminal states, 2 terminal states */) {
     const int g = blockIdx.x * PUCT_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (g >= E.G || (threadIdx.x & 31) != 0) return;
+    if (which != 0 && (E.x_term[g] != 0) != (which == 2)) return;
     GameView V = gzp_view(&E, g);
     gzp_step_post(V);
 }
@@ -248,7 +254,15 @@ struct gz_puct {
     // re-rooting runs on a side stream, concurrently with the propnet pass, node creation and encoding
     // of the same step (the games that re-root take no part in those); joined before the step ends
     cudaStream_t rr_stream = nullptr;
-    cudaEvent_t rr_fork = nullptr, rr_join = nullptr;
+    cudaEvent_t rr_fork = nullptr, rr_join = nullptr, gl_fork = nullptr;
+    // games with a deep goal cone (reversi's piece counting: 596 chunks against 199 for everything else):
+    // the main pass skips it; the terminal states are compacted and evaluated on the side stream, followed
+    // by the creation of their (terminal) nodes — nothing on the way to the network needs them
+    bool split_goals = false;
+    bool side_pending = false;       // side-stream work of the last step has not been joined yet
+    int *t_idx = nullptr, *t_count = nullptr;
+    uint32_t *t_states = nullptr, *t_legal = nullptr;
+    uint8_t *t_term = nullptr, *t_goals = nullptr;
 
     struct HostPoll* hp = nullptr;   // host-buffer poll state (gz_puct_host_poll_*), created on first use
 };
@@ -370,6 +384,17 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     GZ_CUDA(cudaStreamCreateWithFlags(&h->rr_stream, cudaStreamNonBlocking));
     GZ_CUDA(cudaEventCreateWithFlags(&h->rr_fork, cudaEventDisableTiming));
     GZ_CUDA(cudaEventCreateWithFlags(&h->rr_join, cudaEventDisableTiming));
+    GZ_CUDA(cudaEventCreateWithFlags(&h->gl_fork, cudaEventDisableTiming));
+    if (gz_propnet_goal_chunks(pn) >= 64) {
+        h->split_goals = true;
+        GZ_CUDA(cudaMalloc((void**)&h->t_idx, (size_t)E.G * 4));
+        GZ_CUDA(cudaMalloc((void**)&h->t_count, 64));
+        GZ_CUDA(cudaMalloc((void**)&h->t_states, (size_t)E.G * E.SW * 4));
+        GZ_CUDA(cudaMalloc((void**)&h->t_legal, (size_t)E.G * E.LW * 4));
+        GZ_CUDA(cudaMalloc((void**)&h->t_term, (size_t)E.G));
+        GZ_CUDA(cudaMalloc((void**)&h->t_goals, (size_t)E.G * E.R));
+        GZ_CUDA(cudaMemset(h->t_count, 0, 64));
+    }
     GZ_CUDA(cudaMalloc((void**)&h->d_rr_list, (size_t)E.G * 4));
     GZ_CUDA(cudaMalloc((void**)&h->d_rr_count, 64));
     GZ_CUDA(cudaMemset(h->d_rr_count, 0, 64));
@@ -406,6 +431,9 @@ extern "C" void gz_puct_destroy(gz_puct* h) {
     if (h->d_rr_count) cudaFree(h->d_rr_count);
     if (h->rr_fork) cudaEventDestroy(h->rr_fork);
     if (h->rr_join) cudaEventDestroy(h->rr_join);
+    if (h->gl_fork) cudaEventDestroy(h->gl_fork);
+    { void* tv[] = {h->t_idx, h->t_count, h->t_states, h->t_legal, h->t_term, h->t_goals};
+      for (void* d : tv) if (d) cudaFree(d); }
     if (h->rr_stream) cudaStreamDestroy(h->rr_stream);
     if (h->d_role_sizes_off) cudaFree(h->d_role_sizes_off);
     if (h->hp) {
@@ -442,8 +470,36 @@ extern "C" int64_t gz_puct_info(const gz_puct* h, int what) {
 // One engine step. d_policy [G][policy_stride] f32 and d_value [G][n_rewards] f32 are the network's
 // outputs for the planes produced by the previous advance (ignored when nn_fresh == 0, e.g. on the
 // very first call). d_planes receives [G][total_size] of plane_dtype, one row per game.
+// ---- helpers of the forked goal pass
+__global__ void term_gather_kernel(const uint32_t* __restrict__ states, const int* __restrict__ idx,
+                                   const int* __restrict__ count, int SW, uint32_t* __restrict__ out) {
+    const int n = *count;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * SW; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / SW), c = (int)(i % SW);
+        out[i] = states[(int64_t)idx[r] * SW + c];
+    }
+}
+__global__ void term_scatter_kernel(const uint8_t* __restrict__ t_goals, const int* __restrict__ idx,
+                                    const int* __restrict__ count, int R, uint8_t* __restrict__ goals) {
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * R; i += gridDim.x * blockDim.x)
+        goals[(int64_t)idx[i / R] * R + (i % R)] = t_goals[i];
+}
+__global__ void __launch_bounds__(1024) hostpoll_compact_kernel(const uint8_t* __restrict__ need, int G,
+                                                                int* __restrict__ rows, int* __restrict__ count);
+
+// Main stream waits for the side-stream work (re-root, goal pass) of the last step.
+static int join_side(gz_puct* h, cudaStream_t s) {
+    if (h->side_pending) {
+        GZ_CUDA(cudaStreamWaitEvent(s, h->rr_join, 0));
+        h->side_pending = false;
+    }
+    return GZ_OK;
+}
+
 static int advance_impl(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
-                        void* d_planes, int plane_dtype, void* stream, cudaEvent_t* evs /* 6 or null */) {
+                        void* d_planes, int plane_dtype, void* stream, cudaEvent_t* evs /* 6 or null */,
+                        bool defer_join) {
     if (!h) { gz_set_error("null engine"); return GZ_ERR_ARG; }
     if (nn_fresh && (!d_policy || !d_value)) { gz_set_error("network outputs missing"); return GZ_ERR_ARG; }
     if (sub_iters < 1) sub_iters = 1;
@@ -453,6 +509,8 @@ static int advance_impl(gz_puct* h, const float* d_policy, const float* d_value,
     E.nn_value = d_value;
     cudaStream_t s = (cudaStream_t)stream;
     const int blocks = (E.G + PUCT_WARPS_PER_BLOCK - 1) / PUCT_WARPS_PER_BLOCK;
+    int rc = join_side(h, s);                       // a deferred join of the previous step
+    if (rc != GZ_OK) return rc;
     if (evs) GZ_CUDA(cudaEventRecord(evs[0], s));
     for (int it = 0; it < sub_iters; it++) {
         GZ_CUDA(cudaMemsetAsync(h->d_rr_count, 0, 4, s));
@@ -461,41 +519,76 @@ static int advance_impl(gz_puct* h, const float* d_policy, const float* d_value,
             E, (it == 0 && nn_fresh) ? 1 : 0, h->cache_words, h->d_rr_list, h->d_rr_count);
         GZ_CUDA(cudaGetLastError());
         if (evs) GZ_CUDA(cudaEventRecord(evs[1], s));
+        // the last iteration forks: re-rooting, and (split_goals) the goal cone of the terminal states with the
+        // creation of their nodes, run on the side stream beside the propnet pass / node creation / encoding
         const bool fork = (evs == nullptr) && (it + 1 == sub_iters);
+        const bool split = fork && h->split_goals;
         if (fork) {
             GZ_CUDA(cudaEventRecord(h->rr_fork, s));
             GZ_CUDA(cudaStreamWaitEvent(h->rr_stream, h->rr_fork, 0));
             puct_reroot_kernel<<<std::min(E.G, 148), REROOT_THREADS, 0, h->rr_stream>>>(E, h->d_rr_list, h->d_rr_count);
             GZ_CUDA(cudaGetLastError());
-            GZ_CUDA(cudaEventRecord(h->rr_join, h->rr_stream));
         } else {
             puct_reroot_kernel<<<std::min(E.G, 148), REROOT_THREADS, 0, s>>>(E, h->d_rr_list, h->d_rr_count);
             GZ_CUDA(cudaGetLastError());
         }
         if (evs) GZ_CUDA(cudaEventRecord(evs[2], s));
-        int rc = gz_sm_transition_scratch(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
-                                          GZ_GOALS_TERMINAL_ONLY, stream, h->d_pn_scratch);
+        rc = gz_sm_transition_scratch(h->pn, E.G, E.x_in_state, E.x_moves, E.x_state, E.x_legal, E.x_term, E.x_goals,
+                                      split ? GZ_GOALS_NEVER_INTERNAL : GZ_GOALS_TERMINAL_ONLY, stream, h->d_pn_scratch);
         if (rc != GZ_OK) return rc;
         if (evs) GZ_CUDA(cudaEventRecord(evs[3], s));
-        puct_post_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, s>>>(E);
+        if (split) {
+            cudaStream_t ss = h->rr_stream;
+            GZ_CUDA(cudaEventRecord(h->gl_fork, s));
+            GZ_CUDA(cudaStreamWaitEvent(ss, h->gl_fork, 0));
+            hostpoll_compact_kernel<<<1, 1024, 0, ss>>>(E.x_term, E.G, h->t_idx, h->t_count);
+            term_gather_kernel<<<std::min((E.G * E.SW + 255) / 256, 592), 256, 0, ss>>>(E.x_state, h->t_idx, h->t_count, E.SW, h->t_states);
+            GZ_CUDA(cudaGetLastError());
+            rc = gz_sm_eval_devcount(h->pn, E.G, h->t_count, h->t_states, h->t_legal, h->t_term, h->t_goals,
+                                     GZ_GOALS_ALWAYS, (void*)ss, h->d_pn_scratch);
+            if (rc != GZ_OK) return rc;
+            term_scatter_kernel<<<std::min((E.G * E.R + 255) / 256, 148), 256, 0, ss>>>(h->t_goals, h->t_idx, h->t_count, E.R, E.x_goals);
+            puct_post_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, ss>>>(E, 2);       // nodes of the terminal states
+            GZ_CUDA(cudaGetLastError());
+            puct_post_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, s>>>(E, 1);        // everything else
+        } else {
+            puct_post_kernel<<<blocks, PUCT_WARPS_PER_BLOCK * 32, 0, s>>>(E, 0);
+        }
         GZ_CUDA(cudaGetLastError());
+        if (fork) {
+            GZ_CUDA(cudaEventRecord(h->rr_join, h->rr_stream));
+            h->side_pending = true;
+        }
         if (evs) GZ_CUDA(cudaEventRecord(evs[4], s));
     }
     if (d_planes) {
         // every row is encoded (rows of games that do not wait for the network hold a stale but valid
         // state; their network outputs are never read)
-        int rc = gz_encode_layout(h->tr, E.G, E.SW, E.x_state, E.x_in_state, E.x_prevcnt, 1, d_planes, plane_dtype,
-                                  h->plane_c_pad, stream);
+        rc = gz_encode_layout(h->tr, E.G, E.SW, E.x_state, E.x_in_state, E.x_prevcnt, 1, d_planes, plane_dtype,
+                              h->plane_c_pad, stream);
         if (rc != GZ_OK) return rc;
     }
-    if (!evs) GZ_CUDA(cudaStreamWaitEvent(s, h->rr_join, 0));      // join the re-root of this step
+    if (!defer_join) { rc = join_side(h, s); if (rc != GZ_OK) return rc; }
     if (evs) GZ_CUDA(cudaEventRecord(evs[5], s));
     return GZ_OK;
 }
 
 extern "C" int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
                                void* d_planes, int plane_dtype, void* stream) {
-    return advance_impl(h, d_policy, d_value, nn_fresh, sub_iters, d_planes, plane_dtype, stream, nullptr);
+    return advance_impl(h, d_policy, d_value, nn_fresh, sub_iters, d_planes, plane_dtype, stream, nullptr, false);
+}
+
+// Same step, but the side-stream work it forks (re-rooting, the goal pass of terminal states) is left
+// running: the caller may enqueue the network forward right away and must call gz_puct_join (or the next
+// gz_puct_advance*, which joins first) on the same stream before it reads or steps the engine again.
+extern "C" int gz_puct_advance_async(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh,
+                                     int sub_iters, void* d_planes, int plane_dtype, void* stream) {
+    return advance_impl(h, d_policy, d_value, nn_fresh, sub_iters, d_planes, plane_dtype, stream, nullptr, true);
+}
+extern "C" int gz_puct_join(gz_puct* h, void* stream) {
+    if (!h) { gz_set_error("null engine"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    return join_side(h, (cudaStream_t)stream);
 }
 
 // Measurement aid: one engine step (sub_iters == 1) with CUDA events between its launches on `stream`;
@@ -507,7 +600,7 @@ extern "C" int gz_puct_advance_timed(gz_puct* h, const float* d_policy, const fl
     GZ_CUDA(cudaSetDevice(h->device));
     cudaEvent_t evs[6];
     for (int i = 0; i < 6; i++) GZ_CUDA(cudaEventCreate(&evs[i]));
-    int rc = advance_impl(h, d_policy, d_value, nn_fresh, 1, d_planes, plane_dtype, stream, evs);
+    int rc = advance_impl(h, d_policy, d_value, nn_fresh, 1, d_planes, plane_dtype, stream, evs, false);
     if (rc == GZ_OK) {
         cudaError_t e = cudaEventSynchronize(evs[5]);
         if (e != cudaSuccess) { gz_set_error("timed step failed: %s", cudaGetErrorString(e)); rc = GZ_ERR_CUDA; }
@@ -531,6 +624,7 @@ extern "C" const uint8_t* gz_puct_need_eval_ptr(const gz_puct* h) { return h ? h
 extern "C" int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream) {
     if (!h || !d_out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
+    { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
     GZ_CUDA(cudaMemcpyAsync(d_out, h->E.x_need_eval, (size_t)h->E.G, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return GZ_OK;
 }
@@ -717,6 +811,7 @@ extern "C" int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes) {
 extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     if (!h || !out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
+    { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
     cudaStream_t s = (cudaStream_t)stream;
     GZ_CUDA(cudaMemsetAsync(h->d_totals, 0, sizeof(PuctTotals), s));
     puct_totals_kernel<<<(h->E.G + 127) / 128, 128, 0, s>>>(h->E, h->d_totals);
@@ -741,6 +836,7 @@ extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
 extern "C" int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream) {
     if (!h || (!h_out && cap > 0)) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     cudaSetDevice(h->device);
+    if (join_side(h, (cudaStream_t)stream) != GZ_OK) return GZ_ERR_CUDA;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long ready = 0;
     if (cudaMemcpyAsync(&ready, h->E.ready_count, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
@@ -759,6 +855,7 @@ extern "C" int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap
 extern "C" int gz_puct_clear_unique_states(gz_puct* h, void* stream) {
     if (!h) return GZ_ERR_ARG;
     GZ_CUDA(cudaSetDevice(h->device));
+    { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
     GZ_CUDA(cudaMemsetAsync(h->E.uniq_keys, 0, (size_t)h->E.uniq_cap * 8, (cudaStream_t)stream));
     GZ_CUDA(cudaMemsetAsync(h->E.uniq_counts, 0, (size_t)h->E.uniq_cap * 4, (cudaStream_t)stream));
     return GZ_OK;
@@ -773,6 +870,7 @@ __global__ void puct_cmd_kernel(const __grid_constant__ PuctEngine E, int g, int
 extern "C" int gz_puct_command(gz_puct* h, int g, int cmd, int arg, int evals, const uint32_t* h_state, void* stream) {
     if (!h || g < 0 || g >= h->E.G) { gz_set_error("bad game index"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
+    { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
     cudaStream_t s = (cudaStream_t)stream;
     if (cmd == CMD_RESET) {
         if (h_state) GZ_CUDA(cudaMemcpyAsync(h->E.x_in_state + (size_t)g * h->E.SW, h_state, h->E.SW * 4, cudaMemcpyHostToDevice, s));
@@ -814,6 +912,7 @@ extern "C" int gz_puct_snapshot(gz_puct* h, int g, int max_children, int* out_i,
                                 float* prob, float* score, float* next_prob, void* stream) {
     if (!h || g < 0 || g >= h->E.G || max_children < 0) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
+    { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = 16 * 4 + (size_t)max_children * 5 * 4 + 64;
     void* d = nullptr;

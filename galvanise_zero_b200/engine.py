@@ -65,6 +65,8 @@ def _declare(L):
     L.gz_puct_info.argtypes = [vp, ci]
     L.gz_puct_info.restype = i64
     L.gz_puct_advance.argtypes = [vp, vp, vp, ci, ci, vp, ci, vp]
+    L.gz_puct_advance_async.argtypes = [vp, vp, vp, ci, ci, vp, ci, vp]
+    L.gz_puct_join.argtypes = [vp, vp]
     L.gz_puct_totals.argtypes = [vp, dp, vp]
     L.gz_puct_fetch_samples.argtypes = [vp, vp, i64, vp]
     L.gz_puct_fetch_samples.restype = i64
@@ -140,9 +142,15 @@ class PuctEngine(object):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- the poll-equivalent on device tensors
-    def advance(self, policy=None, value=None, sub_iters=1):
+    def join(self):
+        """Waits (on the current stream) for the side-stream work of the last ``advance(..., defer_join=True)``."""
+        _lib.check(self._L.gz_puct_join(self._h, self._stream()))
+
+    def advance(self, policy=None, value=None, sub_iters=1, defer_join=False):
         """policy f32 [G, sum(role sizes)] (role rows concatenated), value f32 [G, n_rewards]: the
         network outputs for the planes returned by the previous call (None on the first call).
+        With ``defer_join`` the step's side-stream work (re-rooting, goal values of terminal states) keeps
+        running while the caller enqueues the network forward; ``join()`` must follow on the same stream.
         Returns planes [G, C, H, W] (bf16) — one row per game; rows of games not waiting for the
         network are to be ignored (their outputs are)."""
         fresh = policy is not None
@@ -150,9 +158,9 @@ class PuctEngine(object):
             assert policy.dtype == torch.float32 and policy.is_contiguous() and policy.shape == self.policy.shape
             assert value.dtype == torch.float32 and value.is_contiguous() and value.shape == self.value.shape
         code = {torch.float32: 0, torch.bfloat16: 1}[self.planes.dtype]
-        _lib.check(self._L.gz_puct_advance(self._h, policy.data_ptr() if fresh else None,
-                                           value.data_ptr() if fresh else None, 1 if fresh else 0,
-                                           sub_iters, self.planes.data_ptr(), code, self._stream()))
+        fn = self._L.gz_puct_advance_async if defer_join else self._L.gz_puct_advance
+        _lib.check(fn(self._h, policy.data_ptr() if fresh else None, value.data_ptr() if fresh else None,
+                      1 if fresh else 0, sub_iters, self.planes.data_ptr(), code, self._stream()))
         return self.planes
 
     def advance_timed(self, policy=None, value=None):

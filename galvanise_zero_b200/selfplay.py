@@ -41,8 +41,10 @@ class SelfPlayRunner(object):
 
     def _step_eager(self):
         e = self.engine
-        e.advance(e.policy, e.value, self.sub_iters)
+        # the network forward overlaps the step's side-stream work (re-rooting, goal pass); joined after it
+        e.advance(e.policy, e.value, self.sub_iters, defer_join=True)
         self._forward()
+        e.join()
 
     def _capture(self):
         e = self.engine

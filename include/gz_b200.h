@@ -170,6 +170,14 @@ int gz_puct_set_config(gz_puct* h, const double* sp_conf, const double* puct_con
 int64_t gz_puct_info(const gz_puct* h, int what);
 int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
                     void* d_planes, int plane_dtype, void* stream);
+/* gz_puct_advance forks part of a step onto an internal side stream (re-rooting of the games that moved; for
+ * games with a deep goal cone, the goal values and nodes of terminal states) and joins it before returning
+ * control of `stream`. The _async variant leaves that work running so that the caller's network forward
+ * overlaps it; gz_puct_join (or the next advance, which joins first) must follow on the same stream before
+ * the engine is read or stepped again. */
+int gz_puct_advance_async(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
+                          void* d_planes, int plane_dtype, void* stream);
+int gz_puct_join(gz_puct* h, void* stream);
 /* Measurement aid: one engine step with CUDA events between its launches; waits for it and returns the
  * device time of each launch in ms: [puct_pre_kernel, puct_reroot_kernel, pn_kernel, puct_post_kernel,
  * encode_kernel]. */
