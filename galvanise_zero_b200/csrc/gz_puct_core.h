@@ -410,24 +410,33 @@ GZP_HDN void gzp_cache_fill(GameView& V, int n) {
     ChildCache& C = V.C;
     GZP_SYNC();
     for (int i = V.lane; i < nc; i += GZP_LANES) {
+        // all loads first, stores after: the cache is addressed through generic pointers, so a store between
+        // two loads would make the second wait for the first one's data (one DRAM round trip per field)
         const int to = CHILD(c_to, c0 + i);
-        C.to[i] = to;
-        C.move[i] = CHILD(c_move, c0 + i);
-        C.trav[i] = CHILD(c_trav, c0 + i);
-        C.prob[i] = CHILD(c_prob, c0 + i);
-        C.prob_orig[i] = CHILD(c_prob_orig, c0 + i);
-        C.next[i] = CHILD(c_next, c0 + i);
+        const int mv = CHILD(c_move, c0 + i);
+        const uint32_t tr = CHILD(c_trav, c0 + i);
+        const float pr = CHILD(c_prob, c0 + i);
+        const float po = CHILD(c_prob_orig, c0 + i);
+        const float nx = CHILD(c_next, c0 + i);
+        float sc = -1.0f;
+        uint32_t vi = 0;
+        int fl = 0, inf = 0;
         if (to >= 0) {
-            C.score[i] = NSCORE(to, lead < 0 ? 0 : lead);
-            C.visits[i] = NODE(n_visits, to);
-            C.flags[i] = NODE(n_flags, to);
-            C.inflight[i] = NODE(n_inflight, to);
-        } else {
-            C.score[i] = -1.0f;
-            C.visits[i] = 0;
-            C.flags[i] = 0;
-            C.inflight[i] = 0;
+            sc = NSCORE(to, lead < 0 ? 0 : lead);
+            vi = NODE(n_visits, to);
+            fl = NODE(n_flags, to);
+            inf = NODE(n_inflight, to);
         }
+        C.to[i] = to;
+        C.move[i] = mv;
+        C.trav[i] = tr;
+        C.prob[i] = pr;
+        C.prob_orig[i] = po;
+        C.next[i] = nx;
+        C.score[i] = sc;
+        C.visits[i] = vi;
+        C.flags[i] = fl;
+        C.inflight[i] = inf;
     }
     GZP_SYNC();
 }
@@ -747,13 +756,17 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
     int32_t* pn = V.pn;
     int32_t* pc = V.pc;
 
-    // setPuctConstant (evaluator.cpp:1300-1307)
+    // setPuctConstant (evaluator.cpp:1300-1307); the node's visit count is read once for the whole function
+    // (nothing below writes it) and the constant is kept in a register besides being stored
+    const uint32_t node_visits = NODE(n_visits, n);
+    float puct_c;
     {
         const float base = 19652.0f;
         const float k = depth == 0 ? cf.puct_constant_root : cf.puct_constant;
-        float pcst = logf(((float)(1u + NODE(n_visits, n)) + base) / base);
+        float pcst = logf(((float)(1u + node_visits) + base) / base);
         pcst += k;
         NODE(n_puct, n) = pcst;
+        puct_c = pcst;
     }
     c->total_sel_nodes++;
     c->total_sel_children += (uint64_t)nc;
@@ -766,9 +779,7 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
     if (depth == 0) gzp_set_dirichlet_noise(V, n);
 
     const float prior_score = gzp_prior_score(V, n, depth);
-    const double sqrt_node_visits = sqrt((double)(NODE(n_visits, n) + 1u));
-    const float puct_c = NODE(n_puct, n);
-    const uint32_t node_visits = NODE(n_visits, n);
+    const double sqrt_node_visits = sqrt((double)(node_visits + 1u));
 
     float best_score = -1;
     int best_child = -1;
@@ -883,28 +894,43 @@ GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
                 NODE(n_flags, n) |= NF_FINALISED;
             }
         }
-        if (gzp_is_finalised(V, n)) {
-            for (int r = 0; r < R; r++) new_scores[r] = NSCORE(n, r);
+        // everything this node needs, loaded in one go (through global pointers the compiler has to assume
+        // that every store may alias the next load, so interleaved read-modify-writes cost a memory round
+        // trip each); the arithmetic below is the reference's, in its order
+        const bool finalised = gzp_is_finalised(V, n);
+        uint32_t visits_u = NODE(n_visits, n);
+        const int inflight = NODE(n_inflight, n);
+        const int c0n = NODE(n_child0, n);
+        float sc[GZP_MAX_ROLES];
+#pragma unroll
+        for (int r = 0; r < GZP_MAX_ROLES; r++) sc[r] = r < R ? NSCORE(n, r) : 0.0f;
+        uint32_t ctrav = 0;
+        float cprob = 0.0f;
+        const int ci = c0n + (choice >= 0 ? choice : 0);
+        if (choice >= 0) { ctrav = CHILD(c_trav, ci); cprob = CHILD(c_prob, ci); }
+        if (finalised) {
+            for (int r = 0; r < R; r++) new_scores[r] = sc[r];
         } else {
             for (int r = 0; r < R; r++) {
-                float visits = (float)NODE(n_visits, n);
+                float visits = (float)visits_u;
                 if (visits > 100000) visits = 100000 + 0.1f * (visits - 100000);
-                const float score = (visits * NSCORE(n, r) + new_scores[r]) / (visits + 1.0f);
+                const float score = (visits * sc[r] + new_scores[r]) / (visits + 1.0f);
+                sc[r] = score;
                 NSCORE(n, r) = score;
             }
         }
-        NODE(n_visits, n) = NODE(n_visits, n) + 1;
-        if (NODE(n_inflight, n) > 0) NODE(n_inflight, n) = NODE(n_inflight, n) - 1;
+        visits_u += 1;
+        NODE(n_visits, n) = visits_u;
+        if (inflight > 0) NODE(n_inflight, n) = inflight - 1;
         if (choice >= 0) {
-            const int ci = NODE(n_child0, n) + choice;
-            CHILD(c_trav, ci) = CHILD(c_trav, ci) + 1;
-            if (NODE(n_visits, n) > 23) {
-                const float cur_score = NSCORE(n, lead);
+            CHILD(c_trav, ci) = ctrav + 1;
+            if (visits_u > 23) {
+                const float cur_score = sc[lead];
                 float apply, mn;
                 if (cur_score > 0.3 && cur_score < 0.7) { apply = 0.995f; mn = 0.02f; }
                 else if (cur_score > 0.15 && cur_score < 0.85) { apply = 0.9975f; mn = 0.03f; }
                 else { apply = 0.9975f; mn = 0.10f; }
-                float p = CHILD(c_prob, ci);
+                float p = cprob;
                 if (p > mn) {
                     p *= apply;
                     p = mn > p ? mn : p;
@@ -912,9 +938,9 @@ GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
                 }
             }
         }
-        if (NODE(n_visits, n) % 100 == 0) {
+        if (visits_u % 100 == 0) {
             // normaliseX (node.h:192-214)
-            const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+            const int nc = NODE(n_nchild, n), c0 = c0n;
             float total = 0;
             for (int i = 0; i < nc; i++) total += CHILD(c_prob, c0 + i);
             if (total > 1.17549435e-38f) {
