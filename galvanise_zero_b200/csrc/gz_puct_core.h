@@ -626,8 +626,8 @@ GZP_HDN void gzp_order_children(GameView& V, int nc, Cmp cmp) {
 // chooseTopVisits (evaluator.cpp:1100-1159). Sort key: traversals desc, then policy_prob desc
 // (node.cpp:346-373), ordered with the restated std::sort.
 // Expects the cache to hold node n's children (gzp_cache_fill).
-GZP_HDN int gzp_choose_top_visits(const GameView& V, int n) {
-    const int nc = NODE(n_nchild, n);
+GZP_HDN int gzp_choose_top_visits(const GameView& V, int n, int nc_known = -1) {
+    const int nc = nc_known >= 0 ? nc_known : NODE(n_nchild, n);
     const PuctConf& cf = gzp_conf(V);
     const ChildCache& C = V.C;
     int* order = C.order;
@@ -662,19 +662,19 @@ GZP_HDN int gzp_choose_top_visits(const GameView& V, int n) {
 }
 
 // priorScore (evaluator.cpp:1195-1224)
-GZP_HDN float gzp_prior_score(const GameView& V, int n, int depth) {
+// node_final = the node's final score for its lead role, node_visits / nc its visit and child counts — the
+// caller has them in registers already (each would otherwise be a dependent global load on the descent).
+GZP_HDN float gzp_prior_score(const GameView& V, int n, int depth, float node_final, uint32_t node_visits, int nc) {
     const PuctConf& cf = gzp_conf(V);
     const ChildCache& C = V.C;
-    const int lead = NODE(n_lead, n);
-    float prior = NFINAL(n, lead);
-    if (NODE(n_visits, n) > 8) {
-        const int best = gzp_choose_top_visits(V, n);
+    float prior = node_final;
+    if (node_visits > 8) {
+        const int best = gzp_choose_top_visits(V, n, nc);
         if (C.to[best] >= 0) prior = C.score[best];
     }
     float fpu = depth == 0 ? cf.fpu_prior_discount_root : cf.fpu_prior_discount;
     if (fpu > 0) {
         float total = 0.0f;
-        const int nc = NODE(n_nchild, n);
         for (int i = 0; i < nc; i++)
             if (C.to[i] >= 0 && C.visits[i] > 0) total += C.prob[i];
         fpu *= sqrtf(total);
@@ -745,7 +745,9 @@ GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n) {
 
 // selectChild (evaluator.cpp:341-517). Appends to the path; returns the child index within the
 // node (or -1 when nothing is selectable, which cannot happen with one evaluation in flight).
-GZP_HDN int gzp_select_child(GameView& V, int n) {
+struct GzpSelInfo { int to; int inflight; };   // the chosen child's node (or -1) and node n's in-flight count, read with the header
+
+GZP_HDN int gzp_select_child(GameView& V, int n, GzpSelInfo* info = nullptr) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     const PuctConf& cf = gzp_conf(V);
@@ -759,6 +761,11 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
     // setPuctConstant (evaluator.cpp:1300-1307); the node's visit count is read once for the whole function
     // (nothing below writes it) and the constant is kept in a register besides being stored
     const uint32_t node_visits = NODE(n_visits, n);
+    const int node_inflight = NODE(n_inflight, n);
+    if (info) { info->to = -1; info->inflight = node_inflight; }
+    float node_finals[GZP_MAX_ROLES];
+#pragma unroll
+    for (int r = 0; r < GZP_MAX_ROLES; r++) node_finals[r] = NFINAL(n, r);      // one 16-byte line, with the header
     float puct_c;
     {
         const float base = 19652.0f;
@@ -772,13 +779,14 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
     c->total_sel_children += (uint64_t)nc;
     if (nc == 1) {
         pn[c->path_len] = n; pc[c->path_len] = 0; c->path_len++;
+        if (info) info->to = CHILD(c_to, c0);
         return 0;
     }
     gzp_cache_fill(V, n);
     ChildCache& C = V.C;
     if (depth == 0) gzp_set_dirichlet_noise(V, n);
 
-    const float prior_score = gzp_prior_score(V, n, depth);
+    const float prior_score = gzp_prior_score(V, n, depth, node_finals[lead < 0 ? 0 : lead], node_visits, nc);
     const double sqrt_node_visits = sqrt((double)(node_visits + 1u));
 
     float best_score = -1;
@@ -812,6 +820,7 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
                 if (child_score > 0.99) {
                     if (depth > 0) {
                         pn[c->path_len] = n; pc[c->path_len] = pick; c->path_len++;
+                        if (info) info->to = to;
                         return pick;
                     }
                     child_score *= 1.0f + puct_c;
@@ -853,6 +862,7 @@ GZP_HDN int gzp_select_child(GameView& V, int n) {
     }
     if (best_child >= 0) {
         pn[c->path_len] = n; pc[c->path_len] = best_child; c->path_len++;
+        if (info) info->to = C.to[best_child];
     }
     return best_child;
 }
@@ -1410,15 +1420,15 @@ GZP_HDN bool gzp_playout_continue(GameView& V) {
             gzp_finish_playout(V, cur);
             return false;
         }
-        const int child = gzp_select_child(V, cur);
+        GzpSelInfo si;
+        const int child = gzp_select_child(V, cur, &si);
         if (child < 0 || c->error) { c->error = c->error ? c->error : GZP_ERR_PATH; return true; }
-        const int ci = NODE(n_child0, cur) + child;
-        if (CHILD(c_to, ci) < 0) {
+        if (si.to < 0) {
             gzp_request_expand(V, cur, child, PUR_PLAYOUT);
             return true;
         }
-        NODE(n_inflight, cur) = NODE(n_inflight, cur) + 1;
-        c->cur = CHILD(c_to, ci);
+        NODE(n_inflight, cur) = si.inflight + 1;
+        c->cur = si.to;
     }
 }
 
