@@ -340,9 +340,10 @@ struct ChildCache {
     int32_t *to, *move, *flags, *inflight, *order;
     uint32_t *trav, *visits;
     float *prob, *prob_orig, *next, *score, *tmp;
+    double* expl;    // per-child exploration term of the current select (computed by the lanes in parallel)
 };
 
-GZP_HD size_t gzp_cache_words(int cap) { return (size_t)12 * (size_t)cap; }
+GZP_HD size_t gzp_cache_words(int cap) { return (size_t)14 * (size_t)cap + 2; }
 
 GZP_HD void gzp_cache_bind(ChildCache& C, uint32_t* mem, int cap) {
     C.cap = cap;
@@ -357,7 +358,9 @@ GZP_HD void gzp_cache_bind(ChildCache& C, uint32_t* mem, int cap) {
     C.prob_orig = (float*)mem; mem += cap;
     C.next = (float*)mem; mem += cap;
     C.score = (float*)mem; mem += cap;
-    C.tmp = (float*)mem;
+    C.tmp = (float*)mem; mem += cap;
+    mem += ((uintptr_t)mem & 4) ? 1 : 0;          // 8-byte alignment for the doubles
+    C.expl = (double*)mem;
 }
 
 struct GameView {
@@ -805,14 +808,22 @@ GZP_HDN int gzp_select_child(GameView& V, int n, GzpSelInfo* info = nullptr) {
         if (sa < 0 && sb < 0) return C.prob_orig[a] > C.prob_orig[b];
         return sa > sb;
     });
+    // the exploration term of every child (an FP64 divide each) does not depend on the scan below: one child
+    // per lane instead of all of them, one after the other, in every lane
+    GZP_SYNC();
+    for (int i = V.lane; i < nc; i += GZP_LANES) {
+        const int traversals_i = (int)C.trav[i] + 1;
+        const double inflight_i = C.to[i] >= 0 ? (double)C.inflight[i] : 0.0;
+        C.expl[i] = (double)(puct_c * C.prob[i]) * sqrt_node_visits / (traversals_i + inflight_i);
+    }
+    GZP_SYNC();
     for (int rank = 0; rank < nc; rank++) {
         const int pick = order[rank];
         const int to = C.to[pick];
         const uint32_t ctrav = C.trav[pick];
         double child_score = prior_score;
-        const int traversals = (int)ctrav + 1;
         const double inflight = to >= 0 ? (double)C.inflight[pick] : 0.0;
-        double exploration = (double)(puct_c * C.prob[pick]) * sqrt_node_visits / (traversals + inflight);
+        double exploration = C.expl[pick];
         if (to >= 0) {
             child_score = C.score[pick];
             const bool fin = (C.flags[pick] & NF_FINALISED) != 0;
