@@ -463,6 +463,7 @@ extern "C" int64_t gz_puct_info(const gz_puct* h, int what) {
         case 6: return h->E.SW;
         case 7: return h->E.max_actions;
         case 8: return h->E.READYCAP;
+        case 9: return h->split_goals ? 10 : 5;   // kernels of this library launched per engine step (sub_iters == 1)
         default: return -1;
     }
 }

@@ -817,6 +817,72 @@ GZP_HDN int gzp_select_child(GameView& V, int n, GzpSelInfo* info = nullptr) {
         C.expl[i] = (double)(puct_c * C.prob[i]) * sqrt_node_visits / (traversals_i + inflight_i);
     }
     GZP_SYNC();
+#ifdef __CUDA_ARCH__
+    // Lane-parallel form of the scan below for the common case: at most 32 children, no evaluation in
+    // flight below this node and the root latch limiter inactive (so the scan draws no random numbers).
+    // Lane r takes the child of rank r. The sequential scan keeps its running best as a FLOAT and compares
+    // the next DOUBLE score against it; because rounding is monotonic, "child r replaces the best" is the
+    // same as "score_r > max(initial, float(score_j) for eligible j < r)" — an exclusive prefix maximum —
+    // and the final choice is the last child that replaced it.
+    const bool latch_on = node_visits > 1000 && node_visits < 40000000 && depth == 0;
+    if (nc <= 32 && !latch_on) {
+        const unsigned full = 0xffffffffu;
+        const int r = V.lane;
+        const bool act = r < nc;
+        const int pick = act ? order[r] : 0;
+        const int to = act ? C.to[pick] : -1;
+        const uint32_t ctrav = act ? C.trav[pick] : 0u;
+        double child_score = prior_score;
+        double exploration = act ? C.expl[pick] : 0.0;
+        bool badfb = false, winret = false;
+        int infl = 0;
+        if (act && to >= 0) {
+            infl = C.inflight[pick];
+            child_score = C.score[pick];
+            if ((C.flags[pick] & NF_FINALISED) != 0) {
+                if (child_score > 0.99) {
+                    if (depth > 0) winret = true;
+                    else child_score *= 1.0f + puct_c;
+                } else if (child_score < 0.01) {
+                    badfb = true;
+                } else {
+                    exploration = 0.0;
+                }
+            }
+        }
+        if (!__any_sync(full, act && ctrav > 0 && infl > 0)) {
+            const unsigned wm = __ballot_sync(full, act && winret);
+            if (wm) {                                   // a proven win below the root: taken at once, lowest rank first
+                const int p0 = order[__ffs(wm) - 1];
+                pn[c->path_len] = n; pc[c->path_len] = p0; c->path_len++;
+                if (info) info->to = C.to[p0];
+                return p0;
+            }
+            const unsigned bm = __ballot_sync(full, act && badfb);
+            const bool elig = act && !badfb;
+            const double score = child_score + exploration;
+            const float neg_inf = -3.402823466e+38f;
+            float run = elig ? (float)score : neg_inf;   // inclusive prefix maximum of the float-rounded scores
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const float o = __shfl_up_sync(full, run, d);
+                if (r >= d) run = fmaxf(run, o);
+            }
+            float before = __shfl_up_sync(full, run, 1);
+            if (r == 0) before = neg_inf;
+            before = fmaxf(before, -1.0f);               // float best_score = -1
+            const unsigned win = __ballot_sync(full, elig && score > (double)before);
+            int best_child = -1;
+            if (win) best_child = order[31 - __clz(win)];
+            else if (bm) best_child = order[31 - __clz(bm)];   // bad_fallback: the last proven loss
+            if (best_child >= 0) {
+                pn[c->path_len] = n; pc[c->path_len] = best_child; c->path_len++;
+                if (info) info->to = C.to[best_child];
+            }
+            return best_child;
+        }
+    }
+#endif
     for (int rank = 0; rank < nc; rank++) {
         const int pick = order[rank];
         const int to = C.to[pick];

@@ -116,6 +116,7 @@ class PuctEngine(object):
         self.state_words = info(6)
         self.max_actions = info(7)
         self.ready_cap = info(8)
+        self.kernels_per_step = info(9)
         tr = self.transformer
         self.plane_shape = (tr.num_channels, tr.num_cols, tr.num_rows)
         self.plane_c_pad = plane_c_pad

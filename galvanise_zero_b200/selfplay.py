@@ -77,8 +77,9 @@ class SelfPlayRunner(object):
 
     @property
     def kernels_per_step(self):
-        """Launches of this repo's own kernels per step: (pre, reroot, propnet, post) x sub_iters + encode."""
-        return 4 * self.sub_iters + 1
+        """Launches of this repo's own kernels per step: pre, re-root, propnet, node creation, encode (+ the
+        forked goal pass: compaction, gather, propnet, scatter, node creation)."""
+        return self.engine.kernels_per_step + 4 * (self.sub_iters - 1)
 
 
 class SelfPlayPool(object):

@@ -166,7 +166,8 @@ int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, int mode, in
 void gz_puct_destroy(gz_puct* h);
 int gz_puct_set_config(gz_puct* h, const double* sp_conf, const double* puct_conf, const double* run_to_end_puct_conf);
 /* what: 0 games, 1 plane row size, 2 policy row size (sum of role sizes), 3 value row size,
- *       4 sample record words, 5 arena bytes, 6 state words, 7 max actions, 8 ready capacity */
+ *       4 sample record words, 5 arena bytes, 6 state words, 7 max actions, 8 ready capacity,
+ *       9 kernels of this library launched per engine step */
 int64_t gz_puct_info(const gz_puct* h, int what);
 int gz_puct_advance(gz_puct* h, const float* d_policy, const float* d_value, int nn_fresh, int sub_iters,
                     void* d_planes, int plane_dtype, void* stream);

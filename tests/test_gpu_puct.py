@@ -44,6 +44,8 @@ def _device_search(eng, evals, n_moves, seed=1):
 
 
 @pytest.mark.parametrize('game,evals,moves', [('reversi', 200, 20), ('breakthrough', 300, 20),
+                                              ('reversi', 1500, 5),      # root visits > 1000: the latch limiter and its RNG draws
+                                              ('breakthroughSmall', 800, 12),
                                               ('chess_15d', 60, 3), ('hexLG13', 40, 3),
                                               ('connect6', 100, 4)])
 def test_device_search_matches_reference(game, evals, moves):
