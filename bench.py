@@ -369,7 +369,8 @@ def run_puct(args, rank, world, local):
                for k in range(P)]
     eng = engines[0]
     net = make_inference_network(eng.transformer, 'small', seed=1234, device=eng.device)
-    if args.staggered and P > 1:
+    if P > 1:
+        # several shards: engine graphs on their own streams, network graphs serialised on one
         runner = StaggeredSelfPlay(engines, net, sub_iters=args.sub_iters)
     else:
         runner = SelfPlayPool(engines, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph)
@@ -665,7 +666,7 @@ def main():
     ap.add_argument('--presteps', type=int, default=3000)
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--pipelines', type=int, default=1)
-    ap.add_argument('--staggered', action='store_true')
+    ap.add_argument('--staggered', action='store_true', help='(implied by --pipelines > 1)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-inline', action='store_true')
     ap.add_argument('--slots', type=int, default=0)

@@ -83,13 +83,14 @@ class SelfPlayRunner(object):
 
 
 class SelfPlayPool(object):
-    """Several independent engine+network pipelines on separate CUDA streams (each with its own
-    graph). While one pipeline's network forward occupies the tensor cores, another pipeline's
-    latency-bound tree kernels run beside it — the device-side analogue of the reference's two
-    managers per worker thread, which overlap CPU search with the GPU call
-    (``src/cpp/supervisor.cpp:79-99,196-231``)."""
+    """One engine+network pipeline per engine on its own CUDA stream, each with its own graph. Used with a
+    single engine; several shards go through StaggeredSelfPlay (engine graphs on their own streams, network
+    graphs serialised on one), which is what overlaps tree kernels with the tower — the device-side analogue
+    of the reference's two managers per worker thread (``src/cpp/supervisor.cpp:79-99,196-231``)."""
 
     def __init__(self, engines, net, sub_iters=1, use_cuda_graph=True):
+        if len(engines) != 1:
+            raise ValueError('SelfPlayPool drives one engine; use StaggeredSelfPlay for several shards')
         dev = engines[0].device
         self.engines = engines
         self.streams = [torch.cuda.Stream(device=dev) for _ in engines]
@@ -205,4 +206,4 @@ class StaggeredSelfPlay(object):
 
     @property
     def kernels_per_step(self):
-        return len(self.engines) * (4 * self.sub_iters + 1)
+        return sum(e.kernels_per_step + 4 * (self.sub_iters - 1) for e in self.engines)
