@@ -24,67 +24,65 @@ def create_c_transformer(transformer, device=None):
 
 
 class PollerBase(object):
-    """``src/ggpzero/util/cppinterface.py:53-153``: drives an engine object's ``poll`` with the
-    network's ``predict_on_batch`` until the engine has nothing left to evaluate."""
+    """Drives an engine object's ``poll`` with the network until the engine has nothing left to evaluate —
+    the contract of ``src/ggpzero/util/cppinterface.py:53-153``: the first poll carries empty arrays, every
+    later one the predictions for the rows of the previous batch; ``None`` from the engine ends a loop and
+    the next loop primes again. Statistics keep the reference's names (``acc_time_polling`` = engine time,
+    ``acc_time_prediction`` = network time)."""
     POLL_AGAIN = "poll_again"
 
     def __init__(self, sm, nn, batch_size=1024, sleep_between_poll=-1):
-        self.sm = sm
-        self.nn = nn
-        self.batch_size = batch_size
+        self.sm, self.nn = sm, nn
+        self.batch_size = batch_size                  # most rows one poll may hand out
         self.sleep_between_poll = sleep_between_poll
-        self.poll_last = None
+        self.poll_last = None                         # predictions waiting to be fed back
         self.reset_stats()
 
     def _get_poller(self):
         raise NotImplementedError
 
     def reset_stats(self):
-        self.num_predictions_calls = 0
-        self.total_predictions = 0
-        self.acc_time_polling = 0
-        self.acc_time_prediction = 0
+        self.num_predictions_calls = self.total_predictions = 0
+        self.acc_time_polling = self.acc_time_prediction = 0
+
+    def _pending_arrays(self, n_heads):
+        import numpy as np
+        if self.poll_last is None:
+            return [np.zeros(0, dtype=np.float32)] * n_heads
+        arrays = list(self.poll_last)
+        assert len(arrays) == n_heads
+        return arrays
 
     def poll(self, do_stats=False):
-        """POLL_AGAIN is returned to indicate that poll() has to be called again."""
+        """One engine call + one network call; returns POLL_AGAIN while the engine wants more."""
         import time
-        import numpy as np
-        transformer = self.nn.gdl_bases_transformer
-        expect_num_arrays = len(transformer.policy_dist_count) + 1
-        if self.poll_last is None:
-            dummy = np.zeros(0, dtype=np.float32)
-            arrays = [dummy for _ in range(expect_num_arrays)]
-        else:
-            arrays = list(self.poll_last)
-        assert len(arrays) == expect_num_arrays
-        s0 = time.time()
-        pred_array = self._get_poller().poll(len(arrays[0]), arrays)
-        if pred_array is None:
+        tr = self.nn.gdl_bases_transformer
+        arrays = self._pending_arrays(len(tr.policy_dist_count) + 1)
+        t_start = time.time()
+        flat = self._get_poller().poll(len(arrays[0]), arrays)
+        t_polled = time.time()
+        if flat is None:
             self.poll_last = None
             return None
-        s1 = time.time()
-        t = transformer
-        num_predictions = len(pred_array) // (t.num_channels * t.channel_size)
-        assert num_predictions <= self.batch_size
-        pred_array = pred_array.reshape(num_predictions, t.num_channels, t.num_cols, t.num_rows)
-        self.poll_last = self.nn.get_model().predict_on_batch(pred_array)
+        rows = len(flat) // (tr.num_channels * tr.channel_size)
+        assert rows <= self.batch_size
+        batch = flat.reshape(rows, tr.num_channels, tr.num_cols, tr.num_rows)     # a view, nothing is copied
+        self.poll_last = self.nn.get_model().predict_on_batch(batch)
         if do_stats:
-            s2 = time.time()
             self.num_predictions_calls += 1
-            self.total_predictions += num_predictions
-            self.acc_time_polling += s1 - s0
-            self.acc_time_prediction += s2 - s1
+            self.total_predictions += rows
+            self.acc_time_polling += t_polled - t_start
+            self.acc_time_prediction += time.time() - t_polled
         return self.POLL_AGAIN
 
     def poll_loop(self, cb=None, do_stats=False):
-        """polls until done; ``cb`` is called every 100 polls and stops the loop when it returns true."""
+        """Polls until the engine is done; every 100 polls ``cb`` may stop the loop by returning true."""
         import time
-        cb_every_n = 100
-        count = 1
+        polls = 0
         while self.poll(do_stats=do_stats) == self.POLL_AGAIN:
-            if count % cb_every_n == 0 and cb is not None and cb():
-                break
-            count += 1
+            polls += 1
+            if cb is not None and polls % 100 == 0 and cb():
+                return
             if self.sleep_between_poll > 0:
                 time.sleep(self.sleep_between_poll)
 
@@ -92,14 +90,17 @@ class PollerBase(object):
         self.nn = nn
 
     def dump_stats(self):
-        print("num of prediction calls", self.num_predictions_calls)
-        print("predictions", self.total_predictions)
-        print("acc_time_polling", self.acc_time_polling)
-        print("acc_time_prediction", self.acc_time_prediction)
+        for label, v in (("num of prediction calls", self.num_predictions_calls),
+                         ("predictions", self.total_predictions),
+                         ("acc_time_polling", self.acc_time_polling),
+                         ("acc_time_prediction", self.acc_time_prediction)):
+            print(label, v)
 
 
 class PlayPoller(PollerBase):
-    """``src/ggpzero/util/cppinterface.py:156-182``."""
+    """Match play: a ``ggpzero_interface.Player`` behind the poll loop (``cppinterface.py:156-182``); the
+    ``player_*`` methods of the engine object are re-exported on the poller."""
+    _FORWARDED = ("reset", "apply_move", "move", "get_move", "update_config", "balance_moves", "tree_debug")
 
     def __init__(self, sm, nn, conf, **engine_kwds):
         import attr
@@ -108,25 +109,24 @@ class PlayPoller(PollerBase):
         super().__init__(sm, nn, batch_size=conf.batch_size)
         self.c_transformer = create_c_transformer(nn.gdl_bases_transformer)
         self.c_player = ggpzero_interface.Player(sm, self.c_transformer, attr.asdict(conf), **engine_kwds)
-        for name in "reset apply_move move get_move update_config balance_moves tree_debug".split():
-            name = "player_" + name
-            setattr(self, name, getattr(self.c_player, name))
+        for suffix in self._FORWARDED:
+            setattr(self, "player_" + suffix, getattr(self.c_player, "player_" + suffix))
 
     def _get_poller(self):
         return self.c_player
 
 
 class Supervisor(PollerBase):
-    """``src/ggpzero/util/cppinterface.py:185-226``."""
+    """Self-play: a ``ggpzero_interface.Supervisor`` behind the poll loop (``cppinterface.py:185-226``)."""
 
     def __init__(self, sm, nn, batch_size=1024, sleep_between_poll=-1, workers=None, identifier="",
                  **engine_kwds):
+        super().__init__(sm, nn, batch_size=batch_size, sleep_between_poll=sleep_between_poll)
         self.c_transformer = create_c_transformer(nn.gdl_bases_transformer)
         self.c_supervisor = ggpzero_interface.Supervisor(sm, self.c_transformer, batch_size, identifier,
                                                          **engine_kwds)
         if workers:
             self.c_supervisor.set_num_workers(workers)
-        super().__init__(sm, nn, batch_size=batch_size, sleep_between_poll=sleep_between_poll)
 
     def _get_poller(self):
         return self.c_supervisor
@@ -139,13 +139,10 @@ class Supervisor(PollerBase):
 
     def fetch_samples(self):
         from .defs import datadesc
-        res = self.c_supervisor.fetch_samples()
-        if res:
-            return [datadesc.Sample(**d) for d in res]
-        return []
+        return [datadesc.Sample(**d) for d in (self.c_supervisor.fetch_samples() or [])]
 
     def add_unique_state(self, s):
-        return      # the reference returns before doing anything as well (cppinterface.py:218-219)
+        """A no-op, as in the reference's wrapper (it returns before doing anything, cppinterface.py:218-219)."""
 
     def clear_unique_states(self):
         self.c_supervisor.clear_unique_states()
