@@ -537,7 +537,7 @@ def run_puct(args, rank, world, local):
             return (n_req, arrs)
 
         pred = (0, [])
-        for _ in range(min(args.presteps, 600)):
+        for _ in range(min(args.presteps, 2000) * len(sup.managers)):     # games desynchronise before timing
             pred = e2e_step(pred)
         m0 = sup.totals()
         h2d = d2h = 0
