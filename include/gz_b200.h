@@ -18,6 +18,11 @@
  *   gz_sm_playout_step           the random playout loop of GdlBasesTransformer.test
  *                                (src/cpp/pyobjects/gdltransformer_impl.cpp:50-124), one ply per call
  *   gz_sm_transition_host        same as gz_sm_transition with host buffers (copies inside)
+ *   gz_transformer_* / gz_encode GdlBasesTransformer and toChannels (src/cpp/gdltransformer.cpp:14-52)
+ *   gz_puct_*                    Supervisor / Player: create, advance (device tensors), host_poll_submit / _wait
+ *                                (numpy poll contract), fetch_samples, command / snapshot (src/cpp/supervisor.cpp,
+ *                                src/cpp/player.cpp, src/cpp/pyobjects/*.cpp)
+ *   gz_permute_state_bits        Translator.translate_basestate, batched (src/ggpzero/util/symmetry.py:153-204)
  */
 #ifndef GZ_B200_H
 #define GZ_B200_H
