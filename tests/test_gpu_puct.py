@@ -129,3 +129,36 @@ def test_selfplay_at_scale_properties():
         assert abs(sum(p for _, p in lead_pol) - 1.0) < 1e-3
         assert all(-0.06 <= x <= 1.06 for x in s['final_score'])
         assert len(s['state']) == 130 and 0 <= s['depth'] <= s['game_length'] <= 64
+
+
+def test_async_advance_matches_joined_advance():
+    """gz_puct_advance_async + gz_puct_join (the network call overlaps the step's side-stream work: re-rooting,
+    goal values and nodes of terminal states) leaves the engine in exactly the state the joined gz_puct_advance
+    does — same counters, same sample records, same trees."""
+    from galvanise_zero_b200.engine import PuctEngine
+    sp = confs.selfplay_config_template(evals_per_move=24)
+    sp.puct_config.dirichlet_noise_pct = -1
+    sp.run_to_end_puct_config.dirichlet_noise_pct = -1
+    a = PuctEngine('reversi', sp, n_games=192, mode=0, node_cap=1024, child_cap=1024 * 16, seed=77)
+    b = PuctEngine('reversi', sp, n_games=192, mode=0, node_cap=1024, child_cap=1024 * 16, seed=77)
+    a.advance(None, None)
+    a.synth_nn(seed=3)
+    b.advance(None, None, defer_join=True)
+    b.synth_nn(seed=3)
+    b.join()
+    for _ in range(2600):
+        a.advance(a.policy, a.value)
+        a.synth_nn(seed=3)
+        b.advance(b.policy, b.value, defer_join=True)
+        b.synth_nn(seed=3)          # runs while the side stream finishes the step
+        b.join()
+    ta, tb = a.totals(), b.totals()
+    assert ta == tb and ta['moves'] > 1000 and ta['games'] > 0 and ta['errors'] == 0
+    ra, rb = a.fetch_sample_records(), b.fetch_sample_records()
+    # records are appended with an atomic counter: same set, order depends on warp scheduling
+    key = lambda r: [tuple(x) for x in r[np.lexsort(r.T[::-1])]]   # noqa: E731
+    assert len(ra) > 0 and len(ra) == len(rb) and key(ra) == key(rb)
+    for g in (0, 57, 191):
+        sa, sb = a.snapshot(g), b.snapshot(g)
+        assert np.array_equal(sa['traversals'], sb['traversals']) and np.array_equal(sa['moves'], sb['moves'])
+        assert sa['nodes'] == sb['nodes'] and sa['root_visits'] == sb['root_visits']
