@@ -301,8 +301,8 @@ def run_propnet(args, rank, world, local):
 
 # ------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of one puct_pre_kernel launch in the bench configuration
-# (ncu --set full capture, profiles/r01_puct_pre_kernel_ncu_full.md)
-PUCT_PRE_NCU_TRAFFIC_BYTES = 56526592
+# (ncu --set full capture, profiles/r01c_puct_pre_kernel_ncu_full.md)
+PUCT_PRE_NCU_TRAFFIC_BYTES = 57936896
 PUCT_GAME = 'reversi'
 PUCT_GAMES_PER_GPU = 4096
 PUCT_EVALS_PER_MOVE = 800
@@ -450,7 +450,7 @@ def run_puct(args, rank, world, local):
                 'mean_path_nodes_per_eval': d_nodes / d_ev, 'mean_children_scanned_per_eval': d_children / d_ev,
                 'mean_children_created_per_eval': d_new / d_ev,
                 'launch_ms': parts['puct_pre_kernel_ms'], 'peak_source': peaks['source'] + ' (HBM copy)',
-                'traffic_source': 'ncu --set full, profiles/r01_puct_pre_kernel_ncu_full.md (dram read+write per launch)'}
+                'traffic_source': 'ncu --set full, profiles/r01c_puct_pre_kernel_ncu_full.md (dram read+write per launch)'}
     flops = net.flops_per_position * Gp
     nn_s = parts['network_forward_ms'] * 1e-3
     nn_ach = flops / nn_s / 1e12
