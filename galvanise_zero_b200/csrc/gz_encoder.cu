@@ -105,7 +105,7 @@ encode_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint
     }
 }
 
-// Fast path (rows of a multiple of 8 elements — every shipped game but hexLG13 in NCHW): the per-element
+// Fast path (any row size whose staging fits in shared memory): the per-element
 // decisions (which base bit, current or previous state, which control channel) do not depend on the
 // state, so a CTA resolves them ONCE into a descriptor table in shared memory and then streams states
 // through it: per 8 output elements one descriptor read each, a bit test on the state words staged in
@@ -114,16 +114,16 @@ encode_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint
 #define ENCF_THREADS 256
 // descriptor: kind in bits 30-31 (0 zero, 1 bit of the state, 2 bit of the OR of previous states,
 // 3 control channel), payload in bits 0-29 (base index / control channel)
-template <typename OutT>
+template <typename OutT, bool STRADDLE /* rows are not a multiple of 8 elements: vectors may span two states */>
 __global__ void __launch_bounds__(ENCF_THREADS)
 encode_fast_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint32_t* __restrict__ states,
                    const uint32_t* __restrict__ prev, const uint8_t* __restrict__ prev_count, int max_prev,
-                   OutT* __restrict__ out, int c_pad, int row_elems) {
+                   OutT* __restrict__ out, int c_pad, int row_elems, int spb /* states per block iteration, multiple of 8 */) {
     extern __shared__ __align__(16) uint32_t fsm[];
     uint32_t* desc = fsm;                                       // [row_elems]
-    uint32_t* cur = desc + row_elems;                           // [ENCF_STATES][sw]
-    uint32_t* por = cur + ENCF_STATES * sw;                     // [ENCF_STATES][sw]
-    uint32_t* ctrl = por + ENCF_STATES * sw;                    // [ENCF_STATES][nc] output bit patterns
+    uint32_t* cur = desc + row_elems;                           // [spb][sw]
+    uint32_t* por = cur + spb * sw;                     // [spb][sw]
+    uint32_t* ctrl = por + spb * sw;                    // [spb][nc] output bit patterns
     const int nc = E.num_control_channels;
     const int n_ch = E.total / E.channel_size;
     const bool has_prev = prev && E.num_prev_states > 0;
@@ -148,10 +148,9 @@ encode_fast_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const
         }
         desc[le0] = d;
     }
-    const int row_vecs = row_elems >> 3;
     constexpr uint32_t ONE = sizeof(OutT) == 2 ? 0x3F80u : 0x3F800000u;
-    for (int64_t n0 = (int64_t)blockIdx.x * ENCF_STATES; n0 < n; n0 += (int64_t)gridDim.x * ENCF_STATES) {
-        const int nb = (int)((n - n0) < ENCF_STATES ? (n - n0) : ENCF_STATES);
+    for (int64_t n0 = (int64_t)blockIdx.x * spb; n0 < n; n0 += (int64_t)gridDim.x * spb) {
+        const int nb = (int)((n - n0) < spb ? (n - n0) : spb);
         __syncthreads();
         for (int i = threadIdx.x; i < nb * sw; i += ENCF_THREADS) {
             const int s = i / sw, w = i - s * sw;
@@ -170,23 +169,28 @@ encode_fast_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const
             ctrl[i] = sizeof(OutT) == 2 ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)) : __float_as_uint(v);
         }
         __syncthreads();
-        const int items = nb * row_vecs;
+        // the block's rows are one contiguous run of nb * row_elems elements starting at a 16-byte boundary
+        // (n0 is a multiple of 8): 8-element vectors over that run, a vector may straddle two states
+        const int flat_n = nb * row_elems;
+        const int items = flat_n >> 3;
         for (int w = threadIdx.x; w < items; w += ENCF_THREADS) {
-            const int s = w / row_vecs, vi = w - s * row_vecs;
-            const uint32_t* cs = cur + s * sw;
-            const uint32_t* ps = por + s * sw;
+            int s = (w * 8) / row_elems;
+            int le = w * 8 - s * row_elems;
             uint32_t v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t d = desc[vi * 8 + k];
+                const uint32_t* cs = cur + s * sw;
+                const uint32_t* ps = por + s * sw;
+                const uint32_t d = desc[STRADDLE ? le : le + k];
                 const uint32_t kind = d >> 30, pl = d & 0x3FFFFFFFu;
                 uint32_t x = 0u;
                 if (kind == 1u) x = ((cs[pl >> 5] >> (pl & 31)) & 1u) ? ONE : 0u;
                 else if (kind == 2u) x = ((ps[pl >> 5] >> (pl & 31)) & 1u) ? ONE : 0u;
                 else if (kind == 3u) x = ctrl[s * nc + pl];
                 v[k] = x;
+                if (STRADDLE) { if (++le == row_elems) { le = 0; ++s; } }
             }
-            OutT* dst = out + (n0 + s) * (int64_t)row_elems + vi * 8;
+            OutT* dst = out + n0 * (int64_t)row_elems + (int64_t)w * 8;
             if (sizeof(OutT) == 2) {
                 *reinterpret_cast<uint4*>(dst) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16),
                                                             v[4] | (v[5] << 16), v[6] | (v[7] << 16));
@@ -194,6 +198,18 @@ encode_fast_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const
                 reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
                 reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
             }
+        }
+        // fewer than 8 elements can remain at the end of the batch's last block
+        for (int e = (items << 3) + threadIdx.x; e < flat_n; e += ENCF_THREADS) {
+            const int s = e / row_elems, le = e - s * row_elems;
+            const uint32_t d = desc[le];
+            const uint32_t kind = d >> 30, pl = d & 0x3FFFFFFFu;
+            uint32_t x = 0u;
+            if (kind == 1u) x = ((cur[s * sw + (pl >> 5)] >> (pl & 31)) & 1u) ? ONE : 0u;
+            else if (kind == 2u) x = ((por[s * sw + (pl >> 5)] >> (pl & 31)) & 1u) ? ONE : 0u;
+            else if (kind == 3u) x = ctrl[s * nc + pl];
+            if (sizeof(OutT) == 2) reinterpret_cast<uint16_t*>(out)[n0 * (int64_t)row_elems + e] = (uint16_t)x;
+            else reinterpret_cast<uint32_t*>(out)[n0 * (int64_t)row_elems + e] = x;
         }
     }
 }
@@ -327,21 +343,26 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
     GZ_CUDA(cudaSetDevice(t->device));
     {
         const int row_elems = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
-        const size_t fsmem = ((size_t)row_elems + (size_t)ENCF_STATES * (2 * state_words + t->num_control_channels)) * 4 + 16;
-        if ((row_elems & 7) == 0 && fsmem <= 200 * 1024 && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32)) {
-            const int64_t blocks = (n + ENCF_STATES - 1) / ENCF_STATES;
+        int spb = ENCF_STATES;                 // (states of hexLG13's size do not fit: generic kernel)
+        auto need = [&](int k) { return ((size_t)row_elems + (size_t)k * (2 * state_words + t->num_control_channels)) * 4 + 16; };
+        const size_t fsmem = need(spb);
+        const bool straddle = (row_elems & 7) != 0;
+        if (fsmem <= 200 * 1024 && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32)) {
+            const int64_t blocks = (n + spb - 1) / spb;
             const int grid = (int)std::min<int64_t>(blocks, (int64_t)t->n_sms * 8);
+#define GZ_ENCF_LAUNCH(T, ST)                                                                                   \
+    do {                                                                                                        \
+        if (fsmem > 48 * 1024)                                                                                  \
+            GZ_CUDA(cudaFuncSetAttribute(encode_fast_kernel<T, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+        encode_fast_kernel<T, ST><<<grid, ENCF_THREADS, fsmem, (cudaStream_t)stream>>>(                            \
+            t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (T*)d_out, c_pad, row_elems, spb);  \
+    } while (0)
             if (out_dtype == GZ_DTYPE_BF16) {
-                if (fsmem > 48 * 1024)
-                    GZ_CUDA(cudaFuncSetAttribute(encode_fast_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                encode_fast_kernel<__nv_bfloat16><<<grid, ENCF_THREADS, fsmem, (cudaStream_t)stream>>>(
-                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (__nv_bfloat16*)d_out, c_pad, row_elems);
+                if (straddle) GZ_ENCF_LAUNCH(__nv_bfloat16, true); else GZ_ENCF_LAUNCH(__nv_bfloat16, false);
             } else {
-                if (fsmem > 48 * 1024)
-                    GZ_CUDA(cudaFuncSetAttribute(encode_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                encode_fast_kernel<float><<<grid, ENCF_THREADS, fsmem, (cudaStream_t)stream>>>(
-                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (float*)d_out, c_pad, row_elems);
+                if (straddle) GZ_ENCF_LAUNCH(float, true); else GZ_ENCF_LAUNCH(float, false);
             }
+#undef GZ_ENCF_LAUNCH
             GZ_CUDA(cudaGetLastError());
             return GZ_OK;
         }
