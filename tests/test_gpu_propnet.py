@@ -96,11 +96,12 @@ def test_wide_games_playout_bit_exact(game, n, steps):
         assert np.array_equal(_np(a), b)
 
 
-@pytest.mark.parametrize('n', [1, 33, 1000, 1024, 5000])
-def test_specialised_kernel_bit_exact(n):
-    """The generated thread-sliced kernel of breakthrough (csrc/gz_spec_breakthrough.cu), forced on for small
+@pytest.mark.parametrize('game,n', [('breakthrough', 1), ('breakthrough', 33), ('breakthrough', 1000),
+                                    ('breakthrough', 1024), ('breakthrough', 5000),
+                                    ('breakthroughSmall', 33), ('breakthroughSmall', 3000)])
+def test_specialised_kernel_bit_exact(game, n):
+    """The generated thread-sliced kernels (csrc/gz_spec_<game>.cu), forced on for small
     batches: playout / transition / eval bit-exact with the C oracle, ragged tails included."""
-    game = 'breakthrough'
     dev = _sm(game)
     assert dev.specialised, 'device program hash does not match the generated kernel: rerun tools/gen_spec_kernel.py'
     dev.set_spec_min_batch(0)
