@@ -8,10 +8,16 @@ Under torchrun (N>1) every rank owns a disjoint range of game slots (no data-pat
 the launching stream, max over ranks. Rank 0 prints ONE JSON line.
 
 Workloads
+  puct     (default) BASELINE config "Reversi 8x8 PUCT self-play, 800 evals/move, small residual net,
+           4096 concurrent games per GPU". One bench step = --advances-per-step (256) engine advances,
+           each followed by one network forward over the leaves, so that the timed region lasts seconds.
+           Every slot's first game starts a uniformly random number of random plies into a game and the
+           run is warmed up (--presteps advances), so the games sit at all plies at once as they do in
+           a long-running job; the reference arm and the in-line CPU baseline get the same treatment.
+           The line also carries BASELINE's first metric under "propnet" (the propnet workload below,
+           measured in the same run on the same GPUs).
   propnet  BASELINE config "Breakthrough 8x8 propnet: batched uniform-random playouts": one step =
            one playout ply over all slots (one launch of the fused choose+transition kernel).
-  puct     BASELINE config "Reversi 8x8 PUCT self-play, 800 evals/move, small residual net,
-           4096 concurrent games per GPU" (see galvanise_zero_b200/selfplay.py).
 """
 import argparse
 import json
@@ -152,16 +158,18 @@ def cpu_baseline_propnet(game, seconds_target=12.0, threads=None):
                           game, slots, steps, threads, secs)}
 
 
-def run_propnet(args, rank, world, local):
+def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
+    """Returns the propnet line (rank 0) or None. `steps` = playout launches in the timed region."""
     import numpy as np
     import torch
     from galvanise_zero_b200.statemachine import DeviceStateMachine
     from galvanise_zero_b200 import lib as gzlib
 
     peaks = load_peaks()
-    game = args.game or PROPNET_GAME
+    steps = steps or args.steps
+    game = (args.game if args.workload == 'propnet' else '') or PROPNET_GAME
     dev = DeviceStateMachine(game, device=local, goals_mode=gzlib.GOALS_ALWAYS)
-    n = args.slots or PROPNET_SLOTS
+    n = (args.slots if args.workload == 'propnet' else 0) or PROPNET_SLOTS
     slot0 = rank * n
     s = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
     l, t, g = dev.alloc_views(n)
@@ -181,7 +189,7 @@ def run_propnet(args, rank, world, local):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         dev.playout_step(s, l, t, g, seed, step, slot0=slot0, counter=cnt)
         step += 1
     ev1.record()
@@ -195,7 +203,7 @@ def run_propnet(args, rank, world, local):
     # ---- roofline of the dominant kernel (pn_kernel<PLAYOUT>): algorithmic bytes / launch time
     tb = transition_bytes(dev)
     per_launch_bytes = tb * n
-    launch_s = (ms * 1e-3) / args.steps
+    launch_s = (ms * 1e-3) / steps
     achieved = per_launch_bytes / launch_s / 1e9
     spec = dev.specialised and n >= (1 << 18)
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
@@ -233,7 +241,7 @@ def run_propnet(args, rank, world, local):
         hs_np, hm_np = hs.numpy().view(np.uint32), hm.numpy()
         for _ in range(2):
             dev.transition_host(hs_np, hm_np, out=out)
-        reps = max(3, min(args.steps, 10))
+        reps = 10
         barrier(world)
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -278,13 +286,16 @@ def run_propnet(args, rank, world, local):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_propnet(game)
+        cpu = cpu_baseline_propnet(game, seconds_target=cpu_seconds)
+    del s, l, t, g
+    torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
             'metric': 'propnet transitions/sec', 'value': value, 'unit': 'transitions/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'n_gpus': world, 'steps': steps, 'warmup': args.warmup,
+            'ms_per_step': ms_max / steps, 'timed_region_s': ms_max * 1e-3,
+            'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u32', 'data': 'synthetic',
             'config': {'workload': '%s propnet, batched uniform-random playouts' % (
                            'breakthrough 8x8' if game == 'breakthrough' else game),
@@ -293,9 +304,10 @@ def run_propnet(args, rank, world, local):
                        'parallelism': 'games sharded across %d GPU(s), no collective' % world,
                        'launch': dev.launch_info},
             'roofline': roofline, 'encoder_roofline': encoder, 'cpu_baseline': cpu, 'e2e': e2e,
-            'gpu_launches': args.steps, 'clocks': clocks,
+            'gpu_launches': steps, 'clocks': clocks,
         }
-        print(json.dumps(line), flush=True)
+        return line
+    return None
 
 
 
@@ -303,11 +315,35 @@ def run_propnet(args, rank, world, local):
 # dram__bytes_read.sum + dram__bytes_write.sum of one puct_pre_kernel launch in the bench configuration
 # (ncu --set full capture, profiles/r01c_puct_pre_kernel_ncu_full.md)
 PUCT_PRE_NCU_TRAFFIC_BYTES = 57936896
+PUCT_PRE_NCU_TRAFFIC_SOURCE = 'ncu --set full, profiles/r01c_puct_pre_kernel_ncu_full.md (dram read+write per launch)'
 PUCT_GAME = 'reversi'
-PUCT_GAMES_PER_GPU = 4096
 PUCT_EVALS_PER_MOVE = 800
-PUCT_WORKLOAD = ('reversi 8x8 PUCT self-play, 800 evals/move, small residual net (64f x 5), '
-                 '4096 concurrent games per GPU')
+# per game: concurrent games per GPU, tree arena sizes, and the ply range the slots' first games are spread over
+# (about the length of a uniformly random game, so that the slots sit at all plies at once)
+PUCT_PRESETS = {
+    'reversi': dict(games=4096, node_cap=4096, child_cap=4096 * 16, stagger_plies=58,
+                    workload='reversi 8x8 PUCT self-play, 800 evals/move, small residual net (64f x 5), '
+                             '4096 concurrent games per GPU'),
+    'breakthrough': dict(games=4096, node_cap=4096, child_cap=4096 * 24, stagger_plies=50,
+                         workload='breakthrough 8x8 PUCT self-play, 800 evals/move, small residual net'),
+    'hexLG13': dict(games=1024, node_cap=4096, child_cap=4096 * 96, stagger_plies=100,
+                    workload='hexLG13 (13x13, swap rule) PUCT self-play, 800 evals/move, small residual net, '
+                             '1024 concurrent games per GPU'),
+    'connect6': dict(games=1024, node_cap=4096, child_cap=4096 * 128, stagger_plies=60,
+                     workload='connect6 19x19 PUCT self-play, 800 evals/move, small residual net'),
+    'amazons_10x10': dict(games=512, node_cap=4096, child_cap=4096 * 512, stagger_plies=50,
+                          workload='amazons 10x10 PUCT self-play, 800 evals/move, small residual net'),
+    'chess_15d': dict(games=1024, node_cap=4096, child_cap=4096 * 32, stagger_plies=60,
+                      workload='chess (15-move draw rule) PUCT self-play, 800 evals/move, small residual net, '
+                               '1024 concurrent games per GPU'),
+}
+CPU_BATCH = 8          # games per reference manager (2 managers per worker thread) in the CPU arms
+CPU_WARM_S = 5.0       # the CPU arms' untimed warm-up
+CPU_WINDOW_S = 20.0    # ... and their timed window (one bounded sample)
+
+
+def puct_game(args):
+    return (args.game if args.workload == 'puct' else '') or PUCT_GAME
 
 
 def puct_selfplay_conf():
@@ -315,27 +351,49 @@ def puct_selfplay_conf():
     return confs.selfplay_config_template(evals_per_move=PUCT_EVALS_PER_MOVE)
 
 
-def cpu_reference_selfplay(seconds=14.0, warm=3.0, threads=None, batch=32):
+def cpu_reference_selfplay(game=PUCT_GAME, seconds=CPU_WINDOW_S, warm=CPU_WARM_S, threads=None, batch=CPU_BATCH,
+                           rng_seed=0x5EED0000):
     """The reference's own C++ PUCT self-play (oracle/_ref: Supervisor worker mode, N threads x 2
     managers x `batch` games, src/cpp/supervisor.cpp:79-99) on the host cores, network replaced by
     the synthetic hash network so that it measures propnet + PUCT + encode (the reference's
-    acc_time_polling notion)."""
-    from galvanise_zero_b200 import bases, cppinterface, lookup, tables
-    from galvanise_zero_b200.defs import datadesc
-    from oracle import gzref
+    acc_time_polling notion). Same regime as the GPU arm: every slot's first game starts a uniformly random
+    number of random plies into a game, then `warm` seconds untimed, then the window. Runs in a child
+    process (the reference's worker threads cannot be stopped, supervisor.cpp:34-40)."""
     threads = threads or max(1, (os.cpu_count() or 2) - 1)
-    gi = lookup.by_name(PUCT_GAME)
-    tr = bases.GdlBasesTransformer(gi, datadesc.generation_for(PUCT_GAME))
-    ct = cppinterface.create_c_transformer(tr)
-    eng = gzref.RefEngine(tables.blob_by_name(PUCT_GAME), ct)
-    st = eng.selfplay(puct_selfplay_conf(), batch, threads, max_seconds=seconds, warm_seconds=warm)
+    code = (
+        'import json, sys\n'
+        'sys.path.insert(0, %r)\n'
+        'from galvanise_zero_b200 import bases, cppinterface, lookup, tables\n'
+        'from galvanise_zero_b200.defs import datadesc, confs\n'
+        'from oracle import gzref\n'
+        'game = %r\n'
+        'tr = bases.GdlBasesTransformer(lookup.by_name(game), datadesc.generation_for(game))\n'
+        'ct = cppinterface.create_c_transformer(tr)\n'
+        'eng = gzref.RefEngine(tables.blob_by_name(game), ct)\n'
+        'sp = confs.selfplay_config_template(evals_per_move=%d)\n'
+        'st = eng.selfplay(sp, %d, %d, max_seconds=%r, warm_seconds=%r, stagger_max_ply=%d, rng_seed=%d)\n'
+        'st.pop("records", None)\n'
+        'print("GZREF " + json.dumps(st), flush=True)\n'
+        'import os; os._exit(0)\n'
+    ) % (ROOT, game, PUCT_EVALS_PER_MOVE, batch, threads, seconds + warm, warm,
+         PUCT_PRESETS[game]['stagger_plies'], rng_seed)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=seconds + warm + 240)
+    st = None
+    for ln in out.stdout.splitlines():
+        if ln.startswith('GZREF '):
+            st = json.loads(ln[6:])
+    if st is None:
+        raise RuntimeError('reference self-play failed: %s' % (out.stderr[-400:] or out.stdout[-400:]))
     w = max(st['window_seconds'], 1e-9)
     return {'value': st['window_moves'] / w, 'unit': 'moves/s', 'cores': threads + 1, 'kind': 'reference',
-            'evals_per_s': st['window_evals'] / w,
+            'evals_per_s': st['window_evals'] / w, 'window_s': w, 'window_moves': st['window_moves'],
             'sample': '%s, reference C++ (puct/evaluator.cpp, selfplay.cpp, supervisor.cpp compiled unmodified '
                       'against shims) in worker mode: %d worker threads x 2 managers x %d games, %d evals/move, '
-                      'synthetic network, %.1f s window after %.1f s warm-up'
-                      % (PUCT_GAME, threads, batch, PUCT_EVALS_PER_MOVE, w, warm)}
+                      'synthetic network; slots start at staggered plies (uniform in [0, %d)), %.1f s window after '
+                      '%.1f s warm-up. The reference search never returns from a fully explored, unconverged '
+                      'end-game tree (evaluator.cpp:782-841), which stalls its manager: its rate decays with '
+                      'the length of the run, so both CPU arms use this same bounded sample'
+                      % (game, threads, batch, PUCT_EVALS_PER_MOVE, PUCT_PRESETS[game]['stagger_plies'], w, warm)}
 
 
 def time_region(fn, device):
@@ -349,34 +407,42 @@ def time_region(fn, device):
     return e0.elapsed_time(e1)
 
 
-def run_puct(args, rank, world, local):
+def run_puct(args, rank, world, local, propnet_line=None):
     import numpy as np
     import torch
     from galvanise_zero_b200.engine import PuctEngine
     from galvanise_zero_b200.nn import make_inference_network
-    from galvanise_zero_b200.selfplay import SelfPlayPool, StaggeredSelfPlay
+    from galvanise_zero_b200.selfplay import SelfPlayPool, StaggeredSelfPlay, staggered_start_states
     from galvanise_zero_b200 import distributed as gzdist
 
     peaks = load_peaks()
     torch.cuda.set_device(local)
-    G = args.slots or PUCT_GAMES_PER_GPU
+    game = puct_game(args)
+    preset = PUCT_PRESETS[game]
+    G = args.slots or preset['games']
     sp = puct_selfplay_conf()
     P = max(1, args.pipelines)
     Gp = G // P
-    engines = [PuctEngine(PUCT_GAME, sp, n_games=G // P, mode=0, device=local,
-                          seed=gzdist.rank_seed(0xB200, rank) + 104729 * k, node_cap=4096, child_cap=4096 * 16,
-                          plane_c_pad=16)
+    K = max(1, args.advances_per_step)
+    engines = [PuctEngine(game, sp, n_games=Gp, mode=0, device=local,
+                          seed=gzdist.rank_seed(0xB200, rank) + 104729 * k, node_cap=preset['node_cap'],
+                          child_cap=preset['child_cap'], plane_c_pad=16 if game == PUCT_GAME else 0)
                for k in range(P)]
     eng = engines[0]
+    # every slot's first game starts a uniformly random number of random plies into a game
+    if not args.no_stagger:
+        for k, e in enumerate(engines):
+            e.set_start_states(staggered_start_states(e.sm, Gp, preset['stagger_plies'], seed=0xB200 + rank,
+                                                      slot0=(rank * P + k) * Gp))
     net = make_inference_network(eng.transformer, 'small', seed=1234, device=eng.device)
     if P > 1:
         # several shards: engine graphs on their own streams, network graphs serialised on one
         runner = StaggeredSelfPlay(engines, net, sub_iters=args.sub_iters)
     else:
         runner = SelfPlayPool(engines, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph)
-    # bring the games to a desynchronised steady state (untimed), then warm up
+    # untimed: let the trees grow and the searches desynchronise, then the contract's warm-up steps
     runner.step(args.presteps)
-    runner.step(args.warmup)
+    runner.step(args.warmup * K)
     barrier(world)
     t_before = runner.totals()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -385,7 +451,7 @@ def run_puct(args, rank, world, local):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     ev0.record()
-    runner.step(args.steps)
+    runner.step(args.steps * K)
     ev1.record()
     barrier(world)
     ms = ev0.elapsed_time(ev1)
@@ -393,17 +459,24 @@ def run_puct(args, rank, world, local):
     t_after = runner.totals()
     d_moves = t_after['moves'] - t_before['moves']
     d_evals = t_after['evals'] - t_before['evals']
+    d_playouts = t_after['playouts'] - t_before['playouts']
     ms_max = all_max(ms, world, eng.device)
     moves = all_sum(d_moves, world, eng.device)
     evals = all_sum(d_evals, world, eng.device)
     value = moves / (ms_max * 1e-3)
+    advances = args.steps * K
+    regime = {'mean_ply_start': t_before['depth_sum'] / G, 'mean_ply_end': t_after['depth_sum'] / G,
+              'nn_batch_fill': d_evals / max(1.0, float(advances) * G),
+              'playouts_per_eval': d_playouts / max(d_evals, 1.0),
+              'games_finished_in_window': t_after['games'] - t_before['games'],
+              'games_finished_total': t_after['games']}
 
-    # ---- per-kernel timing, eager, CUDA events on the launching stream: 40 engine steps with events
+    # ---- per-kernel timing, eager, CUDA events on the launching stream: engine steps with events
     # between the launches (gz_puct_advance_timed), each followed by the real network forward so that the
     # trees keep evolving; the same steps give the algorithmic bytes from the engine's traffic counters
     parts = {}
     with torch.no_grad():
-        reps = 40
+        reps = 200
         acc = {}
         t0c = eng.totals()
         pol, val = net(eng.planes)
@@ -429,7 +502,7 @@ def run_puct(args, rank, world, local):
         with torch.cuda.graph(g_nn):
             net(x)
         g_nn.replay()
-        parts['network_forward_ms'] = time_region(lambda: [g_nn.replay() for _ in range(10)], eng.device) / 10
+        parts['network_forward_ms'] = time_region(lambda: [g_nn.replay() for _ in range(50)], eng.device) / 50
     # roofline of the dominant hand-written kernel, puct_pre_kernel (select + reply + backup + controller):
     # algorithmic bytes per evaluation = sum over path nodes of (32 B node record +
     # 24 B per child scanned) + 24 B per path node written by backup + 20 B per child created
@@ -442,7 +515,8 @@ def run_puct(args, rank, world, local):
     pre_s = parts['puct_pre_kernel_ms'] * 1e-3
     achieved = per_launch / pre_s / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': achieved / peaks['hbm_gbs'], 'traffic': PUCT_PRE_NCU_TRAFFIC_BYTES,
+                'frac': achieved / peaks['hbm_gbs'],
+                'traffic': PUCT_PRE_NCU_TRAFFIC_BYTES if (game == PUCT_GAME and Gp == 4096) else None,
                 'kernel': 'puct_pre_kernel (one warp per game tree: reply + backup + controller + select; '
                           'dependent pointer chasing over a %.1f GB arena, latency-bound)' % (eng.arena_bytes / 1e9),
                 'bytes_per_unit': alg_bytes / d_ev, 'unit_name': 'evaluation', 'units_per_launch': d_ev / reps,
@@ -450,7 +524,7 @@ def run_puct(args, rank, world, local):
                 'mean_path_nodes_per_eval': d_nodes / d_ev, 'mean_children_scanned_per_eval': d_children / d_ev,
                 'mean_children_created_per_eval': d_new / d_ev,
                 'launch_ms': parts['puct_pre_kernel_ms'], 'peak_source': peaks['source'] + ' (HBM copy)',
-                'traffic_source': 'ncu --set full, profiles/r01c_puct_pre_kernel_ncu_full.md (dram read+write per launch)'}
+                'traffic_source': PUCT_PRE_NCU_TRAFFIC_SOURCE}
     flops = net.flops_per_position * Gp
     nn_s = parts['network_forward_ms'] * 1e-3
     nn_ach = flops / nn_s / 1e12
@@ -473,8 +547,12 @@ def run_puct(args, rank, world, local):
         # batch_size games each; the engine step of one overlaps the network call on the other's batch.
         # Supervisor(batch_size = G/2) + one worker therefore holds the configured G concurrent games.
         inline = args.e2e_inline
-        sup = interface.Supervisor(PUCT_GAME, eng.c_transformer, G if inline else G // 2, 'bench', device=local,
-                                   seed=0xE2E + rank, node_cap=2048, child_cap=2048 * 16)
+        sup = interface.Supervisor(game, eng.c_transformer, G if inline else G // 2, 'bench', device=local,
+                                   seed=0xE2E + rank, node_cap=max(1024, preset['node_cap'] // 2),
+                                   child_cap=max(1024, preset['child_cap'] // 2))
+        if not args.no_stagger:
+            sup.start_states_fn = lambda e, k: staggered_start_states(
+                e.sm, e.n_games, preset['stagger_plies'], seed=0xE2E + rank, slot0=(2 * rank + k) * e.n_games)
         sup.start_self_play(0 if inline else 1, attr.asdict(sp))
         R = len(eng.role_sizes)
         h2d = d2h = 0
@@ -537,12 +615,14 @@ def run_puct(args, rank, world, local):
             return (n_req, arrs)
 
         pred = (0, [])
-        for _ in range(min(args.presteps, 2000) * len(sup.managers)):     # games desynchronise before timing
+        n_man = len(sup.managers)
+        for _ in range(min(args.presteps, 2000) * n_man):     # trees grow, searches desynchronise (untimed)
             pred = e2e_step(pred)
+        # as many polls as the device loop ran advances (per manager), i.e. seconds of wall clock
+        reps = max(200, args.steps * K // 2) * n_man
         m0 = sup.totals()
         h2d = d2h = 0
         t_poll = t_nn = 0.0
-        reps = max(20, min(args.steps, 200)) * len(sup.managers)
         barrier(world)
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -552,78 +632,109 @@ def run_puct(args, rank, world, local):
         m1 = sup.totals()
         e2e_moves = all_sum(m1['moves'] - m0['moves'], world, eng.device)
         e2e_evals = all_sum(m1['evals'] - m0['evals'], world, eng.device)
-        e2e = {'value': e2e_moves / dt, 'unit': 'moves/s', 'h2d_bytes_per_step': int(h2d / reps) * len(sup.managers),
-               'd2h_bytes_per_step': int(d2h / reps) * len(sup.managers), 'evals_per_s': e2e_evals / dt,
+        Gs = Gm * n_man
+        e2e = {'value': e2e_moves / dt, 'unit': 'moves/s', 'h2d_bytes_per_step': int(h2d / reps) * n_man * K,
+               'd2h_bytes_per_step': int(d2h / reps) * n_man * K, 'evals_per_s': e2e_evals / dt,
+               'timed_region_s': dt, 'moves_in_window': e2e_moves,
+               'mean_ply_start': m0['depth_sum'] / Gs, 'mean_ply_end': m1['depth_sum'] / Gs,
                'api': 'interface.Supervisor.poll (numpy in / numpy out, reference contract), network fed from pinned host memory',
-               'managers': '%d x %d games (%s)' % (len(sup.managers), Gm, 'inline' if len(sup.managers) == 1 else
+               'managers': '%d x %d games (%s)' % (n_man, Gm, 'inline' if n_man == 1 else
                                                    'worker mode: engine step of one manager overlaps the network call of the other'),
-               'polls': reps, 'rows_per_poll': Gm, 'host_ms_per_poll': {'poll': t_poll * 1e3 / reps, 'network_call': t_nn * 1e3 / reps}}
+               'polls': reps, 'rows_per_poll': Gm, 'bytes_are': 'per bench step = %d polls of each manager' % K,
+               'host_ms_per_poll': {'poll': t_poll * 1e3 / reps, 'network_call': t_nn * 1e3 / reps}}
+        del sup
 
-    # ---- end of 'generation': gather the finished samples to rank 0 (the only collective; untimed)
+    # ---- end of 'generation': gather the finished samples to rank 0 over NCCL (the only collective), timed on its own
     recs = np.concatenate([e.fetch_sample_records() for e in engines], axis=0)
-    gathered = gzdist.gather_sample_records(torch.from_numpy(recs).to(eng.device), dst=0)
+    recs_dev = torch.from_numpy(recs).to(eng.device)
+    barrier(world)
+    tg0 = time.perf_counter()
+    gathered = gzdist.gather_sample_records(recs_dev, dst=0)
+    torch.cuda.synchronize(eng.device)
+    gather_s = all_max(time.perf_counter() - tg0, world, eng.device)
     n_gathered = int(gathered.shape[0]) if gathered is not None else 0
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_reference_selfplay()
+            cpu = cpu_reference_selfplay(game)
         except Exception as exc:   # oracle/_ref missing on this box
             cpu = {'value': None, 'unit': 'moves/s', 'cores': os.cpu_count(), 'kind': 'reference',
                    'sample': 'unavailable: %s' % exc}
 
     if rank == 0:
+        own_launches = advances * runner.kernels_per_step + (propnet_line['gpu_launches'] if propnet_line else 0)
         line = {
             'metric': 'PUCT self-play moves/sec', 'value': value, 'unit': 'moves/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'ms_per_step': ms_max / args.steps, 'timed_region_s': ms_max * 1e-3,
+            'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': PUCT_WORKLOAD, 'games_per_gpu': G, 'evals_per_move': PUCT_EVALS_PER_MOVE,
+            'config': {'workload': preset['workload'], 'games_per_gpu': G, 'evals_per_move': PUCT_EVALS_PER_MOVE,
                        'network': 'random-init small tower, %.1f MFLOP/position' % (net.flops_per_position / 1e6),
-                       'step': 'one engine advance (select/backup + propnet + expand + encode) + one network '
-                               'forward over %d leaves' % G,
+                       'step': '%d engine advances (select/backup + propnet + expand + encode), each followed by one '
+                               'network forward over %d leaves' % (K, G),
+                       'advances_per_step': K, 'ms_per_advance': ms_max / advances,
+                       'regime': 'slots start at staggered plies (uniform in [0, %d) random plies), %d untimed '
+                                 'advances, then the warm-up steps' % (preset['stagger_plies'], args.presteps)
+                                 if not args.no_stagger else 'all slots start at the initial state',
                        'l2': 'tree arenas %.1f GB per GPU >> 126 MB L2' % (sum(e.arena_bytes for e in engines) / 1e9),
                        'presteps': args.presteps, 'cuda_graph': not args.no_graph,
                        'pipelines': '%d engine+network pipelines of %d games each on separate streams' % (P, G // P),
                        'parallelism': 'games sharded across %d GPU(s), no collective on the hot path' % world},
-            'evals_per_s': evals / (ms_max * 1e-3), 'moves_in_window': moves,
+            'evals_per_s': evals / (ms_max * 1e-3), 'moves_in_window': moves, 'regime': regime,
             'roofline': roofline, 'network_roofline': network_roofline, 'kernel_times_ms': parts,
             'cpu_baseline': cpu, 'e2e': e2e,
-            'gpu_launches': args.steps * runner.kernels_per_step, 'clocks': clocks,
+            'gpu_launches': own_launches, 'clocks': clocks,
             'engine_totals': {k: t_after[k] for k in ('errors', 'halted', 'max_nodes', 'max_children', 'games', 'samples')},
-            'samples_gathered_to_rank0': n_gathered,
+            'sample_gather': {'records_on_rank0': n_gathered, 'record_bytes': int(recs.shape[1]) * 4 if recs.ndim == 2 else 0,
+                              'seconds': gather_s, 'collective': 'all_gather of counts + all_gather of padded records (NCCL)'},
+            'propnet': propnet_line,
         }
         print(json.dumps(line), flush=True)
 
 
 def run_reference_puct(args):
+    """Reference arm: the reference's own C++ search on the host cores in the same regime as the GPU arm and the
+    in-line cpu_baseline (staggered plies, warm-up, bounded window); one sample per 5 contract steps, each in a
+    fresh process with its own seeds, and the mean over the samples. With its 'propnet' half next to it."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    game = puct_game(args)
     t0 = time.perf_counter()
-    per_step = 6.0
-    total = max(1, args.steps) * per_step
-    cpu = cpu_reference_selfplay(seconds=min(total, 150.0) + 3.0, warm=3.0)
+    n_samples = max(1, (max(1, args.steps) + 4) // 5)
+    runs = [cpu_reference_selfplay(game, rng_seed=0x5EED0000 + 7919 * i) for i in range(n_samples)]
+    moves = sum(r['window_moves'] for r in runs)
+    secs = sum(r['window_s'] for r in runs)
+    cpu = dict(runs[0])
+    cpu['value'] = moves / secs
+    cpu['evals_per_s'] = sum(r['evals_per_s'] * r['window_s'] for r in runs) / secs
+    cpu['samples'] = [r['value'] for r in runs]
+    cpu['sample'] = '%d x [%s]' % (n_samples, runs[0]['sample'])
+    prop = None
+    if not args.no_propnet and game == PUCT_GAME:
+        prop = reference_propnet_line(args, steps=3)
     dt = time.perf_counter() - t0
     print(json.dumps({
         'impl': 'reference', 'metric': 'PUCT self-play moves/sec', 'value': cpu['value'], 'unit': 'moves/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt * 1e3 / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': PUCT_WORKLOAD, 'evals_per_move': PUCT_EVALS_PER_MOVE,
+        'config': {'workload': PUCT_PRESETS[game]['workload'], 'evals_per_move': PUCT_EVALS_PER_MOVE,
                    'note': 'host-core run of the reference C++ search; concurrent games bounded to what the '
-                           'host threads hold (the GPU arm holds 4096 per GPU)'},
+                           'host threads hold (the GPU arm holds thousands per GPU)'},
         'evals_per_s': cpu['evals_per_s'], 'cpu_baseline': cpu,
-        'e2e': {'value': cpu['value'], 'unit': 'moves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}),
+        'e2e': {'value': cpu['value'], 'unit': 'moves/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'propnet': prop}),
         flush=True)
 
 
-def run_reference(args):
-    """CPU reference arm: the oracle port of the reference's state-machine loop on all host cores."""
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
+def reference_propnet_line(args, steps=None):
+    """CPU reference arm of the propnet metric: the oracle port of the reference's state-machine loop on all host
+    cores (ggplib is absent, so the reference state machine itself cannot be built)."""
     threads = os.cpu_count() or 1
+    steps = steps or args.steps
     from galvanise_zero_b200 import tables
     from oracle import pnref
     blob = tables.blob_by_name(PROPNET_GAME)
@@ -631,49 +742,64 @@ def run_reference(args):
     rate = tr / max(secs, 1e-9)
     plies = 100
     slots = max(threads, int(rate * 3.0 / plies))       # ~3 s of CPU work per step
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 3)):
         pnref.playout_bench(blob, max(threads, slots // 8), plies, 0xB200, threads)
     t0 = time.perf_counter()
     total = 0
-    for k in range(args.steps):
+    for k in range(steps):
         secs, tr, _ = pnref.playout_bench(blob, slots, plies, 0xB200 + k, threads)
         total += tr
     dt = time.perf_counter() - t0
     val = total / dt
     cpu = {'value': val, 'unit': 'transitions/s', 'cores': threads, 'kind': 'port',
-           'sample': '%s: %d slots x %d plies per step, %d host threads (oracle/propnet_ref.c; ggplib '
+           'sample': '%s: %d slots x %d plies per step, %d steps, %d host threads (oracle/propnet_ref.c; ggplib '
                      'is absent so the reference state machine itself cannot be built)' % (
-                         PROPNET_GAME, slots, plies, threads)}
-    print(json.dumps({
+                         PROPNET_GAME, slots, plies, steps, threads)}
+    return {
         'impl': 'reference', 'metric': 'propnet transitions/sec', 'value': val,
-        'unit': 'transitions/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': dt * 1e3 / max(args.steps, 1), 'higher_is_better': True, 'scaling': 'weak',
+        'unit': 'transitions/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3 / max(steps, 1), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
         'config': {'workload': 'breakthrough 8x8 propnet, batched uniform-random playouts'},
         'cpu_baseline': cpu,
         'e2e': {'value': val, 'unit': 'transitions/s', 'h2d_bytes_per_step': 0,
-                'd2h_bytes_per_step': 0}}), flush=True)
+                'd2h_bytes_per_step': 0}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    print(json.dumps(reference_propnet_line(args)), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--steps', type=int, default=0, help='default: 20 (puct), 2000 (propnet)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='puct', choices=['propnet', 'puct'])
     ap.add_argument('--sub-iters', type=int, default=1)
-    ap.add_argument('--presteps', type=int, default=3000)
+    ap.add_argument('--presteps', type=int, default=1500, help='untimed engine advances before the warm-up steps')
+    ap.add_argument('--advances-per-step', type=int, default=256,
+                    help='puct workload: engine advances (+ network forwards) that make up one bench step')
+    ap.add_argument('--propnet-launches-per-step', type=int, default=300,
+                    help='puct workload: playout launches per step of the propnet half of the line')
+    ap.add_argument('--no-propnet', action='store_true', help='puct workload: leave the propnet half out')
+    ap.add_argument('--no-stagger', action='store_true', help='all slots start at the initial state')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--pipelines', type=int, default=1)
     ap.add_argument('--staggered', action='store_true', help='(implied by --pipelines > 1)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-inline', action='store_true')
     ap.add_argument('--slots', type=int, default=0)
-    ap.add_argument('--game', default='', help='propnet workload: another compiled game (default breakthrough)')
+    ap.add_argument('--game', default='', help='another compiled game (propnet default: breakthrough, puct: reversi)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.steps <= 0:
+        args.steps = 20 if args.workload == 'puct' else 2000
     if args.impl == 'reference':
         if args.workload == 'puct':
             run_reference_puct(args)
@@ -682,9 +808,15 @@ def main():
         return
     rank, world, local = dist_setup(args.gpus)
     if args.workload == 'propnet':
-        run_propnet(args, rank, world, local)
+        line = run_propnet(args, rank, world, local)
+        if line is not None:
+            print(json.dumps(line), flush=True)
     else:
-        run_puct(args, rank, world, local)
+        prop = None
+        if not args.no_propnet and puct_game(args) == PUCT_GAME:
+            # BASELINE's first metric, measured in the same run on the same GPUs
+            prop = run_propnet(args, rank, world, local, steps=args.steps * args.propnet_launches_per_step)
+        run_puct(args, rank, world, local, propnet_line=prop)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -170,6 +170,7 @@ struct PuctTotals {
     int dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts;
     int waiting_eval;
     unsigned long long sel_nodes, sel_children, new_children;
+    unsigned long long depth_sum;      // sum over games of the current root's game depth (mean ply = / G)
 };
 
 __global__ void puct_totals_kernel(const __grid_constant__ PuctEngine E, PuctTotals* out) {
@@ -196,6 +197,7 @@ __global__ void puct_totals_kernel(const __grid_constant__ PuctEngine E, PuctTot
     atomicAdd(&out->sel_nodes, (unsigned long long)c.total_sel_nodes);
     atomicAdd(&out->sel_children, (unsigned long long)c.total_sel_children);
     atomicAdd(&out->new_children, (unsigned long long)c.total_new_children);
+    atomicAdd(&out->depth_sum, (unsigned long long)(c.game_depth > 0 ? c.game_depth : 0));
 }
 
 // ---- synthetic network (parity / bench utility): same function as oracle/ref_harness.cpp
@@ -808,7 +810,7 @@ extern "C" int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes) {
 
 // totals: [evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children,
 //          dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval,
-//          ready_count, select_nodes, select_children, new_children]
+//          ready_count, select_nodes, select_children, new_children, depth_sum]   (23 doubles)
 extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     if (!h || !out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
@@ -828,6 +830,7 @@ extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     out[12] = t.fp_resign0; out[13] = t.fp_resign1; out[14] = t.early_run_to_ends; out[15] = t.resigns;
     out[16] = t.aborts; out[17] = t.waiting_eval; out[18] = (double)ready;
     out[19] = (double)t.sel_nodes; out[20] = (double)t.sel_children; out[21] = (double)t.new_children;
+    out[22] = (double)t.depth_sum;
     return GZ_OK;
 }
 
@@ -851,6 +854,24 @@ extern "C" int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap
     cudaMemsetAsync(h->E.ready_count, 0, 8, s);
     cudaStreamSynchronize(s);
     return n;
+}
+
+// Measurement aid (bench.py): the NEXT game of every slot starts from d_states[g] (device, [G][state_words]) instead
+// of the game's initial state, at game depth 0 — slots then sit at different plies from the first step on, which
+// is the distribution a long-running self-play job is in. Positions must not be terminal.
+__global__ void puct_start_pending_kernel(const __grid_constant__ PuctEngine E) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < E.G) E.ctl[g].start_pending = 1;
+}
+extern "C" int gz_puct_set_start_states(gz_puct* h, const uint32_t* d_states, void* stream) {
+    if (!h || !d_states) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    if (h->mode != 0) { gz_set_error("start states apply to self-play engines"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
+    GZ_CUDA(cudaMemcpyAsync(h->E.start_state, d_states, (size_t)h->E.G * h->E.SW * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    puct_start_pending_kernel<<<(h->E.G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->E);
+    GZ_CUDA(cudaGetLastError());
+    return GZ_OK;
 }
 
 extern "C" int gz_puct_clear_unique_states(gz_puct* h, void* stream) {

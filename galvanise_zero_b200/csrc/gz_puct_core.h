@@ -29,10 +29,14 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "gz_libm.h"
+
 #ifdef __CUDACC__
 #define GZP_HD __host__ __device__ __forceinline__
 #define GZP_HDN __host__ __device__
+#define GZP_MEMBER __host__ __device__ __forceinline__
 #else
+#define GZP_MEMBER inline
 #define GZP_HD static inline
 #define GZP_HDN static inline
 #endif
@@ -119,7 +123,7 @@ struct GameCtl {
     // per-manager style stats (selfplaymanager.h:46-72)
     int32_t saw_dupes, no_samples_taken, false_positive_resigns0, false_positive_resigns1,
         number_early_run_to_ends, number_resigns, number_aborts_game_length;
-    int32_t pad;
+    int32_t start_pending;   // the next game of this slot starts from E->start_state[g] (bench / staggered starts)
 };
 
 // sample record header (int32 words), followed by state, prev state, policy pairs
@@ -175,6 +179,7 @@ struct PuctEngine {
     int uniq_cap;             // power of two
     const uint32_t* uniq_mask;  // [SW] createHashMask (gdltransformer.cpp:54-63)
     const uint32_t* init_state; // [SW]
+    uint32_t* start_state;      // [G*SW] per-slot start position of the slot's NEXT game when ctl.start_pending is set
     SpConf conf;
     uint64_t seed;
     int max_iters_per_step;
@@ -686,31 +691,11 @@ GZP_HDN float gzp_prior_score(const GameView& V, int n, int depth, float node_fi
     return prior;
 }
 
-// Gamma(alpha, 1) sample, Marsaglia-Tsang; statistical (not bit-level) counterpart of the
-// reference's std::gamma_distribution<float> (evaluator.cpp:1249-1258).
-GZP_HDN float gzp_gamma(uint64_t* rng, float alpha) {
-    float boost = 1.0f;
-    if (alpha < 1.0f) {
-        double u = gzp_rng_get(rng);
-        if (u < 1e-12) u = 1e-12;
-        boost = (float)pow(u, 1.0 / alpha);
-        alpha += 1.0f;
-    }
-    const double d = alpha - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
-    for (int it = 0; it < 64; it++) {
-        // normal via Box-Muller
-        double u1 = gzp_rng_get(rng), u2 = gzp_rng_get(rng);
-        if (u1 < 1e-12) u1 = 1e-12;
-        const double x = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
-        double v = 1.0 + cc * x;
-        if (v <= 0) continue;
-        v = v * v * v;
-        double u = gzp_rng_get(rng);
-        if (u < 1e-12) u = 1e-12;
-        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return (float)(d * v) * boost;
-    }
-    return (float)d * boost;
-}
+// The evaluator's generator as a 32-bit URBG for the restated library samplers (gz_libm.h).
+struct GzpRng32 {
+    uint64_t* st;
+    GZP_MEMBER uint32_t operator()() { return gzp_rng_next(st); }
+};
 
 // setDirichletNoise (evaluator.cpp:1227-1297)
 GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n) {
@@ -719,10 +704,15 @@ GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n) {
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
     if ((NODE(n_flags, n) & NF_NOISE_SET) || nc < 2 || cf.dirichlet_noise_pct < 0) return;
     if (NSCORE(n, NODE(n_lead, n)) > 0.95) return;
+    // std::gamma_distribution<float> gamma(alpha, 1.0f), one object for all children (evaluator.cpp:1249-1258):
+    // restated bit for bit in gz_libm.h, so the noise vector is the reference's
     const float alpha = 10.83f / nc;
+    GzGammaF gamma;
+    gz_gamma_init(gamma, alpha);
+    GzpRng32 rng{V.c->rng_eval};
     float total_noise = 0.0f;
     for (int i = 0; i < nc; i++) {
-        const float x = gzp_gamma(V.c->rng_eval, alpha);
+        const float x = gz_gamma_float(gamma, rng);
         scratch[i] = x;
         total_noise += x;
     }
@@ -773,7 +763,7 @@ GZP_HDN int gzp_select_child(GameView& V, int n, GzpSelInfo* info = nullptr) {
     {
         const float base = 19652.0f;
         const float k = depth == 0 ? cf.puct_constant_root : cf.puct_constant;
-        float pcst = logf(((float)(1u + node_visits) + base) / base);
+        float pcst = gz_logf(((float)(1u + node_visits) + base) / base);   // std::log(float) == glibc logf
         pcst += k;
         NODE(n_puct, n) = pcst;
         puct_c = pcst;
@@ -1539,7 +1529,14 @@ GZP_HDN void gzp_begin_game(GameView& V) {
     c->in_run_to_end = 0;
     c->in_playout = 0;
     c->conf_sel = 0;
-    gzp_request_root(V, E->init_state);
+    if (c->start_pending) {
+        // staggered start (measurement aid): this slot's game begins from a given position, at depth 0 like
+        // the reference's establishRoot(initial_state) would with that state handed in as the initial one
+        c->start_pending = 0;
+        gzp_request_root(V, E->start_state + (int64_t)V.g * E->SW);
+    } else {
+        gzp_request_root(V, E->init_state);
+    }
 }
 
 // Returns when the game is blocked on the pipeline (c->req != REQ_NONE or c->eval_node >= 0),

@@ -63,6 +63,7 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     E->uniq_counts = (int32_t*)take((size_t)E->uniq_cap * 4);
     E->uniq_mask = (const uint32_t*)take((size_t)E->SW * 4);
     E->init_state = (const uint32_t*)take((size_t)E->SW * 4);
+    E->start_state = (uint32_t*)take(G * E->SW * 4);
     return pos;
 }
 

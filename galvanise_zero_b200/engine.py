@@ -32,7 +32,7 @@ SP_FIELDS = ['oscillate_sampling_pct', 'temperature_for_policy', 'evals_per_move
 TOTAL_KEYS = ['evals', 'moves', 'games', 'samples', 'playouts', 'errors', 'halted', 'first_error',
               'max_nodes', 'max_children', 'dupes', 'no_samples', 'fp_resign0', 'fp_resign1',
               'early_run_to_ends', 'resigns', 'aborts', 'waiting_eval', 'ready',
-              'select_nodes', 'select_children', 'new_children']
+              'select_nodes', 'select_children', 'new_children', 'depth_sum']
 # sample record header (csrc/gz_puct_core.h SR_*)
 SR_DEPTH, SR_GAME_LENGTH, SR_SLOT, SR_MATCH, SR_HAS_RESIGNED, SR_RESIGN_FP, SR_START_DEPTH, SR_VISITS, \
     SR_LEAD, SR_N_PREV, SR_N_CHILDREN = range(1, 12)
@@ -71,6 +71,7 @@ def _declare(L):
     L.gz_puct_fetch_samples.argtypes = [vp, vp, i64, vp]
     L.gz_puct_fetch_samples.restype = i64
     L.gz_puct_clear_unique_states.argtypes = [vp, vp]
+    L.gz_puct_set_start_states.argtypes = [vp, vp, vp]
     L.gz_puct_command.argtypes = [vp, ci, ci, ci, ci, vp, vp]
     L.gz_puct_snapshot.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
     L.gz_synth_nn.argtypes = [vp, ci, i64, ci, u64, ci, ctypes.POINTER(ci), ci, vp, vp, vp]
@@ -200,7 +201,7 @@ class PuctEngine(object):
 
     # ---- results
     def totals(self):
-        out = (ctypes.c_double * 22)()
+        out = (ctypes.c_double * len(TOTAL_KEYS))()
         _lib.check(self._L.gz_puct_totals(self._h, out, self._stream()))
         return dict(zip(TOTAL_KEYS, [float(x) for x in out]))
 
@@ -246,6 +247,12 @@ class PuctEngine(object):
                 resultant_puct_score=[float(f[SR_PUCT_SCORE + i]) for i in range(R)],
                 resultant_puct_visits=int(r[SR_VISITS])))
         return out
+
+    def set_start_states(self, states):
+        """states int32 CUDA tensor [n_games, state_words]: the next game of every slot starts there (depth 0)."""
+        assert states.is_cuda and states.dtype == torch.int32 and states.is_contiguous()
+        assert tuple(states.shape) == (self.n_games, self.state_words)
+        _lib.check(self._L.gz_puct_set_start_states(self._h, states.data_ptr(), self._stream()))
 
     def clear_unique_states(self):
         _lib.check(self._L.gz_puct_clear_unique_states(self._h, self._stream()))

@@ -210,6 +210,9 @@ class Supervisor(object):
         self.managers = []
         self._cur = None            # manager whose planes were handed out by the last poll
         self._primed = False
+        # additive (measurement aid): fn(engine, manager_index) -> int32 CUDA tensor [games, state_words]; the
+        # first game of every slot then starts there instead of the initial state (PuctEngine.set_start_states)
+        self.start_states_fn = None
 
     def set_num_workers(self, n):
         """Not in the reference's method table although its Python wrapper calls it
@@ -227,6 +230,8 @@ class Supervisor(object):
                              seed=self.seed + 104729 * k, node_cap=self.node_cap, child_cap=self.child_cap,
                              c_transformer=self.c_transformer, plane_dtype=torch.float32, sm=dsm)
             dsm = eng.sm                                      # managers share the device program
+            if self.start_states_fn is not None:
+                eng.set_start_states(self.start_states_fn(eng, k))
             stream = torch.cuda.Stream(device=eng.device) if n_man > 1 else None
             self.managers.append(_Manager(eng, stream))
         self.engine = self.managers[0].engine

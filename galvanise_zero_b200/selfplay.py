@@ -12,6 +12,24 @@ import torch
 from .engine import PuctEngine
 
 
+def staggered_start_states(sm, n, max_ply, seed=0xB200, slot0=0):
+    """n positions for ``PuctEngine.set_start_states``: slot i sits ``hash(slot0 + i) % max_ply`` uniformly random
+    plies into a game (device playouts, ``DeviceStateMachine.playout_step``). A long-running self-play job holds
+    its games at all plies at once; starting every slot at the initial state instead measures the opening only.
+    Slots whose random game ended early keep the initial state. Returns int32 [n, state_words] on the device."""
+    idx = torch.arange(slot0, slot0 + n, dtype=torch.int64, device=sm.device)
+    target = ((idx * 2654435761 + (seed & 0xffff)) >> 7) % max(1, int(max_ply))
+    s = torch.zeros((n, sm.state_words), dtype=torch.int32, device=sm.device)
+    legal, term, goals = sm.alloc_views(n)
+    term.fill_(1)                      # the first step resets every slot to the initial state (ply 0)
+    out = sm.initial_states(n)
+    for ply in range(int(max_ply)):
+        sm.playout_step(s, legal, term, goals, seed, ply, slot0=slot0)
+        take = (target == ply) & (term == 0)
+        out = torch.where(take.unsqueeze(1), s, out)
+    return out.contiguous()
+
+
 class SelfPlayRunner(object):
     def __init__(self, engine: PuctEngine, net, sub_iters=1, use_cuda_graph=True, stream=None):
         self.engine = engine

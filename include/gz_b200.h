@@ -204,7 +204,14 @@ int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream);
  * other's batch (the reference's two managers per worker, src/cpp/supervisor.cpp:79-99). */
 int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* const* h_arrays, int n_arrays, void* stream);
 int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes);
-int gz_puct_totals(gz_puct* h, double* h_out22, void* stream);
+/* h_out23: evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children, dupes,
+ * no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval, ready, select_nodes,
+ * select_children, new_children, depth_sum (sum over slots of the current root's game depth). */
+int gz_puct_totals(gz_puct* h, double* h_out23, void* stream);
+/* Measurement aid: the next game of every slot starts from d_states[g] (device, [G][state_words], non-terminal
+ * positions) at game depth 0 instead of the initial state — what handing SelfPlay another `initial_state`
+ * (src/cpp/selfplaymanager.cpp:140, selfplay.cpp:313) does in the reference. Later games start normally. */
+int gz_puct_set_start_states(gz_puct* h, const uint32_t* d_states, void* stream);
 int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream);
 int gz_puct_clear_unique_states(gz_puct* h, void* stream);
 int gz_puct_command(gz_puct* h, int game, int cmd, int arg, int evals, const uint32_t* h_state, void* stream);

@@ -52,6 +52,7 @@ def lib():
         L.gzref_add_board_base.argtypes = [vp, ci, ci]
         L.gzref_add_control_base.argtypes = [vp, ci, ci, ctypes.c_float]
         L.gzref_seed.argtypes = [ctypes.c_uint64]
+        L.gzref_set_stagger.argtypes = [ci, ctypes.c_uint64]
         L.gzref_search.argtypes = [vp, dp, vp, ci, ci, ctypes.c_uint64, ci, vp, vp, vp, vp, vp, vp, vp]
         L.gzref_selfplay.argtypes = [vp, dp, dp, dp, ci, ci, ctypes.c_uint64, ctypes.c_int64,
                                      ctypes.c_double, dp, vp, ctypes.c_int64, ci]
@@ -119,10 +120,13 @@ class RefEngine:
         return out
 
     def selfplay(self, sp_conf, batch_size, num_workers, nn_seed=1, target_samples=0,
-                 max_seconds=10.0, rng_seed=0x5EED0000, sample_capacity=0, srec=0, warm_seconds=0.0):
+                 max_seconds=10.0, rng_seed=0x5EED0000, sample_capacity=0, srec=0, warm_seconds=0.0,
+                 stagger_max_ply=0, stagger_seed=0xB200):
         """Runs the reference Supervisor. With sample_capacity > 0 also returns the samples as an
-        int32 array [n, srec] in the record layout of csrc/gz_puct_core.h (SR_*)."""
+        int32 array [n, srec] in the record layout of csrc/gz_puct_core.h (SR_*). stagger_max_ply > 0:
+        the first game of every slot starts a uniformly random number of random plies (< max) into a game."""
         self.L.gzref_seed(rng_seed)
+        self.L.gzref_set_stagger(int(stagger_max_ply), int(stagger_seed))
         import attr
         d = sp_conf if isinstance(sp_conf, dict) else attr.asdict(sp_conf)
         stats = (ctypes.c_double * 12)()

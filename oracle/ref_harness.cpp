@@ -70,6 +70,29 @@ uint64_t K273::gzref_next_seed() { return g_seed_counter.fetch_add(0x9E3779B97F4
 extern "C" void gzref_seed(uint64_t s) { g_seed_counter.store(s); }
 
 // ------------------------------------------------------------------------------------------------
+// Staggered starts (measurement aid, bench.py): while enabled, every getInitialState() call — the reference makes
+// one per SelfPlay slot (selfplaymanager.cpp:140) — returns a position `hash(slot) % max_ply` uniformly random
+// plies into a game, so that the slots sit at all plies at once like a long-running job instead of all walking
+// through the opening together. gzref_selfplay puts the true initial state back into a slot's buffer once the
+// slot's first game is under way, so every later game starts normally.
+static std::atomic<int> g_stagger_max_ply{0};
+static std::atomic<uint64_t> g_stagger_seed{0};
+static std::atomic<uint64_t> g_stagger_slot{0};
+static std::atomic<uint64_t> g_stagger_total{0};     /* slots to stagger (the self-play slots of one run) */
+extern "C" void gzref_set_stagger(int max_ply, uint64_t seed) {
+    g_stagger_max_ply.store(max_ply);
+    g_stagger_seed.store(seed);
+    g_stagger_slot.store(0);
+    g_stagger_total.store(0);
+}
+static inline uint64_t stagger_mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// ------------------------------------------------------------------------------------------------
 // greenlets on ucontext
 struct greenlet_t {
     ucontext_t ctx;
@@ -167,7 +190,36 @@ public:
         bs->init(gt->n_bases);
         return bs;
     }
-    const GGPLib::BaseState* getInitialState() const override { return initial; }
+    const GGPLib::BaseState* getInitialState() const override {
+        const int max_ply = g_stagger_max_ply.load();
+        if (max_ply <= 0) return initial;
+        return const_cast<ShimStateMachine*>(this)->staggeredState(max_ply);
+    }
+    const GGPLib::BaseState* trueInitialState() const { return initial; }
+    /* a fresh buffer (owned by the caller's slot for the life of the process) holding a random-playout position */
+    GGPLib::BaseState* staggeredState(int max_ply) {
+        const uint64_t slot = g_stagger_slot.fetch_add(1);
+        if (slot >= g_stagger_total.load()) return const_cast<GGPLib::BaseState*>(initial);
+        uint64_t rs = stagger_mix(g_stagger_seed.load() ^ (slot * 0xD1B54A32D192ED03ULL));
+        const int plies = (int)(stagger_mix(rs) % (uint64_t)max_ply);
+        GGPLib::BaseState* cur = newBaseState();
+        GGPLib::BaseState* nxt = newBaseState();
+        cur->assign(initial);
+        for (int p = 0; p < plies; p++) {
+            updateBases(cur);
+            for (int r = 0; r < gt->n_roles; r++) {
+                rs = stagger_mix(rs);
+                jm->set(r, legal_states[r].legals[rs % (uint64_t)legal_states[r].count]);
+            }
+            nextState(jm, nxt);
+            updateBases(nxt);
+            if (isTerminal()) { cur->assign(initial); break; }   // the random game ended early: start normally
+            std::swap(cur, nxt);
+        }
+        free(nxt);
+        updateBases(initial);
+        return cur;
+    }
     void updateBases(const GGPLib::BaseState* bs) override {
         pnref_update_bases(sm, (const uint32_t*)bs->data);
         for (int r = 0; r < gt->n_roles; r++) {
@@ -385,15 +437,22 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
  * SelfPlay::match_count and PuctEvaluator::game_depth. Reads race benignly with the worker threads. */
 struct MoveCounter {
     std::vector<int> last_match, last_depth;
+    std::vector<char> restored;
+    const GGPLib::BaseState* true_initial = nullptr;   // set when the slots were given staggered starts
     double finished_plies = 0;
     double count(const std::vector<SelfPlayManager*>& mans) {
         size_t idx = 0;
         double cur = 0;
         for (SelfPlayManager* m : mans) {
             for (SelfPlay* sp : m->self_plays) {
-                if (idx >= last_match.size()) { last_match.push_back(sp->match_count); last_depth.push_back(0); }
+                if (idx >= last_match.size()) { last_match.push_back(sp->match_count); last_depth.push_back(0); restored.push_back(0); }
                 const int mc = sp->match_count;
                 const int d = sp->pe->game_depth;
+                if (true_initial && !restored[idx] && mc >= 1 && d >= 1) {
+                    /* the slot's first game has left its (staggered) root behind: later games start normally */
+                    const_cast<GGPLib::BaseState*>(sp->initial_state)->assign(true_initial);
+                    restored[idx] = 1;
+                }
                 if (mc != last_match[idx]) {
                     finished_plies += last_depth[idx];
                     last_match[idx] = mc;
@@ -448,6 +507,9 @@ extern "C" int gzref_selfplay(void* h, const double* sp_conf, const double* puct
     sc->run_to_end_early_score = (float)sp_conf[SC_RUN_TO_END_EARLY_SCORE];
     sc->run_to_end_minimum_game_depth = (int)sp_conf[SC_RUN_TO_END_MINIMUM_GAME_DEPTH];
 
+    /* worker threads create their SelfPlay slots asynchronously (supervisor.cpp:196-207): staggering stays armed
+       for exactly the slots of this run */
+    g_stagger_total.store((uint64_t)batch_size * (uint64_t)(num_workers <= 0 ? 1 : 2 * num_workers));
     Supervisor* sup = new Supervisor(sm, tr, batch_size, "gzref");
     if (num_workers <= 0) {
         sup->createInline(sc);
@@ -467,6 +529,7 @@ extern "C" int gzref_selfplay(void* h, const double* sp_conf, const double* puct
     if (sup->inline_sp_manager) managers.push_back(sup->inline_sp_manager);
     for (SelfPlayWorker* w : sup->self_play_workers) { managers.push_back(w->man0); managers.push_back(w->man1); }
     MoveCounter mc;
+    if (g_stagger_max_ply.load() > 0) mc.true_initial = sm->trueInitialState();
     double moves_now = 0, moves_at_warm = 0, evals_at_warm = 0, t_warm = -1;
     const double warm_seconds = out_stats[8];     /* in: seconds to exclude from the rates */
     const double t0 = K273::get_time();

@@ -43,23 +43,32 @@ def _device_search(eng, evals, n_moves, seed=1):
     return out
 
 
-@pytest.mark.parametrize('game,evals,moves', [('reversi', 200, 20), ('breakthrough', 300, 20),
-                                              ('reversi', 1500, 5),      # root visits > 1000: the latch limiter and its RNG draws
-                                              ('breakthroughSmall', 800, 12),
-                                              ('chess_15d', 60, 3), ('hexLG13', 40, 3),
-                                              ('connect6', 100, 4)])
-def test_device_search_matches_reference(game, evals, moves):
+@pytest.mark.parametrize('game,evals,moves,noise', [
+    ('reversi', 200, 20, -1), ('breakthrough', 300, 20, -1),
+    ('reversi', 1500, 5, -1),      # root visits > 1000: the latch limiter and its RNG draws
+    ('breakthroughSmall', 800, 12, -1),
+    ('chess_15d', 60, 3, -1), ('hexLG13', 40, 3, -1),
+    ('connect6', 100, 4, -1),
+    ('amazons_10x10', 120, 3, -1),   # 2176 children at the root: the child staging that does not fit on chip
+    # Dirichlet noise ON (evaluator.cpp:1227-1297; std::gamma_distribution<float> restated in csrc/gz_libm.h):
+    # alpha >= 1 (few children) and the pow-boosted alpha < 1 branch (more than 10 children)
+    ('reversi', 200, 20, 0.25), ('breakthrough', 200, 16, 0.25), ('connect6', 80, 3, 0.25),
+    ('amazons_10x10', 80, 2, 0.25)])
+def test_device_search_matches_reference(game, evals, moves, noise):
     from galvanise_zero_b200.engine import PuctEngine
-    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits')
+    conf = confs.base_puct_config(dirichlet_noise_pct=noise, choose='choose_top_visits')
     sp = confs.selfplay_config_template()
     sp.puct_config = conf
     eng = PuctEngine(game, sp, n_games=1, mode=1, node_cap=8192, child_cap=1 << 18, plane_dtype=torch.float32)
-    ref = gzref.RefEngine(tables.blob_by_name(game), eng.c_transformer).search(conf, evals, n_moves=moves)
+    ref = gzref.RefEngine(tables.blob_by_name(game), eng.c_transformer).search(conf, evals, n_moves=moves,
+                                                                               max_children=4096)
     mine = _device_search(eng, evals, moves)
     assert len(mine) == len(ref)
     worst_tv, same_choice = 0.0, 0
     for a, b in zip(ref, mine):
         assert np.array_equal(a['moves'], b['moves'])
+        if noise > 0:
+            assert np.array_equal(a['policy_prob'], b['policy_prob'])      # the noised priors, bit for bit
         pa = a['traversals'] / max(1, a['traversals'].sum())
         pb = b['traversals'] / max(1, b['traversals'].sum())
         worst_tv = max(worst_tv, 0.5 * float(np.abs(pa - pb).sum()))
@@ -71,12 +80,16 @@ def test_device_search_matches_reference(game, evals, moves):
     assert same_choice >= 0.99 * len(ref)
 
 
-def test_device_selfplay_samples_match_reference():
+@pytest.mark.parametrize('game,G,evals,target,noise,exact', [
+    ('breakthroughSmall', 8, 40, 150, False, False),
+    ('reversi', 4, 50, 60, False, True),
+    ('reversi', 4, 50, 60, True, True)])       # the benchmarked template: noise 0.25 / 0.15 (templates.py:73-129)
+def test_device_selfplay_samples_match_reference(game, G, evals, target, noise, exact):
     from galvanise_zero_b200.engine import PuctEngine
-    game, G, evals, target = 'breakthroughSmall', 8, 40, 150
     sp = confs.selfplay_config_template(evals_per_move=evals)
-    sp.puct_config.dirichlet_noise_pct = -1
-    sp.run_to_end_puct_config.dirichlet_noise_pct = -1
+    if not noise:
+        sp.puct_config.dirichlet_noise_pct = -1
+        sp.run_to_end_puct_config.dirichlet_noise_pct = -1
     eng = PuctEngine(game, sp, n_games=G, mode=0, node_cap=4096, child_cap=1 << 16, plane_dtype=torch.float32)
     srec = eng.srec
     ref = gzref.RefEngine(tables.blob_by_name(game), eng.c_transformer).selfplay(
@@ -107,7 +120,7 @@ def test_device_selfplay_samples_match_reference():
         nc = int(a[11])
         bad += int(not np.array_equal(a[:24 + 2 * sw + 2 * nc], b[:24 + 2 * sw + 2 * nc]))
     print('samples compared', len(common), 'mismatching', bad)
-    assert bad <= 0.01 * len(common)
+    assert bad <= (0 if exact else 0.01 * len(common))
 
 
 def test_selfplay_at_scale_properties():

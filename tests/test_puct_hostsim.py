@@ -4,10 +4,10 @@ unmodified into oracle/_ref/libgzref.so) under an identical synthetic network an
 
 Bar: EXACT equality of root visit counts per move and of every self-play sample record
 (state, previous state, policy, final scores, depth, game length, resign flags) — i.e. total-variation
-distance 0, well inside the stated tolerance (TV <= 0.02). Dirichlet noise is off
-in these runs (the reference draws it with libstdc++'s std::gamma_distribution, which is not
-restated); every other RNG-driven decision (oscillating sampling, temperature move choice, resign
-permission, root latch) is on."""
+distance 0, well inside the stated tolerance (TV <= 0.02). Every RNG-driven decision
+(oscillating sampling, temperature move choice, resign permission, root latch) is on; Dirichlet noise —
+which the reference draws with libstdc++'s std::gamma_distribution<float>, restated bit for bit in
+csrc/gz_libm.h — is off in the first tests and ON in the *_with_dirichlet_noise ones."""
 import numpy as np
 import pytest
 
@@ -46,6 +46,33 @@ def test_visit_counts_match_reference_search(game, evals, moves):
         assert np.array_equal(a['scores'], b['scores'])
 
 
+@pytest.mark.parametrize('game,evals,moves,squash', [('reversi', 200, 14, -1), ('breakthrough', 150, 20, 0.5),
+                                                     ('connect6', 100, 3, -1), ('amazons_10x10', 80, 3, -1)])
+def test_visit_counts_match_with_dirichlet_noise(game, evals, moves, squash):
+    """setDirichletNoise (evaluator.cpp:1227-1297) ON at every root, incl. the alpha < 1 branch (more than 10
+    children: connect6 361, amazons 2176) and the policy squash: priors after noise and visit counts are the
+    reference's, value for value."""
+    from hostsim_util import HostSim
+    ct, eng = _setup(game)
+    conf = confs.base_puct_config(dirichlet_noise_pct=0.25, choose='choose_top_visits',
+                                  noise_policy_squash_pct=squash, noise_policy_squash_prob=0.1)
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    ref = eng.search(conf, evals, n_moves=moves, max_children=4096)
+    mine = HostSim(tables.blob_by_name(game), ct, sp).search(evals, moves)
+    assert len(ref) == len(mine) == moves
+    for a, b in zip(ref, mine):
+        assert np.array_equal(a['policy_prob'], b['policy_prob'])     # the noised priors themselves
+        assert np.array_equal(a['traversals'], b['traversals'])
+        assert a['choice'] == b['choice'] and a['root_visits'] == b['root_visits']
+        assert np.array_equal(a['scores'], b['scores'])
+
+
+def test_selfplay_samples_match_with_dirichlet_noise():
+    """The benchmarked configuration (templates.py:73-129: noise 0.25 in sampled searches, 0.15 in run-to-end)."""
+    _selfplay_samples('reversi', 4, 50, 60, noise=True)
+
+
 def test_backup_finalised_and_temperature_choice_match():
     from hostsim_util import HostSim
     ct, eng = _setup('breakthroughSmall')
@@ -62,11 +89,16 @@ def test_backup_finalised_and_temperature_choice_match():
 @pytest.mark.parametrize('game,G,evals,target', [('breakthrough', 6, 60, 120), ('breakthroughSmall', 8, 40, 150),
                                                  ('reversi', 4, 50, 60)])
 def test_selfplay_samples_match_reference_supervisor(game, G, evals, target):
+    _selfplay_samples(game, G, evals, target, noise=False)
+
+
+def _selfplay_samples(game, G, evals, target, noise):
     from hostsim_util import HostSim
     ct, eng = _setup(game)
     sp = confs.selfplay_config_template(evals_per_move=evals)
-    sp.puct_config.dirichlet_noise_pct = -1
-    sp.run_to_end_puct_config.dirichlet_noise_pct = -1
+    if not noise:
+        sp.puct_config.dirichlet_noise_pct = -1
+        sp.run_to_end_puct_config.dirichlet_noise_pct = -1
     pn = tables.propnet_by_name(game)
     SW = tables.state_words(pn.n_bases)
     srec = 24 + 2 * SW + 2 * max(pn.role_sizes)
