@@ -429,6 +429,9 @@ def run_puct(args, rank, world, local, propnet_line=None):
                           child_cap=preset['child_cap'], plane_c_pad=16 if game == PUCT_GAME else 0)
                for k in range(P)]
     eng = engines[0]
+    if args.max_iters or args.max_work:
+        for e in engines:
+            e.set_step_limits(args.max_iters or 16, args.max_work or (1 << 20))
     # every slot's first game starts a uniformly random number of random plies into a game
     if not args.no_stagger:
         for k, e in enumerate(engines):
@@ -788,6 +791,8 @@ def main():
                     help='puct workload: playout launches per step of the propnet half of the line')
     ap.add_argument('--no-propnet', action='store_true', help='puct workload: leave the propnet half out')
     ap.add_argument('--no-stagger', action='store_true', help='all slots start at the initial state')
+    ap.add_argument('--max-iters', type=int, default=0, help='engine step limit: controller iterations per game')
+    ap.add_argument('--max-work', type=int, default=0, help='engine step limit: tree levels descended per game')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--pipelines', type=int, default=1)
     ap.add_argument('--staggered', action='store_true', help='(implied by --pipelines > 1)')

@@ -65,6 +65,7 @@ puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_wo
     // runs (they are read and written dozens of times per playout; through global memory every
     // read-after-write is an L2 round trip), followed by the child cache
     __shared__ __align__(16) uint32_t ctl_sm[PUCT_WARPS_PER_BLOCK][PUCT_CTL_WORDS];
+    __shared__ int32_t ord_sm[PUCT_WARPS_PER_BLOCK][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * PUCT_WARPS_PER_BLOCK + warp;
     if (g >= E.G) return;
@@ -74,6 +75,7 @@ puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_wo
     for (int i = lane; i < PUCT_CTL_WORDS; i += 32) ctl_sm[warp][i] = gctl[i];
     __syncwarp();
     V.c = reinterpret_cast<GameCtl*>(ctl_sm[warp]);
+    V.ord = ord_sm[warp];
     int32_t *gpn = V.pn, *gpc = V.pc;
     if (cmem) {
         int32_t* spn = reinterpret_cast<int32_t*>(cmem + cache_words);
@@ -357,6 +359,7 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     E.READYCAP = ready_cap > 0 ? ready_cap : 1 << 16;
     E.uniq_cap = 1 << 20;
     E.max_iters_per_step = 16;
+    E.max_work_per_step = 1 << 20;
     E.seed = seed;
     if ((int)tr->policy_sizes.size() != E.R) { gz_set_error("transformer policy heads != roles"); delete h; return GZ_ERR_ARG; }
     for (int r = 0; r < E.R; r++)
@@ -420,6 +423,14 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     GZ_CUDA(cudaGetLastError());
     GZ_CUDA(cudaDeviceSynchronize());
     *out = h;
+    return GZ_OK;
+}
+
+// Per-step limits of the controller (see PuctEngine): iterations and tree levels descended per game and step.
+extern "C" int gz_puct_set_step_limits(gz_puct* h, int max_iters, int max_work) {
+    if (!h || max_iters < 1 || max_work < 1) { gz_set_error("bad step limits"); return GZ_ERR_ARG; }
+    h->E.max_iters_per_step = max_iters;
+    h->E.max_work_per_step = max_work;
     return GZ_OK;
 }
 

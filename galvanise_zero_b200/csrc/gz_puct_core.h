@@ -35,13 +35,20 @@
 #define GZP_HD __host__ __device__ __forceinline__
 #define GZP_HDN __host__ __device__
 #define GZP_MEMBER __host__ __device__ __forceinline__
+#define GZP_RARE __host__ __device__ __noinline__      // off the hot path: one out-of-line copy keeps the kernel's code small
 #else
+#define GZP_RARE static __attribute__((noinline))
 #define GZP_MEMBER inline
 #define GZP_HD static inline
 #define GZP_HDN static inline
 #endif
 
 #define GZP_MAX_ROLES 4
+#ifdef __CUDACC__
+#define GZP_ALIGN(n) __align__(n)
+#else
+#define GZP_ALIGN(n) __attribute__((aligned(n)))
+#endif
 
 // ---- phases of the per-game controller
 enum {
@@ -136,24 +143,44 @@ enum {
     SR_HEADER = 24
 };
 
+// One node: everything select / backup read and write, in one 64-byte line.
+struct GZP_ALIGN(16) GzpNode {
+    int32_t n_parent, n_child0, n_nchild;
+    uint32_t n_visits;
+    int32_t n_inflight, n_flags, n_lead, n_depth;
+    float score[GZP_MAX_ROLES];        // current score per role
+    float final_[GZP_MAX_ROLES];       // the network's (or the terminal) score per role
+};
+// One child of a node, 32 bytes: the edge (move, traversals, priors) AND a copy of the statistics of the node it
+// leads to that the parent's select reads — that node's current score for the PARENT's lead role, its visit
+// count, its finalised flag and in-flight count. The copy is kept current by whoever changes the child node:
+// node creation (gzp_step_post), the network's answer (gzp_reply) and gzp_backup, which walks the playout path
+// from the leaf up and therefore knows, at every node it updates, the parent's record that points to it.
+// select then reads ONE contiguous block per tree level instead of gathering from every child node.
+struct GZP_ALIGN(16) GzpChild {
+    int32_t c_to;                       // node index or -1 (unexpanded)
+    int16_t c_move;                     // the lead role's action index
+    uint8_t c_flags, c_inflight;        // copy of the child node's NF_FINALISED bit / in-flight count
+    uint32_t c_trav;
+    float c_prob, c_prob_orig, c_next;
+    float c_score;                      // copy of the child node's score for this node's lead role (-1: unexpanded)
+    uint32_t c_visits;                  // copy of the child node's visit count
+};
+
 struct PuctEngine {
     int G, R, SW, LW, NCAP, CCAP, MAXD, n_rewards, max_actions;
     int role_sizes[GZP_MAX_ROLES];
     int legal_word_off[GZP_MAX_ROLES + 1];
     int policy_off[GZP_MAX_ROLES];      // offset of role r's policy row inside a concatenated row
     int policy_stride;                  // sum of role sizes
-    // node arrays: index = g*NCAP + n (nodes of a game are in creation order: parent < child)
-    int32_t *n_parent, *n_child0, *n_nchild, *n_inflight, *n_flags, *n_lead, *n_depth;
-    uint32_t* n_visits;
-    float *n_score, *n_final;           // [.. * GZP_MAX_ROLES]
-    float* n_puct;
+    // node records: index = g*NCAP + n (nodes of a game are in creation order: parent < child)
+    GzpNode* nodes;                     // one 64-byte record per node
     uint32_t* n_state;                  // [.. * SW]
     int32_t* n_other;                   // [.. * GZP_MAX_ROLES] every role's only action (non-lead roles)
-    // child arrays: index = g*CCAP + c (blocks in the creation order of their nodes)
-    int32_t *c_to, *c_move, *c_owner;           // c_owner: node the child record belongs to
-    int32_t *n_newidx, *n_newc0;                // re-root scratch: new node index / new child0
-    uint32_t* c_trav;
-    float *c_prob, *c_prob_orig, *c_next;
+    // child records: index = g*CCAP + c (blocks in the creation order of their nodes)
+    GzpChild* children;                 // one 32-byte record per child
+    int32_t* c_owner;                   // node the child record belongs to (node creation and re-rooting only)
+    int32_t *n_newidx, *n_newc0;        // re-root scratch: new node index / new child0
     // per game
     GameCtl* ctl;
     int32_t *path_node, *path_choice;   // [G*MAXD]
@@ -182,7 +209,11 @@ struct PuctEngine {
     uint32_t* start_state;      // [G*SW] per-slot start position of the slot's NEXT game when ctl.start_pending is set
     SpConf conf;
     uint64_t seed;
+    // One engine step lets a game run until it needs the batch pipeline, but at most this many controller
+    // iterations / tree levels descended: playouts that end in terminal or finalised nodes need no pipeline
+    // pass, and the slowest warp sets the duration of the step for all games.
     int max_iters_per_step;
+    int max_work_per_step;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -375,6 +406,8 @@ struct GameView {
     int64_t nb, cb;   // node / child base index of the active arena
     int lane;         // 0..31 on the device (all lanes run the controller redundantly), 0 on the host
     int32_t *pn, *pc; // playout path (node, chosen child); global rows, or a shared-memory copy on the device
+    int32_t* ord;     // device: 32 words of shared memory per warp (rank -> lane permutation of the warp path)
+    int work;         // tree levels descended in this step (the step's work budget, see gzp_step_pre)
     ChildCache C;
 };
 
@@ -392,6 +425,8 @@ GZP_HD GameView gzp_view(const PuctEngine* E, int g, int lane = 0, uint32_t* cac
     v.nb = (int64_t)g * E->NCAP;
     v.cb = (int64_t)g * E->CCAP;
     v.lane = lane;
+    v.ord = nullptr;
+    v.work = 0;
     v.pn = E->path_node + (int64_t)g * E->MAXD;
     v.pc = E->path_choice + (int64_t)g * E->MAXD;
     if (!cache_mem) cache_mem = E->x_cache + (int64_t)g * gzp_cache_words(E->max_actions);
@@ -399,10 +434,10 @@ GZP_HD GameView gzp_view(const PuctEngine* E, int g, int lane = 0, uint32_t* cac
     return v;
 }
 
-#define NODE(field, n) (V.E->field[V.nb + (n)])
-#define CHILD(field, c) (V.E->field[V.cb + (c)])
-#define NSCORE(n, r) (V.E->n_score[(V.nb + (n)) * GZP_MAX_ROLES + (r)])
-#define NFINAL(n, r) (V.E->n_final[(V.nb + (n)) * GZP_MAX_ROLES + (r)])
+#define NODE(field, n) (V.E->nodes[V.nb + (n)].field)
+#define CHILD(field, c) (V.E->children[V.cb + (c)].field)
+#define NSCORE(n, r) (V.E->nodes[V.nb + (n)].score[(r)])
+#define NFINAL(n, r) (V.E->nodes[V.nb + (n)].final_[(r)])
 #define NOTHER(n, r) (V.E->n_other[(V.nb + (n)) * GZP_MAX_ROLES + (r)])
 #define NSTATE(n) (V.E->n_state + (V.nb + (n)) * V.E->SW)
 
@@ -412,41 +447,36 @@ GZP_HD bool gzp_is_terminal(const GameView& V, int n) {
 }
 GZP_HD bool gzp_is_finalised(const GameView& V, int n) { return (NODE(n_flags, n) & NF_FINALISED) != 0; }
 
-// Stage node n's children (and the statistics of their nodes for role `lead`) in the cache.
-GZP_HDN void gzp_cache_fill(GameView& V, int n) {
-    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n), lead = NODE(n_lead, n);
+// Stage node n's children in the cache: one contiguous block of records, two 16-byte loads per child.
+GZP_RARE void gzp_cache_fill(GameView& V, int n) {
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
     ChildCache& C = V.C;
     GZP_SYNC();
     for (int i = V.lane; i < nc; i += GZP_LANES) {
-        // all loads first, stores after: the cache is addressed through generic pointers, so a store between
-        // two loads would make the second wait for the first one's data (one DRAM round trip per field)
-        const int to = CHILD(c_to, c0 + i);
-        const int mv = CHILD(c_move, c0 + i);
-        const uint32_t tr = CHILD(c_trav, c0 + i);
-        const float pr = CHILD(c_prob, c0 + i);
-        const float po = CHILD(c_prob_orig, c0 + i);
-        const float nx = CHILD(c_next, c0 + i);
-        float sc = -1.0f;
-        uint32_t vi = 0;
-        int fl = 0, inf = 0;
-        if (to >= 0) {
-            sc = NSCORE(to, lead < 0 ? 0 : lead);
-            vi = NODE(n_visits, to);
-            fl = NODE(n_flags, to);
-            inf = NODE(n_inflight, to);
-        }
-        C.to[i] = to;
-        C.move[i] = mv;
-        C.trav[i] = tr;
-        C.prob[i] = pr;
-        C.prob_orig[i] = po;
-        C.next[i] = nx;
-        C.score[i] = sc;
-        C.visits[i] = vi;
-        C.flags[i] = fl;
-        C.inflight[i] = inf;
+        const GzpChild k = V.E->children[V.cb + c0 + i];
+        C.to[i] = k.c_to;
+        C.move[i] = k.c_move;
+        C.trav[i] = k.c_trav;
+        C.prob[i] = k.c_prob;
+        C.prob_orig[i] = k.c_prob_orig;
+        C.next[i] = k.c_next;
+        C.score[i] = k.c_to >= 0 ? k.c_score : -1.0f;
+        C.visits[i] = k.c_to >= 0 ? k.c_visits : 0u;
+        C.flags[i] = k.c_to >= 0 ? (int)k.c_flags : 0;
+        C.inflight[i] = k.c_to >= 0 ? (int)k.c_inflight : 0;
     }
     GZP_SYNC();
+}
+
+// The parent's copy of node `to`'s statistics (see GzpChild): called wherever `to` changed and the record that
+// points to it is known.
+GZP_HD void gzp_child_refresh(GameView& V, int parent, int child, int to) {
+    GzpChild& k = V.E->children[V.cb + NODE(n_child0, parent) + child];
+    const int lead = NODE(n_lead, parent);
+    k.c_score = NSCORE(to, lead < 0 ? 0 : lead);
+    k.c_visits = NODE(n_visits, to);
+    k.c_flags = (uint8_t)(NODE(n_flags, to) & NF_FINALISED);
+    k.c_inflight = (uint8_t)(NODE(n_inflight, to) > 255 ? 255 : NODE(n_inflight, to));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -489,7 +519,6 @@ GZP_HDN int gzp_create_node(GameView& V, int parent, int depth) {
     NODE(n_visits, n) = 0;
     NODE(n_inflight, n) = 0;
     NODE(n_nchild, n) = total_children;
-    NODE(n_puct, n) = 1.44f;
     NODE(n_flags, n) = terminal ? NF_FINALISED : 0;
     NODE(n_lead, n) = lead;
     NODE(n_depth, n) = depth;
@@ -530,13 +559,15 @@ GZP_HDN int gzp_create_node(GameView& V, int parent, int depth) {
 #endif
                 x &= x - 1;
                 const int ci = c0 + k++;
-                CHILD(c_to, ci) = -1;
-                CHILD(c_owner, ci) = n;
-                CHILD(c_trav, ci) = 0;
-                CHILD(c_prob_orig, ci) = 1.0f;
-                CHILD(c_prob, ci) = 1.0f;
-                CHILD(c_next, ci) = 0.0f;
-                CHILD(c_move, ci) = (w - E->legal_word_off[lead]) * 32 + b;
+                GzpChild k;
+                k.c_to = -1;
+                k.c_move = (int16_t)((w - E->legal_word_off[lead]) * 32 + b);
+                k.c_flags = 0; k.c_inflight = 0;
+                k.c_trav = 0;
+                k.c_prob = 1.0f; k.c_prob_orig = 1.0f; k.c_next = 0.0f;
+                k.c_score = -1.0f; k.c_visits = 0;
+                V.E->children[V.cb + ci] = k;
+                V.E->c_owner[V.cb + ci] = n;
             }
         }
     } else {
@@ -563,6 +594,27 @@ GZP_HDN void gzp_reply(GameView& V, int n) {
     const int c0 = NODE(n_child0, n);
     const float* pol = E->nn_policy + (int64_t)g * E->policy_stride + E->policy_off[lead];
     float* stage = V.C.tmp;
+#ifdef __CUDA_ARCH__
+    if (nc <= 32) {
+        // warp path: child i in lane i; the sum runs in child order like the reference's loop
+        GzpChild* kids = V.E->children + V.cb + c0;
+        const bool act = V.lane < nc;
+        float st = 0.0f;
+        if (act) {
+            const float p = pol[kids[V.lane].c_move];
+            st = p > 0.001f ? p : 0.001f;
+        }
+        float total = 0.0f;
+        for (int j = 0; j < nc; j++) total += __shfl_sync(0xffffffffu, st, j);
+        if (act) {
+            const float p = st / total;
+            kids[V.lane].c_prob_orig = p;
+            kids[V.lane].c_prob = p;
+        }
+        __syncwarp();
+    } else
+#endif
+    {
     // gather the raw policy of every child (lanes in parallel), then sum in child order
     GZP_SYNC();
     for (int i = V.lane; i < nc; i += GZP_LANES) {
@@ -578,6 +630,7 @@ GZP_HDN void gzp_reply(GameView& V, int n) {
         CHILD(c_prob, c0 + i) = p;
     }
     GZP_SYNC();
+    }
     const float* val = E->nn_value + (int64_t)g * E->n_rewards;
     for (int r = 0; r < E->R; r++) {
         float s = val[r];
@@ -590,6 +643,8 @@ GZP_HDN void gzp_reply(GameView& V, int n) {
         NFINAL(n, r) = s;
         NSCORE(n, r) = s;   // clamp of an already clamped value
     }
+    // n is the node the game's last request created: its parent's record keeps a copy of its score
+    if (V.c->req_parent >= 0) gzp_child_refresh(V, V.c->req_parent, V.c->req_child, n);
 }
 
 
@@ -634,7 +689,7 @@ GZP_HDN void gzp_order_children(GameView& V, int nc, Cmp cmp) {
 // chooseTopVisits (evaluator.cpp:1100-1159). Sort key: traversals desc, then policy_prob desc
 // (node.cpp:346-373), ordered with the restated std::sort.
 // Expects the cache to hold node n's children (gzp_cache_fill).
-GZP_HDN int gzp_choose_top_visits(const GameView& V, int n, int nc_known = -1) {
+GZP_RARE int gzp_choose_top_visits(const GameView& V, int n, int nc_known = -1) {
     const int nc = nc_known >= 0 ? nc_known : NODE(n_nchild, n);
     const PuctConf& cf = gzp_conf(V);
     const ChildCache& C = V.C;
@@ -672,7 +727,7 @@ GZP_HDN int gzp_choose_top_visits(const GameView& V, int n, int nc_known = -1) {
 // priorScore (evaluator.cpp:1195-1224)
 // node_final = the node's final score for its lead role, node_visits / nc its visit and child counts — the
 // caller has them in registers already (each would otherwise be a dependent global load on the descent).
-GZP_HDN float gzp_prior_score(const GameView& V, int n, int depth, float node_final, uint32_t node_visits, int nc) {
+GZP_RARE float gzp_prior_score(const GameView& V, int n, int depth, float node_final, uint32_t node_visits, int nc) {
     const PuctConf& cf = gzp_conf(V);
     const ChildCache& C = V.C;
     float prior = node_final;
@@ -698,7 +753,7 @@ struct GzpRng32 {
 };
 
 // setDirichletNoise (evaluator.cpp:1227-1297)
-GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n) {
+GZP_RARE void gzp_set_dirichlet_noise(GameView& V, int n) {
     float* scratch = V.C.tmp;
     const PuctConf& cf = gzp_conf(V);
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
@@ -736,45 +791,221 @@ GZP_HDN void gzp_set_dirichlet_noise(GameView& V, int n) {
     NODE(n_flags, n) |= NF_NOISE_SET;
 }
 
+struct GzpKid {          // warp path: one lane's child, unpacked (lanes >= nc: an unexpanded dummy)
+    int to, flags, inflight;
+    uint32_t trav, visits;
+    float prob, prob_orig, score;
+    bool act, expanded, fin;
+};
+
+#ifdef __CUDA_ARCH__
+// ------------------------------------------------------------------------------------------------
+// Warp path (device only): nodes with at most 32 children keep child i in lane i's REGISTERS — the 32-byte
+// record is two 16-byte loads per lane, one coalesced block per tree level — and every per-child quantity of
+// selectChild / priorScore / chooseTopVisits / converged is computed by the child's own lane. None of them
+// needs the reference's sorted order as such, only its first element(s) with some property, which is a
+// max-reduction over (key, key, index) as long as the maximum is unique — and when it is not, libstdc++'s
+// insertion sort (n <= 16) keeps equal elements in index order, so the lowest lane wins. Results are those of
+// the generic code below, which still handles everything unusual: more than 32 children, ties among more
+// than 16 children (libstdc++'s introsort decides those), the root latch limiter, children with evaluations
+// in flight, nodes whose children are all proven losses, and the node that receives Dirichlet noise. A
+// warp-path function returns GZP_WARP_PUNT in those cases and the caller falls through to the generic code.
+#define GZP_WARP_PUNT (-2)
+#define GZP_FULL 0xffffffffu
+
+__device__ __forceinline__ unsigned gzp_ordered_bits(float f) {      // monotonic float -> unsigned
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// The first element of the reference's sort by (k1 desc, k2 desc) among the lanes with `pred`:
+// the lane, -1 when no lane has `pred`, GZP_WARP_PUNT when the maximum is shared and n > 16.
+__device__ __forceinline__ int gzp_warp_top(bool pred, unsigned k1, float k2, int nc) {
+    const unsigned any = __ballot_sync(GZP_FULL, pred);
+    if (!any) return -1;
+    const unsigned m1 = __reduce_max_sync(GZP_FULL, pred ? k1 : 0u);
+    const bool p1 = pred && k1 == m1;
+    const unsigned m2 = __reduce_max_sync(GZP_FULL, p1 ? gzp_ordered_bits(k2) : 0u);
+    const unsigned top = __ballot_sync(GZP_FULL, p1 && gzp_ordered_bits(k2) == m2);
+    if (__popc(top) > 1 && nc > 16) return GZP_WARP_PUNT;
+    return __ffs(top) - 1;
+}
+
+__device__ __forceinline__ GzpKid gzp_warp_load_kid(const GameView& V, int c0, int nc) {
+    GzpKid K;
+    K.act = V.lane < nc;
+    GzpChild k;
+    k.c_to = -1; k.c_move = 0; k.c_flags = 0; k.c_inflight = 0; k.c_trav = 0;
+    k.c_prob = 0.0f; k.c_prob_orig = 0.0f; k.c_next = 0.0f; k.c_score = -1.0f; k.c_visits = 0;
+    if (K.act) k = V.E->children[V.cb + c0 + V.lane];
+    K.to = k.c_to;
+    K.expanded = K.act && k.c_to >= 0;
+    K.trav = k.c_trav;
+    K.prob = k.c_prob;
+    K.prob_orig = k.c_prob_orig;
+    K.score = K.expanded ? k.c_score : -1.0f;
+    K.visits = K.expanded ? k.c_visits : 0u;
+    K.flags = K.expanded ? (int)k.c_flags : 0;
+    K.inflight = K.expanded ? (int)k.c_inflight : 0;
+    K.fin = K.expanded && (K.flags & NF_FINALISED) != 0;
+    return K;
+}
+
+// chooseTopVisits (evaluator.cpp:1100-1159): the sorted order is (traversals desc, prior desc)
+__device__ __forceinline__ int gzp_warp_top_visits(const GameView& V, const GzpKid& K, int nc, float ratio) {
+    const bool win = K.fin && K.score > 0.99;
+    const bool loss = K.fin && K.score < 0.01;
+    const int w = gzp_warp_top(K.act && win, K.trav, K.prob, nc);        // the first proven win in sorted order
+    if (w != -1) return w;
+    const bool cand = K.act && !loss;
+    const int i0 = gzp_warp_top(cand, K.trav, K.prob, nc);
+    if (i0 == GZP_WARP_PUNT) return GZP_WARP_PUNT;
+    if (ratio > 0 && i0 >= 0) {
+        const int i1 = gzp_warp_top(cand && V.lane != i0, K.trav, K.prob, nc);
+        if (i1 == GZP_WARP_PUNT) return GZP_WARP_PUNT;
+        if (i1 >= 0) {
+            const int to0 = __shfl_sync(GZP_FULL, K.to, i0), to1 = __shfl_sync(GZP_FULL, K.to, i1);
+            if (to0 >= 0 && to1 >= 0) {
+                const float t0 = (float)__shfl_sync(GZP_FULL, K.trav, i0), t1 = (float)__shfl_sync(GZP_FULL, K.trav, i1);
+                const float s0 = __shfl_sync(GZP_FULL, K.score, i0), s1 = __shfl_sync(GZP_FULL, K.score, i1);
+                if (t1 > t0 * ratio && s1 > s0) return i1;
+                return i0;
+            }
+        }
+    }
+    return gzp_warp_top(K.act, K.trav, K.prob, nc);                       // order[0]
+}
+
+// converged (evaluator.cpp:1342-1362): the two first children by (node visits desc, prior desc)
+__device__ __forceinline__ int gzp_warp_converged(const GameView& V, const GzpKid& K, int nc, int count) {
+    const int a = gzp_warp_top(K.act, K.visits, K.prob, nc);
+    if (a == GZP_WARP_PUNT) return GZP_WARP_PUNT;
+    const int b = gzp_warp_top(K.act && V.lane != a, K.visits, K.prob, nc);
+    if (b == GZP_WARP_PUNT) return GZP_WARP_PUNT;
+    const int toa = __shfl_sync(GZP_FULL, K.to, a), tob = __shfl_sync(GZP_FULL, K.to, b);
+    if (toa >= 0 && tob >= 0) {
+        const float sa = __shfl_sync(GZP_FULL, K.score, a), sb = __shfl_sync(GZP_FULL, K.score, b);
+        const uint32_t va = __shfl_sync(GZP_FULL, K.visits, a), vb = __shfl_sync(GZP_FULL, K.visits, b);
+        if (sa > sb && va > vb + (uint32_t)count) return 1;
+    }
+    return 0;
+}
+
+// selectChild (evaluator.cpp:341-517). The reference scans the children in sortedChildrenSelect order, keeps
+// its running best score as a FLOAT and lets a child replace the best when its DOUBLE score exceeds it. With F
+// the largest float-rounded score, the first child (in scan order) that rounds to F always replaces the best
+// (rounding is monotonic), nothing that rounds below F can replace it afterwards, and a later child that
+// rounds to F replaces it only if its double score is above F. So the scan order matters only among the
+// children that round to F: usually one, and then no order is needed at all.
+__device__ int gzp_warp_select(GameView& V, const GzpKid& K, int nc, uint32_t node_visits, float node_final,
+                               float puct_c, int depth, int* chosen_to) {
+    const PuctConf& cf = gzp_conf(V);
+    const int lane = V.lane;
+    if (node_visits > 1000 && node_visits < 40000000 && depth == 0) return GZP_WARP_PUNT;      // root latch limiter
+    if (__any_sync(GZP_FULL, K.act && K.trav > 0 && K.inflight > 0)) return GZP_WARP_PUNT;     // virtual-loss discount
+    // ---- priorScore (evaluator.cpp:1195-1224)
+    float prior = node_final;
+    if (node_visits > 8) {
+        const int best = gzp_warp_top_visits(V, K, nc, cf.top_visits_best_guess_converge_ratio);
+        if (best == GZP_WARP_PUNT) return GZP_WARP_PUNT;
+        const int bto = __shfl_sync(GZP_FULL, K.to, best);
+        const float bsc = __shfl_sync(GZP_FULL, K.score, best);
+        if (bto >= 0) prior = bsc;
+    }
+    float fpu = depth == 0 ? cf.fpu_prior_discount_root : cf.fpu_prior_discount;
+    if (fpu > 0) {
+        const float mine = (K.expanded && K.visits > 0) ? K.prob : 0.0f;
+        float total = 0.0f;
+        for (int j = 0; j < nc; j++) total += __shfl_sync(GZP_FULL, mine, j);       // in child order, as the reference sums
+        fpu *= sqrtf(total);
+        prior -= fpu;
+    }
+    // ---- this lane's child: score + exploration (evaluator.cpp:393-457)
+    const double sqrt_node_visits = sqrt((double)(node_visits + 1u));
+    double exploration = (double)(puct_c * K.prob) * sqrt_node_visits / ((int)K.trav + 1 + (double)K.inflight);
+    double child_score = prior;
+    bool badfb = false, winret = false;
+    if (K.expanded) {
+        child_score = K.score;
+        if (K.fin) {
+            if (child_score > 0.99) {
+                if (depth > 0) winret = true;
+                else child_score *= 1.0f + puct_c;
+            } else if (child_score < 0.01) {
+                badfb = true;
+            } else {
+                exploration = 0.0;
+            }
+        }
+    }
+    int best_child;
+    const unsigned wm = __ballot_sync(GZP_FULL, K.act && winret);
+    if (wm) {
+        // a proven win below the root is taken at once: the first one in scan order, i.e. the highest score
+        // (expanded children sort by score); equal scores keep index order up to 16 children
+        const unsigned m = __reduce_max_sync(GZP_FULL, (K.act && winret) ? gzp_ordered_bits(K.score) : 0u);
+        const unsigned top = __ballot_sync(GZP_FULL, K.act && winret && gzp_ordered_bits(K.score) == m);
+        if (__popc(top) > 1 && nc > 16) return GZP_WARP_PUNT;
+        best_child = __ffs(top) - 1;
+    } else {
+        const bool elig = K.act && !badfb;
+        const double score = child_score + exploration;
+        const float f = (float)score;
+        const unsigned Fu = __reduce_max_sync(GZP_FULL, elig ? gzp_ordered_bits(f) : 0u);
+        const unsigned S = __ballot_sync(GZP_FULL, elig && gzp_ordered_bits(f) == Fu);
+        if (!S) return GZP_WARP_PUNT;                     // only proven losses: the generic scan picks the fallback
+        const float F = __shfl_sync(GZP_FULL, f, __ffs(S) - 1);
+        if (!(F > -1.0f)) return GZP_WARP_PUNT;           // (float best_score = -1 is never reached by a real score)
+        if (__popc(S) == 1) {
+            best_child = __ffs(S) - 1;
+        } else {
+            if (nc > 16) return GZP_WARP_PUNT;
+            // several children round to F: their scan order decides (stable order of sortedChildrenSelect's
+            // comparator, evaluator.cpp:242-263). pos = this lane's position among them.
+            int pos = 0;
+            const bool inS = (S >> lane) & 1u;
+            for (unsigned rest = S; rest; rest &= rest - 1) {
+                const int j = __ffs(rest) - 1;
+                const float sb = __shfl_sync(GZP_FULL, K.score, j), pob = __shfl_sync(GZP_FULL, K.prob_orig, j);
+                const bool both = K.score < 0 && sb < 0;
+                const bool ji = both ? (pob > K.prob_orig) : (sb > K.score);
+                const bool ij = both ? (K.prob_orig > pob) : (K.score > sb);
+                if (j != lane && (ji || (!ij && j < lane))) pos++;
+            }
+            // the first of them takes the lead; a later one replaces it only with a double score above F
+            const unsigned later = __ballot_sync(GZP_FULL, inS && pos > 0 && score > (double)F);
+            if (later) {
+                const unsigned m = __reduce_max_sync(GZP_FULL, (inS && pos > 0 && score > (double)F) ? (unsigned)pos : 0u);
+                best_child = __ffs(__ballot_sync(GZP_FULL, inS && (unsigned)pos == m)) - 1;
+            } else {
+                best_child = __ffs(__ballot_sync(GZP_FULL, inS && pos == 0)) - 1;
+            }
+        }
+    }
+    *chosen_to = __shfl_sync(GZP_FULL, K.to, best_child);
+    return best_child;
+}
+#endif  // __CUDA_ARCH__
+
 // selectChild (evaluator.cpp:341-517). Appends to the path; returns the child index within the
 // node (or -1 when nothing is selectable, which cannot happen with one evaluation in flight).
 struct GzpSelInfo { int to; int inflight; };   // the chosen child's node (or -1) and node n's in-flight count, read with the header
 
-GZP_HDN int gzp_select_child(GameView& V, int n, GzpSelInfo* info = nullptr) {
-    const PuctEngine* E = V.E;
+// The generic form of selectChild: children staged in the cache, the reference's sorted scan reproduced step by
+// step (any child count, the root latch limiter and the virtual-loss discount with their random draws,
+// Dirichlet noise). The warp path above covers the common case on the device.
+GZP_RARE int gzp_select_child_generic(GameView& V, int n, const GzpNode& nd, GzpSelInfo* info, float puct_c) {
     GameCtl* c = V.c;
     const PuctConf& cf = gzp_conf(V);
     const int depth = c->path_len;
-    if (c->path_len >= E->MAXD) { c->error = GZP_ERR_PATH; return -1; }
-    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
-    const int lead = NODE(n_lead, n);
+    const int nc = nd.n_nchild;
+    const int lead = nd.n_lead;
     int32_t* pn = V.pn;
     int32_t* pc = V.pc;
-
-    // setPuctConstant (evaluator.cpp:1300-1307); the node's visit count is read once for the whole function
-    // (nothing below writes it) and the constant is kept in a register besides being stored
-    const uint32_t node_visits = NODE(n_visits, n);
-    const int node_inflight = NODE(n_inflight, n);
-    if (info) { info->to = -1; info->inflight = node_inflight; }
+    const uint32_t node_visits = nd.n_visits;
     float node_finals[GZP_MAX_ROLES];
 #pragma unroll
-    for (int r = 0; r < GZP_MAX_ROLES; r++) node_finals[r] = NFINAL(n, r);      // one 16-byte line, with the header
-    float puct_c;
-    {
-        const float base = 19652.0f;
-        const float k = depth == 0 ? cf.puct_constant_root : cf.puct_constant;
-        float pcst = gz_logf(((float)(1u + node_visits) + base) / base);   // std::log(float) == glibc logf
-        pcst += k;
-        NODE(n_puct, n) = pcst;
-        puct_c = pcst;
-    }
-    c->total_sel_nodes++;
-    c->total_sel_children += (uint64_t)nc;
-    if (nc == 1) {
-        pn[c->path_len] = n; pc[c->path_len] = 0; c->path_len++;
-        if (info) info->to = CHILD(c_to, c0);
-        return 0;
-    }
+    for (int r = 0; r < GZP_MAX_ROLES; r++) node_finals[r] = nd.final_[r];
     gzp_cache_fill(V, n);
     ChildCache& C = V.C;
     if (depth == 0) gzp_set_dirichlet_noise(V, n);
@@ -934,8 +1165,189 @@ GZP_HDN int gzp_select_child(GameView& V, int n, GzpSelInfo* info = nullptr) {
     return best_child;
 }
 
-// backup (evaluator.cpp:519-656)
-GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
+// `nd` is node n's record as the caller read it (one 64-byte line); `preloaded_kid` (device warp path) this lane's
+// child of n when the caller already holds it.
+GZP_HDN int gzp_select_child(GameView& V, int n, const GzpNode& nd, GzpSelInfo* info = nullptr,
+                             const GzpKid* preloaded_kid = nullptr) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    const PuctConf& cf = gzp_conf(V);
+    const int depth = c->path_len;
+    if (c->path_len >= E->MAXD) { c->error = GZP_ERR_PATH; return -1; }
+    const int nc = nd.n_nchild, c0 = nd.n_child0;
+    const int lead = nd.n_lead;
+    int32_t* pn = V.pn;
+    int32_t* pc = V.pc;
+
+    // setPuctConstant (evaluator.cpp:1300-1307)
+    const uint32_t node_visits = nd.n_visits;
+    const int node_inflight = nd.n_inflight;
+    if (info) { info->to = -1; info->inflight = node_inflight; }
+    float node_finals[GZP_MAX_ROLES];
+#pragma unroll
+    for (int r = 0; r < GZP_MAX_ROLES; r++) node_finals[r] = nd.final_[r];
+    float puct_c;
+    {
+        const float base = 19652.0f;
+        const float k = depth == 0 ? cf.puct_constant_root : cf.puct_constant;
+        float pcst = gz_logf(((float)(1u + node_visits) + base) / base);   // std::log(float) == glibc logf
+        pcst += k;
+        puct_c = pcst;        // (the reference also stores it in the node, for its tree dump only)
+    }
+    c->total_sel_nodes++;
+    c->total_sel_children += (uint64_t)nc;
+    if (nc == 1) {
+        pn[c->path_len] = n; pc[c->path_len] = 0; c->path_len++;
+        if (info) info->to = CHILD(c_to, c0);
+        return 0;
+    }
+    V.work++;
+#ifdef __CUDA_ARCH__
+    // warp path (children in registers) unless this is the root select that has to draw Dirichlet noise first
+    if (nc <= 32 && V.ord &&
+        !(depth == 0 && cf.dirichlet_noise_pct >= 0 && !(nd.n_flags & NF_NOISE_SET) &&
+          !(nd.score[lead < 0 ? 0 : lead] > 0.95))) {
+        const GzpKid K = preloaded_kid ? *preloaded_kid : gzp_warp_load_kid(V, c0, nc);
+        int to = -1;
+        const int pick = gzp_warp_select(V, K, nc, node_visits, node_finals[lead < 0 ? 0 : lead], puct_c, depth, &to);
+        if (pick != GZP_WARP_PUNT) {
+            if (pick >= 0) {
+                pn[c->path_len] = n; pc[c->path_len] = pick; c->path_len++;
+                if (info) info->to = to;
+            }
+            return pick;
+        }
+    }
+#endif
+    return gzp_select_child_generic(V, n, nd, info, puct_c);
+}
+
+#ifdef __CUDA_ARCH__
+// backup on the warp path: lane i owns path element i (paths of at most 32 elements, no MCTS-prover
+// finalisation). The walk from the leaf to the root is sequential only in the scores it hands upwards, and
+// those change only at finalised nodes (which pass their own scores on instead, evaluator.cpp:578-583): the
+// scores reaching element i are those of the nearest finalised element below it, else the leaf's. So every
+// lane can fetch its node record and chosen-child record, apply the reference's update to its own node and
+// write it back at once — two memory round trips for the whole path instead of two per level — and the copy
+// of the child node's statistics kept in the parent's record (GzpChild) comes from the lane below by shuffle.
+__device__ void gzp_backup_warp(GameView& V, const float* new_scores) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    const int R = E->R;
+    const int L = c->path_len;
+    const int lane = V.lane;
+    __syncwarp();
+    const bool act = lane < L;
+    const int n = act ? V.pn[lane] : 0;
+    const int choice = act ? V.pc[lane] : -1;
+    GzpNode nd;
+    nd.n_parent = -1; nd.n_child0 = 0; nd.n_nchild = 0; nd.n_visits = 0; nd.n_inflight = 0; nd.n_flags = 0; nd.n_lead = 0; nd.n_depth = 0;
+#pragma unroll
+    for (int r = 0; r < GZP_MAX_ROLES; r++) { nd.score[r] = 0.0f; nd.final_[r] = 0.0f; }
+    GzpNode* np = V.E->nodes + V.nb + n;
+    if (act) nd = *np;
+    GzpChild* kp = V.E->children + V.cb + nd.n_child0 + (choice >= 0 ? choice : 0);
+    uint32_t ctrav = 0;
+    float cprob = 0.0f;
+    if (act && choice >= 0) { ctrav = kp->c_trav; cprob = kp->c_prob; }
+    const int lead = nd.n_lead;
+    const bool finalised = act && (nd.n_flags & NF_FINALISED) != 0;
+    // the scores that reach this element
+    const unsigned fin_mask = __ballot_sync(GZP_FULL, finalised);
+    const unsigned below_fin = lane >= 31 ? 0u : (fin_mask & ~((2u << lane) - 1u));
+    const int src = below_fin ? __ffs(below_fin) - 1 : lane;
+    float sc[GZP_MAX_ROLES];
+#pragma unroll
+    for (int r = 0; r < GZP_MAX_ROLES; r++) {
+        sc[r] = nd.score[r];
+        if (r < R) {
+            const float from = __shfl_sync(GZP_FULL, nd.score[r], src);
+            const float ns = below_fin ? from : new_scores[r];
+            if (!finalised) {
+                float visits = (float)nd.n_visits;
+                if (visits > 100000) visits = 100000 + 0.1f * (visits - 100000);
+                sc[r] = (visits * sc[r] + ns) / (visits + 1.0f);
+            }
+        }
+    }
+    const uint32_t visits_u = nd.n_visits + 1u;
+    const int inflight = nd.n_inflight > 0 ? nd.n_inflight - 1 : nd.n_inflight;
+    // the statistics of the element below (the node this one's chosen child leads to), after its update
+    const bool have_below = lane + 1 < L;
+    float below_sc = 0.0f;
+#pragma unroll
+    for (int r = 0; r < GZP_MAX_ROLES; r++) {
+        if (r < R) {
+            const float v = __shfl_down_sync(GZP_FULL, sc[r], 1);
+            if (r == (lead < 0 ? 0 : lead)) below_sc = v;
+        }
+    }
+    const uint32_t below_visits = __shfl_down_sync(GZP_FULL, visits_u, 1);
+    const int below_flags = __shfl_down_sync(GZP_FULL, nd.n_flags, 1);
+    const int below_inflight = __shfl_down_sync(GZP_FULL, inflight, 1);
+    bool need_norm = false;
+    if (act) {
+        if (!finalised) {
+#pragma unroll
+            for (int r = 0; r < GZP_MAX_ROLES; r++) if (r < R) np->score[r] = sc[r];
+        }
+        np->n_visits = visits_u;
+        if (nd.n_inflight > 0) np->n_inflight = inflight;
+        if (choice >= 0) {
+            if (have_below) {
+                kp->c_score = below_sc;
+                kp->c_visits = below_visits;
+                kp->c_flags = (uint8_t)(below_flags & NF_FINALISED);
+                kp->c_inflight = (uint8_t)(below_inflight > 255 ? 255 : below_inflight);
+            }
+            kp->c_trav = ctrav + 1;
+            if (visits_u > 23) {
+                const float cur_score = lead == 1 ? sc[1] : lead == 2 ? sc[2] : lead == 3 ? sc[3] : sc[0];
+                float apply, mn;
+                if (cur_score > 0.3 && cur_score < 0.7) { apply = 0.995f; mn = 0.02f; }
+                else if (cur_score > 0.15 && cur_score < 0.85) { apply = 0.9975f; mn = 0.03f; }
+                else { apply = 0.9975f; mn = 0.10f; }
+                float p = cprob;
+                if (p > mn) {
+                    p *= apply;
+                    p = mn > p ? mn : p;
+                    kp->c_prob = p;
+                }
+            }
+        }
+        need_norm = (visits_u % 100 == 0);
+    }
+    // normaliseX (node.h:192-214), once per 100 visits of a node: the generic loops, on the records
+    unsigned norm = __ballot_sync(GZP_FULL, need_norm);
+    while (norm) {
+        const int index = __ffs(norm) - 1;
+        norm &= norm - 1;
+        __syncwarp();
+        const int c0 = __shfl_sync(GZP_FULL, nd.n_child0, index), nc = __shfl_sync(GZP_FULL, nd.n_nchild, index);
+        GzpChild* kids = V.E->children + V.cb + c0;
+        float total = 0;
+        for (int i = 0; i < nc; i++) total += kids[i].c_prob;
+        __syncwarp();
+        if (total > 1.17549435e-38f) {
+            for (int i = lane; i < nc; i += 32) kids[i].c_prob /= total;
+        } else {
+            for (int i = lane; i < nc; i += 32) kids[i].c_prob = (float)(1.0 / nc);
+        }
+    }
+    __syncwarp();
+}
+#endif
+
+// backup (evaluator.cpp:519-656). Walking the path from the leaf up, every node's new statistics are also
+// copied into its parent's child record (the next node on the walk), see GzpChild.
+GZP_RARE void gzp_backup_generic(GameView& V, float* new_scores);
+GZP_HD void gzp_backup(GameView& V, float* new_scores) {
+#ifdef __CUDA_ARCH__
+    if (!gzp_conf(V).backup_finalised && V.c->path_len <= 32) { gzp_backup_warp(V, new_scores); return; }
+#endif
+    gzp_backup_generic(V, new_scores);
+}
+GZP_RARE void gzp_backup_generic(GameView& V, float* new_scores) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     const PuctConf& cf = gzp_conf(V);
@@ -943,21 +1355,37 @@ GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
     const int32_t* pn = V.pn;
     const int32_t* pc = V.pc;
     bool bp_finalised_only_once = cf.backup_finalised != 0;
+    // statistics of the node handled in the previous iteration (the child of this one on the path)
+    bool have_below = false;
+    float below_sc[GZP_MAX_ROLES] = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t below_visits = 0;
+    int below_flags = 0, below_inflight = 0;
     for (int index = c->path_len - 1; index >= 0; index--) {
         const int n = pn[index];
         const int choice = pc[index];
-        const int lead = NODE(n_lead, n);
-        if (bp_finalised_only_once && !gzp_is_finalised(V, n) && lead >= 0) {
+        GzpNode& nd = V.E->nodes[V.nb + n];
+        const int lead = nd.n_lead;
+        const int c0n = nd.n_child0;
+        GzpChild* kids = V.E->children + V.cb + c0n;
+        if (choice >= 0 && have_below) {
+            // before anything reads the children of n: the chosen child's node just changed
+            GzpChild& k = kids[choice];
+            k.c_score = below_sc[lead < 0 ? 0 : lead];
+            k.c_visits = below_visits;
+            k.c_flags = (uint8_t)(below_flags & NF_FINALISED);
+            k.c_inflight = (uint8_t)(below_inflight > 255 ? 255 : below_inflight);
+        }
+        if (bp_finalised_only_once && !(nd.n_flags & NF_FINALISED) && lead >= 0) {
             bp_finalised_only_once = false;
             // forceFinalise
             float best_s = -1;
             int best = -1, win = -1;
             bool more = false;
-            const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
+            const int nc = nd.n_nchild;
             for (int i = 0; i < nc; i++) {
-                const int to = CHILD(c_to, c0 + i);
-                if (to >= 0 && gzp_is_finalised(V, to)) {
-                    const float s = NSCORE(to, lead);
+                const GzpChild& k = kids[i];
+                if (k.c_to >= 0 && (k.c_flags & NF_FINALISED)) {
+                    const float s = k.c_score;
                     if (s > 0.99) { win = i; break; }
                     if (s > best_s) { best_s = s; best = i; }
                 } else {
@@ -966,25 +1394,24 @@ GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
             }
             const int fc = win >= 0 ? win : (more ? -1 : best);
             if (fc >= 0) {
-                const int to = CHILD(c_to, c0 + fc);
-                for (int r = 0; r < R; r++) NSCORE(n, r) = NSCORE(to, r);
-                NODE(n_flags, n) |= NF_FINALISED;
+                const int to = kids[fc].c_to;
+                for (int r = 0; r < R; r++) nd.score[r] = NSCORE(to, r);
+                nd.n_flags |= NF_FINALISED;
             }
         }
         // everything this node needs, loaded in one go (through global pointers the compiler has to assume
         // that every store may alias the next load, so interleaved read-modify-writes cost a memory round
         // trip each); the arithmetic below is the reference's, in its order
-        const bool finalised = gzp_is_finalised(V, n);
-        uint32_t visits_u = NODE(n_visits, n);
-        const int inflight = NODE(n_inflight, n);
-        const int c0n = NODE(n_child0, n);
+        const int flags = nd.n_flags;
+        const bool finalised = (flags & NF_FINALISED) != 0;
+        uint32_t visits_u = nd.n_visits;
+        int inflight = nd.n_inflight;
         float sc[GZP_MAX_ROLES];
 #pragma unroll
-        for (int r = 0; r < GZP_MAX_ROLES; r++) sc[r] = r < R ? NSCORE(n, r) : 0.0f;
+        for (int r = 0; r < GZP_MAX_ROLES; r++) sc[r] = r < R ? nd.score[r] : 0.0f;
         uint32_t ctrav = 0;
         float cprob = 0.0f;
-        const int ci = c0n + (choice >= 0 ? choice : 0);
-        if (choice >= 0) { ctrav = CHILD(c_trav, ci); cprob = CHILD(c_prob, ci); }
+        if (choice >= 0) { ctrav = kids[choice].c_trav; cprob = kids[choice].c_prob; }
         if (finalised) {
             for (int r = 0; r < R; r++) new_scores[r] = sc[r];
         } else {
@@ -993,14 +1420,14 @@ GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
                 if (visits > 100000) visits = 100000 + 0.1f * (visits - 100000);
                 const float score = (visits * sc[r] + new_scores[r]) / (visits + 1.0f);
                 sc[r] = score;
-                NSCORE(n, r) = score;
+                nd.score[r] = score;
             }
         }
         visits_u += 1;
-        NODE(n_visits, n) = visits_u;
-        if (inflight > 0) NODE(n_inflight, n) = inflight - 1;
+        nd.n_visits = visits_u;
+        if (inflight > 0) { inflight -= 1; nd.n_inflight = inflight; }
         if (choice >= 0) {
-            CHILD(c_trav, ci) = ctrav + 1;
+            kids[choice].c_trav = ctrav + 1;
             if (visits_u > 23) {
                 const float cur_score = sc[lead];
                 float apply, mn;
@@ -1011,30 +1438,50 @@ GZP_HDN void gzp_backup(GameView& V, float* new_scores) {
                 if (p > mn) {
                     p *= apply;
                     p = mn > p ? mn : p;
-                    CHILD(c_prob, ci) = p;
+                    kids[choice].c_prob = p;
                 }
             }
         }
         if (visits_u % 100 == 0) {
             // normaliseX (node.h:192-214)
-            const int nc = NODE(n_nchild, n), c0 = c0n;
+            const int nc = nd.n_nchild;
             float total = 0;
-            for (int i = 0; i < nc; i++) total += CHILD(c_prob, c0 + i);
+            for (int i = 0; i < nc; i++) total += kids[i].c_prob;
             if (total > 1.17549435e-38f) {
-                for (int i = 0; i < nc; i++) CHILD(c_prob, c0 + i) /= total;
+                for (int i = 0; i < nc; i++) kids[i].c_prob /= total;
             } else {
-                for (int i = 0; i < nc; i++) CHILD(c_prob, c0 + i) = (float)(1.0 / nc);
+                for (int i = 0; i < nc; i++) kids[i].c_prob = (float)(1.0 / nc);
             }
         }
+        have_below = true;
+#pragma unroll
+        for (int r = 0; r < GZP_MAX_ROLES; r++) below_sc[r] = sc[r];
+        below_visits = visits_u;
+        below_flags = flags;
+        below_inflight = inflight;
     }
 }
 
 // converged (evaluator.cpp:1342-1362); sortedChildren = by visits of the child node desc, ties by
 // policy_prob desc (node.cpp:312-343), unexpanded children count as 0 visits.
-GZP_HDN bool gzp_converged(GameView& V, int count) {
+GZP_RARE bool gzp_converged_generic(GameView& V, int count, int n, int nc);
+// `nd` = the root's record. On the device warp path the root's children are loaded into registers here and
+// handed back through kid / have_kid for the select that follows.
+GZP_HDN bool gzp_converged(GameView& V, int count, const GzpNode& nd, GzpKid* kid = nullptr, bool* have_kid = nullptr) {
     const int n = V.c->root;
-    const int nc = NODE(n_nchild, n);
+    const int nc = nd.n_nchild;
     if (nc < 2) return true;
+#ifdef __CUDA_ARCH__
+    if (nc <= 32 && V.ord) {
+        const GzpKid K = gzp_warp_load_kid(V, nd.n_child0, nc);
+        if (kid) { *kid = K; *have_kid = true; }
+        const int r = gzp_warp_converged(V, K, nc, count);
+        if (r != GZP_WARP_PUNT) return r != 0;
+    }
+#endif
+    return gzp_converged_generic(V, count, n, nc);
+}
+GZP_RARE bool gzp_converged_generic(GameView& V, int count, int n, int nc) {
     gzp_cache_fill(V, n);
     const ChildCache& C = V.C;
     int* order = C.order;
@@ -1060,7 +1507,7 @@ GZP_HD float gzp_temperature(const PuctConf& cf, int depth) {
 }
 
 // getProbabilities (evaluator.cpp:1161-1192): fills next_prob of every child.
-GZP_HDN void gzp_get_probabilities(GameView& V, int n, float temperature, bool use_policy) {
+GZP_RARE void gzp_get_probabilities(GameView& V, int n, float temperature, bool use_policy) {
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
     const float node_visits = (float)(NODE(n_visits, n) + 0.001 * nc);
     float total = 0.0f;
@@ -1075,7 +1522,7 @@ GZP_HDN void gzp_get_probabilities(GameView& V, int n, float temperature, bool u
 }
 
 // chooseTemperature (evaluator.cpp:1473-1510); iteration order = sortedChildren(.., next_prob).
-GZP_HDN int gzp_choose_temperature(GameView& V, int n) {
+GZP_RARE int gzp_choose_temperature(GameView& V, int n) {
     const PuctConf& cf = gzp_conf(V);
     const float temperature = gzp_temperature(cf, NODE(n_depth, n));
     if (temperature < 0) { gzp_cache_fill(V, n); return gzp_choose_top_visits(V, n); }
@@ -1099,7 +1546,7 @@ GZP_HDN int gzp_choose_temperature(GameView& V, int n) {
     return order[nc - 1];
 }
 
-GZP_HDN int gzp_choose(GameView& V, int n) {
+GZP_RARE int gzp_choose(GameView& V, int n) {
     const PuctConf& cf = gzp_conf(V);
     if (cf.choose == 1) return gzp_choose_temperature(V, n);
     gzp_cache_fill(V, n);
@@ -1107,7 +1554,7 @@ GZP_HDN int gzp_choose(GameView& V, int n) {
 }
 
 // resetRootNode (evaluator.cpp:1019-1030)
-GZP_HDN void gzp_reset_root_node(GameView& V) {
+GZP_RARE void gzp_reset_root_node(GameView& V) {
     const int n = V.c->root;
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
     for (int i = 0; i < nc; i++) {
@@ -1175,7 +1622,7 @@ GZP_HDN void gzp_uniq_add(const PuctEngine* E, const uint32_t* st, int lane) {
 
 // ------------------------------------------------------------------------------------------------
 // SelfPlayManager::createSample (selfplaymanager.cpp:72-119) into the game's pending list.
-GZP_HDN void gzp_create_sample(GameView& V, int n) {
+GZP_RARE void gzp_create_sample(GameView& V, int n) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     if (c->n_samples >= E->MAXPEND) { c->error = GZP_ERR_SAMPLES; return; }
@@ -1209,7 +1656,7 @@ GZP_HDN void gzp_create_sample(GameView& V, int n) {
 }
 
 // SelfPlay::addSamples (selfplay.cpp:244-288): stamp the game's samples and publish them.
-GZP_HDN void gzp_add_samples(GameView& V, const float* final_scores, int game_depth) {
+GZP_RARE void gzp_add_samples(GameView& V, const float* final_scores, int game_depth) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     bool fp0 = false, fp1 = false;
@@ -1255,7 +1702,7 @@ GZP_HDN void gzp_add_samples(GameView& V, const float* final_scores, int game_de
 }
 
 // SelfPlay::resign (selfplay.cpp:45-74)
-GZP_HDN bool gzp_resign(GameView& V, int n) {
+GZP_RARE bool gzp_resign(GameView& V, int n) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     const float score = NSCORE(n, NODE(n_lead, n));
@@ -1305,10 +1752,10 @@ GZP_HDN void gzp_reroot_compact(GameView& V, int new_root, int tid, int T, Group
         int reach = 0, nch = 0;
         if (i < N) {
             int q = i;
-            while (q > r && q >= b) q = E->n_parent[nb + q];
+            while (q > r && q >= b) q = E->nodes[nb + q].n_parent;
             if (q == r) reach = 1;
             else if (q > r) reach = E->n_newidx[nb + q] >= 0;     // q < b: decided by an earlier chunk
-            if (reach) nch = E->n_nchild[nb + i];
+            if (reach) nch = E->nodes[nb + i].n_nchild;
         }
         int en, ec, tn, tc;
         grp.scan2(reach, nch, en, ec, tn, tc);
@@ -1320,66 +1767,48 @@ GZP_HDN void gzp_reroot_compact(GameView& V, int new_root, int tid, int T, Group
         child_base += tc;
         grp.sync();
     }
-    // ---- pass 2: children, in place, left to right (new position <= old position)
+    // ---- pass 2: child records, in place, left to right (new position <= old position)
     for (int b = 0; b < NC; b += T) {
         const int k = b + tid;
-        int dst = -1, to = -1, mv = 0, own = 0;
-        uint32_t tr = 0;
-        float p = 0, po = 0, nx = 0;
+        int dst = -1, own = 0;
+        GzpChild rec;
         if (k < NC) {
             const int o = E->c_owner[cb + k];
             const int no = E->n_newidx[nb + o];
             if (no >= 0) {
-                dst = E->n_newc0[nb + o] + (k - E->n_child0[nb + o]);
-                const int t0 = E->c_to[cb + k];
-                to = t0 >= 0 ? E->n_newidx[nb + t0] : -1;
-                mv = E->c_move[cb + k]; tr = E->c_trav[cb + k];
-                p = E->c_prob[cb + k]; po = E->c_prob_orig[cb + k]; nx = E->c_next[cb + k];
+                dst = E->n_newc0[nb + o] + (k - E->nodes[nb + o].n_child0);
+                rec = E->children[cb + k];
+                if (rec.c_to >= 0) rec.c_to = E->n_newidx[nb + rec.c_to];
                 own = no;
             }
         }
         grp.sync();
         if (dst >= 0) {
-            E->c_to[cb + dst] = to; E->c_move[cb + dst] = mv; E->c_owner[cb + dst] = own;
-            E->c_trav[cb + dst] = tr; E->c_prob[cb + dst] = p; E->c_prob_orig[cb + dst] = po; E->c_next[cb + dst] = nx;
+            E->children[cb + dst] = rec;
+            E->c_owner[cb + dst] = own;
         }
         grp.sync();
     }
-    // ---- pass 3: nodes, in place
+    // ---- pass 3: node records, in place
     for (int b = 0; b < N; b += T) {
         const int i = b + tid;
         int dst = -1;
-        int parent = -1, child0 = -1, nchild = 0, inflight = 0, flags = 0, lead = 0, depth = 0;
-        uint32_t visits = 0;
-        float puct = 0, sc[GZP_MAX_ROLES], fn[GZP_MAX_ROLES];
+        GzpNode rec;
         int ot[GZP_MAX_ROLES];
         if (i < N) {
             dst = E->n_newidx[nb + i];
             if (dst >= 0) {
-                const int p0 = E->n_parent[nb + i];
-                parent = (i == r || p0 < 0) ? -1 : E->n_newidx[nb + p0];
-                child0 = E->n_newc0[nb + i];
-                nchild = E->n_nchild[nb + i];
-                if (nchild == 0) child0 = -1;
-                inflight = E->n_inflight[nb + i]; flags = E->n_flags[nb + i]; lead = E->n_lead[nb + i];
-                depth = E->n_depth[nb + i]; visits = E->n_visits[nb + i]; puct = E->n_puct[nb + i];
-                for (int k = 0; k < GZP_MAX_ROLES; k++) {
-                    sc[k] = E->n_score[(nb + i) * GZP_MAX_ROLES + k];
-                    fn[k] = E->n_final[(nb + i) * GZP_MAX_ROLES + k];
-                    ot[k] = E->n_other[(nb + i) * GZP_MAX_ROLES + k];
-                }
+                rec = E->nodes[nb + i];
+                const int p0 = rec.n_parent;
+                rec.n_parent = (i == r || p0 < 0) ? -1 : E->n_newidx[nb + p0];
+                rec.n_child0 = rec.n_nchild == 0 ? -1 : E->n_newc0[nb + i];
+                for (int k = 0; k < GZP_MAX_ROLES; k++) ot[k] = E->n_other[(nb + i) * GZP_MAX_ROLES + k];
             }
         }
         grp.sync();
         if (dst >= 0) {
-            E->n_parent[nb + dst] = parent; E->n_child0[nb + dst] = child0; E->n_nchild[nb + dst] = nchild;
-            E->n_inflight[nb + dst] = inflight; E->n_flags[nb + dst] = flags; E->n_lead[nb + dst] = lead;
-            E->n_depth[nb + dst] = depth; E->n_visits[nb + dst] = visits; E->n_puct[nb + dst] = puct;
-            for (int k = 0; k < GZP_MAX_ROLES; k++) {
-                E->n_score[(nb + dst) * GZP_MAX_ROLES + k] = sc[k];
-                E->n_final[(nb + dst) * GZP_MAX_ROLES + k] = fn[k];
-                E->n_other[(nb + dst) * GZP_MAX_ROLES + k] = ot[k];
-            }
+            E->nodes[nb + dst] = rec;
+            for (int k = 0; k < GZP_MAX_ROLES; k++) E->n_other[(nb + dst) * GZP_MAX_ROLES + k] = ot[k];
         }
         grp.sync();
     }
@@ -1456,12 +1885,12 @@ GZP_HDN void gzp_request_root(GameView& V, const uint32_t* state) {
     for (int r = 0; r < E->R; r++) E->x_moves[(int64_t)V.g * E->R + r] = -1;   // identity transition
 }
 
-GZP_HDN void gzp_finish_playout(GameView& V, int leaf) {
+GZP_HDN void gzp_finish_playout(GameView& V, const GzpNode& leaf) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     float scores[GZP_MAX_ROLES];
-    if (gzp_is_finalised(V, leaf)) c->playouts_finals++;
-    for (int r = 0; r < E->R; r++) scores[r] = NSCORE(leaf, r);
+    if (leaf.n_flags & NF_FINALISED) c->playouts_finals++;
+    for (int r = 0; r < E->R; r++) scores[r] = leaf.score[r];
     gzp_backup(V, scores);
     c->num_tree_playouts++;
     c->total_playouts++;
@@ -1478,17 +1907,21 @@ GZP_HDN void gzp_path_push(GameView& V, int n, int choice) {
 }
 
 // treePlayout (evaluator.cpp:658-720), resumable. Returns true when blocked on an expansion.
-GZP_HDN bool gzp_playout_continue(GameView& V) {
+// `root_nd` / `root_kid`: the root's record (and, on the device warp path, its children) when the caller has
+// just read them and this call starts a playout at the root.
+GZP_HDN bool gzp_playout_continue(GameView& V, const GzpNode* root_nd = nullptr, const GzpKid* root_kid = nullptr) {
     GameCtl* c = V.c;
     while (true) {
         const int cur = c->cur;
-        if (gzp_is_terminal(V, cur) || gzp_is_finalised(V, cur)) {
+        const GzpNode nd = root_nd ? *root_nd : V.E->nodes[V.nb + cur];       // one 64-byte line per tree level
+        if ((nd.n_flags & (NF_FORCE_TERMINAL | NF_FINALISED)) || nd.n_nchild == 0) {
             gzp_path_push(V, cur, -1);
-            gzp_finish_playout(V, cur);
+            gzp_finish_playout(V, nd);
             return false;
         }
         GzpSelInfo si;
-        const int child = gzp_select_child(V, cur, &si);
+        const int child = gzp_select_child(V, cur, nd, &si, root_nd ? root_kid : nullptr);
+        root_nd = nullptr;
         if (child < 0 || c->error) { c->error = c->error ? c->error : GZP_ERR_PATH; return true; }
         if (si.to < 0) {
             gzp_request_expand(V, cur, child, PUR_PLAYOUT);
@@ -1510,7 +1943,7 @@ GZP_HDN void gzp_start_search(GameView& V, int evals, int conf_sel) {
     c->phase = PH_SEARCH;
 }
 
-GZP_HDN void gzp_begin_game(GameView& V) {
+GZP_RARE void gzp_begin_game(GameView& V) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     c->match_count++;
@@ -1556,6 +1989,7 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
     }
     for (int iter = 0; iter < E->max_iters_per_step; iter++) {
         if (c->error) { c->phase = PH_HALT; return; }
+        if (V.work >= E->max_work_per_step) return;
         if (c->req != REQ_NONE) return;
         if (c->mode == 1 && c->phase == PH_AFTER_MOVE && !c->resume) {   // player: move applied
             c->phase = PH_IDLE;
@@ -1568,7 +2002,7 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
             if (c->req_purpose == PUR_PLAYOUT) {
                 if (gzp_is_finalised(V, N) || NODE(n_nchild, N) > 1) {
                     gzp_path_push(V, N, -1);
-                    gzp_finish_playout(V, N);
+                    gzp_finish_playout(V, V.E->nodes[V.nb + N]);
                 } else {
                     NODE(n_inflight, N) = NODE(n_inflight, N) + 1;
                     c->cur = N;
@@ -1624,11 +2058,14 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
             if (!c->in_playout) {
                 const PuctConf& cf = gzp_conf(V);
                 const int root = c->root;
-                const bool is_converged = gzp_converged(V, cf.converged_visits);
+                const GzpNode root_nd = V.E->nodes[V.nb + root];
+                GzpKid root_kid;
+                bool have_kid = false;
+                const bool is_converged = gzp_converged(V, cf.converged_visits, root_nd, &root_kid, &have_kid);
                 const int max_non_converged = (int)(c->max_evaluations * cf.evaluation_multiplier_to_convergence);
                 const int max_tree_playouts = 4 * max_non_converged;
                 bool brk = false;
-                if (gzp_is_finalised(V, root) && c->num_tree_playouts > 100) brk = true;
+                if ((root_nd.n_flags & NF_FINALISED) && c->num_tree_playouts > 100) brk = true;
                 else if (is_converged && c->num_tree_playouts > max_tree_playouts) brk = true;
                 else if (c->n_nodes + 4 > E->NCAP || c->n_children + E->max_actions + 4 > E->CCAP) brk = true;  // arena nearly full ("max nodes")
                 else if (is_converged && c->num_evaluations > c->max_evaluations) brk = true;
@@ -1641,6 +2078,8 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
                 c->cur = root;
                 c->path_len = 0;
                 c->in_playout = 1;
+                if (gzp_playout_continue(V, &root_nd, have_kid ? &root_kid : nullptr)) return;
+                break;
             }
             if (gzp_playout_continue(V)) return;
             break;
@@ -1789,7 +2228,10 @@ GZP_HDN void gzp_step_post(GameView& V) {
     const int N = gzp_create_node(V, parent, depth);
     c->req = REQ_NONE;
     if (N < 0) { c->phase = PH_HALT; return; }
-    if (parent >= 0) CHILD(c_to, NODE(n_child0, parent) + c->req_child) = N;
+    if (parent >= 0) {
+        CHILD(c_to, NODE(n_child0, parent) + c->req_child) = N;
+        gzp_child_refresh(V, parent, c->req_child, N);
+    }
     c->new_node = N;
     c->total_new_children += (uint64_t)NODE(n_nchild, N);
     const bool needs_eval = !gzp_is_finalised(V, N) && NODE(n_nchild, N) > 1;

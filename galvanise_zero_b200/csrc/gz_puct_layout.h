@@ -21,28 +21,13 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     const size_t NN = (size_t)E->G * E->NCAP;
     const size_t CC = (size_t)E->G * E->CCAP;
     const size_t G = (size_t)E->G;
-    E->n_parent = (int32_t*)take(NN * 4);
-    E->n_child0 = (int32_t*)take(NN * 4);
-    E->n_nchild = (int32_t*)take(NN * 4);
-    E->n_inflight = (int32_t*)take(NN * 4);
-    E->n_flags = (int32_t*)take(NN * 4);
-    E->n_lead = (int32_t*)take(NN * 4);
-    E->n_depth = (int32_t*)take(NN * 4);
-    E->n_visits = (uint32_t*)take(NN * 4);
-    E->n_score = (float*)take(NN * 4 * GZP_MAX_ROLES);
-    E->n_final = (float*)take(NN * 4 * GZP_MAX_ROLES);
-    E->n_puct = (float*)take(NN * 4);
+    E->nodes = (GzpNode*)take(NN * sizeof(GzpNode));
     E->n_state = (uint32_t*)take(NN * 4 * E->SW);
     E->n_other = (int32_t*)take(NN * 4 * GZP_MAX_ROLES);
-    E->c_to = (int32_t*)take(CC * 4);
-    E->c_move = (int32_t*)take(CC * 4);
+    E->children = (GzpChild*)take(CC * sizeof(GzpChild));
     E->c_owner = (int32_t*)take(CC * 4);
     E->n_newidx = (int32_t*)take(NN * 4);
     E->n_newc0 = (int32_t*)take(NN * 4);
-    E->c_trav = (uint32_t*)take(CC * 4);
-    E->c_prob = (float*)take(CC * 4);
-    E->c_prob_orig = (float*)take(CC * 4);
-    E->c_next = (float*)take(CC * 4);
     E->ctl = (GameCtl*)take(G * sizeof(GameCtl));
     E->path_node = (int32_t*)take(G * E->MAXD * 4);
     E->path_choice = (int32_t*)take(G * E->MAXD * 4);

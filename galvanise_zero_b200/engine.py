@@ -254,6 +254,10 @@ class PuctEngine(object):
         assert tuple(states.shape) == (self.n_games, self.state_words)
         _lib.check(self._L.gz_puct_set_start_states(self._h, states.data_ptr(), self._stream()))
 
+    def set_step_limits(self, max_iters=16, max_work=1 << 20):
+        self._L.gz_puct_set_step_limits.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        _lib.check(self._L.gz_puct_set_step_limits(self._h, int(max_iters), int(max_work)))
+
     def clear_unique_states(self):
         _lib.check(self._L.gz_puct_clear_unique_states(self._h, self._stream()))
 

@@ -212,6 +212,11 @@ int gz_puct_totals(gz_puct* h, double* h_out23, void* stream);
  * positions) at game depth 0 instead of the initial state — what handing SelfPlay another `initial_state`
  * (src/cpp/selfplaymanager.cpp:140, selfplay.cpp:313) does in the reference. Later games start normally. */
 int gz_puct_set_start_states(gz_puct* h, const uint32_t* d_states, void* stream);
+/* Per engine step a game runs until it needs the batch pipeline (a propnet pass / the network), but at most
+ * `max_iters` controller iterations and `max_work` tree levels descended (playouts that end in terminal or
+ * finalised nodes need no pipeline pass; the slowest game sets the duration of the step). Defaults 16 / unlimited.
+ * No reference counterpart: the reference runs one coroutine per game (src/cpp/scheduler.cpp). */
+int gz_puct_set_step_limits(gz_puct* h, int max_iters, int max_work);
 int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream);
 int gz_puct_clear_unique_states(gz_puct* h, void* stream);
 int gz_puct_command(gz_puct* h, int game, int cmd, int arg, int evals, const uint32_t* h_state, void* stream);

@@ -102,6 +102,7 @@ extern "C" void* hs_create(const int32_t* blob, int64_t n_words, int G, int mode
     E.READYCAP = 1 << 16;
     E.uniq_cap = 1 << 16;
     E.max_iters_per_step = 64;
+    E.max_work_per_step = 1 << 20;
     const size_t bytes = gzp_layout(&E, nullptr);
     H->arena.assign(bytes, 0);
     gzp_layout(&E, H->arena.data());
