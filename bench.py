@@ -338,8 +338,10 @@ PUCT_PRESETS = {
                                '1024 concurrent games per GPU'),
 }
 CPU_BATCH = 8          # games per reference manager (2 managers per worker thread) in the CPU arms
-CPU_WARM_S = 5.0       # the CPU arms' untimed warm-up
-CPU_WINDOW_S = 20.0    # ... and their timed window (one bounded sample)
+CPU_WARM_S = 2.5       # one CPU sample: untimed warm-up ...
+CPU_WINDOW_S = 7.5     # ... and timed window, in a fresh process with its own seeds
+CPU_INLINE_SAMPLES = 3     # the in-line cpu_baseline = mean over this many samples (30 s); the reference arm takes
+CPU_SEED0 = 0x5EED0000     # one sample per 2 contract steps, from the same seed sequence
 
 
 def puct_game(args):
@@ -351,8 +353,23 @@ def puct_selfplay_conf():
     return confs.selfplay_config_template(evals_per_move=PUCT_EVALS_PER_MOVE)
 
 
+def cpu_reference_selfplay_mean(game, n_samples):
+    """Mean over `n_samples` bounded samples (fresh process and seeds each) of the reference's self-play rate."""
+    runs = [cpu_reference_selfplay(game, rng_seed=CPU_SEED0 + 7919 * i) for i in range(n_samples)]
+    moves = sum(r['window_moves'] for r in runs)
+    secs = sum(r['window_s'] for r in runs)
+    cpu = dict(runs[0])
+    cpu['value'] = moves / secs
+    cpu['evals_per_s'] = sum(r['evals_per_s'] * r['window_s'] for r in runs) / secs
+    cpu['samples'] = [r['value'] for r in runs]
+    cpu['window_s'] = secs
+    cpu['window_moves'] = moves
+    cpu['sample'] = '%d x [%s]' % (n_samples, runs[0]['sample'])
+    return cpu
+
+
 def cpu_reference_selfplay(game=PUCT_GAME, seconds=CPU_WINDOW_S, warm=CPU_WARM_S, threads=None, batch=CPU_BATCH,
-                           rng_seed=0x5EED0000):
+                           rng_seed=CPU_SEED0):
     """The reference's own C++ PUCT self-play (oracle/_ref: Supervisor worker mode, N threads x 2
     managers x `batch` games, src/cpp/supervisor.cpp:79-99) on the host cores, network replaced by
     the synthetic hash network so that it measures propnet + PUCT + encode (the reference's
@@ -660,7 +677,7 @@ def run_puct(args, rank, world, local, propnet_line=None):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_reference_selfplay(game)
+            cpu = cpu_reference_selfplay_mean(game, CPU_INLINE_SAMPLES)
         except Exception as exc:   # oracle/_ref missing on this box
             cpu = {'value': None, 'unit': 'moves/s', 'cores': os.cpu_count(), 'kind': 'reference',
                    'sample': 'unavailable: %s' % exc}
@@ -699,22 +716,16 @@ def run_puct(args, rank, world, local, propnet_line=None):
 
 def run_reference_puct(args):
     """Reference arm: the reference's own C++ search on the host cores in the same regime as the GPU arm and the
-    in-line cpu_baseline (staggered plies, warm-up, bounded window); one sample per 5 contract steps, each in a
-    fresh process with its own seeds, and the mean over the samples. With its 'propnet' half next to it."""
+    in-line cpu_baseline (staggered plies, warm-up, bounded window); one sample per 2 contract steps, each in a
+    fresh process with its own seeds (the in-line baseline takes the first CPU_INLINE_SAMPLES of the same
+    sequence), and the mean over the samples. With its 'propnet' half next to it."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     game = puct_game(args)
     t0 = time.perf_counter()
-    n_samples = max(1, (max(1, args.steps) + 4) // 5)
-    runs = [cpu_reference_selfplay(game, rng_seed=0x5EED0000 + 7919 * i) for i in range(n_samples)]
-    moves = sum(r['window_moves'] for r in runs)
-    secs = sum(r['window_s'] for r in runs)
-    cpu = dict(runs[0])
-    cpu['value'] = moves / secs
-    cpu['evals_per_s'] = sum(r['evals_per_s'] * r['window_s'] for r in runs) / secs
-    cpu['samples'] = [r['value'] for r in runs]
-    cpu['sample'] = '%d x [%s]' % (n_samples, runs[0]['sample'])
+    n_samples = max(CPU_INLINE_SAMPLES, (max(1, args.steps) + 1) // 2)
+    cpu = cpu_reference_selfplay_mean(game, n_samples)
     prop = None
     if not args.no_propnet and game == PUCT_GAME:
         prop = reference_propnet_line(args, steps=3)

@@ -173,6 +173,7 @@ struct PuctTotals {
     int waiting_eval;
     unsigned long long sel_nodes, sel_children, new_children;
     unsigned long long depth_sum;      // sum over games of the current root's game depth (mean ply = / G)
+    int error_restarts;                // games abandoned at a per-game capacity limit (their slot started a new game)
 };
 
 __global__ void puct_totals_kernel(const __grid_constant__ PuctEngine E, PuctTotals* out) {
@@ -200,6 +201,7 @@ __global__ void puct_totals_kernel(const __grid_constant__ PuctEngine E, PuctTot
     atomicAdd(&out->sel_children, (unsigned long long)c.total_sel_children);
     atomicAdd(&out->new_children, (unsigned long long)c.total_new_children);
     atomicAdd(&out->depth_sum, (unsigned long long)(c.game_depth > 0 ? c.game_depth : 0));
+    atomicAdd(&out->error_restarts, c.error_restarts);
 }
 
 // ---- synthetic network (parity / bench utility): same function as oracle/ref_harness.cpp
@@ -326,6 +328,13 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
                               const double* puct_conf, const double* rte_conf, uint64_t seed, gz_puct** out) {
     if (!pn || !tr || !out || n_games <= 0 || node_cap < 16 || child_cap < 16) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
     if (!tr->finalized) { gz_set_error("transformer must be finalised"); return GZ_ERR_ARG; }
+    if (tr->num_prev_states > 1) {
+        // the engine keeps ONE ancestor state per leaf and per sample (every shipped generation has
+        // num_previous_states = 1); more would silently encode / sample different planes than
+        // the reference (node.cpp:450-460, selfplaymanager.cpp:78-90)
+        gz_set_error("the device engine supports num_previous_states <= 1, transformer has %d", tr->num_prev_states);
+        return GZ_ERR_LIMIT;
+    }
     *out = nullptr;
     gz_puct* h = new gz_puct();
     h->pn = pn;
@@ -359,7 +368,9 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     E.READYCAP = ready_cap > 0 ? ready_cap : 1 << 16;
     E.uniq_cap = 1 << 20;
     E.max_iters_per_step = 16;
-    E.max_work_per_step = 1 << 20;
+    // self-play: measured on reversi, 6-8 levels give the best moves/s (bench.py --max-work); a single player tree
+    // has nobody to wait for
+    E.max_work_per_step = mode == 0 ? 8 : 1 << 20;
     E.seed = seed;
     if ((int)tr->policy_sizes.size() != E.R) { gz_set_error("transformer policy heads != roles"); delete h; return GZ_ERR_ARG; }
     for (int r = 0; r < E.R; r++)
@@ -821,7 +832,8 @@ extern "C" int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes) {
 
 // totals: [evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children,
 //          dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval,
-//          ready_count, select_nodes, select_children, new_children, depth_sum]   (23 doubles)
+//          ready_count, select_nodes, select_children, new_children, depth_sum, dropped_samples, error_restarts]
+//         (25 doubles)
 extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     if (!h || !out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
@@ -831,23 +843,38 @@ extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     puct_totals_kernel<<<(h->E.G + 127) / 128, 128, 0, s>>>(h->E, h->d_totals);
     GZ_CUDA(cudaGetLastError());
     PuctTotals t;
-    unsigned long long ready = 0;
+    unsigned long long ready[2] = {0, 0};
     GZ_CUDA(cudaMemcpyAsync(&t, h->d_totals, sizeof(t), cudaMemcpyDeviceToHost, s));
-    GZ_CUDA(cudaMemcpyAsync(&ready, h->E.ready_count, 8, cudaMemcpyDeviceToHost, s));
+    GZ_CUDA(cudaMemcpyAsync(ready, h->E.ready_count, 16, cudaMemcpyDeviceToHost, s));
     GZ_CUDA(cudaStreamSynchronize(s));
     out[0] = (double)t.evals; out[1] = (double)t.moves; out[2] = (double)t.games; out[3] = (double)t.samples;
     out[4] = (double)t.playouts; out[5] = t.errors; out[6] = t.halted; out[7] = t.first_error;
     out[8] = t.max_nodes; out[9] = t.max_children; out[10] = t.dupes; out[11] = t.no_samples;
     out[12] = t.fp_resign0; out[13] = t.fp_resign1; out[14] = t.early_run_to_ends; out[15] = t.resigns;
-    out[16] = t.aborts; out[17] = t.waiting_eval; out[18] = (double)ready;
+    out[16] = t.aborts; out[17] = t.waiting_eval;
+    out[18] = (double)std::min<unsigned long long>(ready[0], (unsigned long long)h->E.READYCAP);
     out[19] = (double)t.sel_nodes; out[20] = (double)t.sel_children; out[21] = (double)t.new_children;
     out[22] = (double)t.depth_sum;
+    out[23] = (double)ready[1];          // finished samples dropped because the ready buffer was full
+    out[24] = t.error_restarts;
     return GZ_OK;
 }
 
 // Copies the finished samples to the host (records of gz_puct_info(h,4) int32 words, layout SR_* in
 // gz_puct_core.h) and empties the device buffer. Returns the number of records copied (<= cap), or
 // a negative status. Synchronises `stream`.
+// moves words [from, from + count) of buf to [0, count), from >= 0: one CTA, chunk by chunk, read before write
+__global__ void __launch_bounds__(1024) ready_shift_kernel(int32_t* buf, long long from, long long count) {
+    for (long long base = 0; base < count; base += blockDim.x) {
+        const long long i = base + threadIdx.x;
+        int32_t v = 0;
+        if (i < count) v = buf[from + i];
+        __syncthreads();
+        if (i < count) buf[i] = v;
+        __syncthreads();
+    }
+}
+
 extern "C" int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream) {
     if (!h || (!h_out && cap > 0)) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     cudaSetDevice(h->device);
@@ -856,13 +883,19 @@ extern "C" int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap
     unsigned long long ready = 0;
     if (cudaMemcpyAsync(&ready, h->E.ready_count, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) { gz_set_error("sample count copy failed"); return GZ_ERR_CUDA; }
-    int64_t n = (int64_t)std::min<unsigned long long>(ready, (unsigned long long)h->E.READYCAP);
-    n = std::min<int64_t>(n, cap);
+    const int64_t have = (int64_t)std::min<unsigned long long>(ready, (unsigned long long)h->E.READYCAP);
+    const int64_t n = std::min<int64_t>(have, cap);
     if (n > 0 && cudaMemcpyAsync(h_out, h->E.ready, (size_t)n * h->E.srec * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) {
         gz_set_error("sample copy failed");
         return GZ_ERR_CUDA;
     }
-    cudaMemsetAsync(h->E.ready_count, 0, 8, s);
+    // records that did not fit into the caller's buffer stay, moved to the front, for the next fetch
+    const unsigned long long left = (unsigned long long)(have - n);
+    if (left > 0) {
+        ready_shift_kernel<<<1, 1024, 0, s>>>(h->E.ready, (long long)n * h->E.srec, (long long)left * h->E.srec);
+        if (cudaGetLastError() != cudaSuccess) { gz_set_error("sample shift failed"); return GZ_ERR_CUDA; }
+    }
+    cudaMemcpyAsync(h->E.ready_count, &left, 8, cudaMemcpyHostToDevice, s);
     cudaStreamSynchronize(s);
     return n;
 }
@@ -915,7 +948,8 @@ extern "C" int gz_puct_command(gz_puct* h, int g, int cmd, int arg, int evals, c
 }
 
 // Snapshot of game g: out_i[0..15] (out_i[9+r] = role r's only action at the root) = cmd_done, phase, error, choice, n_nodes, n_children, root visits,
-// lead role; out_f[0] = root score for the lead role; then per child (max_children): move, traversals,
+// lead role; out_f[0] = root score for the lead role, out_f[1 + r] = score of the CHOSEN child's node for role r (-1:
+// unexpanded / nothing chosen), out_f has 8 floats; then per child (max_children): move, traversals,
 // policy_prob, child score (-1 unexpanded), next_prob. Returns the number of children. Synchronises.
 __global__ void puct_snapshot_kernel(const __grid_constant__ PuctEngine E, int g, int max_children, int* oi, float* of,
                                      int* moves, int* trav, float* prob, float* score, float* next_prob) {
@@ -925,12 +959,17 @@ __global__ void puct_snapshot_kernel(const __grid_constant__ PuctEngine E, int g
     oi[6] = 0; oi[7] = 0; oi[8] = 0;
     for (int r = 0; r < GZP_MAX_ROLES; r++) oi[9 + r] = -1;
     of[0] = 0.0f;
+    for (int r = 0; r < GZP_MAX_ROLES; r++) of[1 + r] = -1.0f;
     if (c.root < 0 || c.n_nodes <= 0) return;
     const int n = c.root;
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n), lead = NODE(n_lead, n);
     oi[6] = (int)NODE(n_visits, n); oi[7] = lead; oi[8] = nc;
     for (int r = 0; r < E.R && r < GZP_MAX_ROLES; r++) oi[9 + r] = NOTHER(n, r);   // non-lead roles' only action
     of[0] = NSCORE(n, lead);
+    if (c.choice >= 0 && c.choice < nc) {        // the chosen child's node: its score for EVERY role (player.cpp:105-119)
+        const int to = CHILD(c_to, c0 + c.choice);
+        for (int r = 0; r < E.R && r < GZP_MAX_ROLES; r++) of[1 + r] = to >= 0 ? NSCORE(to, r) : -1.0f;
+    }
     for (int i = 0; i < nc && i < max_children; i++) {
         moves[i] = CHILD(c_move, c0 + i);
         trav[i] = (int)CHILD(c_trav, c0 + i);
@@ -947,12 +986,12 @@ extern "C" int gz_puct_snapshot(gz_puct* h, int g, int max_children, int* out_i,
     GZ_CUDA(cudaSetDevice(h->device));
     { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t bytes = 16 * 4 + (size_t)max_children * 5 * 4 + 64;
+    const size_t bytes = 16 * 4 + 8 * 4 + (size_t)max_children * 5 * 4 + 64;
     void* d = nullptr;
     GZ_CUDA(cudaMalloc(&d, bytes));
     int* di = (int*)d;
     float* df = (float*)(di + 16);
-    int* dm = (int*)(df + 4);
+    int* dm = (int*)(df + 8);
     int* dt = dm + max_children;
     float* dp = (float*)(dt + max_children);
     float* ds = dp + max_children;
@@ -960,7 +999,7 @@ extern "C" int gz_puct_snapshot(gz_puct* h, int g, int max_children, int* out_i,
     puct_snapshot_kernel<<<1, 1, 0, s>>>(h->E, g, max_children, di, df, dm, dt, dp, ds, dn);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_i, di, 16 * 4, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_f, df, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_f, df, 8 * 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && max_children) {
         cudaMemcpyAsync(moves, dm, max_children * 4, cudaMemcpyDeviceToHost, s);
         cudaMemcpyAsync(trav, dt, max_children * 4, cudaMemcpyDeviceToHost, s);

@@ -130,6 +130,8 @@ struct GameCtl {
     // per-manager style stats (selfplaymanager.h:46-72)
     int32_t saw_dupes, no_samples_taken, false_positive_resigns0, false_positive_resigns1,
         number_early_run_to_ends, number_resigns, number_aborts_game_length;
+    int32_t error_restarts;  // games abandoned because a per-game capacity was exceeded (GZP_ERR_NODES / CHILDREN / PATH / SAMPLES)
+    int32_t last_error;
     int32_t start_pending;   // the next game of this slot starts from E->start_state[g] (bench / staggered starts)
 };
 
@@ -199,7 +201,7 @@ struct PuctEngine {
     int MAXPEND, srec;
     int32_t* ready;           // [READYCAP * srec] finished samples
     int READYCAP;
-    unsigned long long* ready_count;
+    unsigned long long* ready_count;   // [0] records appended since the last fetch, [1] records dropped (buffer full)
     // unique states: open-addressing table of 64-bit masked-state hashes with counters
     unsigned long long* uniq_keys;
     int32_t* uniq_counts;
@@ -227,9 +229,19 @@ GZP_HD void gzp_rng_seed(uint64_t* st, uint64_t s) {
         st[i] = z ^ (z >> 31);
     }
 }
+#ifdef __CUDA_ARCH__
+#define GZP_WARP_BARRIER() __syncwarp()
+#else
+#define GZP_WARP_BARRIER() ((void)0)
+#endif
+// On the device all 32 lanes run the controller redundantly against ONE copy of the generator state (shared
+// memory): every lane must have read the old state before any lane writes the new one, whatever the hardware
+// does about lockstep execution, hence the two warp barriers (called from warp-uniform control flow only).
 GZP_HD uint32_t gzp_rng_next(uint64_t* st) {
+    GZP_WARP_BARRIER();
     const uint64_t s0 = st[0];
     uint64_t s1 = st[1];
+    GZP_WARP_BARRIER();
     const uint64_t r = s0 + s1;
     s1 ^= s0;
     st[0] = ((s0 << 55) | (s0 >> 9)) ^ s1 ^ (s1 << 14);
@@ -1694,6 +1706,13 @@ GZP_RARE void gzp_add_samples(GameView& V, const float* final_scores, int game_d
         if (slot < (unsigned long long)E->READYCAP) {
             int32_t* dst = E->ready + (int64_t)slot * E->srec;
             for (int w = V.lane; w < E->srec; w += GZP_LANES) dst[w] = rec[w];
+        } else {
+            // the caller did not fetch for too long: the record is lost, and counted (gz_puct_totals: dropped_samples)
+#ifdef __CUDA_ARCH__
+            if (V.lane == 0) atomicAdd(E->ready_count + 1, 1ULL);
+#else
+            E->ready_count[1]++;
+#endif
         }
         GZP_SYNC();
         c->total_samples++;
@@ -1972,6 +1991,29 @@ GZP_RARE void gzp_begin_game(GameView& V) {
     }
 }
 
+// A self-play game that ran into one of the engine's per-game capacities (tree arena, path length, pending
+// samples — the reference has no such limits) is abandoned: its samples are discarded, the restart is counted
+// and the slot begins a new game. Rule violations (GZP_ERR_SIMULTANEOUS, GZP_ERR_ROOT_TERMINAL) and player-mode
+// errors still halt the slot.
+GZP_HD bool gzp_restart_after_error(GameView& V) {
+    GameCtl* c = V.c;
+    const int e = c->error;
+    const bool recoverable = e == GZP_ERR_NODES || e == GZP_ERR_CHILDREN || e == GZP_ERR_PATH || e == GZP_ERR_SAMPLES;
+    if (c->mode != 0 || !recoverable) return false;
+    c->last_error = e;
+    c->error = GZP_ERR_NONE;
+    c->error_restarts++;
+    c->n_samples = 0;
+    c->req = REQ_NONE;
+    c->eval_node = -1;
+    c->resume = 0;
+    c->in_playout = 0;
+    c->path_len = 0;
+    V.E->x_need_eval[V.g] = 0;
+    c->phase = PH_NEW_GAME;
+    return true;
+}
+
 // Returns when the game is blocked on the pipeline (c->req != REQ_NONE or c->eval_node >= 0),
 // idle, halted, or the per-step iteration budget is spent.
 GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
@@ -1988,7 +2030,11 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
         c->resume = 1;
     }
     for (int iter = 0; iter < E->max_iters_per_step; iter++) {
-        if (c->error) { c->phase = PH_HALT; return; }
+        if (c->error) {
+            if (gzp_restart_after_error(V)) continue;
+            c->phase = PH_HALT;
+            return;
+        }
         if (V.work >= E->max_work_per_step) return;
         if (c->req != REQ_NONE) return;
         if (c->mode == 1 && c->phase == PH_AFTER_MOVE && !c->resume) {   // player: move applied
@@ -2227,7 +2273,10 @@ GZP_HDN void gzp_step_post(GameView& V) {
     const int depth = parent < 0 ? c->game_depth : NODE(n_depth, parent) + 1;
     const int N = gzp_create_node(V, parent, depth);
     c->req = REQ_NONE;
-    if (N < 0) { c->phase = PH_HALT; return; }
+    if (N < 0) {
+        if (!gzp_restart_after_error(V)) c->phase = PH_HALT;
+        return;
+    }
     if (parent >= 0) {
         CHILD(c_to, NODE(n_child0, parent) + c->req_child) = N;
         gzp_child_refresh(V, parent, c->req_child, N);

@@ -43,7 +43,7 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     E->x_cache = (uint32_t*)take(G * gzp_cache_words(E->max_actions) * 4);
     E->pend = (int32_t*)take(G * E->MAXPEND * (size_t)E->srec * 4);
     E->ready = (int32_t*)take((size_t)E->READYCAP * E->srec * 4);
-    E->ready_count = (unsigned long long*)take(8);
+    E->ready_count = (unsigned long long*)take(16);
     E->uniq_keys = (unsigned long long*)take((size_t)E->uniq_cap * 8);
     E->uniq_counts = (int32_t*)take((size_t)E->uniq_cap * 4);
     E->uniq_mask = (const uint32_t*)take((size_t)E->SW * 4);

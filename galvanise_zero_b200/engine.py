@@ -32,7 +32,8 @@ SP_FIELDS = ['oscillate_sampling_pct', 'temperature_for_policy', 'evals_per_move
 TOTAL_KEYS = ['evals', 'moves', 'games', 'samples', 'playouts', 'errors', 'halted', 'first_error',
               'max_nodes', 'max_children', 'dupes', 'no_samples', 'fp_resign0', 'fp_resign1',
               'early_run_to_ends', 'resigns', 'aborts', 'waiting_eval', 'ready',
-              'select_nodes', 'select_children', 'new_children', 'depth_sum']
+              'select_nodes', 'select_children', 'new_children', 'depth_sum', 'dropped_samples',
+              'error_restarts']
 # sample record header (csrc/gz_puct_core.h SR_*)
 SR_DEPTH, SR_GAME_LENGTH, SR_SLOT, SR_MATCH, SR_HAS_RESIGNED, SR_RESIGN_FP, SR_START_DEPTH, SR_VISITS, \
     SR_LEAD, SR_N_PREV, SR_N_CHILDREN = range(1, 12)
@@ -274,7 +275,7 @@ class PuctEngine(object):
     def snapshot(self, game=0, max_children=None):
         mc = max_children or self.max_actions
         oi = np.zeros(16, dtype=np.int32)
-        of = np.zeros(4, dtype=np.float32)
+        of = np.zeros(8, dtype=np.float32)
         moves = np.zeros(mc, dtype=np.int32)
         trav = np.zeros(mc, dtype=np.int32)
         prob = np.zeros(mc, dtype=np.float32)
@@ -288,5 +289,6 @@ class PuctEngine(object):
         return dict(cmd_done=int(oi[0]), phase=int(oi[1]), error=int(oi[2]), choice=int(oi[3]),
                     nodes=int(oi[4]), children=int(oi[5]), root_visits=int(oi[6]), lead_role=int(oi[7]),
                     other_moves=[int(x) for x in oi[9:9 + len(self.role_sizes)]],
-                    root_score=float(of[0]), moves=moves[:n].copy(), traversals=trav[:n].copy(),
+                    root_score=float(of[0]), choice_scores=[float(x) for x in of[1:1 + len(self.role_sizes)]],
+                    moves=moves[:n].copy(), traversals=trav[:n].copy(),
                     policy_prob=prob[:n].copy(), scores=score[:n].copy(), next_prob=nxt[:n].copy())

@@ -301,6 +301,15 @@ class Supervisor(object):
                                          for k in out}
         return out
 
+    def check_health(self):
+        """Raises when game slots were lost (halted) or finished samples were dropped (fetch_samples called too
+        rarely for the ready buffer); the reference's sample vector is unbounded and its games never stop."""
+        t = self.totals()
+        if t['halted'] > 0 or t['dropped_samples'] > 0:
+            raise GGPZeroInterfaceError('device self-play degraded: %d game slots halted (first error %d), %d samples '
+                                        'dropped' % (t['halted'], t['first_error'], t['dropped_samples']))
+        return t
+
     def fetch_samples(self):
         res = []
         for k, m in enumerate(self.managers):
@@ -425,7 +434,8 @@ class Player(object):
             move = int(s['moves'][ch])
         else:
             move = int(s['other_moves'][lead_role_index])
-        return (move, float(s['scores'][ch]), int(s['nodes']))
+        # the chosen child's score FOR THE ROLE ASKED ABOUT (player.cpp:105-119), not for the root's lead role
+        return (move, float(s['choice_scores'][lead_role_index]), int(s['nodes']))
 
     def player_balance_moves(self, max_count):
         """Accepted for API parity; the device engine does not rebalance first moves

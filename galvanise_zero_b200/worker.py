@@ -56,6 +56,7 @@ class SelfPlayWorker(object):
         self.supervisor.poll_loop(do_stats=True, cb=self._cb)
         dt = max(time.time() - t0, 1e-9)
         sup = self.supervisor
+        sup.c_supervisor.check_health()       # halted game slots / dropped samples are an error, not a slow decay
         self.last_stats = {'samples': len(self.samples), 'prediction_calls': sup.num_predictions_calls,
                            'predictions': sup.total_predictions, 'acc_time_polling': sup.acc_time_polling,
                            'acc_time_prediction': sup.acc_time_prediction, 'seconds': dt,

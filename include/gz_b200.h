@@ -204,23 +204,25 @@ int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream);
  * other's batch (the reference's two managers per worker, src/cpp/supervisor.cpp:79-99). */
 int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* const* h_arrays, int n_arrays, void* stream);
 int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes);
-/* h_out23: evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children, dupes,
+/* h_out25: evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children, dupes,
  * no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval, ready, select_nodes,
- * select_children, new_children, depth_sum (sum over slots of the current root's game depth). */
-int gz_puct_totals(gz_puct* h, double* h_out23, void* stream);
+ * select_children, new_children, depth_sum (sum over slots of the current root's game depth), dropped_samples
+ * (finished samples lost because the ready buffer was full: fetch more often), error_restarts (games abandoned at a
+ * per-game capacity limit; their slot started a new game). */
+int gz_puct_totals(gz_puct* h, double* h_out25, void* stream);
 /* Measurement aid: the next game of every slot starts from d_states[g] (device, [G][state_words], non-terminal
  * positions) at game depth 0 instead of the initial state — what handing SelfPlay another `initial_state`
  * (src/cpp/selfplaymanager.cpp:140, selfplay.cpp:313) does in the reference. Later games start normally. */
 int gz_puct_set_start_states(gz_puct* h, const uint32_t* d_states, void* stream);
 /* Per engine step a game runs until it needs the batch pipeline (a propnet pass / the network), but at most
  * `max_iters` controller iterations and `max_work` tree levels descended (playouts that end in terminal or
- * finalised nodes need no pipeline pass; the slowest game sets the duration of the step). Defaults 16 / unlimited.
+ * finalised nodes need no pipeline pass; the slowest game sets the duration of the step). Defaults 16 / 8.
  * No reference counterpart: the reference runs one coroutine per game (src/cpp/scheduler.cpp). */
 int gz_puct_set_step_limits(gz_puct* h, int max_iters, int max_work);
 int64_t gz_puct_fetch_samples(gz_puct* h, int32_t* h_out, int64_t cap, void* stream);
 int gz_puct_clear_unique_states(gz_puct* h, void* stream);
 int gz_puct_command(gz_puct* h, int game, int cmd, int arg, int evals, const uint32_t* h_state, void* stream);
-int gz_puct_snapshot(gz_puct* h, int game, int max_children, int* out_i16, float* out_f1, int* moves, int* trav,
+int gz_puct_snapshot(gz_puct* h, int game, int max_children, int* out_i16, float* out_f8, int* moves, int* trav,
                      float* prob, float* score, float* next_prob, void* stream);
 
 /* Deterministic synthetic policy/value network (include/gz_synth.h) on encoded planes — parity and

@@ -109,10 +109,14 @@ class RefEngine:
                                 evals, n_moves, nn_seed, max_children, counts.ctypes.data,
                                 move.ctypes.data, trav.ctypes.data, prob.ctypes.data,
                                 score.ctypes.data, choice.ctypes.data, root.ctypes.data)
+        cs = np.full((max(n, 1), 4), -1.0, dtype=np.float32)
+        self.L.gzref_last_choice_scores.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        self.L.gzref_last_choice_scores(cs.ctypes.data, cs.size)
         out = []
         for m in range(n):
             k = int(counts[m])
             out.append({'moves': move[m, :k].copy(), 'traversals': trav[m, :k].copy(),
+                        'choice_scores': cs[m].copy(),
                         'policy_prob': prob[m, :k].copy(), 'scores': score[m, :k].copy(),
                         'choice': int(choice[m]), 'root_visits': int(root[m, 0]),
                         'lead_role': int(root[m, 1]), 'root_score': float(root[m, 2]),

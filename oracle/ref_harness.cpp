@@ -366,6 +366,15 @@ static void synth_predict(const TransformerSpec& ts, uint64_t nn_seed, const flo
  *   lead role (-1 when unexpanded), out_choice[m] = index of the chosen child,
  *   out_root[m*4+{0,1,2,3}] = root visits, lead role, root score(lead), #nodes.
  * Returns the number of moves actually searched (stops at terminal). */
+/* scores of the chosen child's node for every role, per move of the last gzref_search (what
+ * Player::puctPlayerGetMove reports for the role it is asked about, player.cpp:105-119) */
+static std::vector<float> g_last_choice_scores;
+extern "C" int gzref_last_choice_scores(float* out, int cap) {
+    const int n = (int)g_last_choice_scores.size() < cap ? (int)g_last_choice_scores.size() : cap;
+    for (int i = 0; i < n; i++) out[i] = g_last_choice_scores[i];
+    return n;
+}
+
 extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* root_state, int evals, int n_moves,
                             uint64_t nn_seed, int max_children, int* out_counts, int* out_move, int* out_trav,
                             float* out_prob, float* out_score, int* out_choice, float* out_root) {
@@ -382,6 +391,7 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
     else root_bs->assign(sm->getInitialState());
     int done_moves = 0;
     const int R = g->gt.n_roles;
+    g_last_choice_scores.clear();
     auto f = [&]() {
         pe->reset(0);
         PuctNode* node = pe->establishRoot(root_bs);
@@ -404,6 +414,8 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
             out_root[m * 4 + 2] = node->getCurrentScore(lead);
             out_root[m * 4 + 3] = (float)pe->nodeCount();
             done_moves = m + 1;
+            for (int r = 0; r < 4; r++)
+                g_last_choice_scores.push_back(r < R && choice->to_node ? choice->to_node->getCurrentScore(r) : -1.0f);
             node = pe->fastApplyMove(choice);
         }
     };

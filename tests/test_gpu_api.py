@@ -159,7 +159,11 @@ def test_play_poller_matches_reference_search(game, evals, moves):
         assert mv == int(r['moves'][r['choice']])
         assert abs(score - float(r['scores'][r['choice']])) < 1e-6
         assert 0.9 * r['nodes'] <= nodes <= r['nodes']   # the reference also counts nodes awaiting release
-        other, _, _ = poller.player_get_move(1 - lead)
+        other, other_score, _ = poller.player_get_move(1 - lead)
+        # the probability reported to the role that is NOT on move is that role's own score of the chosen child
+        # (player.cpp:105-119; PUCTPlayer passes our_role_index whoever is to move)
+        assert abs(other_score - float(r['choice_scores'][1 - lead])) < 1e-6
+        assert abs(score - float(r['choice_scores'][lead])) < 1e-6
         sm.update_bases(state)
         ls = sm.get_legal_state(1 - lead)
         assert ls.get_count() == 1 and ls.get_legal(0) == other       # the non-lead role's only move
@@ -224,3 +228,58 @@ def test_worker_rehost_request_samples_and_generation_file(tmp_path):
     assert len(st) >= tr.num_bases and set(st) <= {0, 1}
     more = w.on_request_samples()                      # resumable
     assert len(more) > 25
+
+
+def test_fetch_with_small_buffer_keeps_the_rest_and_counts_nothing_as_dropped():
+    """gz_puct_fetch_samples hands out at most `cap` records and keeps the others for the next call (the
+    reference's sample vector is unbounded, supervisor.cpp:170-173)."""
+    from galvanise_zero_b200.engine import PuctEngine
+    sp = confs.selfplay_config_template(evals_per_move=20)
+    eng = PuctEngine('breakthroughSmall', sp, n_games=64, mode=0, node_cap=1024, child_cap=1024 * 16)
+    for _ in range(400):
+        eng.run_synthetic(64)
+        if eng.totals()['ready'] >= 40:
+            break
+    t = eng.totals()
+    ready = int(t['ready'])
+    assert ready >= 40 and t['dropped_samples'] == 0
+    first = eng.fetch_sample_records(cap=7)
+    assert len(first) == 7
+    assert int(eng.totals()['ready']) == ready - 7
+    rest = eng.fetch_sample_records()
+    assert len(rest) >= ready - 7
+    keys = {(int(r[3]), int(r[4]), int(r[1])) for r in np.concatenate([first, rest])}
+    assert len(keys) == len(first) + len(rest)            # nothing duplicated, nothing lost
+    assert all(int(r[0]) == 1 for r in rest)
+
+
+def test_full_ready_buffer_is_counted_and_reported():
+    from galvanise_zero_b200.engine import PuctEngine
+    sp = confs.selfplay_config_template(evals_per_move=16)
+    eng = PuctEngine('breakthroughSmall', sp, n_games=64, mode=0, node_cap=1024, child_cap=1024 * 16, ready_cap=8)
+    for _ in range(40):
+        eng.run_synthetic(64)
+    t = eng.totals()
+    assert t['ready'] == 8 and t['dropped_samples'] > 0 and t['samples'] == t['dropped_samples'] + 8
+
+
+def test_engine_rejects_more_than_one_previous_state():
+    from galvanise_zero_b200.engine import PuctEngine
+    from galvanise_zero_b200 import lib as gzlib
+    gen = datadesc.generation_for('reversi', num_previous_states=2)
+    with pytest.raises(gzlib.GzError):
+        PuctEngine('reversi', confs.selfplay_config_template(), n_games=4, generation=gen)
+
+
+def test_game_over_capacity_restarts_instead_of_halting():
+    """A game that exceeds a per-game capacity (here: 3 pending samples) is abandoned and counted; its slot
+    starts a new game instead of halting for good."""
+    from galvanise_zero_b200.engine import PuctEngine
+    sp = confs.selfplay_config_template(evals_per_move=16)
+    sp.oscillate_sampling_pct = 1.0
+    eng = PuctEngine('breakthroughSmall', sp, n_games=32, mode=0, node_cap=1024, child_cap=1024 * 16,
+                     max_pending_samples=3)
+    for _ in range(30):
+        eng.run_synthetic(64)
+    t = eng.totals()
+    assert t['halted'] == 0 and t['errors'] == 0 and t['error_restarts'] > 0 and t['games'] >= 0
