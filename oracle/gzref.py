@@ -87,10 +87,33 @@ class RefEngine:
                                      ct.channels_per_state, ct.num_control_channels,
                                      ct.num_prev_states, ct.num_rewards, ps, len(ct.policy_sizes))
         assert self.h
+        self.ct_total = ct.total_size()
         for b, off in ct.board_bases:
             self.L.gzref_add_board_base(self.h, b, off)
         for b, c, v in ct.control_bases:
             self.L.gzref_add_control_base(self.h, b, c, v)
+
+    def encode(self, states, prev_states=None, prev_count=None):
+        """The reference's compiled GdlBasesTransformer::toChannels on packed states uint32 [n, SW]
+        (prev_states uint32 [n, max_prev, SW], nearest first; prev_count uint8 [n]) -> float32 [n, total]."""
+        states = np.ascontiguousarray(states, dtype=np.uint32)
+        n = states.shape[0]
+        total = self.ct_total
+        out = np.zeros((n, total), dtype=np.float32)
+        pp = pc = None
+        max_prev = 0
+        if prev_states is not None:
+            prev_states = np.ascontiguousarray(prev_states, dtype=np.uint32)
+            max_prev = prev_states.shape[1]
+            pp = prev_states.ctypes.data
+            if prev_count is not None:
+                prev_count = np.ascontiguousarray(prev_count, dtype=np.uint8)
+                pc = prev_count.ctypes.data
+        self.L.gzref_encode.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        got = self.L.gzref_encode(self.h, n, states.ctypes.data, pp, pc, max_prev, out.ctypes.data)
+        assert got == total, (got, total)
+        return out
 
     def search(self, puct_conf, evals, n_moves=1, root_state=None, nn_seed=1, max_children=512,
                rng_seed=0x5EED0000):

@@ -305,6 +305,35 @@ extern "C" void gzref_add_control_base(void* h, int b, int c, float v) {
     GzRef* g = (GzRef*)h; g->ts.ctrl_base.push_back(b); g->ts.ctrl_channel.push_back(c); g->ts.ctrl_value.push_back(v);
 }
 
+/* The reference's own encoder: GdlBasesTransformer::toChannels (gdltransformer.cpp:22-52), compiled unmodified, on
+ * `n` packed states. prev[(i * max_prev + k) * SW ..] = k-th previous state of row i (nearest first), of which the
+ * first prev_count[i] (all max_prev when prev_count is null) are handed over, as PuctNodeRequest::add does while
+ * walking the parents (node.cpp:449-461). out: [n][totalSize()] float32. */
+extern "C" int gzref_encode(void* h, int64_t n, const uint32_t* states, const uint32_t* prev, const uint8_t* prev_count,
+                            int max_prev, float* out) {
+    GzRef* g = (GzRef*)h;
+    ShimStateMachine sm(&g->gt);
+    const GdlBasesTransformer* tr = g->ts.make();
+    const int SW = g->gt.state_words, total = tr->totalSize();
+    GGPLib::BaseState* cur = sm.newBaseState();
+    std::vector<GGPLib::BaseState*> pool;
+    for (int k = 0; k < max_prev; k++) pool.push_back(sm.newBaseState());
+    for (int64_t i = 0; i < n; i++) {
+        std::memcpy(cur->data, states + i * SW, sizeof(uint32_t) * SW);
+        std::vector<const GGPLib::BaseState*> ps;
+        const int cnt = prev ? (prev_count ? prev_count[i] : max_prev) : 0;
+        for (int k = 0; k < cnt && k < max_prev; k++) {
+            std::memcpy(pool[k]->data, prev + (i * max_prev + k) * SW, sizeof(uint32_t) * SW);
+            ps.push_back(pool[k]);
+        }
+        tr->toChannels(cur, ps, out + i * total);
+    }
+    free(cur);
+    for (auto* p : pool) free(p);
+    delete tr;
+    return total;
+}
+
 /* PuctConfig from a flat array, field order = GZ_PUCT_CONF_* below (mirrors config.h:11-53). */
 enum {
     PC_PUCT_CONSTANT = 0, PC_PUCT_CONSTANT_ROOT, PC_DIRICHLET_NOISE_PCT, PC_NOISE_POLICY_SQUASH_PCT,

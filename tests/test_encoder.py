@@ -75,6 +75,54 @@ def test_oracle_prev_state_quirk_all_prev_land_in_group_one():
     assert not got[:, 2 * gs:3 * gs].any()
 
 
+@pytest.mark.parametrize('game', GAMES)
+def test_oracle_encoder_is_the_references_compiled_to_channels(game):
+    """oracle/encoder_ref.c against the reference's own GdlBasesTransformer::toChannels (gdltransformer.cpp:22-52,
+    compiled unmodified into oracle/_ref): same float32 planes on random-played positions with 0, 1 (and for
+    one game 2) previous states — this pins the restatement the GPU encoder is checked against."""
+    from oracle import gzref
+    if not gzref.available():
+        pytest.skip('oracle/_ref cannot be built here')
+    for num_prev in ((1, 2) if game == 'breakthroughSmall' else (1,)):
+        gi, tr, ct = _setup(game, num_prev=num_prev) if num_prev != 1 else _setup(game)
+        enc = RefEncoder.from_c_transformer(ct)
+        ref = gzref.RefEngine(tables.blob_by_name(game), ct)
+        hist = _trajectory(game, n_games=23, plies=16)
+        for k in (0, 3, 15):
+            cur = hist[k]
+            prev = cnt = None
+            if k >= num_prev:
+                prev = np.stack([hist[k - 1 - j] for j in range(num_prev)], axis=1)
+                cnt = (np.arange(cur.shape[0]) % (num_prev + 1)).astype(np.uint8)
+            assert np.array_equal(enc.encode(cur, prev, cnt), ref.encode(cur, prev, cnt))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('game', GAMES)
+def test_gpu_encoder_is_the_references_compiled_to_channels(game):
+    """gz_encode on the device against the reference's compiled toChannels directly (f32 exact, bf16 = rounded f32)."""
+    import torch
+    from oracle import gzref
+    if not gzref.available():
+        pytest.skip('oracle/_ref missing')
+    gi, tr, ct = _setup(game)
+    ct.finalize(tr.num_bases, 0)
+    ref = gzref.RefEngine(tables.blob_by_name(game), ct)
+    hist = _trajectory(game, n_games=29, plies=20)
+    dev = torch.device('cuda', 0)
+    for k in (0, 7, 19):
+        cur = hist[k]
+        prev = hist[k - 1][:, None, :] if k > 0 else None
+        cnt = (np.arange(cur.shape[0]) % 2).astype(np.uint8) if k > 0 else None
+        want = ref.encode(cur, prev, cnt)
+        d_prev = torch.from_numpy(prev.view(np.int32).copy()).to(dev) if prev is not None else None
+        d_cnt = torch.from_numpy(cnt).to(dev) if cnt is not None else None
+        got = ct.encode(torch.from_numpy(cur.view(np.int32)).to(dev), d_prev, d_cnt, dtype=torch.float32).cpu().numpy()
+        assert np.array_equal(got, want)
+        got16 = ct.encode(torch.from_numpy(cur.view(np.int32)).to(dev), d_prev, d_cnt, dtype=torch.bfloat16)
+        assert torch.equal(got16.cpu(), torch.from_numpy(want).to(torch.bfloat16))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('game', GAMES)
 def test_gpu_encoder_bit_exact(game):

@@ -38,6 +38,63 @@ def test_oracle_matches_golden(game):
     assert checked > 20
 
 
+def test_fixtures_cover_the_rules_corner_cases():
+    """The golden trajectories (>= 20 games per game played to their end; hexLG13: 6) contain the situations a
+    propnet is most likely to get wrong, so test_oracle_matches_golden / the GPU propnet tests pin them:
+    reversi forced passes and both kinds of game end, the hex swap, chess castling on both wings, en passant,
+    promotions, check evasions and the step counter running out."""
+    fx = load_fixture('reversi')
+    assert len(fx['games']) >= 20
+    passes = ended = 0
+    for g in fx['games']:
+        ended += int(g[-1]['terminal'])
+        for rec in g:
+            if not rec['terminal'] and all(len(l) == 1 for l in rec['legal']):
+                passes += 1           # the side to move has no stone to place: both roles can only noop
+    assert ended >= 20 and passes >= 3
+
+    fx = load_fixture('hexLG13')
+    swap = [i for i, m in enumerate(fx['inputs'][fx['roles'].index('white')]) if m == 'swap']
+    assert len(swap) == 1
+    wi = fx['roles'].index('white')
+    swaps = sum(1 for g in fx['games'] for rec in g if rec['move'] is not None and rec['move'][wi] == swap[0])
+    offered = sum(1 for g in fx['games'] for rec in g if swap[0] in rec['legal'][wi])
+    assert swaps >= 2 and offered >= len(fx['games']) and sum(int(g[-1]['terminal']) for g in fx['games']) >= 4
+
+    fx = load_fixture('chess_15d')
+    assert len(fx['games']) >= 20
+    bases, inputs = fx['bases'], fx['inputs']
+    ev = dict(castle_k=0, castle_q=0, en_passant=0, promotion=0, step32=0, check=0, terminal=0)
+    for g in fx['games']:
+        ev['terminal'] += int(g[-1]['terminal'])
+        for rec in g:
+            st = set(bases[i] for i in rec['state'])
+            ev['step32'] += int('(step 32)' in st)
+            if rec['move'] is None:
+                continue
+            for r in range(2):
+                m = inputs[r][rec['move'][r]]
+                ev['castle_k'] += int(m == 'castleKingside')
+                ev['castle_q'] += int(m == 'castleQueenside')
+                t = m.strip('()').split()
+                if t[0] != 'move':
+                    continue
+                if t[1] == 'pawn' and t[2] != t[4] and not any(b.startswith('(cell %s %s ' % (t[4], t[5])) for b in st):
+                    ev['en_passant'] += 1          # a pawn captures onto an empty square
+                if t[1] != 'pawn' and ('(cell %s %s white pawn)' % (t[2], t[3]) in st or
+                                       '(cell %s %s black pawn)' % (t[2], t[3]) in st):
+                    ev['promotion'] += 1           # the piece that moves is a pawn and arrives as something else
+                if len(rec['legal'][r]) <= 3 and len(rec['legal'][r]) > 1 and '(step 1)' not in st:
+                    ev['check'] += 1               # almost no legal move: check evasion (or a bare king)
+    assert ev['castle_k'] >= 2 and ev['castle_q'] >= 2 and ev['en_passant'] >= 2, ev
+    assert ev['promotion'] >= 5 and ev['step32'] >= 1 and ev['check'] >= 5 and ev['terminal'] >= 3, ev
+
+    for game in ('breakthrough', 'breakthroughSmall', 'connect6', 'amazons_10x10'):
+        fx = load_fixture(game)
+        assert len(fx['games']) >= 20, game
+    assert sum(int(g[-1]['terminal']) for g in load_fixture('amazons_10x10')['games']) >= 10
+
+
 def test_reversi_action_order_fact():
     """The one ordering fact the reference pins (src/test/test_symmetry.py:90-91): reversi action 1
     is (move 1 1) and rotating it by 90 degrees lands on index 8 = (move 1 8)."""
