@@ -24,12 +24,31 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_extension(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + sources()
+MODULE = os.path.join(CSRC, 'ggpzero_interface.so')       # importable as `ggpzero_interface` with csrc on sys.path
+
+
+def build_module():
+    """The reference's extension module for CPython 3 (csrc/ggpzero_interface.cpp), linked against libgz_b200.so."""
+    import sysconfig
+    import numpy
+    cuda = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    cmd = [os.environ.get('CXX', 'g++'), '-O2', '-std=c++17', '-fPIC', '-shared', '-Wall', '-Wno-missing-field-initializers',
+           '-I' + sysconfig.get_paths()['include'], '-I' + numpy.get_include(), '-I' + os.path.join(cuda, 'include'),
+           '-o', MODULE, os.path.join(CSRC, 'ggpzero_interface.cpp'), '-L' + CSRC, '-l:libgz_b200.so',
+           '-L' + os.path.join(cuda, 'lib64'), '-lcudart', '-Wl,-rpath,$ORIGIN', '-Wl,-rpath,' + os.path.join(cuda, 'lib64')]
     subprocess.check_call(cmd)
+    return MODULE
+
+
+def build_extension(force=False, verbose=False):
+    if not force and not needs_build() and os.path.exists(MODULE) and \
+            os.path.getmtime(MODULE) >= os.path.getmtime(os.path.join(CSRC, 'ggpzero_interface.cpp')):
+        return LIB
+    if force or needs_build():
+        nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + sources()
+        subprocess.check_call(cmd)
+    build_module()
     return LIB
 
 

@@ -6,10 +6,12 @@ from __future__ import annotations
 from . import interface as ggpzero_interface
 
 
-def create_c_transformer(transformer, device=None):
+def create_c_transformer(transformer, device=None, module=None):
     """Python ``GdlBasesTransformer`` (bases.py) -> engine-side transformer; same feeding order as
-    the reference. With ``device`` given the tables are also uploaded (finalised)."""
-    c_transformer = ggpzero_interface.GdlBasesTransformer(
+    the reference (``cppinterface.py:33-50``). With ``device`` given the tables are also uploaded (finalised).
+    ``module``: the extension module to build it with (the compiled ``ggpzero_interface``; default: the ctypes
+    host ``interface.py``)."""
+    c_transformer = (module or ggpzero_interface).GdlBasesTransformer(
         transformer.channel_size, transformer.raw_channels_per_state,
         transformer.num_of_controls_channels, transformer.num_previous_states,
         transformer.num_rewards, transformer.policy_dist_count)
@@ -18,7 +20,7 @@ def create_c_transformer(transformer, device=None):
         c_transformer.add_board_base(b.base_indx, index)
     for c in transformer.control_space:
         c_transformer.add_control_base(c.base_indx, c.channel_id, c.value)
-    if device is not None:
+    if device is not None and hasattr(c_transformer, 'finalize'):
         c_transformer.finalize(transformer.num_bases, device)
     return c_transformer
 

@@ -270,6 +270,7 @@ struct gz_puct {
     uint32_t *t_states = nullptr, *t_legal = nullptr;
     uint8_t *t_term = nullptr, *t_goals = nullptr;
 
+    int* d_status = nullptr;         // gz_puct_status scratch
     struct HostPoll* hp = nullptr;   // host-buffer poll state (gz_puct_host_poll_*), created on first use
 };
 
@@ -451,6 +452,7 @@ extern "C" void gz_puct_destroy(gz_puct* h) {
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->d_totals) cudaFree(h->d_totals);
     if (h->d_pn_scratch) cudaFree(h->d_pn_scratch);
+    if (h->d_status) cudaFree(h->d_status);
     if (h->d_rr_list) cudaFree(h->d_rr_list);
     if (h->d_rr_count) cudaFree(h->d_rr_count);
     if (h->rr_fork) cudaEventDestroy(h->rr_fork);
@@ -931,6 +933,34 @@ extern "C" int gz_puct_clear_unique_states(gz_puct* h, void* stream) {
 __global__ void puct_cmd_kernel(const __grid_constant__ PuctEngine E, int g, int cmd, int arg, int evals) {
     GameCtl& c = E.ctl[g];
     c.cmd = cmd; c.cmd_arg = arg; c.cmd_evals = evals; c.cmd_done = 0;
+}
+
+// Player mode: the host's clock ran out (mode: GZP_STOP_NOW / GZP_STOP_IF_CONVERGED); the running search of game g
+// ends at its next playout boundary. Status: [cmd_done, phase, error, waiting for the network] of game g (one
+// 16-byte copy; synchronises `stream`).
+__global__ void puct_stop_kernel(const __grid_constant__ PuctEngine E, int g, int mode) { E.ctl[g].stop_request = mode; }
+extern "C" int gz_puct_request_stop(gz_puct* h, int g, int mode, void* stream) {
+    if (!h || g < 0 || g >= h->E.G || mode < 0 || mode > 2) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
+    puct_stop_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->E, g, mode);
+    GZ_CUDA(cudaGetLastError());
+    return GZ_OK;
+}
+__global__ void puct_status_kernel(const __grid_constant__ PuctEngine E, int g, int* out) {
+    const GameCtl& c = E.ctl[g];
+    out[0] = c.cmd_done; out[1] = c.phase; out[2] = c.error; out[3] = E.x_need_eval[g];
+}
+extern "C" int gz_puct_status(gz_puct* h, int g, int* h_out4, void* stream) {
+    if (!h || !h_out4 || g < 0 || g >= h->E.G) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
+    GZ_CUDA(cudaSetDevice(h->device));
+    { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
+    if (!h->d_status) GZ_CUDA(cudaMalloc((void**)&h->d_status, 64));
+    puct_status_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->E, g, h->d_status);
+    GZ_CUDA(cudaGetLastError());
+    GZ_CUDA(cudaMemcpyAsync(h_out4, h->d_status, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GZ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return GZ_OK;
 }
 
 extern "C" int gz_puct_command(gz_puct* h, int g, int cmd, int arg, int evals, const uint32_t* h_state, void* stream) {

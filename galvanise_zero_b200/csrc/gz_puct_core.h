@@ -132,6 +132,7 @@ struct GameCtl {
         number_early_run_to_ends, number_resigns, number_aborts_game_length;
     int32_t error_restarts;  // games abandoned because a per-game capacity was exceeded (GZP_ERR_NODES / CHILDREN / PATH / SAMPLES)
     int32_t last_error;
+    int32_t stop_request;    // player mode: the host's clock says stop (1: now, 2: as soon as the search has converged)
     int32_t start_pending;   // the next game of this slot starts from E->start_state[g] (bench / staggered starts)
 };
 
@@ -1875,6 +1876,10 @@ GZP_HDN void gzp_request_reroot(GameView& V, int new_root) {
 // (a propnet transition and possibly a network evaluation); gzp_step_post consumes the propnet
 // outputs and creates the node.
 enum { CMD_NONE = 0, CMD_RESET = 1, CMD_APPLY = 2, CMD_SEARCH = 3 };
+// wall-clock limits of playoutMain (evaluator.cpp:794,820-826: end_time, think_time) live on the host, which
+// tells a running search to stop: GZP_STOP_NOW ("hard" limit, or think time x multiplier without convergence),
+// GZP_STOP_IF_CONVERGED (think time elapsed). Checked where the reference checks its clock: between playouts.
+enum { GZP_STOP_NONE = 0, GZP_STOP_NOW = 1, GZP_STOP_IF_CONVERGED = 2 };
 
 GZP_HDN void gzp_request_expand(GameView& V, int parent, int child, int purpose) {
     const PuctEngine* E = V.E;
@@ -1959,6 +1964,7 @@ GZP_HDN void gzp_start_search(GameView& V, int evals, int conf_sel) {
     c->num_tree_playouts = 0;
     c->playouts_finals = 0;
     c->in_playout = 0;
+    c->stop_request = GZP_STOP_NONE;
     c->phase = PH_SEARCH;
 }
 
@@ -2111,7 +2117,8 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
                 const int max_non_converged = (int)(c->max_evaluations * cf.evaluation_multiplier_to_convergence);
                 const int max_tree_playouts = 4 * max_non_converged;
                 bool brk = false;
-                if ((root_nd.n_flags & NF_FINALISED) && c->num_tree_playouts > 100) brk = true;
+                if (c->stop_request == GZP_STOP_NOW || (c->stop_request == GZP_STOP_IF_CONVERGED && is_converged)) brk = true;
+                else if ((root_nd.n_flags & NF_FINALISED) && c->num_tree_playouts > 100) brk = true;
                 else if (is_converged && c->num_tree_playouts > max_tree_playouts) brk = true;
                 else if (c->n_nodes + 4 > E->NCAP || c->n_children + E->max_actions + 4 > E->CCAP) brk = true;  // arena nearly full ("max nodes")
                 else if (is_converged && c->num_evaluations > c->max_evaluations) brk = true;

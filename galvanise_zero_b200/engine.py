@@ -100,15 +100,39 @@ class PuctEngine(object):
         max_actions = max(self.sm.role_sizes)
         if child_cap is None:
             child_cap = node_cap * max(8, min(max_actions, 64) // 2)
-        self.n_games = n_games
-        self.mode = mode
-        self.plane_dtype = plane_dtype
         h = ctypes.c_void_p()
         _lib.check(self._L.gz_puct_create(
             self.sm._h, self.c_transformer._h, n_games, mode, node_cap, child_cap, max_pending_samples,
             ready_cap, _sp_array(self.sp_conf), _puct_array(self.sp_conf['puct_config']),
             _puct_array(self.sp_conf['run_to_end_puct_config']), seed, ctypes.byref(h)))
-        self._h = h
+        self._owns = True
+        tr = self.transformer
+        self._setup(h, n_games, mode, (tr.num_channels, tr.num_cols, tr.num_rows), tr.num_bases, list(self.sm.role_sizes),
+                    plane_dtype, plane_c_pad)
+
+    @classmethod
+    def from_handle(cls, handle, device, n_bases, role_sizes, plane_shape, mode=0, plane_dtype=torch.float32, sm=None):
+        """A view of an engine owned by somebody else (a native gz_supervisor / gz_player): same methods, no
+        ownership. ``plane_shape`` = (channels, cols, rows)."""
+        self = cls.__new__(cls)
+        self._L = _lib.lib()
+        _declare(self._L)
+        self.game = getattr(sm, 'game', None)
+        self.sm = sm
+        self.transformer = None
+        self.c_transformer = None
+        self.device = torch.device('cuda', device)
+        self._owns = False
+        n_games = int(self._L.gz_puct_info(handle, 0))
+        self._setup(handle, n_games, mode, tuple(plane_shape), n_bases, list(role_sizes), plane_dtype, 0)
+        return self
+
+    def _setup(self, h, n_games, mode, plane_shape, n_bases, role_sizes, plane_dtype, plane_c_pad):
+        self._h = h if isinstance(h, ctypes.c_void_p) else ctypes.c_void_p(h)
+        self.n_games = n_games
+        self.mode = mode
+        self.plane_dtype = plane_dtype
+        self.n_bases = n_bases
         info = lambda w: int(self._L.gz_puct_info(self._h, w))  # noqa: E731
         self.total_size = info(1)
         self.policy_stride = info(2)
@@ -119,27 +143,26 @@ class PuctEngine(object):
         self.max_actions = info(7)
         self.ready_cap = info(8)
         self.kernels_per_step = info(9)
-        tr = self.transformer
-        self.plane_shape = (tr.num_channels, tr.num_cols, tr.num_rows)
+        self.plane_shape = plane_shape
         self.plane_c_pad = plane_c_pad
         if plane_c_pad:
             # channels-last, channel count padded: logical [G, c_pad, H, W] over [G, H, W, c_pad] memory
             self._L.gz_puct_set_plane_layout.argtypes = [ctypes.c_void_p, ctypes.c_int]
             _lib.check(self._L.gz_puct_set_plane_layout(self._h, plane_c_pad))
-            mem = torch.zeros((n_games, tr.num_cols, tr.num_rows, plane_c_pad), dtype=plane_dtype, device=self.device)
+            mem = torch.zeros((n_games, plane_shape[1], plane_shape[2], plane_c_pad), dtype=plane_dtype, device=self.device)
             self.planes = mem.permute(0, 3, 1, 2)
         else:
-            self.planes = torch.zeros((n_games,) + self.plane_shape, dtype=plane_dtype, device=self.device)
+            self.planes = torch.zeros((n_games,) + tuple(plane_shape), dtype=plane_dtype, device=self.device)
         self.policy = torch.zeros((n_games, self.policy_stride), dtype=torch.float32, device=self.device)
         self.value = torch.zeros((n_games, self.n_rewards), dtype=torch.float32, device=self.device)
         self._fresh = False
-        self.role_sizes = list(self.sm.role_sizes)
+        self.role_sizes = list(role_sizes)
 
     def __del__(self):
         h = getattr(self, '_h', None)
-        if h:
+        if h and getattr(self, '_owns', False):
             self._L.gz_puct_destroy(h)
-            self._h = None
+        self._h = None
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -218,7 +241,7 @@ class PuctEngine(object):
         """int32 records -> list of dicts with the keys of ``Supervisor.fetch_samples``
         (``src/cpp/pyobjects/supervisor_impl.cpp:75-118`` == ``datadesc.Sample`` fields)."""
         from . import tables
-        nb = self.transformer.num_bases
+        nb = self.n_bases
         sw = self.state_words
         R = len(self.role_sizes)
         out = []

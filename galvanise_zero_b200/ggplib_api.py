@@ -44,6 +44,14 @@ class BaseState(object):
     def to_string(self):
         return self.words.tobytes()
 
+    @property
+    def ptr(self):
+        """The state as the extension module takes it (``ggpzero_interface.Player.player_move(basestate_ptr, ..)``):
+        the address of the packed uint32 words — the counterpart of ggplib's ``ffi.cast("intptr_t", bs)``
+        (``cppinterface.py:12-30``). Valid while this object is alive and unmodified."""
+        self.words = np.ascontiguousarray(self.words, dtype=np.uint32)
+        return int(self.words.ctypes.data)
+
     def from_string(self, s):
         self.words = np.frombuffer(s, dtype=np.uint32).copy()
 
@@ -76,16 +84,22 @@ class LegalState(object):
 
 class JointMove(object):
     def __init__(self, n_roles):
-        self.moves = [0] * n_roles
+        self.moves = np.zeros(n_roles, dtype=np.int32)
 
     def get(self, ri):
-        return self.moves[ri]
+        return int(self.moves[ri])
 
     def set(self, ri, v):
         self.moves[ri] = int(v)
 
     def get_count(self):
         return len(self.moves)
+
+    @property
+    def ptr(self):
+        """The joint move as the extension module takes it (``player_apply_move(joint_move_ptr)``): the address of
+        one int32 per role."""
+        return int(self.moves.ctypes.data)
 
 
 class StateMachine(object):
@@ -94,6 +108,7 @@ class StateMachine(object):
         self.game = game_info.game
         self.dev = _dev or DeviceStateMachine(self.game, device=device)
         self._h = self.dev._h                       # so that the engine can share the device program
+        self.sm_ptr = self.dev.sm_ptr               # what ggpzero_interface.Supervisor / Player take
         self.role_sizes = self.dev.role_sizes
         self.n_roles = self.dev.n_roles
         self._joint_move = JointMove(self.n_roles)

@@ -125,61 +125,87 @@ class GdlBasesTransformer(object):
 
 
 # ------------------------------------------------------------------------------------------------
-class _Manager(object):
-    """One engine + its stream — the device counterpart of a ``SelfPlayManager``
-    (``src/cpp/selfplaymanager.h:20-114``). The hand-off itself (pinned buffers, copy-in, engine step,
-    compaction of the waiting rows, copy-out) is native: ``gz_puct_host_poll_submit`` / ``_wait``."""
+def _declare_host(L):
+    if getattr(L, '_gz_host_declared', False):
+        return
+    vp, ci, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64
+    dp, fp = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)
+    L.gz_supervisor_create.argtypes = [vp, vp, ci, ctypes.c_char_p, ci, u64, ci, ci, ctypes.POINTER(vp)]
+    L.gz_supervisor_destroy.argtypes = [vp]
+    L.gz_supervisor_start_self_play.argtypes = [vp, ci, dp, dp, dp]
+    L.gz_supervisor_info.argtypes = [vp, ci]
+    L.gz_supervisor_info.restype = i64
+    L.gz_supervisor_engine.argtypes = [vp, ci]
+    L.gz_supervisor_engine.restype = vp
+    L.gz_supervisor_stream.argtypes = [vp, ci]
+    L.gz_supervisor_stream.restype = vp
+    L.gz_supervisor_poll.argtypes = [vp, ci, ctypes.POINTER(vp), ci, ctypes.POINTER(fp)]
+    L.gz_supervisor_fetch_samples.argtypes = [vp, vp, i64, vp]
+    L.gz_supervisor_fetch_samples.restype = i64
+    L.gz_supervisor_clear_unique_states.argtypes = [vp]
+    L.gz_supervisor_totals.argtypes = [vp, dp]
+    L.gz_player_create.argtypes = [vp, vp, dp, ci, u64, ci, ci, ctypes.POINTER(vp)]
+    L.gz_player_destroy.argtypes = [vp]
+    L.gz_player_engine.argtypes = [vp]
+    L.gz_player_engine.restype = vp
+    L.gz_player_info.argtypes = [vp, ci]
+    L.gz_player_info.restype = i64
+    L.gz_player_reset.argtypes = [vp, ci]
+    L.gz_player_update_config.argtypes = [vp, ctypes.c_double, ci, ci]
+    L.gz_player_apply_move.argtypes = [vp, ctypes.POINTER(ci), ci]
+    L.gz_player_move.argtypes = [vp, vp, ci, ctypes.c_double]
+    L.gz_player_get_move.argtypes = [vp, ci, ctypes.POINTER(ci), fp, ctypes.POINTER(ci)]
+    L.gz_player_balance_moves.argtypes = [vp, ci]
+    L.gz_player_tree_debug.argtypes = [vp, ci, vp, vp, vp]
+    L.gz_player_poll.argtypes = [vp, ci, ctypes.POINTER(vp), ci, ctypes.POINTER(fp)]
+    L.gz_player_last_search.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci]
+    L._gz_host_declared = True
 
-    def __init__(self, engine, stream):
-        e = self.engine = engine
-        self.stream = stream                     # None: the caller's current stream (inline mode)
-        self.n_req = 0                           # rows handed out and not yet answered
-        L = e._L
-        L.gz_puct_host_poll_submit.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
-                                               ctypes.c_int, ctypes.c_void_p]
-        L.gz_puct_host_poll_wait.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_float))]
-        self._n_arrays = len(e.role_sizes) + 1
-        self._ptrs = (ctypes.c_void_p * self._n_arrays)()
-        self._planes_ptr = ctypes.POINTER(ctypes.c_float)()
-        self._planes_np = None
+
+def _resolve_sm(sm, device):
+    """sm: a game name, a DeviceStateMachine, a ggplib-shaped StateMachine (ggplib_api) or its ``sm_ptr`` — the
+    reference passes the state machine as a pointer cast to an int (``cppinterface.py:12-30``); here the pointer is
+    the ``gz_propnet*`` of the device program. Returns (DeviceStateMachine or None, handle)."""
+    from .statemachine import DeviceStateMachine
+    if isinstance(sm, str):
+        dsm = DeviceStateMachine(sm, device=device, goals_mode=_lib.GOALS_TERMINAL_ONLY)
+        return dsm, dsm._h
+    if isinstance(sm, int):
+        return None, ctypes.c_void_p(sm)
+    dev = getattr(sm, 'dev', sm)                 # ggplib_api.StateMachine keeps its DeviceStateMachine in .dev
+    if getattr(dev, '_h', None) is None:
+        raise GGPZeroInterfaceError('not a state machine: %r' % (sm,))
+    return dev, dev._h
+
+
+def _check_predictions(arrays, n, widths):
+    if len(arrays) != len(widths):
+        raise GGPZeroInterfaceError('expected %d policy arrays and one value array' % (len(widths) - 1))
+    for a, w in zip(arrays, widths):
+        if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
+            raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
+        if a.size != n * w:
+            raise GGPZeroInterfaceError('prediction array holds %d values, expected %d x %d' % (a.size, n, w))
+
+
+class _Manager(object):
+    """View of one of the native supervisor's managers (one engine + its stream) — the device counterpart of a
+    ``SelfPlayManager`` (``src/cpp/selfplaymanager.h:20-114``)."""
+
+    def __init__(self, engine, stream_ptr):
+        import torch
+        self.engine = engine
+        self.stream = torch.cuda.ExternalStream(stream_ptr, device=engine.device)
 
     def _ctx(self):
-        import contextlib
         import torch
-        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
-
-    def _stream_ptr(self):
-        import torch
-        s = self.stream if self.stream is not None else torch.cuda.current_stream(self.engine.device)
-        return ctypes.c_void_p(s.cuda_stream)
-
-    def launch(self, n_predictions, arrays=None):
-        """Enqueues, without waiting: predictions -> engine rows, one engine step, the compaction of
-        the rows that now wait for the network and the copy of their planes to pinned host memory."""
-        e = self.engine
-        if n_predictions:
-            for i in range(self._n_arrays):
-                self._ptrs[i] = arrays[i].ctypes.data
-        _lib.check(e._L.gz_puct_host_poll_submit(e._h, int(n_predictions), self._ptrs if n_predictions else None,
-                                                 self._n_arrays if n_predictions else 0, self._stream_ptr()))
-
-    def wait(self):
-        e = self.engine
-        n = e._L.gz_puct_host_poll_wait(e._h, ctypes.byref(self._planes_ptr))
-        if n < 0:
-            _lib.check(n)
-        if self._planes_np is None:
-            self._planes_np = np.ctypeslib.as_array(self._planes_ptr, shape=(e.n_games * e.total_size,))
-        self.n_req = n
-        return n
-
-    def planes(self):
-        return self._planes_np[:self.n_req * self.engine.total_size]
+        return torch.cuda.stream(self.stream)
 
 
 class Supervisor(object):
     """``ggpzero_interface.Supervisor(sm, transformer, batch_size, identifier)``
-    (``src/cpp/pyobjects/supervisor_impl.cpp:215-237``) on the device engine.
+    (``src/cpp/pyobjects/supervisor_impl.cpp:215-237``): a ctypes shell over the native ``gz_supervisor``
+    (``csrc/gz_host.cu``), which holds the managers, their streams and the hand-over logic.
 
     ``poll`` keeps the reference's numpy contract (``src/cpp/pyobjects/common.cpp:160-218``): it takes
     the predictions for the rows handed out by the previous poll and returns a 1-D float32 array of
@@ -189,57 +215,71 @@ class Supervisor(object):
     ``start_self_play(num_workers, conf)``: ``num_workers <= 0`` is the reference's inline mode — one
     manager holding ``batch_size`` games, strictly serial. ``num_workers > 0`` is its worker mode
     (``src/cpp/supervisor.cpp:79-99``: two managers per worker so that the search of one overlaps the
-    network call of the other): here, likewise, two managers of ``batch_size`` games each on their own
-    CUDA streams — while the caller runs the network on the batch of one manager, the other manager's engine
-    step runs on the device. Batches alternate between the managers, as ready managers do in the
-    reference (``supervisor.cpp:129-167``)."""
+    network call of the other): two managers of ``batch_size`` games each on their own CUDA streams."""
 
     def __init__(self, sm, c_transformer, batch_size, identifier, device=0, seed=0x5EED0000,
                  node_cap=4096, child_cap=None):
-        self.sm = sm
-        self.game = sm if isinstance(sm, str) else getattr(sm, 'game', None)
-        if self.game is None:
-            raise GGPZeroInterfaceError('Supervisor needs a state machine created by name')
+        self._L = _lib.lib()
+        _declare_host(self._L)
+        self.sm, self._pn = _resolve_sm(sm, device)
         self.c_transformer = c_transformer
         self.batch_size = int(batch_size)
         self.identifier = identifier
         self.device = device
-        self.seed = seed
-        self.node_cap, self.child_cap = node_cap, child_cap
+        L = self._L
+        self.n_bases = int(L.gz_propnet_info(self._pn, _lib.INFO_N_BASES))
+        n_roles = int(L.gz_propnet_info(self._pn, _lib.INFO_N_ROLES))
+        self.role_sizes = [int(L.gz_propnet_info(self._pn, _lib.INFO_ROLE_SIZE0 + r)) for r in range(n_roles)]
+        c_transformer.finalize(self.n_bases, device)
+        h = ctypes.c_void_p()
+        _lib.check(L.gz_supervisor_create(self._pn, c_transformer._h, self.batch_size, str(identifier).encode(), device,
+                                          seed, node_cap, child_cap or 0, ctypes.byref(h)))
+        self._h = h
         self.engine = None
         self.managers = []
-        self._cur = None            # manager whose planes were handed out by the last poll
-        self._primed = False
+        self._ptrs = (ctypes.c_void_p * (n_roles + 1))()
+        self._planes_ptr = ctypes.POINTER(ctypes.c_float)()
+        self._views = {}
         # additive (measurement aid): fn(engine, manager_index) -> int32 CUDA tensor [games, state_words]; the
         # first game of every slot then starts there instead of the initial state (PuctEngine.set_start_states)
         self.start_states_fn = None
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            self.managers = []
+            self.engine = None
+            self._L.gz_supervisor_destroy(h)
+            self._h = None
 
     def set_num_workers(self, n):
         """Not in the reference's method table although its Python wrapper calls it
         (``cppinterface.py:197-198``); accepted and ignored — the device engine has no worker threads."""
 
     def start_self_play(self, num_workers, conf_dict):
-        from .engine import PuctEngine
+        from .engine import PuctEngine, _puct_array, _sp_array
         import torch
-        n_man = 2 if num_workers > 0 else 1
-        sizes = [self.batch_size] * n_man
+        L = self._L
         self.managers = []
-        dsm = self.sm if not isinstance(self.sm, str) else None
-        for k, g in enumerate(sizes):
-            eng = PuctEngine(self.game, conf_dict, n_games=g, mode=0, device=self.device,
-                             seed=self.seed + 104729 * k, node_cap=self.node_cap, child_cap=self.child_cap,
-                             c_transformer=self.c_transformer, plane_dtype=torch.float32, sm=dsm)
-            dsm = eng.sm                                      # managers share the device program
+        _lib.check(L.gz_supervisor_start_self_play(self._h, int(num_workers), _sp_array(conf_dict),
+                                                   _puct_array(conf_dict['puct_config']),
+                                                   _puct_array(conf_dict['run_to_end_puct_config'])))
+        ct = self.c_transformer
+        shape = (ct.num_channels, -1, -1)
+        for k in range(int(L.gz_supervisor_info(self._h, 0))):
+            eng = PuctEngine.from_handle(L.gz_supervisor_engine(self._h, k), self.device, self.n_bases, self.role_sizes,
+                                         (ct.num_channels, ct.channel_size, 1), plane_dtype=torch.float32, sm=self.sm)
+            m = _Manager(eng, L.gz_supervisor_stream(self._h, k))
             if self.start_states_fn is not None:
-                eng.set_start_states(self.start_states_fn(eng, k))
-            stream = torch.cuda.Stream(device=eng.device) if n_man > 1 else None
-            self.managers.append(_Manager(eng, stream))
+                with m._ctx():
+                    eng.set_start_states(self.start_states_fn(eng, k))
+                m.stream.synchronize()
+            self.managers.append(m)
         self.engine = self.managers[0].engine
-        torch.cuda.synchronize(self.engine.device)
-        self._cur = None
-        self._primed = False
+        self.total_size = int(L.gz_supervisor_info(self._h, 2))
+        self._views = {}
 
-    # -- zero-copy path (inline mode)
+    # -- zero-copy path (inline mode): CUDA tensors in, CUDA tensors out, on the caller's stream
     def poll_device(self, policy=None, value=None, sub_iters=1):
         return self.engine.advance(policy, value, sub_iters)
 
@@ -250,56 +290,27 @@ class Supervisor(object):
         None when nothing needs evaluating."""
         if not self.managers:
             raise GGPZeroInterfaceError('start_self_play() has not been called')
-        if not (0 <= n_predictions <= self.batch_size):
-            raise GGPZeroInterfaceError('n_predictions out of range')
-        M = self.managers
-        if not self._primed:
-            if n_predictions != 0:
-                raise GGPZeroInterfaceError('first poll must pass n_predictions == 0')
-            for m in M:
-                m.launch(0)
-            self._primed = True
-            nxt = 0
-        else:
-            cur = self._cur
-            m = M[cur]
-            if n_predictions != m.n_req:
-                raise GGPZeroInterfaceError('expected %d predictions, got %d' % (m.n_req, n_predictions))
-            if n_predictions:
-                e = m.engine
-                R = len(e.role_sizes)
-                if len(arrays) != R + 1:
-                    raise GGPZeroInterfaceError('expected %d policy arrays and one value array' % R)
-                widths = list(e.role_sizes) + [e.n_rewards]
-                for a, w in zip(arrays, widths):
-                    if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
-                        raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
-                    if a.size != n_predictions * w:
-                        raise GGPZeroInterfaceError('prediction array holds %d values, expected %d x %d'
-                                                    % (a.size, n_predictions, w))
-            m.n_req = 0
-            m.launch(n_predictions, arrays)
-            nxt = (cur + 1) % len(M)
-        # hand out the next ready batch; a manager with nothing to evaluate is stepped again
-        for _ in range(64 * len(M)):
-            m = M[nxt]
-            if m.wait() > 0:
-                self._cur = nxt
-                return m.planes()
-            m.launch(0)
-            nxt = (nxt + 1) % len(M)
-        self._primed = False
-        self._cur = None
-        return None
+        if n_predictions:
+            _check_predictions(arrays, n_predictions, self.role_sizes + [self.engine.n_rewards])
+            for i, a in enumerate(arrays):
+                self._ptrs[i] = a.ctypes.data
+        n = self._L.gz_supervisor_poll(self._h, int(n_predictions), self._ptrs if n_predictions else None,
+                                       len(self._ptrs) if n_predictions else 0, ctypes.byref(self._planes_ptr))
+        if n < 0:
+            _lib.check(n)
+        if n == 0:
+            return None
+        addr = ctypes.addressof(self._planes_ptr.contents)
+        view = self._views.get(addr)
+        if view is None:
+            view = self._views[addr] = np.ctypeslib.as_array(self._planes_ptr, shape=(self.batch_size * self.total_size,))
+        return view[:n * self.total_size]
 
     def totals(self):
-        out = None
-        for m in self.managers:
-            with m._ctx():                         # ordered behind the manager's queued engine step
-                t = m.engine.totals()
-            out = t if out is None else {k: (max(out[k], t[k]) if k.startswith('max_') else out[k] + t[k])
-                                         for k in out}
-        return out
+        from .engine import TOTAL_KEYS
+        out = (ctypes.c_double * len(TOTAL_KEYS))()
+        _lib.check(self._L.gz_supervisor_totals(self._h, out))
+        return dict(zip(TOTAL_KEYS, [float(x) for x in out]))
 
     def check_health(self):
         """Raises when game slots were lost (halted) or finished samples were dropped (fetch_samples called too
@@ -311,212 +322,168 @@ class Supervisor(object):
         return t
 
     def fetch_samples(self):
+        """``None`` or a list of dicts with the keys of ``supervisor_impl.cpp:75-118`` (== ``datadesc.Sample``)."""
+        e = self.engine
+        cap = e.ready_cap * len(self.managers)
+        buf = np.zeros((cap, e.srec), dtype=np.int32)
+        man = np.zeros(cap, dtype=np.int32)
+        n = self._L.gz_supervisor_fetch_samples(self._h, buf.ctypes.data, cap, man.ctypes.data)
+        if n < 0:
+            _lib.check(int(n))
         res = []
-        for k, m in enumerate(self.managers):
-            with m._ctx():
-                recs = m.engine.fetch_sample_records()
+        for k in range(len(self.managers)):
+            recs = buf[:n][man[:n] == k]
             if len(recs):
                 ident = self.identifier if len(self.managers) == 1 else '%s_m%d' % (self.identifier, k)
-                res.extend(m.engine.records_to_samples(recs, ident))
+                res.extend(e.records_to_samples(recs, ident))
         return res or None
 
     def add_unique_state(self, bs):
         """The reference's Python wrapper no-ops this call as well (``cppinterface.py:218-219``)."""
 
     def clear_unique_states(self):
-        for m in self.managers:
-            with m._ctx():
-                m.engine.clear_unique_states()
+        _lib.check(self._L.gz_supervisor_clear_unique_states(self._h))
 
 
 # ------------------------------------------------------------------------------------------------
 class Player(object):
     """``ggpzero_interface.Player(sm, transformer, puct_conf_dict)``
-    (``src/cpp/pyobjects/player_impl.cpp:8-129,183-201``, ``src/cpp/player.cpp``) on the device engine
-    in player mode (one tree).
+    (``src/cpp/pyobjects/player_impl.cpp:8-129,183-201``, ``src/cpp/player.cpp``): a ctypes shell over the
+    native ``gz_player`` (``csrc/gz_host.cu``) — the device engine in player mode (one tree).
 
     As in the reference, ``player_apply_move`` / ``player_move`` only *enqueue* work
     (``player.cpp:59-103``); it is carried out by the following ``poll`` calls, which hand out the
-    planes of the leaf to evaluate and return ``None`` once the queue has drained.
+    planes of the leaf to evaluate and return ``None`` once the queue has drained. ``end_time`` and the
+    configuration's ``think_time`` are honoured (the host watches the clock and tells the device search to stop
+    at its next playout boundary, ``evaluator.cpp:794,820-826``).
 
-    Differences from the reference (DESIGN.md §6): one outstanding evaluation per tree whatever
-    ``batch_size`` says; ``end_time`` / ``think_time`` wall-clock limits are not consulted (the search
-    stops on its evaluation budget and convergence rules); ``player_balance_moves`` is accepted and
-    does nothing; ``player_tree_debug`` reports no variation lines."""
-
-    CMD_RESET, CMD_APPLY, CMD_SEARCH = 1, 2, 3
+    Differences from the reference (DESIGN.md §7): one outstanding evaluation per tree whatever
+    ``batch_size`` says; ``player_balance_moves`` is accepted and does nothing; ``player_tree_debug`` reports
+    no variation lines."""
 
     def __init__(self, sm, c_transformer, puct_conf_dict, device=0, seed=0x5EED0001, node_cap=1 << 16,
                  child_cap=None):
-        from .engine import PuctEngine
+        from .engine import PuctEngine, _puct_array
         from .defs import confs
         import attr
         import torch
-        self.sm = sm
-        self.game = sm if isinstance(sm, str) else getattr(sm, 'game', None)
-        if self.game is None:
-            raise GGPZeroInterfaceError('Player needs a state machine created by name')
         if not isinstance(puct_conf_dict, dict):
             raise GGPZeroInterfaceError('puct config must be a dict (attr.asdict(PUCTEvaluatorConfig))')
+        self._L = _lib.lib()
+        _declare_host(self._L)
+        L = self._L
+        self.sm, self._pn = _resolve_sm(sm, device)
         self.conf = dict(attr.asdict(confs.PUCTEvaluatorConfig()))
         self.conf.update(puct_conf_dict)
-        sp = attr.asdict(confs.selfplay_config_template())
-        sp['puct_config'] = dict(self.conf)
-        sp['run_to_end_puct_config'] = dict(self.conf)
-        self._sp = sp
         self.c_transformer = c_transformer
-        self.engine = PuctEngine(self.game, sp, n_games=1, mode=PuctEngine.MODE_PLAYER, device=device, seed=seed,
-                                 node_cap=node_cap, child_cap=child_cap, c_transformer=c_transformer,
-                                 plane_dtype=torch.float32,
-                                 sm=self.sm if not isinstance(self.sm, str) else None)
-        e = self.engine
-        self._host_planes = torch.empty((1, e.total_size), dtype=torch.float32).pin_memory()
-        self._queue = []            # pending (kind, payload) commands, reference: scheduler runnables
-        self._busy = False          # a command is in the engine's mailbox
-        self._current = None
-        self._waiting = 0           # rows handed out by the last poll
-        self._first_play = False
-        self._game_depth = 0
-        self._choice = None         # (snapshot) of the last finished search
-        self._fresh = False
+        self.n_bases = int(L.gz_propnet_info(self._pn, _lib.INFO_N_BASES))
+        n_roles = int(L.gz_propnet_info(self._pn, _lib.INFO_N_ROLES))
+        self.role_sizes = [int(L.gz_propnet_info(self._pn, _lib.INFO_ROLE_SIZE0 + r)) for r in range(n_roles)]
+        c_transformer.finalize(self.n_bases, device)
+        h = ctypes.c_void_p()
+        _lib.check(L.gz_player_create(self._pn, c_transformer._h, _puct_array(self.conf), device, seed, node_cap,
+                                      child_cap or 0, ctypes.byref(h)))
+        self._h = h
+        self.total_size = int(L.gz_player_info(h, 0))
+        self.state_words = int(L.gz_player_info(h, 3))
+        self.max_actions = int(L.gz_player_info(h, 2))
+        self.engine = PuctEngine.from_handle(L.gz_player_engine(h), device, self.n_bases, self.role_sizes,
+                                             (c_transformer.num_channels, c_transformer.channel_size, 1),
+                                             mode=PuctEngine.MODE_PLAYER, plane_dtype=torch.float32, sm=self.sm)
+        self._ptrs = (ctypes.c_void_p * (n_roles + 1))()
+        self._planes_ptr = ctypes.POINTER(ctypes.c_float)()
+        self._planes_np = None
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            self.engine = None
+            self._L.gz_player_destroy(h)
+            self._h = None
 
     # ---- reference method table
     def player_reset(self, game_depth):
-        self._game_depth = int(game_depth)
-        self._first_play = True
-        self._queue = []
-        self._choice = None
+        _lib.check(self._L.gz_player_reset(self._h, int(game_depth)))
 
     def player_update_config(self, think_time, converged_visits, verbose):
-        from .engine import _puct_array, _sp_array
         self.conf['think_time'] = float(think_time)
         self.conf['converged_visits'] = int(converged_visits)
         self.conf['verbose'] = bool(verbose)
-        self._sp['puct_config'] = dict(self.conf)
-        self._sp['run_to_end_puct_config'] = dict(self.conf)
-        e = self.engine
-        _lib.check(e._L.gz_puct_set_config(e._h, _sp_array(self._sp), _puct_array(self.conf),
-                                           _puct_array(self.conf)))
-
-    def _joint_move_list(self, jm):
-        if hasattr(jm, 'get') and hasattr(jm, 'get_count'):
-            return [int(jm.get(i)) for i in range(jm.get_count())]
-        return [int(x) for x in jm]
-
-    def _state_words(self, bs):
-        from . import tables
-        if hasattr(bs, 'to_list'):
-            bits = np.asarray(bs.to_list(), dtype=np.uint8)
-            return tables.pack_state_bits(bits, self.engine.state_words)
-        return np.ascontiguousarray(bs, dtype=np.uint32)
+        _lib.check(self._L.gz_player_update_config(self._h, float(think_time), int(converged_visits), int(bool(verbose))))
 
     def player_apply_move(self, joint_move):
-        moves = self._joint_move_list(joint_move)
-        if self._first_play:
-            self._first_play = False
-            self._queue.append(('reset', None))           # establishRoot(nullptr): the initial state
-        self._queue.append(('apply', moves))
+        if hasattr(joint_move, 'get') and hasattr(joint_move, 'get_count'):
+            moves = [int(joint_move.get(i)) for i in range(joint_move.get_count())]
+        else:
+            moves = [int(x) for x in joint_move]
+        arr = (ctypes.c_int * len(moves))(*moves)
+        _lib.check(self._L.gz_player_apply_move(self._h, arr, len(moves)))
 
     def player_move(self, basestate, evaluations, end_time):
-        self._choice = None
-        if self._first_play:
-            self._first_play = False
-            self._queue.append(('reset', self._state_words(basestate)))
-        self._queue.append(('search', int(evaluations)))
+        from . import tables
+        words = None
+        if basestate is not None:
+            if hasattr(basestate, 'to_list'):
+                words = tables.pack_state_bits(np.asarray(basestate.to_list(), dtype=np.uint8), self.state_words)
+            else:
+                words = np.ascontiguousarray(basestate, dtype=np.uint32)
+        _lib.check(self._L.gz_player_move(self._h, words.ctypes.data if words is not None else None, int(evaluations),
+                                          float(end_time)))
 
     def player_get_move(self, lead_role_index):
-        """-> (legal index of ``lead_role_index``'s move, score of the chosen child or -1, node count)."""
-        s = self._choice
-        if s is None or s['choice'] < 0 or len(s['moves']) == 0:
-            return (-1, -1.0, -1)
-        ch = s['choice']
-        if lead_role_index == s['lead_role']:
-            move = int(s['moves'][ch])
-        else:
-            move = int(s['other_moves'][lead_role_index])
-        # the chosen child's score FOR THE ROLE ASKED ABOUT (player.cpp:105-119), not for the root's lead role
-        return (move, float(s['choice_scores'][lead_role_index]), int(s['nodes']))
+        """-> (legal index of ``lead_role_index``'s move, the chosen child's score FOR THAT ROLE or -1, node count)
+        (``player.cpp:105-119``)."""
+        mv, sc, nodes = ctypes.c_int(), ctypes.c_float(), ctypes.c_int()
+        _lib.check(self._L.gz_player_get_move(self._h, int(lead_role_index), ctypes.byref(mv), ctypes.byref(sc),
+                                              ctypes.byref(nodes)))
+        return (mv.value, float(sc.value), nodes.value)
 
     def player_balance_moves(self, max_count):
         """Accepted for API parity; the device engine does not rebalance first moves
         (``src/cpp/puct/evaluator.cpp:282-339`` is an analysis aid of the tournament tooling)."""
+        _lib.check(self._L.gz_player_balance_moves(self._h, int(max_count)))
 
     def player_tree_debug(self, max_count):
         """-> tuple of (score, lead_role_index, move_index, variation) for the root's most visited
         expanded children (``src/cpp/puct/node.cpp:400-440``); variation lines are not reported."""
-        s = self.engine.snapshot(0)
-        order = sorted(range(len(s['moves'])), key=lambda i: -int(s['traversals'][i]))
-        out = []
-        for i in order[:max(0, int(max_count))]:
-            if s['scores'][i] < 0:
-                continue
-            out.append((float(s['scores'][i]), int(s['lead_role']), int(s['moves'][i]), ()))
-        return tuple(out)
+        n = max(0, int(max_count))
+        sc = np.zeros(max(n, 1), dtype=np.float32)
+        ld = np.zeros(max(n, 1), dtype=np.int32)
+        mv = np.zeros(max(n, 1), dtype=np.int32)
+        k = self._L.gz_player_tree_debug(self._h, n, sc.ctypes.data, ld.ctypes.data, mv.ctypes.data)
+        if k < 0:
+            _lib.check(k)
+        return tuple((float(sc[i]), int(ld[i]), int(mv[i]), ()) for i in range(k))
+
+    def last_search(self):
+        """Additive: the root's children after the last finished search (dict as ``PuctEngine.snapshot``), or None."""
+        mc = self.max_actions
+        oi = np.zeros(16, dtype=np.int32)
+        of = np.zeros(8, dtype=np.float32)
+        mv, tr = np.zeros(mc, dtype=np.int32), np.zeros(mc, dtype=np.int32)
+        pr, sc, nx = np.zeros(mc, dtype=np.float32), np.zeros(mc, dtype=np.float32), np.zeros(mc, dtype=np.float32)
+        n = self._L.gz_player_last_search(self._h, oi.ctypes.data, of.ctypes.data, mv.ctypes.data, tr.ctypes.data,
+                                          pr.ctypes.data, sc.ctypes.data, nx.ctypes.data, mc)
+        if n <= 0:
+            return None
+        R = len(self.role_sizes)
+        return dict(choice=int(oi[3]), nodes=int(oi[4]), root_visits=int(oi[6]), lead_role=int(oi[7]),
+                    other_moves=[int(x) for x in oi[9:9 + R]], root_score=float(of[0]),
+                    choice_scores=[float(x) for x in of[1:1 + R]], moves=mv[:n].copy(), traversals=tr[:n].copy(),
+                    policy_prob=pr[:n].copy(), scores=sc[:n].copy(), next_prob=nx[:n].copy())
 
     # ---- the poll contract (src/cpp/player.cpp:155-173, src/cpp/pyobjects/common.cpp:160-218)
-    def _issue_next(self):
-        e = self.engine
-        kind, payload = self._queue.pop(0)
-        self._current = kind
-        if kind == 'reset':
-            e.command(0, self.CMD_RESET, arg=self._game_depth, state=payload)
-        elif kind == 'apply':
-            s = e.snapshot(0, 0)
-            lead = s['lead_role'] if s['lead_role'] >= 0 else 0
-            e.command(0, self.CMD_APPLY, arg=payload[lead])
-            self._game_depth += 1
-        else:
-            e.command(0, self.CMD_SEARCH, evals=payload)
-        self._busy = True
-
     def poll(self, n_predictions, arrays):
-        import torch
-        e = self.engine
-        if n_predictions != self._waiting:
-            raise GGPZeroInterfaceError('expected %d predictions, got %d' % (self._waiting, n_predictions))
-        fresh = False
         if n_predictions:
-            R = len(e.role_sizes)
-            if len(arrays) != R + 1:
-                raise GGPZeroInterfaceError('expected %d policy arrays and one value array' % R)
-            off = 0
-            row = np.zeros((1, e.policy_stride), dtype=np.float32)
-            for r in range(R):
-                a = arrays[r]
-                if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags['C_CONTIGUOUS']:
-                    raise GGPZeroInterfaceError('predictions must be C-contiguous float32 numpy arrays')
-                row[0, off:off + e.role_sizes[r]] = a.reshape(-1)[:e.role_sizes[r]]
-                off += e.role_sizes[r]
-            e.policy.copy_(torch.from_numpy(row))
-            e.value.copy_(torch.from_numpy(np.ascontiguousarray(arrays[R], dtype=np.float32).reshape(1, e.n_rewards)))
-            fresh = True
-        self._waiting = 0
-        guard = 0
-        while True:
-            if not self._busy:
-                if not self._queue:
-                    return None
-                self._issue_next()
-            e.advance(e.policy if fresh else None, e.value if fresh else None)
-            fresh = False
-            if not hasattr(self, '_need_buf'):
-                self._need_buf = torch.zeros(1, dtype=torch.uint8, device=e.device)
-                e._L.gz_puct_copy_need_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-            _lib.check(e._L.gz_puct_copy_need_eval(e._h, self._need_buf.data_ptr(), e._stream()))
-            need = int(self._need_buf[0].item())                       # device sync
-            if need:
-                self._host_planes.copy_(e.planes.reshape(1, -1).to(torch.float32), non_blocking=True)
-                torch.cuda.current_stream(e.device).synchronize()
-                self._waiting = 1
-                return self._host_planes.numpy().reshape(-1)
-            guard += 1
-            if guard % 4 == 0 or guard < 3:
-                s = e.snapshot(0, 0)
-                if s['error'] or s['cmd_done'] < 0:
-                    raise GGPZeroInterfaceError('device player failed: error %d, cmd_done %d' % (s['error'], s['cmd_done']))
-                if s['cmd_done'] == 1:
-                    self._busy = False
-                    if self._current == 'search':
-                        self._choice = e.snapshot(0)
-            if guard > 10000000:
-                raise GGPZeroInterfaceError('device player did not finish')
+            _check_predictions(arrays, n_predictions, self.role_sizes + [self.engine.n_rewards])
+            for i, a in enumerate(arrays):
+                self._ptrs[i] = a.ctypes.data
+        n = self._L.gz_player_poll(self._h, int(n_predictions), self._ptrs if n_predictions else None,
+                                   len(self._ptrs) if n_predictions else 0, ctypes.byref(self._planes_ptr))
+        if n < 0:
+            _lib.check(n)
+        if n == 0:
+            return None
+        if self._planes_np is None:
+            self._planes_np = np.ctypeslib.as_array(self._planes_ptr, shape=(self.total_size,))
+        return self._planes_np

@@ -54,6 +54,12 @@ class DeviceStateMachine:
         self.specialised = bool(info(10))      # a generated thread-sliced kernel exists for this game
         self.launch_info['specialised'] = self.specialised
 
+    @property
+    def sm_ptr(self) -> int:
+        """The state machine as a pointer cast to an int — what the reference hands to its extension module
+        (``cppinterface.py:12-30``); here the ``gz_propnet*`` of the device program."""
+        return int(self._h.value)
+
     def set_spec_min_batch(self, n: int):
         """Batches of at least ``n`` states use the game-specialised kernel (default 2^18; < 0 disables)."""
         self._L.gz_propnet_set_spec_min_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64]

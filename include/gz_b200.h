@@ -21,7 +21,7 @@
  *   gz_transformer_* / gz_encode GdlBasesTransformer and toChannels (src/cpp/gdltransformer.cpp:14-52)
  *   gz_puct_*                    Supervisor / Player: create, advance (device tensors), host_poll_submit / _wait
  *                                (numpy poll contract), fetch_samples, command / snapshot (src/cpp/supervisor.cpp,
- *                                src/cpp/player.cpp, src/cpp/pyobjects/*.cpp)
+ *                                src/cpp/player.cpp and the files under src/cpp/pyobjects)
  *   gz_permute_state_bits        Translator.translate_basestate, batched (src/ggpzero/util/symmetry.py:153-204)
  */
 #ifndef GZ_B200_H
@@ -224,6 +224,61 @@ int gz_puct_clear_unique_states(gz_puct* h, void* stream);
 int gz_puct_command(gz_puct* h, int game, int cmd, int arg, int evals, const uint32_t* h_state, void* stream);
 int gz_puct_snapshot(gz_puct* h, int game, int max_children, int* out_i16, float* out_f8, int* moves, int* trav,
                      float* prob, float* score, float* next_prob, void* stream);
+
+/* Player mode: one 16-byte status copy of game `game` — [cmd_done, phase, error, waiting for the network] — and
+ * the host's clock talking to a running search (mode 1: stop at the next playout boundary — the hard end_time, or
+ * think_time x multiplier; mode 2: stop as soon as the search has converged — think_time elapsed;
+ * src/cpp/puct/evaluator.cpp:794,820-826). */
+int gz_puct_status(gz_puct* h, int game, int* h_out4, void* stream);
+int gz_puct_request_stop(gz_puct* h, int game, int mode, void* stream);
+
+/* ---- the reference's Supervisor and Player objects, native host side (csrc/gz_host.cu) -----------------------
+ * What src/cpp/pyobjects/supervisor_impl.cpp and player_impl.cpp bind, method for method; the extension module
+ * galvanise_zero_b200/csrc/ggpzero_interface.cpp and the ctypes host galvanise_zero_b200/interface.py are both thin
+ * layers over these calls.
+ *
+ *   gz_supervisor_create            Supervisor(sm_ptr, transformer, batch_size, identifier)  supervisor_impl.cpp:215-237
+ *   gz_supervisor_start_self_play   .start_self_play(num_workers, conf_dict)                 supervisor_impl.cpp:14-32
+ *                                   (configuration as the flat arrays of gz_puct_create; num_workers <= 0: inline,
+ *                                   one manager; > 0: worker mode, two managers, supervisor.cpp:68-99)
+ *   gz_supervisor_poll              .poll(n_predictions, [policy_0.., value])                common.cpp:160-218
+ *                                   returns rows handed out (> 0, *h_planes pinned [rows][total] float32), 0 = None
+ *   gz_supervisor_fetch_samples     .fetch_samples()  (records; the binding turns them into dicts)  :75-128
+ *   gz_supervisor_clear_unique_states                                                        :138-144
+ *   gz_player_create                Player(sm_ptr, transformer, puct_conf_dict)              player_impl.cpp:183-201
+ *   gz_player_reset / _apply_move / _move / _get_move / _update_config / _balance_moves / _tree_debug / _poll
+ *                                   the player_* methods                                      player_impl.cpp:8-129
+ */
+typedef struct gz_supervisor gz_supervisor;
+int gz_supervisor_create(gz_propnet* pn, gz_transformer* tr, int batch_size, const char* identifier, int device,
+                         uint64_t seed, int node_cap, int child_cap, gz_supervisor** out);
+void gz_supervisor_destroy(gz_supervisor* s);
+int gz_supervisor_start_self_play(gz_supervisor* s, int num_workers, const double* sp_conf, const double* puct_conf,
+                                  const double* run_to_end_puct_conf);
+int64_t gz_supervisor_info(const gz_supervisor* s, int what); /* 0 managers, 1 batch size, 2 plane row, 3 record words, 4 roles */
+gz_puct* gz_supervisor_engine(gz_supervisor* s, int manager);
+void* gz_supervisor_stream(gz_supervisor* s, int manager);
+int gz_supervisor_poll(gz_supervisor* s, int n_pred, const float* const* h_arrays, int n_arrays, const float** h_planes);
+int64_t gz_supervisor_fetch_samples(gz_supervisor* s, int32_t* h_out, int64_t cap, int32_t* h_manager);
+int gz_supervisor_clear_unique_states(gz_supervisor* s);
+int gz_supervisor_totals(gz_supervisor* s, double* h_out25);
+
+typedef struct gz_player gz_player;
+int gz_player_create(gz_propnet* pn, gz_transformer* tr, const double* puct_conf, int device, uint64_t seed, int node_cap,
+                     int child_cap, gz_player** out);
+void gz_player_destroy(gz_player* p);
+gz_puct* gz_player_engine(gz_player* p);
+int64_t gz_player_info(const gz_player* p, int what);         /* 0 plane row, 1 roles, 2 max actions, 3 state words */
+int gz_player_reset(gz_player* p, int game_depth);
+int gz_player_update_config(gz_player* p, double think_time, int converged_visits, int verbose);
+int gz_player_apply_move(gz_player* p, const int* joint_move, int n_roles);
+int gz_player_move(gz_player* p, const uint32_t* h_state, int evaluations, double end_time);
+int gz_player_get_move(gz_player* p, int role, int* move, float* score, int* nodes);
+int gz_player_balance_moves(gz_player* p, int max_count);
+int gz_player_tree_debug(gz_player* p, int max_count, float* scores, int* lead, int* moves);
+int gz_player_poll(gz_player* p, int n_pred, const float* const* h_arrays, int n_arrays, const float** h_planes);
+int gz_player_last_search(gz_player* p, int* out_i16, float* out_f8, int* moves, int* trav, float* prob, float* score,
+                          float* next_prob, int cap);
 
 /* Deterministic synthetic policy/value network (include/gz_synth.h) on encoded planes — parity and
  * benchmarking utility; the production network is a PyTorch module. */

@@ -152,7 +152,7 @@ def test_play_poller_matches_reference_search(game, evals, moves):
         poller.poll_loop()
         lead = r['lead_role']
         mv, score, nodes = poller.player_get_move(lead)
-        snap = poller.c_player._choice
+        snap = poller.c_player.last_search()
         assert np.array_equal(snap['moves'], r['moves'])
         assert np.array_equal(snap['traversals'], r['traversals']), 'visit counts differ at move %d' % k
         assert snap['choice'] == r['choice']

@@ -92,7 +92,8 @@ def test_fixtures_cover_the_rules_corner_cases():
     for game in ('breakthrough', 'breakthroughSmall', 'connect6', 'amazons_10x10'):
         fx = load_fixture(game)
         assert len(fx['games']) >= 20, game
-    assert sum(int(g[-1]['terminal']) for g in load_fixture('amazons_10x10')['games']) >= 10
+    for game in ('amazons_10x10', 'connect6'):
+        assert sum(int(g[-1]['terminal']) for g in load_fixture(game)['games']) >= 20, game
 
 
 def test_reversi_action_order_fact():
