@@ -666,6 +666,15 @@ def run_puct(args, rank, world, local, propnet_line=None):
 
     # ---- end of 'generation': gather the finished samples to rank 0 over NCCL (the only collective), timed on its own
     recs = np.concatenate([e.fetch_sample_records() for e in engines], axis=0)
+    produced = int(recs.shape[0])
+    if args.gather_records > 0:
+        # a generation's worth of records (templates.py:171: 20 000 samples) split over the ranks: the records
+        # this run produced, repeated up to this rank's share, so that the collective moves a real generation's bytes
+        share = (args.gather_records + world - 1) // world
+        if produced == 0:
+            recs = np.zeros((share, eng.srec), dtype=np.int32)
+        else:
+            recs = np.concatenate([recs] * ((share + produced - 1) // produced), axis=0)[:share]
     recs_dev = torch.from_numpy(recs).to(eng.device)
     barrier(world)
     tg0 = time.perf_counter()
@@ -708,7 +717,10 @@ def run_puct(args, rank, world, local, propnet_line=None):
             'gpu_launches': own_launches, 'clocks': clocks,
             'engine_totals': {k: t_after[k] for k in ('errors', 'halted', 'max_nodes', 'max_children', 'games', 'samples')},
             'sample_gather': {'records_on_rank0': n_gathered, 'record_bytes': int(recs.shape[1]) * 4 if recs.ndim == 2 else 0,
-                              'seconds': gather_s, 'collective': 'all_gather of counts + all_gather of padded records (NCCL)'},
+                              'bytes_on_rank0': n_gathered * (int(recs.shape[1]) * 4 if recs.ndim == 2 else 0),
+                              'seconds': gather_s, 'produced_by_rank0_in_this_run': produced,
+                              'padded_to_generation_size': args.gather_records if args.gather_records > 0 else None,
+                              'collective': 'all_gather of counts + all_gather of padded records (NCCL over NVLink; gloo in the CPU tests)'},
             'propnet': propnet_line,
         }
         print(json.dumps(line), flush=True)
@@ -802,6 +814,8 @@ def main():
                     help='puct workload: playout launches per step of the propnet half of the line')
     ap.add_argument('--no-propnet', action='store_true', help='puct workload: leave the propnet half out')
     ap.add_argument('--no-stagger', action='store_true', help='all slots start at the initial state')
+    ap.add_argument('--gather-records', type=int, default=20000,
+                    help='records in the timed end-of-generation gather (the run\'s own records repeated; 0: only those produced)')
     ap.add_argument('--max-iters', type=int, default=0, help='engine step limit: controller iterations per game')
     ap.add_argument('--max-work', type=int, default=0, help='engine step limit: tree levels descended per game')
     ap.add_argument('--no-graph', action='store_true')

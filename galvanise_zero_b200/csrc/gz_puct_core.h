@@ -2115,7 +2115,7 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
                 bool have_kid = false;
                 const bool is_converged = gzp_converged(V, cf.converged_visits, root_nd, &root_kid, &have_kid);
                 const int max_non_converged = (int)(c->max_evaluations * cf.evaluation_multiplier_to_convergence);
-                const int max_tree_playouts = 4 * max_non_converged;
+                const int max_tree_playouts = max_non_converged > (1 << 28) ? (1 << 30) : 4 * max_non_converged;
                 bool brk = false;
                 if (c->stop_request == GZP_STOP_NOW || (c->stop_request == GZP_STOP_IF_CONVERGED && is_converged)) brk = true;
                 else if ((root_nd.n_flags & NF_FINALISED) && c->num_tree_playouts > 100) brk = true;
@@ -2126,7 +2126,7 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
                 // Deviation (documented in DESIGN.md): the reference loops forever when a search only
                 // reaches terminal / finalised nodes and the root never 'converges' (no evaluation is
                 // ever counted); a game slot must not be lost, so such a search stops here.
-                else if (c->num_tree_playouts > 64 * max_tree_playouts + 10000) brk = true;
+                else if ((long long)c->num_tree_playouts > 64LL * max_tree_playouts + 10000LL) brk = true;
                 if (brk || c->max_evaluations == 0) { c->phase = PH_MOVE_DONE; break; }
                 c->cur = root;
                 c->path_len = 0;

@@ -176,7 +176,7 @@ def test_player_honours_wall_clock_limits():
 
     def run(player, end_time):
         player.player_reset(0)
-        player.player_move(sm.get_initial_state(), 10 ** 8, end_time)
+        player.player_move(sm.get_initial_state(), 10 ** 7, end_time)
         t0 = time.time()
         planes = player.poll(0, [])
         while planes is not None:
