@@ -169,6 +169,8 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
     steps = steps or args.steps
     game = (args.game if args.workload == 'propnet' else '') or PROPNET_GAME
     dev = DeviceStateMachine(game, device=local, goals_mode=gzlib.GOALS_ALWAYS)
+    if args.group_min_batch is not None:
+        dev.set_group_min_batch(args.group_min_batch)
     n = (args.slots if args.workload == 'propnet' else 0) or PROPNET_SLOTS
     slot0 = rank * n
     s = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
@@ -211,7 +213,10 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^21 slots (ncu --set full)
                 'traffic': (PROPNET_SPEC_NCU_TRAFFIC_BYTES if spec else PROPNET_TABLE_NCU_TRAFFIC_BYTES) if (n == PROPNET_SLOTS and game == PROPNET_GAME) else None,
                 'kernel': 'spec_kernel<GzSpec_%s, PLAYOUT> (game-specialised, thread-sliced)' % game if spec
-                          else ('pn_wide_kernel<MODE_PLAYOUT>' if dev.launch_info['smem_bytes'] == 0 else 'pn_kernel<MODE_PLAYOUT> (table-driven)'),
+                          else ('pn_group_kernel<MODE_PLAYOUT> (1024 games per CTA / cluster, one tile per lane)'
+                                if (args.group_min_batch is None or 0 <= args.group_min_batch <= n) and n >= 1024
+                                else ('pn_wide_kernel<MODE_PLAYOUT>' if dev.launch_info['smem_bytes'] == 0
+                                      else 'pn_kernel<MODE_PLAYOUT> (table-driven)')),
                 'bytes_per_unit': tb, 'units_per_launch': n, 'launch_ms': launch_s * 1e3,
                 'peak_source': peaks['source'] + ' (HBM copy)',
                 'traffic_source': 'profiles/r01b_propnet_spec_kernel_ncu_full.md' if spec
@@ -446,6 +451,8 @@ def run_puct(args, rank, world, local, propnet_line=None):
                           child_cap=preset['child_cap'], plane_c_pad=16 if game == PUCT_GAME else 0)
                for k in range(P)]
     eng = engines[0]
+    if args.group_min_batch is not None:
+        eng.sm.set_group_min_batch(args.group_min_batch)
     if args.max_iters or args.max_work:
         for e in engines:
             e.set_step_limits(args.max_iters or 16, args.max_work or (1 << 20))
@@ -816,6 +823,8 @@ def main():
     ap.add_argument('--no-stagger', action='store_true', help='all slots start at the initial state')
     ap.add_argument('--gather-records', type=int, default=20000,
                     help='records in the timed end-of-generation gather (the run\'s own records repeated; 0: only those produced)')
+    ap.add_argument('--group-min-batch', type=int, default=None,
+                    help='propnet: batches of at least this many states use the group kernel (default 1024; -1: never)')
     ap.add_argument('--max-iters', type=int, default=0, help='engine step limit: controller iterations per game')
     ap.add_argument('--max-work', type=int, default=0, help='engine step limit: tree levels descended per game')
     ap.add_argument('--no-graph', action='store_true')

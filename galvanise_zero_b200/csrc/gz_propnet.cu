@@ -492,10 +492,20 @@ pn_wide_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
     }
 }
 
+#include "gz_propnet_group.cuh"
+
 // ------------------------------------------------------------------------------------------------
 struct gz_propnet {
     int device = 0;
     PnParams P{};
+    // group kernel (gz_propnet_group.cuh): chunk / level tables, cluster size, scratch per launching stream
+    GroupTables GT{};
+    void* d_group_tables = nullptr;
+    int group_cl = 1;                    // CTAs per cluster: 1 (narrow levels) or 8 (wide levels)
+    int group_clusters = 0;              // clusters resident at once
+    int64_t group_stride = 0;            // scratch words per cluster
+    int64_t group_min_batch = GROUP_GAMES;
+    std::vector<std::pair<cudaStream_t, uint32_t*>> group_scratch;
     void* d_arena = nullptr;
     int warps_per_cta = 0;
     int grid_max = 0;
@@ -580,6 +590,59 @@ static int configure_launch(gz_propnet* pn, const int32_t* h) {
     GZ_SET_SMEM(MODE_EVAL, 8); GZ_SET_SMEM(MODE_TRANSITION, 8); GZ_SET_SMEM(MODE_PLAYOUT, 8);
 #undef GZ_SET_SMEM
     (void)h;
+    return GZ_OK;
+}
+
+// Chunk offsets and level boundaries of the three programs, for the group kernel (nobody walks the stream there).
+static int build_group_tables(gz_propnet* pn, const int32_t* h) {
+    const PnParams& P = pn->P;
+    const int offs[3] = {D_OFF_PROG_A, D_OFF_PROG_LT, D_OFF_PROG_GL};
+    std::vector<uint32_t> desc[3];
+    std::vector<int> lf[3];
+    int max_level_chunks = 0;
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t* w = (const uint32_t*)(h + h[offs[k]]);
+        size_t p = 0;
+        lf[k].push_back(0);
+        for (int c = 0; c < P.chunks[k]; ++c) {
+            const uint32_t hdr = w[p];
+            const int nl = P.wide ? (int)(hdr & 0xffu) : (int)(hdr & 0xffu);          // literal rows (narrow: even)
+            if (p >= (1u << 28) || nl > 8) { gz_set_error("program outside the group kernel's limits (%d literal rows)", nl); return GZ_ERR_LIMIT; }
+            desc[k].push_back((uint32_t)p | ((uint32_t)nl << 28));
+            p += P.wide ? (33 + 32 * (size_t)nl) : (17 + 32 * (size_t)(nl >> 1));
+            if (hdr & 0x100u) {
+                max_level_chunks = std::max(max_level_chunks, c + 1 - lf[k].back());
+                lf[k].push_back(c + 1);
+            }
+        }
+        if (lf[k].back() != P.chunks[k]) lf[k].push_back(P.chunks[k]);            // (a stream always ends on a level)
+        if (desc[k].empty()) desc[k].push_back(0);
+    }
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    size_t pos = 0, o_desc[3], o_lf[3];
+    for (int k = 0; k < 3; ++k) { o_desc[k] = pos; pos += al(desc[k].size() * 4); o_lf[k] = pos; pos += al(lf[k].size() * 4); }
+    std::vector<uint8_t> buf(pos, 0);
+    for (int k = 0; k < 3; ++k) {
+        memcpy(buf.data() + o_desc[k], desc[k].data(), desc[k].size() * 4);
+        memcpy(buf.data() + o_lf[k], lf[k].data(), lf[k].size() * 4);
+    }
+    GZ_CUDA(cudaMalloc(&pn->d_group_tables, pos));
+    GZ_CUDA(cudaMemcpy(pn->d_group_tables, buf.data(), pos, cudaMemcpyHostToDevice));
+    for (int k = 0; k < 3; ++k) {
+        pn->GT.desc[k] = (const uint32_t*)((const uint8_t*)pn->d_group_tables + o_desc[k]);
+        pn->GT.level_first[k] = (const int*)((const uint8_t*)pn->d_group_tables + o_lf[k]);
+        pn->GT.n_levels[k] = (int)lf[k].size() - 1;
+    }
+    // levels wider than a CTA's 16 warps can use: spread them over a cluster of 8 CTAs
+    pn->group_cl = max_level_chunks > 4 * GROUP_WARPS ? 8 : 1;
+    // Measured (profiles/r02_propnet_games.md): the group kernel pays two L2 round trips per level, the per-tile
+    // kernels a shared-memory access. Programs with few, wide levels (chess_15d: 34 levels of up to 300 chunks,
+    // hexLG13: 19 of up to 1400) run 2.5-3x faster in groups; deep narrow ones (reversi: 175 levels of 4 chunks)
+    // stay with the per-tile kernels unless asked (gz_propnet_set_group_min_batch).
+    pn->group_min_batch = pn->group_cl == 8 ? GROUP_GAMES : -1;
+    pn->group_clusters = pn->group_cl == 8 ? pn->n_sms / 8 : pn->n_sms;
+    const int64_t slices = std::max<int64_t>((int64_t)P.nbw * 32 * GROUP_TILES, (int64_t)GROUP_TILES * GZ_PN_MAX_ROLES * 32);
+    pn->group_stride = (((int64_t)P.val_words * GROUP_TILES + slices + 2 * GROUP_TILES) + 31) & ~(int64_t)31;
     return GZ_OK;
 }
 
@@ -695,6 +758,7 @@ extern "C" int gz_propnet_create(const int32_t* h, int64_t n_words, int device, 
     P.legal_lit32 = P.wide ? (const uint32_t*)(base + o_legal32) : nullptr;
     P.goal_lit32 = P.wide ? (const uint32_t*)(base + o_glit32) : nullptr;
     int rc = configure_launch(pn, h);
+    if (rc == GZ_OK) rc = build_group_tables(pn, h);
     if (rc != GZ_OK) { cudaFree(pn->d_arena); delete pn; return rc; }
     pn->spec = gz_spec_find(fnv1a64(h, (size_t)n_words * 4));
     *out = pn;
@@ -707,6 +771,8 @@ extern "C" void gz_propnet_destroy(gz_propnet* pn) {
     if (pn->d_arena) cudaFree(pn->d_arena);
     if (pn->d_scratch) cudaFree(pn->d_scratch);
     for (auto& ws : pn->wide_scratch) cudaFree(ws.second);
+    for (auto& ws : pn->group_scratch) cudaFree(ws.second);
+    if (pn->d_group_tables) cudaFree(pn->d_group_tables);
     if (pn->host_stream) cudaStreamDestroy(pn->host_stream);
     delete pn;
 }
@@ -714,6 +780,13 @@ extern "C" void gz_propnet_destroy(gz_propnet* pn) {
 extern "C" int gz_propnet_set_spec_min_batch(gz_propnet* pn, int64_t min_batch) {
     if (!pn) { gz_set_error("null propnet"); return GZ_ERR_ARG; }
     pn->spec_min_batch = min_batch;
+    return GZ_OK;
+}
+
+// Batches of at least `min_batch` states (default 1024 = one group) go through the group kernel; < 0 disables it.
+extern "C" int gz_propnet_set_group_min_batch(gz_propnet* pn, int64_t min_batch) {
+    if (!pn) { gz_set_error("null propnet"); return GZ_ERR_ARG; }
+    pn->group_min_batch = min_batch;
     return GZ_OK;
 }
 
@@ -779,6 +852,46 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
             gz_set_error("specialised kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return GZ_ERR_CUDA;
         }
+        return GZ_OK;
+    }
+    if (pn->group_min_batch >= 0 && n >= pn->group_min_batch && !n_dev) {
+        // a thousand games and more: the group kernel (one tile per lane, chunks of a level over a CTA / cluster)
+        static std::mutex gmu;
+        const int64_t n_groups = (n + GROUP_GAMES - 1) / GROUP_GAMES;
+        const int clusters = (int)std::min<int64_t>(n_groups, pn->group_clusters);
+        uint32_t* scratch = own_scratch;
+        if (!scratch) {
+            std::lock_guard<std::mutex> lk(gmu);
+            for (auto& ws : pn->group_scratch) if (ws.first == st) scratch = ws.second;
+            if (!scratch) {
+                const size_t bytes = (size_t)pn->group_clusters * (size_t)pn->group_stride * 4;
+                cudaError_t e = cudaMalloc((void**)&scratch, bytes);
+                if (e != cudaSuccess) { gz_set_error("cudaMalloc of %.1f MB propnet group scratch failed: %s", bytes / 1e6, cudaGetErrorString(e)); return GZ_ERR_CUDA; }
+                pn->group_scratch.emplace_back(st, scratch);
+            }
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(clusters * pn->group_cl));
+        cfg.blockDim = dim3(GROUP_WARPS * 32);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)pn->group_cl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e;
+        const int64_t stride = pn->group_stride;
+        const int* nd = nullptr;
+#define GZ_GROUP_LAUNCH(W, C)                                                                                          \
+        e = cudaLaunchKernelEx(&cfg, pn_group_kernel<MODE, W, C>, pn->P, pn->GT, n, slot0, states_in, moves_in, states_out, \
+                               legal, terminal, goals, moves_out, transitions, seed, step, goals_mode, scratch, stride, nd)
+        if (pn->P.wide) { if (pn->group_cl == 8) GZ_GROUP_LAUNCH(true, 8); else GZ_GROUP_LAUNCH(true, 1); }
+        else { if (pn->group_cl == 8) GZ_GROUP_LAUNCH(false, 8); else GZ_GROUP_LAUNCH(false, 1); }
+#undef GZ_GROUP_LAUNCH
+        if (e != cudaSuccess) { gz_set_error("group kernel launch failed: %s", cudaGetErrorString(e)); return GZ_ERR_CUDA; }
         return GZ_OK;
     }
     if (pn->P.wide) {
@@ -848,7 +961,12 @@ extern "C" int gz_sm_transition(gz_propnet* pn, int64_t n, const uint32_t* d_sta
 // gz_propnet_wide_scratch_bytes() bytes, so that an engine's steps can be captured in a CUDA graph and
 // engines on different streams never share a value array.
 extern "C" int64_t gz_propnet_wide_scratch_bytes(const gz_propnet* pn) {
-    return (pn && pn->P.wide) ? (int64_t)pn->wide_grid * pn->wide_stride * 4 : 0;
+    if (!pn) return 0;
+    // one caller-owned region serves whichever kernel a launch picks: the per-CTA value arrays of the wide
+    // kernel and the per-cluster value arrays of the group kernel
+    const int64_t wide = pn->P.wide ? (int64_t)pn->wide_grid * pn->wide_stride * 4 : 0;
+    const int64_t group = pn->group_min_batch >= 0 ? (int64_t)pn->group_clusters * pn->group_stride * 4 : 0;
+    return std::max(wide, group);
 }
 extern "C" int gz_sm_transition_scratch(gz_propnet* pn, int64_t n, const uint32_t* d_states, const int16_t* d_moves,
                                         uint32_t* d_next, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,

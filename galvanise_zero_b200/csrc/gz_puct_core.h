@@ -1657,15 +1657,16 @@ GZP_RARE void gzp_create_sample(GameView& V, int n) {
     }
     int32_t* p = rec + SR_HEADER;
     const uint32_t* st = NSTATE(n);
-    for (int w = 0; w < E->SW; w++) p[w] = (int32_t)st[w];
+    for (int w = V.lane; w < E->SW; w += GZP_LANES) p[w] = (int32_t)st[w];
     p += E->SW;
     const uint32_t* ps = E->root_prev_state + (int64_t)V.g * E->SW;
-    for (int w = 0; w < E->SW; w++) p[w] = c->root_has_prev ? (int32_t)ps[w] : 0;
+    for (int w = V.lane; w < E->SW; w += GZP_LANES) p[w] = c->root_has_prev ? (int32_t)ps[w] : 0;
     p += E->SW;
-    for (int i = 0; i < nc; i++) {
+    for (int i = V.lane; i < nc; i += GZP_LANES) {
         p[2 * i] = CHILD(c_move, c0 + i);
         reinterpret_cast<float*>(p)[2 * i + 1] = CHILD(c_next, c0 + i);
     }
+    GZP_SYNC();
 }
 
 // SelfPlay::addSamples (selfplay.cpp:244-288): stamp the game's samples and publish them.
@@ -1890,7 +1891,8 @@ GZP_HDN void gzp_request_expand(GameView& V, int parent, int child, int purpose)
     c->req_purpose = purpose;
     uint32_t* xin = E->x_in_state + (int64_t)V.g * E->SW;
     const uint32_t* st = NSTATE(parent);
-    for (int w = 0; w < E->SW; w++) xin[w] = st[w];
+    for (int w = V.lane; w < E->SW; w += GZP_LANES) xin[w] = st[w];      // (hexLG13: 932 words per state)
+    GZP_SYNC();
     const int lead = NODE(n_lead, parent);
     const int ci = NODE(n_child0, parent) + child;
     for (int r = 0; r < E->R; r++)
@@ -1905,7 +1907,8 @@ GZP_HDN void gzp_request_root(GameView& V, const uint32_t* state) {
     c->req_child = -1;
     c->req_purpose = PUR_ROOT;
     uint32_t* xin = E->x_in_state + (int64_t)V.g * E->SW;
-    for (int w = 0; w < E->SW; w++) xin[w] = state[w];
+    for (int w = V.lane; w < E->SW; w += GZP_LANES) xin[w] = state[w];
+    GZP_SYNC();
     for (int r = 0; r < E->R; r++) E->x_moves[(int64_t)V.g * E->R + r] = -1;   // identity transition
 }
 

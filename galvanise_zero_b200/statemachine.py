@@ -60,6 +60,12 @@ class DeviceStateMachine:
         (``cppinterface.py:12-30``); here the ``gz_propnet*`` of the device program."""
         return int(self._h.value)
 
+    def set_group_min_batch(self, n: int):
+        """Batches of at least ``n`` states use the group kernel (1024 games per CTA / cluster, one tile per lane;
+        default 1024; < 0 disables, 0 forces it for every batch)."""
+        self._L.gz_propnet_set_group_min_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        _lib.check(self._L.gz_propnet_set_group_min_batch(self._h, int(n)))
+
     def set_spec_min_batch(self, n: int):
         """Batches of at least ``n`` states use the game-specialised kernel (default 2^18; < 0 disables)."""
         self._L.gz_propnet_set_spec_min_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64]

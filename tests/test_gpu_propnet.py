@@ -146,6 +146,62 @@ def test_specialised_kernel_bit_exact(game, n):
         assert np.array_equal(_np(a), b)
 
 
+@pytest.mark.parametrize('game,n,steps', [('breakthrough', 1100, 60), ('breakthroughSmall', 2048, 40), ('reversi', 1500, 66),
+                                          ('connect6', 1024, 20), ('amazons_10x10', 1030, 24), ('chess_15d', 1100, 24),
+                                          ('hexLG13', 1024, 8), ('reversi', 5, 20), ('chess_15d', 37, 12)])
+def test_group_kernel_bit_exact(game, n, steps):
+    """The group kernel (gz_propnet_group.cuh: 1024 games per CTA or cluster, one tile per lane) on full and
+    ragged groups, forced also for tiny batches: playout plies (legal masks, moves, next states, terminal, goals,
+    transition count) against the C oracle; then transition / eval entry points and the terminal-only goals mode
+    against the per-tile kernels on the same positions."""
+    dev = _sm(game)
+    dev.set_group_min_batch(0)
+    dev.set_spec_min_batch(-1)
+    assert dev.launch_info is not None
+    ref = RefStateMachine(tables.blob_by_name(game))
+    seed = 0x6709 + n
+    s_r = np.zeros((n, ref.state_words), dtype=np.uint32)
+    l_r = np.zeros((n, ref.legal_words), dtype=np.uint32)
+    t_r = np.ones(n, dtype=np.uint8)
+    g_r = np.zeros((n, ref.n_roles), dtype=np.uint8)
+    m_r = np.zeros((n, ref.n_roles), dtype=np.int16)
+    s_d = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
+    l_d, t_d, g_d = dev.alloc_views(n)
+    t_d.fill_(1)
+    m_d = torch.zeros((n, dev.n_roles), dtype=torch.int16, device=dev.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev.device)
+    total = 0
+    for step in range(steps):
+        prev_d = s_d.clone()
+        total += ref.playout_step(3, seed, step, s_r, l_r, t_r, g_r, m_r)
+        dev.playout_step(s_d, l_d, t_d, g_d, seed, step, slot0=3, moves_out=m_d, counter=cnt)
+        assert np.array_equal(_np(m_d), m_r), (game, step, 'moves')
+        assert np.array_equal(_np(s_d), s_r), (game, step, 'states')
+        assert np.array_equal(_np(l_d), l_r), (game, step, 'legal')
+        assert np.array_equal(_np(t_d), t_r), (game, step, 'terminal')
+        assert np.array_equal(_np(g_d), g_r), (game, step, 'goals')
+    assert int(cnt.item()) == total
+    # transition with given moves (rows restarted by the last ply: identity move -1) and eval: group vs tile kernels
+    mv = m_d.clone()
+    out_g = dev.transition(prev_d, mv)
+    ev_g = dev.eval(s_d)
+    dev.set_group_min_batch(-1)
+    out_t = dev.transition(prev_d, mv)
+    ev_t = dev.eval(s_d)
+    for a, b in zip(out_g + ev_g, out_t + ev_t):
+        assert torch.equal(a, b)
+    live = (m_r[:, 0] >= 0)
+    assert np.array_equal(_np(out_g[0])[live], s_r[live])
+    # terminal-only goals
+    dev2 = _sm(game, goals_mode=gzlib.GOALS_TERMINAL_ONLY)
+    dev2.set_group_min_batch(0)
+    dev2.set_spec_min_batch(-1)
+    lg, tm, gl = dev2.eval(s_d)
+    gl = _np(gl)
+    assert np.array_equal(_np(tm), t_r) and np.array_equal(_np(lg), l_r)
+    assert np.array_equal(gl[t_r == 1], g_r[t_r == 1]) and (gl[t_r == 0] == 255).all()
+
+
 @pytest.mark.parametrize('game', ['breakthrough', 'reversi'])
 def test_transition_eval_and_host_api(game):
     dev = _sm(game)
