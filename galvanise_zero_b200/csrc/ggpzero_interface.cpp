@@ -277,13 +277,14 @@ static PyObject* supervisor_clear_unique_states(PySupervisor* self, PyObject*) {
 }
 static PyObject* supervisor_set_num_workers(PySupervisor*, PyObject*) { Py_RETURN_NONE; }
 static PyObject* supervisor_totals(PySupervisor* self, PyObject*) {
-    double t[25];
+    double t[26];
     if (gz_supervisor_totals(self->s, t) != GZ_OK) return fail();
-    static const char* K[25] = {"evals", "moves", "games", "samples", "playouts", "errors", "halted", "first_error", "max_nodes",
+    static const char* K[26] = {"evals", "moves", "games", "samples", "playouts", "errors", "halted", "first_error", "max_nodes",
         "max_children", "dupes", "no_samples", "fp_resign0", "fp_resign1", "early_run_to_ends", "resigns", "aborts",
-        "waiting_eval", "ready", "select_nodes", "select_children", "new_children", "depth_sum", "dropped_samples", "error_restarts"};
+        "waiting_eval", "ready", "select_nodes", "select_children", "new_children", "depth_sum", "dropped_samples", "error_restarts",
+        "transpositions"};
     PyObject* d = PyDict_New();
-    for (int i = 0; i < 25; i++) { PyObject* v = PyFloat_FromDouble(t[i]); PyDict_SetItemString(d, K[i], v); Py_DECREF(v); }
+    for (int i = 0; i < 26; i++) { PyObject* v = PyFloat_FromDouble(t[i]); PyDict_SetItemString(d, K[i], v); Py_DECREF(v); }
     return d;
 }
 static PyMethodDef supervisor_methods[] = {

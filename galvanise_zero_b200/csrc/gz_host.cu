@@ -199,16 +199,16 @@ extern "C" int gz_supervisor_clear_unique_states(gz_supervisor* s) {
 }
 
 // Sums (max_* / first_error: maxima) of gz_puct_totals over the managers.
-extern "C" int gz_supervisor_totals(gz_supervisor* s, double* h_out25) {
-    if (!s || !h_out25) { gz_set_error("null argument"); return GZ_ERR_ARG; }
-    for (int i = 0; i < 25; i++) h_out25[i] = 0;
+extern "C" int gz_supervisor_totals(gz_supervisor* s, double* h_out26) {
+    if (!s || !h_out26) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    for (int i = 0; i < 26; i++) h_out26[i] = 0;
     for (auto& m : s->man) {
-        double t[25];
+        double t[26];
         int rc = gz_puct_totals(m.eng, t, (void*)m.stream);
         if (rc != GZ_OK) return rc;
-        for (int i = 0; i < 25; i++) {
-            if (i == 7 || i == 8 || i == 9) h_out25[i] = std::max(h_out25[i], t[i]);
-            else h_out25[i] += t[i];
+        for (int i = 0; i < 26; i++) {
+            if (i == 7 || i == 8 || i == 9) h_out26[i] = std::max(h_out26[i], t[i]);
+            else h_out26[i] += t[i];
         }
     }
     return GZ_OK;

@@ -173,6 +173,7 @@ struct PuctTotals {
     int waiting_eval;
     unsigned long long sel_nodes, sel_children, new_children;
     unsigned long long depth_sum;      // sum over games of the current root's game depth (mean ply = / G)
+    unsigned long long transpositions; // expansions that attached an existing node (lookup_transpositions)
     int error_restarts;                // games abandoned at a per-game capacity limit (their slot started a new game)
 };
 
@@ -202,6 +203,7 @@ __global__ void puct_totals_kernel(const __grid_constant__ PuctEngine E, PuctTot
     atomicAdd(&out->new_children, (unsigned long long)c.total_new_children);
     atomicAdd(&out->depth_sum, (unsigned long long)(c.game_depth > 0 ? c.game_depth : 0));
     atomicAdd(&out->error_restarts, c.error_restarts);
+    atomicAdd(&out->transpositions, (unsigned long long)c.total_transpositions);
 }
 
 // ---- synthetic network (parity / bench utility): same function as oracle/ref_harness.cpp
@@ -317,8 +319,9 @@ extern "C" int gz_puct_set_config(gz_puct* h, const double* sp_conf, const doubl
     fill_sp_conf(h->E.conf, sp_conf);
     fill_puct_conf(h->E.conf.puct, puct_conf);
     fill_puct_conf(h->E.conf.run_to_end, rte_conf);
-    if (h->E.conf.puct.lookup_transpositions || h->E.conf.run_to_end.lookup_transpositions) {
-        gz_set_error("lookup_transpositions is not supported by the device engine");
+    if ((h->E.conf.puct.lookup_transpositions || h->E.conf.run_to_end.lookup_transpositions) && h->d_arena && !h->E.tt_cap) {
+        // the table is sized and allocated with the trees
+        gz_set_error("lookup_transpositions must be set when the engine is created");
         return GZ_ERR_LIMIT;
     }
     return GZ_OK;
@@ -378,6 +381,12 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
         if (tr->policy_sizes[r] != E.role_sizes[r]) { gz_set_error("policy size of role %d: %d != %d actions", r, tr->policy_sizes[r], E.role_sizes[r]); delete h; return GZ_ERR_ARG; }
     int rc = gz_puct_set_config(h, sp_conf, puct_conf, rte_conf);
     if (rc != GZ_OK) { delete h; return rc; }
+    E.tt_cap = 0;
+    if (E.conf.puct.lookup_transpositions || E.conf.run_to_end.lookup_transpositions) {
+        // transposition table (evaluator.cpp:52,144-173): load factor <= 1/2 of the node arena
+        E.tt_cap = 32;
+        while (E.tt_cap < 2 * E.NCAP) E.tt_cap *= 2;
+    }
     GZ_CUDA(cudaSetDevice(h->device));
     h->arena_bytes = gzp_layout(&E, nullptr);
     cudaError_t e = cudaMalloc(&h->d_arena, h->arena_bytes);
@@ -834,8 +843,8 @@ extern "C" int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes) {
 
 // totals: [evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children,
 //          dupes, no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval,
-//          ready_count, select_nodes, select_children, new_children, depth_sum, dropped_samples, error_restarts]
-//         (25 doubles)
+//          ready_count, select_nodes, select_children, new_children, depth_sum, dropped_samples, error_restarts,
+//          transpositions] (26 doubles)
 extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     if (!h || !out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
@@ -859,6 +868,7 @@ extern "C" int gz_puct_totals(gz_puct* h, double* out, void* stream) {
     out[22] = (double)t.depth_sum;
     out[23] = (double)ready[1];          // finished samples dropped because the ready buffer was full
     out[24] = t.error_restarts;
+    out[25] = (double)t.transpositions;
     return GZ_OK;
 }
 

@@ -21,8 +21,10 @@
 // expression so that, with identical network outputs, visit counts are identical.
 //
 // Scope notes: one outstanding evaluation per tree (PuctConfig.batch_size == 1, the self-play
-// setting, templates.py:76); transposition lookup is not implemented (off in self-play,
-// confs.py:72-73); games in which two roles have a real choice in the same state are rejected.
+// setting, templates.py:76); games in which two roles have a real choice in the same state are rejected.
+// With PuctConfig.lookup_transpositions the trees are DAGs (a node reached by several move orders is shared,
+// evaluator.cpp:216-239): the copy of a child node's statistics kept in its parent's child record (GzpChild)
+// would go stale in the parents a backup does not pass through, so select then reads the child nodes themselves.
 #ifndef GZ_PUCT_CORE_H
 #define GZ_PUCT_CORE_H
 
@@ -127,6 +129,7 @@ struct GameCtl {
     // traffic accounting for the roofline: nodes passed through by select, children
     // scanned there, children written by node creation
     uint64_t total_sel_nodes, total_sel_children, total_new_children;
+    uint64_t total_transpositions;      // expansions that attached an existing node (stats.num_transpositions_attached)
     // per-manager style stats (selfplaymanager.h:46-72)
     int32_t saw_dupes, no_samples_taken, false_positive_resigns0, false_positive_resigns1,
         number_early_run_to_ends, number_resigns, number_aborts_game_length;
@@ -208,6 +211,11 @@ struct PuctEngine {
     int32_t* uniq_counts;
     int uniq_cap;             // power of two
     const uint32_t* uniq_mask;  // [SW] createHashMask (gdltransformer.cpp:54-63)
+    // transposition table (PuctConfig.lookup_transpositions, evaluator.cpp:144-173): per game an open-addressing
+    // map masked state hash -> node index; tt_cap == 0: off
+    unsigned long long* tt_keys;    // [G * tt_cap]
+    int32_t* tt_node;               // [G * tt_cap]
+    int tt_cap;                     // power of two >= 2 * NCAP
     const uint32_t* init_state; // [SW]
     uint32_t* start_state;      // [G*SW] per-slot start position of the slot's NEXT game when ctl.start_pending is set
     SpConf conf;
@@ -477,6 +485,14 @@ GZP_RARE void gzp_cache_fill(GameView& V, int n) {
         C.visits[i] = k.c_to >= 0 ? k.c_visits : 0u;
         C.flags[i] = k.c_to >= 0 ? (int)k.c_flags : 0;
         C.inflight[i] = k.c_to >= 0 ? (int)k.c_inflight : 0;
+        if (V.E->tt_cap && k.c_to >= 0) {          // shared nodes: the record's copy may be stale, read the node
+            const int lead = NODE(n_lead, n);
+            const GzpNode& t = V.E->nodes[V.nb + k.c_to];
+            C.score[i] = t.score[lead < 0 ? 0 : lead];
+            C.visits[i] = t.n_visits;
+            C.flags[i] = t.n_flags & NF_FINALISED;
+            C.inflight[i] = t.n_inflight;
+        }
     }
     GZP_SYNC();
 }
@@ -844,7 +860,7 @@ __device__ __forceinline__ int gzp_warp_top(bool pred, unsigned k1, float k2, in
     return __ffs(top) - 1;
 }
 
-__device__ __forceinline__ GzpKid gzp_warp_load_kid(const GameView& V, int c0, int nc) {
+__device__ __forceinline__ GzpKid gzp_warp_load_kid(const GameView& V, int c0, int nc, int lead) {
     GzpKid K;
     K.act = V.lane < nc;
     GzpChild k;
@@ -860,6 +876,13 @@ __device__ __forceinline__ GzpKid gzp_warp_load_kid(const GameView& V, int c0, i
     K.visits = K.expanded ? k.c_visits : 0u;
     K.flags = K.expanded ? (int)k.c_flags : 0;
     K.inflight = K.expanded ? (int)k.c_inflight : 0;
+    if (V.E->tt_cap && K.expanded) {               // shared nodes: the record's copy may be stale, read the node
+        const GzpNode& t = V.E->nodes[V.nb + k.c_to];
+        K.score = t.score[lead < 0 ? 0 : lead];
+        K.visits = t.n_visits;
+        K.flags = t.n_flags & NF_FINALISED;
+        K.inflight = t.n_inflight;
+    }
     K.fin = K.expanded && (K.flags & NF_FINALISED) != 0;
     return K;
 }
@@ -1220,7 +1243,7 @@ GZP_HDN int gzp_select_child(GameView& V, int n, const GzpNode& nd, GzpSelInfo* 
     if (nc <= 32 && V.ord &&
         !(depth == 0 && cf.dirichlet_noise_pct >= 0 && !(nd.n_flags & NF_NOISE_SET) &&
           !(nd.score[lead < 0 ? 0 : lead] > 0.95))) {
-        const GzpKid K = preloaded_kid ? *preloaded_kid : gzp_warp_load_kid(V, c0, nc);
+        const GzpKid K = preloaded_kid ? *preloaded_kid : gzp_warp_load_kid(V, c0, nc, lead);
         int to = -1;
         const int pick = gzp_warp_select(V, K, nc, node_visits, node_finals[lead < 0 ? 0 : lead], puct_c, depth, &to);
         if (pick != GZP_WARP_PUNT) {
@@ -1486,7 +1509,7 @@ GZP_HDN bool gzp_converged(GameView& V, int count, const GzpNode& nd, GzpKid* ki
     if (nc < 2) return true;
 #ifdef __CUDA_ARCH__
     if (nc <= 32 && V.ord) {
-        const GzpKid K = gzp_warp_load_kid(V, nd.n_child0, nc);
+        const GzpKid K = gzp_warp_load_kid(V, nd.n_child0, nc, nd.n_lead);
         if (kid) { *kid = K; *have_kid = true; }
         const int r = gzp_warp_converged(V, K, nc, count);
         if (r != GZP_WARP_PUNT) return r != 0;
@@ -1634,6 +1657,71 @@ GZP_HDN void gzp_uniq_add(const PuctEngine* E, const uint32_t* st, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Transposition table (evaluator.cpp:144-173): keyed by the state under the transformer's hash mask; a hit needs
+// the same game depth (the reference refuses others, they could close a cycle). Entries are added when a node is
+// created (first node with a state wins, as std::unordered_map::emplace) and the table is rebuilt from the kept
+// nodes when the tree is re-rooted (the reference erases the released nodes' keys; the two differ only when the
+// same masked state sits at two depths of one tree).
+GZP_HD bool gzp_masked_equal(const PuctEngine* E, const uint32_t* a, const uint32_t* b) {
+    for (int w = 0; w < E->SW; w++)
+        if ((a[w] ^ b[w]) & E->uniq_mask[w]) return false;
+    return true;
+}
+GZP_HDN void gzp_tt_clear(GameView& V) {
+    const PuctEngine* E = V.E;
+    if (!E->tt_cap) return;
+    GZP_SYNC();
+    for (int i = V.lane; i < E->tt_cap; i += GZP_LANES) {
+        E->tt_keys[(int64_t)V.g * E->tt_cap + i] = 0ULL;
+        E->tt_node[(int64_t)V.g * E->tt_cap + i] = 0x7fffffff;
+    }
+    GZP_SYNC();
+}
+// single-threaded insert (node creation); `atomic` for the parallel rebuild after re-rooting
+GZP_HDN void gzp_tt_insert(const PuctEngine* E, int g, int64_t nb, int node, bool atomic) {
+    if (!E->tt_cap) return;
+    uint64_t key = gzp_state_hash(E, E->n_state + (nb + node) * E->SW);
+    if (!key) key = 1;                              // 0 marks an empty slot
+    unsigned long long* keys = E->tt_keys + (int64_t)g * E->tt_cap;
+    int32_t* nodes = E->tt_node + (int64_t)g * E->tt_cap;
+    uint32_t pos = (uint32_t)(key & (uint64_t)(E->tt_cap - 1));
+    for (int probe = 0; probe < E->tt_cap; probe++) {
+#ifdef __CUDA_ARCH__
+        if (atomic) {
+            const unsigned long long prev = atomicCAS(&keys[pos], 0ULL, (unsigned long long)key);
+            if (prev == 0ULL || prev == key) { atomicMin(&nodes[pos], node); return; }
+        } else
+#endif
+        {
+            (void)atomic;
+            if (keys[pos] == 0ULL) { keys[pos] = key; nodes[pos] = node; return; }
+            if (keys[pos] == key) { if (node < nodes[pos]) nodes[pos] = node; return; }
+        }
+        pos = (pos + 1) & (uint32_t)(E->tt_cap - 1);
+    }
+}
+// lookupNode: the node holding `state` (masked) at `depth`, or -1
+GZP_HDN int gzp_tt_find(const GameView& V, const uint32_t* state, int depth) {
+    const PuctEngine* E = V.E;
+    if (!E->tt_cap) return -1;
+    uint64_t key = gzp_state_hash(E, state);
+    if (!key) key = 1;
+    const unsigned long long* keys = E->tt_keys + (int64_t)V.g * E->tt_cap;
+    const int32_t* nodes = E->tt_node + (int64_t)V.g * E->tt_cap;
+    uint32_t pos = (uint32_t)(key & (uint64_t)(E->tt_cap - 1));
+    for (int probe = 0; probe < E->tt_cap; probe++) {
+        if (keys[pos] == 0ULL) return -1;
+        if (keys[pos] == key) {
+            const int n = nodes[pos];
+            if (n < V.c->n_nodes && gzp_masked_equal(E, state, NSTATE(n)))
+                return NODE(n_depth, n) == depth ? n : -1;
+        }
+        pos = (pos + 1) & (uint32_t)(E->tt_cap - 1);
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // SelfPlayManager::createSample (selfplaymanager.cpp:72-119) into the game's pending list.
 GZP_RARE void gzp_create_sample(GameView& V, int n) {
     const PuctEngine* E = V.E;
@@ -1766,16 +1854,41 @@ GZP_HDN void gzp_reroot_compact(GameView& V, int new_root, int tid, int T, Group
         const uint32_t* st = E->n_state + (nb + c->root) * E->SW;
         for (int w = tid; w < E->SW; w += T) ps[w] = st[w];
     }
+    // ---- pass 0 (transposition tables only): the tree is a DAG, a shared node is kept when ANY kept node links to
+    // it (the reference's ref counts, evaluator.cpp:113-140) and a linking parent may have been created after the
+    // node it links to. Marks spread along the child links, one depth level per round at worst.
+    const bool dag = E->tt_cap != 0;
+    if (dag) {
+        for (int i = tid; i < N; i += T) E->n_newidx[nb + i] = i == r ? 0 : -1;
+        grp.sync();
+        for (;;) {
+            int changed = 0;
+            for (int k = tid; k < NC; k += T) {
+                const int to = E->children[cb + k].c_to;
+                if (to >= 0 && E->n_newidx[nb + to] < 0 && E->n_newidx[nb + E->c_owner[cb + k]] >= 0) {
+                    E->n_newidx[nb + to] = 0;
+                    changed = 1;
+                }
+            }
+            int e0, e1, total, t1;
+            grp.scan2(changed, 0, e0, e1, total, t1);
+            if (!total) break;
+        }
+    }
     // ---- pass 1: reachability + new indices, chunk by chunk in index order
     int node_base = 0, child_base = 0;
     for (int b = 0; b < N; b += T) {
         const int i = b + tid;
         int reach = 0, nch = 0;
         if (i < N) {
-            int q = i;
-            while (q > r && q >= b) q = E->nodes[nb + q].n_parent;
-            if (q == r) reach = 1;
-            else if (q > r) reach = E->n_newidx[nb + q] >= 0;     // q < b: decided by an earlier chunk
+            if (dag) {
+                reach = E->n_newidx[nb + i] >= 0;
+            } else {
+                int q = i;
+                while (q > r && q >= b) q = E->nodes[nb + q].n_parent;
+                if (q == r) reach = 1;
+                else if (q > r) reach = E->n_newidx[nb + q] >= 0;     // q < b: decided by an earlier chunk
+            }
             if (reach) nch = E->nodes[nb + i].n_nchild;
         }
         int en, ec, tn, tc;
@@ -1821,7 +1934,7 @@ GZP_HDN void gzp_reroot_compact(GameView& V, int new_root, int tid, int T, Group
             if (dst >= 0) {
                 rec = E->nodes[nb + i];
                 const int p0 = rec.n_parent;
-                rec.n_parent = (i == r || p0 < 0) ? -1 : E->n_newidx[nb + p0];
+                rec.n_parent = (i == r || p0 < 0) ? -1 : E->n_newidx[nb + p0];    // a shared node's creator may be gone: -1
                 rec.n_child0 = rec.n_nchild == 0 ? -1 : E->n_newc0[nb + i];
                 for (int k = 0; k < GZP_MAX_ROLES; k++) ot[k] = E->n_other[(nb + i) * GZP_MAX_ROLES + k];
             }
@@ -1846,6 +1959,16 @@ GZP_HDN void gzp_reroot_compact(GameView& V, int new_root, int tid, int T, Group
             if (dst >= 0) for (int w = 0; w < nw; w++) E->n_state[(nb + dst) * E->SW + w0 + w] = tmp[w];
             grp.sync();
         }
+    }
+    if (dag) {
+        // the table is rebuilt from the kept nodes (the reference erases the released nodes' keys one by one)
+        for (int i = tid; i < E->tt_cap; i += T) {
+            E->tt_keys[(int64_t)V.g * E->tt_cap + i] = 0ULL;
+            E->tt_node[(int64_t)V.g * E->tt_cap + i] = 0x7fffffff;
+        }
+        grp.sync();
+        for (int i = tid; i < node_base; i += T) gzp_tt_insert(E, V.g, nb, i, true);
+        grp.sync();
     }
     if (tid == 0) {
         c->root = 0;
@@ -1990,6 +2113,7 @@ GZP_RARE void gzp_begin_game(GameView& V) {
     c->in_run_to_end = 0;
     c->in_playout = 0;
     c->conf_sel = 0;
+    gzp_tt_clear(V);
     if (c->start_pending) {
         // staggered start (measurement aid): this slot's game begins from a given position, at depth 0 like
         // the reference's establishRoot(initial_state) would with that state handed in as the initial one
@@ -2241,6 +2365,7 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
             c->cmd = CMD_NONE;
             if (cmd == CMD_RESET) {
                 c->n_nodes = 0; c->n_children = 0; c->root = -1; c->root_has_prev = 0;
+                gzp_tt_clear(V);
                 c->game_depth = c->cmd_arg;
                 c->in_run_to_end = 0; c->in_playout = 0; c->conf_sel = 0;
                 // root state was placed in x_in_state by the host
@@ -2281,6 +2406,20 @@ GZP_HDN void gzp_step_post(GameView& V) {
     if (c->phase == PH_HALT || c->req == REQ_NONE || c->req == REQ_REROOT) return;
     const int parent = c->req == REQ_ROOT ? -1 : c->req_parent;
     const int depth = parent < 0 ? c->game_depth : NODE(n_depth, parent) + 1;
+    if (parent >= 0 && E->tt_cap && gzp_conf(V).lookup_transpositions) {
+        // expandChild (evaluator.cpp:216-239): the state is already in the tree at this depth -> share its node;
+        // the playout then ends (or walks on through a forced move) without a new evaluation
+        const int found = gzp_tt_find(V, E->x_state + (int64_t)V.g * E->SW, depth);
+        if (found >= 0) {
+            c->req = REQ_NONE;
+            CHILD(c_to, NODE(n_child0, parent) + c->req_child) = found;
+            gzp_child_refresh(V, parent, c->req_child, found);
+            c->new_node = found;
+            c->total_transpositions++;
+            c->resume = 1;
+            return;
+        }
+    }
     const int N = gzp_create_node(V, parent, depth);
     c->req = REQ_NONE;
     if (N < 0) {
@@ -2292,6 +2431,7 @@ GZP_HDN void gzp_step_post(GameView& V) {
         gzp_child_refresh(V, parent, c->req_child, N);
     }
     c->new_node = N;
+    if (gzp_conf(V).lookup_transpositions) gzp_tt_insert(E, V.g, V.nb, N, false);
     c->total_new_children += (uint64_t)NODE(n_nchild, N);
     const bool needs_eval = !gzp_is_finalised(V, N) && NODE(n_nchild, N) > 1;
     if (needs_eval) {

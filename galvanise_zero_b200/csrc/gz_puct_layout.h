@@ -9,7 +9,7 @@
 #include "gz_puct_core.h"
 
 // Assigns all array pointers of E inside [base, base+return). With base == nullptr only the size
-// is computed. Dimensions (G, R, SW, LW, NCAP, CCAP, MAXD, MAXPEND, srec, READYCAP, uniq_cap,
+// is computed. Dimensions (G, R, SW, LW, NCAP, CCAP, MAXD, MAXPEND, srec, READYCAP, uniq_cap, tt_cap,
 // n_rewards, policy_stride) must be set beforehand.
 static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     size_t pos = 0;
@@ -49,6 +49,8 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     E->uniq_mask = (const uint32_t*)take((size_t)E->SW * 4);
     E->init_state = (const uint32_t*)take((size_t)E->SW * 4);
     E->start_state = (uint32_t*)take(G * E->SW * 4);
+    E->tt_keys = (unsigned long long*)take(G * (size_t)E->tt_cap * 8);      // tt_cap == 0: no transposition table
+    E->tt_node = (int32_t*)take(G * (size_t)E->tt_cap * 4);
     return pos;
 }
 

@@ -33,7 +33,7 @@ TOTAL_KEYS = ['evals', 'moves', 'games', 'samples', 'playouts', 'errors', 'halte
               'max_nodes', 'max_children', 'dupes', 'no_samples', 'fp_resign0', 'fp_resign1',
               'early_run_to_ends', 'resigns', 'aborts', 'waiting_eval', 'ready',
               'select_nodes', 'select_children', 'new_children', 'depth_sum', 'dropped_samples',
-              'error_restarts']
+              'error_restarts', 'transpositions']
 # sample record header (csrc/gz_puct_core.h SR_*)
 SR_DEPTH, SR_GAME_LENGTH, SR_SLOT, SR_MATCH, SR_HAS_RESIGNED, SR_RESIGN_FP, SR_START_DEPTH, SR_VISITS, \
     SR_LEAD, SR_N_PREV, SR_N_CHILDREN = range(1, 12)

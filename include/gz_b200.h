@@ -204,12 +204,13 @@ int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream);
  * other's batch (the reference's two managers per worker, src/cpp/supervisor.cpp:79-99). */
 int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* const* h_arrays, int n_arrays, void* stream);
 int gz_puct_host_poll_wait(gz_puct* h, const float** h_planes);
-/* h_out25: evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children, dupes,
+/* h_out26: evals, moves, games, samples, playouts, errors, halted, first_error, max_nodes, max_children, dupes,
  * no_samples, fp_resign0, fp_resign1, early_run_to_ends, resigns, aborts, waiting_eval, ready, select_nodes,
  * select_children, new_children, depth_sum (sum over slots of the current root's game depth), dropped_samples
  * (finished samples lost because the ready buffer was full: fetch more often), error_restarts (games abandoned at a
- * per-game capacity limit; their slot started a new game). */
-int gz_puct_totals(gz_puct* h, double* h_out25, void* stream);
+ * per-game capacity limit; their slot started a new game), transpositions (expansions that attached an existing node:
+ * PuctConfig.lookup_transpositions, stats.num_transpositions_attached, src/cpp/puct/evaluator.cpp:224-226). */
+int gz_puct_totals(gz_puct* h, double* h_out26, void* stream);
 /* Measurement aid: the next game of every slot starts from d_states[g] (device, [G][state_words], non-terminal
  * positions) at game depth 0 instead of the initial state — what handing SelfPlay another `initial_state`
  * (src/cpp/selfplaymanager.cpp:140, selfplay.cpp:313) does in the reference. Later games start normally. */
@@ -261,7 +262,7 @@ void* gz_supervisor_stream(gz_supervisor* s, int manager);
 int gz_supervisor_poll(gz_supervisor* s, int n_pred, const float* const* h_arrays, int n_arrays, const float** h_planes);
 int64_t gz_supervisor_fetch_samples(gz_supervisor* s, int32_t* h_out, int64_t cap, int32_t* h_manager);
 int gz_supervisor_clear_unique_states(gz_supervisor* s);
-int gz_supervisor_totals(gz_supervisor* s, double* h_out25);
+int gz_supervisor_totals(gz_supervisor* s, double* h_out26);
 
 typedef struct gz_player gz_player;
 int gz_player_create(gz_propnet* pn, gz_transformer* tr, const double* puct_conf, int device, uint64_t seed, int node_cap,

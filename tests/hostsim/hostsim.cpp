@@ -103,12 +103,17 @@ extern "C" void* hs_create(const int32_t* blob, int64_t n_words, int G, int mode
     E.uniq_cap = 1 << 16;
     E.max_iters_per_step = 64;
     E.max_work_per_step = 1 << 20;
-    const size_t bytes = gzp_layout(&E, nullptr);
-    H->arena.assign(bytes, 0);
-    gzp_layout(&E, H->arena.data());
     fill_sp(E.conf, sp_conf);
     fill_conf(E.conf.puct, puct_conf);
     fill_conf(E.conf.run_to_end, rte_conf);
+    E.tt_cap = 0;
+    if (E.conf.puct.lookup_transpositions || E.conf.run_to_end.lookup_transpositions) {
+        E.tt_cap = 32;
+        while (E.tt_cap < 2 * E.NCAP) E.tt_cap *= 2;
+    }
+    const size_t bytes = gzp_layout(&E, nullptr);
+    H->arena.assign(bytes, 0);
+    gzp_layout(&E, H->arena.data());
     E.seed = rng_seed;
     // init state and hash mask (every base the transformer looks at, gdltransformer.cpp:54-63)
     pnref_initial_state(H->sm, (uint32_t*)E.init_state);
@@ -245,5 +250,6 @@ extern "C" int hs_root_children(void* h, int g, int max_children, int* moves, in
 
 extern "C" unsigned long long hs_ready_count(void* h) { return *((HostSim*)h)->E.ready_count; }
 extern "C" const int32_t* hs_ready(void* h) { return ((HostSim*)h)->E.ready; }
+extern "C" unsigned long long hs_transpositions(void* h, int g) { return ((HostSim*)h)->E.ctl[g].total_transpositions; }
 extern "C" int hs_srec(void* h) { return ((HostSim*)h)->E.srec; }
 extern "C" int hs_sizeof_ctl() { return (int)sizeof(GameCtl); }

@@ -30,6 +30,8 @@ def lib():
         L.hs_ready.restype = ctypes.POINTER(ctypes.c_int32)
         L.hs_ready.argtypes = [vp]
         L.hs_srec.argtypes = [vp]
+        L.hs_transpositions.restype = ctypes.c_ulonglong
+        L.hs_transpositions.argtypes = [vp, ci]
         L.hs_ctl.restype = vp
         L.hs_ctl.argtypes = [vp, ci]
         _L = L
@@ -94,6 +96,9 @@ class HostSim:
             if rc != 1:
                 break
         return out
+
+    def transpositions(self, g=0):
+        return int(self.L.hs_transpositions(self.h, g))
 
     def step(self, n=1):
         for _ in range(n):

@@ -80,13 +80,44 @@ def test_device_search_matches_reference(game, evals, moves, noise):
     assert same_choice >= 0.99 * len(ref)
 
 
+@pytest.mark.parametrize('game,evals,moves', [('breakthroughSmall', 400, 20), ('reversi', 600, 10), ('connect6', 150, 3)])
+def test_device_search_with_transposition_lookup_matches_reference(game, evals, moves):
+    """PuctConfig.lookup_transpositions (evaluator.cpp:144-173,216-239): per-game device hash map, shared nodes,
+    DAG-aware re-rooting in puct_reroot_kernel (parallel mark rounds + parallel table rebuild)."""
+    from galvanise_zero_b200.engine import PuctEngine
+    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits', lookup_transpositions=True)
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    eng = PuctEngine(game, sp, n_games=1, mode=1, node_cap=8192, child_cap=1 << 18, plane_dtype=torch.float32)
+    ref = gzref.RefEngine(tables.blob_by_name(game), eng.c_transformer).search(conf, evals, n_moves=moves,
+                                                                               max_children=4096)
+    mine = _device_search(eng, evals, moves)
+    assert len(mine) == len(ref)
+    for a, b in zip(ref, mine):
+        assert np.array_equal(a['moves'], b['moves'])
+        assert np.array_equal(a['traversals'], b['traversals'])
+        assert a['choice'] == b['choice']
+    if game != 'connect6':
+        assert eng.totals()['transpositions'] > 10
+
+
+def test_device_selfplay_with_transposition_lookup_matches_reference():
+    _device_selfplay('breakthroughSmall', 8, 40, 150, False, True, transpositions=True)
+
+
 @pytest.mark.parametrize('game,G,evals,target,noise,exact', [
     ('breakthroughSmall', 8, 40, 150, False, False),
     ('reversi', 4, 50, 60, False, True),
     ('reversi', 4, 50, 60, True, True)])       # the benchmarked template: noise 0.25 / 0.15 (templates.py:73-129)
 def test_device_selfplay_samples_match_reference(game, G, evals, target, noise, exact):
+    _device_selfplay(game, G, evals, target, noise, exact)
+
+
+def _device_selfplay(game, G, evals, target, noise, exact, transpositions=False):
     from galvanise_zero_b200.engine import PuctEngine
     sp = confs.selfplay_config_template(evals_per_move=evals)
+    sp.puct_config.lookup_transpositions = transpositions
+    sp.run_to_end_puct_config.lookup_transpositions = transpositions
     if not noise:
         sp.puct_config.dirichlet_noise_pct = -1
         sp.run_to_end_puct_config.dirichlet_noise_pct = -1

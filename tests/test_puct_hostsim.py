@@ -73,6 +73,32 @@ def test_selfplay_samples_match_with_dirichlet_noise():
     _selfplay_samples('reversi', 4, 50, 60, noise=True)
 
 
+@pytest.mark.parametrize('game,evals,moves', [('breakthroughSmall', 400, 20), ('reversi', 600, 10), ('connect6', 200, 4),
+                                              ('amazons_10x10', 150, 3)])
+def test_transposition_lookup_matches_reference(game, evals, moves):
+    """PuctConfig.lookup_transpositions (evaluator.cpp:144-173,216-239): a state reached by two move orders shares
+    one node (the tree becomes a DAG), the playout that finds it ends without an evaluation, and re-rooting keeps
+    every node some kept node still links to. Visit counts, node counts and the number of attached transpositions
+    are the reference's."""
+    from hostsim_util import HostSim
+    ct, eng = _setup(game)
+    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits', lookup_transpositions=True)
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    ref = eng.search(conf, evals, n_moves=moves, max_children=4096)
+    hs = HostSim(tables.blob_by_name(game), ct, sp)
+    mine = hs.search(evals, moves, max_children=4096)
+    assert len(ref) == len(mine) == moves
+    for m, (a, b) in enumerate(zip(ref, mine)):
+        assert np.array_equal(a['moves'], b['moves'])
+        assert np.array_equal(a['traversals'], b['traversals'])
+        assert a['choice'] == b['choice'] and a['root_visits'] == b['root_visits']
+        assert np.array_equal(a['scores'], b['scores'])
+        assert a['nodes'] == b['nodes'] + m     # the reference keeps the chain of past roots, the arena does not
+    if game in ('breakthroughSmall', 'reversi'):
+        assert hs.transpositions() > 10     # the case is not vacuous (the wide games rarely transpose this shallow)
+
+
 def test_backup_finalised_and_temperature_choice_match():
     from hostsim_util import HostSim
     ct, eng = _setup('breakthroughSmall')
@@ -92,10 +118,17 @@ def test_selfplay_samples_match_reference_supervisor(game, G, evals, target):
     _selfplay_samples(game, G, evals, target, noise=False)
 
 
-def _selfplay_samples(game, G, evals, target, noise):
+def test_selfplay_samples_match_with_transposition_lookup():
+    """Whole games with shared nodes: every re-root rebuilds the table, samples stay the reference's."""
+    _selfplay_samples('breakthroughSmall', 6, 60, 150, noise=False, transpositions=True)
+
+
+def _selfplay_samples(game, G, evals, target, noise, transpositions=False):
     from hostsim_util import HostSim
     ct, eng = _setup(game)
     sp = confs.selfplay_config_template(evals_per_move=evals)
+    sp.puct_config.lookup_transpositions = transpositions
+    sp.run_to_end_puct_config.lookup_transpositions = transpositions
     if not noise:
         sp.puct_config.dirichlet_noise_pct = -1
         sp.run_to_end_puct_config.dirichlet_noise_pct = -1
