@@ -1,11 +1,18 @@
-"""Board symmetries of states and actions — mirror of
-``src/ggpzero/util/symmetry.py`` (``Translator``, ``Prescription``, ``create_translator``), plus the tables
-that let the device apply a symmetry to a whole batch of packed states with one bit-permutation kernel
-(``gz_permute_state_bits``) and to dense policy rows with one gather.
+"""Board symmetries of states and actions.
 
-Base strings are ``(true (cell 1 1 red))`` and action strings ``(does black (move 1 1))`` (lookup.GameModel);
-coordinates are translated exactly as the reference does: optional ``reflect_vertical`` first, then
-``rot_count`` anti-clockwise quarter turns.
+The public surface is the one ``src/ggpzero/util/symmetry.py`` offers (``Translator`` with ``add_basetype`` /
+``add_action_type`` / ``add_skip_base`` / ``add_skip_action`` / ``translate_basestate`` / ``translate_action``,
+``Prescription``, ``create_translator``); the inside is built the way the device wants it: a symmetry is a
+**permutation table**. Every base and every action is parsed once into (root term, board-coordinate slots as integer
+indices into the game's coordinate lists); the eight board symmetries are 2x2 integer maps on those indices
+(``reflect``: column c -> n-1-c; one anti-clockwise quarter turn: (c, r) -> (r, n-1-c)), applied to whole arrays with
+numpy; the resulting tables ``dest[i]`` are cached per (reflection, rotation count) and shared by the host methods
+(an index lookup) and by ``DeviceSymmetry`` (one bit-permutation kernel over a batch of packed states, one gather
+over dense policy rows).
+
+Base strings are ``(true (cell 1 1 red))``, action strings ``(does black (move 1 1))`` (lookup.GameModel). A
+symmetry is applied as the reference applies it: the optional vertical-axis reflection first, then ``rot_count``
+anti-clockwise quarter turns (symmetry.py:4-20,100-118).
 """
 from __future__ import annotations
 
@@ -14,135 +21,134 @@ import numpy as np
 from .gdl.parser import parse_sexprs
 
 
-def reflect_vertical(x, y, x_cords, y_cords):
-    return x_cords[len(x_cords) - x_cords.index(x) - 1], y
-
-
-def reflect_horizontal(x, y, x_cords, y_cords):
-    return x, y_cords[len(y_cords) - y_cords.index(y) - 1]
-
-
-def rotate_90(x, y, x_cords, y_cords):
-    """anti-clockwise (symmetry.py:14-20)"""
-    assert len(x_cords) == len(y_cords)
-    x_idx, y_idx = x_cords.index(x), y_cords.index(y)
-    return x_cords[y_idx], y_cords[len(x_cords) - x_idx - 1]
-
-
-def symbolize(txt, pos):
-    """``(true (cell 1 1 red))`` , 1 -> ('cell', '1', '1', 'red'); a bare term becomes a 1-tuple."""
+def _terms_of(txt, pos):
     t = parse_sexprs(txt)[0][pos]
     return tuple(t) if isinstance(t, (tuple, list)) else (t,)
+
+
+def _slots(v):
+    return tuple(v) if isinstance(v, (list, tuple)) else (v,)
+
+
+class _TermTable(object):
+    """One family of ground terms (the bases, or one role's actions) and its symmetry permutations."""
+
+    def __init__(self, terms, n_cols, n_rows, col_of, row_of):
+        self.terms = terms                        # tuple of symbols per entry, root term first
+        self.index = {t: i for i, t in enumerate(terms)}
+        self.n_cols, self.n_rows = n_cols, n_rows
+        self.col_of, self.row_of = col_of, row_of
+        self.moving = {}                          # root term -> (column slots, row slots)
+        self.fixed = set()                        # root terms a symmetry leaves alone
+        self._perm = {}
+
+    def permutation(self, do_reflection, rot_count):
+        key = (bool(do_reflection), int(rot_count) % 4)
+        if key in self._perm:
+            return self._perm[key]
+        if key[1] and self.n_cols != self.n_rows:
+            raise ValueError('quarter turns need a square board')
+        n = self.n_cols
+        dest = np.arange(len(self.terms), dtype=np.int32)
+        x_names = sorted(self.col_of, key=self.col_of.get)
+        y_names = sorted(self.row_of, key=self.row_of.get)
+        for root, (xs, ys) in self.moving.items():
+            members = [i for i, t in enumerate(self.terms) if t[0] == root]
+            if not members:
+                continue
+            cols = np.array([[self.col_of[self.terms[i][k]] for k in xs] for i in members], dtype=np.int64)
+            rows = np.array([[self.row_of[self.terms[i][k]] for k in ys] for i in members], dtype=np.int64)
+            if key[0]:
+                cols = self.n_cols - 1 - cols
+            for _ in range(key[1]):
+                cols, rows = rows, n - 1 - cols
+            for m, i in enumerate(members):
+                t = list(self.terms[i])
+                for k, (xk, yk) in enumerate(zip(xs, ys)):
+                    t[xk] = x_names[cols[m, k]]
+                    t[yk] = y_names[rows[m, k]]
+                dest[i] = self.index[tuple(t)]
+        unknown = sorted({t[0] for t in self.terms} - set(self.moving) - self.fixed)
+        if unknown:
+            raise Exception("Not supported term(s) %s" % ', '.join(unknown))
+        if len(np.unique(dest)) != len(dest):
+            raise AssertionError('a symmetry must permute the terms')
+        self._perm[key] = dest
+        return dest
 
 
 class Translator(object):
     def __init__(self, game_info, x_cords, y_cords):
         self.game_info = game_info
-        self.x_cords = list(x_cords)
-        self.y_cords = list(y_cords)
-        self.base_symbols = [symbolize(b, 1) for b in game_info.model.bases]
-        self.base_root_term_indexes = {}
-        self.base_root_term_to_mapping = {}
-        self.action_list = [[symbolize(a, 2) for a in game_info.model.actions[ri]]
-                            for ri in range(len(game_info.model.roles))]
-        self.action_index = [{t: i for i, t in enumerate(lst)} for lst in self.action_list]
-        self.action_root_term_indexes = {}
-        self.skip_base_root_terms = set()
-        self.skip_action_root_term = set()
+        self.x_cords, self.y_cords = list(x_cords), list(y_cords)
+        col_of = {c: i for i, c in enumerate(self.x_cords)}
+        row_of = {c: i for i, c in enumerate(self.y_cords)}
+        model = game_info.model
+        self._bases = _TermTable([_terms_of(b, 1) for b in model.bases], len(col_of), len(row_of), col_of, row_of)
+        self._actions = [_TermTable([_terms_of(a, 2) for a in model.actions[ri]], len(col_of), len(row_of), col_of, row_of)
+                         for ri in range(len(model.roles))]
 
-    @staticmethod
-    def _aslist(v):
-        return list(v) if isinstance(v, (list, tuple)) else [v]
-
+    # ---- registration (what gamedesc.GameSymmetries prescribes)
     def add_basetype(self, root_term, x_terms_idx, y_terms_idx):
-        assert root_term not in self.base_root_term_indexes
-        self.base_root_term_indexes[root_term] = self._aslist(x_terms_idx), self._aslist(y_terms_idx)
-        mapping = self.base_root_term_to_mapping[root_term] = {}
-        for indx, terms in enumerate(self.base_symbols):
-            if terms[0] == root_term:
-                mapping[terms[1:]] = indx
+        assert root_term not in self._bases.moving
+        xs, ys = _slots(x_terms_idx), _slots(y_terms_idx)
+        assert len(xs) == len(ys)
+        self._bases.moving[root_term] = (xs, ys)
+        self._bases._perm.clear()
 
     def add_action_type(self, root_term, x_terms_idx, y_terms_idx):
-        assert root_term not in self.action_root_term_indexes
-        self.action_root_term_indexes[root_term] = self._aslist(x_terms_idx), self._aslist(y_terms_idx)
+        xs, ys = _slots(x_terms_idx), _slots(y_terms_idx)
+        assert len(xs) == len(ys)
+        for t in self._actions:
+            assert root_term not in t.moving
+            t.moving[root_term] = (xs, ys)
+            t._perm.clear()
 
     def add_skip_base(self, root_term):
-        self.skip_base_root_terms.add(root_term)
+        self._bases.fixed.add(root_term)
 
     def add_skip_action(self, root_term):
-        self.skip_action_root_term.add(root_term)
+        for t in self._actions:
+            t.fixed.add(root_term)
 
-    def translate_terms(self, terms, x_terms_idx, y_terms_idx, do_reflection, rot_count):
-        assert len(x_terms_idx) == len(y_terms_idx)
-        new_terms = list(terms)
-        for xi, yi in zip(x_terms_idx, y_terms_idx):
-            x, y = terms[xi], terms[yi]
-            if do_reflection:
-                x, y = reflect_vertical(x, y, self.x_cords, self.y_cords)
-            for _ in range(rot_count):
-                x, y = rotate_90(x, y, self.x_cords, self.y_cords)
-            new_terms[xi], new_terms[yi] = x, y
-        return tuple(new_terms)
+    # ---- the tables
+    def base_permutation(self, do_reflection, rot_count):
+        """dest[i] = index base i moves to (a permutation of range(n_bases))."""
+        return self._bases.permutation(do_reflection, rot_count)
 
+    def action_permutation(self, role_index, do_reflection, rot_count):
+        return self._actions[role_index].permutation(do_reflection, rot_count)
+
+    @property
+    def action_list(self):
+        return [t.terms for t in self._actions]
+
+    # ---- per-item queries are table look-ups
     def translate_base_index(self, indx, do_reflection, rot_count):
-        terms = self.base_symbols[indx]
-        if terms[0] in self.skip_base_root_terms:
-            return indx
-        if terms[0] not in self.base_root_term_indexes:
-            raise Exception("Not supported base %s" % str(terms))
-        xi, yi = self.base_root_term_indexes[terms[0]]
-        new_terms = self.translate_terms(terms, xi, yi, do_reflection, rot_count)
-        return self.base_root_term_to_mapping[new_terms[0]][new_terms[1:]]
+        return int(self.base_permutation(do_reflection, rot_count)[indx])
 
     def translate_basestate(self, basestate, do_reflection, rot_count):
-        assert isinstance(basestate, (tuple, list)) and len(basestate) == len(self.base_symbols)
-        new_basestate = [0] * len(basestate)
-        for indx in range(len(basestate)):
-            if basestate[indx]:
-                new_basestate[self.translate_base_index(indx, do_reflection, rot_count)] = 1
-        return new_basestate
+        dest = self.base_permutation(do_reflection, rot_count)
+        assert len(basestate) == len(dest)
+        out = np.zeros(len(dest), dtype=np.int64)
+        out[dest] = np.asarray(basestate, dtype=np.int64) != 0
+        return out.tolist()
 
     translate_basestate_faster = translate_basestate
 
     def translate_action(self, role_index, legal, do_reflection, rot_count):
-        terms = self.action_list[role_index][legal]
-        if terms[0] in self.skip_action_root_term:
-            return legal
-        xi, yi = self.action_root_term_indexes[terms[0]]
-        new_terms = self.translate_terms(terms, xi, yi, do_reflection, rot_count)
-        return self.action_index[role_index][new_terms]
-
-    # ---- tables for the batched device path
-    def base_permutation(self, do_reflection, rot_count):
-        """dest[i] = index the base i moves to (a permutation of range(n_bases))."""
-        n = len(self.base_symbols)
-        dest = np.array([self.translate_base_index(i, do_reflection, rot_count) for i in range(n)], dtype=np.int32)
-        assert len(set(dest.tolist())) == n, 'a symmetry must permute the bases'
-        return dest
-
-    def action_permutation(self, role_index, do_reflection, rot_count):
-        n = len(self.action_list[role_index])
-        dest = np.array([self.translate_action(role_index, a, do_reflection, rot_count) for a in range(n)],
-                        dtype=np.int32)
-        assert len(set(dest.tolist())) == n
-        return dest
+        return int(self.action_permutation(role_index, do_reflection, rot_count)[legal])
 
 
 class Prescription(object):
-    """symmetry.py:228-254: which (reflection, rotation count) pairs a game uses."""
+    """Which (reflection, rotation count) pairs a game's description asks for (symmetry.py:228-254); the identity
+    comes first, reflected variants after the plain ones."""
 
     def __init__(self, desc):
-        self.prescription = []
         assert not (desc.do_rotations_90 and desc.do_rotations_180)
-        if desc.do_rotations_90 or desc.do_rotations_180:
-            rotations = (0, 2) if desc.do_rotations_180 else (0, 1, 2, 3)
-            self.prescription += [(False, r) for r in rotations]
-            if desc.do_reflection:
-                self.prescription += [(True, r) for r in rotations]
-        elif desc.do_reflection:
-            self.prescription += [(False, 0), (True, 0)]
-        else:
-            self.prescription += [(False, 0)]
+        turns = (0, 1, 2, 3) if desc.do_rotations_90 else (0, 2) if desc.do_rotations_180 else (0,)
+        mirrors = (False, True) if desc.do_reflection else (False,)
+        self.prescription = [(m, r) for m in mirrors for r in turns]
 
     def __iter__(self):
         return iter(self.prescription)
@@ -150,14 +156,14 @@ class Prescription(object):
 
 def create_translator(game_info, game_desc, game_symmetries):
     t = Translator(game_info, game_desc.x_cords, game_desc.y_cords)
-    for ab in game_symmetries.apply_bases:
-        t.add_basetype(ab.base_term, ab.x_terms_idx, ab.y_terms_idx)
-    for ac in game_symmetries.apply_actions:
-        t.add_action_type(ac.base_term, ac.x_terms_idx, ac.y_terms_idx)
-    for term in game_symmetries.skip_bases:
-        t.add_skip_base(term)
-    for term in game_symmetries.skip_actions:
-        t.add_skip_action(term)
+    for rule in game_symmetries.apply_bases:
+        t.add_basetype(rule.base_term, rule.x_terms_idx, rule.y_terms_idx)
+    for rule in game_symmetries.apply_actions:
+        t.add_action_type(rule.base_term, rule.x_terms_idx, rule.y_terms_idx)
+    for root in game_symmetries.skip_bases:
+        t.add_skip_base(root)
+    for root in game_symmetries.skip_actions:
+        t.add_skip_action(root)
     return t
 
 
