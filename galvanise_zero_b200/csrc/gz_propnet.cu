@@ -638,8 +638,11 @@ static int build_group_tables(gz_propnet* pn, const int32_t* h) {
     // Measured (profiles/r02_propnet_games.md): the group kernel pays two L2 round trips per level, the per-tile
     // kernels a shared-memory access. Programs with few, wide levels (chess_15d: 34 levels of up to 300 chunks,
     // hexLG13: 19 of up to 1400) run 2.5-3x faster in groups; deep narrow ones (reversi: 175 levels of 4 chunks)
-    // stay with the per-tile kernels unless asked (gz_propnet_set_group_min_batch).
-    pn->group_min_batch = pn->group_cl == 8 ? GROUP_GAMES : -1;
+    // stay with the per-tile kernels unless asked (gz_propnet_set_group_min_batch) — and so does every narrow-format
+    // game, whatever its widest level: reversi's goal cone has one level of more than 64 chunks, yet its group
+    // kernel is 15x slower than pn_kernel (r2i_pn_reversi_*: 10 M vs 158 M transitions/s; amazons 24 M vs 44 M,
+    // connect6 92 M vs 685 M), and inside the PUCT step it cost 1.23 ms against 0.31 ms.
+    pn->group_min_batch = (P.wide && pn->group_cl == 8) ? GROUP_GAMES : -1;
     pn->group_clusters = pn->group_cl == 8 ? pn->n_sms / 8 : pn->n_sms;
     const int64_t slices = std::max<int64_t>((int64_t)P.nbw * 32 * GROUP_TILES, (int64_t)GROUP_TILES * GZ_PN_MAX_ROLES * 32);
     pn->group_stride = (((int64_t)P.val_words * GROUP_TILES + slices + 2 * GROUP_TILES) + 31) & ~(int64_t)31;
