@@ -20,8 +20,11 @@
 // Arithmetic types (float vs double, rounding points) follow the reference expression by
 // expression so that, with identical network outputs, visit counts are identical.
 //
-// Scope notes: one outstanding evaluation per tree (PuctConfig.batch_size == 1, the self-play
-// setting, templates.py:76); games in which two roles have a real choice in the same state are rejected.
+// Scope notes: games in which two roles have a real choice in the same state are rejected. Self-play runs one
+// evaluation per tree at a time (PuctConfig.batch_size == 1, templates.py:76); a Player's search with
+// batch_size > 1 runs the reference's batch_size - 1 playoutWorker coroutines beside playoutMain
+// (evaluator.cpp:722-742,1050-1069) as resumable state machines under a restatement of NetworkScheduler's
+// run queue (scheduler.cpp:131-203), see "Intra-tree workers" below.
 // With PuctConfig.lookup_transpositions the trees are DAGs (a node reached by several move orders is shared,
 // evaluator.cpp:216-239): the copy of a child node's statistics kept in its parent's child record (GzpChild)
 // would go stale in the parents a backup does not pass through, so select then reads the child nodes themselves.
@@ -106,6 +109,37 @@ struct SpConf {
     int abort_max_length;
     PuctConf puct;
     PuctConf run_to_end;
+};
+
+// ---- intra-tree workers (PuctConfig.batch_size > 1): one record per coroutine of a search, and the per-game
+// run queue that replaces NetworkScheduler::mainLoop for them
+#define GZP_MAX_EB 64
+enum {
+    CO_DEAD = 0,
+    CO_MAIN_START,        // onNextMove: spawn the workers (evaluator.cpp:1050-1065)
+    CO_MAIN_TOP,          // top of playoutMain's loop (evaluator.cpp:782)
+    CO_MAIN_COLLECT,      // "collect workers" (evaluator.cpp:1076-1079)
+    CO_WORKER_TOP,        // top of playoutWorker's loop (evaluator.cpp:723)
+    CO_WORKER_RESUMED,    // ... after its yield
+    CO_DESCEND,           // inside treePlayout's loop at node `cur`
+    CO_SELECT_RESUMED,    // after the yield inside selectChild (bad fallback with unselectable siblings)
+    CO_AFTER_PROPNET,     // expandChild: waiting for the propnet pass / node creation
+    CO_AFTER_EVAL         // createNode: blocked in NetworkScheduler::evaluate
+};
+struct GzpCo {
+    int32_t st;
+    int32_t cur, path_len;
+    int32_t req_parent, req_child;   // the child it is expanding (that child is `unselectable` meanwhile)
+    int32_t node;                    // the node created for it
+    int32_t sel_to;                  // CO_SELECT_RESUMED: the node the chosen child leads to
+    int32_t evaluated;               // the node went to the network (counts as an evaluation when the coroutine resumes)
+};
+struct GzpSched {
+    int32_t n_run, n_req, n_yld;     // runnables (FIFO), requestors, yielders
+    int32_t current;                 // coroutine that owns the controller (it may be waiting for the propnet pass), -1
+    int32_t worker_count, do_playouts, flush_wait, active;
+    int32_t run[GZP_MAX_EB + 1], req[GZP_MAX_EB + 1], yld[GZP_MAX_EB + 1];
+    GzpCo co[GZP_MAX_EB];            // 0: the search itself (onNextMove / playoutMain), 1..: playoutWorker
 };
 
 // ---- per-game controller record
@@ -195,11 +229,19 @@ struct PuctEngine {
     uint32_t *x_in_state, *x_state, *x_legal;   // [G*SW], [G*SW], [G*LW]
     int16_t* x_moves;                           // [G*R]   (-1 = identity / inactive)
     uint8_t *x_term, *x_goals, *x_prevcnt;      // [G], [G*R], [G]
-    uint8_t* x_need_eval;                       // [G] 1 when the row of planes is a live request
+    uint8_t* x_need_eval;                       // [G*EB] 1 when the row of planes is a live request
+    // evaluation rows: EB per game (a Player with PuctConfig.batch_size > 1 hands up to batch_size leaves of its one
+    // tree to the network at once; self-play: 1). Row of game g, request k: g*EB + k. The encoder reads e_state /
+    // e_prev / e_prevcnt; with EB == 1 these ARE x_state / x_in_state / x_prevcnt.
+    int EB;
+    uint32_t *e_state, *e_prev;                 // [G*EB*SW]
+    uint8_t* e_prevcnt;                         // [G*EB]
+    GzpSched* sched;                            // [G] when EB > 1, else null
+    int32_t *co_path_node, *co_path_choice;     // [G*EB*MAXD] playout path of every coroutine (EB > 1)
     uint32_t* x_cache;                          // [G * 12 * max_actions] child staging when it does not fit on chip
-    // network outputs, one row per game
-    const float* nn_policy;   // [G * policy_stride]  role rows concatenated
-    const float* nn_value;    // [G * n_rewards]
+    // network outputs, one row per evaluation row
+    const float* nn_policy;   // [G*EB * policy_stride]  role rows concatenated
+    const float* nn_value;    // [G*EB * n_rewards]
     // samples
     int32_t* pend;            // [G * MAXPEND * srec] per-game pending samples
     int MAXPEND, srec;
@@ -468,6 +510,27 @@ GZP_HD bool gzp_is_terminal(const GameView& V, int n) {
 }
 GZP_HD bool gzp_is_finalised(const GameView& V, int n) { return (NODE(n_flags, n) & NF_FINALISED) != 0; }
 
+// Select must read the child nodes themselves (not the copies in the parent's child records) when a node can be
+// reached through several records: transposition tables, and intra-tree workers (a child's node is attached to its
+// record only when its creator resumes, and the reference's workers can create two nodes for one forced child).
+GZP_HD bool gzp_direct_stats(const PuctEngine* E) { return E->tt_cap != 0 || E->EB > 1; }
+
+// Intra-tree workers: how many coroutines are inside expandChild on a child of `parent` (child index `child`, or any
+// child when child < 0) — PuctNodeChild::unselectable / PuctNode::unselectable_count (evaluator.cpp:228-233).
+enum { CF_UNSELECTABLE = 0x100, CF_BLOCKED = 0x200 };    // bits of ChildCache::flags beside NF_FINALISED
+GZP_HD int gzp_pending_on(const PuctEngine* E, int g, int parent, int child) {
+    if (E->EB <= 1) return 0;
+    const GzpSched& S = E->sched[g];
+    if (!S.active) return 0;
+    int n = 0;
+    for (int k = 0; k < E->EB; k++) {
+        const GzpCo& co = S.co[k];
+        if ((co.st == CO_AFTER_PROPNET || co.st == CO_AFTER_EVAL) && co.req_parent == parent &&
+            (child < 0 || co.req_child == child)) n++;
+    }
+    return n;
+}
+
 // Stage node n's children in the cache: one contiguous block of records, two 16-byte loads per child.
 GZP_RARE void gzp_cache_fill(GameView& V, int n) {
     const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n);
@@ -485,14 +548,17 @@ GZP_RARE void gzp_cache_fill(GameView& V, int n) {
         C.visits[i] = k.c_to >= 0 ? k.c_visits : 0u;
         C.flags[i] = k.c_to >= 0 ? (int)k.c_flags : 0;
         C.inflight[i] = k.c_to >= 0 ? (int)k.c_inflight : 0;
-        if (V.E->tt_cap && k.c_to >= 0) {          // shared nodes: the record's copy may be stale, read the node
+        if (gzp_direct_stats(V.E) && k.c_to >= 0) {   // the record's copy may be stale, read the node
             const int lead = NODE(n_lead, n);
             const GzpNode& t = V.E->nodes[V.nb + k.c_to];
             C.score[i] = t.score[lead < 0 ? 0 : lead];
             C.visits[i] = t.n_visits;
             C.flags[i] = t.n_flags & NF_FINALISED;
             C.inflight[i] = t.n_inflight;
+            // every child of that node is being expanded by someone (evaluator.cpp:389-393)
+            if (V.E->EB > 1 && t.n_nchild > 0 && gzp_pending_on(V.E, V.g, k.c_to, -1) == t.n_nchild) C.flags[i] |= CF_BLOCKED;
         }
+        if (V.E->EB > 1 && gzp_pending_on(V.E, V.g, n, i) > 0) C.flags[i] |= CF_UNSELECTABLE;
     }
     GZP_SYNC();
 }
@@ -615,13 +681,13 @@ GZP_HDN int gzp_create_node(GameView& V, int parent, int depth) {
 }
 
 // PuctNodeRequest::reply (node.cpp:463-511) from this game's row of network outputs.
-GZP_HDN void gzp_reply(GameView& V, int n) {
+GZP_HDN void gzp_reply(GameView& V, int n, int k = 0, bool refresh_parent = true) {
     const PuctEngine* E = V.E;
-    const int g = V.g;
+    const int64_t row = (int64_t)V.g * E->EB + k;        // evaluation row k of this game
     const int lead = NODE(n_lead, n);
     const int nc = NODE(n_nchild, n);
     const int c0 = NODE(n_child0, n);
-    const float* pol = E->nn_policy + (int64_t)g * E->policy_stride + E->policy_off[lead];
+    const float* pol = E->nn_policy + row * E->policy_stride + E->policy_off[lead];
     float* stage = V.C.tmp;
 #ifdef __CUDA_ARCH__
     if (nc <= 32) {
@@ -660,7 +726,7 @@ GZP_HDN void gzp_reply(GameView& V, int n) {
     }
     GZP_SYNC();
     }
-    const float* val = E->nn_value + (int64_t)g * E->n_rewards;
+    const float* val = E->nn_value + row * E->n_rewards;
     for (int r = 0; r < E->R; r++) {
         float s = val[r];
         if (E->n_rewards == 3) {
@@ -673,7 +739,7 @@ GZP_HDN void gzp_reply(GameView& V, int n) {
         NSCORE(n, r) = s;   // clamp of an already clamped value
     }
     // n is the node the game's last request created: its parent's record keeps a copy of its score
-    if (V.c->req_parent >= 0) gzp_child_refresh(V, V.c->req_parent, V.c->req_child, n);
+    if (refresh_parent && V.c->req_parent >= 0) gzp_child_refresh(V, V.c->req_parent, V.c->req_child, n);
 }
 
 
@@ -876,7 +942,7 @@ __device__ __forceinline__ GzpKid gzp_warp_load_kid(const GameView& V, int c0, i
     K.visits = K.expanded ? k.c_visits : 0u;
     K.flags = K.expanded ? (int)k.c_flags : 0;
     K.inflight = K.expanded ? (int)k.c_inflight : 0;
-    if (V.E->tt_cap && K.expanded) {               // shared nodes: the record's copy may be stale, read the node
+    if (gzp_direct_stats(V.E) && K.expanded) {     // the record's copy may be stale, read the node
         const GzpNode& t = V.E->nodes[V.nb + k.c_to];
         K.score = t.score[lead < 0 ? 0 : lead];
         K.visits = t.n_visits;
@@ -1025,7 +1091,11 @@ __device__ int gzp_warp_select(GameView& V, const GzpKid& K, int nc, uint32_t no
 
 // selectChild (evaluator.cpp:341-517). Appends to the path; returns the child index within the
 // node (or -1 when nothing is selectable, which cannot happen with one evaluation in flight).
-struct GzpSelInfo { int to; int inflight; };   // the chosen child's node (or -1) and node n's in-flight count, read with the header
+struct GzpSelInfo {
+    int to; int inflight;   // the chosen child's node (or -1) and node n's in-flight count, read with the header
+    int yield_first;        // intra-tree workers: the reference yields before returning this child (evaluator.cpp:492-497)
+    int blocked;            // ... nothing selectable, every candidate is being expanded (stats.num_blocked)
+};
 
 // The generic form of selectChild: children staged in the cache, the reference's sorted scan reproduced step by
 // step (any child count, the root latch limiter and the virtual-loss discount with their random draws,
@@ -1056,6 +1126,7 @@ GZP_RARE int gzp_select_child_generic(GameView& V, int n, const GzpNode& nd, Gzp
     int bad_fallback = -1;
     float best_fallback_score = -1;
     int best_fallback = -1;
+    int unselectables = 0;
 
     // iterate children in sortedChildrenSelect order (evaluator.cpp:242-263): key sa = node score
     // for the lead role (-1 when unexpanded); both negative -> policy_prob_orig desc, else sa desc.
@@ -1082,7 +1153,7 @@ GZP_RARE int gzp_select_child_generic(GameView& V, int n, const GzpNode& nd, Gzp
     // same as "score_r > max(initial, float(score_j) for eligible j < r)" — an exclusive prefix maximum —
     // and the final choice is the last child that replaced it.
     const bool latch_on = node_visits > 1000 && node_visits < 40000000 && depth == 0;
-    if (nc <= 32 && !latch_on) {
+    if (nc <= 32 && !latch_on && V.E->EB == 1) {
         const unsigned full = 0xffffffffu;
         const int r = V.lane;
         const bool act = r < nc;
@@ -1142,6 +1213,7 @@ GZP_RARE int gzp_select_child_generic(GameView& V, int n, const GzpNode& nd, Gzp
 #endif
     for (int rank = 0; rank < nc; rank++) {
         const int pick = order[rank];
+        if (C.flags[pick] & (CF_UNSELECTABLE | CF_BLOCKED)) { unselectables++; continue; }   // evaluator.cpp:384-394
         const int to = C.to[pick];
         const uint32_t ctrav = C.trav[pick];
         double child_score = prior_score;
@@ -1192,7 +1264,10 @@ GZP_RARE int gzp_select_child_generic(GameView& V, int n, const GzpNode& nd, Gzp
     }
     if (best_child < 0) {
         if (best_fallback >= 0) best_child = best_child_score >= 0 ? best_child_score : best_fallback;
-        else if (bad_fallback >= 0) best_child = bad_fallback;
+        else if (bad_fallback >= 0) {
+            if (unselectables > 0 && info) info->yield_first = 1;
+            best_child = bad_fallback;
+        } else if (info) info->blocked = 1;
     }
     if (best_child >= 0) {
         pn[c->path_len] = n; pc[c->path_len] = best_child; c->path_len++;
@@ -1218,7 +1293,7 @@ GZP_HDN int gzp_select_child(GameView& V, int n, const GzpNode& nd, GzpSelInfo* 
     // setPuctConstant (evaluator.cpp:1300-1307)
     const uint32_t node_visits = nd.n_visits;
     const int node_inflight = nd.n_inflight;
-    if (info) { info->to = -1; info->inflight = node_inflight; }
+    if (info) { info->to = -1; info->inflight = node_inflight; info->yield_first = 0; info->blocked = 0; }
     float node_finals[GZP_MAX_ROLES];
 #pragma unroll
     for (int r = 0; r < GZP_MAX_ROLES; r++) node_finals[r] = nd.final_[r];
@@ -1240,7 +1315,7 @@ GZP_HDN int gzp_select_child(GameView& V, int n, const GzpNode& nd, GzpSelInfo* 
     V.work++;
 #ifdef __CUDA_ARCH__
     // warp path (children in registers) unless this is the root select that has to draw Dirichlet noise first
-    if (nc <= 32 && V.ord &&
+    if (nc <= 32 && V.ord && E->EB == 1 &&
         !(depth == 0 && cf.dirichlet_noise_pct >= 0 && !(nd.n_flags & NF_NOISE_SET) &&
           !(nd.score[lead < 0 ? 0 : lead] > 0.95))) {
         const GzpKid K = preloaded_kid ? *preloaded_kid : gzp_warp_load_kid(V, c0, nc, lead);
@@ -1971,7 +2046,8 @@ GZP_HDN void gzp_reroot_compact(GameView& V, int new_root, int tid, int T, Group
         grp.sync();
     }
     if (tid == 0) {
-        c->root = 0;
+        // a tree's new root is its first kept node; in a DAG shared nodes created before it may precede it
+        c->root = E->n_newidx[nb + r];
         c->n_nodes = node_base;
         c->n_children = child_base;
         c->game_depth++;
@@ -2142,9 +2218,309 @@ GZP_HD bool gzp_restart_after_error(GameView& V) {
     c->resume = 0;
     c->in_playout = 0;
     c->path_len = 0;
-    V.E->x_need_eval[V.g] = 0;
+    V.E->x_need_eval[(int64_t)V.g * V.E->EB] = 0;
     c->phase = PH_NEW_GAME;
     return true;
+}
+
+
+// playoutMain's list of break conditions (evaluator.cpp:782-841); true: the search is over.
+GZP_HDN bool gzp_search_over(GameView& V, const GzpNode& root_nd, GzpKid* root_kid, bool* have_kid) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    const PuctConf& cf = gzp_conf(V);
+    const bool is_converged = gzp_converged(V, cf.converged_visits, root_nd, root_kid, have_kid);
+    const int max_non_converged = (int)(c->max_evaluations * cf.evaluation_multiplier_to_convergence);
+    const int max_tree_playouts = max_non_converged > (1 << 28) ? (1 << 30) : 4 * max_non_converged;
+    if (c->stop_request == GZP_STOP_NOW || (c->stop_request == GZP_STOP_IF_CONVERGED && is_converged)) return true;
+    if ((root_nd.n_flags & NF_FINALISED) && c->num_tree_playouts > 100) return true;
+    if (is_converged && c->num_tree_playouts > max_tree_playouts) return true;
+    // arena nearly full ("max nodes"); every coroutine of a search with workers may still add a node before the next check
+    if (c->n_nodes + 4 * E->EB > E->NCAP || c->n_children + E->max_actions * E->EB + 4 > E->CCAP) return true;
+    if (is_converged && c->num_evaluations > c->max_evaluations) return true;
+    if (!is_converged && c->num_evaluations > max_non_converged) return true;
+    // Deviation (documented in DESIGN.md): the reference loops forever when a search only reaches terminal /
+    // finalised nodes and the root never 'converges' (no evaluation is ever counted); a game slot must not be
+    // lost, so such a search stops here.
+    if ((long long)c->num_tree_playouts > 64LL * max_tree_playouts + 10000LL) return true;
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Intra-tree workers (PuctConfig.batch_size > 1, a Player's search). The reference runs playoutMain and
+// batch_size - 1 playoutWorker coroutines (greenlets) over ONE tree; a coroutine runs until it blocks in
+// NetworkScheduler::evaluate (its leaf joins the batch) or yields, and NetworkScheduler::mainLoop
+// (scheduler.cpp:131-203) picks the next one from a FIFO of runnables, hands the batch to the network when it is
+// full or nobody can run, answers the requestors in order and re-queues them, then the yielders. The order in
+// which coroutines touch the tree decides every visit count, so that schedule is restated here exactly: each
+// coroutine is a resumable state machine (GzpCo), the queues live in GzpSched. One difference in mechanics, none
+// in order: a coroutine that expands a child waits for the engine's propnet pass while keeping the controller
+// (nobody else runs in between — in the reference the state machine call is synchronous).
+//
+// All lanes of the warp run this code redundantly on one copy of the queues in global memory: every read of
+// queue state is bracketed by warp barriers before anything is written back.
+enum { CO_R_PROPNET = 1, CO_R_BLOCKED, CO_R_YIELD, CO_R_DONE };
+
+GZP_HD int gzp_sync_load(const int32_t* p) {
+    GZP_SYNC();
+    const int v = *p;
+    GZP_SYNC();
+    return v;
+}
+GZP_HD void gzp_queue_push(int32_t* q, int32_t* n, int k) {
+    const int m = gzp_sync_load(n);
+    q[m] = k;
+    *n = m + 1;
+    GZP_SYNC();
+}
+
+GZP_HD void gzp_co_bind(GameView& V, int k) {     // the controller's playout context becomes coroutine k's
+    const PuctEngine* E = V.E;
+    GzpSched& S = E->sched[V.g];
+    V.pn = E->co_path_node + ((int64_t)V.g * E->EB + k) * E->MAXD;
+    V.pc = E->co_path_choice + ((int64_t)V.g * E->EB + k) * E->MAXD;
+    V.c->cur = S.co[k].cur;
+    V.c->path_len = S.co[k].path_len;
+}
+GZP_HD void gzp_co_save(GameView& V, int k) {
+    GzpSched& S = V.E->sched[V.g];
+    GZP_SYNC();
+    S.co[k].cur = V.c->cur;
+    S.co[k].path_len = V.c->path_len;
+    GZP_SYNC();
+}
+
+GZP_HDN void gzp_sched_start(GameView& V) {       // Player::puctPlayerMove: one runnable, the search itself
+    GzpSched& S = V.E->sched[V.g];
+    GZP_SYNC();
+    S.n_run = 1; S.run[0] = 0; S.n_req = 0; S.n_yld = 0; S.current = -1;
+    S.worker_count = 0; S.do_playouts = 1; S.flush_wait = 0; S.active = 1;
+    for (int k = 0; k < GZP_MAX_EB; k++) { S.co[k].st = CO_DEAD; S.co[k].req_parent = -1; S.co[k].req_child = -1; }
+    S.co[0].st = CO_MAIN_START;
+    GZP_SYNC();
+}
+
+// the end of a playout for coroutine k: back to the top of its loop
+GZP_HD int gzp_co_loop_top(int k) { return k == 0 ? CO_MAIN_TOP : CO_WORKER_TOP; }
+
+// Runs coroutine k until it gives up the controller. Returns CO_R_*.
+GZP_HDN int gzp_co_run(GameView& V, int k) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    GzpSched& S = E->sched[V.g];
+    GzpCo& co = S.co[k];
+    gzp_co_bind(V, k);
+    for (int guard = 0; guard < (1 << 20); guard++) {
+        if (c->error) return CO_R_DONE;
+        const int st = gzp_sync_load(&co.st);
+        switch (st) {
+        case CO_MAIN_START: {
+            // onNextMove (evaluator.cpp:1032-1069): the workers are queued behind whatever is runnable
+            const int root = c->root;
+            const int B = gzp_conf(V).batch_size < E->EB ? gzp_conf(V).batch_size : E->EB;
+            if (B > 1 && !gzp_is_finalised(V, root) && (c->max_evaluations < 0 || c->max_evaluations > 100)) {
+                for (int w = 1; w < B; w++) {
+                    S.co[w].st = CO_WORKER_TOP;
+                    gzp_queue_push(S.run, &S.n_run, w);
+                }
+                S.worker_count = B - 1;
+            }
+            co.st = c->max_evaluations != 0 ? CO_MAIN_TOP : CO_MAIN_COLLECT;
+            break;
+        }
+        case CO_MAIN_TOP: {
+            const GzpNode root_nd = V.E->nodes[V.nb + c->root];
+            bool have_kid = false;
+            GzpKid kid;
+            if (gzp_search_over(V, root_nd, &kid, &have_kid)) { co.st = CO_MAIN_COLLECT; break; }
+            c->cur = c->root;
+            c->path_len = 0;
+            co.st = CO_DESCEND;
+            break;
+        }
+        case CO_MAIN_COLLECT: {
+            // do_playouts = false; while (worker_count > 0) yield();
+            S.do_playouts = 0;
+            if (gzp_sync_load(&S.worker_count) > 0) { gzp_co_save(V, k); return CO_R_YIELD; }
+            co.st = CO_DEAD;
+            return CO_R_DONE;
+        }
+        case CO_WORKER_TOP: {
+            if (!gzp_sync_load(&S.do_playouts)) { co.st = CO_DEAD; S.worker_count = gzp_sync_load(&S.worker_count) - 1; return CO_R_DONE; }
+            if (c->num_tree_playouts % 10000 == 0) { co.st = CO_WORKER_RESUMED; gzp_co_save(V, k); return CO_R_YIELD; }
+            co.st = CO_WORKER_RESUMED;
+            break;
+        }
+        case CO_WORKER_RESUMED: {
+            if (gzp_is_finalised(V, c->root)) { co.st = CO_DEAD; S.worker_count = gzp_sync_load(&S.worker_count) - 1; return CO_R_DONE; }
+            c->cur = c->root;
+            c->path_len = 0;
+            co.st = CO_DESCEND;
+            break;
+        }
+        case CO_DESCEND: {
+            // treePlayout's loop (evaluator.cpp:666-707)
+            const int cur = c->cur;
+            const GzpNode nd = V.E->nodes[V.nb + cur];
+            if ((nd.n_flags & (NF_FORCE_TERMINAL | NF_FINALISED)) || nd.n_nchild == 0) {
+                gzp_path_push(V, cur, -1);
+                gzp_finish_playout(V, nd);
+                co.st = gzp_co_loop_top(k);
+                break;
+            }
+            GzpSelInfo si;
+            const int child = gzp_select_child(V, cur, nd, &si);
+            if (c->error) return CO_R_DONE;
+            if (child < 0) {                    // nothing selectable right now: yield, then select again
+                gzp_co_save(V, k);
+                return CO_R_YIELD;
+            }
+            if (si.yield_first) {               // the yield inside selectChild; the chosen child is an expanded node
+                co.sel_to = si.to;
+                co.st = CO_SELECT_RESUMED;
+                gzp_co_save(V, k);
+                return CO_R_YIELD;
+            }
+            if (si.to < 0) {
+                // expandChild: the child is unselectable from here until this coroutine has its node
+                co.req_parent = cur;
+                co.req_child = child;
+                co.st = CO_AFTER_PROPNET;
+                gzp_request_expand(V, cur, child, PUR_PLAYOUT);
+                gzp_co_save(V, k);
+                return CO_R_PROPNET;
+            }
+            NODE(n_inflight, cur) = si.inflight + 1;
+            c->cur = si.to;
+            break;
+        }
+        case CO_SELECT_RESUMED: {
+            const int cur = c->cur;
+            NODE(n_inflight, cur) = NODE(n_inflight, cur) + 1;
+            c->cur = co.sel_to;
+            co.st = CO_DESCEND;
+            break;
+        }
+        case CO_AFTER_PROPNET: {
+            // gzp_step_post has looked the state up / created the node
+            const int N = c->new_node;
+            co.node = N;
+            co.st = CO_AFTER_EVAL;
+            if (c->eval_node >= 0) {            // createNode -> NetworkScheduler::evaluate: join the batch and wait
+                c->eval_node = -1;
+                co.evaluated = 1;
+                gzp_queue_push(S.req, &S.n_req, k);
+                gzp_co_save(V, k);
+                return CO_R_BLOCKED;
+            }
+            co.evaluated = 0;                   // a shared node, a finalised one or a forced move: straight on
+            break;
+        }
+        case CO_AFTER_EVAL: {
+            // back in createNode / expandChild with the node in hand (evaluator.cpp:207-214, 232-236)
+            const int N = co.node;
+            if (co.evaluated) { c->num_evaluations++; c->total_evals++; }
+            const int parent = co.req_parent, child = co.req_child;
+            CHILD(c_to, NODE(n_child0, parent) + child) = N;
+            gzp_child_refresh(V, parent, child, N);
+            co.req_parent = -1;
+            co.req_child = -1;
+            if (gzp_is_finalised(V, N) || NODE(n_nchild, N) > 1) {
+                gzp_path_push(V, N, -1);
+                gzp_finish_playout(V, V.E->nodes[V.nb + N]);
+                co.st = gzp_co_loop_top(k);
+            } else {
+                NODE(n_inflight, N) = NODE(n_inflight, N) + 1;
+                c->cur = N;
+                co.st = CO_DESCEND;
+            }
+            break;
+        }
+        default:
+            return CO_R_DONE;
+        }
+    }
+    c->error = GZP_ERR_PATH;
+    return CO_R_DONE;
+}
+
+// NetworkScheduler::mainLoop for one game. Returns true when the engine step ends here for this game (a propnet
+// request is posted, the batch waits for the network, or the step's budget is spent); false when the search is over.
+GZP_HDN bool gzp_sched_run(GameView& V, bool nn_fresh) {
+    const PuctEngine* E = V.E;
+    GameCtl* c = V.c;
+    GzpSched& S = E->sched[V.g];
+    if (!gzp_sync_load(&S.active)) gzp_sched_start(V);
+    if (gzp_sync_load(&S.flush_wait)) {
+        if (!nn_fresh) return true;                         // the batch is still with the network
+        // "once we return, we must handle the results before doing anything else": every requestor gets its
+        // answer, in order, and joins the runnables; then the yielders (scheduler.cpp:176-197)
+        const int nreq = gzp_sync_load(&S.n_req);
+        for (int i = 0; i < nreq; i++) {
+            const int k = S.req[i];
+            E->x_need_eval[(int64_t)V.g * E->EB + i] = 0;
+            gzp_reply(V, S.co[k].node, i, false);
+            gzp_queue_push(S.run, &S.n_run, k);
+        }
+        const int nyld = gzp_sync_load(&S.n_yld);
+        for (int i = 0; i < nyld; i++) gzp_queue_push(S.run, &S.n_run, S.yld[i]);
+        GZP_SYNC();
+        S.n_req = 0; S.n_yld = 0; S.flush_wait = 0;
+        GZP_SYNC();
+    }
+    for (int iter = 0; iter < 4 * GZP_MAX_EB; iter++) {
+        int k = gzp_sync_load(&S.current);
+        if (k < 0) {
+            const int nrun = gzp_sync_load(&S.n_run), nreq = gzp_sync_load(&S.n_req), nyld = gzp_sync_load(&S.n_yld);
+            bool jump = false;
+            if (nrun == 0) {
+                if (nreq == 0) {
+                    if (nyld > 0) {
+                        for (int i = 0; i < nyld; i++) gzp_queue_push(S.run, &S.n_run, S.yld[i]);
+                        GZP_SYNC();
+                        S.n_yld = 0;
+                        GZP_SYNC();
+                        continue;
+                    }
+                    // nothing left to run: the search's coroutine has returned
+                    GZP_SYNC();
+                    S.active = 0;
+                    GZP_SYNC();
+                    V.pn = E->co_path_node + (int64_t)V.g * E->EB * E->MAXD;
+                    V.pc = E->co_path_choice + (int64_t)V.g * E->EB * E->MAXD;
+                    c->path_len = 0;
+                    c->in_playout = 0;
+                    c->phase = PH_MOVE_DONE;
+                    return false;
+                }
+                jump = true;
+            }
+            const int B = gzp_conf(V).batch_size < E->EB ? gzp_conf(V).batch_size : E->EB;
+            if (!jump && nreq >= (B < 1 ? 1 : B)) jump = true;
+            if (jump) {
+                // hand the batch to the network: rows 0 .. nreq-1 of this game were staged by gzp_step_post
+                GZP_SYNC();
+                for (int i = 0; i < nreq; i++) E->x_need_eval[(int64_t)V.g * E->EB + i] = 1;
+                S.flush_wait = 1;
+                GZP_SYNC();
+                return true;
+            }
+            k = S.run[0];
+            GZP_SYNC();
+            for (int i = 1; i < nrun; i++) { const int v = S.run[i]; GZP_SYNC(); S.run[i - 1] = v; GZP_SYNC(); }
+            S.n_run = nrun - 1;
+            S.current = k;
+            GZP_SYNC();
+        }
+        const int r = gzp_co_run(V, k);
+        if (c->error) return true;
+        if (r == CO_R_PROPNET) return true;                 // keeps the controller across the propnet pass
+        GZP_SYNC();
+        S.current = -1;
+        GZP_SYNC();
+        if (r == CO_R_YIELD) gzp_queue_push(S.yld, &S.n_yld, k);
+    }
+    return true;                                            // budget of this step spent; carries on next step
 }
 
 // Returns when the game is blocked on the pipeline (c->req != REQ_NONE or c->eval_node >= 0),
@@ -2153,9 +2529,15 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     if (c->phase == PH_HALT) return;
+    if (E->EB > 1 && c->phase == PH_SEARCH) {
+        // a Player's search with intra-tree workers: its own scheduler consumes the network's answers
+        if (c->req != REQ_NONE) return;
+        if (gzp_sched_run(V, nn_fresh)) return;
+        nn_fresh = false;
+    }
     if (c->eval_node >= 0) {
         if (!nn_fresh) return;          // still waiting for the network
-        E->x_need_eval[V.g] = 0;
+        E->x_need_eval[(int64_t)V.g * E->EB] = 0;
         gzp_reply(V, c->eval_node);
         c->num_evaluations++;
         c->total_evals++;
@@ -2234,27 +2616,16 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
             break;
         }
         case PH_SEARCH: {
+            if (E->EB > 1) {                           // a Player's search: the coroutines of "Intra-tree workers"
+                if (gzp_sched_run(V, false)) return;
+                break;
+            }
             if (!c->in_playout) {
-                const PuctConf& cf = gzp_conf(V);
                 const int root = c->root;
                 const GzpNode root_nd = V.E->nodes[V.nb + root];
                 GzpKid root_kid;
                 bool have_kid = false;
-                const bool is_converged = gzp_converged(V, cf.converged_visits, root_nd, &root_kid, &have_kid);
-                const int max_non_converged = (int)(c->max_evaluations * cf.evaluation_multiplier_to_convergence);
-                const int max_tree_playouts = max_non_converged > (1 << 28) ? (1 << 30) : 4 * max_non_converged;
-                bool brk = false;
-                if (c->stop_request == GZP_STOP_NOW || (c->stop_request == GZP_STOP_IF_CONVERGED && is_converged)) brk = true;
-                else if ((root_nd.n_flags & NF_FINALISED) && c->num_tree_playouts > 100) brk = true;
-                else if (is_converged && c->num_tree_playouts > max_tree_playouts) brk = true;
-                else if (c->n_nodes + 4 > E->NCAP || c->n_children + E->max_actions + 4 > E->CCAP) brk = true;  // arena nearly full ("max nodes")
-                else if (is_converged && c->num_evaluations > c->max_evaluations) brk = true;
-                else if (!is_converged && c->num_evaluations > max_non_converged) brk = true;
-                // Deviation (documented in DESIGN.md): the reference loops forever when a search only
-                // reaches terminal / finalised nodes and the root never 'converges' (no evaluation is
-                // ever counted); a game slot must not be lost, so such a search stops here.
-                else if ((long long)c->num_tree_playouts > 64LL * max_tree_playouts + 10000LL) brk = true;
-                if (brk || c->max_evaluations == 0) { c->phase = PH_MOVE_DONE; break; }
+                if (gzp_search_over(V, root_nd, &root_kid, &have_kid) || c->max_evaluations == 0) { c->phase = PH_MOVE_DONE; break; }
                 c->cur = root;
                 c->path_len = 0;
                 c->in_playout = 1;
@@ -2406,16 +2777,20 @@ GZP_HDN void gzp_step_post(GameView& V) {
     if (c->phase == PH_HALT || c->req == REQ_NONE || c->req == REQ_REROOT) return;
     const int parent = c->req == REQ_ROOT ? -1 : c->req_parent;
     const int depth = parent < 0 ? c->game_depth : NODE(n_depth, parent) + 1;
+    // a Player's search with intra-tree workers: the expanding coroutine keeps the controller (gzp_sched_run) and
+    // attaches the node to its parent's record itself, when the reference's createNode would have returned
+    const bool workers = E->EB > 1 && c->phase == PH_SEARCH;
     if (parent >= 0 && E->tt_cap && gzp_conf(V).lookup_transpositions) {
         // expandChild (evaluator.cpp:216-239): the state is already in the tree at this depth -> share its node;
         // the playout then ends (or walks on through a forced move) without a new evaluation
         const int found = gzp_tt_find(V, E->x_state + (int64_t)V.g * E->SW, depth);
         if (found >= 0) {
             c->req = REQ_NONE;
-            CHILD(c_to, NODE(n_child0, parent) + c->req_child) = found;
-            gzp_child_refresh(V, parent, c->req_child, found);
             c->new_node = found;
             c->total_transpositions++;
+            if (workers) return;                 // the coroutine attaches it when it resumes (gzp_co_run)
+            CHILD(c_to, NODE(n_child0, parent) + c->req_child) = found;
+            gzp_child_refresh(V, parent, c->req_child, found);
             c->resume = 1;
             return;
         }
@@ -2426,7 +2801,7 @@ GZP_HDN void gzp_step_post(GameView& V) {
         if (!gzp_restart_after_error(V)) c->phase = PH_HALT;
         return;
     }
-    if (parent >= 0) {
+    if (parent >= 0 && !workers) {
         CHILD(c_to, NODE(n_child0, parent) + c->req_child) = N;
         gzp_child_refresh(V, parent, c->req_child, N);
     }
@@ -2436,9 +2811,18 @@ GZP_HDN void gzp_step_post(GameView& V) {
     const bool needs_eval = !gzp_is_finalised(V, N) && NODE(n_nchild, N) > 1;
     if (needs_eval) {
         c->eval_node = N;
-        E->x_need_eval[V.g] = 1;
-        E->x_prevcnt[V.g] = parent >= 0 ? 1 : (c->root_has_prev ? 1 : 0);
-    } else {
+        // the evaluation row: row 0 of the game, or — workers — the next free row of the batch being collected
+        // (its request flag is raised when the batch goes to the network, gzp_sched_run)
+        const int k = workers ? E->sched[V.g].n_req : 0;
+        const int64_t row = (int64_t)V.g * E->EB + k;
+        if (!workers) E->x_need_eval[row] = 1;
+        E->e_prevcnt[row] = parent >= 0 ? 1 : (c->root_has_prev ? 1 : 0);
+        if (E->EB > 1) {
+            const uint32_t* xs = E->x_state + (int64_t)V.g * E->SW;
+            const uint32_t* xp = E->x_in_state + (int64_t)V.g * E->SW;
+            for (int w = 0; w < E->SW; w++) { E->e_state[row * E->SW + w] = xs[w]; E->e_prev[row * E->SW + w] = xp[w]; }
+        }
+    } else if (!workers) {
         c->resume = 1;
     }
 }

@@ -9,7 +9,7 @@
 #include "gz_puct_core.h"
 
 // Assigns all array pointers of E inside [base, base+return). With base == nullptr only the size
-// is computed. Dimensions (G, R, SW, LW, NCAP, CCAP, MAXD, MAXPEND, srec, READYCAP, uniq_cap, tt_cap,
+// is computed. Dimensions (G, EB, R, SW, LW, NCAP, CCAP, MAXD, MAXPEND, srec, READYCAP, uniq_cap, tt_cap,
 // n_rewards, policy_stride) must be set beforehand.
 static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     size_t pos = 0;
@@ -21,6 +21,7 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     const size_t NN = (size_t)E->G * E->NCAP;
     const size_t CC = (size_t)E->G * E->CCAP;
     const size_t G = (size_t)E->G;
+    const size_t EB = (size_t)(E->EB < 1 ? 1 : E->EB);
     E->nodes = (GzpNode*)take(NN * sizeof(GzpNode));
     E->n_state = (uint32_t*)take(NN * 4 * E->SW);
     E->n_other = (int32_t*)take(NN * 4 * GZP_MAX_ROLES);
@@ -39,7 +40,23 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
     E->x_term = (uint8_t*)take(G);
     E->x_goals = (uint8_t*)take(G * E->R);
     E->x_prevcnt = (uint8_t*)take(G);
-    E->x_need_eval = (uint8_t*)take(G);
+    E->x_need_eval = (uint8_t*)take(G * EB);
+    if (EB > 1) {
+        // intra-tree workers: EB evaluation rows per game and the coroutines' queues / paths
+        E->e_state = (uint32_t*)take(G * EB * E->SW * 4);
+        E->e_prev = (uint32_t*)take(G * EB * E->SW * 4);
+        E->e_prevcnt = (uint8_t*)take(G * EB);
+        E->sched = (GzpSched*)take(G * sizeof(GzpSched));
+        E->co_path_node = (int32_t*)take(G * EB * E->MAXD * 4);
+        E->co_path_choice = (int32_t*)take(G * EB * E->MAXD * 4);
+    } else {
+        E->e_state = E->x_state;
+        E->e_prev = E->x_in_state;
+        E->e_prevcnt = E->x_prevcnt;
+        E->sched = nullptr;
+        E->co_path_node = E->path_node;
+        E->co_path_choice = E->path_choice;
+    }
     E->x_cache = (uint32_t*)take(G * gzp_cache_words(E->max_actions) * 4);
     E->pend = (int32_t*)take(G * E->MAXPEND * (size_t)E->srec * 4);
     E->ready = (int32_t*)take((size_t)E->READYCAP * E->srec * 4);

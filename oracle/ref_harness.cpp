@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -411,7 +412,8 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
     ShimStateMachine* sm = new ShimStateMachine(&g->gt);
     const GdlBasesTransformer* tr = g->ts.make();
     PuctConfig* conf = make_puct_config(puct_conf);
-    NetworkScheduler* sched = new NetworkScheduler(tr, 1);
+    /* Player (player.cpp:27-36): the scheduler's batch is PuctConfig.batch_size; 1 = the self-play setting */
+    NetworkScheduler* sched = new NetworkScheduler(tr, conf->batch_size > 1 ? conf->batch_size : 1);
     sched->createMainLoop();
     PuctEvaluator* pe = new PuctEvaluator(sm, sched, tr);
     pe->updateConf(conf);
@@ -446,6 +448,7 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
             for (int r = 0; r < 4; r++)
                 g_last_choice_scores.push_back(r < R && choice->to_node ? choice->to_node->getCurrentScore(r) : -1.0f);
             node = pe->fastApplyMove(choice);
+            if (getenv("GZREF_TRACE")) fprintf(stderr, "A %d nodes %d root_visits %d\n", m, (int)pe->nodeCount(), (int)node->visits);
         }
     };
     sched->addRunnable(f);
@@ -460,6 +463,7 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
         sched->poll(&pred, &ready);
         if (ready.buf_count == 0) break;
         const int n = ready.buf_count / total;
+        if (getenv("GZREF_TRACE")) fprintf(stderr, "B %d\n", n);
         synth_predict(g->ts, nn_seed, ready.channel_buf, n, policies, values);
         pred.policies.resize(policies.size());
         for (size_t r = 0; r < policies.size(); r++) pred.policies[r] = policies[r].data();

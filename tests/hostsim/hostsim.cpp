@@ -106,6 +106,8 @@ extern "C" void* hs_create(const int32_t* blob, int64_t n_words, int G, int mode
     fill_sp(E.conf, sp_conf);
     fill_conf(E.conf.puct, puct_conf);
     fill_conf(E.conf.run_to_end, rte_conf);
+    E.EB = 1;
+    if (mode == 1 && E.conf.puct.batch_size > 1) E.EB = E.conf.puct.batch_size > GZP_MAX_EB ? GZP_MAX_EB : E.conf.puct.batch_size;
     E.tt_cap = 0;
     if (E.conf.puct.lookup_transpositions || E.conf.run_to_end.lookup_transpositions) {
         E.tt_cap = 32;
@@ -128,8 +130,8 @@ extern "C" void* hs_create(const int32_t* blob, int64_t n_words, int G, int mode
         mask[ctrl_bc[2 * i] >> 5] |= 1u << (ctrl_bc[2 * i] & 31);
     }
     H->total = encref_total_size(H->enc);
-    H->policy.assign((size_t)G * E.policy_stride, 0.0f);
-    H->value.assign((size_t)G * num_rewards, 0.0f);
+    H->policy.assign((size_t)G * E.EB * E.policy_stride, 0.0f);
+    H->value.assign((size_t)G * E.EB * num_rewards, 0.0f);
     H->planes.assign((size_t)H->total, 0.0f);
     E.nn_policy = H->policy.data();
     E.nn_value = H->value.data();
@@ -185,11 +187,12 @@ extern "C" void hs_step(void* h) {
         GameView V = gzp_view(&E, g);
         gzp_step_post(V);
     }
-    for (int g = 0; g < E.G; g++) {
+    if (getenv("GZREF_TRACE")) { int n = 0; for (int g = 0; g < E.G * E.EB; g++) n += E.x_need_eval[g] != 0; if (n) fprintf(stderr, "B %d\n", n); }
+    for (int g = 0; g < E.G * E.EB; g++) {          // evaluation rows
         if (!E.x_need_eval[g]) continue;
-        const uint32_t* prev = E.x_in_state + (size_t)g * E.SW;
+        const uint32_t* prev = E.e_prev + (size_t)g * E.SW;
         const uint32_t* ptrs[1] = {prev};
-        encref_to_channels(H->enc, E.x_state + (size_t)g * E.SW, ptrs, E.x_prevcnt[g] ? 1 : 0, H->planes.data());
+        encref_to_channels(H->enc, E.e_state + (size_t)g * E.SW, ptrs, E.e_prevcnt[g] ? 1 : 0, H->planes.data());
         const uint64_t hh = gz_synth_hash_planes_f32(H->planes.data(), H->total, H->nn_seed);
         for (int r = 0; r < E.R; r++)
             for (int a = 0; a < E.role_sizes[r]; a++)

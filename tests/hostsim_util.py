@@ -95,6 +95,11 @@ class HostSim:
             rc = L.hs_wait(self.h, g, 100000)
             if rc != 1:
                 break
+            if os.environ.get('GZREF_TRACE'):
+                import sys
+                ti = np.zeros(max_children, dtype=np.int32); tf = np.zeros(max_children, dtype=np.float32); inf = np.zeros(8, dtype=np.float32)
+                L.hs_root_children(self.h, g, max_children, ti.ctypes.data, ti.ctypes.data, tf.ctypes.data, tf.ctypes.data, inf.ctypes.data)
+                print('A %d nodes %d root_visits %d' % (m, int(inf[3]), int(inf[0])), file=sys.stderr)
         return out
 
     def transpositions(self, g=0):

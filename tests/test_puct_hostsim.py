@@ -99,6 +99,34 @@ def test_transposition_lookup_matches_reference(game, evals, moves):
         assert hs.transpositions() > 10     # the case is not vacuous (the wide games rarely transpose this shallow)
 
 
+@pytest.mark.parametrize('game,evals,moves,batch,tt,noise', [
+    ('breakthroughSmall', 400, 20, 8, False, -1), ('reversi', 600, 12, 32, False, -1),
+    ('reversi', 300, 20, 4, False, 0.25), ('breakthrough', 500, 12, 16, True, -1),
+    ('connect6', 200, 3, 32, False, -1), ('amazons_10x10', 150, 2, 8, False, -1),
+    ('reversi', 60, 6, 32, False, -1)])      # <= 100 evaluations: no workers are spawned (evaluator.cpp:1057)
+def test_intra_tree_workers_match_reference(game, evals, moves, batch, tt, noise):
+    """PuctConfig.batch_size > 1 (a Player's default is 32, confs.py:64): playoutMain and batch_size - 1 playoutWorker
+    coroutines share one tree (evaluator.cpp:722-742,1050-1079), leaves are evaluated in batches, in-flight visits
+    discount select (evaluator.cpp:402-405,443-446, with their random draws) and children being expanded are
+    unselectable. The reference's greenlet schedule (scheduler.cpp:131-203) decides every visit count; the restated
+    run queue reproduces it: identical root statistics after every search of a game."""
+    from hostsim_util import HostSim
+    ct, eng = _setup(game)
+    conf = confs.base_puct_config(dirichlet_noise_pct=noise, choose='choose_top_visits', batch_size=batch,
+                                  lookup_transpositions=tt)
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    ref = eng.search(conf, evals, n_moves=moves, max_children=4096)
+    mine = HostSim(tables.blob_by_name(game), ct, sp, ncap=1 << 14, ccap=1 << 21).search(evals, moves, max_children=4096)
+    assert len(ref) == len(mine) == moves
+    for a, b in zip(ref, mine):
+        assert np.array_equal(a['moves'], b['moves'])
+        assert np.array_equal(a['traversals'], b['traversals'])
+        assert a['choice'] == b['choice'] and a['root_visits'] == b['root_visits']
+        assert np.array_equal(a['policy_prob'], b['policy_prob'])
+        assert np.array_equal(a['scores'], b['scores'])
+
+
 def test_backup_finalised_and_temperature_choice_match():
     from hostsim_util import HostSim
     ct, eng = _setup('breakthroughSmall')
