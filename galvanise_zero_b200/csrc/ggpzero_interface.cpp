@@ -388,7 +388,7 @@ static PyObject* player_poll(PyPlayer* self, PyObject* args) {
     const int rows = gz_player_poll(self->p, n, ptrs.empty() ? nullptr : ptrs.data(), (int)ptrs.size(), &planes);
     if (rows < 0) return fail();
     if (rows == 0) Py_RETURN_NONE;
-    return planes_array(planes, (Py_ssize_t)gz_player_info(self->p, 0));
+    return planes_array(planes, (Py_ssize_t)rows * gz_player_info(self->p, 0));     // rows leaves, flat (common.cpp:200-218)
 }
 static PyMethodDef player_methods[] = {
     {"player_reset", (PyCFunction)player_reset, METH_VARARGS, "player_reset(game_depth)"},

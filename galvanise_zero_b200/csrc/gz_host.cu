@@ -227,7 +227,7 @@ struct gz_player {
     struct Cmd { int kind; std::vector<int> moves; std::vector<uint32_t> state; int evals; double end_time; };
     std::deque<Cmd> queue;      // kind: 1 reset, 2 apply, 3 search
     bool busy = false, fresh = false, first_play = false;
-    int current = 0, waiting = 0, game_depth = 0;
+    int current = 0, waiting = 0, game_depth = 0, rows = 1;
     double search_start = 0, search_end_time = -1;
     int stop_sent = 0;
     // the finished search
@@ -270,14 +270,16 @@ extern "C" int gz_player_create(gz_propnet* pn, gz_transformer* tr, const double
     p->n_rewards = (int)gz_puct_info(p->eng, 3);
     p->sw = (int)gz_puct_info(p->eng, 6);
     p->max_actions = (int)gz_puct_info(p->eng, 7);
+    p->rows = (int)gz_puct_info(p->eng, 10);       // leaves one poll may hand out: PuctConfig.batch_size (player.cpp:32)
+    const size_t EB = (size_t)p->rows;
     GZ_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    GZ_CUDA(cudaMalloc((void**)&p->d_policy, (size_t)p->policy_stride * 4));
-    GZ_CUDA(cudaMalloc((void**)&p->d_value, (size_t)p->n_rewards * 4));
-    GZ_CUDA(cudaMalloc((void**)&p->d_planes, (size_t)p->total * 4));
-    GZ_CUDA(cudaMemset(p->d_policy, 0, (size_t)p->policy_stride * 4));
-    GZ_CUDA(cudaMemset(p->d_value, 0, (size_t)p->n_rewards * 4));
-    GZ_CUDA(cudaHostAlloc((void**)&p->h_planes, (size_t)p->total * 4, cudaHostAllocDefault));
-    GZ_CUDA(cudaHostAlloc((void**)&p->h_row, (size_t)(p->policy_stride + p->n_rewards) * 4, cudaHostAllocDefault));
+    GZ_CUDA(cudaMalloc((void**)&p->d_policy, EB * p->policy_stride * 4));
+    GZ_CUDA(cudaMalloc((void**)&p->d_value, EB * p->n_rewards * 4));
+    GZ_CUDA(cudaMalloc((void**)&p->d_planes, EB * p->total * 4));
+    GZ_CUDA(cudaMemset(p->d_policy, 0, EB * p->policy_stride * 4));
+    GZ_CUDA(cudaMemset(p->d_value, 0, EB * p->n_rewards * 4));
+    GZ_CUDA(cudaHostAlloc((void**)&p->h_planes, EB * p->total * 4, cudaHostAllocDefault));
+    GZ_CUDA(cudaHostAlloc((void**)&p->h_row, EB * (p->policy_stride + p->n_rewards) * 4, cudaHostAllocDefault));
     p->ch_moves.resize(maxa); p->ch_trav.resize(maxa); p->ch_prob.resize(maxa); p->ch_score.resize(maxa); p->ch_next.resize(maxa);
     *out = p;
     return GZ_OK;
@@ -297,9 +299,9 @@ extern "C" void gz_player_destroy(gz_player* p) {
 }
 
 extern "C" gz_puct* gz_player_engine(gz_player* p) { return p ? p->eng : nullptr; }
-extern "C" int64_t gz_player_info(const gz_player* p, int what) {   // 0 plane row size, 1 roles, 2 max actions, 3 state words
+extern "C" int64_t gz_player_info(const gz_player* p, int what) {   // 0 plane row size, 1 roles, 2 max actions, 3 state words, 4 most rows per poll
     if (!p) return -1;
-    switch (what) { case 0: return p->total; case 1: return p->n_roles; case 2: return p->max_actions; case 3: return p->sw; default: return -1; }
+    switch (what) { case 0: return p->total; case 1: return p->n_roles; case 2: return p->max_actions; case 3: return p->sw; case 4: return p->rows; default: return -1; }
 }
 
 // puctPlayerReset (player.cpp:52-57)
@@ -428,8 +430,9 @@ static int player_watch_clock(gz_player* p) {
     return GZ_OK;
 }
 
-// Player::poll (player.cpp:155-173, common.cpp:160-218): returns 1 with *h_planes = the leaf to evaluate
-// ([total] float32, pinned, valid until the next poll), 0 when the queued work is done, or a negative gz_status.
+// Player::poll (player.cpp:155-173, common.cpp:160-218): returns n >= 1 with *h_planes = the n leaves to evaluate
+// ([n][total] float32, pinned, valid until the next poll; n <= PuctConfig.batch_size), 0 when the queued work is done,
+// or a negative gz_status. The next poll brings their n predictions (role r: [n][A_r], value: [n][rewards]).
 extern "C" int gz_player_poll(gz_player* p, int n_pred, const float* const* h_arrays, int n_arrays, const float** h_planes) {
     if (!p) { gz_set_error("null player"); return GZ_ERR_ARG; }
     if (n_pred != p->waiting) { gz_set_error("expected %d predictions, got %d", p->waiting, n_pred); return GZ_ERR_ARG; }
@@ -437,10 +440,15 @@ extern "C" int gz_player_poll(gz_player* p, int n_pred, const float* const* h_ar
     bool fresh = false;
     if (n_pred) {
         if (!h_arrays || n_arrays != p->n_roles + 1) { gz_set_error("expected %d policy arrays and one value array", p->n_roles); return GZ_ERR_ARG; }
-        for (int r = 0; r < p->n_roles; r++) memcpy(p->h_row + p->policy_off[r], h_arrays[r], (size_t)p->role_sizes[r] * 4);
-        memcpy(p->h_row + p->policy_stride, h_arrays[p->n_roles], (size_t)p->n_rewards * 4);
-        GZ_CUDA(cudaMemcpyAsync(p->d_policy, p->h_row, (size_t)p->policy_stride * 4, cudaMemcpyHostToDevice, p->stream));
-        GZ_CUDA(cudaMemcpyAsync(p->d_value, p->h_row + p->policy_stride, (size_t)p->n_rewards * 4, cudaMemcpyHostToDevice, p->stream));
+        // role r's array is [n_pred][A_r]; the engine reads rows of concatenated roles, then the value rows
+        float* hv = p->h_row + (size_t)p->rows * p->policy_stride;
+        for (int i = 0; i < n_pred; i++) {
+            for (int r = 0; r < p->n_roles; r++)
+                memcpy(p->h_row + (size_t)i * p->policy_stride + p->policy_off[r], h_arrays[r] + (size_t)i * p->role_sizes[r], (size_t)p->role_sizes[r] * 4);
+            memcpy(hv + (size_t)i * p->n_rewards, h_arrays[p->n_roles] + (size_t)i * p->n_rewards, (size_t)p->n_rewards * 4);
+        }
+        GZ_CUDA(cudaMemcpyAsync(p->d_policy, p->h_row, (size_t)n_pred * p->policy_stride * 4, cudaMemcpyHostToDevice, p->stream));
+        GZ_CUDA(cudaMemcpyAsync(p->d_value, hv, (size_t)n_pred * p->n_rewards * 4, cudaMemcpyHostToDevice, p->stream));
         fresh = true;
     }
     p->waiting = 0;
@@ -461,11 +469,12 @@ extern "C" int gz_player_poll(gz_player* p, int n_pred, const float* const* h_ar
         if (rc != GZ_OK) return rc;
         if (st[2] || st[0] < 0) { gz_set_error("device player failed: error %d, cmd_done %d", st[2], st[0]); return GZ_ERR_LIMIT; }
         if (st[3]) {
-            GZ_CUDA(cudaMemcpyAsync(p->h_planes, p->d_planes, (size_t)p->total * 4, cudaMemcpyDeviceToHost, p->stream));
+            // the rows a batch hands out are the first st[3] rows of the game, in requestor order
+            GZ_CUDA(cudaMemcpyAsync(p->h_planes, p->d_planes, (size_t)st[3] * p->total * 4, cudaMemcpyDeviceToHost, p->stream));
             GZ_CUDA(cudaStreamSynchronize(p->stream));
-            p->waiting = 1;
+            p->waiting = st[3];
             if (h_planes) *h_planes = p->h_planes;
-            return 1;
+            return st[3];
         }
         if (st[0] == 1) {
             p->busy = false;

@@ -77,7 +77,7 @@ puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_wo
     V.c = reinterpret_cast<GameCtl*>(ctl_sm[warp]);
     V.ord = ord_sm[warp];
     int32_t *gpn = V.pn, *gpc = V.pc;
-    if (cmem) {
+    if (cmem && E.EB == 1) {    // (intra-tree workers: every coroutine has its own path, in global memory)
         int32_t* spn = reinterpret_cast<int32_t*>(cmem + cache_words);
         int32_t* spc = spn + E.MAXD;
         const int pl = V.c->path_len;
@@ -89,7 +89,7 @@ puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_wo
     __syncwarp();
     // games that just played a move ask for their tree to be re-rooted: hand their ids to the re-root kernel
     if (lane == 0 && V.c->req == REQ_REROOT) rr_list[atomicAdd(rr_count, 1)] = g;
-    if (cmem) {
+    if (cmem && E.EB == 1) {
         const int pl = V.c->path_len;
         for (int i = lane; i < pl; i += 32) { gpn[i] = V.pn[i]; gpc[i] = V.pc[i]; }
     }
@@ -381,6 +381,17 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
         if (tr->policy_sizes[r] != E.role_sizes[r]) { gz_set_error("policy size of role %d: %d != %d actions", r, tr->policy_sizes[r], E.role_sizes[r]); delete h; return GZ_ERR_ARG; }
     int rc = gz_puct_set_config(h, sp_conf, puct_conf, rte_conf);
     if (rc != GZ_OK) { delete h; return rc; }
+    // evaluation rows per game: a Player's search hands up to PuctConfig.batch_size leaves of its tree to the network
+    // at once (player.cpp:27-36: the scheduler's batch is the configuration's); self-play keeps one per game
+    E.EB = 1;
+    if (mode == GZ_PUCT_MODE_PLAYER && E.conf.puct.batch_size > 1) {
+        if (E.conf.puct.batch_size > GZP_MAX_EB) {
+            gz_set_error("PuctConfig.batch_size %d: the device player runs at most %d playout coroutines per tree", E.conf.puct.batch_size, GZP_MAX_EB);
+            delete h;
+            return GZ_ERR_LIMIT;
+        }
+        E.EB = E.conf.puct.batch_size;
+    }
     E.tt_cap = 0;
     if (E.conf.puct.lookup_transpositions || E.conf.run_to_end.lookup_transpositions) {
         // transposition table (evaluator.cpp:52,144-173): load factor <= 1/2 of the node arena
@@ -499,6 +510,7 @@ extern "C" int64_t gz_puct_info(const gz_puct* h, int what) {
         case 7: return h->E.max_actions;
         case 8: return h->E.READYCAP;
         case 9: return h->split_goals ? 10 : 5;   // kernels of this library launched per engine step (sub_iters == 1)
+        case 10: return h->E.EB;                  // evaluation rows per game (planes / policy / value rows = G * EB)
         default: return -1;
     }
 }
@@ -600,7 +612,7 @@ static int advance_impl(gz_puct* h, const float* d_policy, const float* d_value,
     if (d_planes) {
         // every row is encoded (rows of games that do not wait for the network hold a stale but valid
         // state; their network outputs are never read)
-        rc = gz_encode_layout(h->tr, E.G, E.SW, E.x_state, E.x_in_state, E.x_prevcnt, 1, d_planes, plane_dtype,
+        rc = gz_encode_layout(h->tr, (int64_t)E.G * E.EB, E.SW, E.e_state, E.e_prev, E.e_prevcnt, 1, d_planes, plane_dtype,
                               h->plane_c_pad, stream);
         if (rc != GZ_OK) return rc;
     }
@@ -661,7 +673,7 @@ extern "C" int gz_puct_copy_need_eval(gz_puct* h, uint8_t* d_out, void* stream) 
     if (!h || !d_out) { gz_set_error("null argument"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(h->device));
     { int jrc = join_side(h, (cudaStream_t)stream); if (jrc != GZ_OK) return jrc; }
-    GZ_CUDA(cudaMemcpyAsync(d_out, h->E.x_need_eval, (size_t)h->E.G, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    GZ_CUDA(cudaMemcpyAsync(d_out, h->E.x_need_eval, (size_t)h->E.G * h->E.EB, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return GZ_OK;
 }
 
@@ -959,7 +971,9 @@ extern "C" int gz_puct_request_stop(gz_puct* h, int g, int mode, void* stream) {
 }
 __global__ void puct_status_kernel(const __grid_constant__ PuctEngine E, int g, int* out) {
     const GameCtl& c = E.ctl[g];
-    out[0] = c.cmd_done; out[1] = c.phase; out[2] = c.error; out[3] = E.x_need_eval[g];
+    int waiting = 0;                     // evaluation rows of this game handed to the network (rows g*EB .. + waiting)
+    for (int k = 0; k < E.EB; k++) waiting += E.x_need_eval[(int64_t)g * E.EB + k] != 0;
+    out[0] = c.cmd_done; out[1] = c.phase; out[2] = c.error; out[3] = waiting;
 }
 extern "C" int gz_puct_status(gz_puct* h, int g, int* h_out4, void* stream) {
     if (!h || !h_out4 || g < 0 || g >= h->E.G) { gz_set_error("bad argument"); return GZ_ERR_ARG; }

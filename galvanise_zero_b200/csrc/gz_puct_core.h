@@ -2225,7 +2225,7 @@ GZP_HD bool gzp_restart_after_error(GameView& V) {
 
 
 // playoutMain's list of break conditions (evaluator.cpp:782-841); true: the search is over.
-GZP_HDN bool gzp_search_over(GameView& V, const GzpNode& root_nd, GzpKid* root_kid, bool* have_kid) {
+GZP_HD bool gzp_search_over(GameView& V, const GzpNode& root_nd, GzpKid* root_kid, bool* have_kid) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     const PuctConf& cf = gzp_conf(V);
@@ -2290,7 +2290,7 @@ GZP_HD void gzp_co_save(GameView& V, int k) {
     GZP_SYNC();
 }
 
-GZP_HDN void gzp_sched_start(GameView& V) {       // Player::puctPlayerMove: one runnable, the search itself
+GZP_RARE void gzp_sched_start(GameView& V) {       // Player::puctPlayerMove: one runnable, the search itself
     GzpSched& S = V.E->sched[V.g];
     GZP_SYNC();
     S.n_run = 1; S.run[0] = 0; S.n_req = 0; S.n_yld = 0; S.current = -1;
@@ -2304,7 +2304,7 @@ GZP_HDN void gzp_sched_start(GameView& V) {       // Player::puctPlayerMove: one
 GZP_HD int gzp_co_loop_top(int k) { return k == 0 ? CO_MAIN_TOP : CO_WORKER_TOP; }
 
 // Runs coroutine k until it gives up the controller. Returns CO_R_*.
-GZP_HDN int gzp_co_run(GameView& V, int k) {
+GZP_RARE int gzp_co_run(GameView& V, int k) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     GzpSched& S = E->sched[V.g];
@@ -2446,7 +2446,7 @@ GZP_HDN int gzp_co_run(GameView& V, int k) {
 
 // NetworkScheduler::mainLoop for one game. Returns true when the engine step ends here for this game (a propnet
 // request is posted, the batch waits for the network, or the step's budget is spent); false when the search is over.
-GZP_HDN bool gzp_sched_run(GameView& V, bool nn_fresh) {
+GZP_RARE bool gzp_sched_run(GameView& V, bool nn_fresh) {
     const PuctEngine* E = V.E;
     GameCtl* c = V.c;
     GzpSched& S = E->sched[V.g];
@@ -2616,10 +2616,8 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
             break;
         }
         case PH_SEARCH: {
-            if (E->EB > 1) {                           // a Player's search: the coroutines of "Intra-tree workers"
-                if (gzp_sched_run(V, false)) return;
-                break;
-            }
+            if (E->EB > 1) return;                     // a Player's search with intra-tree workers: the next step's
+                                                       // gzp_sched_run (top of this function) takes it from here
             if (!c->in_playout) {
                 const int root = c->root;
                 const GzpNode root_nd = V.E->nodes[V.nb + root];

@@ -143,18 +143,20 @@ class PuctEngine(object):
         self.max_actions = info(7)
         self.ready_cap = info(8)
         self.kernels_per_step = info(9)
+        self.eval_rows = info(10)            # evaluation rows per game (a Player with PuctConfig.batch_size > 1)
+        rows = n_games * self.eval_rows     # row g * eval_rows + k = request k of game g
         self.plane_shape = plane_shape
         self.plane_c_pad = plane_c_pad
         if plane_c_pad:
             # channels-last, channel count padded: logical [G, c_pad, H, W] over [G, H, W, c_pad] memory
             self._L.gz_puct_set_plane_layout.argtypes = [ctypes.c_void_p, ctypes.c_int]
             _lib.check(self._L.gz_puct_set_plane_layout(self._h, plane_c_pad))
-            mem = torch.zeros((n_games, plane_shape[1], plane_shape[2], plane_c_pad), dtype=plane_dtype, device=self.device)
+            mem = torch.zeros((rows, plane_shape[1], plane_shape[2], plane_c_pad), dtype=plane_dtype, device=self.device)
             self.planes = mem.permute(0, 3, 1, 2)
         else:
-            self.planes = torch.zeros((n_games,) + tuple(plane_shape), dtype=plane_dtype, device=self.device)
-        self.policy = torch.zeros((n_games, self.policy_stride), dtype=torch.float32, device=self.device)
-        self.value = torch.zeros((n_games, self.n_rewards), dtype=torch.float32, device=self.device)
+            self.planes = torch.zeros((rows,) + tuple(plane_shape), dtype=plane_dtype, device=self.device)
+        self.policy = torch.zeros((rows, self.policy_stride), dtype=torch.float32, device=self.device)
+        self.value = torch.zeros((rows, self.n_rewards), dtype=torch.float32, device=self.device)
         self._fresh = False
         self.role_sizes = list(role_sizes)
 

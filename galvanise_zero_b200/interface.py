@@ -357,9 +357,12 @@ class Player(object):
     configuration's ``think_time`` are honoured (the host watches the clock and tells the device search to stop
     at its next playout boundary, ``evaluator.cpp:794,820-826``).
 
-    Differences from the reference: one outstanding evaluation per tree whatever
-    ``batch_size`` says; ``player_balance_moves`` is accepted and does nothing; ``player_tree_debug`` reports
-    no variation lines."""
+    ``PuctConfig.batch_size`` > 1 (the reference's default is 32) runs the reference's intra-tree workers: a poll
+    hands out up to ``batch_size`` leaves of the one tree and expects as many predictions back
+    (``evaluator.cpp:722-742,1050-1079``, ``scheduler.cpp:131-203``).
+
+    Differences from the reference (DESIGN.md §7): ``player_balance_moves`` is accepted and does nothing;
+    ``player_tree_debug`` reports no variation lines."""
 
     def __init__(self, sm, c_transformer, puct_conf_dict, device=0, seed=0x5EED0001, node_cap=1 << 16,
                  child_cap=None):
@@ -387,6 +390,7 @@ class Player(object):
         self.total_size = int(L.gz_player_info(h, 0))
         self.state_words = int(L.gz_player_info(h, 3))
         self.max_actions = int(L.gz_player_info(h, 2))
+        self.rows_per_poll = int(L.gz_player_info(h, 4))      # PuctConfig.batch_size (most leaves one poll hands out)
         self.engine = PuctEngine.from_handle(L.gz_player_engine(h), device, self.n_bases, self.role_sizes,
                                              (c_transformer.num_channels, c_transformer.channel_size, 1),
                                              mode=PuctEngine.MODE_PLAYER, plane_dtype=torch.float32, sm=self.sm)
@@ -485,5 +489,5 @@ class Player(object):
         if n == 0:
             return None
         if self._planes_np is None:
-            self._planes_np = np.ctypeslib.as_array(self._planes_ptr, shape=(self.total_size,))
-        return self._planes_np
+            self._planes_np = np.ctypeslib.as_array(self._planes_ptr, shape=(self.rows_per_poll * self.total_size,))
+        return self._planes_np[:n * self.total_size]        # n leaves, flat (PuctConfig.batch_size at most)

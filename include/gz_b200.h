@@ -269,7 +269,7 @@ int gz_player_create(gz_propnet* pn, gz_transformer* tr, const double* puct_conf
                      int child_cap, gz_player** out);
 void gz_player_destroy(gz_player* p);
 gz_puct* gz_player_engine(gz_player* p);
-int64_t gz_player_info(const gz_player* p, int what);         /* 0 plane row, 1 roles, 2 max actions, 3 state words */
+int64_t gz_player_info(const gz_player* p, int what);         /* 0 plane row, 1 roles, 2 max actions, 3 state words, 4 most rows per poll */
 int gz_player_reset(gz_player* p, int game_depth);
 int gz_player_update_config(gz_player* p, double think_time, int converged_visits, int verbose);
 int gz_player_apply_move(gz_player* p, const int* joint_move, int n_roles);

@@ -127,8 +127,9 @@ class _SynthNN(object):
         return out + [np.ascontiguousarray(val)]
 
 
-@pytest.mark.parametrize('game,evals,moves', [('reversi', 150, 12), ('breakthroughSmall', 200, 10)])
-def test_play_poller_matches_reference_search(game, evals, moves):
+@pytest.mark.parametrize('game,evals,moves,batch', [('reversi', 150, 12, 1), ('breakthroughSmall', 200, 10, 1),
+                                                    ('reversi', 300, 10, 32), ('breakthroughSmall', 400, 12, 8)])
+def test_play_poller_matches_reference_search(game, evals, moves, batch):
     """PUCTPlayer's call sequence (src/ggpzero/player/puctplayer.py:60-95) through PlayPoller /
     ggpzero_interface.Player against the reference's PuctEvaluator (oracle/_ref), same synthetic
     network: identical root visit counts, choices and reported scores, move after move."""
@@ -137,10 +138,13 @@ def test_play_poller_matches_reference_search(game, evals, moves):
         pytest.skip('oracle/_ref missing')
     gi = lookup.by_name(game)
     tr = bases.GdlBasesTransformer(gi, datadesc.generation_for(game))
-    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits')
+    # batch > 1: the reference's intra-tree workers (PUCTEvaluatorConfig.batch_size, default 32) — every poll hands
+    # out up to `batch` leaves of the one tree (evaluator.cpp:722-742,1050-1079)
+    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits', batch_size=batch)
     nn = _SynthNN(tr)
     sm = gi.get_sm()
-    poller = cppinterface.PlayPoller(sm, nn, conf)
+    # (the in-flight discount of select draws random numbers: same generator seed as the reference harness)
+    poller = cppinterface.PlayPoller(sm, nn, conf, seed=0x5EED0000)
     ref = gzref.RefEngine(tables.blob_by_name(game), poller.c_transformer).search(conf, evals, n_moves=moves)
     assert len(ref) > 3
 
@@ -177,7 +181,7 @@ def test_play_poller_matches_reference_search(game, evals, moves):
         nxt = sm.new_base_state()
         sm.next_state(jm, nxt)
         state = nxt
-    assert nn.calls > evals
+    assert nn.calls > (evals if batch == 1 else evals // batch)
 
 
 def test_supervisor_poller_wrapper_collects_samples():

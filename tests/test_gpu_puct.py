@@ -101,6 +101,31 @@ def test_device_search_with_transposition_lookup_matches_reference(game, evals, 
         assert eng.totals()['transpositions'] > 10
 
 
+@pytest.mark.parametrize('game,evals,moves,batch,tt,noise', [
+    ('breakthroughSmall', 400, 16, 8, False, -1), ('reversi', 600, 10, 32, False, -1),
+    ('reversi', 300, 12, 4, False, 0.25), ('breakthrough', 500, 10, 16, True, -1),
+    ('connect6', 200, 3, 32, False, -1), ('amazons_10x10', 150, 2, 8, False, -1)])
+def test_device_search_with_intra_tree_workers_matches_reference(game, evals, moves, batch, tt, noise):
+    """PuctConfig.batch_size > 1: playoutMain + batch_size - 1 playoutWorker coroutines on one tree, leaves evaluated
+    in batches of up to batch_size rows per game (evaluator.cpp:722-742,1050-1079; scheduler.cpp:131-203). The
+    reference is run with its scheduler's batch = the configuration's, as Player does (player.cpp:27-36)."""
+    from galvanise_zero_b200.engine import PuctEngine
+    conf = confs.base_puct_config(dirichlet_noise_pct=noise, choose='choose_top_visits', batch_size=batch,
+                                  lookup_transpositions=tt)
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    eng = PuctEngine(game, sp, n_games=1, mode=1, node_cap=1 << 14, child_cap=1 << 21, plane_dtype=torch.float32)
+    assert eng.eval_rows == batch and eng.planes.shape[0] == batch
+    ref = gzref.RefEngine(tables.blob_by_name(game), eng.c_transformer).search(conf, evals, n_moves=moves,
+                                                                               max_children=4096)
+    mine = _device_search(eng, evals, moves)
+    assert len(mine) == len(ref)
+    for a, b in zip(ref, mine):
+        assert np.array_equal(a['moves'], b['moves'])
+        assert np.array_equal(a['traversals'], b['traversals'])
+        assert a['choice'] == b['choice'] and a['root_visits'] == b['root_visits']
+
+
 def test_device_selfplay_with_transposition_lookup_matches_reference():
     _device_selfplay('breakthroughSmall', 8, 40, 150, False, True, transpositions=True)
 
