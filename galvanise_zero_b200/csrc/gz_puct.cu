@@ -85,8 +85,18 @@ puct_pre_kernel(const __grid_constant__ PuctEngine E, int nn_fresh, int cache_wo
         __syncwarp();
         V.pn = spn; V.pc = spc;
     }
+    const long long dbg_t0 = E.dbg_cycles ? clock64() : 0;
+    const int dbg_phase0 = V.c->phase;
+    const unsigned long long dbg_po0 = V.c->total_playouts, dbg_mv0 = V.c->total_moves;
     gzp_step_pre(V, nn_fresh != 0);
     __syncwarp();
+    if (E.dbg_cycles && lane == 0) {
+        long long* d = E.dbg_cycles + (int64_t)g * 4;
+        d[0] = clock64() - dbg_t0;
+        d[1] = dbg_phase0 * 256 + V.c->phase;
+        d[2] = (long long)(V.c->total_playouts - dbg_po0);
+        d[3] = (long long)(V.c->total_moves - dbg_mv0) * 65536 + V.c->path_len * 256 + (V.c->req & 255);
+    }
     // games that just played a move ask for their tree to be re-rooted: hand their ids to the re-root kernel
     if (lane == 0 && V.c->req == REQ_REROOT) rr_list[atomicAdd(rr_count, 1)] = g;
     if (cmem && E.EB == 1) {
@@ -372,9 +382,14 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     E.READYCAP = ready_cap > 0 ? ready_cap : 1 << 16;
     E.uniq_cap = 1 << 20;
     E.max_iters_per_step = 16;
-    // self-play: measured on reversi, 6-8 levels give the best moves/s (bench.py --max-work); a single player tree
-    // has nobody to wait for
-    E.max_work_per_step = mode == 0 ? 8 : 1 << 20;
+    // self-play: the slowest warp sets the duration of puct_pre_kernel for all games (end-game trees run playout
+    // after playout into terminal nodes without ever needing the pipeline: 8 playouts = 210 us against 40 us for
+    // a game that descends once). Budget in tree levels, forced moves included, plus 2 per finished playout;
+    // measured on reversi (bench.py --max-work, steady state): 6 -> 13.95 K, 12 -> 14.06 K, 24 -> 13.29 K,
+    // 40 -> 12.52 K moves/s. A single player tree has nobody to wait for.
+    E.max_work_per_step = mode == 0 ? 12 : 1 << 20;
+    { const char* pf = getenv("GZ_PUCT_PREFETCH"); E.prefetch_nodes = (pf && pf[0] == '0') ? 0 : 1; }   // measurement switch
+    E.dbg_cycles = nullptr;
     E.seed = seed;
     if ((int)tr->policy_sizes.size() != E.R) { gz_set_error("transformer policy heads != roles"); delete h; return GZ_ERR_ARG; }
     for (int r = 0; r < E.R; r++)
@@ -663,6 +678,14 @@ extern "C" int gz_puct_advance_timed(gz_puct* h, const float* d_policy, const fl
 extern "C" int gz_puct_set_plane_layout(gz_puct* h, int c_pad) {
     if (!h || c_pad < 0 || (c_pad & 7) || (c_pad && c_pad < h->tr->E.total / h->tr->E.channel_size)) { gz_set_error("bad plane layout"); return GZ_ERR_ARG; }
     h->plane_c_pad = c_pad;
+    return GZ_OK;
+}
+
+// Measurement aid: d_buf = device int64 [G][4] or null; every puct_pre_kernel launch then records, per game, the
+// cycles its warp spent, entry / exit phase, playouts finished and moves played in that step.
+extern "C" int gz_puct_set_debug_cycles(gz_puct* h, long long* d_buf) {
+    if (!h) { gz_set_error("null engine"); return GZ_ERR_ARG; }
+    h->E.dbg_cycles = d_buf;
     return GZ_OK;
 }
 

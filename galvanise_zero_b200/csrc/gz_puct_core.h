@@ -267,6 +267,8 @@ struct PuctEngine {
     // pass, and the slowest warp sets the duration of the step for all games.
     int max_iters_per_step;
     int max_work_per_step;
+    int prefetch_nodes;       // device select: prefetch the node records of a node's expanded children (gzp_warp_load_kid)
+    long long* dbg_cycles;    // measurement aid (gz_puct_set_debug_cycles): per game [cycles in puct_pre_kernel, entry/exit phase, playouts, moves]
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -942,6 +944,12 @@ __device__ __forceinline__ GzpKid gzp_warp_load_kid(const GameView& V, int c0, i
     K.visits = K.expanded ? k.c_visits : 0u;
     K.flags = K.expanded ? (int)k.c_flags : 0;
     K.inflight = K.expanded ? (int)k.c_inflight : 0;
+    // Whichever child select picks, the next tree level starts with that child's node record: every lane asks L2
+    // for its own child's record now, so that the DRAM round trip runs under the select arithmetic instead of
+    // after it (one of the two dependent round trips per level; 64 bytes per expanded child of extra traffic on a
+    // path that uses 3 % of the DRAM bandwidth).
+    if (K.expanded && V.E->prefetch_nodes)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(V.E->nodes + V.nb + k.c_to));
     if (gzp_direct_stats(V.E) && K.expanded) {     // the record's copy may be stale, read the node
         const GzpNode& t = V.E->nodes[V.nb + k.c_to];
         K.score = t.score[lead < 0 ? 0 : lead];
@@ -1294,6 +1302,14 @@ GZP_HDN int gzp_select_child(GameView& V, int n, const GzpNode& nd, GzpSelInfo* 
     const uint32_t node_visits = nd.n_visits;
     const int node_inflight = nd.n_inflight;
     if (info) { info->to = -1; info->inflight = node_inflight; info->yield_first = 0; info->blocked = 0; }
+    c->total_sel_nodes++;
+    c->total_sel_children += (uint64_t)nc;
+    V.work++;                 // the step's work budget counts every tree level, forced moves included
+    if (nc == 1) {
+        pn[c->path_len] = n; pc[c->path_len] = 0; c->path_len++;
+        if (info) info->to = CHILD(c_to, c0);
+        return 0;
+    }
     float node_finals[GZP_MAX_ROLES];
 #pragma unroll
     for (int r = 0; r < GZP_MAX_ROLES; r++) node_finals[r] = nd.final_[r];
@@ -1305,14 +1321,6 @@ GZP_HDN int gzp_select_child(GameView& V, int n, const GzpNode& nd, GzpSelInfo* 
         pcst += k;
         puct_c = pcst;        // (the reference also stores it in the node, for its tree dump only)
     }
-    c->total_sel_nodes++;
-    c->total_sel_children += (uint64_t)nc;
-    if (nc == 1) {
-        pn[c->path_len] = n; pc[c->path_len] = 0; c->path_len++;
-        if (info) info->to = CHILD(c_to, c0);
-        return 0;
-    }
-    V.work++;
 #ifdef __CUDA_ARCH__
     // warp path (children in registers) unless this is the root select that has to draw Dirichlet noise first
     if (nc <= 32 && V.ord && E->EB == 1 &&
@@ -2121,6 +2129,7 @@ GZP_HDN void gzp_finish_playout(GameView& V, const GzpNode& leaf) {
     c->num_tree_playouts++;
     c->total_playouts++;
     c->in_playout = 0;
+    V.work += 2;              // the fixed cost of a playout (convergence check, backup) in tree levels, roughly
 }
 
 GZP_HDN void gzp_path_push(GameView& V, int n, int choice) {

@@ -215,6 +215,9 @@ int gz_puct_totals(gz_puct* h, double* h_out26, void* stream);
  * positions) at game depth 0 instead of the initial state — what handing SelfPlay another `initial_state`
  * (src/cpp/selfplaymanager.cpp:140, selfplay.cpp:313) does in the reference. Later games start normally. */
 int gz_puct_set_start_states(gz_puct* h, const uint32_t* d_states, void* stream);
+/* Measurement aid: d_buf = device int64 [G][4] (or null to stop): per game the cycles its warp spent in the last
+ * puct_pre_kernel launch, entry*256+exit phase, playouts finished, moves*65536 + path_len*256 + request. */
+int gz_puct_set_debug_cycles(gz_puct* h, long long* d_buf);
 /* Per engine step a game runs until it needs the batch pipeline (a propnet pass / the network), but at most
  * `max_iters` controller iterations and `max_work` tree levels descended (playouts that end in terminal or
  * finalised nodes need no pipeline pass; the slowest game sets the duration of the step). Defaults 16 / 8.

@@ -103,6 +103,8 @@ extern "C" void* hs_create(const int32_t* blob, int64_t n_words, int G, int mode
     E.uniq_cap = 1 << 16;
     E.max_iters_per_step = 64;
     E.max_work_per_step = 1 << 20;
+    E.prefetch_nodes = 0;
+    E.dbg_cycles = nullptr;
     fill_sp(E.conf, sp_conf);
     fill_conf(E.conf.puct, puct_conf);
     fill_conf(E.conf.run_to_end, rte_conf);
