@@ -168,7 +168,9 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
     peaks = load_peaks()
     steps = steps or args.steps
     game = (args.game if args.workload == 'propnet' else '') or PROPNET_GAME
-    dev = DeviceStateMachine(game, device=local, goals_mode=gzlib.GOALS_ALWAYS)
+    # goal values for terminal states only: what the reference's path reads (src/cpp/puct/node.cpp:153-221; its
+    # random playouts, src/cpp/pyobjects/gdltransformer_impl.cpp:50-124, read none at all)
+    dev = DeviceStateMachine(game, device=local, goals_mode=gzlib.GOALS_TERMINAL_ONLY)
     if args.group_min_batch is not None:
         dev.set_group_min_batch(args.group_min_batch)
     n = (args.slots if args.workload == 'propnet' else 0) or PROPNET_SLOTS
@@ -208,14 +210,38 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
     launch_s = (ms * 1e-3) / steps
     achieved = per_launch_bytes / launch_s / 1e9
     spec = dev.specialised and n >= (1 << 18)
+    ps = dev.program_stats
+    wide = ps['wide']
+    # the group kernel is the default for wide-format games from 1024 states up; others only when asked
+    group_used = (not spec) and ((args.group_min_batch is None and wide and n >= 1024) or
+                                 (args.group_min_batch is not None and 0 <= args.group_min_batch <= n))
+    # ---- the secondary bound: gate work. A table-driven kernel evaluates the next-state cone and
+    # the legal / terminal cone once per 32-game tile (the goal cone only for tiles holding a terminal state): one
+    # warp instruction handles 32 literals (lane = gate) of 32 games (bit-sliced word), and a literal costs about 3
+    # of them (program word, value word, combine) plus ~10 per 32-gate chunk. The specialised kernel's count is
+    # measured (ncu, profiles/r01b_propnet_spec_kernel_ncu_full.md: 66.9 M warp instructions per 2^21 transitions).
+    SM_COUNT, SCHED_PER_SM, SM_HZ = 148, 4, 1.965e9
+    issue_rate = SM_COUNT * SCHED_PER_SM * SM_HZ                       # warp instructions / s, whole GPU
+    lits = ps['literals'][0] + ps['literals'][1]
+    chunks = ps['chunks'][0] + ps['chunks'][1]
+    if spec:
+        wi_per_transition, wi_src = 66.9e6 / (1 << 21), 'ncu smsp__inst_executed.sum of the specialised kernel'
+    else:
+        wi_per_transition, wi_src = (3.0 * lits / 32 + 10.0 * chunks) / 32, 'model: 3 warp instructions per 32 literals + 10 per chunk, per 32-game tile'
+    issue_bound = issue_rate / wi_per_transition
+    compute = {'bound': 'issue', 'gates': ps['gates'], 'literals': ps['literals'], 'chunks': ps['chunks'],
+               'warp_instructions_per_transition': wi_per_transition, 'source': wi_src,
+               'peak': issue_bound, 'unit': 'transitions/s', 'achieved': value, 'frac': value / (issue_bound * world),
+               'note': 'next-state + legal/terminal cones (the goal cone runs only for tiles with a terminal state); '
+                       'peak = %d SMs x %d schedulers x %.3f GHz / warp instructions per transition, per GPU' % (SM_COUNT, SCHED_PER_SM, SM_HZ / 1e9)}
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                 'frac': achieved / peaks['hbm_gbs'],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^21 slots (ncu --set full)
                 'traffic': (PROPNET_SPEC_NCU_TRAFFIC_BYTES if spec else PROPNET_TABLE_NCU_TRAFFIC_BYTES) if (n == PROPNET_SLOTS and game == PROPNET_GAME) else None,
                 'kernel': 'spec_kernel<GzSpec_%s, PLAYOUT> (game-specialised, thread-sliced)' % game if spec
                           else ('pn_group_kernel<MODE_PLAYOUT> (1024 games per CTA / cluster, one tile per lane)'
-                                if (args.group_min_batch is None or 0 <= args.group_min_batch <= n) and n >= 1024
-                                else ('pn_wide_kernel<MODE_PLAYOUT>' if dev.launch_info['smem_bytes'] == 0
+                                if group_used
+                                else ('pn_wide_kernel<MODE_PLAYOUT>' if wide
                                       else 'pn_kernel<MODE_PLAYOUT> (table-driven)')),
                 'bytes_per_unit': tb, 'units_per_launch': n, 'launch_ms': launch_s * 1e3,
                 'peak_source': peaks['source'] + ' (HBM copy)',
@@ -308,7 +334,7 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
                            n * (dev.state_words * 4 + dev.legal_words * 4 + 1 + dev.n_roles) / 1e6),
                        'parallelism': 'games sharded across %d GPU(s), no collective' % world,
                        'launch': dev.launch_info},
-            'roofline': roofline, 'encoder_roofline': encoder, 'cpu_baseline': cpu, 'e2e': e2e,
+            'roofline': roofline, 'compute_roofline': compute, 'encoder_roofline': encoder, 'cpu_baseline': cpu, 'e2e': e2e,
             'gpu_launches': steps, 'clocks': clocks,
         }
         return line

@@ -523,6 +523,10 @@ struct gz_propnet {
     std::vector<std::pair<cudaStream_t, uint32_t*>> wide_scratch;
     int wide_grid = 0;
     int64_t wide_stride = 0;
+    // deferred goal pass (deferred_goals): compacted copies of the terminal states of a batch, per launching stream
+    struct GoalScratch { cudaStream_t st; int64_t cap; void* mem; };
+    std::vector<GoalScratch> goal_scratch;
+    int64_t deferred_goals_min_batch = 4096;
 };
 
 extern "C" int gz_version(void) { return 100; }
@@ -775,6 +779,7 @@ extern "C" void gz_propnet_destroy(gz_propnet* pn) {
     if (pn->d_scratch) cudaFree(pn->d_scratch);
     for (auto& ws : pn->wide_scratch) cudaFree(ws.second);
     for (auto& ws : pn->group_scratch) cudaFree(ws.second);
+    for (auto& gs : pn->goal_scratch) cudaFree(gs.mem);
     if (pn->d_group_tables) cudaFree(pn->d_group_tables);
     if (pn->host_stream) cudaStreamDestroy(pn->host_stream);
     delete pn;
@@ -947,6 +952,10 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
     return GZ_OK;
 }
 
+static bool use_deferred_goals(const gz_propnet* pn, int64_t n, int goals_mode);
+static int deferred_goals(gz_propnet* pn, int64_t n, const uint32_t* states, const uint8_t* terminal, uint8_t* goals,
+                          void* stream);
+
 extern "C" int gz_sm_eval(gz_propnet* pn, int64_t n, const uint32_t* d_states, uint32_t* d_legal,
                           uint8_t* d_terminal, uint8_t* d_goals, int goals_mode, void* stream) {
     return launch<MODE_EVAL>(pn, n, 0, d_states, nullptr, nullptr, d_legal, d_terminal, d_goals, nullptr,
@@ -956,8 +965,108 @@ extern "C" int gz_sm_eval(gz_propnet* pn, int64_t n, const uint32_t* d_states, u
 extern "C" int gz_sm_transition(gz_propnet* pn, int64_t n, const uint32_t* d_states, const int16_t* d_moves,
                                 uint32_t* d_next, uint32_t* d_legal, uint8_t* d_terminal, uint8_t* d_goals,
                                 int goals_mode, void* stream) {
+    if (pn && use_deferred_goals(pn, n, goals_mode)) {
+        int rc = launch<MODE_TRANSITION>(pn, n, 0, d_states, d_moves, d_next, d_legal, d_terminal, d_goals,
+                                         nullptr, nullptr, 0, 0, GZ_GOALS_NEVER_INTERNAL, stream);
+        if (rc != GZ_OK) return rc;
+        return deferred_goals(pn, n, d_next, d_terminal, d_goals, stream);
+    }
     return launch<MODE_TRANSITION>(pn, n, 0, d_states, d_moves, d_next, d_legal, d_terminal, d_goals,
                                    nullptr, nullptr, 0, 0, goals_mode, stream);
+}
+
+// ---- deferred goal pass ---------------------------------------------------------------------------
+// The reference reads goal values only of terminal states (src/cpp/puct/node.cpp:153-221; its random playouts,
+// src/cpp/pyobjects/gdltransformer_impl.cpp:50-124, never do). A bit-sliced kernel evaluates a cone for the whole
+// 32-game tile as soon as ONE game of the tile needs it, and reversi's goal cone (piece counting: 596 of its 795
+// chunks, too large to stage in shared memory) then costs more than everything else together: with games at all
+// plies at once 40 % of the tiles hold a terminal state although 1.7 % of the games do. For goals_mode
+// GZ_GOALS_TERMINAL_ONLY and a game with a deep goal cone the main pass therefore skips the cone, and the terminal
+// states of the batch are compacted, evaluated as dense tiles and their goal values scattered back — the same
+// values, 20x less goal work (the PUCT engine does the same inside its step, gz_puct.cu).
+__global__ void dg_compact_kernel(const uint8_t* __restrict__ terminal, int64_t n, int* __restrict__ idx,
+                                  int* __restrict__ count) {
+    // unordered compaction: one atomic per warp
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~(int64_t)31; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + lane;
+        const bool t = i < n && terminal[i] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, t);
+        if (!m) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (t) idx[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    }
+}
+__global__ void dg_gather_kernel(const uint32_t* __restrict__ states, const int* __restrict__ idx,
+                                 const int* __restrict__ count, int SW, uint32_t* __restrict__ out) {
+    const int64_t total = (int64_t)*count * SW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / SW;
+        out[i] = states[(int64_t)idx[r] * SW + (i - r * SW)];
+    }
+}
+__global__ void dg_scatter_kernel(const uint8_t* __restrict__ t_goals, const int* __restrict__ idx,
+                                  const int* __restrict__ count, int R, uint8_t* __restrict__ goals) {
+    const int64_t total = (int64_t)*count * R;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / R;
+        goals[(int64_t)idx[r] * R + (i - r * R)] = t_goals[i];
+    }
+}
+
+static bool use_deferred_goals(const gz_propnet* pn, int64_t n, int goals_mode) {
+    return goals_mode == GZ_GOALS_TERMINAL_ONLY && pn->P.chunks[2] >= 64 && pn->deferred_goals_min_batch >= 0 &&
+           n >= pn->deferred_goals_min_batch && !(pn->spec && pn->spec_min_batch >= 0 && n >= pn->spec_min_batch);
+}
+
+// goal values of the terminal states among `states` (flags in `terminal`), written into `goals`
+static int deferred_goals(gz_propnet* pn, int64_t n, const uint32_t* states, const uint8_t* terminal, uint8_t* goals,
+                          void* stream) {
+    const PnParams& P = pn->P;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_idx = al((size_t)n * 4), b_cnt = 256, b_states = al((size_t)n * P.state_words * 4),
+                 b_legal = al((size_t)n * P.legal_words * 4), b_term = al((size_t)n), b_goals = al((size_t)n * P.n_roles);
+    uint8_t* mem = nullptr;
+    {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& gs : pn->goal_scratch)
+            if (gs.st == st && gs.cap >= n) mem = (uint8_t*)gs.mem;
+        if (!mem) {
+            const size_t bytes = b_idx + b_cnt + b_states + b_legal + b_term + b_goals;
+            cudaError_t e = cudaMalloc((void**)&mem, bytes);
+            if (e != cudaSuccess) { gz_set_error("cudaMalloc of %.1f MB for the deferred goal pass failed: %s", bytes / 1e6, cudaGetErrorString(e)); return GZ_ERR_CUDA; }
+            pn->goal_scratch.push_back({st, n, mem});
+        }
+    }
+    int* d_idx = (int*)mem;
+    int* d_count = (int*)(mem + b_idx);
+    uint32_t* t_states = (uint32_t*)(mem + b_idx + b_cnt);
+    uint32_t* t_legal = (uint32_t*)(mem + b_idx + b_cnt + b_states);
+    uint8_t* t_term = mem + b_idx + b_cnt + b_states + b_legal;
+    uint8_t* t_goals = t_term + b_term;
+    GZ_CUDA(cudaMemsetAsync(d_count, 0, 4, st));
+    const int cgrid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)pn->n_sms * 8);
+    dg_compact_kernel<<<cgrid, 256, 0, st>>>(terminal, n, d_idx, d_count);
+    dg_gather_kernel<<<pn->n_sms * 4, 256, 0, st>>>(states, d_idx, d_count, P.state_words, t_states);
+    GZ_CUDA(cudaGetLastError());
+    int rc = launch<MODE_EVAL>(pn, n, 0, t_states, nullptr, nullptr, t_legal, t_term, t_goals, nullptr, nullptr, 0, 0,
+                               GZ_GOALS_ALWAYS, stream, nullptr, d_count);
+    if (rc != GZ_OK) return rc;
+    dg_scatter_kernel<<<pn->n_sms * 2, 256, 0, st>>>(t_goals, d_idx, d_count, P.n_roles, goals);
+    GZ_CUDA(cudaGetLastError());
+    return GZ_OK;
+}
+
+// Batches of at least `min_batch` states of a game with a deep goal cone evaluate it in a compacted second pass when
+// goals are wanted for terminal states only (default 4096; < 0: never).
+extern "C" int gz_propnet_set_deferred_goals_min_batch(gz_propnet* pn, int64_t min_batch) {
+    if (!pn) { gz_set_error("null propnet"); return GZ_ERR_ARG; }
+    pn->deferred_goals_min_batch = min_batch;
+    return GZ_OK;
 }
 
 // Internal (not part of the C-ABI): wide games evaluated with a caller-owned scratch region of
@@ -991,6 +1100,12 @@ extern "C" int gz_sm_playout_step(gz_propnet* pn, int64_t slot0, int64_t n, uint
                                   uint32_t* d_states, uint32_t* d_legal, uint8_t* d_terminal,
                                   uint8_t* d_goals, int16_t* d_moves_out,
                                   unsigned long long* d_transitions, int goals_mode, void* stream) {
+    if (pn && use_deferred_goals(pn, n, goals_mode)) {
+        int rc = launch<MODE_PLAYOUT>(pn, n, slot0, d_states, nullptr, d_states, d_legal, d_terminal, d_goals,
+                                      d_moves_out, d_transitions, seed, step, GZ_GOALS_NEVER_INTERNAL, stream);
+        if (rc != GZ_OK) return rc;
+        return deferred_goals(pn, n, d_states, d_terminal, d_goals, stream);
+    }
     return launch<MODE_PLAYOUT>(pn, n, slot0, d_states, nullptr, d_states, d_legal, d_terminal, d_goals,
                                 d_moves_out, d_transitions, seed, step, goals_mode, stream);
 }

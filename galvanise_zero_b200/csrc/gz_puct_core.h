@@ -1501,10 +1501,12 @@ GZP_RARE void gzp_backup_generic(GameView& V, float* new_scores) {
             int best = -1, win = -1;
             bool more = false;
             const int nc = nd.n_nchild;
+            const bool direct = gzp_direct_stats(V.E);    // shared nodes: the records' copies may be stale
             for (int i = 0; i < nc; i++) {
                 const GzpChild& k = kids[i];
-                if (k.c_to >= 0 && (k.c_flags & NF_FINALISED)) {
-                    const float s = k.c_score;
+                const bool fin = k.c_to >= 0 && (direct ? (NODE(n_flags, k.c_to) & NF_FINALISED) != 0 : (k.c_flags & NF_FINALISED) != 0);
+                if (fin) {
+                    const float s = direct ? NSCORE(k.c_to, lead) : k.c_score;
                     if (s > 0.99) { win = i; break; }
                     if (s > best_s) { best_s = s; best = i; }
                 } else {

@@ -37,6 +37,14 @@ class DeviceStateMachine:
         blob = np.ascontiguousarray(devprog.pack_device_program(self.propnet), dtype=np.int32)
         h = ctypes.c_void_p()
         _lib.check(self._L.gz_propnet_create(blob.ctypes.data, len(blob), device, ctypes.byref(h)))
+        # size of the three gate programs (next-state cone A, legal/terminal cone LT, goal cone GL): the work a
+        # transition costs whatever the bytes it moves (bench.py reports the issue-rate bound from these)
+        self.program_stats = {
+            'gates': [int(blob[devprog.D_N_GATES_A]), int(blob[devprog.D_N_GATES_LT]), int(blob[devprog.D_N_GATES_GL])],
+            'literals': [int(blob[devprog.D_N_LITS_A]), int(blob[devprog.D_N_LITS_LT]), int(blob[devprog.D_N_LITS_GL])],
+            'chunks': [int(blob[devprog.D_CHUNKS_A]), int(blob[devprog.D_CHUNKS_LT]), int(blob[devprog.D_CHUNKS_GL])],
+            'wide': bool(blob[devprog.D_WIDE]),
+        }
         self._h = h
         info = lambda w: int(self._L.gz_propnet_info(self._h, w))  # noqa: E731
         self.n_bases = info(_lib.INFO_N_BASES)
@@ -65,6 +73,12 @@ class DeviceStateMachine:
         default 1024; < 0 disables, 0 forces it for every batch)."""
         self._L.gz_propnet_set_group_min_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         _lib.check(self._L.gz_propnet_set_group_min_batch(self._h, int(n)))
+
+    def set_deferred_goals_min_batch(self, n: int):
+        """GOALS_TERMINAL_ONLY on a game with a deep goal cone: batches of at least ``n`` states evaluate the cone in a
+        compacted second pass over the terminal states only (default 4096; < 0 disables)."""
+        self._L.gz_propnet_set_deferred_goals_min_batch.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        _lib.check(self._L.gz_propnet_set_deferred_goals_min_batch(self._h, int(n)))
 
     def set_spec_min_batch(self, n: int):
         """Batches of at least ``n`` states use the game-specialised kernel (default 2^18; < 0 disables)."""

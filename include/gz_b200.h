@@ -68,6 +68,15 @@ int64_t gz_propnet_info(const gz_propnet* pn, int what);
  * for batches of at least `min_batch` states (default 2^18); min_batch < 0 disables it, 0 forces it. The
  * table-driven kernel and the specialised one return identical results. */
 int gz_propnet_set_spec_min_batch(gz_propnet* pn, int64_t min_batch);
+/* Wide-format games (chess_15d, hexLG13) evaluate batches of at least `min_batch` states (default 1024) with the
+ * group kernel (1024 games per CTA / cluster, one tile per lane); < 0 disables it, 0 forces it; other games only
+ * when asked. Identical results. */
+int gz_propnet_set_group_min_batch(gz_propnet* pn, int64_t min_batch);
+/* GZ_GOALS_TERMINAL_ONLY on a game with a deep goal cone (reversi's piece counting): batches of at least `min_batch`
+ * states (default 4096; < 0: never) skip the cone in the main pass and evaluate it in a second pass over the
+ * compacted terminal states only — the reference reads goal values of terminal states only
+ * (src/cpp/puct/node.cpp:153-221). Identical results. */
+int gz_propnet_set_deferred_goals_min_batch(gz_propnet* pn, int64_t min_batch);
 
 /* Layouts (n = number of states, R = roles):
  *   states  uint32 [n][state_words]   packed bases, LSB first, rows padded to 16 B

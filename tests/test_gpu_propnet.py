@@ -251,6 +251,45 @@ def test_goals_terminal_only_mode():
     assert (gl[t == 0] == 255).all()
 
 
+def test_deferred_goal_pass_bit_exact():
+    """reversi, goals for terminal states only: the compacted second pass over the terminal states (default from 4096
+    states up) returns what the one-pass kernel and the C oracle return — goal values of every terminal state, 255
+    elsewhere — on playout plies and on transitions with given moves."""
+    game = 'reversi'
+    a = _sm(game, goals_mode=gzlib.GOALS_TERMINAL_ONLY)
+    b = _sm(game, goals_mode=gzlib.GOALS_TERMINAL_ONLY)
+    b.set_deferred_goals_min_batch(-1)
+    ref = RefStateMachine(tables.blob_by_name(game))
+    n = 8192 + 37
+    sa = torch.zeros((n, a.state_words), dtype=torch.int32, device=a.device)
+    sb = torch.zeros_like(sa)
+    la, ta, ga = a.alloc_views(n)
+    lb, tb, gb = b.alloc_views(n)
+    ta.fill_(1); tb.fill_(1)
+    s = np.zeros((n, ref.state_words), dtype=np.uint32)
+    l = np.zeros((n, ref.legal_words), dtype=np.uint32)
+    t = np.ones(n, dtype=np.uint8)
+    g = np.zeros((n, ref.n_roles), dtype=np.uint8)
+    seen_terminal = 0
+    for step in range(75):
+        a.playout_step(sa, la, ta, ga, 11, step)
+        b.playout_step(sb, lb, tb, gb, 11, step)
+        ref.playout_step(0, 11, step, s, l, t, g, None)
+        if step % 6 == 5 or step > 55:
+            assert np.array_equal(_np(sa).view(np.uint32), s) and np.array_equal(_np(ta), t)
+            assert np.array_equal(_np(ga), _np(gb))
+            gl = _np(ga)
+            assert np.array_equal(gl[t == 1], g[t == 1]) and (gl[t == 0] == 255).all()
+            seen_terminal += int(t.sum())
+    assert seen_terminal > 100
+    # transition with given moves from the last positions (terminal rows: identity move)
+    mv = torch.full((n, a.n_roles), -1, dtype=torch.int16, device=a.device)
+    na, la2, ta2, ga2 = a.transition(sa, mv)
+    nb, lb2, tb2, gb2 = b.transition(sb, mv)
+    assert np.array_equal(_np(ga2), _np(gb2)) and np.array_equal(_np(ta2), _np(tb2))
+    assert (_np(ga2)[_np(ta2) == 1] != 255).any()
+
+
 def test_empty_and_bad_arguments():
     dev = _sm('breakthrough')
     s = torch.zeros((0, dev.state_words), dtype=torch.int32, device=dev.device)

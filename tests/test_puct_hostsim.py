@@ -127,6 +127,24 @@ def test_intra_tree_workers_match_reference(game, evals, moves, batch, tt, noise
         assert np.array_equal(a['scores'], b['scores'])
 
 
+@pytest.mark.parametrize('batch,tt', [(1, True), (8, False), (8, True)])
+def test_backup_finalised_with_shared_nodes_matches(batch, tt):
+    """MCTS-prover style finalisation (backup_finalised, evaluator.cpp:524-571) reads the children's nodes; with
+    transpositions or workers a node has several parent records, so nothing may rely on a record's copy."""
+    from hostsim_util import HostSim
+    ct, eng = _setup('breakthroughSmall')
+    conf = confs.base_puct_config(dirichlet_noise_pct=-1, backup_finalised=True, choose='choose_top_visits',
+                                  batch_size=batch, lookup_transpositions=tt)
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    ref = eng.search(conf, 400, n_moves=30)
+    mine = HostSim(tables.blob_by_name('breakthroughSmall'), ct, sp).search(400, 30)
+    assert len(ref) == len(mine) and len(ref) > 8
+    for a, b in zip(ref, mine):
+        assert np.array_equal(a['traversals'], b['traversals']) and a['choice'] == b['choice']
+        assert np.array_equal(a['scores'], b['scores'])
+
+
 def test_backup_finalised_and_temperature_choice_match():
     from hostsim_util import HostSim
     ct, eng = _setup('breakthroughSmall')
