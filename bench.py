@@ -492,7 +492,8 @@ def run_puct(args, rank, world, local, propnet_line=None):
         # several shards: engine graphs on their own streams, network graphs serialised on one
         runner = StaggeredSelfPlay(engines, net, sub_iters=args.sub_iters)
     else:
-        runner = SelfPlayPool(engines, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph)
+        runner = SelfPlayPool(engines, net, sub_iters=args.sub_iters, use_cuda_graph=not args.no_graph,
+                              compact=not args.full_batches)
     # untimed: let the trees grow and the searches desynchronise, then the contract's warm-up steps
     runner.step(args.presteps)
     runner.step(args.warmup * K)
@@ -504,7 +505,9 @@ def run_puct(args, rank, world, local, propnet_line=None):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     ev0.record()
+    rows0 = sum(getattr(r, 'rows_done', 0) for r in getattr(runner, 'runners', []))
     runner.step(args.steps * K)
+    rows1 = sum(getattr(r, 'rows_done', 0) for r in getattr(runner, 'runners', []))
     ev1.record()
     barrier(world)
     ms = ev0.elapsed_time(ev1)
@@ -521,6 +524,8 @@ def run_puct(args, rank, world, local, propnet_line=None):
     regime = {'mean_ply_start': t_before['depth_sum'] / G, 'mean_ply_end': t_after['depth_sum'] / G,
               'nn_batch_fill': d_evals / max(1.0, float(advances) * G),
               'playouts_per_eval': d_playouts / max(d_evals, 1.0),
+              # compacted batches: rows the network actually ran over per advance (0: full batches of G rows)
+              'network_rows_per_advance': (rows1 - rows0) / float(max(1, args.steps * K)),
               'games_finished_in_window': t_after['games'] - t_before['games'],
               'games_finished_total': t_after['games']}
 
@@ -620,25 +625,32 @@ def run_puct(args, rank, world, local, propnet_line=None):
         out_pin = [torch.empty((Gm, w), dtype=torch.float32).pin_memory() for w in list(eng.role_sizes) + [eng.n_rewards]]
         out_np = [t.numpy() for t in out_pin]
 
-        def nn_static():
-            xb = x_dev.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        # poll hands out only the rows that wait for the network (the reference's contract): the forward runs over the
+        # smallest captured batch size that holds them (steps of Gm/8 rows), not over all Gm rows
+        buckets = sorted({max(1, (Gm * k) // 8) for k in range(2, 9)})
+
+        def nn_static(b):
+            xb = x_dev[:b].to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
             p_, v_ = net(xb)
             off = 0
             for r in range(R):
-                out_dev[r].copy_(p_[:, off:off + eng.role_sizes[r]])
+                out_dev[r][:b].copy_(p_[:, off:off + eng.role_sizes[r]])
                 off += eng.role_sizes[r]
-            out_dev[R].copy_(v_)
+            out_dev[R][:b].copy_(v_)
+        g_e2e = {}
         with torch.no_grad():
             side2 = torch.cuda.Stream(device=eng.device)
             side2.wait_stream(torch.cuda.current_stream(eng.device))
             with torch.cuda.stream(side2):
-                for _ in range(3):
-                    nn_static()
+                for b in buckets:
+                    for _ in range(3):
+                        nn_static(b)
             torch.cuda.current_stream(eng.device).wait_stream(side2)
             torch.cuda.synchronize(eng.device)
-            g_e2e = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_e2e):
-                nn_static()
+            for b in buckets:
+                g_e2e[b] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_e2e[b]):
+                    nn_static(b)
 
         t_poll = t_nn = 0.0
 
@@ -656,7 +668,7 @@ def run_puct(args, rank, world, local, propnet_line=None):
             xin = torch.from_numpy(planes).view((n_req,) + eng.plane_shape)
             x_dev[:n_req].copy_(xin, non_blocking=True)
             h2d += planes.nbytes
-            g_e2e.replay()
+            g_e2e[next(b for b in buckets if b >= n_req)].replay()
             for k in range(R + 1):
                 out_pin[k][:n_req].copy_(out_dev[k][:n_req], non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
@@ -690,7 +702,8 @@ def run_puct(args, rank, world, local, propnet_line=None):
                'd2h_bytes_per_step': int(d2h / reps) * n_man * K, 'evals_per_s': e2e_evals / dt,
                'timed_region_s': dt, 'moves_in_window': e2e_moves,
                'mean_ply_start': m0['depth_sum'] / Gs, 'mean_ply_end': m1['depth_sum'] / Gs,
-               'api': 'interface.Supervisor.poll (numpy in / numpy out, reference contract), network fed from pinned host memory',
+               'api': 'interface.Supervisor.poll (numpy in / numpy out, reference contract), network fed from pinned host memory; '
+                      'the forward is a CUDA graph per batch size in steps of %d rows, the smallest that holds the rows handed out' % (Gm // 8),
                'managers': '%d x %d games (%s)' % (n_man, Gm, 'inline' if n_man == 1 else
                                                    'worker mode: engine step of one manager overlaps the network call of the other'),
                'polls': reps, 'rows_per_poll': Gm, 'bytes_are': 'per bench step = %d polls of each manager' % K,
@@ -734,8 +747,12 @@ def run_puct(args, rank, world, local, propnet_line=None):
             'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': preset['workload'], 'games_per_gpu': G, 'evals_per_move': PUCT_EVALS_PER_MOVE,
                        'network': 'random-init small tower, %.1f MFLOP/position' % (net.flops_per_position / 1e6),
-                       'step': '%d engine advances (select/backup + propnet + expand + encode), each followed by one '
-                               'network forward over %d leaves' % (K, G),
+                       'step': ('%d engine advances (select/backup + propnet + expand + encode) over %d games, each followed by '
+                                'one network forward over the leaves that wait for it (compacted on the device, batch sizes '
+                                'in steps of %d rows; see regime.network_rows_per_advance)' % (K, G, max(1, G // 32)))
+                               if (P == 1 and not args.no_graph and not args.full_batches) else
+                               ('%d engine advances (select/backup + propnet + expand + encode), each followed by one '
+                                'network forward over %d leaves' % (K, G)),
                        'advances_per_step': K, 'ms_per_advance': ms_max / advances,
                        'regime': 'slots start at staggered plies (uniform in [0, %d) random plies), %d untimed '
                                  'advances, then the warm-up steps' % (preset['stagger_plies'], args.presteps)
@@ -856,6 +873,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--pipelines', type=int, default=1)
     ap.add_argument('--staggered', action='store_true', help='(implied by --pipelines > 1)')
+    ap.add_argument('--full-batches', action='store_true',
+                    help='puct: the network runs over all G rows every advance instead of the compacted waiting rows')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-inline', action='store_true')
     ap.add_argument('--slots', type=int, default=0)

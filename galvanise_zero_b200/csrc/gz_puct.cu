@@ -283,6 +283,10 @@ struct gz_puct {
     uint8_t *t_term = nullptr, *t_goals = nullptr;
 
     int* d_status = nullptr;         // gz_puct_status scratch
+    // compacted network batches (gz_puct_compact_requests / gz_puct_advance_compact)
+    int *c_rows = nullptr, *c_count = nullptr;     // waiting rows (ascending); [0] how many wait, [1] how many were handed out
+    float *c_pol = nullptr, *c_val = nullptr;      // predictions scattered back to game rows
+    uint8_t* c_answered = nullptr;                 // per game: its prediction arrived with this step
     struct HostPoll* hp = nullptr;   // host-buffer poll state (gz_puct_host_poll_*), created on first use
 };
 
@@ -293,7 +297,8 @@ struct HostPoll {
     int* h_count = nullptr;                                          // pinned
     float *d_stage_pol = nullptr, *d_stage_val = nullptr;            // [G][..] predictions in hand-out order
     float *d_pol = nullptr, *d_val = nullptr;                        // [G][..] predictions in game order
-    float *d_planes = nullptr, *d_planes_c = nullptr;                // [G][total] all games / compacted
+    float *d_planes = nullptr, *d_planes_c = nullptr;                // [G][total] all games / (unused)
+    float* h_planes_dev = nullptr;                                   // device address of the pinned h_planes
     int *d_rows = nullptr, *d_count = nullptr;
     cudaEvent_t ev = nullptr, ev_in = nullptr;
     int outstanding = 0;      // rows handed out by the last wait
@@ -390,6 +395,7 @@ extern "C" int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, i
     E.max_work_per_step = mode == 0 ? 12 : 1 << 20;
     { const char* pf = getenv("GZ_PUCT_PREFETCH"); E.prefetch_nodes = (pf && pf[0] == '0') ? 0 : 1; }   // measurement switch
     E.dbg_cycles = nullptr;
+    E.x_answered = nullptr;
     E.seed = seed;
     if ((int)tr->policy_sizes.size() != E.R) { gz_set_error("transformer policy heads != roles"); delete h; return GZ_ERR_ARG; }
     for (int r = 0; r < E.R; r++)
@@ -488,6 +494,8 @@ extern "C" void gz_puct_destroy(gz_puct* h) {
     if (h->d_totals) cudaFree(h->d_totals);
     if (h->d_pn_scratch) cudaFree(h->d_pn_scratch);
     if (h->d_status) cudaFree(h->d_status);
+    { void* cv[] = {h->c_rows, h->c_count, h->c_pol, h->c_val, h->c_answered};
+      for (void* d : cv) if (d) cudaFree(d); }
     if (h->d_rr_list) cudaFree(h->d_rr_list);
     if (h->d_rr_count) cudaFree(h->d_rr_count);
     if (h->rr_fork) cudaEventDestroy(h->rr_fork);
@@ -689,6 +697,100 @@ extern "C" int gz_puct_set_debug_cycles(gz_puct* h, long long* d_buf) {
     return GZ_OK;
 }
 
+// ---- compacted network batches on the device ----------------------------------------------------
+// In a long-running job a quarter of the games do not wait for the network after a step (their playouts ended in
+// terminal or finalised nodes, their searches are over): the network need not see their rows. compact_requests
+// lists the waiting rows (ascending), keeps at most `cap` of them and gathers their planes into a dense batch;
+// advance_compact takes the predictions in that order. Requests beyond the cap simply stay pending — their games
+// wait one more step — so a caller may size the batch from a STALE count (read back asynchronously, no host
+// synchronisation in the loop) and still be correct.
+__global__ void compact_cap_kernel(const int* __restrict__ count, int cap, int* __restrict__ n_out) {
+    *n_out = *count < cap ? *count : cap;
+}
+__global__ void compact_gather_kernel(const uint4* __restrict__ planes, const int* __restrict__ rows,
+                                      const int* __restrict__ n_ptr, int row_vec, uint4* __restrict__ out) {
+    const int n = *n_ptr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * row_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / row_vec), c = (int)(i - (int64_t)r * row_vec);
+        out[i] = planes[(int64_t)rows[r] * row_vec + c];
+    }
+}
+__global__ void compact_scatter_kernel(const float* __restrict__ pol_c, const float* __restrict__ val_c,
+                                       const int* __restrict__ rows, const int* __restrict__ n_ptr, int stride, int nrew,
+                                       float* __restrict__ pol, float* __restrict__ val, uint8_t* __restrict__ answered) {
+    const int n = *n_ptr;
+    const int per = stride + nrew;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * per; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / per), c = (int)(i - (int64_t)r * per);
+        const int g = rows[r];
+        if (c < stride) pol[(int64_t)g * stride + c] = pol_c[(int64_t)r * stride + c];
+        else val[(int64_t)g * nrew + (c - stride)] = val_c[(int64_t)r * nrew + (c - stride)];
+        if (c == 0) answered[g] = 1;
+    }
+}
+
+static int compact_init(gz_puct* h) {
+    if (h->c_rows) return GZ_OK;
+    if (h->E.EB != 1) { gz_set_error("compacted batches are a self-play feature (one evaluation row per game)"); return GZ_ERR_ARG; }
+    const size_t G = (size_t)h->E.G;
+    GZ_CUDA(cudaSetDevice(h->device));
+    GZ_CUDA(cudaMalloc((void**)&h->c_rows, G * 4));
+    GZ_CUDA(cudaMalloc((void**)&h->c_count, 256));
+    GZ_CUDA(cudaMemset(h->c_count, 0, 256));
+    GZ_CUDA(cudaMalloc((void**)&h->c_pol, G * h->E.policy_stride * 4));
+    GZ_CUDA(cudaMalloc((void**)&h->c_val, G * h->E.n_rewards * 4));
+    GZ_CUDA(cudaMalloc((void**)&h->c_answered, G));
+    GZ_CUDA(cudaMemset(h->c_pol, 0, G * h->E.policy_stride * 4));
+    GZ_CUDA(cudaMemset(h->c_val, 0, G * h->E.n_rewards * 4));
+    GZ_CUDA(cudaMemset(h->c_answered, 0, G));
+    return GZ_OK;
+}
+
+// d_planes: what gz_puct_advance wrote ([G] rows of row_bytes bytes, a multiple of 16); d_planes_c receives the
+// first min(waiting, cap) waiting rows. h_count_pinned (optional, pinned host memory) receives the UNCAPPED number
+// of waiting rows with an asynchronous copy.
+extern "C" int gz_puct_compact_requests(gz_puct* h, int cap, const void* d_planes, int64_t row_bytes, void* d_planes_c,
+                                        int* h_count_pinned, void* stream) {
+    if (!h || !d_planes || !d_planes_c || cap < 1 || row_bytes <= 0 || (row_bytes & 15)) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
+    int rc = compact_init(h);
+    if (rc != GZ_OK) return rc;
+    GZ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    // no join with the step's side-stream work here (re-rooting; goal values and nodes of terminal states): a terminal
+    // state's node never asks for the network, so the request flags are complete once the main stream's node creation
+    // has run, and the network forward that follows keeps overlapping that work
+    hostpoll_compact_kernel<<<1, 1024, 0, s>>>(h->E.x_need_eval, h->E.G, h->c_rows, h->c_count);
+    compact_cap_kernel<<<1, 1, 0, s>>>(h->c_count, cap, h->c_count + 1);
+    const int row_vec = (int)(row_bytes / 16);
+    const int64_t work = (int64_t)std::min(cap, h->E.G) * row_vec;
+    compact_gather_kernel<<<(int)std::min<int64_t>((work + 255) / 256, 1184), 256, 0, s>>>(
+        (const uint4*)d_planes, h->c_rows, h->c_count + 1, row_vec, (uint4*)d_planes_c);
+    GZ_CUDA(cudaGetLastError());
+    if (h_count_pinned) GZ_CUDA(cudaMemcpyAsync(h_count_pinned, h->c_count, 4, cudaMemcpyDeviceToHost, s));
+    return GZ_OK;
+}
+
+// The step that follows gz_puct_compact_requests: d_policy_c / d_value_c hold the network's outputs for the rows of
+// the compacted batch, in its order.
+extern "C" int gz_puct_advance_compact(gz_puct* h, const float* d_policy_c, const float* d_value_c, int sub_iters,
+                                       void* d_planes, int plane_dtype, void* stream, int defer_join) {
+    if (!h || !d_policy_c || !d_value_c) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    int rc = compact_init(h);
+    if (rc != GZ_OK) return rc;
+    GZ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = join_side(h, s);
+    if (rc != GZ_OK) return rc;
+    const int64_t work = (int64_t)h->E.G * (h->E.policy_stride + h->E.n_rewards);
+    compact_scatter_kernel<<<(int)std::min<int64_t>((work + 255) / 256, 1184), 256, 0, s>>>(
+        d_policy_c, d_value_c, h->c_rows, h->c_count + 1, h->E.policy_stride, h->E.n_rewards, h->c_pol, h->c_val, h->c_answered);
+    GZ_CUDA(cudaGetLastError());
+    h->E.x_answered = h->c_answered;
+    rc = advance_impl(h, h->c_pol, h->c_val, 1, sub_iters, d_planes, plane_dtype, stream, nullptr, defer_join != 0);
+    h->E.x_answered = nullptr;
+    return rc;
+}
+
 extern "C" const uint8_t* gz_puct_need_eval_ptr(const gz_puct* h) { return h ? h->E.x_need_eval : nullptr; }
 
 // Copies the per-game "waiting for the network" flags (uint8 [G]) into a caller-owned device buffer.
@@ -780,14 +882,14 @@ static int hostpoll_init(gz_puct* h) {
     GZ_CUDA(cudaSetDevice(h->device));
     GZ_CUDA(cudaHostAlloc((void**)&q->h_pol, G * st * 4, cudaHostAllocDefault));
     GZ_CUDA(cudaHostAlloc((void**)&q->h_val, G * nr * 4, cudaHostAllocDefault));
-    GZ_CUDA(cudaHostAlloc((void**)&q->h_planes, G * tot * 4, cudaHostAllocDefault));
+    GZ_CUDA(cudaHostAlloc((void**)&q->h_planes, G * tot * 4, cudaHostAllocMapped));
     GZ_CUDA(cudaHostAlloc((void**)&q->h_count, 64, cudaHostAllocDefault));
     GZ_CUDA(cudaMalloc((void**)&q->d_stage_pol, G * st * 4));
     GZ_CUDA(cudaMalloc((void**)&q->d_stage_val, G * nr * 4));
     GZ_CUDA(cudaMalloc((void**)&q->d_pol, G * st * 4));
     GZ_CUDA(cudaMalloc((void**)&q->d_val, G * nr * 4));
     GZ_CUDA(cudaMalloc((void**)&q->d_planes, G * tot * 4));
-    GZ_CUDA(cudaMalloc((void**)&q->d_planes_c, G * tot * 4));
+    GZ_CUDA(cudaHostGetDevicePointer((void**)&q->h_planes_dev, q->h_planes, 0));
     GZ_CUDA(cudaMalloc((void**)&q->d_rows, G * 4));
     GZ_CUDA(cudaMalloc((void**)&q->d_count, 64));
     GZ_CUDA(cudaMemset(q->d_pol, 0, G * st * 4));
@@ -851,11 +953,13 @@ extern "C" int gz_puct_host_poll_submit(gz_puct* h, int n_pred, const float* con
     hostpoll_compact_kernel<<<1, 1024, 0, s>>>(E.x_need_eval, E.G, q->d_rows, q->d_count);
     GZ_CUDA(cudaGetLastError());
     const int64_t gw = (int64_t)E.G * h->total_size / 4;
+    // the gather writes straight into the pinned host buffer (unified addressing: the kernel's 16-byte stores are
+    // posted PCIe writes), so only the rows that wait for the network cross the bus — no device staging copy and no
+    // device-to-host copy of all G rows whose length the host would have to know first
     hostpoll_gather_kernel<<<(int)std::min<int64_t>((gw + 255) / 256, 1184), 256, 0, s>>>(
-        q->d_planes, q->d_rows, q->d_count, h->total_size, q->d_planes_c);
+        q->d_planes, q->d_rows, q->d_count, h->total_size, q->h_planes_dev);
     GZ_CUDA(cudaGetLastError());
     GZ_CUDA(cudaMemcpyAsync(q->h_count, q->d_count, 4, cudaMemcpyDeviceToHost, s));
-    GZ_CUDA(cudaMemcpyAsync(q->h_planes, q->d_planes_c, (size_t)E.G * h->total_size * 4, cudaMemcpyDeviceToHost, s));
     GZ_CUDA(cudaEventRecord(q->ev, s));
     q->outstanding = 0;
     q->in_flight = true;

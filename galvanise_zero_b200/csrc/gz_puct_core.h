@@ -230,6 +230,8 @@ struct PuctEngine {
     int16_t* x_moves;                           // [G*R]   (-1 = identity / inactive)
     uint8_t *x_term, *x_goals, *x_prevcnt;      // [G], [G*R], [G]
     uint8_t* x_need_eval;                       // [G*EB] 1 when the row of planes is a live request
+    uint8_t* x_answered;                        // [G] or null: compacted batches — 1 when this step brought the game's
+                                                // prediction (a request beyond the batch's cap waits one more step)
     // evaluation rows: EB per game (a Player with PuctConfig.batch_size > 1 hands up to batch_size leaves of its one
     // tree to the network at once; self-play: 1). Row of game g, request k: g*EB + k. The encoder reads e_state /
     // e_prev / e_prevcnt; with EB == 1 these ARE x_state / x_in_state / x_prevcnt.
@@ -2548,6 +2550,13 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
     }
     if (c->eval_node >= 0) {
         if (!nn_fresh) return;          // still waiting for the network
+        if (E->x_answered) {            // compacted batch: did this game's row fit into it?
+            GZP_SYNC();
+            const bool answered = E->x_answered[V.g] != 0;
+            GZP_SYNC();
+            if (!answered) return;
+            E->x_answered[V.g] = 0;
+        }
         E->x_need_eval[(int64_t)V.g * E->EB] = 0;
         gzp_reply(V, c->eval_node);
         c->num_evaluations++;

@@ -76,6 +76,8 @@ def _declare(L):
     L.gz_puct_command.argtypes = [vp, ci, ci, ci, ci, vp, vp]
     L.gz_puct_snapshot.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
     L.gz_synth_nn.argtypes = [vp, ci, i64, ci, u64, ci, ctypes.POINTER(ci), ci, vp, vp, vp]
+    L.gz_puct_compact_requests.argtypes = [vp, ci, vp, i64, vp, vp, vp]
+    L.gz_puct_advance_compact.argtypes = [vp, vp, vp, ci, vp, ci, vp, ci]
     L._gz_puct_declared = True
 
 
@@ -189,6 +191,37 @@ class PuctEngine(object):
         fn = self._L.gz_puct_advance_async if defer_join else self._L.gz_puct_advance
         _lib.check(fn(self._h, policy.data_ptr() if fresh else None, value.data_ptr() if fresh else None,
                       1 if fresh else 0, sub_iters, self.planes.data_ptr(), code, self._stream()))
+        return self.planes
+
+    # ---- compacted network batches: only the rows that wait for the network are handed out
+    def compact_requests(self, cap=None, count_pinned=None):
+        """After ``advance``: gathers the planes of the (at most ``cap``) waiting rows, in ascending game order, into a
+        dense batch and returns it (``[cap, C, H, W]`` view; rows beyond the number handed out are stale). Requests
+        beyond ``cap`` stay pending. ``count_pinned``: a pinned int32 tensor that receives the number of waiting rows
+        asynchronously (read it later to size the next batches)."""
+        cap = self.n_games if cap is None else int(cap)
+        if getattr(self, '_planes_c', None) is None:
+            # same memory layout as the planes (channels-last padded: logical [G, c_pad, H, W] over [G, H, W, c_pad])
+            if self.plane_c_pad:
+                mem = torch.zeros((self.planes.shape[0], self.plane_shape[1], self.plane_shape[2], self.plane_c_pad),
+                                  dtype=self.planes.dtype, device=self.device)
+                self._planes_c = mem.permute(0, 3, 1, 2)
+            else:
+                self._planes_c = torch.zeros_like(self.planes, memory_format=torch.contiguous_format)
+        row_bytes = self.planes[0].numel() * self.planes.element_size()
+        _lib.check(self._L.gz_puct_compact_requests(
+            self._h, cap, self.planes.data_ptr(), row_bytes, self._planes_c.data_ptr(),
+            count_pinned.data_ptr() if count_pinned is not None else None, self._stream()))
+        return self._planes_c[:cap]
+
+    def advance_compact(self, policy_c, value_c, sub_iters=1, defer_join=False):
+        """The step after ``compact_requests``: ``policy_c`` / ``value_c`` are the network's outputs for the rows of the
+        compacted batch, in its order (at least as many rows as were handed out)."""
+        assert policy_c.dtype == torch.float32 and policy_c.is_contiguous() and policy_c.shape[1] == self.policy_stride
+        assert value_c.dtype == torch.float32 and value_c.is_contiguous() and value_c.shape[1] == self.n_rewards
+        code = {torch.float32: 0, torch.bfloat16: 1}[self.planes.dtype]
+        _lib.check(self._L.gz_puct_advance_compact(self._h, policy_c.data_ptr(), value_c.data_ptr(), sub_iters,
+                                                   self.planes.data_ptr(), code, self._stream(), 1 if defer_join else 0))
         return self.planes
 
     def advance_timed(self, policy=None, value=None):

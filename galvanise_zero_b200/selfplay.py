@@ -100,20 +100,110 @@ class SelfPlayRunner(object):
         return self.engine.kernels_per_step + 4 * (self.sub_iters - 1)
 
 
+class CompactSelfPlayRunner(object):
+    """Engine step + network forward over the rows that WAIT for the network only (``PuctEngine.compact_requests`` /
+    ``advance_compact``) — what the reference's poll hands its network (``src/cpp/supervisor.cpp:101-168``). In a
+    long-running job a quarter of the games need no evaluation after a step (their playouts ended in terminal nodes,
+    their searches are over). Shapes must be static for CUDA graphs, so one graph is captured per batch size in steps
+    of G/32 rows; the host picks the graph from the count of waiting rows the device reported a few steps ago (an
+    asynchronous copy into pinned memory, never waited for). A count that grew in the meantime is harmless: requests
+    beyond the batch stay pending and their games wait one more step."""
+
+    def __init__(self, engine: PuctEngine, net, sub_iters=1, stream=None, margin=1.03):
+        self.engine = e = engine
+        self.net = net
+        self.sub_iters = sub_iters
+        self.stream = stream
+        self.margin = margin
+        self.steps_done = 0
+        self.rows_done = 0
+        G = e.n_games
+        q = max(1, G // 32)
+        self.buckets = sorted({min(G, q * k) for k in range(14, 33)})
+        self.count = torch.full((1,), G, dtype=torch.int32).pin_memory()
+        self.pol_c = torch.zeros_like(e.policy)
+        self.val_c = torch.zeros_like(e.value)
+        torch.backends.cudnn.benchmark = True
+        self.graphs = {}
+        with torch.no_grad():
+            e.advance(None, None, sub_iters)
+            self._batch(G)
+            torch.cuda.synchronize(e.device)
+            side = torch.cuda.Stream(device=e.device)
+            for b in self.buckets:
+                side.wait_stream(torch.cuda.current_stream(e.device))
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        self._step_eager(b)
+                torch.cuda.current_stream(e.device).wait_stream(side)
+                torch.cuda.synchronize(e.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_eager(b)
+                self.graphs[b] = g
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(e.device))
+
+    def _batch(self, b):
+        e = self.engine
+        x = e.compact_requests(b, self.count)
+        if not e.plane_c_pad:
+            x = x.contiguous(memory_format=torch.channels_last)
+        pol, val = self.net(x)
+        self.pol_c[:b].copy_(pol)
+        self.val_c[:b].copy_(val)
+
+    def _step_eager(self, b):
+        e = self.engine
+        e.advance_compact(self.pol_c, self.val_c, self.sub_iters, defer_join=True)
+        self._batch(b)
+        e.join()
+
+    def _pick(self):
+        want = int(int(self.count[0]) * self.margin) + 16
+        for b in self.buckets:
+            if b >= want:
+                return b
+        return self.buckets[-1]
+
+    def step(self, n=1):
+        with torch.no_grad():
+            ctx = torch.cuda.stream(self.stream) if self.stream is not None else None
+            if ctx is not None:
+                ctx.__enter__()
+            try:
+                for _ in range(n):
+                    b = self._pick()
+                    self.graphs[b].replay()
+                    self.rows_done += b
+            finally:
+                if ctx is not None:
+                    ctx.__exit__(None, None, None)
+        self.steps_done += n
+
+    @property
+    def kernels_per_step(self):
+        """own launches per step: the engine's, plus compaction (list, cap, gather) and the scatter of the predictions"""
+        return self.engine.kernels_per_step + 4 + 4 * (self.sub_iters - 1)
+
+
 class SelfPlayPool(object):
     """One engine+network pipeline per engine on its own CUDA stream, each with its own graph. Used with a
     single engine; several shards go through StaggeredSelfPlay (engine graphs on their own streams, network
     graphs serialised on one), which is what overlaps tree kernels with the tower — the device-side analogue
     of the reference's two managers per worker thread (``src/cpp/supervisor.cpp:79-99,196-231``)."""
 
-    def __init__(self, engines, net, sub_iters=1, use_cuda_graph=True):
+    def __init__(self, engines, net, sub_iters=1, use_cuda_graph=True, compact=False):
         if len(engines) != 1:
             raise ValueError('SelfPlayPool drives one engine; use StaggeredSelfPlay for several shards')
         dev = engines[0].device
         self.engines = engines
         self.streams = [torch.cuda.Stream(device=dev) for _ in engines]
-        self.runners = [SelfPlayRunner(e, net, sub_iters, use_cuda_graph, stream=s)
-                        for e, s in zip(engines, self.streams)]
+        if compact and use_cuda_graph:
+            self.runners = [CompactSelfPlayRunner(e, net, sub_iters, stream=s) for e, s in zip(engines, self.streams)]
+        else:
+            self.runners = [SelfPlayRunner(e, net, sub_iters, use_cuda_graph, stream=s)
+                            for e, s in zip(engines, self.streams)]
         self.device = dev
 
     def step(self, n=1):

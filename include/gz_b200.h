@@ -224,6 +224,18 @@ int gz_puct_totals(gz_puct* h, double* h_out26, void* stream);
  * positions) at game depth 0 instead of the initial state — what handing SelfPlay another `initial_state`
  * (src/cpp/selfplaymanager.cpp:140, selfplay.cpp:313) does in the reference. Later games start normally. */
 int gz_puct_set_start_states(gz_puct* h, const uint32_t* d_states, void* stream);
+/* Compacted network batches on the device (self-play engines). After a step, gz_puct_compact_requests lists the rows
+ * that wait for the network (ascending game order), keeps at most `cap` of them and gathers their planes (rows of
+ * row_bytes bytes, a multiple of 16, as gz_puct_advance wrote them) into d_planes_c; h_count_pinned (optional, pinned
+ * host memory) receives the uncapped number of waiting rows with an asynchronous copy. gz_puct_advance_compact is the
+ * next step: d_policy_c [n][policy_stride] / d_value_c [n][rewards] are the network's outputs for those rows in that
+ * order. Requests beyond the cap stay pending (their games wait one more step), so the batch may be sized from a
+ * stale count without synchronising. This is what the reference's poll does with host arrays
+ * (src/cpp/supervisor.cpp:101-168: only the waiting games' planes are handed out). */
+int gz_puct_compact_requests(gz_puct* h, int cap, const void* d_planes, int64_t row_bytes, void* d_planes_c,
+                             int* h_count_pinned, void* stream);
+int gz_puct_advance_compact(gz_puct* h, const float* d_policy_c, const float* d_value_c, int sub_iters, void* d_planes,
+                            int plane_dtype, void* stream, int defer_join);
 /* Measurement aid: d_buf = device int64 [G][4] (or null to stop): per game the cycles its warp spent in the last
  * puct_pre_kernel launch, entry*256+exit phase, playouts finished, moves*65536 + path_len*256 + request. */
 int gz_puct_set_debug_cycles(gz_puct* h, long long* d_buf);

