@@ -84,6 +84,43 @@ __device__ __forceinline__ void tile_sync() {
     if (WPT == 1) __syncwarp(); else __syncthreads();
 }
 
+// Chunk offsets and level boundaries of the three programs (built at load time, build_group_tables): whoever
+// evaluates only SOME chunks of a level (the warps of a shared tile, the group kernel) indexes them directly
+// instead of walking the stream.
+struct GroupTables {
+    const uint32_t* desc[3];     // per chunk: word offset into the program | literal rows << 28
+    const int* level_first[3];   // per level: index of its first chunk; [n_levels] = n_chunks
+    int n_levels[3];
+};
+#define GZ_GROUP_TABLES_DEFINED 1
+
+// ---- bulk staging (TMA, non-tensor form): one thread issues cp.async.bulk global -> shared for a whole gate
+// program and everybody waits on an mbarrier transaction count (SASS: UBLKCP + SYNCS), instead of 256 threads
+// copying it word by word through registers
+__device__ __forceinline__ void bulk_bar_init(uint64_t* bar) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_bar_expect(uint64_t* bar, uint32_t bytes) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_bar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+}
+
 // Evaluates one chunk stream on the tile's value array. With WPT > 1 the CTA's WPT warps share the
 // tile: warp `wt` evaluates chunks wt, wt+WPT, ... and the CTA meets at every level boundary.
 template <int WPT>
@@ -107,6 +144,36 @@ __device__ __forceinline__ void run_program(const uint32_t* __restrict__ prog, i
         }
         p += 17 + 32 * nl2;
         if (hdr & 0x100u) tile_sync<WPT>();
+    }
+}
+
+// The same evaluation for a tile shared by WPT warps, driven by the chunk / level tables: warp wt takes chunks
+// wt, wt+WPT, .. of every level and nobody walks the headers of chunks it does not evaluate (in the PUCT step,
+// where a tile has a CTA to itself, that dependent walk was a third of the kernel's stall samples).
+template <int WPT>
+__device__ __forceinline__ void run_program_levels(const uint32_t* __restrict__ prog, const uint32_t* __restrict__ desc,
+                                                   const int* __restrict__ level_first, int n_levels,
+                                                   uint32_t* __restrict__ val, int lane, int wt) {
+    int c_lo = __ldg(level_first);
+    for (int l = 0; l < n_levels; ++l) {
+        const int c_hi = __ldg(level_first + l + 1);
+        for (int c = c_lo + wt; c < c_hi; c += WPT) {
+            const uint32_t d = __ldg(desc + c);
+            const uint32_t* p = prog + (d & 0x0fffffffu);
+            const int nl2 = (int)(d >> 28) >> 1;
+            const uint32_t ow = p[1 + (lane >> 1)];
+            const uint32_t out = (lane & 1) ? (ow >> 16) : (ow & 0xffffu);
+            uint32_t acc = 0xffffffffu;
+            const uint32_t* lp = p + 17 + lane;
+#pragma unroll 2
+            for (int k = 0; k < nl2; ++k) {
+                const uint32_t pr = lp[k * 32];
+                acc &= lit_word(val, pr & 0xffffu) & lit_word(val, pr >> 16);
+            }
+            val[out] = acc;
+        }
+        c_lo = c_hi;
+        tile_sync<WPT>();
     }
 }
 
@@ -145,7 +212,7 @@ __device__ __forceinline__ void store_rows(uint32_t* __restrict__ dst, int row_w
 
 template <int MODE, int WPT>
 __global__ void __launch_bounds__(1024, 1)
-pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
+pn_kernel(const __grid_constant__ PnParams P, const __grid_constant__ GroupTables GT, int64_t n, int64_t slot0,
           const uint32_t* states_in, const int16_t* __restrict__ moves_in,
           uint32_t* states_out, uint32_t* legal,
           uint8_t* terminal, uint8_t* __restrict__ goals, int16_t* __restrict__ moves_out,
@@ -154,22 +221,49 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
     extern __shared__ __align__(16) uint32_t smem[];
     if (n_dev) n = (int64_t)*n_dev;      // batch size decided on the device (compacted sub-batches)
 
-    // ---- stage gate programs in shared memory (those the host decided fit)
+    // ---- stage gate programs in shared memory (those the host decided fit): one bulk copy each, in flight while
+    // the first tile's rows are loaded and transposed; everybody waits on the barrier before the first program runs
+    __shared__ __align__(8) uint64_t stage_bar;
     const uint32_t* prog[3];
+    bool staging = false;
     {
         uint32_t* sp = smem;
+        uint32_t bytes[3];
+        uint32_t total = 0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
+            bytes[k] = 0;
             if (P.staged[k]) {
-                for (int i = threadIdx.x; i < P.words[k]; i += blockDim.x) sp[i] = P.prog[k][i];
+                bytes[k] = (uint32_t)((P.words[k] + 3) & ~3) * 4u;    // (the device copy is padded to 16 bytes)
+                total += bytes[k];
                 prog[k] = sp;
                 sp += (P.words[k] + 3) & ~3;
             } else {
                 prog[k] = P.prog[k];
             }
         }
+        staging = total != 0;
+        if (staging) {
+            if (threadIdx.x == 0) bulk_bar_init(&stage_bar);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_bar_expect(&stage_bar, total);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (bytes[k]) bulk_copy_g2s(const_cast<uint32_t*>(prog[k]), P.prog[k], bytes[k], &stage_bar);
+            }
+        }
     }
-    __syncthreads();
+    if (WPT > 1) {
+        // the chunk / level tables are read through the read-only path: touch them once so that the per-level
+        // look-ups hit in L1
+        for (int k = 0; k < 3; ++k) {
+            for (int i = threadIdx.x * 32; i < P.chunks[k]; i += blockDim.x * 32)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(GT.desc[k] + i));
+            for (int i = threadIdx.x * 32; i <= GT.n_levels[k]; i += blockDim.x * 32)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(GT.level_first[k] + i));
+        }
+    }
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -253,9 +347,11 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
         }   // io
         tile_sync<WPT>();
 
+        if (staging) { bulk_bar_wait(&stage_bar, 0); staging = false; }    // (first tile only: phase 0 completes once)
         if (MODE != MODE_EVAL) {
             // ---- next-state cone
-            run_program<WPT>(prog[0], P.chunks[0], val, lane, wt);
+            if (WPT > 1) run_program_levels<WPT>(prog[0], GT.desc[0], GT.level_first[0], GT.n_levels[0], val, lane, wt);
+            else run_program<WPT>(prog[0], P.chunks[0], val, lane, wt);
             if (io) {
             for (int j = 0; j < P.nbw; ++j) {
                 const int b = j * 32 + lane;
@@ -283,10 +379,14 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
         tile_sync<WPT>();
 
         // ---- views of the (new) state: legal masks, terminal, goals
-        run_program<WPT>(prog[1], P.chunks[1], val, lane, wt);
+        if (WPT > 1) run_program_levels<WPT>(prog[1], GT.desc[1], GT.level_first[1], GT.n_levels[1], val, lane, wt);
+        else run_program<WPT>(prog[1], P.chunks[1], val, lane, wt);
         const uint32_t tw = lit_word(val, (uint32_t)P.terminal_lit) & valid_mask;
         const bool need_goals = (goals_mode == GZ_GOALS_ALWAYS) || (goals_mode == GZ_GOALS_TERMINAL_ONLY && tw != 0u);
-        if (need_goals) run_program<WPT>(prog[2], P.chunks[2], val, lane, wt);
+        if (need_goals) {
+            if (WPT > 1) run_program_levels<WPT>(prog[2], GT.desc[2], GT.level_first[2], GT.n_levels[2], val, lane, wt);
+            else run_program<WPT>(prog[2], P.chunks[2], val, lane, wt);
+        }
 
         if (io) {
         for (int j = 0; j < P.lw_used; ++j) {
@@ -316,6 +416,7 @@ pn_kernel(const __grid_constant__ PnParams P, int64_t n, int64_t slot0,
         }   // io
         tile_sync<WPT>();
     }
+    if (staging) bulk_bar_wait(&stage_bar, 0);     // a warp without a tile: the copy into this CTA's memory must land first
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -933,10 +1034,10 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
         const size_t smem = (size_t)pn->P.staged_words * 4 + (size_t)pn->P.warp_words * 4;
         const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)pn->grid_max * 8);
         if (wpt == 8)
-            pn_kernel<MODE, 8><<<grid, 8 * 32, smem, st>>>(pn->P, n, slot0, states_in, moves_in, states_out, legal,
+            pn_kernel<MODE, 8><<<grid, 8 * 32, smem, st>>>(pn->P, pn->GT, n, slot0, states_in, moves_in, states_out, legal,
                                                           terminal, goals, moves_out, transitions, seed, step, goals_mode, n_dev);
         else
-            pn_kernel<MODE, 4><<<grid, 4 * 32, smem, st>>>(pn->P, n, slot0, states_in, moves_in, states_out, legal,
+            pn_kernel<MODE, 4><<<grid, 4 * 32, smem, st>>>(pn->P, pn->GT, n, slot0, states_in, moves_in, states_out, legal,
                                                           terminal, goals, moves_out, transitions, seed, step, goals_mode, n_dev);
     } else {
         // one persistent CTA per SM; medium batches shrink the CTA so that tiles spread over all SMs
@@ -945,7 +1046,7 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
         const int grid2 = (int)std::min<int64_t>((n_tiles + block_warps - 1) / block_warps, pn->grid_max);
         const size_t smem = (size_t)pn->P.staged_words * 4 + (size_t)block_warps * pn->P.warp_words * 4;
         pn_kernel<MODE, 1><<<grid2, block_warps * 32, smem, st>>>(
-            pn->P, n, slot0, states_in, moves_in, states_out, legal, terminal, goals, moves_out, transitions,
+            pn->P, pn->GT, n, slot0, states_in, moves_in, states_out, legal, terminal, goals, moves_out, transitions,
             seed, step, goals_mode, n_dev);
     }
     GZ_CUDA(cudaGetLastError());

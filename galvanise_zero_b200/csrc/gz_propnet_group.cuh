@@ -27,11 +27,13 @@
 #define GROUP_TILES 32
 #define GROUP_GAMES (GROUP_TILES * 32)
 
+#ifndef GZ_GROUP_TABLES_DEFINED
 struct GroupTables {
     const uint32_t* desc[3];     // per chunk: word offset into the program | literal rows << 28
     const int* level_first[3];   // per level: index of its first chunk; [n_levels] = n_chunks
     int n_levels[3];
 };
+#endif
 
 template <int CL>
 __device__ __forceinline__ void group_sync() {
