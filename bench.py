@@ -344,9 +344,9 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
 
 # ------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of one puct_pre_kernel launch in the bench configuration
-# (ncu --set full capture, profiles/r01c_puct_pre_kernel_ncu_full.md)
-PUCT_PRE_NCU_TRAFFIC_BYTES = 57936896
-PUCT_PRE_NCU_TRAFFIC_SOURCE = 'ncu --set full, profiles/r01c_puct_pre_kernel_ncu_full.md (dram read+write per launch)'
+# (ncu --set full capture in the bench's own steady-state regime, profiles/r02_puct_pre_kernel_ncu_full.md)
+PUCT_PRE_NCU_TRAFFIC_BYTES = 36432128
+PUCT_PRE_NCU_TRAFFIC_SOURCE = 'ncu --set full, profiles/r02_puct_pre_kernel_ncu_full.md (dram read+write per launch)'
 PUCT_GAME = 'reversi'
 PUCT_EVALS_PER_MOVE = 800
 # per game: concurrent games per GPU, tree arena sizes, and the ply range the slots' first games are spread over

@@ -946,10 +946,9 @@ __device__ __forceinline__ GzpKid gzp_warp_load_kid(const GameView& V, int c0, i
     K.visits = K.expanded ? k.c_visits : 0u;
     K.flags = K.expanded ? (int)k.c_flags : 0;
     K.inflight = K.expanded ? (int)k.c_inflight : 0;
-    // Whichever child select picks, the next tree level starts with that child's node record: every lane asks L2
-    // for its own child's record now, so that the DRAM round trip runs under the select arithmetic instead of
-    // after it (one of the two dependent round trips per level; 64 bytes per expanded child of extra traffic on a
-    // path that uses 3 % of the DRAM bandwidth).
+    // (measurement switch GZ_PUCT_PREFETCH=1) Whichever child select picks, the next tree level starts with that
+    // child's node record: every lane asks L2 for its own child's record now, so that the DRAM round trip runs
+    // under the select arithmetic instead of after it. Measured: no gain, see gz_puct.cu.
     if (K.expanded && V.E->prefetch_nodes)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(V.E->nodes + V.nb + k.c_to));
     if (gzp_direct_stats(V.E) && K.expanded) {     // the record's copy may be stale, read the node
