@@ -370,12 +370,17 @@ static PyObject* player_balance_moves(PyPlayer* self, PyObject* args) {
 static PyObject* player_tree_debug(PyPlayer* self, PyObject* args) {
     int n = 0;
     if (!PyArg_ParseTuple(args, "i", &n)) return nullptr;
-    std::vector<float> sc(n > 0 ? n : 1);
-    std::vector<int> ld(n > 0 ? n : 1), mv(n > 0 ? n : 1);
-    const int k = gz_player_tree_debug(self->p, n > 0 ? n : 0, sc.data(), ld.data(), mv.data());
+    const int m = n > 0 ? n : 1;
+    std::vector<float> sc(m);
+    std::vector<int> ld(m), mv(m), vl(m), vp((size_t)m * 20);
+    const int k = gz_player_tree_debug_lines(self->p, n > 0 ? n : 0, sc.data(), ld.data(), mv.data(), vl.data(), vp.data());
     if (k < 0) return fail();
     PyObject* out = PyTuple_New(k);
-    for (int i = 0; i < k; i++) PyTuple_SET_ITEM(out, i, Py_BuildValue("(fii())", sc[i], ld[i], mv[i]));
+    for (int i = 0; i < k; i++) {        // (score, lead role, move, ((lead role, move), ..)) as player_impl.cpp:75-100
+        PyObject* var = PyTuple_New(vl[i]);
+        for (int j = 0; j < vl[i]; j++) PyTuple_SET_ITEM(var, j, Py_BuildValue("(ii)", vp[i * 20 + 2 * j], vp[i * 20 + 2 * j + 1]));
+        PyTuple_SET_ITEM(out, i, Py_BuildValue("(fiiN)", sc[i], ld[i], mv[i], var));
+    }
     return out;
 }
 static PyObject* player_poll(PyPlayer* self, PyObject* args) {

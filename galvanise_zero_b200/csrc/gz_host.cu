@@ -363,28 +363,29 @@ extern "C" int gz_player_get_move(gz_player* p, int role, int* move, float* scor
 // puctBalanceFirstMoves (evaluator.cpp:282-339): an analysis aid of the tournament tooling; accepted, no effect
 extern "C" int gz_player_balance_moves(gz_player* p, int max_count) { (void)max_count; return p ? GZ_OK : GZ_ERR_ARG; }
 
-// treeDebug (player.cpp:137-153, node.cpp:400-440): the root's expanded children by visits; variation lines
-// below them are not reported. Returns the count written (<= max_count).
-extern "C" int gz_player_tree_debug(gz_player* p, int max_count, float* scores, int* lead, int* moves) {
-    if (!p) return GZ_ERR_ARG;
-    int oi[16];
-    float of[8];
-    const int cap = p->max_actions;
-    std::vector<int> mv(cap), tr(cap);
-    std::vector<float> pr(cap), sc(cap), nx(cap);
-    const int n = gz_puct_snapshot(p->eng, 0, cap, oi, of, mv.data(), tr.data(), pr.data(), sc.data(), nx.data(), (void*)p->stream);
+// treeDebug (player.cpp:137-153, node.cpp:376-441): the root's expanded children by traversals (then score) with the
+// principal variation below each (10 plies at most, nodes with at least 100 visits). scores / lead / moves: one per
+// line; var_len[i] pairs (lead role, move) at var_pairs + i * 20. Returns the count written (<= max_count).
+extern "C" int gz_puct_tree_debug(gz_puct* h, int g, int max_count, int depth, int* h_out_i, float* h_out_f, void* stream);
+extern "C" int gz_player_tree_debug_lines(gz_player* p, int max_count, float* scores, int* lead, int* moves, int* var_len,
+                                          int* var_pairs) {
+    if (!p || !scores || !lead || !moves) { gz_set_error("null argument"); return GZ_ERR_ARG; }
+    if (max_count <= 0) return 0;
+    const int depth = 10, stride = 3 + 2 * depth;
+    std::vector<int> oi((size_t)max_count * stride);
+    std::vector<float> of(max_count);
+    const int n = gz_puct_tree_debug(p->eng, 0, max_count, depth, oi.data(), of.data(), (void*)p->stream);
     if (n < 0) return n;
-    std::vector<int> order(n);
-    for (int i = 0; i < n; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tr[a] > tr[b]; });
-    int k = 0;
-    for (int i = 0; i < n && k < max_count; i++) {
-        const int c = order[i];
-        if (sc[c] < 0) continue;
-        scores[k] = sc[c]; lead[k] = oi[7]; moves[k] = mv[c];
-        k++;
+    for (int i = 0; i < n; i++) {
+        const int* li = oi.data() + (size_t)i * stride;
+        scores[i] = of[i]; lead[i] = li[0]; moves[i] = li[1];
+        if (var_len) var_len[i] = li[2];
+        if (var_pairs) for (int k = 0; k < 2 * li[2]; k++) var_pairs[i * 2 * depth + k] = li[3 + k];
     }
-    return k;
+    return n;
+}
+extern "C" int gz_player_tree_debug(gz_player* p, int max_count, float* scores, int* lead, int* moves) {
+    return gz_player_tree_debug_lines(p, max_count, scores, lead, moves, nullptr, nullptr);
 }
 
 static int player_issue_next(gz_player* p) {

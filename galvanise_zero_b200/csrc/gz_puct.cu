@@ -1197,6 +1197,92 @@ extern "C" int gz_puct_snapshot(gz_puct* h, int g, int max_children, int* out_i,
     return out_i[8];
 }
 
+// Player::treeDebugInfo / PuctNode::debug (player.cpp:137-153, node.cpp:376-441): the root's children ordered by
+// traversals, then by their node's score for the root's lead role; for each of the first max_count that is expanded:
+// score, lead role, move, and the principal variation below it — at every node with at least 100 visits the child
+// with the most traversals (ties: larger prior), up to `depth` plies — as (lead role, move) pairs.
+// out_i per line: [lead, move, n_var, var pairs (2 * depth)]; out_f per line: score. Returns lines written.
+__global__ void puct_tree_debug_kernel(const __grid_constant__ PuctEngine E, int g, int max_count, int depth,
+                                       int* out_n, int* out_i, float* out_f) {
+    GameView V = gzp_view(&E, g);
+    const GameCtl& c = *V.c;
+    *out_n = 0;
+    if (c.root < 0 || c.n_nodes <= 0) return;
+    const int n = c.root;
+    const int nc = NODE(n_nchild, n), c0 = NODE(n_child0, n), lead = NODE(n_lead, n);
+    const int stride = 3 + 2 * depth;
+    int lines = 0;
+    // selection of the next child in sortedChildrenDebug order: strictly after (prev_trav, prev_score, prev_index)
+    long long prev_trav = 1ll << 40;
+    float prev_score = 3.0e38f;
+    int prev_idx = -1;
+    const int limit = max_count < nc ? max_count : nc;
+    for (int rank = 0; rank < limit; rank++) {
+        int best = -1;
+        long long bt = -1;
+        float bs = -3.0e38f;
+        for (int i = 0; i < nc; i++) {
+            const long long t = (long long)CHILD(c_trav, c0 + i);
+            const int to = CHILD(c_to, c0 + i);
+            const float sc = to >= 0 ? NSCORE(to, lead) : -1.0f;
+            // comes after the previous pick?
+            const bool after = t < prev_trav || (t == prev_trav && (sc < prev_score || (sc == prev_score && i > prev_idx)));
+            if (!after) continue;
+            if (best < 0 || t > bt || (t == bt && sc > bs)) { best = i; bt = t; bs = sc; }
+        }
+        if (best < 0) break;
+        prev_trav = bt; prev_score = bs; prev_idx = best;
+        const int to0 = CHILD(c_to, c0 + best);
+        if (to0 < 0) continue;                      // PuctNode::debug leaves an unexpanded child's line empty
+        int* li = out_i + lines * stride;
+        li[0] = lead;
+        li[1] = CHILD(c_move, c0 + best);
+        out_f[lines] = NSCORE(to0, lead);
+        int nv = 0, cur = to0;
+        for (int d = 0; d < depth; d++) {
+            if (cur < 0 || NODE(n_nchild, cur) == 0 || NODE(n_visits, cur) < 100u) break;
+            const int kc = NODE(n_nchild, cur), k0 = NODE(n_child0, cur);
+            int top = 0;
+            for (int i = 1; i < kc; i++) {
+                const uint32_t ti = CHILD(c_trav, k0 + i), tt = CHILD(c_trav, k0 + top);
+                if (ti > tt || (ti == tt && CHILD(c_prob, k0 + i) > CHILD(c_prob, k0 + top))) top = i;
+            }
+            li[3 + 2 * nv] = NODE(n_lead, cur);
+            li[4 + 2 * nv] = CHILD(c_move, k0 + top);
+            nv++;
+            cur = CHILD(c_to, k0 + top);
+        }
+        li[2] = nv;
+        lines++;
+    }
+    *out_n = lines;
+}
+
+extern "C" int gz_puct_tree_debug(gz_puct* h, int g, int max_count, int depth, int* h_out_i, float* h_out_f, void* stream) {
+    if (!h || g < 0 || g >= h->E.G || max_count < 0 || depth < 0 || !h_out_i || !h_out_f) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
+    if (max_count == 0) return 0;
+    GZ_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    { int jrc = join_side(h, s); if (jrc != GZ_OK) return jrc; }
+    const int stride = 3 + 2 * depth;
+    const size_t bytes = 16 + (size_t)max_count * stride * 4 + (size_t)max_count * 4;
+    void* d = nullptr;
+    GZ_CUDA(cudaMalloc(&d, bytes));
+    int* dn = (int*)d;
+    int* di = dn + 4;
+    float* df = (float*)(di + (size_t)max_count * stride);
+    puct_tree_debug_kernel<<<1, 1, 0, s>>>(h->E, g, max_count, depth, dn, di, df);
+    int lines = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&lines, dn, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out_i, di, (size_t)max_count * stride * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out_f, df, (size_t)max_count * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (e != cudaSuccess) { gz_set_error("tree debug failed: %s", cudaGetErrorString(e)); return GZ_ERR_CUDA; }
+    return lines;
+}
+
 extern "C" int gz_synth_nn(const void* d_planes, int plane_dtype, int64_t n, int total, uint64_t seed, int n_roles,
                            const int* h_role_sizes, int n_rewards, float* d_policy, float* d_value, void* stream) {
     if (!d_planes || !d_policy || !d_value || n_roles < 1 || n_roles > GZP_MAX_ROLES) { gz_set_error("bad argument"); return GZ_ERR_ARG; }

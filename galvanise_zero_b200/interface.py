@@ -157,6 +157,7 @@ def _declare_host(L):
     L.gz_player_get_move.argtypes = [vp, ci, ctypes.POINTER(ci), fp, ctypes.POINTER(ci)]
     L.gz_player_balance_moves.argtypes = [vp, ci]
     L.gz_player_tree_debug.argtypes = [vp, ci, vp, vp, vp]
+    L.gz_player_tree_debug_lines.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     L.gz_player_poll.argtypes = [vp, ci, ctypes.POINTER(vp), ci, ctypes.POINTER(fp)]
     L.gz_player_last_search.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci]
     L._gz_host_declared = True
@@ -361,8 +362,7 @@ class Player(object):
     hands out up to ``batch_size`` leaves of the one tree and expects as many predictions back
     (``evaluator.cpp:722-742,1050-1079``, ``scheduler.cpp:131-203``).
 
-    Differences from the reference (DESIGN.md §7): ``player_balance_moves`` is accepted and does nothing;
-    ``player_tree_debug`` reports no variation lines."""
+    Differences from the reference: ``player_balance_moves`` is accepted and does nothing."""
 
     def __init__(self, sm, c_transformer, puct_conf_dict, device=0, seed=0x5EED0001, node_cap=1 << 16,
                  child_cap=None):
@@ -448,16 +448,20 @@ class Player(object):
         _lib.check(self._L.gz_player_balance_moves(self._h, int(max_count)))
 
     def player_tree_debug(self, max_count):
-        """-> tuple of (score, lead_role_index, move_index, variation) for the root's most visited
-        expanded children (``src/cpp/puct/node.cpp:400-440``); variation lines are not reported."""
+        """-> tuple of (score, lead_role_index, move_index, variation) for the root's expanded children by traversals,
+        ``variation`` = the principal line below each as ((lead_role_index, move_index), ..): at most 10 plies, through
+        nodes with at least 100 visits (``src/cpp/puct/node.cpp:376-441``, ``player_impl.cpp:67-100``)."""
         n = max(0, int(max_count))
-        sc = np.zeros(max(n, 1), dtype=np.float32)
-        ld = np.zeros(max(n, 1), dtype=np.int32)
-        mv = np.zeros(max(n, 1), dtype=np.int32)
-        k = self._L.gz_player_tree_debug(self._h, n, sc.ctypes.data, ld.ctypes.data, mv.ctypes.data)
+        m = max(n, 1)
+        sc = np.zeros(m, dtype=np.float32)
+        ld, mv, vl = np.zeros(m, dtype=np.int32), np.zeros(m, dtype=np.int32), np.zeros(m, dtype=np.int32)
+        vp = np.zeros((m, 10, 2), dtype=np.int32)
+        k = self._L.gz_player_tree_debug_lines(self._h, n, sc.ctypes.data, ld.ctypes.data, mv.ctypes.data,
+                                               vl.ctypes.data, vp.ctypes.data)
         if k < 0:
             _lib.check(k)
-        return tuple((float(sc[i]), int(ld[i]), int(mv[i]), ()) for i in range(k))
+        return tuple((float(sc[i]), int(ld[i]), int(mv[i]),
+                      tuple((int(vp[i, j, 0]), int(vp[i, j, 1])) for j in range(int(vl[i])))) for i in range(k))
 
     def last_search(self):
         """Additive: the root's children after the last finished search (dict as ``PuctEngine.snapshot``), or None."""

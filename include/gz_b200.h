@@ -239,6 +239,9 @@ int gz_puct_advance_compact(gz_puct* h, const float* d_policy_c, const float* d_
 /* Measurement aid: d_buf = device int64 [G][4] (or null to stop): per game the cycles its warp spent in the last
  * puct_pre_kernel launch, entry*256+exit phase, playouts finished, moves*65536 + path_len*256 + request. */
 int gz_puct_set_debug_cycles(gz_puct* h, long long* d_buf);
+/* PuctNode::debug for game g's root (src/cpp/puct/node.cpp:376-441): per line h_out_i[(3 + 2*depth) * i] = lead role,
+ * move, n pairs, then the (lead role, move) pairs of the variation; h_out_f[i] = score. Returns the lines written. */
+int gz_puct_tree_debug(gz_puct* h, int g, int max_count, int depth, int* h_out_i, float* h_out_f, void* stream);
 /* Per engine step a game runs until it needs the batch pipeline (a propnet pass / the network), but at most
  * `max_iters` controller iterations and `max_work` tree levels descended (playouts that end in terminal or
  * finalised nodes need no pipeline pass; the slowest game sets the duration of the step). Defaults 16 / 8.
@@ -301,6 +304,10 @@ int gz_player_move(gz_player* p, const uint32_t* h_state, int evaluations, doubl
 int gz_player_get_move(gz_player* p, int role, int* move, float* score, int* nodes);
 int gz_player_balance_moves(gz_player* p, int max_count);
 int gz_player_tree_debug(gz_player* p, int max_count, float* scores, int* lead, int* moves);
+/* ... with the variation lines of PuctNode::debug (src/cpp/puct/node.cpp:400-441): var_len[i] (lead role, move) pairs
+ * at var_pairs + 20 * i (at most 10 plies). */
+int gz_player_tree_debug_lines(gz_player* p, int max_count, float* scores, int* lead, int* moves, int* var_len,
+                               int* var_pairs);
 int gz_player_poll(gz_player* p, int n_pred, const float* const* h_arrays, int n_arrays, const float** h_planes);
 int gz_player_last_search(gz_player* p, int* out_i16, float* out_f8, int* moves, int* trav, float* prob, float* score,
                           float* next_prob, int cap);

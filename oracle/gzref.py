@@ -135,11 +135,20 @@ class RefEngine:
         cs = np.full((max(n, 1), 4), -1.0, dtype=np.float32)
         self.L.gzref_last_choice_scores.argtypes = [ctypes.c_void_p, ctypes.c_int]
         self.L.gzref_last_choice_scores(cs.ctypes.data, cs.size)
+        dbg = np.zeros((max(n, 1), 3, 25), dtype=np.float32)
+        self.L.gzref_last_debug.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        self.L.gzref_last_debug(dbg.ctypes.data, dbg.size)
         out = []
         for m in range(n):
             k = int(counts[m])
+            lines = []
+            for ln in dbg[m]:
+                if ln[0] > 0:       # (an unexpanded child leaves its line empty, node.cpp:412-414)
+                    nv = int(ln[4])
+                    lines.append((float(ln[1]), int(ln[2]), int(ln[3]),
+                                  tuple((int(ln[5 + 2 * v]), int(ln[6 + 2 * v])) for v in range(nv))))
             out.append({'moves': move[m, :k].copy(), 'traversals': trav[m, :k].copy(),
-                        'choice_scores': cs[m].copy(),
+                        'choice_scores': cs[m].copy(), 'tree_debug': tuple(lines),
                         'policy_prob': prob[m, :k].copy(), 'scores': score[m, :k].copy(),
                         'choice': int(choice[m]), 'root_visits': int(root[m, 0]),
                         'lead_role': int(root[m, 1]), 'root_score': float(root[m, 2]),

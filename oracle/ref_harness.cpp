@@ -405,6 +405,15 @@ extern "C" int gzref_last_choice_scores(float* out, int cap) {
     return n;
 }
 
+/* PuctNode::debug of the root's first three children in debug order, per move of the last gzref_search
+ * (Player::treeDebugInfo, player.cpp:137-153): per line 24 floats = valid, score, lead, move, n pairs, 10 x (lead, move) */
+static std::vector<float> g_last_debug;
+extern "C" int gzref_last_debug(float* out, int cap) {
+    const int n = (int)g_last_debug.size() < cap ? (int)g_last_debug.size() : cap;
+    for (int i = 0; i < n; i++) out[i] = g_last_debug[i];
+    return n;
+}
+
 extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* root_state, int evals, int n_moves,
                             uint64_t nn_seed, int max_children, int* out_counts, int* out_move, int* out_trav,
                             float* out_prob, float* out_score, int* out_choice, float* out_root) {
@@ -423,6 +432,7 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
     int done_moves = 0;
     const int R = g->gt.n_roles;
     g_last_choice_scores.clear();
+    g_last_debug.clear();
     auto f = [&]() {
         pe->reset(0);
         PuctNode* node = pe->establishRoot(root_bs);
@@ -447,6 +457,20 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
             done_moves = m + 1;
             for (int r = 0; r < 4; r++)
                 g_last_choice_scores.push_back(r < R && choice->to_node ? choice->to_node->getCurrentScore(r) : -1.0f);
+            for (int ii = 0; ii < 3; ii++) {
+                PuctNodeDebug info;
+                info.score = -2.0f; info.lead_role_index = -2; info.move_index = -2;
+                if (ii < node->num_children) PuctNode::debug(node, ii, 10, info);
+                float line[25] = {0};
+                line[0] = info.lead_role_index != -2 ? 1.0f : 0.0f;
+                line[1] = info.score; line[2] = (float)info.lead_role_index; line[3] = (float)info.move_index;
+                line[4] = (float)info.variation.size();
+                for (size_t v = 0; v < info.variation.size() && v < 10; v++) {
+                    line[5 + 2 * v] = (float)info.variation[v].lead_role_index;
+                    line[6 + 2 * v] = (float)info.variation[v].move_index;
+                }
+                for (int q = 0; q < 25; q++) g_last_debug.push_back(line[q]);
+            }
             node = pe->fastApplyMove(choice);
             if (getenv("GZREF_TRACE")) fprintf(stderr, "A %d nodes %d root_visits %d\n", m, (int)pe->nodeCount(), (int)node->visits);
         }

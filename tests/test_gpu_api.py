@@ -128,6 +128,7 @@ class _SynthNN(object):
 
 
 @pytest.mark.parametrize('game,evals,moves,batch', [('reversi', 150, 12, 1), ('breakthroughSmall', 200, 10, 1),
+                                                    ('breakthroughSmall', 2500, 4, 1),     # variation lines several plies deep
                                                     ('reversi', 300, 10, 32), ('breakthroughSmall', 400, 12, 8)])
 def test_play_poller_matches_reference_search(game, evals, moves, batch):
     """PUCTPlayer's call sequence (src/ggpzero/player/puctplayer.py:60-95) through PlayPoller /
@@ -173,6 +174,10 @@ def test_play_poller_matches_reference_search(game, evals, moves, batch):
         assert ls.get_count() == 1 and ls.get_legal(0) == other       # the non-lead role's only move
         dbg = poller.player_tree_debug(3)
         assert len(dbg) >= 1 and dbg[0][1] == lead
+        # Player::treeDebugInfo (player.cpp:137-153): scores, moves and the variation lines are the reference's
+        assert len(dbg) == len(r['tree_debug'])
+        for mine_ln, ref_ln in zip(dbg, r['tree_debug']):
+            assert abs(mine_ln[0] - ref_ln[0]) < 1e-6 and mine_ln[1:] == ref_ln[1:]
         jm = sm.get_joint_move()
         jm.set(lead, mv)
         jm.set(1 - lead, other)
