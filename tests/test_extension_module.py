@@ -145,7 +145,10 @@ def test_player_through_the_extension_module_matches_reference_search():
         other, other_score, _ = player.player_get_move(1 - lead)
         assert abs(other_score - float(r['choice_scores'][1 - lead])) < 1e-6
         dbg = player.player_tree_debug(3)
-        assert len(dbg) >= 1 and dbg[0][1] == lead and dbg[0][3] == ()
+        assert len(dbg) >= 1 and dbg[0][1] == lead
+        assert len(dbg) == len(r['tree_debug'])      # (score, lead, move, ((lead, move), ..)), player_impl.cpp:67-100
+        for mine_ln, ref_ln in zip(dbg, r['tree_debug']):
+            assert abs(mine_ln[0] - ref_ln[0]) < 1e-6 and tuple(mine_ln[1:]) == tuple(ref_ln[1:])
         jm = sm.get_joint_move()
         jm.set(lead, mv)
         jm.set(1 - lead, other)
