@@ -250,7 +250,20 @@ pn_kernel(const __grid_constant__ PnParams P, const __grid_constant__ GroupTable
                 prog[k] = P.prog[k];
             }
         }
-        staging = total != 0;
+        staging = total != 0 && WPT > 1;
+        if (WPT == 1 && total != 0) {
+            // a persistent CTA of many warps with a tile each: plain cooperative copy (measured: the bulk-copy path
+            // costs this configuration 5 % — reversi 573 -> 534 M transitions/s — for no gain, staging happens once)
+            uint32_t* dst = smem;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (P.staged[k]) {
+                    for (int i = threadIdx.x; i < P.words[k]; i += blockDim.x) dst[i] = P.prog[k][i];
+                    dst += (P.words[k] + 3) & ~3;
+                }
+            }
+            __syncthreads();
+        }
         if (staging) {
             if (threadIdx.x == 0) bulk_bar_init(&stage_bar);
             __syncthreads();
