@@ -345,7 +345,7 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
 # ------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of one puct_pre_kernel launch in the bench configuration
 # (ncu --set full capture in the bench's own steady-state regime, profiles/r02_puct_pre_kernel_ncu_full.md)
-PUCT_PRE_NCU_TRAFFIC_BYTES = 36432128
+PUCT_PRE_NCU_TRAFFIC_BYTES = 40281600     # 20.21 MB read + 20.07 MB written, final capture of round 2
 PUCT_PRE_NCU_TRAFFIC_SOURCE = 'ncu --set full, profiles/r02_puct_pre_kernel_ncu_full.md (dram read+write per launch)'
 PUCT_GAME = 'reversi'
 PUCT_EVALS_PER_MOVE = 800

@@ -770,6 +770,7 @@ static int build_group_tables(gz_propnet* pn, const int32_t* h) {
     // connect6 92 M vs 685 M), and inside the PUCT step it cost 1.23 ms against 0.31 ms.
     pn->group_min_batch = (P.wide && pn->group_cl == 8) ? GROUP_GAMES : -1;
     pn->group_clusters = pn->group_cl == 8 ? pn->n_sms / 8 : pn->n_sms;
+    { const char* gc = getenv("GZ_GROUP_CLUSTERS"); if (gc && atoi(gc) > 0) pn->group_clusters = std::min(pn->group_clusters, atoi(gc)); }   // measurement switch
     const int64_t slices = std::max<int64_t>((int64_t)P.nbw * 32 * GROUP_TILES, (int64_t)GROUP_TILES * GZ_PN_MAX_ROLES * 32);
     pn->group_stride = (((int64_t)P.val_words * GROUP_TILES + slices + 2 * GROUP_TILES) + 31) & ~(int64_t)31;
     return GZ_OK;
