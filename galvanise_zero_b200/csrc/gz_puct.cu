@@ -710,8 +710,9 @@ extern "C" int gz_puct_set_debug_cycles(gz_puct* h, long long* d_buf) {
 __global__ void compact_cap_kernel(const int* __restrict__ count, int cap, int* __restrict__ n_out) {
     *n_out = *count < cap ? *count : cap;
 }
-__global__ void compact_gather_kernel(const uint4* __restrict__ planes, const int* __restrict__ rows,
-                                      const int* __restrict__ n_ptr, int row_vec, uint4* __restrict__ out) {
+template <typename T>
+__global__ void compact_gather_kernel(const T* __restrict__ planes, const int* __restrict__ rows,
+                                      const int* __restrict__ n_ptr, int row_vec, T* __restrict__ out) {
     const int n = *n_ptr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n * row_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / row_vec), c = (int)(i - (int64_t)r * row_vec);
@@ -754,7 +755,7 @@ static int compact_init(gz_puct* h) {
 // of waiting rows with an asynchronous copy.
 extern "C" int gz_puct_compact_requests(gz_puct* h, int cap, const void* d_planes, int64_t row_bytes, void* d_planes_c,
                                         int* h_count_pinned, void* stream) {
-    if (!h || !d_planes || !d_planes_c || cap < 1 || row_bytes <= 0 || (row_bytes & 15)) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
+    if (!h || !d_planes || !d_planes_c || cap < 1 || row_bytes <= 0 || (row_bytes & 1)) { gz_set_error("bad argument"); return GZ_ERR_ARG; }
     int rc = compact_init(h);
     if (rc != GZ_OK) return rc;
     GZ_CUDA(cudaSetDevice(h->device));
@@ -764,10 +765,17 @@ extern "C" int gz_puct_compact_requests(gz_puct* h, int cap, const void* d_plane
     // has run, and the network forward that follows keeps overlapping that work
     hostpoll_compact_kernel<<<1, 1024, 0, s>>>(h->E.x_need_eval, h->E.G, h->c_rows, h->c_count);
     compact_cap_kernel<<<1, 1, 0, s>>>(h->c_count, cap, h->c_count + 1);
-    const int row_vec = (int)(row_bytes / 16);
+    // rows are copied in the widest unit their size allows (hexLG13: 5 x 13 x 13 bf16 = 1690 bytes -> 2-byte units)
+    const int unit = (row_bytes % 16 == 0 && ((uintptr_t)d_planes % 16 == 0) && ((uintptr_t)d_planes_c % 16 == 0)) ? 16 : (row_bytes % 4 == 0 ? 4 : 2);
+    const int row_vec = (int)(row_bytes / unit);
     const int64_t work = (int64_t)std::min(cap, h->E.G) * row_vec;
-    compact_gather_kernel<<<(int)std::min<int64_t>((work + 255) / 256, 1184), 256, 0, s>>>(
-        (const uint4*)d_planes, h->c_rows, h->c_count + 1, row_vec, (uint4*)d_planes_c);
+    const int ggrid = (int)std::min<int64_t>((work + 255) / 256, 1184);
+    if (unit == 16)
+        compact_gather_kernel<uint4><<<ggrid, 256, 0, s>>>((const uint4*)d_planes, h->c_rows, h->c_count + 1, row_vec, (uint4*)d_planes_c);
+    else if (unit == 4)
+        compact_gather_kernel<uint32_t><<<ggrid, 256, 0, s>>>((const uint32_t*)d_planes, h->c_rows, h->c_count + 1, row_vec, (uint32_t*)d_planes_c);
+    else
+        compact_gather_kernel<uint16_t><<<ggrid, 256, 0, s>>>((const uint16_t*)d_planes, h->c_rows, h->c_count + 1, row_vec, (uint16_t*)d_planes_c);
     GZ_CUDA(cudaGetLastError());
     if (h_count_pinned) GZ_CUDA(cudaMemcpyAsync(h_count_pinned, h->c_count, 4, cudaMemcpyDeviceToHost, s));
     return GZ_OK;

@@ -226,7 +226,7 @@ int gz_puct_totals(gz_puct* h, double* h_out26, void* stream);
 int gz_puct_set_start_states(gz_puct* h, const uint32_t* d_states, void* stream);
 /* Compacted network batches on the device (self-play engines). After a step, gz_puct_compact_requests lists the rows
  * that wait for the network (ascending game order), keeps at most `cap` of them and gathers their planes (rows of
- * row_bytes bytes, a multiple of 16, as gz_puct_advance wrote them) into d_planes_c; h_count_pinned (optional, pinned
+ * row_bytes bytes as gz_puct_advance wrote them) into d_planes_c; h_count_pinned (optional, pinned
  * host memory) receives the uncapped number of waiting rows with an asynchronous copy. gz_puct_advance_compact is the
  * next step: d_policy_c [n][policy_stride] / d_value_c [n][rewards] are the network's outputs for those rows in that
  * order. Requests beyond the cap stay pending (their games wait one more step), so the batch may be sized from a

@@ -253,6 +253,27 @@ def test_compacted_batches_match_full_batches():
     assert same >= 0.95 * len(common), (same, len(common))   # (the UniqueStates table is shared between games)
 
 
+def test_compacted_batches_with_rows_that_are_not_16_byte_multiples():
+    """Plane rows of 6x6 boards (and hexLG13's 13x13) are not a multiple of 16 bytes: the gather falls back to narrower
+    units. The dense batch holds exactly the waiting games' planes, in ascending game order."""
+    from galvanise_zero_b200.engine import PuctEngine
+    sp = confs.selfplay_config_template(evals_per_move=24)
+    G = 96
+    e = PuctEngine('breakthroughSmall', sp, n_games=G, mode=0, node_cap=1024, child_cap=1024 * 24, seed=5)
+    assert (e.planes[0].numel() * e.planes.element_size()) % 16 != 0
+    cnt = torch.zeros(1, dtype=torch.int32).pin_memory()
+    e.run_synthetic(200)
+    dense = e.compact_requests(G, cnt)
+    torch.cuda.synchronize()
+    need = torch.zeros(G, dtype=torch.uint8, device=e.device)
+    e._L.gz_puct_copy_need_eval.argtypes = [__import__('ctypes').c_void_p] * 3
+    e._L.gz_puct_copy_need_eval(e._h, need.data_ptr(), e._stream())
+    torch.cuda.synchronize()
+    rows = torch.nonzero(need).flatten()
+    assert int(cnt[0]) == len(rows) and 0 < len(rows) <= G
+    assert torch.equal(dense[:len(rows)], e.planes[rows])
+
+
 def test_async_advance_matches_joined_advance():
     """gz_puct_advance_async + gz_puct_join (the network call overlaps the step's side-stream work: re-rooting,
     goal values and nodes of terminal states) leaves the engine in exactly the state the joined gz_puct_advance

@@ -5,9 +5,11 @@ import numpy as np
 import torch
 from galvanise_zero_b200.engine import PuctEngine
 from galvanise_zero_b200.defs import confs
-G = 4096
+G = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+GAME = sys.argv[2] if len(sys.argv) > 2 else 'reversi'
+CC = int(sys.argv[4]) if len(sys.argv) > 4 else 4096 * 16
 sp = confs.selfplay_config_template(evals_per_move=800)
-eng = PuctEngine('reversi', sp, n_games=G, mode=0, node_cap=4096, child_cap=4096 * 16)
+eng = PuctEngine(GAME, sp, n_games=G, mode=0, node_cap=4096, child_cap=CC)
 eng.run_synthetic(int(sys.argv[1]) if len(sys.argv) > 1 else 3000)
 buf = torch.zeros((G, 4), dtype=torch.int64, device=eng.device)
 eng._L.gz_puct_set_debug_cycles.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
