@@ -784,6 +784,47 @@ GZP_HDN void gzp_order_children(GameView& V, int nc, Cmp cmp) {
     gzp_std_sort(order, nc, cmp);
 }
 
+#ifdef __CUDA_ARCH__
+// Wide nodes (hexLG13 170 children, connect6 361, amazons 2176): ranking every child against every other through the
+// comparator costs two comparator calls per pair. Both orders used on the select path are lexicographic orders
+// of plain values, so a child gets ONE 64-bit key (larger = earlier) and the ranking loop is a load, a compare and
+// an add per pair. Equal keys (= children the comparator calls equivalent) hand the node back to
+// gzp_order_children, whose restated std::sort decides ties as the reference's library does.
+__device__ __forceinline__ unsigned gzp_fkey(float f) {          // monotonic float -> unsigned (-0 -> +0 first)
+    const unsigned u = __float_as_uint(f + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __noinline__ bool gzp_order_by_key(GameView& V, int nc, const unsigned long long* key) {
+    int* order = V.C.order;
+    int* rk = reinterpret_cast<int*>(V.C.tmp);
+    __syncwarp();
+    bool tie = false;
+    for (int i = V.lane; i < nc; i += 32) {
+        const unsigned long long ki = key[i];
+        int rank = 0;
+        for (int j = 0; j < nc; j++) {
+            const unsigned long long kj = key[j];
+            rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
+            tie |= kj == ki && j != i;
+        }
+        rk[i] = rank;
+    }
+    if (__any_sync(0xffffffffu, tie)) {
+        // equivalent children (a synthetic network floors many priors to the same 0.001): the restated introsort
+        // decides, as the reference's library would — with the keys as its comparator (the same truth table as
+        // the value comparator for every pair, a third of its instructions)
+        __syncwarp();
+        for (int i = 0; i < nc; i++) order[i] = i;
+        gzp_std_sort(order, nc, [key](int a, int b) { return key[a] > key[b]; });
+        __syncwarp();
+        return true;
+    }
+    for (int i = V.lane; i < nc; i += 32) order[rk[i]] = i;
+    __syncwarp();
+    return true;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // chooseTopVisits (evaluator.cpp:1100-1159). Sort key: traversals desc, then policy_prob desc
 // (node.cpp:346-373), ordered with the restated std::sort.
@@ -793,6 +834,17 @@ GZP_RARE int gzp_choose_top_visits(const GameView& V, int n, int nc_known = -1) 
     const PuctConf& cf = gzp_conf(V);
     const ChildCache& C = V.C;
     int* order = C.order;
+    bool ordered = false;
+#ifdef __CUDA_ARCH__
+    if (nc > 32) {
+        unsigned long long* key = reinterpret_cast<unsigned long long*>(C.expl);     // (free until select fills it)
+        __syncwarp();
+        for (int i = V.lane; i < nc; i += 32)
+            key[i] = ((unsigned long long)(unsigned)(int)C.trav[i] << 32) | gzp_fkey(C.prob[i]);
+        ordered = gzp_order_by_key(const_cast<GameView&>(V), nc, key);
+    }
+#endif
+    if (!ordered)
     gzp_order_children(const_cast<GameView&>(V), nc, [&C](int a, int b) {
         const int ta = (int)C.trav[a], tb = (int)C.trav[b];
         if (ta == tb) return C.prob[a] > C.prob[b];
@@ -1140,6 +1192,21 @@ GZP_RARE int gzp_select_child_generic(GameView& V, int n, const GzpNode& nd, Gzp
     // iterate children in sortedChildrenSelect order (evaluator.cpp:242-263): key sa = node score
     // for the lead role (-1 when unexpanded); both negative -> policy_prob_orig desc, else sa desc.
     int* order = C.order;
+    bool ordered = false;
+#ifdef __CUDA_ARCH__
+    if (nc > 32) {
+        // children with a non-negative score first, by score; the others (unexpanded, or a lost terminal's -0.05)
+        // after them, by their original prior — the comparator below, as one key
+        unsigned long long* key = reinterpret_cast<unsigned long long*>(C.expl);     // (filled with the exploration terms afterwards)
+        __syncwarp();
+        for (int i = V.lane; i < nc; i += 32) {
+            const float sc = C.score[i];
+            key[i] = sc < 0 ? (unsigned long long)gzp_fkey(C.prob_orig[i]) : ((1ULL << 32) | gzp_fkey(sc));
+        }
+        ordered = gzp_order_by_key(V, nc, key);
+    }
+#endif
+    if (!ordered)
     gzp_order_children(V, nc, [&C](int a, int b) {
         const float sa = C.score[a], sb = C.score[b];     // -1 when unexpanded
         if (sa < 0 && sb < 0) return C.prob_orig[a] > C.prob_orig[b];
@@ -1607,6 +1674,17 @@ GZP_RARE bool gzp_converged_generic(GameView& V, int count, int n, int nc) {
     gzp_cache_fill(V, n);
     const ChildCache& C = V.C;
     int* order = C.order;
+    bool ordered = false;
+#ifdef __CUDA_ARCH__
+    if (nc > 32) {
+        unsigned long long* key = reinterpret_cast<unsigned long long*>(C.expl);
+        __syncwarp();
+        for (int i = V.lane; i < nc; i += 32)
+            key[i] = ((unsigned long long)(unsigned)(int)C.visits[i] << 32) | gzp_fkey(C.prob[i]);
+        ordered = gzp_order_by_key(V, nc, key);
+    }
+#endif
+    if (!ordered)
     gzp_order_children(V, nc, [&C](int a, int b) {
         const int va = (int)C.visits[a], vb = (int)C.visits[b];     // 0 when unexpanded
         if (va == vb) return C.prob[a] > C.prob[b];
