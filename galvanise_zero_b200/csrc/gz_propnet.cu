@@ -689,7 +689,8 @@ static int configure_launch(gz_propnet* pn, const int32_t* h) {
     P.warp_words = ((P.val_words + 32 * rs + P.nbw * 32) + 3) & ~3;
     const size_t warp_bytes = (size_t)P.warp_words * 4;
     // stage programs (A, LT, GL in that priority) while at least MIN_WARPS warps still fit
-    const int MIN_WARPS = 8;
+    int MIN_WARPS = 8;
+    { const char* mw = getenv("GZ_PN_MIN_WARPS"); if (mw && atoi(mw) > 0) MIN_WARPS = atoi(mw); }   // measurement switch
     size_t staged = 0;
     for (int k = 0; k < 3; ++k) {
         const size_t w = (size_t)((P.words[k] + 3) & ~3) * 4;
