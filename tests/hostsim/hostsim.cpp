@@ -42,6 +42,8 @@ struct HostSim {
     pnref_sm* sm;
     encref* enc;
     std::vector<float> policy, value, planes;
+    std::vector<uint8_t> answered;     // compacted batches: which games' predictions arrived with this step
+    int answer_cap = 0;                // > 0: at most this many requests are answered per step (the rest wait)
     uint64_t nn_seed;
     int total;
     std::vector<int> legal_word_off;
@@ -191,8 +193,14 @@ extern "C" void hs_step(void* h) {
         gzp_step_post(V);
     }
     if (getenv("GZREF_TRACE")) { int n = 0; for (int g = 0; g < E.G * E.EB; g++) n += E.x_need_eval[g] != 0; if (n) fprintf(stderr, "B %d\n", n); }
+    int answered_now = 0;
     for (int g = 0; g < E.G * E.EB; g++) {          // evaluation rows
         if (!E.x_need_eval[g]) continue;
+        if (H->answer_cap > 0) {                     // gz_puct_compact_requests: ascending rows, capped; overflow waits
+            if (answered_now >= H->answer_cap) continue;
+            H->answered[g] = 1;
+            answered_now++;
+        }
         const uint32_t* prev = E.e_prev + (size_t)g * E.SW;
         const uint32_t* ptrs[1] = {prev};
         encref_to_channels(H->enc, E.e_state + (size_t)g * E.SW, ptrs, E.e_prevcnt[g] ? 1 : 0, H->planes.data());
@@ -202,6 +210,15 @@ extern "C" void hs_step(void* h) {
                 H->policy[(size_t)g * E.policy_stride + E.policy_off[r] + a] = gz_synth_policy(hh, (uint32_t)r, (uint32_t)a);
         gz_synth_values(hh, E.n_rewards, &H->value[(size_t)g * E.n_rewards]);
     }
+}
+
+/* compacted batches (gz_puct_compact_requests / gz_puct_advance_compact): at most `cap` requests per step get their
+ * prediction, the others stay pending */
+extern "C" void hs_set_answer_cap(void* h, int cap) {
+    HostSim* H = (HostSim*)h;
+    H->answer_cap = cap;
+    H->answered.assign((size_t)H->E.G * H->E.EB, 0);
+    H->E.x_answered = cap > 0 ? H->answered.data() : nullptr;
 }
 
 extern "C" GameCtl* hs_ctl(void* h, int g) { return &((HostSim*)h)->E.ctl[g]; }

@@ -30,6 +30,7 @@ def lib():
         L.hs_ready.restype = ctypes.POINTER(ctypes.c_int32)
         L.hs_ready.argtypes = [vp]
         L.hs_srec.argtypes = [vp]
+        L.hs_set_answer_cap.argtypes = [vp, ci]
         L.hs_transpositions.restype = ctypes.c_ulonglong
         L.hs_transpositions.argtypes = [vp, ci]
         L.hs_ctl.restype = vp
@@ -101,6 +102,9 @@ class HostSim:
                 L.hs_root_children(self.h, g, max_children, ti.ctypes.data, ti.ctypes.data, tf.ctypes.data, tf.ctypes.data, inf.ctypes.data)
                 print('A %d nodes %d root_visits %d' % (m, int(inf[3]), int(inf[0])), file=sys.stderr)
         return out
+
+    def set_answer_cap(self, cap):
+        self.L.hs_set_answer_cap(self.h, int(cap))
 
     def transpositions(self, g=0):
         return int(self.L.hs_transpositions(self.h, g))

@@ -203,8 +203,9 @@ def test_selfplay_at_scale_properties():
 def test_compacted_batches_match_full_batches():
     """gz_puct_compact_requests / gz_puct_advance_compact: the network sees only the rows that wait for it. With a cap
     that holds every request the engine ends in exactly the state the full-batch loop leaves it in; with a cap that is
-    too small the overflow waits one more step — every game still plays the same game (its sample records are the
-    same), just later."""
+    too small the overflow waits one more step — nobody is lost, and the samples both runs produce for the same
+    (slot, match, depth) agree (games interact only through the shared UniqueStates table; the exact statement, on
+    searches without that coupling, is tests/test_puct_hostsim.py::test_capped_batches_...)."""
     from galvanise_zero_b200.engine import PuctEngine
     sp = confs.selfplay_config_template(evals_per_move=24)
     sp.puct_config.dirichlet_noise_pct = -1

@@ -164,6 +164,46 @@ def test_selfplay_samples_match_reference_supervisor(game, G, evals, target):
     _selfplay_samples(game, G, evals, target, noise=False)
 
 
+def test_capped_batches_defer_requests_without_changing_any_search():
+    """Compacted network batches (gz_puct_compact_requests / gz_puct_advance_compact): when the batch holds fewer
+    rows than there are requests, the overflow keeps its request and waits one more step. A search is a deterministic
+    process of its own, so four trees searched side by side end with the same visit counts whether one, two or all
+    four requests are answered per step."""
+    from hostsim_util import HostSim
+    ct, eng = _setup('reversi')
+    conf = confs.base_puct_config(dirichlet_noise_pct=0.25, choose='choose_top_visits')
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    G, evals = 4, 150
+    results = []
+    for cap in (0, 1, 2):
+        hs = HostSim(tables.blob_by_name('reversi'), ct, sp, G=G, mode=1)
+        hs.set_answer_cap(cap)
+        L = hs.L
+        for g in range(G):
+            L.hs_cmd_reset(hs.h, g, None, 0)
+        for g in range(G):
+            assert L.hs_wait(hs.h, g, 100000) == 1
+        for g in range(G):
+            L.hs_cmd_search(hs.h, g, evals)
+        for g in range(G):
+            assert L.hs_wait(hs.h, g, 10000000) == 1
+        per_game = []
+        for g in range(G):
+            moves = np.zeros(128, dtype=np.int32); trav = np.zeros(128, dtype=np.int32)
+            prob = np.zeros(128, dtype=np.float32); score = np.zeros(128, dtype=np.float32)
+            info = np.zeros(8, dtype=np.float32)
+            k = L.hs_root_children(hs.h, g, 128, moves.ctypes.data, trav.ctypes.data, prob.ctypes.data,
+                                   score.ctypes.data, info.ctypes.data)
+            per_game.append((trav[:k].copy(), prob[:k].copy(), score[:k].copy(), int(info[0])))
+        results.append(per_game)
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+    # the games differ from each other (their own RNG streams draw their own root noise)
+    assert not np.array_equal(results[0][0][1], results[0][1][1])
+
+
 def test_selfplay_samples_match_with_transposition_lookup():
     """Whole games with shared nodes: every re-root rebuilds the table, samples stay the reference's."""
     _selfplay_samples('breakthroughSmall', 6, 60, 150, noise=False, transpositions=True)
