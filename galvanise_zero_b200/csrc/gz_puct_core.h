@@ -1148,6 +1148,143 @@ __device__ int gzp_warp_select(GameView& V, const GzpKid& K, int nc, uint32_t no
     *chosen_to = __shfl_sync(GZP_FULL, K.to, best_child);
     return best_child;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Wide nodes on the device (more than 32 children: hexLG13 170, connect6 361, chess): the same order-free
+// formulation as gzp_warp_select / gzp_warp_top_visits, over the children staged in shared memory, every lane
+// taking children lane, lane+32, ... — no ordering pass, no sequential scan. Anything the formulation does not
+// cover (the root latch limiter, evaluations in flight below the node, candidates that tie for the maximum) is
+// handed to the generic path, which reproduces the reference's scan step by step.
+__device__ __noinline__ int gzp_wide_top(const GameView& V, int nc, int which, int skip) {
+    // which: 0 all children, 1 proven wins, 2 everything but proven losses; skip: a child to leave out (-1: none)
+    // key: (traversals desc, prior desc) as chooseTopVisits orders (node.cpp:346-373)
+    const ChildCache& C = V.C;
+    unsigned m1 = 0, any = 0;
+    for (int i = V.lane; i < nc; i += 32) {
+        const bool fin = C.to[i] >= 0 && (C.flags[i] & NF_FINALISED);
+        const bool win = fin && C.score[i] > 0.99, loss = fin && C.score[i] < 0.01;
+        const bool pred = i != skip && (which == 0 || (which == 1 ? win : !loss));
+        if (pred) { any = 1; m1 = C.trav[i] > m1 ? C.trav[i] : m1; }
+    }
+    if (!__any_sync(GZP_FULL, any != 0)) return -1;
+    m1 = __reduce_max_sync(GZP_FULL, any ? m1 : 0u);
+    unsigned m2 = 0;
+    for (int i = V.lane; i < nc; i += 32) {
+        const bool fin = C.to[i] >= 0 && (C.flags[i] & NF_FINALISED);
+        const bool win = fin && C.score[i] > 0.99, loss = fin && C.score[i] < 0.01;
+        const bool pred = i != skip && (which == 0 || (which == 1 ? win : !loss));
+        if (pred && C.trav[i] == m1) { const unsigned k = gzp_ordered_bits(C.prob[i]); m2 = k > m2 ? k : m2; }
+    }
+    m2 = __reduce_max_sync(GZP_FULL, m2);
+    int count = 0, idx = 0x7fffffff;
+    for (int i = V.lane; i < nc; i += 32) {
+        const bool fin = C.to[i] >= 0 && (C.flags[i] & NF_FINALISED);
+        const bool win = fin && C.score[i] > 0.99, loss = fin && C.score[i] < 0.01;
+        const bool pred = i != skip && (which == 0 || (which == 1 ? win : !loss));
+        if (pred && C.trav[i] == m1 && gzp_ordered_bits(C.prob[i]) == m2) { count++; idx = i < idx ? i : idx; }
+    }
+    count = __reduce_add_sync(GZP_FULL, count);
+    if (count > 1) return GZP_WARP_PUNT;          // equivalent candidates: std::sort's tie order decides (nc > 16 here)
+    return __reduce_min_sync(GZP_FULL, idx);
+}
+
+__device__ __noinline__ int gzp_wide_top_visits(const GameView& V, int nc, float ratio) {
+    const ChildCache& C = V.C;
+    const int w = gzp_wide_top(V, nc, 1, -1);              // the first proven win in sorted order
+    if (w != -1) return w;
+    const int i0 = gzp_wide_top(V, nc, 2, -1);
+    if (i0 == GZP_WARP_PUNT) return GZP_WARP_PUNT;
+    if (ratio > 0 && i0 >= 0) {
+        const int i1 = gzp_wide_top(V, nc, 2, i0);
+        if (i1 == GZP_WARP_PUNT) return GZP_WARP_PUNT;
+        if (i1 >= 0 && C.to[i0] >= 0 && C.to[i1] >= 0) {
+            const float t0 = (float)C.trav[i0], t1 = (float)C.trav[i1];
+            if (t1 > t0 * ratio && C.score[i1] > C.score[i0]) return i1;
+            return i0;
+        }
+    }
+    return gzp_wide_top(V, nc, 0, -1);                      // order[0]
+}
+
+__device__ __noinline__ int gzp_wide_select(GameView& V, int n, int nc, uint32_t node_visits, float node_final, float puct_c,
+                                            int depth, int* chosen_to) {
+    const PuctConf& cf = gzp_conf(V);
+    ChildCache& C = V.C;
+    if (node_visits > 1000 && node_visits < 40000000 && depth == 0) return GZP_WARP_PUNT;      // root latch limiter
+    gzp_cache_fill(V, n);
+    bool vl = false;
+    for (int i = V.lane; i < nc; i += 32) vl |= C.trav[i] > 0 && C.to[i] >= 0 && C.inflight[i] > 0;
+    if (__any_sync(GZP_FULL, vl)) return GZP_WARP_PUNT;                                       // virtual-loss discount
+    // ---- priorScore (evaluator.cpp:1195-1224)
+    float prior = node_final;
+    if (node_visits > 8) {
+        const int best = gzp_wide_top_visits(V, nc, cf.top_visits_best_guess_converge_ratio);
+        if (best == GZP_WARP_PUNT) return GZP_WARP_PUNT;
+        if (best >= 0 && C.to[best] >= 0) prior = C.score[best];
+    }
+    float fpu = depth == 0 ? cf.fpu_prior_discount_root : cf.fpu_prior_discount;
+    if (fpu > 0) {
+        float total = 0.0f;                      // in child order, as the reference sums
+        for (int j = 0; j < nc; j++) total += (C.to[j] >= 0 && C.visits[j] > 0) ? C.prob[j] : 0.0f;
+        fpu *= sqrtf(total);
+        prior -= fpu;
+    }
+    // ---- every child's score + exploration (evaluator.cpp:393-457), float-rounded into C.tmp; -inf = not eligible
+    const double sqrt_node_visits = sqrt((double)(node_visits + 1u));
+    const float neg_inf = -3.402823466e+38f;
+    unsigned win_best = 0;
+    int win_cnt = 0, win_idx = 0x7fffffff;
+    __syncwarp();
+    for (int i = V.lane; i < nc; i += 32) {
+        const bool expanded = C.to[i] >= 0;
+        double exploration = (double)(puct_c * C.prob[i]) * sqrt_node_visits / ((int)C.trav[i] + 1 + (expanded ? (double)C.inflight[i] : 0.0));
+        double child_score = prior;
+        bool badfb = false, winret = false;
+        if (expanded) {
+            child_score = C.score[i];
+            if (C.flags[i] & NF_FINALISED) {
+                if (child_score > 0.99) {
+                    if (depth > 0) winret = true;
+                    else child_score *= 1.0f + puct_c;
+                } else if (child_score < 0.01) {
+                    badfb = true;
+                } else {
+                    exploration = 0.0;
+                }
+            }
+        }
+        C.tmp[i] = badfb ? neg_inf : (float)(child_score + exploration);
+        if (winret) { const unsigned k = gzp_ordered_bits(C.score[i]); if (k > win_best) win_best = k; }
+    }
+    __syncwarp();
+    int best_child;
+    const unsigned wb = __reduce_max_sync(GZP_FULL, win_best);
+    if (wb) {
+        // a proven win below the root is taken at once: the highest score; equal scores -> the generic scan decides
+        for (int i = V.lane; i < nc; i += 32) {
+            const bool winret = depth > 0 && C.to[i] >= 0 && (C.flags[i] & NF_FINALISED) && C.score[i] > 0.99;
+            if (winret && gzp_ordered_bits(C.score[i]) == wb) { win_cnt++; win_idx = i < win_idx ? i : win_idx; }
+        }
+        if (__reduce_add_sync(GZP_FULL, win_cnt) > 1) return GZP_WARP_PUNT;
+        best_child = __reduce_min_sync(GZP_FULL, win_idx);
+    } else {
+        unsigned fu = 0;
+        for (int i = V.lane; i < nc; i += 32)
+            if (C.tmp[i] != neg_inf) { const unsigned k = gzp_ordered_bits(C.tmp[i]); fu = k > fu ? k : fu; }
+        const unsigned Fu = __reduce_max_sync(GZP_FULL, fu);
+        if (!Fu) return GZP_WARP_PUNT;                   // only proven losses: the generic scan picks the fallback
+        int cnt = 0, idx = 0x7fffffff;
+        float F = 0.0f;
+        for (int i = V.lane; i < nc; i += 32)
+            if (C.tmp[i] != neg_inf && gzp_ordered_bits(C.tmp[i]) == Fu) { cnt++; idx = i < idx ? i : idx; F = C.tmp[i]; }
+        if (__reduce_add_sync(GZP_FULL, cnt) != 1) return GZP_WARP_PUNT;      // several children round to F: scan order decides
+        best_child = __reduce_min_sync(GZP_FULL, idx);
+        F = C.tmp[best_child];
+        if (!(F > -1.0f)) return GZP_WARP_PUNT;          // (float best_score = -1 is never reached by a real score)
+    }
+    *chosen_to = C.to[best_child];
+    return best_child;
+}
 #endif  // __CUDA_ARCH__
 
 // selectChild (evaluator.cpp:341-517). Appends to the path; returns the child index within the
@@ -1402,6 +1539,16 @@ GZP_HDN int gzp_select_child(GameView& V, int n, const GzpNode& nd, GzpSelInfo* 
                 pn[c->path_len] = n; pc[c->path_len] = pick; c->path_len++;
                 if (info) info->to = to;
             }
+            return pick;
+        }
+    } else if (nc > 32 && V.ord && E->EB == 1 && E->tt_cap == 0 && V.C.cap >= nc &&
+               !(depth == 0 && cf.dirichlet_noise_pct >= 0 && !(nd.n_flags & NF_NOISE_SET) &&
+                 !(nd.score[lead < 0 ? 0 : lead] > 0.95))) {
+        int to = -1;
+        const int pick = gzp_wide_select(V, n, nc, node_visits, node_finals[lead < 0 ? 0 : lead], puct_c, depth, &to);
+        if (pick != GZP_WARP_PUNT && pick >= 0) {
+            pn[c->path_len] = n; pc[c->path_len] = pick; c->path_len++;
+            if (info) info->to = to;
             return pick;
         }
     }
