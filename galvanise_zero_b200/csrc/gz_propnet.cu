@@ -624,6 +624,7 @@ struct gz_propnet {
     GroupTables GT{};
     void* d_group_tables = nullptr;
     int group_cl = 1;                    // CTAs per cluster: 1 (narrow levels) or 8 (wide levels)
+    bool group_cl16_ok = false;          // clusters of 16 CTAs can be launched (non-portable size, opt-in per kernel)
     int group_clusters = 0;              // clusters resident at once
     int64_t group_stride = 0;            // scratch words per cluster
     int64_t group_min_batch = GROUP_GAMES;
@@ -770,6 +771,15 @@ static int build_group_tables(gz_propnet* pn, const int32_t* h) {
     // kernel is 15x slower than pn_kernel (r2i_pn_reversi_*: 10 M vs 158 M transitions/s; amazons 24 M vs 44 M,
     // connect6 92 M vs 685 M), and inside the PUCT step it cost 1.23 ms against 0.31 ms.
     pn->group_min_batch = (P.wide && pn->group_cl == 8) ? GROUP_GAMES : -1;
+    if (P.wide && pn->group_cl == 8) {
+        const char* off = getenv("GZ_GROUP_NO_CL16");        // measurement switch
+        bool ok = !(off && off[0] == '1');
+        ok = ok && cudaFuncSetAttribute(pn_group_kernel<MODE_EVAL, true, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(pn_group_kernel<MODE_TRANSITION, true, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(pn_group_kernel<MODE_PLAYOUT, true, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        cudaGetLastError();
+        pn->group_cl16_ok = ok;
+    }
     pn->group_clusters = pn->group_cl == 8 ? pn->n_sms / 8 : pn->n_sms;
     { const char* gc = getenv("GZ_GROUP_CLUSTERS"); if (gc && atoi(gc) > 0) pn->group_clusters = std::min(pn->group_clusters, atoi(gc)); }   // measurement switch
     const int64_t slices = std::max<int64_t>((int64_t)P.nbw * 32 * GROUP_TILES, (int64_t)GROUP_TILES * GZ_PN_MAX_ROLES * 32);
@@ -1002,14 +1012,18 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
                 pn->group_scratch.emplace_back(st, scratch);
             }
         }
+        // few groups (the PUCT step of a wide game: 1024 games = ONE group): a cluster of 16 CTAs (non-portable
+        // size) spreads a level's chunks over twice as many SMs; large batches keep 8, which divides 148 SMs better
+        int cl = pn->group_cl;
+        if (cl == 8 && pn->P.wide && pn->group_cl16_ok && n_groups <= (int64_t)(pn->n_sms / 16)) cl = 16;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(clusters * pn->group_cl));
+        cfg.gridDim = dim3((unsigned)(clusters * cl));
         cfg.blockDim = dim3(GROUP_WARPS * 32);
         cfg.dynamicSmemBytes = 0;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)pn->group_cl;
+        attr[0].val.clusterDim.x = (unsigned)cl;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
@@ -1020,7 +1034,7 @@ static int launch(gz_propnet* pn, int64_t n, int64_t slot0, const uint32_t* stat
 #define GZ_GROUP_LAUNCH(W, C)                                                                                          \
         e = cudaLaunchKernelEx(&cfg, pn_group_kernel<MODE, W, C>, pn->P, pn->GT, n, slot0, states_in, moves_in, states_out, \
                                legal, terminal, goals, moves_out, transitions, seed, step, goals_mode, scratch, stride, nd)
-        if (pn->P.wide) { if (pn->group_cl == 8) GZ_GROUP_LAUNCH(true, 8); else GZ_GROUP_LAUNCH(true, 1); }
+        if (pn->P.wide) { if (cl == 16) GZ_GROUP_LAUNCH(true, 16); else if (cl == 8) GZ_GROUP_LAUNCH(true, 8); else GZ_GROUP_LAUNCH(true, 1); }
         else { if (pn->group_cl == 8) GZ_GROUP_LAUNCH(false, 8); else GZ_GROUP_LAUNCH(false, 1); }
 #undef GZ_GROUP_LAUNCH
         if (e != cudaSuccess) { gz_set_error("group kernel launch failed: %s", cudaGetErrorString(e)); return GZ_ERR_CUDA; }
