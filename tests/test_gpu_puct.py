@@ -226,19 +226,16 @@ def test_compacted_batches_match_full_batches():
                          pol.data_ptr(), val.data_ptr(), e._stream())
     b.advance(None, None); nn_compact(b, G, pol_b, val_b)
     c.advance(None, None); nn_compact(c, 96, pol_c, val_c)
-    seen_partial = False
     for _ in range(2600):
         a.advance(a.policy, a.value); a.synth_nn(seed=3)
         b.advance_compact(pol_b, val_b); nn_compact(b, G, pol_b, val_b)
     torch.cuda.synchronize()
     assert 0 < int(cnt[0]) <= G
-    seen_partial = int(cnt[0]) < G
     ta, tb = a.totals(), b.totals()
     assert ta == tb and ta['moves'] > 1000 and ta['errors'] == 0
     ra, rb = a.fetch_sample_records(), b.fetch_sample_records()
     key = lambda r: [tuple(x) for x in r[np.lexsort(r.T[::-1])]]   # noqa: E731
     assert len(ra) > 0 and key(ra) == key(rb)
-    assert seen_partial or True
     # a cap of half the games: requests overflow, nobody is lost
     got = []
     for _ in range(9000):
