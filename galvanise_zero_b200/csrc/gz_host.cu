@@ -225,7 +225,7 @@ struct gz_player {
     float *d_policy = nullptr, *d_value = nullptr, *d_planes = nullptr, *h_planes = nullptr, *h_row = nullptr;
     std::vector<double> sp_conf, puct_conf;
     struct Cmd { int kind; std::vector<int> moves; std::vector<uint32_t> state; int evals; double end_time; };
-    std::deque<Cmd> queue;      // kind: 1 reset, 2 apply, 3 search
+    std::deque<Cmd> queue;      // kind: 1 reset, 2 apply, 3 search, 4 balance the first `evals` root moves
     bool busy = false, fresh = false, first_play = false;
     int current = 0, waiting = 0, game_depth = 0, rows = 1;
     double search_start = 0, search_end_time = -1;
@@ -360,8 +360,15 @@ extern "C" int gz_player_get_move(gz_player* p, int role, int* move, float* scor
     return GZ_OK;
 }
 
-// puctBalanceFirstMoves (evaluator.cpp:282-339): an analysis aid of the tournament tooling; accepted, no effect
-extern "C" int gz_player_balance_moves(gz_player* p, int max_count) { (void)max_count; return p ? GZ_OK : GZ_ERR_ARG; }
+// Player::balanceNode (player.cpp:121-135) -> PuctEvaluator::balanceFirstMoves (evaluator.cpp:282-339): enqueued; the
+// following polls search the first max_count root moves until each has as many traversals as the most visited one.
+// Needs the search tree's workers (PuctConfig.batch_size > 1, the reference's default); with batch_size 1 the call
+// is accepted and does nothing.
+extern "C" int gz_player_balance_moves(gz_player* p, int max_count) {
+    if (!p) return GZ_ERR_ARG;
+    if (max_count > 0 && p->rows > 1 && !p->first_play) p->queue.push_back({4, {}, {}, max_count, -1});
+    return GZ_OK;
+}
 
 // treeDebug (player.cpp:137-153, node.cpp:376-441): the root's expanded children by traversals (then score) with the
 // principal variation below each (10 plies at most, nodes with at least 100 visits). scores / lead / moves: one per
@@ -404,6 +411,8 @@ static int player_issue_next(gz_player* p) {
         const int lead = oi[7] >= 0 ? oi[7] : 0;
         rc = gz_puct_command(p->eng, 0, GZ_PUCT_CMD_APPLY, c.moves[lead], 0, nullptr, (void*)p->stream);
         p->game_depth++;
+    } else if (c.kind == 4) {
+        rc = gz_puct_command(p->eng, 0, GZ_PUCT_CMD_BALANCE, c.evals, 0, nullptr, (void*)p->stream);
     } else {
         rc = gz_puct_command(p->eng, 0, GZ_PUCT_CMD_SEARCH, 0, c.evals, nullptr, (void*)p->stream);
         p->search_start = gz_now();

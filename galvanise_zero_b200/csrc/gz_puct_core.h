@@ -124,8 +124,13 @@ enum {
     CO_DESCEND,           // inside treePlayout's loop at node `cur`
     CO_SELECT_RESUMED,    // after the yield inside selectChild (bad fallback with unselectable siblings)
     CO_AFTER_PROPNET,     // expandChild: waiting for the propnet pass / node creation
-    CO_AFTER_EVAL         // createNode: blocked in NetworkScheduler::evaluate
+    CO_AFTER_EVAL,        // createNode: blocked in NetworkScheduler::evaluate
+    // balanceFirstMoves (evaluator.cpp:282-339): the first moves of the root are searched until they have as many
+    // traversals as the most visited one
+    CO_BAL_START, CO_BAL_NEXT, CO_BAL_LOOP, CO_BAL_WAIT,
+    CO_BAL_WORKER         // one playout below a given root child, then done
 };
+enum { CO_KIND_LOOP = 0, CO_KIND_ONCE = 1 };       // after a playout: back to the top of the loop / finished
 struct GzpCo {
     int32_t st;
     int32_t cur, path_len;
@@ -133,13 +138,18 @@ struct GzpCo {
     int32_t node;                    // the node created for it
     int32_t sel_to;                  // CO_SELECT_RESUMED: the node the chosen child leads to
     int32_t evaluated;               // the node went to the network (counts as an evaluation when the coroutine resumes)
+    int32_t kind;                    // CO_KIND_*
+    int32_t pad[3];
 };
 struct GzpSched {
     int32_t n_run, n_req, n_yld;     // runnables (FIFO), requestors, yielders
     int32_t current;                 // coroutine that owns the controller (it may be waiting for the propnet pass), -1
     int32_t worker_count, do_playouts, flush_wait, active;
-    int32_t run[GZP_MAX_EB + 1], req[GZP_MAX_EB + 1], yld[GZP_MAX_EB + 1];
-    GzpCo co[GZP_MAX_EB];            // 0: the search itself (onNextMove / playoutMain), 1..: playoutWorker
+    int32_t run[GZP_MAX_EB + 2], req[GZP_MAX_EB + 2], yld[GZP_MAX_EB + 2];
+    GzpCo co[GZP_MAX_EB + 1];        // 0: the search itself (onNextMove / playoutMain / balanceFirstMoves), 1..: workers
+    // balanceFirstMoves
+    int32_t balance, bal_max, bal_i, bal_wanted;
+    int32_t bal_order[32];           // the root's children by traversals (first bal_max of them)
 };
 
 // ---- per-game controller record
@@ -527,7 +537,7 @@ GZP_HD int gzp_pending_on(const PuctEngine* E, int g, int parent, int child) {
     const GzpSched& S = E->sched[g];
     if (!S.active) return 0;
     int n = 0;
-    for (int k = 0; k < E->EB; k++) {
+    for (int k = 0; k <= E->EB; k++) {
         const GzpCo& co = S.co[k];
         if ((co.st == CO_AFTER_PROPNET || co.st == CO_AFTER_EVAL) && co.req_parent == parent &&
             (child < 0 || co.req_child == child)) n++;
@@ -2311,7 +2321,7 @@ GZP_HDN void gzp_request_reroot(GameView& V, int new_root) {
 // into a resumable state machine. gzp_step_pre runs until the game needs the batch pipeline
 // (a propnet transition and possibly a network evaluation); gzp_step_post consumes the propnet
 // outputs and creates the node.
-enum { CMD_NONE = 0, CMD_RESET = 1, CMD_APPLY = 2, CMD_SEARCH = 3 };
+enum { CMD_NONE = 0, CMD_RESET = 1, CMD_APPLY = 2, CMD_SEARCH = 3, CMD_BALANCE = 4 };
 // wall-clock limits of playoutMain (evaluator.cpp:794,820-826: end_time, think_time) live on the host, which
 // tells a running search to stop: GZP_STOP_NOW ("hard" limit, or think time x multiplier without convergence),
 // GZP_STOP_IF_CONVERGED (think time elapsed). Checked where the reference checks its clock: between playouts.
@@ -2514,8 +2524,8 @@ GZP_HD void gzp_queue_push(int32_t* q, int32_t* n, int k) {
 GZP_HD void gzp_co_bind(GameView& V, int k) {     // the controller's playout context becomes coroutine k's
     const PuctEngine* E = V.E;
     GzpSched& S = E->sched[V.g];
-    V.pn = E->co_path_node + ((int64_t)V.g * E->EB + k) * E->MAXD;
-    V.pc = E->co_path_choice + ((int64_t)V.g * E->EB + k) * E->MAXD;
+    V.pn = E->co_path_node + ((int64_t)V.g * (E->EB + 1) + k) * E->MAXD;
+    V.pc = E->co_path_choice + ((int64_t)V.g * (E->EB + 1) + k) * E->MAXD;
     V.c->cur = S.co[k].cur;
     V.c->path_len = S.co[k].path_len;
 }
@@ -2532,8 +2542,8 @@ GZP_RARE void gzp_sched_start(GameView& V) {       // Player::puctPlayerMove: on
     GZP_SYNC();
     S.n_run = 1; S.run[0] = 0; S.n_req = 0; S.n_yld = 0; S.current = -1;
     S.worker_count = 0; S.do_playouts = 1; S.flush_wait = 0; S.active = 1;
-    for (int k = 0; k < GZP_MAX_EB; k++) { S.co[k].st = CO_DEAD; S.co[k].req_parent = -1; S.co[k].req_child = -1; }
-    S.co[0].st = CO_MAIN_START;
+    for (int k = 0; k <= GZP_MAX_EB; k++) { S.co[k].st = CO_DEAD; S.co[k].req_parent = -1; S.co[k].req_child = -1; S.co[k].kind = CO_KIND_LOOP; }
+    S.co[0].st = S.balance ? CO_BAL_START : CO_MAIN_START;
     GZP_SYNC();
 }
 
@@ -2602,6 +2612,7 @@ GZP_RARE int gzp_co_run(GameView& V, int k) {
             if ((nd.n_flags & (NF_FORCE_TERMINAL | NF_FINALISED)) || nd.n_nchild == 0) {
                 gzp_path_push(V, cur, -1);
                 gzp_finish_playout(V, nd);
+                if (co.kind == CO_KIND_ONCE) { co.st = CO_DEAD; S.worker_count = gzp_sync_load(&S.worker_count) - 1; return CO_R_DONE; }
                 co.st = gzp_co_loop_top(k);
                 break;
             }
@@ -2665,12 +2676,79 @@ GZP_RARE int gzp_co_run(GameView& V, int k) {
             if (gzp_is_finalised(V, N) || NODE(n_nchild, N) > 1) {
                 gzp_path_push(V, N, -1);
                 gzp_finish_playout(V, V.E->nodes[V.nb + N]);
+                if (co.kind == CO_KIND_ONCE) { co.st = CO_DEAD; S.worker_count = gzp_sync_load(&S.worker_count) - 1; return CO_R_DONE; }
                 co.st = gzp_co_loop_top(k);
             } else {
                 NODE(n_inflight, N) = NODE(n_inflight, N) + 1;
                 c->cur = N;
                 co.st = CO_DESCEND;
             }
+            break;
+        }
+        case CO_BAL_START: {
+            // balanceFirstMoves (evaluator.cpp:282-339): children by traversals (std::sort, sortedTraversals :265-278)
+            const int root = c->root;
+            if (gzp_is_terminal(V, root)) { co.st = CO_DEAD; return CO_R_DONE; }
+            const int nc = NODE(n_nchild, root);
+            int mm = S.bal_max < nc ? S.bal_max : nc;
+            if (mm > 32) mm = 32;
+            gzp_cache_fill(V, root);
+            ChildCache& C = V.C;
+            int* order = C.order;
+            for (int i = 0; i < nc; i++) order[i] = i;
+            gzp_std_sort(order, nc, [&C](int a, int b) { return C.trav[a] > C.trav[b]; });
+            GZP_SYNC();
+            for (int i = 0; i < mm; i++) S.bal_order[i] = order[i];
+            S.bal_max = mm;
+            S.bal_i = 0;
+            S.bal_wanted = mm > 0 ? (int)C.trav[order[0]] : 0;
+            GZP_SYNC();
+            co.st = CO_BAL_NEXT;
+            break;
+        }
+        case CO_BAL_NEXT: {
+            const int i = gzp_sync_load(&S.bal_i) + 1;
+            GZP_SYNC();
+            S.bal_i = i;
+            GZP_SYNC();
+            if (i >= gzp_sync_load(&S.bal_max)) { co.st = CO_DEAD; return CO_R_DONE; }
+            co.st = CO_BAL_LOOP;
+            break;
+        }
+        case CO_BAL_LOOP: {
+            const int root = c->root;
+            const int child = S.bal_order[gzp_sync_load(&S.bal_i)];
+            const int ci = NODE(n_child0, root) + child;
+            const int to = CHILD(c_to, ci);
+            if ((int)CHILD(c_trav, ci) >= gzp_sync_load(&S.bal_wanted) || to < 0 || gzp_is_terminal(V, to)) { co.st = CO_BAL_NEXT; break; }
+            // batch_size playouts below this child, each its own coroutine, then wait for all of them
+            const int B = gzp_conf(V).batch_size < E->EB ? gzp_conf(V).batch_size : E->EB;
+            for (int w = 1; w <= B; w++) {
+                S.co[w].st = CO_BAL_WORKER;
+                S.co[w].kind = CO_KIND_ONCE;
+                S.co[w].cur = child;            // (which root child; the worker turns it into its path)
+                gzp_queue_push(S.run, &S.n_run, w);
+            }
+            GZP_SYNC();
+            S.worker_count = B;
+            GZP_SYNC();
+            co.st = CO_BAL_WAIT;
+            break;
+        }
+        case CO_BAL_WAIT: {
+            if (gzp_sync_load(&S.worker_count) > 0) { gzp_co_save(V, k); return CO_R_YIELD; }
+            co.st = CO_BAL_LOOP;
+            break;
+        }
+        case CO_BAL_WORKER: {
+            // path = [(root, child)]; treePlayout(child's node, path)
+            const int root = c->root;
+            const int child = co.cur;
+            const int to = CHILD(c_to, NODE(n_child0, root) + child);
+            c->path_len = 0;
+            gzp_path_push(V, root, child);
+            c->cur = to;
+            co.st = CO_DESCEND;
             break;
         }
         default:
@@ -2723,10 +2801,18 @@ GZP_RARE bool gzp_sched_run(GameView& V, bool nn_fresh) {
                     GZP_SYNC();
                     S.active = 0;
                     GZP_SYNC();
-                    V.pn = E->co_path_node + (int64_t)V.g * E->EB * E->MAXD;
-                    V.pc = E->co_path_choice + (int64_t)V.g * E->EB * E->MAXD;
+                    V.pn = E->co_path_node + (int64_t)V.g * (E->EB + 1) * E->MAXD;
+                    V.pc = E->co_path_choice + (int64_t)V.g * (E->EB + 1) * E->MAXD;
                     c->path_len = 0;
                     c->in_playout = 0;
+                    if (gzp_sync_load(&S.balance)) {           // balanceFirstMoves returns to the caller, no move is chosen
+                        GZP_SYNC();
+                        S.balance = 0;
+                        GZP_SYNC();
+                        c->phase = PH_IDLE;
+                        c->cmd_done = 1;
+                        return true;
+                    }
                     c->phase = PH_MOVE_DONE;
                     return false;
                 }
@@ -3002,6 +3088,23 @@ GZP_HDN void gzp_step_pre(GameView& V, bool nn_fresh = true) {
                 return;
             } else if (cmd == CMD_SEARCH) {
                 gzp_start_search(V, c->cmd_evals, 0);
+            } else if (cmd == CMD_BALANCE) {
+                // Player::balanceNode (player.cpp:121-135): only a search tree with workers can do it here; without
+                // them (batch_size 1) the call is accepted and does nothing
+                if (E->EB > 1 && c->root >= 0 && c->cmd_arg > 0) {
+                    GzpSched& S = E->sched[V.g];
+                    GZP_SYNC();
+                    S.balance = 1;
+                    S.bal_max = c->cmd_arg;
+                    S.active = 0;
+                    GZP_SYNC();
+                    c->conf_sel = 0;
+                    c->in_playout = 0;
+                    c->stop_request = GZP_STOP_NONE;
+                    c->phase = PH_SEARCH;
+                } else {
+                    c->cmd_done = 1;
+                }
             }
             break;
         }

@@ -47,8 +47,8 @@ static inline size_t gzp_layout(PuctEngine* E, uint8_t* base) {
         E->e_prev = (uint32_t*)take(G * EB * E->SW * 4);
         E->e_prevcnt = (uint8_t*)take(G * EB);
         E->sched = (GzpSched*)take(G * sizeof(GzpSched));
-        E->co_path_node = (int32_t*)take(G * EB * E->MAXD * 4);
-        E->co_path_choice = (int32_t*)take(G * EB * E->MAXD * 4);
+        E->co_path_node = (int32_t*)take(G * (EB + 1) * E->MAXD * 4);
+        E->co_path_choice = (int32_t*)take(G * (EB + 1) * E->MAXD * 4);
     } else {
         E->e_state = E->x_state;
         E->e_prev = E->x_in_state;

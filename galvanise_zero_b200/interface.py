@@ -362,7 +362,8 @@ class Player(object):
     hands out up to ``batch_size`` leaves of the one tree and expects as many predictions back
     (``evaluator.cpp:722-742,1050-1079``, ``scheduler.cpp:131-203``).
 
-    Differences from the reference: ``player_balance_moves`` is accepted and does nothing."""
+    Differences from the reference: ``player_balance_moves`` needs ``batch_size`` > 1 (it runs on the
+    search tree's workers); with ``batch_size`` 1 it is accepted and does nothing."""
 
     def __init__(self, sm, c_transformer, puct_conf_dict, device=0, seed=0x5EED0001, node_cap=1 << 16,
                  child_cap=None):

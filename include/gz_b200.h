@@ -173,6 +173,7 @@ typedef struct gz_puct gz_puct;
 #define GZ_PUCT_CMD_RESET 1
 #define GZ_PUCT_CMD_APPLY 2
 #define GZ_PUCT_CMD_SEARCH 3
+#define GZ_PUCT_CMD_BALANCE 4   /* arg = how many of the root's first moves (PuctEvaluator::balanceFirstMoves, evaluator.cpp:282-339) */
 
 int gz_puct_create(gz_propnet* pn, gz_transformer* tr, int n_games, int mode, int node_cap, int child_cap,
                    int max_pending_samples, int ready_cap, const double* sp_conf, const double* puct_conf,

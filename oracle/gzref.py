@@ -135,6 +135,14 @@ class RefEngine:
         cs = np.full((max(n, 1), 4), -1.0, dtype=np.float32)
         self.L.gzref_last_choice_scores.argtypes = [ctypes.c_void_p, ctypes.c_int]
         self.L.gzref_last_choice_scores(cs.ctypes.data, cs.size)
+        bal = np.zeros(max(n, 1) * (max_children + 1), dtype=np.int32)
+        self.L.gzref_last_balance.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        nb = self.L.gzref_last_balance(bal.ctypes.data, bal.size)
+        balance, pos = [], 0
+        while pos < nb:
+            k = int(bal[pos])
+            balance.append(bal[pos + 1:pos + 1 + k].copy())
+            pos += 1 + k
         dbg = np.zeros((max(n, 1), 3, 25), dtype=np.float32)
         self.L.gzref_last_debug.argtypes = [ctypes.c_void_p, ctypes.c_int]
         self.L.gzref_last_debug(dbg.ctypes.data, dbg.size)
@@ -149,11 +157,17 @@ class RefEngine:
                                   tuple((int(ln[5 + 2 * v]), int(ln[6 + 2 * v])) for v in range(nv))))
             out.append({'moves': move[m, :k].copy(), 'traversals': trav[m, :k].copy(),
                         'choice_scores': cs[m].copy(), 'tree_debug': tuple(lines),
+                        'balanced_traversals': balance[m] if m < len(balance) else None,
                         'policy_prob': prob[m, :k].copy(), 'scores': score[m, :k].copy(),
                         'choice': int(choice[m]), 'root_visits': int(root[m, 0]),
                         'lead_role': int(root[m, 1]), 'root_score': float(root[m, 2]),
                         'nodes': int(root[m, 3])})
         return out
+
+    def set_balance(self, max_moves):
+        """Every search of ``search`` is followed by ``balanceFirstMoves(max_moves)`` (0: off)."""
+        self.L.gzref_set_balance.argtypes = [ctypes.c_int]
+        self.L.gzref_set_balance(int(max_moves))
 
     def selfplay(self, sp_conf, batch_size, num_workers, nn_seed=1, target_samples=0,
                  max_seconds=10.0, rng_seed=0x5EED0000, sample_capacity=0, srec=0, warm_seconds=0.0,

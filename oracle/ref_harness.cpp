@@ -408,6 +408,16 @@ extern "C" int gzref_last_choice_scores(float* out, int cap) {
 /* PuctNode::debug of the root's first three children in debug order, per move of the last gzref_search
  * (Player::treeDebugInfo, player.cpp:137-153): per line 24 floats = valid, score, lead, move, n pairs, 10 x (lead, move) */
 static std::vector<float> g_last_debug;
+/* Player::balanceNode (player.cpp:121-135): when > 0, every search of gzref_search is followed by
+ * balanceFirstMoves(max_moves) (evaluator.cpp:282-339) and the root's traversals after it are kept */
+static int g_balance_moves = 0;
+static std::vector<int> g_last_balance;          /* per move: num_children, then that many traversal counts */
+extern "C" void gzref_set_balance(int max_moves) { g_balance_moves = max_moves; }
+extern "C" int gzref_last_balance(int* out, int cap) {
+    const int n = (int)g_last_balance.size() < cap ? (int)g_last_balance.size() : cap;
+    for (int i = 0; i < n; i++) out[i] = g_last_balance[i];
+    return n;
+}
 extern "C" int gzref_last_debug(float* out, int cap) {
     const int n = (int)g_last_debug.size() < cap ? (int)g_last_debug.size() : cap;
     for (int i = 0; i < n; i++) out[i] = g_last_debug[i];
@@ -433,6 +443,7 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
     const int R = g->gt.n_roles;
     g_last_choice_scores.clear();
     g_last_debug.clear();
+    g_last_balance.clear();
     auto f = [&]() {
         pe->reset(0);
         PuctNode* node = pe->establishRoot(root_bs);
@@ -470,6 +481,11 @@ extern "C" int gzref_search(void* h, const double* puct_conf, const uint32_t* ro
                     line[6 + 2 * v] = (float)info.variation[v].move_index;
                 }
                 for (int q = 0; q < 25; q++) g_last_debug.push_back(line[q]);
+            }
+            if (g_balance_moves > 0) {
+                pe->balanceFirstMoves(g_balance_moves);
+                g_last_balance.push_back(node->num_children);
+                for (int c = 0; c < node->num_children; c++) g_last_balance.push_back((int)node->getNodeChild(R, c)->traversals);
             }
             node = pe->fastApplyMove(choice);
             if (getenv("GZREF_TRACE")) fprintf(stderr, "A %d nodes %d root_visits %d\n", m, (int)pe->nodeCount(), (int)node->visits);

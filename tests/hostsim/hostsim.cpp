@@ -235,6 +235,10 @@ extern "C" void hs_cmd_search(void* h, int g, int evals) {
     GameCtl& c = ((HostSim*)h)->E.ctl[g];
     c.cmd = CMD_SEARCH; c.cmd_evals = evals; c.cmd_done = 0;
 }
+extern "C" void hs_cmd_balance(void* h, int g, int max_moves) {
+    GameCtl& c = ((HostSim*)h)->E.ctl[g];
+    c.cmd = CMD_BALANCE; c.cmd_arg = max_moves; c.cmd_done = 0;
+}
 extern "C" void hs_cmd_apply(void* h, int g, int lead_move) {
     GameCtl& c = ((HostSim*)h)->E.ctl[g];
     c.cmd = CMD_APPLY; c.cmd_arg = lead_move; c.cmd_done = 0;

@@ -23,6 +23,7 @@ def lib():
         L.hs_cmd_reset.argtypes = [vp, ci, vp, ci]
         L.hs_cmd_search.argtypes = [vp, ci, ci]
         L.hs_cmd_apply.argtypes = [vp, ci, ci]
+        L.hs_cmd_balance.argtypes = [vp, ci, ci]
         L.hs_wait.argtypes = [vp, ci, ci]
         L.hs_root_children.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
         L.hs_ready_count.restype = ctypes.c_ulonglong
@@ -64,7 +65,7 @@ class HostSim:
             self.L.hs_destroy(self.h)
             self.h = None
 
-    def search(self, evals, n_moves, root_state=None, g=0, max_children=512):
+    def search(self, evals, n_moves, root_state=None, g=0, max_children=512, balance=0):
         L = self.L
         rs = np.ascontiguousarray(root_state, dtype=np.uint32) if root_state is not None else None
         L.hs_cmd_reset(self.h, g, rs.ctypes.data if rs is not None else None, 0)
@@ -88,7 +89,15 @@ class HostSim:
             k = L.hs_root_children(self.h, g, max_children, moves.ctypes.data, trav.ctypes.data,
                                    prob.ctypes.data, score.ctypes.data, info.ctypes.data)
             choice = int(info[4])
-            out.append({'moves': moves[:k].copy(), 'traversals': trav[:k].copy(),
+            balanced = None
+            if balance > 0:
+                L.hs_cmd_balance(self.h, g, balance)
+                assert L.hs_wait(self.h, g, 10000000) == 1
+                bt = np.zeros(max_children, dtype=np.int32)
+                L.hs_root_children(self.h, g, max_children, tmp_i.ctypes.data, bt.ctypes.data, tmp_f.ctypes.data,
+                                   tmp_f.ctypes.data, probe.ctypes.data)
+                balanced = bt[:k].copy()
+            out.append({'moves': moves[:k].copy(), 'traversals': trav[:k].copy(), 'balanced_traversals': balanced,
                         'policy_prob': prob[:k].copy(), 'scores': score[:k].copy(), 'choice': choice,
                         'root_visits': int(info[0]), 'lead_role': int(info[1]),
                         'root_score': float(info[2]), 'nodes': int(info[3])})

@@ -189,6 +189,52 @@ def test_play_poller_matches_reference_search(game, evals, moves, batch):
     assert nn.calls > (evals if batch == 1 else evals // batch)
 
 
+def test_player_balance_moves_matches_reference():
+    """PUCTPlayer.balance_moves (src/ggpzero/player/puctplayer.py:97-98) -> Player::balanceNode ->
+    PuctEvaluator::balanceFirstMoves (evaluator.cpp:282-339) through the poll loop: the root's traversal counts after
+    balancing the first three moves are the reference's, and so is every later search on the balanced tree."""
+    from oracle import gzref
+    if not gzref.available():
+        pytest.skip('oracle/_ref missing')
+    game, evals, moves, batch, k = 'reversi', 300, 5, 8, 3
+    gi = lookup.by_name(game)
+    tr = bases.GdlBasesTransformer(gi, datadesc.generation_for(game))
+    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits', batch_size=batch)
+    nn = _SynthNN(tr)
+    sm = gi.get_sm()
+    poller = cppinterface.PlayPoller(sm, nn, conf, seed=0x5EED0000)
+    eng = gzref.RefEngine(tables.blob_by_name(game), poller.c_transformer)
+    eng.set_balance(k)
+    try:
+        ref = eng.search(conf, evals, n_moves=moves)
+    finally:
+        eng.set_balance(0)
+    poller.player_reset(0)
+    state = sm.get_initial_state()
+    grew = 0
+    for r in ref:
+        poller.player_move(state, evals, -1.0)
+        poller.poll_loop()
+        lead = r['lead_role']
+        mv, _, _ = poller.player_get_move(lead)
+        assert np.array_equal(poller.c_player.last_search()['traversals'], r['traversals'])
+        poller.player_balance_moves(k)
+        poller.poll_loop()
+        snap = poller.c_player.engine.snapshot(0)
+        assert np.array_equal(snap['traversals'], r['balanced_traversals'])
+        grew += int(snap['traversals'].sum() > r['traversals'].sum())
+        other, _, _ = poller.player_get_move(1 - lead)
+        jm = sm.get_joint_move()
+        jm.set(lead, mv)
+        jm.set(1 - lead, other)
+        poller.player_apply_move(jm)
+        poller.poll_loop()
+        nxt = sm.new_base_state()
+        sm.next_state(jm, nxt)
+        state = nxt
+    assert grew >= 2
+
+
 def test_supervisor_poller_wrapper_collects_samples():
     """cppinterface.Supervisor (src/ggpzero/util/cppinterface.py:185-226) driven with poll_loop and
     a callback, as Worker.on_request_samples does (src/ggpzero/distributed/worker.py:176-191)."""

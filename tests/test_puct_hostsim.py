@@ -145,6 +145,34 @@ def test_backup_finalised_with_shared_nodes_matches(batch, tt):
         assert np.array_equal(a['scores'], b['scores'])
 
 
+@pytest.mark.parametrize('game,evals,batch,k', [('breakthroughSmall', 300, 8, 4), ('reversi', 400, 16, 3),
+                                                ('reversi', 300, 2, 5)])
+def test_balance_first_moves_matches_reference(game, evals, batch, k):
+    """Player::balanceNode -> PuctEvaluator::balanceFirstMoves (player.cpp:121-135, evaluator.cpp:282-339): after a
+    search, the k most visited root children get batches of batch_size playouts until each has as many traversals as
+    the most visited one. Same traversal counts as the reference, move after move."""
+    from hostsim_util import HostSim
+    ct, eng = _setup(game)
+    conf = confs.base_puct_config(dirichlet_noise_pct=-1, choose='choose_top_visits', batch_size=batch)
+    sp = confs.selfplay_config_template()
+    sp.puct_config = conf
+    eng.set_balance(k)
+    try:
+        ref = eng.search(conf, evals, n_moves=6, max_children=512)
+    finally:
+        eng.set_balance(0)
+    mine = HostSim(tables.blob_by_name(game), ct, sp, ncap=1 << 14, ccap=1 << 20).search(evals, 6, balance=k)
+    assert len(ref) == len(mine) == 6
+    grew = 0
+    for a, b in zip(ref, mine):
+        assert np.array_equal(a['traversals'], b['traversals'])
+        assert np.array_equal(a['balanced_traversals'], b['balanced_traversals'])
+        grew += int(b['balanced_traversals'].sum() > b['traversals'].sum())
+        assert b['balanced_traversals'].sum() >= b['traversals'].sum()
+        assert a['choice'] == b['choice']
+    assert grew >= 3                   # the case is not vacuous
+
+
 def test_backup_finalised_and_temperature_choice_match():
     from hostsim_util import HostSim
     ct, eng = _setup('breakthroughSmall')
