@@ -729,6 +729,36 @@ def run_puct(args, rank, world, local, propnet_line=None):
     gather_s = all_max(time.perf_counter() - tg0, world, eng.device)
     n_gathered = int(gathered.shape[0]) if gathered is not None else 0
 
+    # ---- the step after the gather (the trainer's DataCache.sync, nn/datacache.py:700-760): the gathered
+    # generation's records -> planes + dense policy rows + value rows on the device (csrc/gz_training.cu)
+    training = None
+    if rank == 0 and gathered is not None and n_gathered > 0:
+        try:
+            from galvanise_zero_b200.datacache import TrainingBatcher
+            tb = TrainingBatcher(eng.transformer, eng.c_transformer, eng.state_words, device=local)
+            gathered = gathered.contiguous()
+            for _ in range(3):
+                bad0 = tb.arrays(gathered, plane_dtype=torch.bfloat16, check=True)['bad']
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(eng.device)
+            reps_t = 10
+            t0e.record()
+            for _ in range(reps_t):
+                arr = tb.arrays(gathered, plane_dtype=torch.bfloat16)
+            t1e.record()
+            torch.cuda.synchronize(eng.device)
+            t_ms = t0e.elapsed_time(t1e) / reps_t
+            out_bytes = arr['planes'][0].numel() * 2 + sum(p.shape[1] for p in arr['policies']) * 4 + arr['value'].shape[1] * 4
+            alg = int(gathered.shape[1]) * 4 + out_bytes          # a record read once, its rows written once
+            ach = alg * n_gathered / (t_ms * 1e-3) / 1e9
+            training = {'records': n_gathered, 'ms': t_ms, 'records_per_s': n_gathered / (t_ms * 1e-3),
+                        'bytes_per_record': alg, 'bound': 'hbm', 'achieved': ach, 'peak': load_peaks()['hbm_gbs'],
+                        'unit': 'GB/s', 'frac': ach / load_peaks()['hbm_gbs'],
+                        'kernels': 'rec_unpack_kernel + encode kernel (+ memset of the policy rows), bf16 planes',
+                        'check_sample_failures': bad0}
+        except Exception as exc:
+            training = {'unavailable': repr(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -766,6 +796,7 @@ def run_puct(args, rank, world, local, propnet_line=None):
             'cpu_baseline': cpu, 'e2e': e2e,
             'gpu_launches': own_launches, 'clocks': clocks,
             'engine_totals': {k: t_after[k] for k in ('errors', 'halted', 'max_nodes', 'max_children', 'games', 'samples')},
+            'training_batch': training,
             'sample_gather': {'records_on_rank0': n_gathered, 'record_bytes': int(recs.shape[1]) * 4 if recs.ndim == 2 else 0,
                               'bytes_on_rank0': n_gathered * (int(recs.shape[1]) * 4 if recs.ndim == 2 else 0),
                               'seconds': gather_s, 'produced_by_rank0_in_this_run': produced,

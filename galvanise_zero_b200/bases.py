@@ -163,6 +163,47 @@ class GdlBasesTransformer(object):
             ch = np.transpose(ch, (1, 2, 0))
         return ch
 
+    # ---- sample -> network output rows (nn/bases.py:289-321; the draw head's value row is
+    # GdlBasesTransformer_Draws.value_to_array, :323-335 — chosen here by generation_descr.draw_head)
+    def check_sample(self, sample):
+        from .gendata import decode_state
+        state = sample.state
+        if isinstance(state, str):
+            state = decode_state(state)
+        assert len(state) >= self.num_bases          # (>=: the reference's encode / decode may pad)
+        assert len(sample.final_score) == self.final_score_count
+        assert isinstance(sample, datadesc.Sample)
+        for policy in sample.policies:
+            total = 0.0
+            for _, p in policy:
+                assert -0.01 < p < 1.01
+                total += p
+            assert 0.99 < total < 1.01
+        return sample
+
+    def policy_to_array(self, policy, role_index):
+        array = np.zeros(self.policy_dist_count[role_index], dtype='float32')
+        for idx, prob in policy:
+            array[idx] = prob
+        return array
+
+    def value_to_array(self, values):
+        if self.num_rewards == 3:
+            assert abs(sum(values) - 1.0) < 0.01
+            assert len(values) == 2
+            if abs(values[0] - 0.5) < 0.01:
+                assert abs(values[1] - 0.5) < 0.01
+                return np.array([0.0, 0.0, 1.0], dtype='float32')
+            return np.array([values[0], values[1], 0.0], dtype='float32')
+        assert len(values) == self.role_count
+        return np.array(values, dtype='float32')
+
+    def get_symmetries_desc(self):
+        gds = gamedesc.GameSymmetries()
+        if hasattr(gds, self.game):
+            return getattr(gds, self.game)()
+        return None
+
     def encode_tables(self):
         """(board_base, board_offset, control_base, control_channel, control_value) arrays in the
         order ``create_c_transformer`` feeds them to the engine (cppinterface.py:33-50)."""
@@ -173,3 +214,6 @@ class GdlBasesTransformer(object):
         cc = np.array([c.channel_id for c in self.control_space], dtype=np.int32)
         cv = np.array([c.value for c in self.control_space], dtype=np.float32)
         return bb, bo, cb, cc, cv
+
+
+GdlBasesTransformer_Draws = GdlBasesTransformer      # (the value row follows generation_descr.draw_head)

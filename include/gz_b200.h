@@ -313,6 +313,51 @@ int gz_player_poll(gz_player* p, int n_pred, const float* const* h_arrays, int n
 int gz_player_last_search(gz_player* p, int* out_i16, float* out_f8, int* moves, int* trav, float* prob, float* score,
                           float* next_prob, int cap);
 
+/* ------------------------------------------------------------------------------------------------
+ * Sample records (what gz_puct_fetch_samples / gz_supervisor_fetch_samples return, int32 words, `record words`
+ * of gz_puct_info per record) = the fields of datadesc.Sample (src/ggpzero/defs/datadesc.py:8-54) as
+ * Supervisor.fetch_samples hands them out (src/cpp/pyobjects/supervisor_impl.cpp:75-118):
+ * a header of GZ_SR_HEADER words, the state row, the previous-state row (valid when GZ_SR_N_PREV is 1), then
+ * GZ_SR_N_CHILDREN (action index of the lead role, probability as float bits) pairs. */
+#define GZ_SR_DEPTH 1
+#define GZ_SR_GAME_LENGTH 2
+#define GZ_SR_SLOT 3
+#define GZ_SR_MATCH 4
+#define GZ_SR_HAS_RESIGNED 5
+#define GZ_SR_RESIGN_FP 6
+#define GZ_SR_START_DEPTH 7
+#define GZ_SR_VISITS 8
+#define GZ_SR_LEAD 9          /* role whose policy the pairs are; -1: no lead role */
+#define GZ_SR_N_PREV 10
+#define GZ_SR_N_CHILDREN 11
+#define GZ_SR_FINAL_SCORE 12  /* float[4] */
+#define GZ_SR_PUCT_SCORE 16   /* float[4] */
+#define GZ_SR_OTHER_MOVES 20  /* int[4]: the single move of every role that is not the lead role */
+#define GZ_SR_HEADER 24
+
+/* Sample records -> training arrays, batched on the device: what the reference's trainer does per sample in
+ * DataCache.sync (src/ggpzero/nn/datacache.py:700-760) with the transformer (src/ggpzero/nn/bases.py):
+ * final scores clamped to [0, 1] (datacache.py:716-718), state_to_channels(state, prev_states) (bases.py:242-287)
+ * -> d_planes [n][total_size] of plane_dtype, policy_to_array(policy, role) (bases.py:305-310) -> d_policy[r]
+ * float [n][policy_sizes[r]] (the lead role's pairs; every other role its single move with probability 1,
+ * src/cpp/selfplaymanager.cpp:95-108), value_to_array(final_score) (bases.py:312-314; with n_values == 3 the draw
+ * head of GdlBasesTransformer_Draws, :323-335) -> d_value float [n][n_values]; d_bad (may be NULL) receives the
+ * number of records that fail check_sample (bases.py:289-303: every probability in (-0.01, 1.01), the lead
+ * role's sum in (0.99, 1.01), action indices inside the role's policy width; the draw head's own asserts).
+ * Augmentation (DataCache.augment_data, datacache.py:597-671): with d_sym (int32 [n], one symmetry id per record,
+ * 0 <= id < n_sym) the state rows go through d_base_src (int32 [n_sym][n_bases]: new bit j = old bit src[j], the
+ * inverse of Translator.translate_basestate's map, src/ggpzero/util/symmetry.py:153-204) and every action index
+ * through d_action_dest[r] (int32 [n_sym][policy_sizes[r]]: translate_action, symmetry.py:206-225); d_sym NULL:
+ * records as they are. Output row i is made from record d_index[i] (int32 [n]; NULL: record i) of the n_records
+ * records, so that one record can appear under several symmetries. d_scratch: gz_records_to_training_scratch_bytes(n, state_words) bytes. */
+int64_t gz_records_to_training_scratch_bytes(int64_t n, int state_words);
+int gz_records_to_training(gz_transformer* t, int64_t n, int64_t n_records, int record_words, int state_words,
+                           int n_roles, const int32_t* d_records, const int32_t* d_index, const int32_t* d_sym,
+                           int n_sym, const int32_t* d_base_src,
+                           const int32_t* const* d_action_dest, void* d_planes, int plane_dtype,
+                           float* const* d_policy, float* d_value, int n_values, int32_t* d_bad, void* d_scratch,
+                           void* stream);
+
 /* Deterministic synthetic policy/value network (include/gz_synth.h) on encoded planes — parity and
  * benchmarking utility; the production network is a PyTorch module. */
 int gz_synth_nn(const void* d_planes, int plane_dtype, int64_t n, int total, uint64_t seed, int n_roles,
