@@ -751,7 +751,26 @@ def run_puct(args, rank, world, local, propnet_line=None):
             out_bytes = arr['planes'][0].numel() * 2 + sum(p.shape[1] for p in arr['policies']) * 4 + arr['value'].shape[1] * 4
             alg = int(gathered.shape[1]) * 4 + out_bytes          # a record read once, its rows written once
             ach = alg * n_gathered / (t_ms * 1e-3) / 1e9
-            training = {'records': n_gathered, 'ms': t_ms, 'records_per_s': n_gathered / (t_ms * 1e-3),
+            # the same kernels over 2^20 output rows (every record repeated through the row index: the rows written,
+            # 1.2 GB, no longer fit the L2): the figure the HBM roofline applies to
+            big = None
+            if n_gathered >= 1024:
+                rows_big = 1 << 20
+                idx_big = (torch.arange(rows_big, device=eng.device, dtype=torch.int64) % n_gathered).to(torch.int32)
+                for _ in range(2):
+                    tb.arrays(gathered, plane_dtype=torch.bfloat16, index=idx_big)
+                torch.cuda.synchronize(eng.device)
+                t0e.record()
+                for _ in range(5):
+                    tb.arrays(gathered, plane_dtype=torch.bfloat16, index=idx_big)
+                t1e.record()
+                torch.cuda.synchronize(eng.device)
+                b_ms = t0e.elapsed_time(t1e) / 5
+                b_ach = alg * rows_big / (b_ms * 1e-3) / 1e9
+                big = {'rows': rows_big, 'ms': b_ms, 'rows_per_s': rows_big / (b_ms * 1e-3), 'achieved': b_ach,
+                       'unit': 'GB/s', 'frac': b_ach / load_peaks()['hbm_gbs']}
+                del idx_big
+            training = {'records': n_gathered, 'ms': t_ms, 'large_batch': big, 'records_per_s': n_gathered / (t_ms * 1e-3),
                         'bytes_per_record': alg, 'bound': 'hbm', 'achieved': ach, 'peak': load_peaks()['hbm_gbs'],
                         'unit': 'GB/s', 'frac': ach / load_peaks()['hbm_gbs'],
                         'kernels': 'rec_unpack_kernel + encode kernel (+ memset of the policy rows), bf16 planes',

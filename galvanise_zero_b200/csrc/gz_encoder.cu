@@ -320,6 +320,15 @@ extern "C" int gz_transformer_finalize(gz_transformer* t, int n_bases, int devic
     return GZ_OK;
 }
 
+#include "gz_encoder_col.cuh"
+
+// batches of at least this many states whose rows are a multiple of 8 elements go to encode_col_kernel
+static int64_t g_col_min_batch = 16384;
+extern "C" int gz_encode_set_column_kernel_min_batch(int64_t min_batch) {
+    g_col_min_batch = min_batch < 0 ? ((int64_t)1 << 62) : min_batch;
+    return GZ_OK;
+}
+
 extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
                                 const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
                                 int out_dtype, int c_pad, void* stream);
@@ -341,6 +350,25 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
     if (c_pad != 0 && (c_pad < t->E.total / t->E.channel_size || (c_pad & 7))) { gz_set_error("c_pad must be a multiple of 8 and >= the channel count"); return GZ_ERR_ARG; }
     if ((((uintptr_t)d_out) & 15) != 0) { gz_set_error("plane buffer must be 16-byte aligned"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(t->device));
+    if (n >= g_col_min_batch && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32)) {
+        const int row_elems = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
+        const int BW = 2 * state_words + t->num_control_channels + 1;
+        int S = 64;
+        auto need = [&](int k) { return ((size_t)row_elems + (size_t)k * BW) * 4; };
+        while (S > 8 && need(S) > 48 * 1024) S >>= 1;
+        if ((row_elems & 7) == 0 && need(S) <= 48 * 1024) {
+            const int64_t blocks = (n + S - 1) / S;
+            const int grid = (int)std::min<int64_t>(blocks, (int64_t)t->n_sms * 8);
+            if (out_dtype == GZ_DTYPE_BF16)
+                encode_col_kernel<__nv_bfloat16><<<grid, ENCC_THREADS, need(S), (cudaStream_t)stream>>>(
+                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (__nv_bfloat16*)d_out, c_pad, row_elems, S);
+            else
+                encode_col_kernel<float><<<grid, ENCC_THREADS, need(S), (cudaStream_t)stream>>>(
+                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (float*)d_out, c_pad, row_elems, S);
+            GZ_CUDA(cudaGetLastError());
+            return GZ_OK;
+        }
+    }
     {
         const int row_elems = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
         int spb = ENCF_STATES;                 // (states of hexLG13's size do not fit: generic kernel)

@@ -1,0 +1,146 @@
+// gz_encoder_col.cuh — the column-owned plane encoder for large batches (rows that are a multiple of 8 elements).
+//
+// encode_fast_kernel (gz_encoder.cu) interprets one descriptor per output ELEMENT per state: ~30 instructions per
+// element (descriptor fetch and decode, three divergent kinds), which bounds it at 15-25 % of the HBM roofline
+// although the work is a pure stream (profiles/r02_bench_propnet_games.jsonl). Here a thread OWNS one 8-element
+// column of the plane row — the same 8 descriptors for every state — decodes them once into registers (word
+// offset, shift, mask, multiplier: a bit of the state, a bit of the OR of the previous states, a control
+// channel's value or a constant zero all become `((word >> shift) & mask) * mul`) and then streams the states of
+// the CTA's tile through them: per 8 output elements 8 shared-memory loads, 24 ALU instructions and one 128-bit
+// store (bf16; two for f32). Thread t writes flat chunk t + i * (threads in use), so a warp's stores are one
+// contiguous 512-byte (bf16) run whatever the row size; a thread's column never changes because the stride is a
+// multiple of the chunks per row.
+//
+// Results are those of encode_kernel / encode_fast_kernel (tests/test_encoder.py runs all against the C oracle
+// and the reference's compiled toChannels); tests/hostsim/ctasim_encoder.cpp compiles this header for the CPU.
+#ifndef GZ_ENCODER_COL_CUH
+#define GZ_ENCODER_COL_CUH
+
+#include "gz_encoder.cuh"
+
+#define ENCC_THREADS 256
+// (the CPU validation build, tests/hostsim/ctasim_encoder.cpp, substitutes a pointer to its own buffer)
+#ifndef ENCC_DYNAMIC_SMEM
+#define ENCC_DYNAMIC_SMEM(name) extern __shared__ __align__(16) uint32_t name[]
+#endif
+
+// the row's element descriptors (shared with the description in gz_encoder.cu: kind in bits 30-31 — 0 zero, 1 bit
+// of the state, 2 bit of the OR of the previous states, 3 control channel —, payload in bits 0-29)
+__device__ __forceinline__ void encc_build_desc(const EncParams& E, uint32_t* desc, int row_elems, int c_pad,
+                                                bool has_prev, int tid, int nthreads) {
+    const int n_ch = E.total / E.channel_size;
+    for (int le0 = tid; le0 < row_elems; le0 += nthreads) {
+        int le = le0;
+        uint32_t d = 0u;
+        bool live = true;
+        if (c_pad > 0) {                                  // [H*W][c_pad] rows: element = (cell, channel)
+            const int pos = le / c_pad, c = le - pos * c_pad;
+            live = c < n_ch;
+            le = c * E.channel_size + pos;
+        }
+        if (live) {
+            if (le < E.board_total) {
+                const int g = le / E.group_size;
+                const int b = E.src_base[le - g * E.group_size];
+                if (b >= 0 && g == 0) d = (1u << 30) | (uint32_t)b;
+                else if (b >= 0 && g == 1 && has_prev) d = (2u << 30) | (uint32_t)b;
+            } else {
+                d = (3u << 30) | (uint32_t)((le - E.board_total) / E.channel_size);
+            }
+        }
+        desc[le0] = d;
+    }
+}
+
+template <typename OutT>
+struct EnccColumn {          // one thread's column: 8 decoded descriptors
+    uint32_t off[8], sh[8], msk[8], mul[8];
+};
+
+template <typename OutT>
+__device__ __forceinline__ void encc_load_column(EnccColumn<OutT>& C, const uint32_t* desc, int c, int sw, int nc) {
+    constexpr uint32_t ONE = sizeof(OutT) == 2 ? 0x3F80u : 0x3F800000u;
+    constexpr uint32_t FULL = sizeof(OutT) == 2 ? 0xFFFFu : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t d = desc[c * 8 + k];
+        const uint32_t kind = d >> 30, pl = d & 0x3FFFFFFFu;
+        uint32_t off = (uint32_t)(2 * sw + nc), sh = 0u, msk = 0u, mul = 0u;          // the tile's zero word
+        if (kind == 1u) { off = pl >> 5; sh = pl & 31u; msk = 1u; mul = ONE; }
+        else if (kind == 2u) { off = (uint32_t)sw + (pl >> 5); sh = pl & 31u; msk = 1u; mul = ONE; }
+        else if (kind == 3u) { off = (uint32_t)(2 * sw) + pl; msk = FULL; mul = 1u; }
+        C.off[k] = off; C.sh[k] = sh; C.msk[k] = msk; C.mul[k] = mul;
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(ENCC_THREADS)
+encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint32_t* __restrict__ states,
+                  const uint32_t* __restrict__ prev, const uint8_t* __restrict__ prev_count, int max_prev,
+                  OutT* __restrict__ out, int c_pad, int row_elems /* multiple of 8 */, int S /* states per tile */) {
+    ENCC_DYNAMIC_SMEM(csm);
+    uint32_t* desc = csm;                                        // [row_elems]
+    uint32_t* blk = desc + row_elems;                            // [S][BW]: state | OR of previous states | control values | 0
+    const int nc = E.num_control_channels;
+    const int BW = 2 * sw + nc + 1;
+    const bool has_prev = prev && E.num_prev_states > 0;
+    const int t = threadIdx.x;
+    encc_build_desc(E, desc, row_elems, c_pad, has_prev, t, ENCC_THREADS);
+    __syncthreads();
+    const int CPR = row_elems >> 3;                              // 8-element chunks per row
+    const bool wide = CPR >= ENCC_THREADS;
+    const int J = wide ? 1 : ENCC_THREADS / CPR;                 // states in flight per pass over the columns
+    const int NT = wide ? ENCC_THREADS : J * CPR;                // threads in use
+    const int NCG = wide ? (CPR + ENCC_THREADS - 1) / ENCC_THREADS : 1;
+    const int j = wide ? 0 : t / CPR;
+    const int c0 = wide ? t : t - j * CPR;
+    EnccColumn<OutT> C;
+    if (NCG == 1 && t < NT) encc_load_column<OutT>(C, desc, c0, sw, nc);
+    for (int64_t n0 = (int64_t)blockIdx.x * S; n0 < n; n0 += (int64_t)gridDim.x * S) {
+        const int nb = (int)((n - n0) < S ? (n - n0) : S);
+        __syncthreads();                                         // the previous tile has been read
+        for (int i = t; i < nb * sw; i += ENCC_THREADS) {
+            const int s = i / sw, w = i - s * sw;
+            blk[s * BW + w] = states[(n0 + s) * sw + w];
+            uint32_t p = 0u;
+            if (has_prev) {
+                const int np = prev_count ? prev_count[n0 + s] : max_prev;
+                for (int k = 0; k < np && k < max_prev; ++k) p |= prev[((n0 + s) * max_prev + k) * sw + w];
+            }
+            blk[s * BW + sw + w] = p;
+        }
+        for (int i = t; i < nb; i += ENCC_THREADS) blk[i * BW + 2 * sw + nc] = 0u;
+        __syncthreads();
+        for (int i = t; i < nb * nc; i += ENCC_THREADS) {
+            const int s = i / nc, c = i - s * nc;
+            const float v = enc_control_value(E, blk + s * BW, c);
+            blk[s * BW + 2 * sw + c] =
+                sizeof(OutT) == 2 ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)) : __float_as_uint(v);
+        }
+        __syncthreads();
+        if (t < NT) {
+            for (int cg = 0; cg < NCG; ++cg) {
+                const int c = cg * ENCC_THREADS + c0;
+                if (c >= CPR) break;
+                if (NCG > 1) encc_load_column<OutT>(C, desc, c, sw, nc);
+                OutT* dst0 = out + n0 * (int64_t)row_elems + (int64_t)c * 8;
+                for (int s = j; s < nb; s += J) {
+                    const uint32_t* b = blk + s * BW;
+                    uint32_t v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = ((b[C.off[k]] >> C.sh[k]) & C.msk[k]) * C.mul[k];
+                    OutT* dst = dst0 + (int64_t)s * row_elems;
+                    if (sizeof(OutT) == 2) {
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16),
+                                                                    v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+                    } else {
+                        reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                        reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+#endif  // GZ_ENCODER_COL_CUH

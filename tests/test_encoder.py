@@ -183,3 +183,120 @@ def test_gpu_encoder_channels_last_padded_layout(game, c_pad):
                     dtype=torch.bfloat16, c_pad=c_pad).float().cpu().numpy().reshape(19, tr.channel_size, c_pad)
     assert np.array_equal(got[:, :, :tr.num_channels], want.transpose(0, 2, 1))
     assert not got[:, :, tr.num_channels:].any()
+
+
+# ------------------------------------------------------------------------------------------------
+# encode_col_kernel (csrc/gz_encoder_col.cuh): the column-owned kernel for large batches
+COL_GAMES = ['reversi', 'breakthrough', 'connect6', 'amazons_10x10', 'chess_15d']      # rows of a multiple of 8 elements
+
+
+def _ctasim_encode(ct, n_bases, cur, prev, cnt, dtype, c_pad=0, S=8, grid=2):
+    """The kernel's own source compiled for the CPU (tests/hostsim/ctasim_encoder.cpp: 256 threads per CTA)."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'hostsim')
+    subprocess.check_call(['make', '-s', '-C', here, 'libctasim.so'])
+    L = ctypes.CDLL(os.path.join(here, 'libctasim.so'))
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    L.cs_encode_col.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, ci, ctypes.c_int64, ci, vp, vp, vp, ci, vp, ci, ci, ci, ci]
+    group = ct.channels_per_state * ct.channel_size
+    src = np.full(group, -1, dtype=np.int32)
+    for b, off in ct.board_bases:                      # (gz_transformer_finalize builds the same table)
+        src[off] = b
+    cb = np.array([b for b, c, v in ct.control_bases], dtype=np.int32)
+    cc = np.array([c for b, c, v in ct.control_bases], dtype=np.int32)
+    cv = np.array([v for b, c, v in ct.control_bases], dtype=np.float32)
+    cur = np.ascontiguousarray(cur, dtype=np.uint32)
+    n, sw = cur.shape
+    total = ct.total_size()
+    row = ct.channel_size * c_pad if c_pad else total
+    out = np.full((n, row), 0x7777 if dtype == 1 else 0x77777777, dtype=np.uint16 if dtype == 1 else np.uint32)
+    max_prev = 0
+    if prev is not None:
+        prev = np.ascontiguousarray(prev, dtype=np.uint32)
+        max_prev = prev.shape[1]
+    rc = L.cs_encode_col(src.ctypes.data, group, cb.ctypes.data, cc.ctypes.data, cv.ctypes.data, len(cb),
+                         ct.channel_size, ct.num_prev_states, ct.num_control_channels, n, sw, cur.ctypes.data,
+                         prev.ctypes.data if prev is not None else None,
+                         cnt.ctypes.data if cnt is not None else None, max_prev, out.ctypes.data, dtype, c_pad, S, grid)
+    assert rc == 0
+    return out
+
+
+def _bf16_bits(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize('game', COL_GAMES)
+def test_column_kernel_source_under_cta_emulation_is_bit_exact(game):
+    gi, tr, ct = _setup(game)
+    enc = RefEncoder.from_c_transformer(ct)
+    big = game in ('connect6', 'chess_15d')
+    n = 13 if big else 37
+    hist = _trajectory(game, n_games=n, plies=9)
+    cur, prev = hist[8], hist[7][:, None, :]
+    cnt = (np.arange(n) % 2).astype(np.uint8)
+    want = enc.encode(cur, prev, cnt)
+    got = _ctasim_encode(ct, tr.num_bases, cur, prev, cnt, 0, S=8, grid=2)          # ragged last tile, grid stride
+    assert np.array_equal(got.view(np.float32), want)
+    got16 = _ctasim_encode(ct, tr.num_bases, cur, prev, cnt, 1, S=5, grid=1)
+    assert np.array_equal(got16, _bf16_bits(want))
+    want0 = enc.encode(cur)                                                          # no previous states at all
+    assert np.array_equal(_ctasim_encode(ct, tr.num_bases, cur, None, None, 0, S=16, grid=3).view(np.float32), want0)
+    if not big:
+        c_pad = 16
+        w3 = enc.encode(cur, prev).reshape(n, tr.num_channels, tr.channel_size)
+        g3 = _ctasim_encode(ct, tr.num_bases, cur, prev, None, 1, c_pad=c_pad, S=8, grid=2).reshape(n, tr.channel_size, c_pad)
+        assert np.array_equal(g3[:, :, :tr.num_channels], _bf16_bits(w3.transpose(0, 2, 1)))
+        assert not g3[:, :, tr.num_channels:].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('game', COL_GAMES)
+def test_gpu_column_kernel_bit_exact(game):
+    """gz_encode with the column kernel forced (any batch size) against the C oracle: f32 exact, bf16 = rounded
+    f32, ragged batch, some roots without a previous state, the padded channels-last layout; and the default
+    dispatch (a batch above the threshold) gives the same planes as the small-batch kernels."""
+    import ctypes
+    import torch
+    from galvanise_zero_b200 import lib as gzlib
+    gi, tr, ct = _setup(game)
+    ct.finalize(tr.num_bases, 0)
+    enc = RefEncoder.from_c_transformer(ct)
+    L = gzlib.lib()
+    L.gz_encode_set_column_kernel_min_batch.argtypes = [ctypes.c_int64]
+    n = 331
+    hist = _trajectory(game, n_games=n, plies=12)
+    dev = torch.device('cuda', 0)
+    try:
+        L.gz_encode_set_column_kernel_min_batch(1)
+        for k in (0, 5, 11):
+            cur = hist[k]
+            prev = hist[k - 1][:, None, :] if k > 0 else None
+            cnt = (np.arange(n) % 3 != 0).astype(np.uint8) if k > 0 else None
+            want = enc.encode(cur, prev, cnt)
+            d_cur = torch.from_numpy(cur.view(np.int32)).to(dev)
+            d_prev = torch.from_numpy(prev.view(np.int32).copy()).to(dev) if prev is not None else None
+            d_cnt = torch.from_numpy(cnt).to(dev) if cnt is not None else None
+            assert np.array_equal(ct.encode(d_cur, d_prev, d_cnt, dtype=torch.float32).cpu().numpy(), want)
+            assert torch.equal(ct.encode(d_cur, d_prev, d_cnt, dtype=torch.bfloat16).cpu(),
+                               torch.from_numpy(want).to(torch.bfloat16))
+            if k == 11:
+                w3 = want.reshape(n, tr.num_channels, tr.channel_size)
+                g3 = ct.encode(d_cur, d_prev, d_cnt, dtype=torch.bfloat16, c_pad=16).float().cpu().numpy()
+                g3 = g3.reshape(n, tr.channel_size, 16)
+                assert np.array_equal(g3[:, :, :tr.num_channels], w3.transpose(0, 2, 1)) and not g3[:, :, tr.num_channels:].any()
+        # default dispatch: a batch above the threshold takes the column kernel, below it the small-batch kernels
+        L.gz_encode_set_column_kernel_min_batch(16384)
+        reps = 16384 // n + 1
+        big = torch.from_numpy(np.tile(hist[11], (reps, 1)).view(np.int32)).to(dev)
+        bigp = torch.from_numpy(np.tile(hist[10], (reps, 1)).view(np.int32).copy()).to(dev).reshape(-1, 1, big.shape[1])
+        a = ct.encode(big, bigp, dtype=torch.bfloat16)
+        L.gz_encode_set_column_kernel_min_batch(-1)
+        b = ct.encode(big, bigp, dtype=torch.bfloat16)
+        assert a.shape[0] >= 16384 and torch.equal(a, b)
+    finally:
+        L.gz_encode_set_column_kernel_min_batch(16384)
