@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -328,6 +329,11 @@ extern "C" int gz_encode_set_column_kernel_min_batch(int64_t min_batch) {
     g_col_min_batch = min_batch < 0 ? ((int64_t)1 << 62) : min_batch;
     return GZ_OK;
 }
+static int g_col_tile = 0;          // states per tile, 0: the default (see gz_encode_layout)
+extern "C" int gz_encode_set_column_kernel_tile(int tile_states) {
+    g_col_tile = tile_states;
+    return GZ_OK;
+}
 
 extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32_t* d_states,
                                 const uint32_t* d_prev, const uint8_t* d_prev_count, int max_prev, void* d_out,
@@ -353,7 +359,13 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
     if (n >= g_col_min_batch && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32)) {
         const int row_elems = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
         const int BW = 2 * state_words + t->num_control_channels + 1;
-        int S = 64;
+        // measured (tools/bench_encoder.py, profiles/r02_encoder_column_kernel.jsonl): bf16 rows like large tiles,
+        // f32 rows small ones
+        // the tile: bf16 rows like up to 256 states in at most 18 KB of staged words, f32 rows up to 64 in 8 KB
+        const bool half = out_dtype == GZ_DTYPE_BF16;
+        int S = g_col_tile >= 8 ? g_col_tile : (half ? 256 : 64);
+        if (g_col_tile < 8)
+            while (S > 8 && (size_t)S * BW * 4 > (half ? 18u : 8u) * 1024) S >>= 1;
         auto need = [&](int k) { return ((size_t)row_elems + (size_t)k * BW) * 4; };
         while (S > 8 && need(S) > 48 * 1024) S >>= 1;
         if ((row_elems & 7) == 0 && need(S) <= 48 * 1024) {

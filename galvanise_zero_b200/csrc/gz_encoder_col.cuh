@@ -69,6 +69,7 @@ __device__ __forceinline__ void encc_load_column(EnccColumn<OutT>& C, const uint
         if (kind == 1u) { off = pl >> 5; sh = pl & 31u; msk = 1u; mul = ONE; }
         else if (kind == 2u) { off = (uint32_t)sw + (pl >> 5); sh = pl & 31u; msk = 1u; mul = ONE; }
         else if (kind == 3u) { off = (uint32_t)(2 * sw) + pl; msk = FULL; mul = 1u; }
+        if (sizeof(OutT) == 2 && (k & 1)) mul <<= 16;        // bf16: the odd element of a pair lands in the high half
         C.off[k] = off; C.sh[k] = sh; C.msk[k] = msk; C.mul[k] = mul;
     }
 }
@@ -96,18 +97,24 @@ encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const 
     const int c0 = wide ? t : t - j * CPR;
     EnccColumn<OutT> C;
     if (NCG == 1 && t < NT) encc_load_column<OutT>(C, desc, c0, sw, nc);
+    const int step_s = ENCC_THREADS / sw, step_w = ENCC_THREADS - step_s * sw;     // (s, w) of word i + ENCC_THREADS
     for (int64_t n0 = (int64_t)blockIdx.x * S; n0 < n; n0 += (int64_t)gridDim.x * S) {
         const int nb = (int)((n - n0) < S ? (n - n0) : S);
         __syncthreads();                                         // the previous tile has been read
-        for (int i = t; i < nb * sw; i += ENCC_THREADS) {
-            const int s = i / sw, w = i - s * sw;
-            blk[s * BW + w] = states[(n0 + s) * sw + w];
-            uint32_t p = 0u;
-            if (has_prev) {
-                const int np = prev_count ? prev_count[n0 + s] : max_prev;
-                for (int k = 0; k < np && k < max_prev; ++k) p |= prev[((n0 + s) * max_prev + k) * sw + w];
+        {   // the tile's state words are one contiguous run in HBM; (state, word) advance without a division
+            int s = t / sw, w = t - s * sw;
+            const uint32_t* src = states + n0 * sw;
+            for (int i = t; i < nb * sw; i += ENCC_THREADS) {
+                uint32_t p = 0u;
+                if (has_prev) {
+                    const int np = prev_count ? prev_count[n0 + s] : max_prev;
+                    for (int k = 0; k < np && k < max_prev; ++k) p |= prev[((n0 + s) * max_prev + k) * sw + w];
+                }
+                blk[s * BW + w] = src[i];
+                blk[s * BW + sw + w] = p;
+                s += step_s; w += step_w;
+                if (w >= sw) { w -= sw; ++s; }
             }
-            blk[s * BW + sw + w] = p;
         }
         for (int i = t; i < nb; i += ENCC_THREADS) blk[i * BW + 2 * sw + nc] = 0u;
         __syncthreads();
@@ -126,14 +133,18 @@ encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const 
                 OutT* dst0 = out + n0 * (int64_t)row_elems + (int64_t)c * 8;
                 for (int s = j; s < nb; s += J) {
                     const uint32_t* b = blk + s * BW;
-                    uint32_t v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = ((b[C.off[k]] >> C.sh[k]) & C.msk[k]) * C.mul[k];
                     OutT* dst = dst0 + (int64_t)s * row_elems;
                     if (sizeof(OutT) == 2) {
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16),
-                                                                    v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+                        uint32_t v[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)            // two elements per word: the multipliers place them
+                            v[k] = ((b[C.off[2 * k]] >> C.sh[2 * k]) & C.msk[2 * k]) * C.mul[2 * k] +
+                                   ((b[C.off[2 * k + 1]] >> C.sh[2 * k + 1]) & C.msk[2 * k + 1]) * C.mul[2 * k + 1];
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
                     } else {
+                        uint32_t v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = ((b[C.off[k]] >> C.sh[k]) & C.msk[k]) * C.mul[k];
                         reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
                         reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
                     }

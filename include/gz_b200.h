@@ -145,6 +145,8 @@ int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32
 /* Batches of at least `min_batch` states whose plane rows are a multiple of 8 elements are encoded by the
  * column-owned kernel (csrc/gz_encoder_col.cuh; default 16384, negative: never) — same results, a tuning switch. */
 int gz_encode_set_column_kernel_min_batch(int64_t min_batch);
+/* measurement switch of that kernel: states per tile (0: default) */
+int gz_encode_set_column_kernel_tile(int tile_states);
 
 /* Board symmetry of packed states, batched (src/ggpzero/util/symmetry.py:153-204 translate_basestate): bit j of
  * every output state = bit d_src[j] of the input state (d_src: int32 [n_bases], a permutation; padding bits

@@ -244,6 +244,8 @@ def test_column_kernel_source_under_cta_emulation_is_bit_exact(game):
     assert np.array_equal(got.view(np.float32), want)
     got16 = _ctasim_encode(ct, tr.num_bases, cur, prev, cnt, 1, S=5, grid=1)
     assert np.array_equal(got16, _bf16_bits(want))
+    got16 = _ctasim_encode(ct, tr.num_bases, cur, prev, cnt, 1, S=64, grid=1)        # one tile holds the batch
+    assert np.array_equal(got16, _bf16_bits(want))
     want0 = enc.encode(cur)                                                          # no previous states at all
     assert np.array_equal(_ctasim_encode(ct, tr.num_bases, cur, None, None, 0, S=16, grid=3).view(np.float32), want0)
     if not big:
@@ -273,7 +275,8 @@ def test_gpu_column_kernel_bit_exact(game):
     dev = torch.device('cuda', 0)
     try:
         L.gz_encode_set_column_kernel_min_batch(1)
-        for k in (0, 5, 11):
+        for k, tile in zip((0, 5, 11, 11), (0, 16, 0, 64)):
+            L.gz_encode_set_column_kernel_tile(tile)
             cur = hist[k]
             prev = hist[k - 1][:, None, :] if k > 0 else None
             cnt = (np.arange(n) % 3 != 0).astype(np.uint8) if k > 0 else None
@@ -285,9 +288,10 @@ def test_gpu_column_kernel_bit_exact(game):
             assert torch.equal(ct.encode(d_cur, d_prev, d_cnt, dtype=torch.bfloat16).cpu(),
                                torch.from_numpy(want).to(torch.bfloat16))
             if k == 11:
+                cp = 16 if tr.num_channels <= 16 else 32
                 w3 = want.reshape(n, tr.num_channels, tr.channel_size)
-                g3 = ct.encode(d_cur, d_prev, d_cnt, dtype=torch.bfloat16, c_pad=16).float().cpu().numpy()
-                g3 = g3.reshape(n, tr.channel_size, 16)
+                g3 = ct.encode(d_cur, d_prev, d_cnt, dtype=torch.bfloat16, c_pad=cp).float().cpu().numpy()
+                g3 = g3.reshape(n, tr.channel_size, cp)
                 assert np.array_equal(g3[:, :, :tr.num_channels], w3.transpose(0, 2, 1)) and not g3[:, :, tr.num_channels:].any()
         # default dispatch: a batch above the threshold takes the column kernel, below it the small-batch kernels
         L.gz_encode_set_column_kernel_min_batch(16384)
@@ -300,3 +304,4 @@ def test_gpu_column_kernel_bit_exact(game):
         assert a.shape[0] >= 16384 and torch.equal(a, b)
     finally:
         L.gz_encode_set_column_kernel_min_batch(16384)
+        L.gz_encode_set_column_kernel_tile(0)
