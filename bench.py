@@ -309,7 +309,9 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
         enc_ms = e0.elapsed_time(e1) / 20
         eb = 2 * ((dev.n_bases + 7) // 8) + 2 * ct.total_size()
         ach = eb * ne / (enc_ms * 1e-3) / 1e9
-        encoder = {'kernel': 'encode_kernel<bf16>', 'positions_per_launch': ne, 'launch_ms': enc_ms,
+        col = ne >= 16384 and ct.total_size() % 8 == 0
+        encoder = {'kernel': 'encode_col_kernel<bf16> (column-owned, csrc/gz_encoder_col.cuh)' if col
+                             else 'encode_fast_kernel<bf16> / encode_kernel<bf16>', 'positions_per_launch': ne, 'launch_ms': enc_ms,
                    'bytes_per_unit': eb, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                    'frac': ach / peaks['hbm_gbs'], 'planes': [tr.num_channels, tr.num_cols, tr.num_rows]}
     except Exception as exc:           # a game without a plane description

@@ -366,6 +366,8 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
         int S = g_col_tile >= 8 ? g_col_tile : (half ? 256 : 64);
         if (g_col_tile < 8)
             while (S > 8 && (size_t)S * BW * 4 > (half ? 18u : 8u) * 1024) S >>= 1;
+        if (g_col_tile < 8)                      // mid-size batches: enough tiles for every SM's resident CTAs
+            while (S > 8 && (n + S - 1) / S < (int64_t)t->n_sms * 4) S >>= 1;
         auto need = [&](int k) { return ((size_t)row_elems + (size_t)k * BW) * 4; };
         while (S > 8 && need(S) > 48 * 1024) S >>= 1;
         if ((row_elems & 7) == 0 && need(S) <= 48 * 1024) {
