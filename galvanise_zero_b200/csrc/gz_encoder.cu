@@ -356,16 +356,24 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
     if (c_pad != 0 && (c_pad < t->E.total / t->E.channel_size || (c_pad & 7))) { gz_set_error("c_pad must be a multiple of 8 and >= the channel count"); return GZ_ERR_ARG; }
     if ((((uintptr_t)d_out) & 15) != 0) { gz_set_error("plane buffer must be 16-byte aligned"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(t->device));
-    if (n >= g_col_min_batch && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32)) {
-        const int row_elems = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
+    const int row_elems_c = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
+    if (n >= g_col_min_batch && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32) && (row_elems_c & 7) == 0 &&
+        row_elems_c >= 8) {
+        const int row_elems = row_elems_c;
         const int BW = 2 * state_words + t->num_control_channels + 1;
-        // measured (tools/bench_encoder.py, profiles/r02_encoder_column_kernel.jsonl): bf16 rows like large tiles,
-        // f32 rows small ones
-        // the tile: bf16 rows like up to 256 states in at most 18 KB of staged words, f32 rows up to 64 in 8 KB
+        // the tile (measured, profiles/r02_encoder_column_kernel.jsonl): what matters is the number of 8-element
+        // chunks a thread stores per tile — about 40 for bf16 rows, about 12 for f32 rows
         const bool half = out_dtype == GZ_DTYPE_BF16;
-        int S = g_col_tile >= 8 ? g_col_tile : (half ? 256 : 64);
-        if (g_col_tile < 8)
-            while (S > 8 && (size_t)S * BW * 4 > (half ? 18u : 8u) * 1024) S >>= 1;
+        int S = g_col_tile;
+        if (g_col_tile < 8) {
+            const int CPR = row_elems >> 3;
+            const int NT = CPR >= ENCC_THREADS ? ENCC_THREADS : (ENCC_THREADS / CPR) * CPR;
+            const double want = (half ? 40.0 : 12.0) * NT / CPR;
+            S = 8;
+            while (S < 256 && (double)S * 1.4142 < want) S <<= 1;          // nearest power of two
+            const int lo = 32, hi = half ? 256 : 64;
+            S = S < lo ? lo : (S > hi ? hi : S);
+        }
         if (g_col_tile < 8)                      // mid-size batches: enough tiles for every SM's resident CTAs
             while (S > 8 && (n + S - 1) / S < (int64_t)t->n_sms * 4) S >>= 1;
         auto need = [&](int k) { return ((size_t)row_elems + (size_t)k * BW) * 4; };

@@ -24,6 +24,22 @@
 #define ENCC_DYNAMIC_SMEM(name) extern __shared__ __align__(16) uint32_t name[]
 #endif
 
+// Shared-memory addresses of the staged words are kept as plain 32-bit shared-window addresses, so that the inner
+// loop advances them with one add each and loads with ld.shared (the CPU validation build uses host pointers).
+#ifndef ENCC_HOST_BUILD
+typedef uint32_t encc_addr_t;
+__device__ __forceinline__ encc_addr_t encc_addr(const uint32_t* p) { return (encc_addr_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t encc_lds(encc_addr_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+#else
+typedef uintptr_t encc_addr_t;
+static inline encc_addr_t encc_addr(const uint32_t* p) { return (encc_addr_t)p; }
+static inline uint32_t encc_lds(encc_addr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
+#endif
+
 // the row's element descriptors (shared with the description in gz_encoder.cu: kind in bits 30-31 — 0 zero, 1 bit
 // of the state, 2 bit of the OR of the previous states, 3 control channel —, payload in bits 0-29)
 __device__ __forceinline__ void encc_build_desc(const EncParams& E, uint32_t* desc, int row_elems, int c_pad,
@@ -53,12 +69,14 @@ __device__ __forceinline__ void encc_build_desc(const EncParams& E, uint32_t* de
 }
 
 template <typename OutT>
-struct EnccColumn {          // one thread's column: 8 decoded descriptors
-    uint32_t off[8], sh[8], msk[8], mul[8];
+struct EnccColumn {          // one thread's column: 8 decoded descriptors (addr: the word of the thread's first state)
+    encc_addr_t addr[8];
+    uint32_t sh[8], msk[8], mul[8];
 };
 
 template <typename OutT>
-__device__ __forceinline__ void encc_load_column(EnccColumn<OutT>& C, const uint32_t* desc, int c, int sw, int nc) {
+__device__ __forceinline__ void encc_load_column(EnccColumn<OutT>& C, const uint32_t* desc, int c, int sw, int nc,
+                                                 const uint32_t* first /* the staged words of the thread's first state */) {
     constexpr uint32_t ONE = sizeof(OutT) == 2 ? 0x3F80u : 0x3F800000u;
     constexpr uint32_t FULL = sizeof(OutT) == 2 ? 0xFFFFu : 0xFFFFFFFFu;
 #pragma unroll
@@ -70,12 +88,12 @@ __device__ __forceinline__ void encc_load_column(EnccColumn<OutT>& C, const uint
         else if (kind == 2u) { off = (uint32_t)sw + (pl >> 5); sh = pl & 31u; msk = 1u; mul = ONE; }
         else if (kind == 3u) { off = (uint32_t)(2 * sw) + pl; msk = FULL; mul = 1u; }
         if (sizeof(OutT) == 2 && (k & 1)) mul <<= 16;        // bf16: the odd element of a pair lands in the high half
-        C.off[k] = off; C.sh[k] = sh; C.msk[k] = msk; C.mul[k] = mul;
+        C.addr[k] = encc_addr(first + off); C.sh[k] = sh; C.msk[k] = msk; C.mul[k] = mul;
     }
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(ENCC_THREADS)
+__global__ void __launch_bounds__(ENCC_THREADS, 4)
 encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint32_t* __restrict__ states,
                   const uint32_t* __restrict__ prev, const uint8_t* __restrict__ prev_count, int max_prev,
                   OutT* __restrict__ out, int c_pad, int row_elems /* multiple of 8 */, int S /* states per tile */) {
@@ -96,7 +114,7 @@ encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const 
     const int j = wide ? 0 : t / CPR;
     const int c0 = wide ? t : t - j * CPR;
     EnccColumn<OutT> C;
-    if (NCG == 1 && t < NT) encc_load_column<OutT>(C, desc, c0, sw, nc);
+    if (NCG == 1 && t < NT) encc_load_column<OutT>(C, desc, c0, sw, nc, blk + j * BW);
     const int step_s = ENCC_THREADS / sw, step_w = ENCC_THREADS - step_s * sw;     // (s, w) of word i + ENCC_THREADS
     for (int64_t n0 = (int64_t)blockIdx.x * S; n0 < n; n0 += (int64_t)gridDim.x * S) {
         const int nb = (int)((n - n0) < S ? (n - n0) : S);
@@ -129,26 +147,32 @@ encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const 
             for (int cg = 0; cg < NCG; ++cg) {
                 const int c = cg * ENCC_THREADS + c0;
                 if (c >= CPR) break;
-                if (NCG > 1) encc_load_column<OutT>(C, desc, c, sw, nc);
-                OutT* dst0 = out + n0 * (int64_t)row_elems + (int64_t)c * 8;
-                for (int s = j; s < nb; s += J) {
-                    const uint32_t* b = blk + s * BW;
-                    OutT* dst = dst0 + (int64_t)s * row_elems;
+                if (NCG > 1) encc_load_column<OutT>(C, desc, c, sw, nc, blk + j * BW);
+                OutT* dst = out + n0 * (int64_t)row_elems + (int64_t)c * 8 + (int64_t)j * row_elems;
+                const int64_t dstep = (int64_t)J * row_elems;
+                const encc_addr_t astep = (encc_addr_t)(J * BW) * 4;
+                int iters = 0;
+                for (int s = j; s < nb; s += J, ++iters) {
                     if (sizeof(OutT) == 2) {
                         uint32_t v[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k)            // two elements per word: the multipliers place them
-                            v[k] = ((b[C.off[2 * k]] >> C.sh[2 * k]) & C.msk[2 * k]) * C.mul[2 * k] +
-                                   ((b[C.off[2 * k + 1]] >> C.sh[2 * k + 1]) & C.msk[2 * k + 1]) * C.mul[2 * k + 1];
+                            v[k] = ((encc_lds(C.addr[2 * k]) >> C.sh[2 * k]) & C.msk[2 * k]) * C.mul[2 * k] +
+                                   ((encc_lds(C.addr[2 * k + 1]) >> C.sh[2 * k + 1]) & C.msk[2 * k + 1]) * C.mul[2 * k + 1];
                         *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
                     } else {
                         uint32_t v[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = ((b[C.off[k]] >> C.sh[k]) & C.msk[k]) * C.mul[k];
+                        for (int k = 0; k < 8; ++k) v[k] = ((encc_lds(C.addr[k]) >> C.sh[k]) & C.msk[k]) * C.mul[k];
                         reinterpret_cast<uint4*>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
                         reinterpret_cast<uint4*>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
                     }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) C.addr[k] += astep;
+                    dst += dstep;
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) C.addr[k] -= astep * (encc_addr_t)iters;      // back to the first state (next tile)
             }
         }
     }

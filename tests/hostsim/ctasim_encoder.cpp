@@ -40,6 +40,7 @@ static inline void sim_syncthreads() { g_cta_barrier->arrive_and_wait(); }
 static inline uint32_t sim_float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 #define __float_as_uint sim_float_as_uint
 #define ENCC_DYNAMIC_SMEM(name) uint32_t* name = g_cta_smem
+#define ENCC_HOST_BUILD 1
 
 #include "../../galvanise_zero_b200/csrc/gz_encoder_col.cuh"
 
