@@ -753,11 +753,11 @@ def run_puct(args, rank, world, local, propnet_line=None):
             out_bytes = arr['planes'][0].numel() * 2 + sum(p.shape[1] for p in arr['policies']) * 4 + arr['value'].shape[1] * 4
             alg = int(gathered.shape[1]) * 4 + out_bytes          # a record read once, its rows written once
             ach = alg * n_gathered / (t_ms * 1e-3) / 1e9
-            # the same kernels over 2^20 output rows (every record repeated through the row index: the rows written,
-            # 1.2 GB, no longer fit the L2): the figure the HBM roofline applies to
+            # the same kernels over up to 2^20 output rows (every record repeated through the row index: the rows
+            # written, 1.2 GB for reversi, no longer fit the L2): the figure the HBM roofline applies to
             big = None
             if n_gathered >= 1024:
-                rows_big = 1 << 20
+                rows_big = max(1 << 14, min(1 << 20, int(4e9 // max(1, out_bytes))))      # at most ~4 GB of rows
                 idx_big = (torch.arange(rows_big, device=eng.device, dtype=torch.int64) % n_gathered).to(torch.int32)
                 for _ in range(2):
                     tb.arrays(gathered, plane_dtype=torch.bfloat16, index=idx_big)

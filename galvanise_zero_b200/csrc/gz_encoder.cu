@@ -329,6 +329,11 @@ extern "C" int gz_encode_set_column_kernel_min_batch(int64_t min_batch) {
     g_col_min_batch = min_batch < 0 ? ((int64_t)1 << 62) : min_batch;
     return GZ_OK;
 }
+static int g_col_ragged = 0;        // rows that are not a multiple of 8 elements through the column kernel too (units of states)
+extern "C" int gz_encode_set_column_kernel_ragged(int on) {
+    g_col_ragged = on ? 1 : 0;
+    return GZ_OK;
+}
 static int g_col_tile = 0;          // states per tile, 0: the default (see gz_encode_layout)
 extern "C" int gz_encode_set_column_kernel_tile(int tile_states) {
     g_col_tile = tile_states;
@@ -357,18 +362,21 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
     if ((((uintptr_t)d_out) & 15) != 0) { gz_set_error("plane buffer must be 16-byte aligned"); return GZ_ERR_ARG; }
     GZ_CUDA(cudaSetDevice(t->device));
     const int row_elems_c = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
-    if (n >= g_col_min_batch && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32) && (row_elems_c & 7) == 0 &&
-        row_elems_c >= 8) {
+    if (n >= g_col_min_batch && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32) && row_elems_c >= 8 &&
+        ((row_elems_c & 7) == 0 || g_col_ragged)) {
         const int row_elems = row_elems_c;
+        // rows that are not a multiple of 8 elements go in units of U states (gz_encoder_col.cuh)
+        int U = 1;
+        while ((U * row_elems) & 7) U <<= 1;
         const int BW = 2 * state_words + t->num_control_channels + 1;
         // the tile (measured, profiles/r02_encoder_column_kernel.jsonl): what matters is the number of 8-element
         // chunks a thread stores per tile — about 40 for bf16 rows, about 12 for f32 rows
         const bool half = out_dtype == GZ_DTYPE_BF16;
         int S = g_col_tile;
         if (g_col_tile < 8) {
-            const int CPR = row_elems >> 3;
+            const int CPR = (U * row_elems) >> 3;
             const int NT = CPR >= ENCC_THREADS ? ENCC_THREADS : (ENCC_THREADS / CPR) * CPR;
-            const double want = (half ? 40.0 : 12.0) * NT / CPR;
+            const double want = (half ? 40.0 : 12.0) * NT / CPR * U;       // states
             S = 8;
             while (S < 256 && (double)S * 1.4142 < want) S <<= 1;          // nearest power of two
             const int lo = 32, hi = half ? 256 : 64;
@@ -376,17 +384,23 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
         }
         if (g_col_tile < 8)                      // mid-size batches: enough tiles for every SM's resident CTAs
             while (S > 8 && (n + S - 1) / S < (int64_t)t->n_sms * 4) S >>= 1;
-        auto need = [&](int k) { return ((size_t)row_elems + (size_t)k * BW) * 4; };
-        while (S > 8 && need(S) > 48 * 1024) S >>= 1;
-        if ((row_elems & 7) == 0 && need(S) <= 48 * 1024) {
+        auto need = [&](int k) { return ((size_t)U * row_elems + (size_t)k * BW) * 4; };
+        const size_t cap = U == 1 ? 48 * 1024 : 160 * 1024;     // (large states — hexLG13 — need the opt-in limit)
+        while (S > 8 && need(S) > cap) S >>= 1;
+        if (S >= U && (S % U) == 0 && need(S) <= cap) {
             const int64_t blocks = (n + S - 1) / S;
             const int grid = (int)std::min<int64_t>(blocks, (int64_t)t->n_sms * 8);
-            if (out_dtype == GZ_DTYPE_BF16)
+            if (out_dtype == GZ_DTYPE_BF16) {
+                if (need(S) > 48 * 1024)
+                    GZ_CUDA(cudaFuncSetAttribute(encode_col_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(S)));
                 encode_col_kernel<__nv_bfloat16><<<grid, ENCC_THREADS, need(S), (cudaStream_t)stream>>>(
-                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (__nv_bfloat16*)d_out, c_pad, row_elems, S);
-            else
+                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (__nv_bfloat16*)d_out, c_pad, row_elems, S, U);
+            } else {
+                if (need(S) > 48 * 1024)
+                    GZ_CUDA(cudaFuncSetAttribute(encode_col_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(S)));
                 encode_col_kernel<float><<<grid, ENCC_THREADS, need(S), (cudaStream_t)stream>>>(
-                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (float*)d_out, c_pad, row_elems, S);
+                    t->E, n, state_words, d_states, d_prev, d_prev_count, max_prev, (float*)d_out, c_pad, row_elems, S, U);
+            }
             GZ_CUDA(cudaGetLastError());
             return GZ_OK;
         }

@@ -1,4 +1,4 @@
-// gz_encoder_col.cuh — the column-owned plane encoder for large batches (rows that are a multiple of 8 elements).
+// gz_encoder_col.cuh — the column-owned plane encoder for large batches.
 //
 // encode_fast_kernel (gz_encoder.cu) interprets one descriptor per output ELEMENT per state: ~30 instructions per
 // element (descriptor fetch and decode, three divergent kinds), which bounds it at 15-25 % of the HBM roofline
@@ -10,6 +10,11 @@
 // store (bf16; two for f32). Thread t writes flat chunk t + i * (threads in use), so a warp's stores are one
 // contiguous 512-byte (bf16) run whatever the row size; a thread's column never changes because the stride is a
 // multiple of the chunks per row.
+//
+// Rows that are not a multiple of 8 elements (hexLG13: 845, breakthroughSmall: 180) are handled in UNITS of
+// U = 8 / gcd(8, row) consecutive states: a unit is a multiple of 8 elements, its descriptor pattern is the same for
+// every unit, and a chunk that straddles two states simply reads its elements from two staged states (the state
+// within the unit is part of the descriptor). States beyond the batch's last complete unit are written element-wise.
 //
 // Results are those of encode_kernel / encode_fast_kernel (tests/test_encoder.py runs all against the C oracle
 // and the reference's compiled toChannels); tests/hostsim/ctasim_encoder.cpp compiles this header for the CPU.
@@ -42,10 +47,12 @@ static inline uint32_t encc_lds(encc_addr_t a) { return *reinterpret_cast<const 
 
 // the row's element descriptors (shared with the description in gz_encoder.cu: kind in bits 30-31 — 0 zero, 1 bit
 // of the state, 2 bit of the OR of the previous states, 3 control channel —, payload in bits 0-29)
+// (units: bits 27-29 hold the state within the unit, the payload is 27 bits)
 __device__ __forceinline__ void encc_build_desc(const EncParams& E, uint32_t* desc, int row_elems, int c_pad,
-                                                bool has_prev, int tid, int nthreads) {
+                                                bool has_prev, int tid, int nthreads, int U) {
     const int n_ch = E.total / E.channel_size;
-    for (int le0 = tid; le0 < row_elems; le0 += nthreads) {
+    for (int e0 = tid; e0 < U * row_elems; e0 += nthreads) {
+        const int su = e0 / row_elems, le0 = e0 - su * row_elems;
         int le = le0;
         uint32_t d = 0u;
         bool live = true;
@@ -64,7 +71,8 @@ __device__ __forceinline__ void encc_build_desc(const EncParams& E, uint32_t* de
                 d = (3u << 30) | (uint32_t)((le - E.board_total) / E.channel_size);
             }
         }
-        desc[le0] = d;
+        if (d) d |= (uint32_t)su << 27;
+        desc[e0] = d;
     }
 }
 
@@ -76,19 +84,20 @@ struct EnccColumn {          // one thread's column: 8 decoded descriptors (addr
 
 template <typename OutT>
 __device__ __forceinline__ void encc_load_column(EnccColumn<OutT>& C, const uint32_t* desc, int c, int sw, int nc,
-                                                 const uint32_t* first /* the staged words of the thread's first state */) {
+                                                 const uint32_t* first /* the staged words of the thread's first unit */) {
+    const int BW = 2 * sw + nc + 1;
     constexpr uint32_t ONE = sizeof(OutT) == 2 ? 0x3F80u : 0x3F800000u;
     constexpr uint32_t FULL = sizeof(OutT) == 2 ? 0xFFFFu : 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t d = desc[c * 8 + k];
-        const uint32_t kind = d >> 30, pl = d & 0x3FFFFFFFu;
+        const uint32_t kind = d >> 30, su = (d >> 27) & 7u, pl = d & 0x07FFFFFFu;
         uint32_t off = (uint32_t)(2 * sw + nc), sh = 0u, msk = 0u, mul = 0u;          // the tile's zero word
         if (kind == 1u) { off = pl >> 5; sh = pl & 31u; msk = 1u; mul = ONE; }
         else if (kind == 2u) { off = (uint32_t)sw + (pl >> 5); sh = pl & 31u; msk = 1u; mul = ONE; }
         else if (kind == 3u) { off = (uint32_t)(2 * sw) + pl; msk = FULL; mul = 1u; }
         if (sizeof(OutT) == 2 && (k & 1)) mul <<= 16;        // bf16: the odd element of a pair lands in the high half
-        C.addr[k] = encc_addr(first + off); C.sh[k] = sh; C.msk[k] = msk; C.mul[k] = mul;
+        C.addr[k] = encc_addr(first + su * BW + off); C.sh[k] = sh; C.msk[k] = msk; C.mul[k] = mul;
     }
 }
 
@@ -96,25 +105,27 @@ template <typename OutT>
 __global__ void __launch_bounds__(ENCC_THREADS, 4)
 encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const uint32_t* __restrict__ states,
                   const uint32_t* __restrict__ prev, const uint8_t* __restrict__ prev_count, int max_prev,
-                  OutT* __restrict__ out, int c_pad, int row_elems /* multiple of 8 */, int S /* states per tile */) {
+                  OutT* __restrict__ out, int c_pad, int row_elems, int S /* states per tile, a multiple of U */,
+                  int U /* states per unit: U * row_elems is a multiple of 8 */) {
     ENCC_DYNAMIC_SMEM(csm);
-    uint32_t* desc = csm;                                        // [row_elems]
-    uint32_t* blk = desc + row_elems;                            // [S][BW]: state | OR of previous states | control values | 0
+    uint32_t* desc = csm;                                        // [U * row_elems]
+    uint32_t* blk = desc + U * row_elems;                            // [S][BW]: state | OR of previous states | control values | 0
     const int nc = E.num_control_channels;
     const int BW = 2 * sw + nc + 1;
     const bool has_prev = prev && E.num_prev_states > 0;
     const int t = threadIdx.x;
-    encc_build_desc(E, desc, row_elems, c_pad, has_prev, t, ENCC_THREADS);
+    encc_build_desc(E, desc, row_elems, c_pad, has_prev, t, ENCC_THREADS, U);
     __syncthreads();
-    const int CPR = row_elems >> 3;                              // 8-element chunks per row
+    const int unit_elems = U * row_elems;
+    const int CPR = unit_elems >> 3;                             // 8-element chunks per unit
     const bool wide = CPR >= ENCC_THREADS;
-    const int J = wide ? 1 : ENCC_THREADS / CPR;                 // states in flight per pass over the columns
+    const int J = wide ? 1 : ENCC_THREADS / CPR;                 // units in flight per pass over the columns
     const int NT = wide ? ENCC_THREADS : J * CPR;                // threads in use
     const int NCG = wide ? (CPR + ENCC_THREADS - 1) / ENCC_THREADS : 1;
     const int j = wide ? 0 : t / CPR;
     const int c0 = wide ? t : t - j * CPR;
     EnccColumn<OutT> C;
-    if (NCG == 1 && t < NT) encc_load_column<OutT>(C, desc, c0, sw, nc, blk + j * BW);
+    if (NCG == 1 && t < NT) encc_load_column<OutT>(C, desc, c0, sw, nc, blk + j * U * BW);
     const int step_s = ENCC_THREADS / sw, step_w = ENCC_THREADS - step_s * sw;     // (s, w) of word i + ENCC_THREADS
     for (int64_t n0 = (int64_t)blockIdx.x * S; n0 < n; n0 += (int64_t)gridDim.x * S) {
         const int nb = (int)((n - n0) < S ? (n - n0) : S);
@@ -143,16 +154,17 @@ encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const 
                 sizeof(OutT) == 2 ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)) : __float_as_uint(v);
         }
         __syncthreads();
+        const int nbu = nb / U;                                  // complete units of the tile
         if (t < NT) {
             for (int cg = 0; cg < NCG; ++cg) {
                 const int c = cg * ENCC_THREADS + c0;
                 if (c >= CPR) break;
-                if (NCG > 1) encc_load_column<OutT>(C, desc, c, sw, nc, blk + j * BW);
-                OutT* dst = out + n0 * (int64_t)row_elems + (int64_t)c * 8 + (int64_t)j * row_elems;
-                const int64_t dstep = (int64_t)J * row_elems;
-                const encc_addr_t astep = (encc_addr_t)(J * BW) * 4;
+                if (NCG > 1) encc_load_column<OutT>(C, desc, c, sw, nc, blk + j * U * BW);
+                OutT* dst = out + n0 * (int64_t)row_elems + (int64_t)c * 8 + (int64_t)j * unit_elems;
+                const int64_t dstep = (int64_t)J * unit_elems;
+                const encc_addr_t astep = (encc_addr_t)(J * U * BW) * 4;
                 int iters = 0;
-                for (int s = j; s < nb; s += J, ++iters) {
+                for (int u = j; u < nbu; u += J, ++iters) {
                     if (sizeof(OutT) == 2) {
                         uint32_t v[4];
 #pragma unroll
@@ -172,8 +184,23 @@ encode_col_kernel(const __grid_constant__ EncParams E, int64_t n, int sw, const 
                     dst += dstep;
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) C.addr[k] -= astep * (encc_addr_t)iters;      // back to the first state (next tile)
+                for (int k = 0; k < 8; ++k) C.addr[k] -= astep * (encc_addr_t)iters;      // back to the first unit (next tile)
             }
+        }
+        // states beyond the last complete unit (the end of a batch that is not a multiple of U): element by element
+        for (int e = t; e < (nb - nbu * U) * row_elems; e += ENCC_THREADS) {
+            constexpr uint32_t ONE = sizeof(OutT) == 2 ? 0x3F80u : 0x3F800000u;
+            const int sr = e / row_elems, le = e - sr * row_elems, s = nbu * U + sr;
+            const uint32_t d = desc[le];
+            const uint32_t kind = d >> 30, pl = d & 0x07FFFFFFu;
+            const uint32_t* b = blk + s * BW;
+            uint32_t x = 0u;
+            if (kind == 1u) x = ((b[pl >> 5] >> (pl & 31u)) & 1u) ? ONE : 0u;
+            else if (kind == 2u) x = ((b[sw + (pl >> 5)] >> (pl & 31u)) & 1u) ? ONE : 0u;
+            else if (kind == 3u) x = b[2 * sw + pl];
+            const int64_t o = (n0 + s) * (int64_t)row_elems + le;
+            if (sizeof(OutT) == 2) reinterpret_cast<uint16_t*>(out)[o] = (uint16_t)x;
+            else reinterpret_cast<uint32_t*>(out)[o] = x;
         }
     }
 }

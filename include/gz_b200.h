@@ -147,6 +147,9 @@ int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, const uint32
 int gz_encode_set_column_kernel_min_batch(int64_t min_batch);
 /* measurement switch of that kernel: states per tile (0: default) */
 int gz_encode_set_column_kernel_tile(int tile_states);
+/* rows that are NOT a multiple of 8 elements (hexLG13, breakthroughSmall) through the column kernel as well, in units
+ * of 8 / gcd(8, row) states (default off: validated against the oracle, not yet measured on a B200) */
+int gz_encode_set_column_kernel_ragged(int on);
 
 /* Board symmetry of packed states, batched (src/ggpzero/util/symmetry.py:153-204 translate_basestate): bit j of
  * every output state = bit d_src[j] of the input state (d_src: int32 [n_bases], a permutation; padding bits

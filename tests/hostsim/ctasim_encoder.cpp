@@ -57,9 +57,11 @@ extern "C" int cs_encode_col(const int* src_base, int group_size, const int* ctr
     E.board_total = group_size * (num_prev_states + 1);
     E.total = E.board_total + num_control_channels * channel_size;
     const int row_elems = c_pad > 0 ? channel_size * c_pad : E.total;
-    if (row_elems & 7) return -1;
+    int U = 1;
+    while ((U * row_elems) & 7) U <<= 1;
+    if (S % U) return -1;
     const int BW = 2 * sw + num_control_channels + 1;
-    std::vector<uint32_t> smem((size_t)row_elems + (size_t)S * BW);
+    std::vector<uint32_t> smem((size_t)U * row_elems + (size_t)S * BW);
     sim_gridDim = {grid, 1, 1};
     for (int b = 0; b < grid; ++b) {
         std::barrier<> bar(ENCC_THREADS);
@@ -72,10 +74,10 @@ extern "C" int cs_encode_col(const int* src_base, int group_size, const int* ctr
                 sim_threadIdx = {t, 0, 0};
                 if (out_dtype == 1)
                     encode_col_kernel<__nv_bfloat16>(E, n, sw, states, prev, prev_count, max_prev, (__nv_bfloat16*)out,
-                                                     c_pad, row_elems, S);
+                                                     c_pad, row_elems, S, U);
                 else
                     encode_col_kernel<float>(E, n, sw, states, prev, prev_count, max_prev, (float*)out, c_pad,
-                                             row_elems, S);
+                                             row_elems, S, U);
             });
         for (auto& x : th) x.join();
     }

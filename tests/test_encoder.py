@@ -188,6 +188,7 @@ def test_gpu_encoder_channels_last_padded_layout(game, c_pad):
 # ------------------------------------------------------------------------------------------------
 # encode_col_kernel (csrc/gz_encoder_col.cuh): the column-owned kernel for large batches
 COL_GAMES = ['reversi', 'breakthrough', 'connect6', 'amazons_10x10', 'chess_15d']      # rows of a multiple of 8 elements
+RAGGED_GAMES = ['breakthroughSmall', 'hexLG13']      # rows of 180 / 845 elements: units of 2 / 8 states
 
 
 def _ctasim_encode(ct, n_bases, cur, prev, cnt, dtype, c_pad=0, S=8, grid=2):
@@ -230,25 +231,25 @@ def _bf16_bits(x):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize('game', COL_GAMES)
+@pytest.mark.parametrize('game', COL_GAMES + RAGGED_GAMES)
 def test_column_kernel_source_under_cta_emulation_is_bit_exact(game):
     gi, tr, ct = _setup(game)
     enc = RefEncoder.from_c_transformer(ct)
-    big = game in ('connect6', 'chess_15d')
-    n = 13 if big else 37
+    big = game in ('connect6', 'chess_15d', 'hexLG13')
+    n = 13 if big else 37                      # (ragged rows: 13 = one unit of 8 + 5 states written element-wise)
     hist = _trajectory(game, n_games=n, plies=9)
     cur, prev = hist[8], hist[7][:, None, :]
     cnt = (np.arange(n) % 2).astype(np.uint8)
     want = enc.encode(cur, prev, cnt)
     got = _ctasim_encode(ct, tr.num_bases, cur, prev, cnt, 0, S=8, grid=2)          # ragged last tile, grid stride
     assert np.array_equal(got.view(np.float32), want)
-    got16 = _ctasim_encode(ct, tr.num_bases, cur, prev, cnt, 1, S=5, grid=1)
+    got16 = _ctasim_encode(ct, tr.num_bases, cur, prev, cnt, 1, S=5 if game in COL_GAMES else 16, grid=1)
     assert np.array_equal(got16, _bf16_bits(want))
     got16 = _ctasim_encode(ct, tr.num_bases, cur, prev, cnt, 1, S=64, grid=1)        # one tile holds the batch
     assert np.array_equal(got16, _bf16_bits(want))
     want0 = enc.encode(cur)                                                          # no previous states at all
     assert np.array_equal(_ctasim_encode(ct, tr.num_bases, cur, None, None, 0, S=16, grid=3).view(np.float32), want0)
-    if not big:
+    if not big and game in COL_GAMES:
         c_pad = 16
         w3 = enc.encode(cur, prev).reshape(n, tr.num_channels, tr.channel_size)
         g3 = _ctasim_encode(ct, tr.num_bases, cur, prev, None, 1, c_pad=c_pad, S=8, grid=2).reshape(n, tr.channel_size, c_pad)
@@ -257,7 +258,7 @@ def test_column_kernel_source_under_cta_emulation_is_bit_exact(game):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('game', COL_GAMES)
+@pytest.mark.parametrize('game', COL_GAMES + RAGGED_GAMES)
 def test_gpu_column_kernel_bit_exact(game):
     """gz_encode with the column kernel forced (any batch size) against the C oracle: f32 exact, bf16 = rounded
     f32, ragged batch, some roots without a previous state, the padded channels-last layout; and the default
@@ -270,7 +271,8 @@ def test_gpu_column_kernel_bit_exact(game):
     enc = RefEncoder.from_c_transformer(ct)
     L = gzlib.lib()
     L.gz_encode_set_column_kernel_min_batch.argtypes = [ctypes.c_int64]
-    n = 331
+    L.gz_encode_set_column_kernel_ragged(1 if game in RAGGED_GAMES else 0)
+    n = 331 if game != 'hexLG13' else 45
     hist = _trajectory(game, n_games=n, plies=12)
     dev = torch.device('cuda', 0)
     try:
@@ -287,7 +289,7 @@ def test_gpu_column_kernel_bit_exact(game):
             assert np.array_equal(ct.encode(d_cur, d_prev, d_cnt, dtype=torch.float32).cpu().numpy(), want)
             assert torch.equal(ct.encode(d_cur, d_prev, d_cnt, dtype=torch.bfloat16).cpu(),
                                torch.from_numpy(want).to(torch.bfloat16))
-            if k == 11:
+            if k == 11 and game in COL_GAMES:
                 cp = 16 if tr.num_channels <= 16 else 32
                 w3 = want.reshape(n, tr.num_channels, tr.channel_size)
                 g3 = ct.encode(d_cur, d_prev, d_cnt, dtype=torch.bfloat16, c_pad=cp).float().cpu().numpy()
@@ -305,3 +307,4 @@ def test_gpu_column_kernel_bit_exact(game):
     finally:
         L.gz_encode_set_column_kernel_min_batch(16384)
         L.gz_encode_set_column_kernel_tile(0)
+        L.gz_encode_set_column_kernel_ragged(0)

@@ -17,9 +17,12 @@ PEAK = json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PE
 L = gzlib.lib()
 L.gz_encode_set_column_kernel_tile.argtypes = [ctypes.c_int]
 L.gz_encode_set_column_kernel_min_batch.argtypes = [ctypes.c_int64]
+RAGGED = os.environ.get('GZ_BENCH_RAGGED', '') == '1'         # rows that are not a multiple of 8 elements through the column kernel
+L.gz_encode_set_column_kernel_ragged(1 if RAGGED else 0)
+SLOTS = int(os.environ.get('GZ_BENCH_SLOTS', str(1 << 19)))
 for game in (sys.argv[1:] or ['reversi', 'connect6', 'amazons_10x10', 'chess_15d']):
     dev = DeviceStateMachine(game, device=0)
-    n = 1 << 19
+    n = SLOTS
     s = torch.zeros((n, dev.state_words), dtype=torch.int32, device=dev.device)
     l, t, g = dev.alloc_views(n)
     t.fill_(1)
@@ -32,9 +35,12 @@ for game in (sys.argv[1:] or ['reversi', 'connect6', 'amazons_10x10', 'chess_15d
     for dtype in (torch.bfloat16, torch.float32):
         out = torch.empty((n, ct.total_size()), dtype=dtype, device=dev.device)
         bytes_per = 2 * ((dev.n_bases + 7) // 8) + out.element_size() * ct.total_size()
-        for label, mb, tile in (('encode_fast_kernel', -1, 0), ('encode_col_kernel S=32', 1, 32), ('encode_col_kernel S=64', 1, 64),
-                                ('encode_col_kernel S=128', 1, 128), ('encode_col_kernel S=256', 1, 256),
-                                ('encode_col_kernel default', 1, 0)):
+        configs = (('encode_fast_kernel', -1, 0), ('encode_col_kernel S=32', 1, 32), ('encode_col_kernel S=64', 1, 64),
+                   ('encode_col_kernel S=128', 1, 128), ('encode_col_kernel S=256', 1, 256), ('encode_col_kernel default', 1, 0))
+        if RAGGED:
+            configs = (('small-batch kernels', -1, 0), ('encode_col_kernel S=8', 1, 8), ('encode_col_kernel S=16', 1, 16),
+                       ('encode_col_kernel default', 1, 0))
+        for label, mb, tile in configs:
             L.gz_encode_set_column_kernel_min_batch(mb)
             L.gz_encode_set_column_kernel_tile(tile)
             for _ in range(3):
@@ -54,3 +60,4 @@ for game in (sys.argv[1:] or ['reversi', 'connect6', 'amazons_10x10', 'chess_15d
     torch.cuda.empty_cache()
 L.gz_encode_set_column_kernel_min_batch(16384)
 L.gz_encode_set_column_kernel_tile(0)
+L.gz_encode_set_column_kernel_ragged(0)
