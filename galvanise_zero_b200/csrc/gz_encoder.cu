@@ -329,9 +329,12 @@ extern "C" int gz_encode_set_column_kernel_min_batch(int64_t min_batch) {
     g_col_min_batch = min_batch < 0 ? ((int64_t)1 << 62) : min_batch;
     return GZ_OK;
 }
-static int g_col_ragged = 0;        // rows that are not a multiple of 8 elements through the column kernel too (units of states)
+// rows that are not a multiple of 8 elements through the column kernel too (units of states): -1 (default) where a
+// tile fits the 48 KB every kernel may use (breakthroughSmall: measured 3.1x the small-batch kernels), 1 always
+// (hexLG13's 3.7 KB states need the opt-in limit: bit-exact on a B200, not yet measured), 0 never
+static int g_col_ragged = -1;
 extern "C" int gz_encode_set_column_kernel_ragged(int on) {
-    g_col_ragged = on ? 1 : 0;
+    g_col_ragged = on < 0 ? -1 : (on ? 1 : 0);
     return GZ_OK;
 }
 static int g_col_tile = 0;          // states per tile, 0: the default (see gz_encode_layout)
@@ -363,7 +366,7 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
     GZ_CUDA(cudaSetDevice(t->device));
     const int row_elems_c = c_pad > 0 ? t->E.channel_size * c_pad : t->E.total;
     if (n >= g_col_min_batch && (out_dtype == GZ_DTYPE_BF16 || out_dtype == GZ_DTYPE_F32) && row_elems_c >= 8 &&
-        ((row_elems_c & 7) == 0 || g_col_ragged)) {
+        ((row_elems_c & 7) == 0 || g_col_ragged != 0)) {
         const int row_elems = row_elems_c;
         // rows that are not a multiple of 8 elements go in units of U states (gz_encoder_col.cuh)
         int U = 1;
@@ -385,7 +388,7 @@ extern "C" int gz_encode_layout(gz_transformer* t, int64_t n, int state_words, c
         if (g_col_tile < 8)                      // mid-size batches: enough tiles for every SM's resident CTAs
             while (S > 8 && (n + S - 1) / S < (int64_t)t->n_sms * 4) S >>= 1;
         auto need = [&](int k) { return ((size_t)U * row_elems + (size_t)k * BW) * 4; };
-        const size_t cap = U == 1 ? 48 * 1024 : 160 * 1024;     // (large states — hexLG13 — need the opt-in limit)
+        const size_t cap = (U > 1 && g_col_ragged == 1) ? 160 * 1024 : 48 * 1024;     // (large states — hexLG13 — need the opt-in limit)
         while (S > 8 && need(S) > cap) S >>= 1;
         if (S >= U && (S % U) == 0 && need(S) <= cap) {
             const int64_t blocks = (n + S - 1) / S;

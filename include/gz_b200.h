@@ -148,7 +148,8 @@ int gz_encode_set_column_kernel_min_batch(int64_t min_batch);
 /* measurement switch of that kernel: states per tile (0: default) */
 int gz_encode_set_column_kernel_tile(int tile_states);
 /* rows that are NOT a multiple of 8 elements (hexLG13, breakthroughSmall) through the column kernel as well, in units
- * of 8 / gcd(8, row) states (default off: validated against the oracle, not yet measured on a B200) */
+ * of 8 / gcd(8, row) states: -1 (default) where a tile of states fits 48 KB of shared memory (breakthroughSmall),
+ * 1 always (hexLG13: opt-in shared memory; bit-exact on a B200, not measured), 0 never */
 int gz_encode_set_column_kernel_ragged(int on);
 
 /* Board symmetry of packed states, batched (src/ggpzero/util/symmetry.py:153-204 translate_basestate): bit j of

@@ -307,4 +307,4 @@ def test_gpu_column_kernel_bit_exact(game):
     finally:
         L.gz_encode_set_column_kernel_min_batch(16384)
         L.gz_encode_set_column_kernel_tile(0)
-        L.gz_encode_set_column_kernel_ragged(0)
+        L.gz_encode_set_column_kernel_ragged(-1)

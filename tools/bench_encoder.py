@@ -18,7 +18,7 @@ L = gzlib.lib()
 L.gz_encode_set_column_kernel_tile.argtypes = [ctypes.c_int]
 L.gz_encode_set_column_kernel_min_batch.argtypes = [ctypes.c_int64]
 RAGGED = os.environ.get('GZ_BENCH_RAGGED', '') == '1'         # rows that are not a multiple of 8 elements through the column kernel
-L.gz_encode_set_column_kernel_ragged(1 if RAGGED else 0)
+L.gz_encode_set_column_kernel_ragged(1 if RAGGED else -1)
 SLOTS = int(os.environ.get('GZ_BENCH_SLOTS', str(1 << 19)))
 for game in (sys.argv[1:] or ['reversi', 'connect6', 'amazons_10x10', 'chess_15d']):
     dev = DeviceStateMachine(game, device=0)
@@ -60,4 +60,4 @@ for game in (sys.argv[1:] or ['reversi', 'connect6', 'amazons_10x10', 'chess_15d
     torch.cuda.empty_cache()
 L.gz_encode_set_column_kernel_min_batch(16384)
 L.gz_encode_set_column_kernel_tile(0)
-L.gz_encode_set_column_kernel_ragged(0)
+L.gz_encode_set_column_kernel_ragged(-1)
