@@ -109,6 +109,12 @@ class TrainingBatcher(object):
         idx = keep.nonzero()                                                               # row-major: sample-major
         return idx[:, 0].to(torch.int32).contiguous(), idx[:, 1].to(torch.int32).contiguous()
 
+    def arrays_from_samples(self, samples, **kw):
+        """``arrays`` for ``datadesc.Sample`` objects / fetch_samples dicts (e.g. ``gendata.read_gendata(path).samples``)."""
+        import torch
+        recs = samples_to_records(samples, self.transformer, self.state_words)
+        return self.arrays(torch.from_numpy(recs).to(self.device), **kw)
+
     # ---- the arrays
     def arrays(self, records, plane_dtype=None, check=False, index=None, sym=None):
         """records: int32 CUDA tensor [n, record_words]. Returns a dict: ``planes`` [rows, C, H, W] (float32, or
@@ -149,6 +155,62 @@ class TrainingBatcher(object):
 
 
 _SR_HEADER = 24        # include/gz_b200.h GZ_SR_HEADER
+(_SR_DEPTH, _SR_GAME_LENGTH, _SR_SLOT, _SR_MATCH, _SR_HAS_RESIGNED, _SR_RESIGN_FP, _SR_START_DEPTH, _SR_VISITS, _SR_LEAD,
+ _SR_N_PREV, _SR_N_CHILDREN) = range(1, 12)
+_SR_FINAL_SCORE, _SR_PUCT_SCORE, _SR_OTHER_MOVES = 12, 16, 20
+
+
+def samples_to_records(samples, transformer, state_words, record_words=None):
+    """``datadesc.Sample`` objects (or the dicts of ``Supervisor.fetch_samples``) -> int32 sample records
+    (include/gz_b200.h GZ_SR_*), the inverse of ``PuctEngine.records_to_samples`` — what lets a generation file
+    written by the reference (``gendata_<game>_<step>.json.gz`` through ``gendata.read_gendata``) feed
+    ``TrainingBatcher.arrays``. States may be bit lists or the reference's base64 strings (``util/state.py``). The
+    role with the longest policy is the record's lead role (ties: the first); every other role must hold exactly
+    one (move, probability) pair, as ``SelfPlayManager::createSample`` writes them (selfplaymanager.cpp:95-108)."""
+    from . import tables
+    from .gendata import decode_state
+    widths = list(transformer.policy_dist_count)
+    nb = transformer.num_bases
+    rw = record_words or (_SR_HEADER + 2 * state_words + 2 * max(widths))
+    recs = np.zeros((len(samples), rw), dtype=np.int32)
+    f = recs.view(np.float32)
+    get = (lambda s, k: s[k]) if samples and isinstance(samples[0], dict) else getattr
+    for i, s in enumerate(samples):
+        policies = get(s, 'policies')
+        assert len(policies) == len(widths), 'one policy per role'
+        lead = max(range(len(widths)), key=lambda ri: (len(policies[ri]), -ri))
+        pairs = policies[lead]
+        assert _SR_HEADER + 2 * state_words + 2 * len(pairs) <= rw, 'policy longer than a record holds'
+        bits = np.asarray(decode_state(get(s, 'state')), dtype=np.uint8)[:nb]
+        recs[i, _SR_HEADER:_SR_HEADER + state_words] = tables.pack_state_bits(bits, state_words).view(np.int32)
+        prevs = get(s, 'prev_states')
+        assert len(prevs) <= 1, 'sample records carry at most one previous state'
+        if prevs:
+            pb = np.asarray(decode_state(prevs[0]), dtype=np.uint8)[:nb]
+            recs[i, _SR_HEADER + state_words:_SR_HEADER + 2 * state_words] = tables.pack_state_bits(pb, state_words).view(np.int32)
+        recs[i, _SR_N_PREV] = len(prevs)
+        recs[i, _SR_LEAD] = lead
+        recs[i, _SR_N_CHILDREN] = len(pairs)
+        p0 = _SR_HEADER + 2 * state_words
+        recs[i, p0:p0 + 2 * len(pairs):2] = [int(m) for m, _ in pairs]
+        f[i, p0 + 1:p0 + 2 * len(pairs):2] = [float(p) for _, p in pairs]
+        for ri, pol in enumerate(policies):
+            if ri != lead:
+                assert len(pol) == 1, 'a role that is not on move has one (move, 1.0) pair'
+            recs[i, _SR_OTHER_MOVES + ri] = int(pol[0][0])
+        fs = get(s, 'final_score')
+        ps = get(s, 'resultant_puct_score')
+        for ri in range(len(widths)):
+            f[i, _SR_FINAL_SCORE + ri] = fs[ri]
+            if ri < len(ps):
+                f[i, _SR_PUCT_SCORE + ri] = ps[ri]
+        recs[i, _SR_DEPTH] = get(s, 'depth')
+        recs[i, _SR_GAME_LENGTH] = get(s, 'game_length')
+        recs[i, _SR_HAS_RESIGNED] = int(bool(get(s, 'has_resigned')))
+        recs[i, _SR_RESIGN_FP] = int(bool(get(s, 'resign_false_positive')))
+        recs[i, _SR_START_DEPTH] = get(s, 'starting_sample_depth')
+        recs[i, _SR_VISITS] = get(s, 'resultant_puct_visits')
+    return recs
 
 
 def game_symmetries(game):

@@ -104,6 +104,40 @@ def test_oracle_rows_equal_the_python_transformer_on_decoded_samples(game):
                                         final_score=fs))
 
 
+@pytest.mark.parametrize('game', ['reversi', 'connect6'])
+def test_samples_to_records_is_the_inverse_of_records_to_samples(game, tmp_path):
+    """Sample objects — also after a trip through a generation file in the reference's format, states as base64
+    strings — pack back into the records they came from (the fields the array builder reads), so a file written by
+    the reference can feed the device path."""
+    from galvanise_zero_b200 import gendata
+    from galvanise_zero_b200.datacache import samples_to_records
+    gi, tr, ct, sm = _setup(game)
+    recs = synthetic_records(tr, sm, 40, seed=77)
+    f = recs.view(np.float32)
+    for i in range(len(recs)):                       # (file floats are rounded to 5 decimals: use values that survive)
+        for r in range(2):
+            f[i, tref.SR_FINAL_SCORE + r] = np.float32(round(float(f[i, tref.SR_FINAL_SCORE + r]), 5))
+    dicts = _sample_dicts(recs, tr, sm)
+    back = samples_to_records(dicts, tr, sm.state_words, recs.shape[1])
+    used = [tref.SR_LEAD, tref.SR_N_PREV, tref.SR_N_CHILDREN, tref.SR_DEPTH] + list(range(tref.SR_FINAL_SCORE, tref.SR_FINAL_SCORE + 2))
+    assert np.array_equal(back[:, used], recs[:, used]) and np.array_equal(back[:, H:], recs[:, H:])
+    for i in range(len(recs)):
+        o = 1 - recs[i, tref.SR_LEAD]
+        assert back[i, tref.SR_OTHER_MOVES + o] == recs[i, tref.SR_OTHER_MOVES + o]
+    samples = [gendata.encode_sample_states(datadesc.Sample(**d)) for d in dicts]
+    path = str(tmp_path / gendata.gendata_filename(game, 7))
+    gendata.write_gendata(path, game, 'gen_x', samples)
+    gen = gendata.read_gendata(path)
+    again = samples_to_records(gen.samples, tr, sm.state_words, recs.shape[1])
+    st = slice(H, H + 2 * sm.state_words)
+    assert np.array_equal(again[:, st], recs[:, st]) and np.array_equal(again[:, used[:3]], recs[:, used[:3]])
+    enc = RefEncoder.from_c_transformer(ct)
+    a = tref.records_to_training(again, sm.state_words, tr.num_bases, tr.policy_dist_count, tr.num_rewards, enc)
+    b = tref.records_to_training(recs, sm.state_words, tr.num_bases, tr.policy_dist_count, tr.num_rewards, enc)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    assert all(np.allclose(x, y, atol=1e-5) for x, y in zip(a[1], b[1]))        # (probabilities rounded by the file format)
+
+
 def test_host_value_policy_and_check_functions():
     gi, tr, ct, sm = _setup('reversi')                       # draw head (data/reversi_8x8/generations/*.json)
     assert tr.num_rewards == 3 and bases.GdlBasesTransformer_Draws is bases.GdlBasesTransformer
