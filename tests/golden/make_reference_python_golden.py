@@ -1,0 +1,156 @@
+#!/usr/bin/env python
+"""Golden vectors from the REFERENCE'S OWN Python transformer, generated in the build container:
+
+    python tests/golden/make_reference_python_golden.py        # needs /root/reference
+
+`ggpzero.nn.bases` (src/ggpzero/nn/bases.py) and `ggpzero.defs.{datadesc,gamedesc}` are imported unmodified from
+/root/reference/src. What they import from packages that are not in this container is stubbed with the surface
+they touch: `ggplib.util.symbols.SymbolFactory.symbolize` (an s-expression reader returning nested lists of str;
+`Term` = str), `ggplib.db.lookup.GameInfo` (a type to isinstance against), `ggplib.util.log`, and
+`ggpzero_interface.buf_to_tuple_reverse_bytes` (np.unpackbits). The game model (roles, bases, actions as GDL strings)
+comes from this build's compiler — the base / action ORDER is this build's (unpinned by the reference, DESIGN.md
+§2); everything computed FROM that order is the reference's code:
+
+  * `GdlBasesTransformer.__init__` / `init_spaces` / `create_board_space` / `create_control_space`
+    (bases.py:62-240) with the reference's `gamedesc.Games()` descriptions -> board / control tables,
+  * `state_to_channels(state, prev_states)` (bases.py:242-287) on positions reached by random play,
+  * `policy_to_array`, `value_to_array` (plain and the draw head's, bases.py:305-335) and `check_sample`
+    (bases.py:289-303) on sample records,
+
+stored in tests/golden/refpy_<game>.json.gz and checked by tests/test_reference_python_golden.py against
+galvanise_zero_b200/bases.py, the C oracle encoder (oracle/encoder_ref.c), oracle/training_ref.py and — on a GPU —
+gz_encode / gz_records_to_training."""
+import gzip
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, '..', '..'))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+GAMES = ['reversi', 'breakthrough', 'breakthroughSmall', 'connect6', 'amazons_10x10', 'chess_15d', 'hexLG13']
+
+
+def install_stubs():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class SymbolFactory(object):
+        def to_symbols(self, s):
+            toks = s.replace('(', ' ( ').replace(')', ' ) ').split()
+
+            def parse(i):
+                out = []
+                while i < len(toks):
+                    t = toks[i]
+                    if t == '(':
+                        sub, i = parse(i + 1)
+                        out.append(sub)
+                    elif t == ')':
+                        return out, i + 1
+                    else:
+                        out.append(t)
+                        i += 1
+                return out, i
+            return parse(0)[0]
+
+        def symbolize(self, s):
+            return self.to_symbols(s)[0]
+
+    class GameInfo(object):
+        pass
+
+    class _Log(object):
+        def __getattr__(self, k):
+            return lambda *a, **kw: None
+
+    mod('ggplib').__path__ = []
+    mod('ggplib.util', log=_Log()).__path__ = []
+    mod('ggplib.util.symbols', SymbolFactory=SymbolFactory, Term=str, ListTerm=list)
+    mod('ggplib.util.log')
+    mod('ggplib.db').__path__ = []
+    mod('ggplib.db.lookup', GameInfo=GameInfo)
+    mod('ggpzero_interface',
+        buf_to_tuple_reverse_bytes=lambda buf: tuple(bool(x) for x in np.unpackbits(np.frombuffer(buf, dtype=np.uint8))))
+    return GameInfo
+
+
+def main(games):
+    GameInfo = install_stubs()
+    sys.path.insert(0, '/root/reference/src')
+    from ggpzero.defs import datadesc as ref_datadesc
+    from ggpzero.nn import bases as ref_bases
+    from galvanise_zero_b200 import lookup, tables
+    from galvanise_zero_b200.defs import datadesc as my_datadesc
+    from oracle.pnref import RefStateMachine
+    import test_training_batch as ttb              # synthetic_records (records over reachable states)
+    from oracle import training_ref as tref
+
+    for game in games:
+        mine = lookup.by_name(game)
+        gi = GameInfo()
+        gi.game = game
+        gi.model = types.SimpleNamespace(roles=list(mine.model.roles), bases=list(mine.model.bases),
+                                         actions=[list(a) for a in mine.model.actions])
+        gd = my_datadesc.generation_for(game)
+        ref_gd = ref_datadesc.GenerationDescription(game=game, name='b200_synthetic', channel_last=False,
+                                                    multiple_policy_heads=True, num_previous_states=gd.num_previous_states,
+                                                    draw_head=gd.draw_head)
+        cls = ref_bases.GdlBasesTransformer_Draws if gd.draw_head else ref_bases.GdlBasesTransformer
+        tr = cls(gi, ref_gd)
+        out = dict(game=game, n_bases=len(gi.model.bases), policy_dist_count=list(tr.policy_dist_count),
+                   num_channels=tr.num_channels, num_rows=tr.num_rows, num_cols=tr.num_cols,
+                   raw_channels_per_state=tr.raw_channels_per_state,
+                   num_of_controls_channels=tr.num_of_controls_channels, num_rewards=tr.num_rewards,
+                   board_space=[[b.base_indx, b.channel_id, b.x_idx, b.y_idx] for b in tr.board_space],
+                   control_space=[[c.base_indx, c.channel_id, float(c.value)] for c in tr.control_space])
+        # ---- sample records over reachable positions, then the reference's per-sample functions
+        sm = RefStateMachine(tables.blob_by_name(game))
+        my_tr = types.SimpleNamespace(policy_dist_count=list(tr.policy_dist_count))
+        n = 6 if game in ('hexLG13', 'chess_15d') else 12
+        recs = ttb.synthetic_records(my_tr, sm, n, seed=4242, corrupt={1})
+        nb = len(gi.model.bases)
+        rows = []
+        for r in recs:
+            state, prevs, policies, final_score = tref.decode_record(r, sm.state_words, nb, len(tr.policy_dist_count))
+            state = [int(x) for x in state]
+            prevs = [[int(x) for x in p] for p in prevs]
+            planes = tr.state_to_channels(state, prevs)
+            assert planes.shape == (tr.num_channels, tr.num_cols, tr.num_rows), planes.shape
+            flat = np.asarray(planes, dtype=np.float32).reshape(-1)
+            nz = np.nonzero(flat)[0]
+            fs = [max(0.0, min(1.0, v)) for v in final_score]                     # datacache.py:716-718
+            pol = [tr.policy_to_array(p, ri) for ri, p in enumerate(policies)]
+            try:
+                val = [float(x) for x in tr.value_to_array(fs)]
+            except AssertionError:
+                val = None
+            sample = ref_datadesc.Sample(state=state, prev_states=prevs, policies=policies, final_score=fs)
+            try:
+                tr.check_sample(sample)
+                ok = True
+            except AssertionError:
+                ok = False
+            rows.append(dict(record=[int(x) for x in r],
+                             planes_nonzero=[[int(i), float(flat[i])] for i in nz],
+                             policy_nonzero=[[[int(i), float(a[i])] for i in np.nonzero(a)[0]] for a in pol],
+                             value=val, check_sample=ok))
+        out['state_words'] = sm.state_words
+        out['samples'] = rows
+        path = os.path.join(HERE, 'refpy_%s.json.gz' % game)
+        with gzip.open(path, 'wt') as f:
+            json.dump(out, f, separators=(',', ':'))
+        print(game, 'board', len(out['board_space']), 'control', len(out['control_space']), 'samples', len(rows),
+              os.path.getsize(path), 'bytes')
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:] or GAMES)

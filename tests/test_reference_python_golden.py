@@ -1,0 +1,109 @@
+"""Golden vectors computed by the reference's OWN Python transformer (src/ggpzero/nn/bases.py imported unmodified
+from /root/reference by tests/golden/make_reference_python_golden.py, ggplib stubbed): board / control tables of
+GdlBasesTransformer, state_to_channels planes, policy_to_array / value_to_array rows and check_sample verdicts for
+sample records over reachable positions of all seven games.
+
+CPU: galvanise_zero_b200/bases.py (tables, planes, rows, verdicts), the C oracle encoder and oracle/training_ref.py
+reproduce them exactly — which pins those restatements to outputs of the reference's code rather than to a reading
+of it. GPU: gz_records_to_training (encoder + rec_unpack_kernel) reproduces them through the C-ABI."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from galvanise_zero_b200 import bases, cppinterface, lookup
+from galvanise_zero_b200.defs import datadesc
+from oracle import training_ref as tref
+from oracle.pnref import RefEncoder
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GAMES = ['reversi', 'breakthrough', 'breakthroughSmall', 'connect6', 'amazons_10x10', 'chess_15d', 'hexLG13']
+
+
+def _golden(game):
+    with gzip.open(os.path.join(HERE, 'golden', 'refpy_%s.json.gz' % game), 'rt') as f:
+        return json.load(f)
+
+
+def _dense(pairs, size):
+    a = np.zeros(size, dtype=np.float32)
+    for i, v in pairs:
+        a[i] = np.float32(v)
+    return a
+
+
+def _setup(game):
+    tr = bases.GdlBasesTransformer(lookup.by_name(game), datadesc.generation_for(game))
+    return tr, cppinterface.create_c_transformer(tr)
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_transformer_tables_are_the_references(game):
+    g = _golden(game)
+    tr, ct = _setup(game)
+    assert tr.num_bases == g['n_bases'] and list(tr.policy_dist_count) == g['policy_dist_count']
+    assert (tr.num_channels, tr.num_rows, tr.num_cols) == (g['num_channels'], g['num_rows'], g['num_cols'])
+    assert tr.raw_channels_per_state == g['raw_channels_per_state']
+    assert tr.num_of_controls_channels == g['num_of_controls_channels'] and tr.num_rewards == g['num_rewards']
+    assert [[b.base_indx, b.channel_id, b.x_idx, b.y_idx] for b in tr.board_space] == g['board_space']
+    assert [[c.base_indx, c.channel_id, float(c.value)] for c in tr.control_space] == g['control_space']
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_planes_rows_and_verdicts_are_the_references(game):
+    g = _golden(game)
+    tr, ct = _setup(game)
+    sw, nb, widths, nv = g['state_words'], g['n_bases'], g['policy_dist_count'], g['num_rewards']
+    recs = np.array([s['record'] for s in g['samples']], dtype=np.int32)
+    total = tr.num_channels * tr.channel_size
+    want_planes = np.stack([_dense(s['planes_nonzero'], total) for s in g['samples']])
+    want_pol = [np.stack([_dense(s['policy_nonzero'][ri], widths[ri]) for s in g['samples']]) for ri in range(len(widths))]
+    # the oracle restatement (C encoder + training_ref) straight from the records
+    planes, pols, vals, bad = tref.records_to_training(recs, sw, nb, widths, nv, RefEncoder.from_c_transformer(ct))
+    assert np.array_equal(planes, want_planes)
+    assert all(np.array_equal(a, b) for a, b in zip(pols, want_pol))
+    assert bad == sum(1 for s in g['samples'] if not s['check_sample']) and bad >= 1
+    for i, s in enumerate(g['samples']):
+        if s['value'] is not None:
+            assert vals[i].tolist() == [np.float32(v) for v in s['value']]
+    # the Python mirror of the transformer on the decoded samples
+    for i, s in enumerate(g['samples']):
+        state, prevs, policies, final_score = tref.decode_record(recs[i], sw, nb, len(widths))
+        assert np.array_equal(tr.state_to_channels(state, prevs).reshape(-1), want_planes[i])
+        fs = [max(0.0, min(1.0, v)) for v in final_score]
+        for ri in range(len(widths)):
+            assert np.array_equal(tr.policy_to_array(policies[ri], ri), want_pol[ri][i])
+        if s['value'] is not None:
+            assert tr.value_to_array(fs).tolist() == [np.float32(v) for v in s['value']]
+        sample = datadesc.Sample(state=[int(x) for x in state], prev_states=[[int(x) for x in p] for p in prevs],
+                                 policies=policies, final_score=fs)
+        if s['check_sample']:
+            tr.check_sample(sample)
+        else:
+            with pytest.raises(AssertionError):
+                tr.check_sample(sample)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('game', GAMES)
+def test_device_arrays_are_the_references(game):
+    import torch
+    from galvanise_zero_b200.datacache import TrainingBatcher
+    g = _golden(game)
+    tr, ct = _setup(game)
+    widths = g['policy_dist_count']
+    recs = np.array([s['record'] for s in g['samples']], dtype=np.int32)
+    total = tr.num_channels * tr.channel_size
+    want_planes = np.stack([_dense(s['planes_nonzero'], total) for s in g['samples']])
+    out = TrainingBatcher(tr, ct, g['state_words'], device=0).arrays(torch.from_numpy(recs).cuda(), check=True)
+    assert np.array_equal(out['planes'].reshape(len(recs), -1).cpu().numpy(), want_planes)
+    for ri in range(len(widths)):
+        want = np.stack([_dense(s['policy_nonzero'][ri], widths[ri]) for s in g['samples']])
+        assert np.array_equal(out['policies'][ri].cpu().numpy(), want)
+    got_v = out['value'].cpu().numpy()
+    for i, s in enumerate(g['samples']):
+        if s['value'] is not None:
+            assert got_v[i].tolist() == [np.float32(v) for v in s['value']]
+    assert out['bad'] == sum(1 for s in g['samples'] if not s['check_sample'])
