@@ -5,8 +5,8 @@
 
 `ggpzero.nn.bases` (src/ggpzero/nn/bases.py) and `ggpzero.defs.{datadesc,gamedesc}` are imported unmodified from
 /root/reference/src. What they import from packages that are not in this container is stubbed with the surface
-they touch: `ggplib.util.symbols.SymbolFactory.symbolize` (an s-expression reader returning nested lists of str;
-`Term` = str), `ggplib.db.lookup.GameInfo` (a type to isinstance against), `ggplib.util.log`, and
+they touch: `ggplib.util.symbols.SymbolFactory.symbolize` (an s-expression reader returning nested `ListTerm`s — a
+tuple subclass — of `Term`s — a str subclass), `ggplib.db.lookup.GameInfo` (a type to isinstance against), `ggplib.util.log`, and
 `ggpzero_interface.buf_to_tuple_reverse_bytes` (np.unpackbits). The game model (roles, bases, actions as GDL strings)
 comes from this build's compiler — the base / action ORDER is this build's (unpinned by the reference, DESIGN.md
 §2); everything computed FROM that order is the reference's code:
@@ -16,6 +16,11 @@ comes from this build's compiler — the base / action ORDER is this build's (un
   * `state_to_channels(state, prev_states)` (bases.py:242-287) on positions reached by random play,
   * `policy_to_array`, `value_to_array` (plain and the draw head's, bases.py:305-335) and `check_sample`
     (bases.py:289-303) on sample records,
+
+  * `ggpzero.util.symmetry` (src/ggpzero/util/symmetry.py, imported unmodified as well): `create_translator` with the
+    reference's `gamedesc.GameSymmetries`, `Prescription`, and for every prescription entry the destination of every
+    base (`translate_basestate_helper`; skipped bases stay) and of every action (`translate_action`), plus whole
+    states through `translate_basestate` -> tests/golden/refpy_symmetry_<game>.json.gz,
 
 stored in tests/golden/refpy_<game>.json.gz and checked by tests/test_reference_python_golden.py against
 galvanise_zero_b200/bases.py, the C oracle encoder (oracle/encoder_ref.c), oracle/training_ref.py and — on a GPU —
@@ -43,6 +48,12 @@ def install_stubs():
         sys.modules[name] = m
         return m
 
+    class Term(str):
+        pass
+
+    class ListTerm(tuple):
+        pass
+
     class SymbolFactory(object):
         def to_symbols(self, s):
             toks = s.replace('(', ' ( ').replace(')', ' ) ').split()
@@ -53,11 +64,11 @@ def install_stubs():
                     t = toks[i]
                     if t == '(':
                         sub, i = parse(i + 1)
-                        out.append(sub)
+                        out.append(ListTerm(sub))
                     elif t == ')':
                         return out, i + 1
                     else:
-                        out.append(t)
+                        out.append(Term(t))
                         i += 1
                 return out, i
             return parse(0)[0]
@@ -74,7 +85,7 @@ def install_stubs():
 
     mod('ggplib').__path__ = []
     mod('ggplib.util', log=_Log()).__path__ = []
-    mod('ggplib.util.symbols', SymbolFactory=SymbolFactory, Term=str, ListTerm=list)
+    mod('ggplib.util.symbols', SymbolFactory=SymbolFactory, Term=Term, ListTerm=ListTerm)
     mod('ggplib.util.log')
     mod('ggplib.db').__path__ = []
     mod('ggplib.db.lookup', GameInfo=GameInfo)
@@ -143,6 +154,36 @@ def main(games):
                              planes_nonzero=[[int(i), float(flat[i])] for i in nz],
                              policy_nonzero=[[[int(i), float(a[i])] for i in np.nonzero(a)[0]] for a in pol],
                              value=val, check_sample=ok))
+        # ---- the reference's symmetry translator
+        from ggpzero.util import symmetry as ref_symmetry
+        from ggpzero.defs import gamedesc as ref_gamedesc
+        gds = ref_gamedesc.GameSymmetries()
+        if hasattr(gds, game):
+            desc = getattr(gds, game)()
+            t = ref_symmetry.create_translator(gi, tr.game_desc, desc)
+            pres = [[bool(r), int(k)] for r, k in ref_symmetry.Prescription(desc)]
+            base_dest, action_dest = [], []
+            for refl, rot in pres:
+                dest = []
+                for idx, terms in enumerate(t.base_symbols):
+                    if terms[0] in t.skip_base_root_terms:
+                        dest.append(idx)
+                    else:
+                        dest.append(int(t.translate_basestate_helper(terms, refl, rot)))
+                base_dest.append(dest)
+                action_dest.append([[int(t.translate_action(ri, a, refl, rot)) for a in range(len(gi.model.actions[ri]))]
+                                    for ri in range(len(gi.model.roles))])
+            states = []
+            for r in recs[:3]:
+                bits = [int(x) for x in tref.decode_record(r, sm.state_words, nb, len(tr.policy_dist_count))[0]]
+                states.append(dict(bits_set=[i for i, b in enumerate(bits) if b],
+                                   translated=[[i for i, b in enumerate(t.translate_basestate(bits, refl, rot)) if b]
+                                               for refl, rot in pres]))
+            sym = dict(game=game, prescription=pres, base_dest=base_dest, action_dest=action_dest, states=states)
+            spath = os.path.join(HERE, 'refpy_symmetry_%s.json.gz' % game)
+            with gzip.open(spath, 'wt') as f:
+                json.dump(sym, f, separators=(',', ':'))
+            print(game, 'symmetry', pres, os.path.getsize(spath), 'bytes')
         out['state_words'] = sm.state_words
         out['samples'] = rows
         path = os.path.join(HERE, 'refpy_%s.json.gz' % game)

@@ -107,3 +107,36 @@ def test_device_arrays_are_the_references(game):
         if s['value'] is not None:
             assert got_v[i].tolist() == [np.float32(v) for v in s['value']]
     assert out['bad'] == sum(1 for s in g['samples'] if not s['check_sample'])
+
+
+SYM_GAMES = ['reversi', 'breakthrough', 'breakthroughSmall', 'connect6', 'amazons_10x10', 'hexLG13']
+
+
+@pytest.mark.parametrize('game', SYM_GAMES)
+def test_symmetry_tables_are_the_references(game):
+    """Prescription, the destination of every base and of every action under every prescription entry, and whole
+    translated states: computed by the reference's own `ggpzero.util.symmetry` (Translator / create_translator /
+    Prescription imported unmodified) with the reference's `gamedesc.GameSymmetries`."""
+    from galvanise_zero_b200 import symmetry
+    from galvanise_zero_b200.defs import gamedesc
+    with gzip.open(os.path.join(HERE, 'golden', 'refpy_symmetry_%s.json.gz' % game), 'rt') as f:
+        g = json.load(f)
+    gi = lookup.by_name(game)
+    desc = gamedesc.get_symmetries_desc(game)
+    t = symmetry.create_translator(gi, getattr(gamedesc.Games(), game)(), desc)
+    pres = [[bool(r), int(k)] for r, k in symmetry.Prescription(desc)]
+    assert pres == g['prescription']
+    nb = len(gi.model.bases)
+    for k, (refl, rot) in enumerate(pres):
+        assert np.asarray(t.base_permutation(refl, rot)).tolist() == g['base_dest'][k]
+        for ri in range(len(gi.model.roles)):
+            assert np.asarray(t.action_permutation(ri, refl, rot)).tolist() == g['action_dest'][k][ri]
+        assert t.translate_action(0, 1, refl, rot) == g['action_dest'][k][0][1]
+        assert t.translate_base_index(nb - 1, refl, rot) == g['base_dest'][k][nb - 1]
+        for st in g['states']:
+            bits = [0] * nb
+            for i in st['bits_set']:
+                bits[i] = 1
+            got = t.translate_basestate(bits, refl, rot)
+            assert [i for i, b in enumerate(got) if b] == st['translated'][k]
+    assert gamedesc.get_symmetries_desc('chess_15d') is None        # (the reference has none for chess either)
