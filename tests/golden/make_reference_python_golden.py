@@ -193,5 +193,37 @@ def main(games):
               os.path.getsize(path), 'bytes')
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and '--configs' not in sys.argv:
     main(sys.argv[1:] or GAMES)
+
+
+def configs_golden():
+    """attr.asdict of the reference's own config classes and templates (src/ggpzero/defs/{confs,templates,datadesc}.py,
+    imported unmodified) -> tests/golden/refpy_configs.json: the config surface the engine must accept verbatim
+    (SURVEY.md appendix A)."""
+    import attr
+    install_stubs()
+    sys.path.insert(0, '/root/reference/src')
+    from ggpzero.defs import confs, datadesc, templates
+    out = dict(
+        PUCTEvaluatorConfig=attr.asdict(confs.PUCTEvaluatorConfig()),
+        PUCTPlayerConfig=attr.asdict(confs.PUCTPlayerConfig()),
+        SelfPlayConfig=attr.asdict(confs.SelfPlayConfig()),
+        base_puct_config=attr.asdict(templates.base_puct_config()),
+        base_puct_config_overridden=attr.asdict(templates.base_puct_config(dirichlet_noise_pct=0.15, random_scale=0.75)),
+        selfplay_config_template=attr.asdict(templates.selfplay_config_template()),
+        fields=dict(Sample=[a.name for a in attr.fields(datadesc.Sample)],
+                    GenerationDescription=[a.name for a in attr.fields(datadesc.GenerationDescription)],
+                    GenerationSamples=[a.name for a in attr.fields(datadesc.GenerationSamples)]),
+        GenerationDescription=attr.asdict(datadesc.GenerationDescription()),
+        default_generation_desc=attr.asdict(templates.default_generation_desc('reversi', multiple_policy_heads=True,
+                                                                               num_previous_states=1)))
+    out['default_generation_desc'].pop('date_created')          # (a timestamp)
+    path = os.path.join(HERE, 'refpy_configs.json')
+    with open(path, 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=False)
+    print('configs', os.path.getsize(path), 'bytes')
+
+
+if __name__ == '__main__' and '--configs' in sys.argv:
+    configs_golden()

@@ -140,3 +140,30 @@ def test_symmetry_tables_are_the_references(game):
             got = t.translate_basestate(bits, refl, rot)
             assert [i for i, b in enumerate(got) if b] == st['translated'][k]
     assert gamedesc.get_symmetries_desc('chess_15d') is None        # (the reference has none for chess either)
+
+
+def test_config_surface_is_the_references():
+    """attr.asdict of the reference's own PUCTEvaluatorConfig / PUCTPlayerConfig / SelfPlayConfig, of its templates
+    (base_puct_config, selfplay_config_template) and the field lists of its datadesc classes — keys, order and
+    defaults — equal this build's: the dicts `start_self_play` / `Player` receive are the reference's verbatim."""
+    import attr
+    from galvanise_zero_b200.defs import confs
+    with open(os.path.join(HERE, 'golden', 'refpy_configs.json')) as f:
+        g = json.load(f)
+
+    def same(ref, mine):
+        assert list(ref) == list(mine) and ref == mine
+
+    same(g['PUCTEvaluatorConfig'], attr.asdict(confs.PUCTEvaluatorConfig()))
+    same(g['PUCTPlayerConfig'], attr.asdict(confs.PUCTPlayerConfig()))
+    same(g['SelfPlayConfig'], attr.asdict(confs.SelfPlayConfig()))
+    same(g['base_puct_config'], attr.asdict(confs.base_puct_config()))
+    same(g['base_puct_config_overridden'], attr.asdict(confs.base_puct_config(dirichlet_noise_pct=0.15, random_scale=0.75)))
+    same(g['selfplay_config_template'], attr.asdict(confs.selfplay_config_template()))
+    same(g['GenerationDescription'], attr.asdict(datadesc.GenerationDescription()))
+    for name, fields in g['fields'].items():
+        assert [a.name for a in attr.fields(getattr(datadesc, name))] == fields
+    gd = attr.asdict(datadesc.generation_for('reversi', draw_head=False))
+    for k, v in g['default_generation_desc'].items():
+        if k not in ('name',):
+            assert gd[k] == v, k
