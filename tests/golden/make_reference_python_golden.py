@@ -193,7 +193,7 @@ def main(games):
               os.path.getsize(path), 'bytes')
 
 
-if __name__ == '__main__' and '--configs' not in sys.argv:
+if __name__ == '__main__' and '--configs' not in sys.argv and '--gendata' not in sys.argv:
     main(sys.argv[1:] or GAMES)
 
 
@@ -227,3 +227,52 @@ def configs_golden():
 
 if __name__ == '__main__' and '--configs' in sys.argv:
     configs_golden()
+
+
+def gendata_golden():
+    """A generation of samples serialised by the reference's OWN writer (`attrutil.attr_to_json(GenerationSamples)`,
+    src/ggpzero/util/attrutil.py, what `ServerBroker.save_sample_data` writes, distributed/server.py:300-322) ->
+    tests/golden/refpy_gendata_reversi.json, with the records the samples came from."""
+    import attr
+    install_stubs()
+    sys.path.insert(0, '/root/reference/src')
+    from ggpzero.defs import datadesc as ref_datadesc
+    from ggpzero.util import attrutil
+    from galvanise_zero_b200 import bases, gendata, lookup, tables
+    from galvanise_zero_b200.defs import datadesc
+    from oracle.pnref import RefStateMachine
+    import test_training_batch as ttb
+    game = 'reversi'
+    tr = bases.GdlBasesTransformer(lookup.by_name(game), datadesc.generation_for(game))
+    sm = RefStateMachine(tables.blob_by_name(game))
+    recs = ttb.synthetic_records(tr, sm, 5, seed=99)
+    f = recs.view(np.float32)
+    for i in range(len(recs)):             # values that survive the file's 5-decimal floats
+        nc = recs[i, 11]
+        p0 = 24 + 2 * sm.state_words
+        f[i, p0 + 1:p0 + 2 * nc:2] = np.round(f[i, p0 + 1:p0 + 2 * nc:2].astype(np.float64), 5).astype(np.float32)
+        f[i, 12:14] = np.round(f[i, 12:14].astype(np.float64), 5).astype(np.float32)
+    mine = [gendata.encode_sample_states(datadesc.Sample(**d)) for d in ttb._sample_dicts(recs, tr, sm)]
+    for k, s in enumerate(mine):
+        s.match_identifier = 'golden_%d' % k
+        s.resultant_puct_score = [0.25, 0.75]
+        s.policies = [[(int(m), float('%.5f' % p)) for m, p in pol] for pol in s.policies]
+        s.final_score = [float('%.5f' % v) for v in s.final_score]
+    ref_samples = [ref_datadesc.Sample(**attr.asdict(s, recurse=False)) for s in mine]
+    ref_gen = ref_datadesc.GenerationSamples(game=game, date_created='2026/01/01 00:00', with_generation='golden_gen_7',
+                                             num_samples=len(ref_samples), samples=ref_samples)
+    ref_json = attrutil.attr_to_json(ref_gen, pretty=False)
+    my_gen = datadesc.GenerationSamples(game=game, date_created='2026/01/01 00:00', with_generation='golden_gen_7',
+                                        num_samples=len(mine), samples=mine)
+    my_json = gendata.generation_to_json(my_gen)
+    # (the reference's reader, attrutil.json_to_attr, pops keys from the dict it iterates over — Python 2 only — so
+    # it cannot be run here; the two files are compared as JSON documents instead)
+    assert json.loads(my_json) == json.loads(ref_json), 'the two writers disagree'
+    path = os.path.join(HERE, 'refpy_gendata_reversi.json')
+    with open(path, 'w') as fo:
+        json.dump(dict(reference_json=ref_json, records=[[int(x) for x in r] for r in recs]), fo)
+    print('gendata', os.path.getsize(path), 'bytes; this build writer produces the same JSON document')
+
+
+if __name__ == '__main__' and '--gendata' in sys.argv:
+    gendata_golden()

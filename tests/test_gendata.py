@@ -59,3 +59,27 @@ def test_generation_file_has_the_reference_layout(tmp_path):
     assert back.game == 'reversi' and len(back.samples) == 4
     assert gendata.decode_state(back.samples[2].state)[:30] == tuple([1, 0, 1] * 10)
     assert back.samples[1].policies[0][1] == (7, 0.87654) and back.samples[3].depth == 3
+
+
+def test_generation_file_written_by_the_references_own_serialiser():
+    """tests/golden/refpy_gendata_reversi.json holds a generation serialised by the reference's own
+    `attrutil.attr_to_json` (imported unmodified by tests/golden/make_reference_python_golden.py --gendata): this
+    build reads it, writes the same JSON document back, and its samples pack into the records they came from."""
+    import json
+    import os
+    import numpy as np
+    from galvanise_zero_b200 import bases, lookup, tables
+    from galvanise_zero_b200.datacache import samples_to_records
+    from galvanise_zero_b200.defs import datadesc
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, 'golden', 'refpy_gendata_reversi.json')) as f:
+        g = json.load(f)
+    gen = gendata.generation_from_json(g['reference_json'])
+    assert gen.game == 'reversi' and gen.with_generation == 'golden_gen_7' and gen.num_samples == len(gen.samples) == 5
+    assert json.loads(gendata.generation_to_json(gen)) == json.loads(g['reference_json'])
+    tr = bases.GdlBasesTransformer(lookup.by_name('reversi'), datadesc.generation_for('reversi'))
+    recs = np.array(g['records'], dtype=np.int32)
+    sw = tables.state_words(tr.num_bases)
+    back = samples_to_records(gen.samples, tr, sw, recs.shape[1])
+    assert np.array_equal(back[:, 24:], recs[:, 24:])                    # states, previous states, (move, probability) pairs
+    assert np.array_equal(back[:, [9, 10, 11, 12, 13]], recs[:, [9, 10, 11, 12, 13]])   # lead, n_prev, n_children, final scores
