@@ -219,6 +219,11 @@ def configs_golden():
         default_generation_desc=attr.asdict(templates.default_generation_desc('reversi', multiple_policy_heads=True,
                                                                                num_previous_states=1)))
     out['default_generation_desc'].pop('date_created')          # (a timestamp)
+    import types as _types
+    shape = _types.SimpleNamespace(role_count=2, num_rows=8, num_cols=8, num_channels=5, policy_dist_count=[65, 65])
+    out['nn_model_config_template'] = {h: attr.asdict(templates.nn_model_config_template('reversi', h, shape))
+                                       for h in ('small', 'medium', 'large')}
+    out['nn_model_config_template']['NNModelConfig'] = attr.asdict(confs.NNModelConfig())
     path = os.path.join(HERE, 'refpy_configs.json')
     with open(path, 'w') as f:
         json.dump(out, f, indent=1, sort_keys=False)

@@ -167,3 +167,10 @@ def test_config_surface_is_the_references():
     for k, v in g['default_generation_desc'].items():
         if k not in ('name',):
             assert gd[k] == v, k
+    # the network shapes of templates.nn_model_config_template (the benchmarked "small" tower: 64 filters x 5 blocks)
+    import types
+    from galvanise_zero_b200 import nn as gznn
+    shape = types.SimpleNamespace(role_count=2, num_rows=8, num_cols=8, num_channels=5, policy_dist_count=[65, 65])
+    for hint in ('small', 'medium', 'large'):
+        same(g['nn_model_config_template'][hint], attr.asdict(gznn.nn_model_config_template(shape, hint)))
+    same(g['nn_model_config_template']['NNModelConfig'], attr.asdict(gznn.NNModelConfig()))
