@@ -323,7 +323,8 @@ extern "C" int gz_transformer_finalize(gz_transformer* t, int n_bases, int devic
 
 #include "gz_encoder_col.cuh"
 
-// batches of at least this many states whose rows are a multiple of 8 elements go to encode_col_kernel
+// batches of at least this many states go to encode_col_kernel (gz_encoder_col.cuh); smaller ones — the PUCT step —
+// keep encode_fast_kernel / encode_kernel
 static int64_t g_col_min_batch = 16384;
 extern "C" int gz_encode_set_column_kernel_min_batch(int64_t min_batch) {
     g_col_min_batch = min_batch < 0 ? ((int64_t)1 << 62) : min_batch;
