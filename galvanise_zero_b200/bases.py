@@ -163,46 +163,45 @@ class GdlBasesTransformer(object):
             ch = np.transpose(ch, (1, 2, 0))
         return ch
 
-    # ---- sample -> network output rows (nn/bases.py:289-321; the draw head's value row is
-    # GdlBasesTransformer_Draws.value_to_array, :323-335 — chosen here by generation_descr.draw_head)
+    # ---- sample -> network output rows. Same names and results as nn/bases.py:289-321 (the draw head's value row is
+    # GdlBasesTransformer_Draws.value_to_array, :323-335 — chosen here by generation_descr.draw_head); written over
+    # numpy arrays. tests/test_reference_python_golden.py holds them to the reference's own outputs.
     def check_sample(self, sample):
+        """Raises AssertionError for a sample the reference's check rejects; returns the sample otherwise."""
         from .gendata import decode_state
-        state = sample.state
-        if isinstance(state, str):
-            state = decode_state(state)
-        assert len(state) >= self.num_bases          # (>=: the reference's encode / decode may pad)
-        assert len(sample.final_score) == self.final_score_count
         assert isinstance(sample, datadesc.Sample)
+        state = decode_state(sample.state) if isinstance(sample.state, str) else sample.state
+        assert len(state) >= self.num_bases, 'state shorter than the base count'      # (>=: the codec pads to bytes)
+        assert len(sample.final_score) == self.final_score_count
         for policy in sample.policies:
+            probs = np.array([p for _, p in policy], dtype=np.float64)
+            assert np.all((probs > -0.01) & (probs < 1.01)), 'probability out of range'
             total = 0.0
-            for _, p in policy:
-                assert -0.01 < p < 1.01
-                total += p
-            assert 0.99 < total < 1.01
+            for p in probs:                      # (left to right, as the reference adds them)
+                total += float(p)
+            assert 0.99 < total < 1.01, 'probabilities do not sum to one'
         return sample
 
     def policy_to_array(self, policy, role_index):
-        array = np.zeros(self.policy_dist_count[role_index], dtype='float32')
-        for idx, prob in policy:
-            array[idx] = prob
+        array = np.zeros(self.policy_dist_count[role_index], dtype=np.float32)
+        if len(policy):
+            idx, probs = zip(*policy)
+            array[np.asarray(idx, dtype=np.int64)] = np.asarray(probs, dtype=np.float32)   # (a repeated index: the last wins)
         return array
 
     def value_to_array(self, values):
-        if self.num_rewards == 3:
-            assert abs(sum(values) - 1.0) < 0.01
-            assert len(values) == 2
-            if abs(values[0] - 0.5) < 0.01:
-                assert abs(values[1] - 0.5) < 0.01
-                return np.array([0.0, 0.0, 1.0], dtype='float32')
-            return np.array([values[0], values[1], 0.0], dtype='float32')
-        assert len(values) == self.role_count
-        return np.array(values, dtype='float32')
+        values = [float(v) for v in values]
+        if self.num_rewards != 3:
+            assert len(values) == self.role_count
+            return np.asarray(values, dtype=np.float32)
+        # draw head: (win 0, win 1, draw) — a 0.5 / 0.5 result is the draw class
+        assert len(values) == 2 and abs(values[0] + values[1] - 1.0) < 0.01
+        drawn = abs(values[0] - 0.5) < 0.01
+        assert not drawn or abs(values[1] - 0.5) < 0.01
+        return np.asarray([0.0, 0.0, 1.0] if drawn else [values[0], values[1], 0.0], dtype=np.float32)
 
     def get_symmetries_desc(self):
-        gds = gamedesc.GameSymmetries()
-        if hasattr(gds, self.game):
-            return getattr(gds, self.game)()
-        return None
+        return getattr(gamedesc.GameSymmetries(), self.game, lambda: None)()
 
     def encode_tables(self):
         """(board_base, board_offset, control_base, control_channel, control_value) arrays in the

@@ -102,68 +102,75 @@ class Match(object):
 
 
 class PUCTPlayer(MatchPlayer):
+    """Match player over ``PlayPoller``. Public surface as in the reference (``poller``, ``last_probability``,
+    ``last_node_count``, ``identifier``, the hooks, ``balance_moves`` / ``tree_debug`` / ``update_config``); the body
+    is organised around two small tables — every role's ``noop`` legal and the playout budget by "is it our move"."""
     poller = None
     last_probability = -1
     last_node_count = -1
 
     def __init__(self, conf, **engine_kwds):
-        assert isinstance(conf, (confs.PUCTPlayerConfig, confs.PUCTEvaluatorConfig))
+        if not isinstance(conf, (confs.PUCTPlayerConfig, confs.PUCTEvaluatorConfig)):
+            raise TypeError('PUCTPlayer wants a PUCTPlayerConfig')
         self.conf = conf
-        if conf.playouts_per_iteration > 0:
-            self.identifier = "%s_%s_%s" % (self.conf.name, conf.playouts_per_iteration, conf.generation)
-        else:
-            self.identifier = "%s_%s" % (self.conf.name, conf.generation)
+        parts = [conf.name] + ([conf.playouts_per_iteration] if conf.playouts_per_iteration > 0 else []) + [conf.generation]
+        self.identifier = '_'.join(str(x) for x in parts)          # name[_playouts]_generation (puctplayer.py:21-24)
         super().__init__(self.identifier)
-        self.sm = None
-        self._engine_kwds = engine_kwds          # (seed, node_cap ... of ggpzero_interface.Player; none in the reference)
+        self.sm = self.nn = None
+        self.noop_legals = None                   # per role: the legal index of its noop
+        self._engine_kwds = engine_kwds           # (seed, node_cap ... of ggpzero_interface.Player; none in the reference)
+
+    # ---- set-up: a state machine, the generation's network and the poller, once per game type ("*" in the
+    # generation name: the newest one, looked up again for every match — puctplayer.py:35-60)
+    def _build(self):
+        game_info = self.match.game_info
+        self.sm = game_info.get_sm()
+        self.nn = get_manager().load_network(game_info.game, self.conf.generation)
+        self.poller = PlayPoller(self.sm, self.nn, self.conf.evaluator_config, **self._engine_kwds)
+        self.noop_legals = []
+        for actions in game_info.model.actions:
+            found = [i for i, a in enumerate(actions) if 'noop' in a]
+            if not found:
+                raise ValueError('did not find noop among a role\'s actions')
+            self.noop_legals.append(found[0])
+        # (the reference keeps them as two attributes)
+        self.role0_noop_legal, self.role1_noop_legal = self.noop_legals[0], self.noop_legals[1]
+
+    def on_meta_gaming(self, finish_time):
+        if self.sm is None or '*' in self.conf.generation:
+            self._build()
+        self.poller.player_reset(self.match.game_depth)
 
     def cleanup(self):
         if self.poller is not None:
             self.poller.player_reset(0)
 
-    def on_meta_gaming(self, finish_time):
-        if self.sm is None or "*" in self.conf.generation:
-            game_info = self.match.game_info
-            self.sm = game_info.get_sm()
-            self.nn = get_manager().load_network(game_info.game, self.conf.generation)
-            self.poller = PlayPoller(self.sm, self.nn, self.conf.evaluator_config, **self._engine_kwds)
-
-            def get_noop_idx(actions):
-                for idx, a in enumerate(actions):
-                    if "noop" in a:
-                        return idx
-                assert False, "did not find noop"
-
-            self.role0_noop_legal, self.role1_noop_legal = map(get_noop_idx, game_info.model.actions)
-        self.poller.player_reset(self.match.game_depth)
-
     def on_apply_move(self, joint_move):
         self.poller.player_apply_move(joint_move_to_ptr(joint_move))
         self.poller.poll_loop()
 
+    # ---- who is on move: the first role (of two) that is NOT reduced to its lone noop; the other one must be
+    # (puctplayer.py:68-80 asserts the same of a turn-taking game)
+    def _only_noop(self, ri):
+        legals = self.sm.get_legal_state(ri)
+        noops = self.noop_legals if self.noop_legals is not None else (self.role0_noop_legal, self.role1_noop_legal)
+        return legals.get_count() == 1 and legals.get_legal(0) == noops[ri]
+
     def lead_role_index(self):
-        """Who is on move in the current state: the role whose only legal is not ``noop`` (puctplayer.py:68-80)."""
-        current_state = self.match.get_current_state()
-        self.sm.update_bases(current_state)
-        if (self.sm.get_legal_state(0).get_count() == 1 and
-                self.sm.get_legal_state(0).get_legal(0) == self.role0_noop_legal):
+        self.sm.update_bases(self.match.get_current_state())
+        if self._only_noop(0):
             return 1
-        assert (self.sm.get_legal_state(1).get_count() == 1 and
-                self.sm.get_legal_state(1).get_legal(0) == self.role1_noop_legal)
+        if not self._only_noop(1):
+            raise AssertionError('not a turn-taking position: neither role is reduced to noop')
         return 0
 
     def on_next_move(self, finish_time):
-        lead_role_index = self.lead_role_index()
-        if lead_role_index == self.match.our_role_index:
-            max_iterations = self.conf.playouts_per_iteration
-        else:
-            max_iterations = self.conf.playouts_per_iteration_noop
-        current_state = self.match.get_current_state()
-        self.poller.player_move(basestate_to_ptr(current_state), max_iterations, finish_time)
+        ours = self.match.our_role_index
+        budget = {True: self.conf.playouts_per_iteration, False: self.conf.playouts_per_iteration_noop}
+        iterations = budget[self.lead_role_index() == ours]
+        self.poller.player_move(basestate_to_ptr(self.match.get_current_state()), iterations, finish_time)
         self.poller.poll_loop()
-        move, prob, node_count = self.poller.player_get_move(self.match.our_role_index)
-        self.last_probability = prob
-        self.last_node_count = node_count
+        move, self.last_probability, self.last_node_count = self.poller.player_get_move(ours)
         return move
 
     def balance_moves(self, max_count):
