@@ -193,7 +193,7 @@ def main(games):
               os.path.getsize(path), 'bytes')
 
 
-if __name__ == '__main__' and '--configs' not in sys.argv and '--gendata' not in sys.argv:
+if __name__ == '__main__' and not any(a in sys.argv for a in ('--configs', '--gendata', '--variants')):
     main(sys.argv[1:] or GAMES)
 
 
@@ -281,3 +281,56 @@ def gendata_golden():
 
 if __name__ == '__main__' and '--gendata' in sys.argv:
     gendata_golden()
+
+
+def variants_golden():
+    """The reference's `state_to_channels` for other generation shapes — no previous state, two previous states,
+    channels last — on reversi and connect6 -> tests/golden/refpy_variants.json.gz."""
+    GameInfo = install_stubs()
+    sys.path.insert(0, '/root/reference/src')
+    from ggpzero.defs import datadesc as ref_datadesc
+    from ggpzero.nn import bases as ref_bases
+    from galvanise_zero_b200 import lookup, tables
+    from oracle.pnref import RefStateMachine
+    out = {}
+    for game in ('reversi', 'connect6'):
+        mine = lookup.by_name(game)
+        gi = GameInfo()
+        gi.game = game
+        gi.model = types.SimpleNamespace(roles=list(mine.model.roles), bases=list(mine.model.bases),
+                                         actions=[list(a) for a in mine.model.actions])
+        sm = RefStateMachine(tables.blob_by_name(game))
+        n = 5
+        s = np.zeros((n, sm.state_words), dtype=np.uint32)
+        l = np.zeros((n, sm.legal_words), dtype=np.uint32)
+        t = np.ones(n, dtype=np.uint8)
+        g = np.zeros((n, sm.n_roles), dtype=np.uint8)
+        hist = []
+        for step in range(8):
+            sm.playout_step(0, 2024, step, s, l, t, g, None)
+            hist.append(s.copy())
+        nb = len(gi.model.bases)
+        bits = lambda w: [int(x) for x in tables.unpack_state_bits(w, nb)]      # noqa: E731
+        cases = []
+        for num_prev, channel_last in ((0, False), (2, False), (1, True), (3, False)):
+            gd = ref_datadesc.GenerationDescription(game=game, name='v', channel_last=channel_last,
+                                                    multiple_policy_heads=True, num_previous_states=num_prev)
+            tr = ref_bases.GdlBasesTransformer(gi, gd)
+            rows = []
+            for i in range(n):
+                for have in sorted({0, min(1, num_prev), num_prev}):
+                    prevs = [bits(hist[6 - k][i]) for k in range(have)]
+                    planes = np.asarray(tr.state_to_channels(bits(hist[7][i]), prevs), dtype=np.float32)
+                    flat = planes.reshape(-1)
+                    rows.append(dict(i=i, have=have, shape=list(planes.shape),
+                                     nonzero=[[int(j), float(flat[j])] for j in np.nonzero(flat)[0]]))
+            cases.append(dict(num_previous_states=num_prev, channel_last=channel_last, num_channels=tr.num_channels, rows=rows))
+        out[game] = dict(states=[[[int(x) for x in hist[k][i]] for i in range(n)] for k in range(8)], cases=cases)
+    path = os.path.join(HERE, 'refpy_variants.json.gz')
+    with gzip.open(path, 'wt') as f:
+        json.dump(out, f, separators=(',', ':'))
+    print('variants', os.path.getsize(path), 'bytes')
+
+
+if __name__ == '__main__' and '--variants' in sys.argv:
+    variants_golden()

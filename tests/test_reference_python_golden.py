@@ -174,3 +174,34 @@ def test_config_surface_is_the_references():
     for hint in ('small', 'medium', 'large'):
         same(g['nn_model_config_template'][hint], attr.asdict(gznn.nn_model_config_template(shape, hint)))
     same(g['nn_model_config_template']['NNModelConfig'], attr.asdict(gznn.NNModelConfig()))
+
+
+def test_other_generation_shapes_are_the_references():
+    """No previous state, two / three previous states (each in its own channel group, fewer handed in than the
+    generation has), channels last: `bases.GdlBasesTransformer.state_to_channels` equals the reference's own; with
+    at most one previous state the C oracle encoder (the engine's toChannels restatement) agrees as well."""
+    from galvanise_zero_b200 import tables
+    with gzip.open(os.path.join(HERE, 'golden', 'refpy_variants.json.gz'), 'rt') as f:
+        g = json.load(f)
+    for game, d in g.items():
+        gi = lookup.by_name(game)
+        nb = len(gi.model.bases)
+        hist = np.array(d['states'], dtype=np.uint32)                       # [ply][game][word]
+        bits = lambda w: [int(x) for x in tables.unpack_state_bits(w, nb)]  # noqa: E731
+        for case in d['cases']:
+            gd = datadesc.GenerationDescription(game=game, name='v', channel_last=case['channel_last'],
+                                                multiple_policy_heads=True, num_previous_states=case['num_previous_states'])
+            tr = bases.GdlBasesTransformer(gi, gd)
+            assert tr.num_channels == case['num_channels']
+            enc = RefEncoder.from_c_transformer(cppinterface.create_c_transformer(tr))
+            for row in case['rows']:
+                i, have = row['i'], row['have']
+                prevs = [bits(hist[6 - k][i]) for k in range(have)]
+                planes = tr.state_to_channels(bits(hist[7][i]), prevs)
+                assert list(planes.shape) == row['shape']
+                want = _dense(row['nonzero'], planes.size)
+                assert np.array_equal(planes.reshape(-1), want)
+                if not case['channel_last'] and case['num_previous_states'] <= 1:
+                    pw = hist[6][i][None, None, :] if have else None
+                    got = enc.encode(hist[7][i][None, :], pw)[0]
+                    assert np.array_equal(got, want)
