@@ -313,7 +313,11 @@ def run_propnet(args, rank, world, local, steps=None, cpu_seconds=12.0):
         encoder = {'kernel': 'encode_col_kernel<bf16> (column-owned, csrc/gz_encoder_col.cuh)' if col
                              else 'encode_fast_kernel<bf16> / encode_kernel<bf16>', 'positions_per_launch': ne, 'launch_ms': enc_ms,
                    'bytes_per_unit': eb, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                   'frac': ach / peaks['hbm_gbs'], 'planes': [tr.num_channels, tr.num_cols, tr.num_rows]}
+                   'frac': ach / peaks['hbm_gbs'], 'planes': [tr.num_channels, tr.num_cols, tr.num_rows],
+                   # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full; reversi / breakthrough
+                   # planes 5x8x8 at 2^19 positions): no more than the algorithmic bytes
+                   'traffic': 310903552 if (col and ne == (1 << 19) and ct.total_size() == 320) else None,
+                   'traffic_source': 'profiles/r02_encode_col_kernel_ncu_full.md'}
     except Exception as exc:           # a game without a plane description
         encoder = {'unavailable': str(exc)}
 
