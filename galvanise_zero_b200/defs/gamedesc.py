@@ -140,9 +140,9 @@ class Symmetries(object):
     skip_bases = attr.ib(default=attr.Factory(list))
     apply_actions = attr.ib(default=attr.Factory(list))
     skip_actions = attr.ib(default=attr.Factory(list))
+    do_reflection = attr.ib(default=False)           # (field order as in the reference: positional construction)
     do_rotations_90 = attr.ib(default=False)
     do_rotations_180 = attr.ib(default=False)
-    do_reflection = attr.ib(default=False)
 
 
 class GameSymmetries(object):

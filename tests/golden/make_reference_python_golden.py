@@ -219,6 +219,10 @@ def configs_golden():
         default_generation_desc=attr.asdict(templates.default_generation_desc('reversi', multiple_policy_heads=True,
                                                                                num_previous_states=1)))
     out['default_generation_desc'].pop('date_created')          # (a timestamp)
+    from ggpzero.defs import gamedesc
+    out['gamedesc'] = {g: attr.asdict(getattr(gamedesc.Games(), g)()) for g in GAMES}
+    out['game_symmetries'] = {g: attr.asdict(getattr(gamedesc.GameSymmetries(), g)()) for g in GAMES
+                              if hasattr(gamedesc.GameSymmetries(), g)}
     import types as _types
     shape = _types.SimpleNamespace(role_count=2, num_rows=8, num_cols=8, num_channels=5, policy_dist_count=[65, 65])
     out['nn_model_config_template'] = {h: attr.asdict(templates.nn_model_config_template('reversi', h, shape))

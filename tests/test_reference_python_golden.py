@@ -167,6 +167,13 @@ def test_config_surface_is_the_references():
     for k, v in g['default_generation_desc'].items():
         if k not in ('name',):
             assert gd[k] == v, k
+    # the game descriptions and symmetry descriptions of defs/gamedesc.py for the compiled games
+    from galvanise_zero_b200.defs import gamedesc
+    for game, ref in g['gamedesc'].items():
+        same(ref, json.loads(json.dumps(attr.asdict(getattr(gamedesc.Games(), game)()))))
+    for game, ref in g['game_symmetries'].items():
+        same(ref, json.loads(json.dumps(attr.asdict(getattr(gamedesc.GameSymmetries(), game)()))))
+    assert sorted(g['game_symmetries']) == sorted(x for x in g['gamedesc'] if gamedesc.get_symmetries_desc(x) is not None)
     # the network shapes of templates.nn_model_config_template (the benchmarked "small" tower: 64 filters x 5 blocks)
     import types
     from galvanise_zero_b200 import nn as gznn
